@@ -1,0 +1,126 @@
+/* gten_b200.h -- C-ABI of libgten_b200.so: the B200 (sm_100a) implementation of tinyllama.cpp's
+ * transformer-forward hot path.
+ *
+ * The reference has no FFI; its boundary is the C++ `gten` API.  This header is the thin
+ * C layer the C++ drop-in headers in include/gten/ call, and what any other host language would bind
+ * (ctypes stub: tinyllama.cpp_b200/capi.py).  Each entry point names the reference
+ * interface it stands in for (paths relative to the reference repo).
+ *
+ * Conventions: every function returns 0 on success and a non-zero code on failure, with a message in
+ * gtb_last_error(); nothing throws across the boundary.  The C++ wrappers turn non-zero into the
+ * reference's assert-and-exit convention (gten/log.h:6-23).  One host thread <-> one CUDA stream <->
+ * one GPU (the reference API is single-threaded and not re-entrant, gten/ops.h:37).
+ * Pointers named d_* are device pointers obtained from gtb_malloc; h_* are host pointers.
+ * There is NO CPU fallback: without a CUDA device every call fails with GTB_ERR_NO_DEVICE.
+ */
+#ifndef GTEN_B200_H
+#define GTEN_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* dtype codes = enum class Dtype, gten/gten_types.h:20-26 */
+enum { GTB_I32 = 0, GTB_F16 = 1, GTB_F32 = 2, GTB_Q8 = 3, GTB_Q4 = 4 };
+enum { GTB_OK = 0, GTB_ERR_CUDA = 1, GTB_ERR_ARG = 2, GTB_ERR_NO_DEVICE = 3, GTB_ERR_STATE = 4 };
+
+/* tensor ids of a TinyLlama checkpoint in file order (tinyllama.cpp:345-391) */
+enum {
+    GTB_T_EMBED = 0, GTB_T_FINAL_NORM = 1, GTB_T_LM_HEAD = 2,
+    GTB_T_Q = 10, GTB_T_K = 11, GTB_T_V = 12, GTB_T_O = 13, GTB_T_GATE = 14, GTB_T_UP = 15, GTB_T_DOWN = 16,
+    GTB_T_ATTN_NORM = 17, GTB_T_FFN_NORM = 18
+};
+/* activation ids: the module `acv` buffers of one AttentionBlock (gten/modules.h:147-167) */
+enum {
+    GTB_A_EMB = 0, GTB_A_FINAL_NORM = 1,
+    GTB_A_ATTN_NORM = 10, GTB_A_Q = 11, GTB_A_K = 12, GTB_A_V = 13, GTB_A_ATTN_OUT = 14, GTB_A_O = 15,
+    GTB_A_INP_RES = 16, GTB_A_FFN_NORM = 17, GTB_A_GATE = 18, GTB_A_UP = 19, GTB_A_DOWN = 20, GTB_A_ATTN_RES = 21
+};
+
+/* ---- context ------------------------------------------------------------------------------------- */
+const char* gtb_last_error(void);
+const char* gtb_version(void);
+int gtb_init(int device);                       /* select device, create the stream; idempotent */
+int gtb_device_count(int* n);
+int gtb_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+int gtb_sync(void);                             /* wait for the library stream */
+void* gtb_stream(void);                         /* the cudaStream_t every launch uses (for CUDA-event timing) */
+int64_t gtb_launch_count(void);                 /* kernels launched by this library since load */
+int64_t gtb_mem_allocated(void);                /* replaces G_TensorMemAllocated, gten/tensor.h:17 */
+
+/* ---- memory (Tensor storage, gten/tensor.cpp:27-67) ---------------------------------------------- */
+int gtb_malloc(void** d_ptr, size_t nbytes);
+int gtb_free(void* d_ptr);
+int gtb_memset(void* d_ptr, int value, size_t nbytes);
+int gtb_h2d(void* d_dst, const void* h_src, size_t nbytes);     /* async on the library stream */
+int gtb_d2h(void* h_dst, const void* d_src, size_t nbytes);     /* returns after the copy completed */
+int gtb_d2d(void* d_dst, const void* d_src, size_t nbytes);
+int gtb_host_alloc(void** h_ptr, size_t nbytes);                /* pinned staging */
+int gtb_host_free(void* h_ptr);
+
+/* ---- weights: upload = one-time repack of a gten payload into the device layout ------------------ */
+/* (payload layout = the bytes read_into_weight stores, tinyllama.cpp:301-321: Q4Block/Q8Block rows or fp16) */
+typedef struct gtb_weight* gtb_weight_t;
+int gtb_weight_upload(gtb_weight_t* out, const void* h_payload, int dtype, int rows, int cols);
+int gtb_weight_from_device(gtb_weight_t* out, const void* d_payload, int dtype, int rows, int cols);
+int gtb_weight_free(gtb_weight_t w);
+int gtb_weight_nbytes(gtb_weight_t w, size_t* nbytes);
+/* dequantise rows [row0,row0+nrows) from the DEVICE layout to fp32 (bit-exact vs quants.h:69-90) */
+int gtb_weight_dequant(gtb_weight_t w, int row0, int nrows, float* h_out);
+
+/* ---- row codecs (gten/quants.h:92-143, gten/ops.h:40-96); buffers hold `rows` rows, reference layout */
+int gtb_write_rows_from_float(const float* d_in, void* d_out, int out_dtype, int rows, int n);
+int gtb_read_rows_to_float(const void* d_in, int in_dtype, float* d_out, int rows, int n);
+
+/* ---- ops (gten/ops.h); activations are device buffers in the reference's own row layout ---------- */
+int gtb_token_embed(gtb_weight_t w, const int32_t* d_tokens, void* d_out, int out_dtype, int n_ctx, int start_pos); /* ops.h:554 */
+int gtb_matmul_2d(const void* d_x, int x_dtype, int n_ctx, gtb_weight_t w, void* d_out, int out_dtype,
+                  int out_is_1d, int start_pos);                                                                    /* ops.h:651 */
+int gtb_rms_norm(const void* d_x, int dtype, int n_ctx, int n_embd, const void* d_weight_f16, void* d_out, int start_pos); /* ops.h:806 */
+int gtb_rotary_emb(void* d_x, int dtype, int n_ctx, int n_embd, int d_head, int start_pos);                        /* ops.h:757 */
+int gtb_silu(const void* d_x, int dtype, int n_ctx, int n_embd, void* d_out, int start_pos);                       /* ops.h:700,708 */
+int gtb_mul(const void* d_a, const void* d_b, int dtype, int n_ctx, int n_embd, void* d_out, int start_pos);       /* ops.h:853,861 */
+int gtb_add(const void* d_a, const void* d_b, int dtype, int n_ctx, int n_embd, void* d_out, int start_pos);       /* ops.h:900 */
+/* causal GQA attention over rows [start_pos, n_ctx); K/V rows 0..n_ctx-1 are read from d_k/d_v (the K/V
+ * Linear outputs ARE the cache, gten/modules.cpp:196-201).  d_qk may be NULL: scores stay on chip. */
+int gtb_qkv_attn(const void* d_q, const void* d_k, const void* d_v, void* d_qk, void* d_out, int dtype,
+                 int n_ctx, int n_heads, int n_kv_heads, int d_head, int max_ctx, int start_pos);                  /* ops.h:1118 */
+
+/* ---- engine: the whole TinyLlama::logits graph (tinyllama.cpp:45-61) resident on the GPU ---------- */
+typedef struct gtb_engine* gtb_engine_t;
+typedef struct {
+    int n_vocab, n_embd, n_ffn, n_layers, n_heads, n_groups;   /* TinyLLamaParams, tinyllama.cpp:12-20 */
+    int max_ctx;                                               /* TinyLlama{n_ctx, dtype} */
+    int wdtype;                                                /* GTB_F16 / GTB_Q8 / GTB_Q4; activations follow tinyllama.cpp:258-265 */
+} gtb_model_config;
+
+int gtb_engine_create(gtb_engine_t* out, const gtb_model_config* cfg);
+int gtb_engine_destroy(gtb_engine_t e);
+/* load_from_ckpt's per-tensor step (tinyllama.cpp:301-321): payload size is checked like the reference does */
+int gtb_engine_set_weight(gtb_engine_t e, int layer, int tensor_id, const void* h_payload, size_t nbytes);
+int gtb_engine_load_gten(gtb_engine_t e, const char* path);              /* tinyllama.cpp:336-392 */
+/* TinyLlama::logits(tokens, start_pos): tokens = ALL ids so far (host), rows [start_pos, n) are computed,
+ * logits of the last row are written to h_logits (n_vocab floats).  Order-exact (greedy-identical) path. */
+int gtb_engine_logits(gtb_engine_t e, const int32_t* h_tokens, int n_tokens, int start_pos, float* h_logits);
+/* greedy_sample's loop (tinyllama.cpp:395-440) kept on the device: prefill rows [0,n_prompt), then n_new
+ * argmax steps (strict '>', lowest index wins); h_tokens has room for n_prompt+n_new ids.  No EOS stop
+ * unless eos_id >= 0.  Returns the number of generated ids in *n_generated. */
+int gtb_engine_generate(gtb_engine_t e, int32_t* h_tokens, int n_prompt, int n_new, int eos_id, int* n_generated);
+/* fine-grained control used by bench.py and the tests */
+int gtb_engine_reset(gtb_engine_t e);
+int gtb_engine_prefill(gtb_engine_t e, const int32_t* h_tokens, int n_tokens);     /* exact path, rows [0,n) */
+int gtb_engine_decode(gtb_engine_t e, int n_steps);                                /* n greedy steps, device-resident */
+int gtb_engine_position(gtb_engine_t e, int* pos);
+int gtb_engine_read_tokens(gtb_engine_t e, int32_t* h_tokens, int first, int count);
+int gtb_engine_read_logits(gtb_engine_t e, float* h_logits);
+/* decoded fp32 row of a module activation for the LAST processed row (debug/parity) */
+int gtb_engine_acv(gtb_engine_t e, int layer, int acv_id, float* h_out, int* width);
+int gtb_engine_set_option(gtb_engine_t e, const char* name, int value);            /* "graph", "capture_acv" */
+int gtb_engine_weight_bytes(gtb_engine_t e, size_t* nbytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GTEN_B200_H */

@@ -1,0 +1,248 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI (ctypes), against the CPU checker on the
+same seeded inputs.  The checker is the real reference (oracle/_ref) when its prebuilt library travelled to
+this box, else the plain-C restatement.  Everything is integer/bit exact: Q8 codes, fp16 bits, fp32 logits.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import F16, F32, Q4, Q8
+from tinyllama_cpp_b200 import weights as W
+
+pytestmark = pytest.mark.gpu
+ADT = {F16: F16, Q8: Q8, Q4: Q8}
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from tinyllama_cpp_b200 import capi
+    capi.init(0)
+    return capi
+
+
+def rand_rows(rng, rows, n, scale=1.0):
+    return (rng.standard_normal((rows, n)) * scale).astype(np.float32)
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def test_device_is_blackwell(capi):
+    info = capi.device_info()
+    assert info["cc"][0] == 10, info
+
+
+@pytest.mark.parametrize("wdt", [Q4, Q8, F16])
+@pytest.mark.parametrize("shape", [(8, 2048), (37, 5632), (256, 64)])
+def test_dequantised_weights_bit_exact(capi, checker, wdt, shape):
+    rows, cols = shape
+    rng = np.random.default_rng(rows)
+    pay = W.quantize_payload(rand_rows(rng, rows, cols, 0.02), wdt)
+    w = capi.Weight(pay, wdt, rows, cols)
+    ref = np.stack([checker.read_row(r, wdt, cols) for r in pay.reshape(rows, -1)])
+    assert np.array_equal(bits(w.dequant()), bits(ref))
+    assert w.nbytes() == pay.size          # repack keeps the byte count (roofline denominator unchanged)
+
+
+@pytest.mark.parametrize("n", [1, 5, 31, 32, 33, 100, 2048, 5632])
+def test_row_codecs(capi, checker, n):
+    rng = np.random.default_rng(n)
+    x = np.concatenate([rand_rows(rng, 2, n, s) for s in (0.0, 1e-4, 1.0, 40.0)])
+    for dt in (Q8, F16, F32):
+        enc = capi.write_rows(x, dt)
+        assert np.array_equal(enc, checker.encode_rows(x, dt)), (n, dt)
+        assert np.array_equal(bits(capi.read_rows(enc, dt, n)), bits(checker.decode_rows(enc, dt, n)))
+
+
+def test_q8_rounding_ties(capi, checker):
+    """roundf is half-away-from-zero; build rows whose scaled values sit exactly on .5 (quants.h:64)."""
+    x = np.zeros((4, 32), np.float32)
+    x[:, 0] = 127.0
+    x[0, 1:] = np.arange(31) + 0.5
+    x[1, 1:] = -(np.arange(31) + 0.5)
+    x[2, 1:] = np.nextafter(np.float32(np.arange(31) + 0.5), np.float32(0))
+    x[3, 1:] = np.nextafter(np.float32(np.arange(31) + 0.5), np.float32(1e9))
+    assert np.array_equal(capi.write_rows(x, Q8), checker.encode_rows(x, Q8))
+
+
+@pytest.mark.parametrize("wdt", [Q4, Q8, F16])
+@pytest.mark.parametrize("shape", [(2048, 2048), (256, 2048), (100, 5632), (515, 2048)])
+def test_matmul_2d(capi, checker, wdt, shape):
+    n_out, k = shape
+    adt = ADT[wdt]
+    rng = np.random.default_rng(n_out * 7 + wdt)
+    n_ctx = 3
+    x = checker.encode_rows(rand_rows(rng, n_ctx, k, 1.3), adt)
+    pay = W.quantize_payload(rand_rows(rng, n_out, k, 0.02), wdt)
+    w = capi.Weight(pay, wdt, n_out, k)
+    for start in (0, 2):
+        got = capi.matmul_2d(x, adt, n_ctx, w, adt, start_pos=start)
+        ref = checker.matmul_2d(x, adt, n_ctx, k, pay, wdt, n_out, adt, start_pos=start)
+        assert np.array_equal(got[start:], ref[start:]), (wdt, shape, start)
+    got = capi.matmul_2d(x, adt, n_ctx, w, F32, out_1d=True, start_pos=n_ctx - 1)
+    ref = checker.matmul_2d(x, adt, n_ctx, k, pay, wdt, n_out, F32, out_1d=True, start_pos=n_ctx - 1)
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("adt", [Q8, F16])
+def test_elementwise_ops(capi, checker, adt):
+    rng = np.random.default_rng(70 + adt)
+    for n_ctx, n in ((4, 2048), (2, 5632), (3, 256)):
+        x = checker.encode_rows(rand_rows(rng, n_ctx, n, 2.0), adt)
+        y = checker.encode_rows(rand_rows(rng, n_ctx, n, 0.7), adt)
+        wn = (1 + 0.1 * rng.standard_normal(n)).astype(np.float16)
+        assert np.array_equal(capi.rms_norm(x, adt, n_ctx, n, wn), checker.rms_norm(x, adt, n_ctx, n, wn))
+        assert np.array_equal(capi.silu(x, adt, n_ctx, n), checker.silu(x, adt, n_ctx, n))
+        assert np.array_equal(capi.mul(x, y, adt, n_ctx, n), checker.mul(x, y, adt, n_ctx, n))
+        assert np.array_equal(capi.add(x, y, adt, n_ctx, n), checker.add(x, y, adt, n_ctx, n))
+        assert np.array_equal(capi.rotary_emb(x, adt, n_ctx, n, 64), checker.rotary_emb(x, adt, n_ctx, n, 64))
+        a = capi.rotary_emb(x, adt, n_ctx, n, 64, start_pos=n_ctx - 1)
+        assert np.array_equal(a, checker.rotary_emb(x, adt, n_ctx, n, 64, start_pos=n_ctx - 1))
+
+
+def test_silu_extremes(capi, checker):
+    """expf path: large |x| (under/overflow branches of glibc expf), zeros, tiny values."""
+    v = np.array([0, -0.0, 1e-30, -1e-30, 20, -20, 87.9, -87.9, 88.5, -88.5, 89, -89, 103.9, -103.9, 104.5, -104.5, 1e4, -1e4,
+                  0.5, -0.5, 3.25, -3.25, 7, -7, 15.5, -15.5, 31, -31, 50, -50, 65000, -65000], np.float32).reshape(1, 32)
+    x = checker.encode_rows(v, F16)
+    assert np.array_equal(capi.silu(x, F16, 1, 32), checker.silu(x, F16, 1, 32))
+    x32 = np.ascontiguousarray(v).view(np.uint8).reshape(1, -1)
+    assert np.array_equal(capi.silu(x32, F32, 1, 32), checker.silu(x32, F32, 1, 32))
+
+
+def test_rms_norm_exact_sum_adversarial(capi, checker):
+    """The in-order 2048-term fp32 sum (ops.h:765-767) is reproduced by a parallel exact algorithm; stress it."""
+    rng = np.random.default_rng(5)
+    n = 2048
+    rows = []
+    for mode in range(8):
+        for _ in range(6):
+            if mode == 0:
+                r = rng.standard_normal(n)
+            elif mode == 1:
+                r = np.ldexp(rng.integers(1, 5, n).astype(np.float64), -rng.integers(0, 6, n))      # many rounding ties
+            elif mode == 2:
+                r = np.where(rng.random(n) < 0.3, 0.0, np.abs(rng.standard_normal(n)) * np.ldexp(1.0, rng.integers(-20, 20, n)))
+            elif mode == 3:
+                r = np.full(n, 1.0)                                                              # sum crosses many binades on exact powers of two
+            elif mode == 4:
+                r = np.concatenate([np.full(1, 300.0), np.full(n - 1, 1e-3)])                    # tiny terms under a big head
+            elif mode == 5:
+                r = np.concatenate([np.full(n - 1, 1e-3), np.full(1, 300.0)])
+            elif mode == 6:
+                r = np.zeros(n); r[rng.integers(0, n, 5)] = rng.standard_normal(5) * 10
+            else:
+                r = rng.standard_normal(n) * np.ldexp(1.0, rng.integers(-8, 8))
+            rows.append(r.astype(np.float32))
+    x = np.stack(rows)
+    wn = np.ones(n, np.float16)
+    x32 = np.ascontiguousarray(x).view(np.uint8).reshape(len(rows), -1)
+    assert np.array_equal(capi.rms_norm(x32, F32, len(rows), n, wn), checker.rms_norm(x32, F32, len(rows), n, wn))
+    for adt in (Q8, F16):
+        xe = checker.encode_rows(x, adt)
+        assert np.array_equal(capi.rms_norm(xe, adt, len(rows), n, wn), checker.rms_norm(xe, adt, len(rows), n, wn))
+
+
+@pytest.mark.parametrize("wdt", [Q4, Q8, F16])
+def test_token_embed(capi, checker, wdt):
+    rng = np.random.default_rng(9)
+    n_vocab, n = 50, 2048
+    adt = ADT[wdt]
+    pay = W.quantize_payload(rand_rows(rng, n_vocab, n, 0.02), wdt)
+    toks = rng.integers(0, n_vocab, 6).astype(np.int32)
+    w = capi.Weight(pay, wdt, n_vocab, n)
+    assert np.array_equal(capi.token_embed(w, toks, adt), checker.token_embed(pay, wdt, n_vocab, n, toks, adt))
+    got = capi.token_embed(w, toks, adt, start_pos=5)
+    assert np.array_equal(got[5:], checker.token_embed(pay, wdt, n_vocab, n, toks, adt, start_pos=5)[5:])
+
+
+@pytest.mark.parametrize("adt", [Q8, F16])
+@pytest.mark.parametrize("n_ctx,max_ctx", [(1, 64), (7, 64), (8, 64), (9, 64), (33, 128), (40, 128), (64, 256), (100, 512)])
+def test_attention(capi, checker, adt, n_ctx, max_ctx):
+    """Multi-row and single-row calls inside the reference's valid domain."""
+    assert (2 * n_ctx <= max_ctx) if adt == F16 else (((n_ctx + 31) // 32) * 34 <= max_ctx)
+    rng = np.random.default_rng(n_ctx + adt)
+    H, G, D = 32, 4, 64
+    q = checker.encode_rows(rand_rows(rng, n_ctx, H * D), adt)
+    k = checker.encode_rows(rand_rows(rng, n_ctx, G * D), adt)
+    v = checker.encode_rows(rand_rows(rng, n_ctx, G * D), adt)
+    for start in sorted({0, n_ctx - 1}):
+        got = capi.qkv_attn(q, k, v, adt, n_ctx, H, G, D, max_ctx, start_pos=start)
+        ref = checker.qkv_attn(q, k, v, adt, n_ctx, H, G, D, max_ctx, start_pos=start)
+        assert np.array_equal(got[start:], ref[start:]), (adt, n_ctx, start)
+
+
+@pytest.mark.parametrize("adt", [Q8, F16])
+def test_attention_long_context_decode_row(capi, adt):
+    """A single decode row at t = 2048 (full KV, BASELINE config 3) against the plain-C restatement."""
+    port = oracle.port()
+    rng = np.random.default_rng(2048)
+    H, G, D, n_ctx = 32, 4, 64, 2048
+    q = port.encode_rows(rand_rows(rng, n_ctx, H * D), adt)
+    k = port.encode_rows(rand_rows(rng, n_ctx, G * D), adt)
+    v = port.encode_rows(rand_rows(rng, n_ctx, G * D), adt)
+    got = capi.qkv_attn(q, k, v, adt, n_ctx, H, G, D, n_ctx, start_pos=n_ctx - 1)
+    ref = port.qkv_attn(q, k, v, adt, n_ctx, H, G, D, n_ctx, start_pos=n_ctx - 1)
+    assert np.array_equal(got[-1], ref[-1])
+
+
+@pytest.mark.parametrize("wdt", [Q4, Q8, F16])
+def test_engine_mini_model(capi, checker, wdt):
+    """Teacher-forced logits, free-running greedy tokens and every per-layer activation, bit for bit."""
+    cfg = W.mini_config(n_layers=3, n_vocab=300)
+    wl = list(W.synth_weights(cfg, wdt, seed=21))
+    max_ctx = 128
+    cm = checker.model(cfg, max_ctx, wdt).load(wl)
+    e = capi.Engine(cfg, max_ctx, wdt).load(wl)
+    prompt = W.synth_prompt(5, 33, cfg.n_vocab)
+    n_new = 20
+    ct, _, clog = cm.generate(prompt, n_new, want_logits=True)
+    gt = e.generate(prompt, n_new)
+    assert np.array_equal(gt, ct)
+    # graph replay and eager launches agree
+    e.set_option("graph", 0)
+    assert np.array_equal(e.generate(prompt, n_new), ct)
+    # logits() with the reference's calling protocol (all tokens so far + start_pos)
+    assert np.array_equal(bits(e.logits(ct[:33], 0)), bits(clog[0]))
+    for i in (1, 2, 7, n_new - 1):
+        n = 33 + i
+        assert np.array_equal(bits(e.logits(ct[:n], n - 1)), bits(clog[i])), i
+    # per-layer activations of the last processed row
+    e.set_option("capture_acv", 1)
+    n = 33 + n_new - 1
+    e.logits(ct[:n], n - 1)
+    cm.capture_row(n - 1)
+    cm.logits(ct[:n], n - 1)
+    for layer in range(cfg.n_layers):
+        for name, aid in oracle.LAYER_ACVS.items():
+            assert np.array_equal(bits(e.acv(layer, aid)), bits(cm.acv(layer, aid, n - 1))), (layer, name)
+    assert np.array_equal(bits(e.acv(0, oracle.A_FINAL_NORM)), bits(cm.acv(0, oracle.A_FINAL_NORM, n - 1)))
+    assert np.array_equal(bits(e.acv(0, oracle.A_EMB)), bits(cm.acv(0, oracle.A_EMB, n - 1)))
+    e.close(); cm.close()
+
+
+def test_engine_errors(capi):
+    cfg = W.mini_config(n_layers=1, n_vocab=64)
+    e = capi.Engine(cfg, 16, Q4)
+    with pytest.raises(capi.GtbError, match="not loaded"):
+        e.logits(np.zeros(4, np.int32), 0)
+    with pytest.raises(capi.GtbError, match="does not match the expected size"):
+        e.set_weight(0, W.T_Q, np.zeros(10, np.uint8))
+    e.load(W.synth_weights(cfg, Q4, seed=2))
+    with pytest.raises(capi.GtbError, match="exceed provided maximum ctx size"):
+        e.logits(np.zeros(17, np.int32), 0)
+    e.close()
+
+
+def test_gten_file_roundtrip(capi, checker, tmp_path):
+    cfg = W.mini_config(n_layers=1, n_vocab=64)
+    wl = list(W.synth_weights(cfg, Q8, seed=4))
+    path = tmp_path / "mini.q8.gten"
+    W.write_gten(path, cfg, Q8, wl)
+    assert all(np.array_equal(a[2], b[2]) for a, b in zip(wl, W.read_gten(path, cfg, Q8)))
+    e = capi.Engine(cfg, 32, Q8).load_gten(path)
+    cm = checker.model(cfg, 32, Q8).load(wl)
+    prompt = W.synth_prompt(1, 5, cfg.n_vocab)
+    assert np.array_equal(e.generate(prompt, 6), cm.generate(prompt, 6)[0])
+    e.close(); cm.close()

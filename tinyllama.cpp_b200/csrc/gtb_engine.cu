@@ -1,0 +1,761 @@
+// gtb_engine.cu -- the whole TinyLlama::logits graph (tinyllama.cpp:45-61) resident on one GPU.
+//
+// One sequence row = 5 phase kernels per layer (see gtb_kernels.cuh) + embedding + lm_head + argmax, all on
+// the library stream; position / token live in device memory so a captured CUDA graph replays every row
+// and the greedy loop (tinyllama.cpp:395-440) never returns to the host between tokens.
+#include <math.h>
+#include <string.h>
+
+#include <fstream>
+#include <vector>
+
+#include "gtb_internal.h"
+#include "gtb_kernels.cuh"
+
+namespace gtb {
+
+enum { PRO_ENCODE = 0, PRO_NORM = 1, PRO_SILU_MUL = 2 };
+
+struct DevState {
+    int pos;        // row to process next
+    int nctx_min;   // n_ctx of the current logits() call (P row length / P.V lane split), SURVEY App. A
+    int stop;       // set when eos was generated
+    int n_gen;
+};
+
+struct GemvMat {
+    const void* data;
+    const uint16_t* scales;
+    int rows;
+    float* out;
+};
+
+struct PhaseArgs {
+    int K;
+    int n_mats;
+    GemvMat mat[3];
+    const float* src0;
+    const float* src1;
+    const uint16_t* normw;
+    float* res_out;
+    float* cap0;
+    float* cap1;
+    float* cap2;
+};
+
+template <int WT, int PRO>
+__global__ void __launch_bounds__(NT) k_phase_gemv(PhaseArgs a) {
+    constexpr int AT = (WT == DT_F16) ? DT_F16 : DT_Q8;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int K = a.K;
+    // carve: [act][ps (per warp)][xbuf][ExactSumSmem]
+    ActView av = act_carve(AT, K, smem);
+    size_t off = (act_bytes(AT, K) + 15) & ~(size_t)15;
+    float* ps = reinterpret_cast<float*>(smem + off);
+    const size_t ps_warp = gemv_ps_bytes(WT, K) / NWARP;
+    off += gemv_ps_bytes(WT, K);
+    const bool c0 = blockIdx.x == 0;
+    if (PRO == PRO_ENCODE) {
+        pro_encode<AT>(av, a.src0, K, c0 ? a.cap0 : nullptr);
+    } else if (PRO == PRO_NORM) {
+        float* xbuf = reinterpret_cast<float*>(smem + off);
+        off += (size_t)K * 4;
+        off = (off + 15) & ~(size_t)15;
+        ExactSumSmem& es = *reinterpret_cast<ExactSumSmem*>(smem + off);
+        pro_norm<AT>(av, a.src0, a.src1, a.normw, K, xbuf, es, c0 ? a.res_out : nullptr,
+                     c0 ? a.cap0 : nullptr, c0 ? a.cap1 : nullptr, c0 ? a.cap2 : nullptr);
+    } else {
+        pro_silu_mul<AT>(av, a.src0, a.src1, K, c0 ? a.cap0 : nullptr, c0 ? a.cap1 : nullptr);
+    }
+    __syncthreads();
+    float* my_ps = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ps) + ps_warp * (threadIdx.x >> 5));
+    int done = 0;
+    for (int m = 0; m < a.n_mats; m++)
+        gemv_matrix<WT>(a.mat[m].data, a.mat[m].scales, a.mat[m].rows, K, av, my_ps, a.mat[m].out, done, &done);
+}
+
+static size_t phase_smem(int wt, int pro, int K) {
+    const int at = (wt == DT_F16) ? DT_F16 : DT_Q8;
+    size_t s = (act_bytes(at, K) + 15) & ~(size_t)15;
+    s += gemv_ps_bytes(wt, K);
+    if (pro == PRO_NORM) { s += (size_t)K * 4; s = (s + 15) & ~(size_t)15; s += sizeof(ExactSumSmem); }
+    return s + 16;
+}
+
+// ---------------------------------------------------------------- embedding (gten/ops.h:514-564)
+template <int WT>
+__global__ void __launch_bounds__(NT) k_embed(const void* __restrict__ wdata, const uint16_t* __restrict__ wsc, int n_embd,
+                                               const int32_t* __restrict__ tokens, const DevState* __restrict__ st,
+                                               float* __restrict__ xres, float* cap) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t row = (size_t)tokens[st->pos];
+    for (int b = wid; b < n_embd / 32; b += NWARP) {
+        const int e = b * 32 + lane;
+        float v;
+        if (WT == DT_F16) {
+            const int c = e >> 6, r = e & 63, l = r & 7, ii = r >> 3;
+            v = h2f(reinterpret_cast<const uint16_t*>(wdata)[((row * (n_embd / 64) + c) * 8 + l) * 8 + ii]);   // memcpy of the fp16 row
+        } else {
+            const size_t blk = row * (n_embd / 32) + b;
+            const float delta = h2f(wsc[blk]);
+            const int pb = perm_byte(lane);
+            if (WT == DT_Q8) {
+                const int8_t q = reinterpret_cast<const int8_t*>(wdata)[blk * 32 + pb];                      // memcpy of the Q8 row
+                v = __fmul_rn((float)q, delta);
+            } else {
+                // Q4 row: dequantise, then re-encode as Q8 (ops.h:522-528)
+                const int j = lane & 15;
+                const int l = (j & 7) >> 1, pos = (j & 1) + 2 * (j >> 3);
+                const uint8_t byte = reinterpret_cast<const uint8_t*>(wdata)[blk * 16 + l * 4 + pos];
+                const int q = (int)((lane < 16) ? (byte >> 4) : (byte & 0x0f)) - 7;
+                v = q8_roundtrip_lane(__fmul_rn((float)q, delta));
+            }
+        }
+        xres[e] = v;
+        if (cap) cap[e] = v;
+    }
+}
+
+// ---------------------------------------------------------------- attention phase
+struct AttnArgs {
+    const float* rqkv;        // raw q | k | v of this row
+    int n_embd, kv_dim, n_heads, gsz;
+    uint8_t* kq; uint16_t* ks; uint8_t* vq; uint16_t* vs;
+    const float* rope_cos; const float* rope_sin;    // [max_ctx][32], host-built with the reference's libm calls
+    const DevState* st;
+    float* out;               // raw attention output [n_embd]
+    float* cap_q; float* cap_k; float* cap_v;
+};
+
+template <int AT>
+__global__ void __launch_bounds__(NT) k_attn(AttnArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    AttnSmem& sm = *reinterpret_cast<AttnSmem*>(smem);
+    float* sc = reinterpret_cast<float*>(smem + ((sizeof(AttnSmem) + 15) & ~(size_t)15));
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int h = blockIdx.x, g = h / a.gsz;
+    const int pos = a.st->pos;
+    const int n_ctx = max(a.st->nctx_min, pos + 1);
+    const bool writer = (h % a.gsz) == 0;
+    // first re-encode of the Linear outputs (q: warps 0,1; k: 2,3; v: 4,5), gten/ops.h:645-646
+    if (wid < 6) {
+        const int which = wid >> 1, half = wid & 1;
+        const float* src = (which == 0) ? a.rqkv + h * 64 : (which == 1) ? a.rqkv + a.n_embd + g * 64 : a.rqkv + a.n_embd + a.kv_dim + g * 64;
+        const float x = src[half * 32 + lane];
+        if (which < 2) {
+            sm.tmp[wid][lane] = roundtrip<AT>(x);
+        } else if (AT == DT_F16) {
+            const uint16_t hb = f2h(x);
+            sm.vf[half * 32 + lane] = h2f(hb);
+            if (writer) reinterpret_cast<uint16_t*>(a.vq)[(size_t)pos * a.kv_dim + g * 64 + half * 32 + lane] = hb;
+            if (writer && a.cap_v) a.cap_v[g * 64 + half * 32 + lane] = h2f(hb);
+        } else {
+            uint16_t dh;
+            const int q = q8_encode_lane(x, &dh);
+            const float d = __fmul_rn((float)q, h2f(dh));
+            sm.vf[half * 32 + lane] = d;
+            if (writer) {
+                a.vq[(size_t)pos * a.kv_dim + g * 64 + half * 32 + lane] = (uint8_t)(int8_t)q;
+                if (lane == 0) a.vs[(size_t)pos * (a.kv_dim / 32) + g * 2 + half] = dh;
+                if (a.cap_v) a.cap_v[g * 64 + half * 32 + lane] = d;
+            }
+        }
+    }
+    __syncthreads();
+    // RoPE on q and k (gten/ops.h:733-751), then the second re-encode (ops.h:753)
+    if (wid < 4) {
+        const int which = wid >> 1, half = wid & 1;
+        const float x0 = sm.tmp[which * 2][lane], x1 = sm.tmp[which * 2 + 1][lane];
+        const float cs = a.rope_cos[(size_t)pos * 32 + lane], sn = a.rope_sin[(size_t)pos * 32 + lane];
+        const float o = (half == 0) ? __fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn))
+                                    : __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs));
+        if (AT == DT_F16) {
+            const uint16_t hb = f2h(o);
+            const float d = h2f(hb);
+            if (which == 0) { sm.qf[half * 32 + lane] = d; if (a.cap_q) a.cap_q[h * 64 + half * 32 + lane] = d; }
+            else {
+                sm.kf[half * 32 + lane] = d;
+                if (writer) reinterpret_cast<uint16_t*>(a.kq)[(size_t)pos * a.kv_dim + g * 64 + half * 32 + lane] = hb;
+                if (writer && a.cap_k) a.cap_k[g * 64 + half * 32 + lane] = d;
+            }
+        } else {
+            uint16_t dh;
+            const int q = q8_encode_lane(o, &dh);
+            const float delta = h2f(dh);
+            const int pb = perm_byte(lane);
+            if (which == 0) {
+                reinterpret_cast<int8_t*>(sm.qw)[half * 32 + pb] = (int8_t)q;
+                if (lane == 0) sm.qd[half] = delta;
+                if (a.cap_q) a.cap_q[h * 64 + half * 32 + lane] = __fmul_rn((float)q, delta);
+            } else {
+                reinterpret_cast<int8_t*>(sm.kw)[half * 32 + pb] = (int8_t)q;
+                if (lane == 0) sm.kd[half] = delta;
+                if (writer) {
+                    a.kq[(size_t)pos * a.kv_dim + g * 64 + half * 32 + pb] = (uint8_t)(int8_t)q;
+                    if (lane == 0) a.ks[(size_t)pos * (a.kv_dim / 32) + g * 2 + half] = dh;
+                    if (a.cap_k) a.cap_k[g * 64 + half * 32 + lane] = __fmul_rn((float)q, delta);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    KVCache kv{a.kq, a.ks, a.vq, a.vs, a.kv_dim};
+    attn_core<AT>(sm, sc, kv, g, pos, n_ctx, true, a.out + h * 64);
+}
+
+// ---------------------------------------------------------------- argmax + bookkeeping (tinyllama.cpp:416-434)
+__global__ void __launch_bounds__(1024) k_argmax_advance(const float* __restrict__ logits, int n, int32_t* tokens,
+                                                          DevState* st, int eos_id) {
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float best = -INFINITY;
+    int arg = 0x7fffffff;
+    for (int j = tid; j < n; j += blockDim.x) {
+        const float v = logits[j];
+        if (v > best) { best = v; arg = j; }        // ascending j per thread: first maximum wins
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
+    }
+    if (lane == 0) { sv[wid] = best; si[wid] = arg; }
+    __syncthreads();
+    if (wid == 0) {
+        best = sv[lane]; arg = si[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
+        }
+        if (lane == 0) {
+            if (arg == 0x7fffffff) arg = 0;          // all -inf/NaN: the reference's loop leaves max_index = 0
+            const int pos = st->pos;
+            tokens[pos + 1] = arg;
+            st->pos = pos + 1;
+            st->n_gen += 1;
+            if (arg == eos_id) st->stop = 1;
+        }
+    }
+}
+
+__global__ void k_advance(DevState* st) { st->pos += 1; }
+
+// ---------------------------------------------------------------- host side
+struct LayerW {
+    gtb_weight_t q = nullptr, k = nullptr, v = nullptr, o = nullptr, gate = nullptr, up = nullptr, down = nullptr;
+    uint16_t* attn_norm = nullptr;
+    uint16_t* ffn_norm = nullptr;
+    uint8_t *kq = nullptr, *vq = nullptr;
+    uint16_t *ks = nullptr, *vs = nullptr;
+};
+
+}  // namespace gtb
+
+using namespace gtb;
+
+struct gtb_engine {
+    gtb_model_config cfg{};
+    int adtype = 0, d_head = 0, kv_dim = 0, gsz = 0;
+    gtb_weight_t embed = nullptr, lm_head = nullptr;
+    uint16_t* final_norm = nullptr;
+    std::vector<LayerW> L;
+    float *rope_cos = nullptr, *rope_sin = nullptr;
+    // per-row buffers
+    float *xres = nullptr, *hres = nullptr, *rqkv = nullptr, *rattn = nullptr, *ro = nullptr, *rg = nullptr, *ru = nullptr,
+          *rd = nullptr, *logits = nullptr, *xfinal = nullptr;
+    int32_t* tokens = nullptr;
+    DevState* st = nullptr;
+    float* cap = nullptr;            // [n_layers][12][capw] + [2][capw]
+    int capw = 0;
+    bool capture = false;
+    bool use_graph = true;
+    cudaGraphExec_t g_body = nullptr, g_head = nullptr;
+    int g_eos = -2;
+    int grid = 0;
+    int host_pos = 0;
+    size_t weight_bytes = 0;
+    int launches_body = 0, launches_head = 0;
+};
+
+namespace {
+
+float* capp(gtb_engine* e, int layer, int aid) {
+    if (!e->capture) return nullptr;
+    if (aid == GTB_A_EMB) return e->cap + (size_t)e->cfg.n_layers * 12 * e->capw;
+    if (aid == GTB_A_FINAL_NORM) return e->cap + ((size_t)e->cfg.n_layers * 12 + 1) * e->capw;
+    return e->cap + ((size_t)layer * 12 + (aid - GTB_A_ATTN_NORM)) * e->capw;
+}
+
+template <int WT, int PRO>
+int launch_phase(gtb_engine* e, const PhaseArgs& a) {
+    const size_t smem = phase_smem(WT, PRO, a.K);
+    static bool attr_done = false;            // one per template instantiation
+    if (!attr_done) {
+        GTB_CUDA(cudaFuncSetAttribute(k_phase_gemv<WT, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+    }
+    k_phase_gemv<WT, PRO><<<e->grid, NT, smem, ctx().stream>>>(a);
+    GTB_LAUNCHED();
+    return GTB_OK;
+}
+
+GemvMat matof(gtb_weight_t w, float* out) { return GemvMat{w->data, w->scales, w->rows, out}; }
+
+template <int WT>
+int enqueue_row(gtb_engine* e, bool with_head, int eos_id) {
+    constexpr int AT = (WT == DT_F16) ? DT_F16 : DT_Q8;
+    const gtb_model_config& c = e->cfg;
+    cudaStream_t st = ctx().stream;
+    const int E = c.n_embd, F = c.n_ffn, KV = e->kv_dim;
+    k_embed<WT><<<1, NT, 0, st>>>(e->embed->data, e->embed->scales, E, e->tokens, e->st, e->xres, capp(e, 0, GTB_A_EMB));
+    GTB_LAUNCHED();
+    static bool attn_attr = false;
+    if (!attn_attr) {
+        GTB_CUDA(cudaFuncSetAttribute(k_attn<AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attn_attr = true;
+    }
+    const size_t attn_smem = ((sizeof(AttnSmem) + 15) & ~(size_t)15) + (size_t)((c.max_ctx + 63) / 32 * 32) * 4;
+    for (int li = 0; li < c.n_layers; li++) {
+        LayerW& l = e->L[li];
+        {   // P1: residual/norm prologue + q|k|v
+            PhaseArgs a{};
+            a.K = E; a.n_mats = 3;
+            a.mat[0] = matof(l.q, e->rqkv); a.mat[1] = matof(l.k, e->rqkv + E); a.mat[2] = matof(l.v, e->rqkv + E + KV);
+            a.src0 = (li == 0) ? e->xres : e->hres;
+            a.src1 = (li == 0) ? nullptr : e->rd;
+            a.normw = l.attn_norm;
+            a.res_out = e->xres;
+            a.cap0 = (li == 0) ? nullptr : capp(e, li - 1, GTB_A_DOWN);
+            a.cap1 = (li == 0) ? nullptr : capp(e, li - 1, GTB_A_ATTN_RES);
+            a.cap2 = capp(e, li, GTB_A_ATTN_NORM);
+            int r = launch_phase<WT, PRO_NORM>(e, a);
+            if (r) return r;
+        }
+        {   // P2: attention
+            AttnArgs a{};
+            a.rqkv = e->rqkv; a.n_embd = E; a.kv_dim = KV; a.n_heads = c.n_heads; a.gsz = e->gsz;
+            a.kq = l.kq; a.ks = l.ks; a.vq = l.vq; a.vs = l.vs;
+            a.rope_cos = e->rope_cos; a.rope_sin = e->rope_sin; a.st = e->st; a.out = e->rattn;
+            a.cap_q = capp(e, li, GTB_A_Q); a.cap_k = capp(e, li, GTB_A_K); a.cap_v = capp(e, li, GTB_A_V);
+            k_attn<AT><<<c.n_heads, NT, attn_smem, st>>>(a);
+            GTB_LAUNCHED();
+        }
+        {   // P3: o-proj
+            PhaseArgs a{};
+            a.K = E; a.n_mats = 1; a.mat[0] = matof(l.o, e->ro);
+            a.src0 = e->rattn; a.cap0 = capp(e, li, GTB_A_ATTN_OUT);
+            int r = launch_phase<WT, PRO_ENCODE>(e, a);
+            if (r) return r;
+        }
+        {   // P4: residual/norm prologue + gate|up
+            PhaseArgs a{};
+            a.K = E; a.n_mats = 2; a.mat[0] = matof(l.gate, e->rg); a.mat[1] = matof(l.up, e->ru);
+            a.src0 = e->xres; a.src1 = e->ro; a.normw = l.ffn_norm; a.res_out = e->hres;
+            a.cap0 = capp(e, li, GTB_A_O); a.cap1 = capp(e, li, GTB_A_INP_RES); a.cap2 = capp(e, li, GTB_A_FFN_NORM);
+            int r = launch_phase<WT, PRO_NORM>(e, a);
+            if (r) return r;
+        }
+        {   // P5: SiLU*up prologue + down
+            PhaseArgs a{};
+            a.K = F; a.n_mats = 1; a.mat[0] = matof(l.down, e->rd);
+            a.src0 = e->rg; a.src1 = e->ru; a.cap0 = capp(e, li, GTB_A_GATE); a.cap1 = capp(e, li, GTB_A_UP);
+            int r = launch_phase<WT, PRO_SILU_MUL>(e, a);
+            if (r) return r;
+        }
+    }
+    if (with_head || e->capture) {   // final residual + norm + lm_head (tinyllama.cpp:57-58)
+        PhaseArgs a{};
+        a.K = E; a.n_mats = with_head ? 1 : 0;
+        a.mat[0] = matof(e->lm_head, e->logits);
+        a.src0 = e->hres; a.src1 = e->rd; a.normw = e->final_norm; a.res_out = e->xfinal;
+        a.cap0 = capp(e, c.n_layers - 1, GTB_A_DOWN); a.cap1 = capp(e, c.n_layers - 1, GTB_A_ATTN_RES);
+        a.cap2 = capp(e, 0, GTB_A_FINAL_NORM);
+        int r = launch_phase<WT, PRO_NORM>(e, a);
+        if (r) return r;
+    }
+    if (with_head) {
+        k_argmax_advance<<<1, 1024, 0, st>>>(e->logits, c.n_vocab, e->tokens, e->st, eos_id);
+        GTB_LAUNCHED();
+    } else {
+        k_advance<<<1, 1, 0, st>>>(e->st);
+        GTB_LAUNCHED();
+    }
+    return GTB_OK;
+}
+
+int enqueue_row_dt(gtb_engine* e, bool with_head, int eos_id) {
+    switch (e->cfg.wdtype) {
+        case GTB_F16: return enqueue_row<DT_F16>(e, with_head, eos_id);
+        case GTB_Q8: return enqueue_row<DT_Q8>(e, with_head, eos_id);
+        default: return enqueue_row<DT_Q4>(e, with_head, eos_id);
+    }
+}
+
+void drop_graphs(gtb_engine* e) {
+    if (e->g_body) { cudaGraphExecDestroy(e->g_body); e->g_body = nullptr; }
+    if (e->g_head) { cudaGraphExecDestroy(e->g_head); e->g_head = nullptr; }
+}
+
+int build_graph(gtb_engine* e, bool with_head, int eos_id, cudaGraphExec_t* out, int* n_launches) {
+    cudaStream_t st = ctx().stream;
+    // make sure every cudaFuncSetAttribute happened outside capture: run one row eagerly on scratch state? No --
+    // attributes are set lazily inside launch_phase, which is legal during capture (not a stream operation).
+    const int64_t before = ctx().launches;
+    GTB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int r = enqueue_row_dt(e, with_head, eos_id);
+    cudaGraph_t g = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(st, &g);
+    *n_launches = (int)(ctx().launches - before);
+    ctx().launches = before;
+    if (r) { if (g) cudaGraphDestroy(g); return r; }
+    if (ce != cudaSuccess) return fail(GTB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(out, g, 0);
+    cudaGraphDestroy(g);
+    if (ce != cudaSuccess) return fail(GTB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+    return GTB_OK;
+}
+
+// rows to run: `n_body` rows without lm_head, then `n_head` rows with lm_head + argmax
+int run_rows(gtb_engine* e, int n_body, int n_head, int eos_id) {
+    cudaStream_t st = ctx().stream;
+    if (e->use_graph && !e->capture) {
+        if (n_body > 0 && !e->g_body) { int r = build_graph(e, false, -1, &e->g_body, &e->launches_body); if (r) return r; }
+        if (n_head > 0 && (!e->g_head || e->g_eos != eos_id)) {
+            if (e->g_head) { cudaGraphExecDestroy(e->g_head); e->g_head = nullptr; }
+            int r = build_graph(e, true, eos_id, &e->g_head, &e->launches_head);
+            if (r) return r;
+            e->g_eos = eos_id;
+        }
+        for (int i = 0; i < n_body; i++) { GTB_CUDA(cudaGraphLaunch(e->g_body, st)); ctx().launches += e->launches_body; }
+        for (int i = 0; i < n_head; i++) { GTB_CUDA(cudaGraphLaunch(e->g_head, st)); ctx().launches += e->launches_head; }
+    } else {
+        for (int i = 0; i < n_body; i++) { int r = enqueue_row_dt(e, false, -1); if (r) return r; }
+        for (int i = 0; i < n_head; i++) { int r = enqueue_row_dt(e, true, eos_id); if (r) return r; }
+    }
+    return GTB_OK;
+}
+
+int set_state(gtb_engine* e, int pos, int nctx_min) {
+    DevState s{pos, nctx_min, 0, 0};
+    GTB_CUDA(cudaMemcpyAsync(e->st, &s, sizeof s, cudaMemcpyHostToDevice, ctx().stream));
+    GTB_CUDA(cudaStreamSynchronize(ctx().stream));      // `s` is a stack object
+    return GTB_OK;
+}
+
+size_t expect_bytes(const gtb_engine* e, int tid, int* rows, int* cols, int* dt) {
+    const gtb_model_config& c = e->cfg;
+    int r = 0, k = c.n_embd, d = c.wdtype;
+    switch (tid) {
+        case GTB_T_EMBED: case GTB_T_LM_HEAD: r = c.n_vocab; break;
+        case GTB_T_Q: case GTB_T_O: r = c.n_embd; break;
+        case GTB_T_K: case GTB_T_V: r = e->kv_dim; break;
+        case GTB_T_GATE: case GTB_T_UP: r = c.n_ffn; break;
+        case GTB_T_DOWN: r = c.n_embd; k = c.n_ffn; break;
+        case GTB_T_FINAL_NORM: case GTB_T_ATTN_NORM: case GTB_T_FFN_NORM: r = 1; d = GTB_F16; break;   // norm weights are fp16 (modules.cpp:84)
+        default: return 0;
+    }
+    *rows = r; *cols = k; *dt = d;
+    return (size_t)r * row_nbytes(d, k);
+}
+
+}  // namespace
+
+extern "C" {
+
+int gtb_engine_create(gtb_engine_t* out, const gtb_model_config* cfg) {
+    GTB_CHECK_INIT();
+    GTB_ARG(out && cfg);
+    GTB_ARG(cfg->wdtype == GTB_F16 || cfg->wdtype == GTB_Q8 || cfg->wdtype == GTB_Q4);
+    GTB_ARG(cfg->n_embd % 64 == 0 && cfg->n_ffn % 64 == 0 && cfg->n_heads > 0 && cfg->n_groups > 0);
+    GTB_ARG(cfg->n_embd / cfg->n_heads == 64);               // d_head is a compile-time constant of the attention kernel
+    GTB_ARG(cfg->n_heads % cfg->n_groups == 0 && cfg->max_ctx > 0 && cfg->n_layers > 0 && cfg->n_vocab > 0);
+    GTB_ARG(cfg->n_embd <= NT * ES_EPT * 4);
+    auto* e = new gtb_engine();
+    e->cfg = *cfg;
+    e->adtype = (cfg->wdtype == GTB_F16) ? GTB_F16 : GTB_Q8;  // tinyllama.cpp:258-265
+    e->d_head = 64;
+    e->kv_dim = 64 * cfg->n_groups;
+    e->gsz = cfg->n_heads / cfg->n_groups;
+    e->grid = ctx().sm_count;
+    e->L.resize(cfg->n_layers);
+    const int E = cfg->n_embd, F = cfg->n_ffn, KV = e->kv_dim, MC = cfg->max_ctx;
+    auto dalloc = [&](void** p, size_t n) -> int { GTB_CUDA(cudaMalloc(p, n)); GTB_CUDA(cudaMemsetAsync(*p, 0, n, ctx().stream)); ctx().mem += (int64_t)n; return GTB_OK; };
+    int r = 0;
+    for (auto& l : e->L) {
+        const size_t code_bytes = (size_t)MC * KV * (e->adtype == GTB_F16 ? 2 : 1);
+        r |= dalloc((void**)&l.kq, code_bytes); r |= dalloc((void**)&l.vq, code_bytes);
+        if (e->adtype == GTB_Q8) { r |= dalloc((void**)&l.ks, (size_t)MC * (KV / 32) * 2); r |= dalloc((void**)&l.vs, (size_t)MC * (KV / 32) * 2); }
+        r |= dalloc((void**)&l.attn_norm, (size_t)E * 2); r |= dalloc((void**)&l.ffn_norm, (size_t)E * 2);
+    }
+    r |= dalloc((void**)&e->final_norm, (size_t)E * 2);
+    r |= dalloc((void**)&e->xres, E * 4); r |= dalloc((void**)&e->hres, E * 4); r |= dalloc((void**)&e->xfinal, E * 4);
+    r |= dalloc((void**)&e->rqkv, (size_t)(E + 2 * KV) * 4); r |= dalloc((void**)&e->rattn, E * 4); r |= dalloc((void**)&e->ro, E * 4);
+    r |= dalloc((void**)&e->rg, F * 4); r |= dalloc((void**)&e->ru, F * 4); r |= dalloc((void**)&e->rd, E * 4);
+    r |= dalloc((void**)&e->logits, (size_t)cfg->n_vocab * 4);
+    r |= dalloc((void**)&e->tokens, (size_t)(MC + 2) * 4);
+    r |= dalloc((void**)&e->st, sizeof(DevState));
+    e->capw = (F > E) ? F : E;
+    r |= dalloc((void**)&e->cap, ((size_t)cfg->n_layers * 12 + 2) * e->capw * 4);
+    r |= dalloc((void**)&e->rope_cos, (size_t)MC * 32 * 4); r |= dalloc((void**)&e->rope_sin, (size_t)MC * 32 * 4);
+    if (r) { return r; }
+    {   // RoPE table with the reference's own expressions and libm (gten/ops.h:728-746; SURVEY §7 hard part 4)
+        std::vector<float> cs((size_t)MC * 32), sn((size_t)MC * 32);
+        const float d = 64.0f;
+        for (int p = 0; p < MC; p++) {
+            const float m = static_cast<float>(p);
+            for (int j = 0; j < 32; j++) {
+                const float m_theta_i = m * powf(10000.0f, -(2.0f * j / d));
+                cs[(size_t)p * 32 + j] = cosf(m_theta_i);
+                sn[(size_t)p * 32 + j] = sinf(m_theta_i);
+            }
+        }
+        GTB_CUDA(cudaMemcpy(e->rope_cos, cs.data(), cs.size() * 4, cudaMemcpyHostToDevice));
+        GTB_CUDA(cudaMemcpy(e->rope_sin, sn.data(), sn.size() * 4, cudaMemcpyHostToDevice));
+    }
+    GTB_CUDA(cudaStreamSynchronize(ctx().stream));
+    *out = e;
+    return GTB_OK;
+}
+
+int gtb_engine_destroy(gtb_engine_t e) {
+    if (!e) return GTB_OK;
+    GTB_CHECK_INIT();
+    cudaStreamSynchronize(ctx().stream);
+    drop_graphs(e);
+    for (auto& l : e->L) {
+        gtb_weight_free(l.q); gtb_weight_free(l.k); gtb_weight_free(l.v); gtb_weight_free(l.o);
+        gtb_weight_free(l.gate); gtb_weight_free(l.up); gtb_weight_free(l.down);
+        cudaFree(l.attn_norm); cudaFree(l.ffn_norm); cudaFree(l.kq); cudaFree(l.vq); cudaFree(l.ks); cudaFree(l.vs);
+    }
+    gtb_weight_free(e->embed); gtb_weight_free(e->lm_head);
+    void* bufs[] = {e->final_norm, e->xres, e->hres, e->xfinal, e->rqkv, e->rattn, e->ro, e->rg, e->ru, e->rd, e->logits,
+                    e->tokens, e->st, e->cap, e->rope_cos, e->rope_sin};
+    for (void* b : bufs) cudaFree(b);
+    delete e;
+    return GTB_OK;
+}
+
+int gtb_engine_set_weight(gtb_engine_t e, int layer, int tensor_id, const void* h_payload, size_t nbytes) {
+    GTB_CHECK_INIT();
+    GTB_ARG(e && h_payload);
+    int rows = 0, cols = 0, dt = 0;
+    const size_t expect = expect_bytes(e, tensor_id, &rows, &cols, &dt);
+    GTB_ARG(expect != 0);
+    if (nbytes != expect)   // the reference's per-tensor check, tinyllama.cpp:316-319
+        return fail(GTB_ERR_ARG, "Weight %d/%d data size: %zu does not match the expected size: %zu.", layer, tensor_id, nbytes, expect);
+    const bool per_layer = tensor_id >= GTB_T_Q;
+    GTB_ARG(!per_layer || (layer >= 0 && layer < e->cfg.n_layers));
+    if (dt == GTB_F16 && rows == 1) {
+        uint16_t* dst = (tensor_id == GTB_T_FINAL_NORM) ? e->final_norm : (tensor_id == GTB_T_ATTN_NORM) ? e->L[layer].attn_norm : e->L[layer].ffn_norm;
+        GTB_CUDA(cudaMemcpy(dst, h_payload, nbytes, cudaMemcpyHostToDevice));
+        return GTB_OK;
+    }
+    gtb_weight_t* slot = nullptr;
+    switch (tensor_id) {
+        case GTB_T_EMBED: slot = &e->embed; break;
+        case GTB_T_LM_HEAD: slot = &e->lm_head; break;
+        case GTB_T_Q: slot = &e->L[layer].q; break;
+        case GTB_T_K: slot = &e->L[layer].k; break;
+        case GTB_T_V: slot = &e->L[layer].v; break;
+        case GTB_T_O: slot = &e->L[layer].o; break;
+        case GTB_T_GATE: slot = &e->L[layer].gate; break;
+        case GTB_T_UP: slot = &e->L[layer].up; break;
+        case GTB_T_DOWN: slot = &e->L[layer].down; break;
+        default: return fail(GTB_ERR_ARG, "bad tensor id %d", tensor_id);
+    }
+    if (*slot) { e->weight_bytes -= (*slot)->nbytes; gtb_weight_free(*slot); *slot = nullptr; drop_graphs(e); }
+    int r = gtb_weight_upload(slot, h_payload, dt, rows, cols);
+    if (r == GTB_OK) e->weight_bytes += (*slot)->nbytes;
+    return r;
+}
+
+int gtb_engine_load_gten(gtb_engine_t e, const char* path) {
+    GTB_CHECK_INIT();
+    GTB_ARG(e && path);
+    std::ifstream f(path, std::ios::binary);
+    if (!f.is_open()) return fail(GTB_ERR_ARG, "cannot open %s", path);
+    int64_t magic = 0;
+    f.read(reinterpret_cast<char*>(&magic), 8);
+    if (magic != 0x454c49464e455447LL) return fail(GTB_ERR_ARG, "Magic number in the binary does not match the expected one.");
+    std::vector<char> buf;
+    auto one = [&](int layer, int tid) -> int {
+        for (int rep = 0; rep < 2; rep++) {                       // layer header, then weight name (tinyllama.cpp:301-334)
+            int32_t n = 0;
+            f.read(reinterpret_cast<char*>(&n), 4);
+            if (!f || n < 0 || n > 4096) return fail(GTB_ERR_ARG, "corrupt .gten record header");
+            f.seekg(n, std::ios::cur);
+        }
+        int32_t nb = 0;
+        f.read(reinterpret_cast<char*>(&nb), 4);
+        if (!f || nb < 0) return fail(GTB_ERR_ARG, "corrupt .gten payload size");
+        buf.resize((size_t)nb);
+        f.read(buf.data(), nb);
+        if (!f) return fail(GTB_ERR_ARG, "truncated .gten file");
+        return gtb_engine_set_weight(e, layer, tid, buf.data(), (size_t)nb);
+    };
+    int r = one(0, GTB_T_EMBED);
+    static const int order[] = {GTB_T_Q, GTB_T_K, GTB_T_V, GTB_T_O, GTB_T_GATE, GTB_T_UP, GTB_T_DOWN, GTB_T_ATTN_NORM, GTB_T_FFN_NORM};
+    for (int li = 0; li < e->cfg.n_layers && !r; li++)
+        for (int t : order) { r = one(li, t); if (r) break; }
+    if (!r) r = one(0, GTB_T_FINAL_NORM);
+    if (!r) r = one(0, GTB_T_LM_HEAD);
+    return r;
+}
+
+static int check_loaded(gtb_engine_t e) {
+    if (!e->embed || !e->lm_head) return fail(GTB_ERR_STATE, "engine weights are not loaded");
+    for (auto& l : e->L)
+        if (!l.q || !l.k || !l.v || !l.o || !l.gate || !l.up || !l.down) return fail(GTB_ERR_STATE, "engine weights are not loaded");
+    return GTB_OK;
+}
+
+int gtb_engine_reset(gtb_engine_t e) {
+    GTB_CHECK_INIT();
+    GTB_ARG(e);
+    e->host_pos = 0;
+    return set_state(e, 0, 0);
+}
+
+int gtb_engine_logits(gtb_engine_t e, const int32_t* h_tokens, int n_tokens, int start_pos, float* h_logits) {
+    GTB_CHECK_INIT();
+    GTB_ARG(e && h_tokens && n_tokens > 0 && start_pos >= 0 && start_pos < n_tokens);
+    if (n_tokens > e->cfg.max_ctx)   // tinyllama.cpp:46-49
+        return fail(GTB_ERR_ARG, "Number of prompt tokens (%d) exceed provided maximum ctx size (%d)", n_tokens, e->cfg.max_ctx);
+    int r = check_loaded(e);
+    if (r) return r;
+    GTB_CUDA(cudaMemcpyAsync(e->tokens + start_pos, h_tokens + start_pos, (size_t)(n_tokens - start_pos) * 4, cudaMemcpyHostToDevice, ctx().stream));
+    r = set_state(e, start_pos, n_tokens);
+    if (r) return r;
+    r = run_rows(e, n_tokens - start_pos - 1, 1, -1);
+    if (r) return r;
+    e->host_pos = n_tokens;
+    if (h_logits) {
+        GTB_CUDA(cudaMemcpyAsync(h_logits, e->logits, (size_t)e->cfg.n_vocab * 4, cudaMemcpyDeviceToHost, ctx().stream));
+    }
+    GTB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return GTB_OK;
+}
+
+int gtb_engine_prefill(gtb_engine_t e, const int32_t* h_tokens, int n_tokens) {
+    GTB_CHECK_INIT();
+    GTB_ARG(e && h_tokens && n_tokens > 0 && n_tokens < e->cfg.max_ctx);
+    int r = check_loaded(e);
+    if (r) return r;
+    GTB_CUDA(cudaMemcpyAsync(e->tokens, h_tokens, (size_t)n_tokens * 4, cudaMemcpyHostToDevice, ctx().stream));
+    r = set_state(e, 0, n_tokens);
+    if (r) return r;
+    // the last prompt row also produces logits and the first generated token (greedy_sample's i == 0 step)
+    r = run_rows(e, n_tokens - 1, 1, -1);
+    if (r) return r;
+    e->host_pos = n_tokens;
+    return GTB_OK;
+}
+
+int gtb_engine_decode(gtb_engine_t e, int n_steps) {
+    GTB_CHECK_INIT();
+    GTB_ARG(e && n_steps >= 0);
+    if (e->host_pos + n_steps > e->cfg.max_ctx) return fail(GTB_ERR_ARG, "decode past max_ctx (%d + %d > %d)", e->host_pos, n_steps, e->cfg.max_ctx);
+    int r = run_rows(e, 0, n_steps, -1);
+    if (r) return r;
+    e->host_pos += n_steps;
+    return GTB_OK;
+}
+
+int gtb_engine_generate(gtb_engine_t e, int32_t* h_tokens, int n_prompt, int n_new, int eos_id, int* n_generated) {
+    GTB_CHECK_INIT();
+    GTB_ARG(e && h_tokens && n_prompt > 0 && n_new > 0);
+    if (n_prompt + n_new - 1 > e->cfg.max_ctx) return fail(GTB_ERR_ARG, "n_prompt + n_new - 1 exceeds max_ctx");
+    int r = check_loaded(e);
+    if (r) return r;
+    GTB_CUDA(cudaMemcpyAsync(e->tokens, h_tokens, (size_t)n_prompt * 4, cudaMemcpyHostToDevice, ctx().stream));
+    r = set_state(e, 0, n_prompt);
+    if (r) return r;
+    r = run_rows(e, n_prompt - 1, 1, eos_id);
+    if (r) return r;
+    int produced = 1;
+    if (eos_id < 0) {
+        r = run_rows(e, 0, n_new - 1, eos_id);
+        if (r) return r;
+        produced = n_new;
+    } else {
+        // with an EOS stop the host looks at the flag every 16 tokens (the reference checks every token, :426)
+        while (produced < n_new) {
+            DevState s;
+            GTB_CUDA(cudaMemcpyAsync(&s, e->st, sizeof s, cudaMemcpyDeviceToHost, ctx().stream));
+            GTB_CUDA(cudaStreamSynchronize(ctx().stream));
+            if (s.stop) break;
+            const int chunk = (n_new - produced < 16) ? n_new - produced : 16;
+            // run one token at a time inside the chunk so that nothing is generated after an EOS
+            r = run_rows(e, 0, 1, eos_id);
+            if (r) return r;
+            produced += 1;
+            (void)chunk;
+        }
+    }
+    GTB_CUDA(cudaMemcpyAsync(h_tokens + n_prompt, e->tokens + n_prompt, (size_t)produced * 4, cudaMemcpyDeviceToHost, ctx().stream));
+    GTB_CUDA(cudaStreamSynchronize(ctx().stream));
+    e->host_pos = n_prompt + produced - 1;
+    if (n_generated) *n_generated = produced;
+    return GTB_OK;
+}
+
+int gtb_engine_position(gtb_engine_t e, int* pos) {
+    GTB_CHECK_INIT();
+    GTB_ARG(e && pos);
+    DevState s;
+    GTB_CUDA(cudaMemcpyAsync(&s, e->st, sizeof s, cudaMemcpyDeviceToHost, ctx().stream));
+    GTB_CUDA(cudaStreamSynchronize(ctx().stream));
+    *pos = s.pos;
+    return GTB_OK;
+}
+
+int gtb_engine_read_tokens(gtb_engine_t e, int32_t* h_tokens, int first, int count) {
+    GTB_CHECK_INIT();
+    GTB_ARG(e && h_tokens && first >= 0 && count > 0 && first + count <= e->cfg.max_ctx + 2);
+    GTB_CUDA(cudaMemcpyAsync(h_tokens, e->tokens + first, (size_t)count * 4, cudaMemcpyDeviceToHost, ctx().stream));
+    GTB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return GTB_OK;
+}
+
+int gtb_engine_read_logits(gtb_engine_t e, float* h_logits) {
+    GTB_CHECK_INIT();
+    GTB_ARG(e && h_logits);
+    GTB_CUDA(cudaMemcpyAsync(h_logits, e->logits, (size_t)e->cfg.n_vocab * 4, cudaMemcpyDeviceToHost, ctx().stream));
+    GTB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return GTB_OK;
+}
+
+int gtb_engine_acv(gtb_engine_t e, int layer, int acv_id, float* h_out, int* width) {
+    GTB_CHECK_INIT();
+    GTB_ARG(e && h_out);
+    if (!e->capture) return fail(GTB_ERR_STATE, "activation capture is off: gtb_engine_set_option(e, \"capture_acv\", 1)");
+    int w = e->cfg.n_embd;
+    if (acv_id == GTB_A_K || acv_id == GTB_A_V) w = e->kv_dim;
+    if (acv_id == GTB_A_GATE || acv_id == GTB_A_UP) w = e->cfg.n_ffn;
+    GTB_ARG(acv_id == GTB_A_EMB || acv_id == GTB_A_FINAL_NORM || (acv_id >= GTB_A_ATTN_NORM && acv_id <= GTB_A_ATTN_RES && layer >= 0 && layer < e->cfg.n_layers));
+    const float* src = capp(e, layer, acv_id);
+    GTB_CUDA(cudaMemcpyAsync(h_out, src, (size_t)w * 4, cudaMemcpyDeviceToHost, ctx().stream));
+    GTB_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (width) *width = w;
+    return GTB_OK;
+}
+
+int gtb_engine_set_option(gtb_engine_t e, const char* name, int value) {
+    GTB_ARG(e && name);
+    if (!strcmp(name, "graph")) { e->use_graph = value != 0; return GTB_OK; }
+    if (!strcmp(name, "capture_acv")) { e->capture = value != 0; drop_graphs(e); return GTB_OK; }
+    if (!strcmp(name, "grid")) { GTB_ARG(value > 0); e->grid = value; drop_graphs(e); return GTB_OK; }
+    return fail(GTB_ERR_ARG, "unknown option %s", name);
+}
+
+int gtb_engine_weight_bytes(gtb_engine_t e, size_t* nbytes) {
+    GTB_ARG(e && nbytes);
+    *nbytes = e->weight_bytes;
+    return GTB_OK;
+}
+
+}  // extern "C"
