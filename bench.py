@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- batch-1 greedy decode throughput of the tinyllama.cpp forward hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload q4|q8|f16] [--impl b200|reference]
+
+One "step" = one decoded token = one pass of the hot path (TinyLlama::logits for one new row + argmax).
+Default workload = BASELINE.json configs[2], the configuration north_star's target is quoted on:
+TinyLlama-1.1B Q4, batch 1, greedy, context ending at the full 2048-token KV cache (prompt = 2048 - K - W
+synthetic ids, then W untimed + K timed decode steps).  Random-init weights in gten format (seeded, synthetic).
+
+value   : tokens/s with everything resident in HBM: K CUDA-graph replays back to back, device-side argmax,
+          timed with CUDA events on the library stream (max over ranks).
+e2e     : the same K steps through the reference-facing call with HOST buffers, exactly the protocol of
+          greedy_sample (tinyllama.cpp:402-434): gtb_engine_logits(tokens, n, n-1) -> 128 KB of fp32 logits back
+          to the host -> host argmax -> append; H2D/D2H inside the timed region.
+N > 1   : independent replicas (one process per GPU, disjoint sequences, no collective on the data path);
+          torch.distributed is used only for the start barrier and the max-over-ranks reduction.
+--impl reference : the reference's own CPU implementation (oracle/_ref, the unmodified sources built with
+          -O3 -fopenmp -mavx -mf16c; the plain-C port if that library is absent) on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+import gtb  # noqa: E402,F401
+from tinyllama_cpp_b200 import weights as W  # noqa: E402
+
+WORKLOADS = {
+    # name: (wdtype, BASELINE.json config index, description)
+    "q4": (W.Q4, 2, "TinyLlama-1.1B Q4 (-q4) batch-1 greedy decode ending at the full 2048-token KV cache (BASELINE.json configs[2])"),
+    "q8": (W.Q8, 1, "TinyLlama-1.1B Q8 (-q8) batch-1 greedy decode after a 128-token prompt (BASELINE.json configs[1])"),
+    "f16": (W.F16, 0, "TinyLlama-1.1B FP16 batch-1 greedy decode after a 128-token prompt (BASELINE.json configs[0])"),
+}
+DTYPE_STR = {W.Q4: "q4 weights x q8 activations: int32 block dots, fp32 ordered accumulation",
+             W.Q8: "q8 weights x q8 activations: int32 block dots, fp32 ordered accumulation",
+             W.F16: "fp16 weights x fp16 activations: fp32 ordered accumulation"}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def run_reference(args, wdt, desc):
+    """The reference's CPU implementation on the host cores (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import oracle
+    lib = oracle.best()
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cfg = W.TINYLLAMA
+    n_prompt = 32
+    max_ctx = n_prompt + args.warmup + args.steps + 2
+    m = lib.model(cfg, max_ctx, wdt).load(W.synth_weights(cfg, wdt, seed=1))
+    toks = list(W.synth_prompt(7, n_prompt, cfg.n_vocab))
+    lg = m.logits(np.array(toks, np.int32), 0)
+    toks.append(int(np.argmax(lg)))
+    for _ in range(args.warmup):
+        lg = m.logits(np.array(toks, np.int32), len(toks) - 1)
+        toks.append(int(np.argmax(lg)))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        lg = m.logits(np.array(toks, np.int32), len(toks) - 1)
+        toks.append(int(np.argmax(lg)))
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    sample = f"{args.steps} decode steps after a {n_prompt}-token prompt (t = {n_prompt + args.warmup + 1}..{len(toks) - 1}); short context: the reference's attention is single-threaded"
+    print(json.dumps({
+        "impl": "reference", "metric": "decode_tokens_per_s", "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_STR[wdt], "data": "synthetic",
+        "config": {"workload": desc, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": lib.kind, "sample": sample},
+        "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def cpu_baseline(wdt, seconds_budget=20.0):
+    """Reference CPU path on a bounded sample (rank 0, N=1 only)."""
+    import oracle
+    lib = oracle.best()
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cfg = W.TINYLLAMA
+    n_prompt, n_steps = 16, 48
+    m = lib.model(cfg, n_prompt + n_steps + 4, wdt).load(W.synth_weights(cfg, wdt, seed=1))
+    toks = list(W.synth_prompt(7, n_prompt, cfg.n_vocab))
+    lg = m.logits(np.array(toks, np.int32), 0)
+    toks.append(int(np.argmax(lg)))
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(n_steps):
+        lg = m.logits(np.array(toks, np.int32), len(toks) - 1)
+        toks.append(int(np.argmax(lg)))
+        done += 1
+        if time.perf_counter() - t0 > seconds_budget:
+            break
+    dt = time.perf_counter() - t0
+    m.close()
+    return {"value": done / dt, "unit": "tokens/s", "cores": cores, "kind": lib.kind,
+            "sample": f"{done} decode steps after a {n_prompt}-token prompt (t = {n_prompt + 1}..{n_prompt + done}), same synthetic weights"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=512)
+    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--workload", choices=list(WORKLOADS), default="q4")
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    wdt, cfg_idx, desc = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wdt, desc)
+
+    import torch
+    from tinyllama_cpp_b200 import capi
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    capi.init(local)
+    torch.cuda.set_device(local)
+    cfg = W.TINYLLAMA
+    K, Wm = args.steps, args.warmup
+    if args.workload == "q4":
+        max_ctx = 2048
+        n_prompt = max_ctx + 1 - K - Wm          # the last timed row is position 2047 (t = 2048)
+        if n_prompt < 16:
+            n_prompt, max_ctx = 16, 16 + K + Wm - 1
+    else:
+        n_prompt = 128
+        max_ctx = n_prompt + K + Wm - 1
+    t_setup = time.time()
+    eng = capi.Engine(cfg, max_ctx + 1, wdt).load(W.synth_weights(cfg, wdt, seed=1))
+    prompt = W.synth_prompt(7 + rank, n_prompt, cfg.n_vocab)       # disjoint sequences per replica
+    stream = torch.cuda.ExternalStream(capi.stream_handle(), device=torch.device("cuda", local))
+    hbm_peak, peak_src = measured_peaks()
+
+    def barrier():
+        capi.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- resident path: prefill (untimed, exact row-by-row path), W warm-up steps, K timed steps
+    eng.prefill(prompt)
+    eng.decode(Wm - 1)            # prefill already produced the first new token
+    barrier()
+    l0 = capi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        ev0.record(stream)
+        eng.decode(K)
+        ev1.record(stream)
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = capi.launch_count() - l0
+    pos_end = eng.position()
+    assert pos_end == n_prompt + Wm - 1 + K, (pos_end, n_prompt, Wm, K)
+    toks_resident = eng.read_tokens(0, pos_end + 1)
+
+    # ---- e2e path: host buffers, the reference's per-token protocol
+    e2e = None
+    if not args.no_e2e:
+        eng.prefill(prompt)
+        eng.decode(Wm - 1)
+        toks = eng.read_tokens(0, n_prompt + Wm).astype(np.int32)
+        buf = np.zeros(max_ctx + 2, np.int32)
+        n = toks.size
+        buf[:n] = toks
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            lg = eng.logits(buf[:n], n - 1)                 # 4 B H2D + n_vocab*4 B D2H inside
+            buf[n] = int(np.argmax(lg))                      # first maximum wins, like tinyllama.cpp:416-424
+            n += 1
+        capi.sync()
+        e2e_s = time.perf_counter() - t0
+        assert np.array_equal(buf[:n], toks_resident[:n]), "e2e and resident greedy sequences differ"
+        e2e_local = e2e_s
+    else:
+        e2e_local = float("nan")
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_local * 1e3], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+        lt = torch.tensor([launches], device=f"cuda:{local}", dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt[0])
+    else:
+        e2e_ms = e2e_local * 1e3
+    value = world * K / (ms * 1e-3)
+    t_mean = n_prompt + Wm + (K - 1) / 2.0                 # mean sequence length over the timed steps
+    bytes_per_tok = cfg.decode_bytes(wdt, int(round(t_mean)))
+    achieved = bytes_per_tok * (K / (ms * 1e-3)) / 1e9     # per GPU
+    clocks = clk.summary()
+
+    if rank == 0:
+        out = {
+            "metric": "decode_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": DTYPE_STR[wdt], "data": "synthetic",
+            "config": {"workload": desc, "baseline_config_index": cfg_idx, "n_prompt": n_prompt, "max_ctx": max_ctx,
+                       "seq_len_timed": [n_prompt + Wm, n_prompt + Wm + K - 1], "batch": 1, "replicas": world,
+                       "weights": "random-init, seeded, gten format", "l2": "inputs larger than L2: every step streams "
+                       f"{cfg.weight_bytes_per_token(wdt) / 1e6:.0f} MB of weights (L2 = 126 MB)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "one decode step (all kernels of one token)",
+                         "algorithmic_bytes_per_step": bytes_per_tok},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        if not args.no_e2e:
+            out["e2e"] = {"value": world * K / (e2e_ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": 4,
+                          "d2h_bytes_per_step": cfg.n_vocab * 4}
+        if world == 1 and not args.no_cpu_baseline:
+            eng.close()
+            out["cpu_baseline"] = cpu_baseline(wdt)
+        out["setup_s"] = round(time.time() - t_setup, 1)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

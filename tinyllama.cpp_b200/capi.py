@@ -185,6 +185,7 @@ def write_rows(x: np.ndarray, dtype: int) -> np.ndarray:
     x = np.ascontiguousarray(x, np.float32)
     rows, n = x.shape
     din, dout = DeviceBuffer.from_host(x), DeviceBuffer(rows * W.row_nbytes(dtype, n))
+    check(lib().gtb_memset(dout.ptr, 0, dout.nbytes))     # bytes past a partial last block are never written
     check(lib().gtb_write_rows_from_float(din.ptr, dout.ptr, dtype, rows, n))
     return dout.to_host(np.uint8, (rows, -1))
 
