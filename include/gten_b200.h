@@ -117,7 +117,11 @@ int gtb_engine_read_tokens(gtb_engine_t e, int32_t* h_tokens, int first, int cou
 int gtb_engine_read_logits(gtb_engine_t e, float* h_logits);
 /* decoded fp32 row of a module activation for the LAST processed row (debug/parity) */
 int gtb_engine_acv(gtb_engine_t e, int layer, int acv_id, float* h_out, int* width);
-int gtb_engine_set_option(gtb_engine_t e, const char* name, int value);            /* "graph", "capture_acv" */
+/* options: "mega" (1: persistent cooperative kernel, default; 0: one kernel per phase), "graph" (CUDA-graph replay of
+ * the per-phase path), "capture_acv", "grid", "pf_ahead" (L2 prefetch distance in GEMV phases), "prof" */
+int gtb_engine_set_option(gtb_engine_t e, const char* name, int value);
+/* "prof": globaltimer stamps (ns) taken by CTA 0 at every phase boundary of the last processed row */
+int gtb_engine_read_prof(gtb_engine_t e, long long* h_out, int count);
 int gtb_engine_weight_bytes(gtb_engine_t e, size_t* nbytes);
 
 #ifdef __cplusplus

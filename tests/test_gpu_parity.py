@@ -205,9 +205,17 @@ def test_engine_mini_model(capi, checker, wdt):
     ct, _, clog = cm.generate(prompt, n_new, want_logits=True)
     gt = e.generate(prompt, n_new)
     assert np.array_equal(gt, ct)
-    # graph replay and eager launches agree
+    # the default path is the persistent megakernel; the one-kernel-per-phase path (graph replay and eager) agrees
+    e.set_option("mega", 0)
+    assert np.array_equal(e.generate(prompt, n_new), ct)
     e.set_option("graph", 0)
     assert np.array_equal(e.generate(prompt, n_new), ct)
+    e.set_option("mega", 1)
+    # an EOS stops the device-side loop: generation ends with the first occurrence of that id
+    eos = int(ct[33 + 5])
+    first = 33 + int(np.argmax(ct[33:] == eos))
+    got = e.generate(prompt, n_new, eos_id=eos)
+    assert np.array_equal(got, ct[:first + 1])
     # logits() with the reference's calling protocol (all tokens so far + start_pos)
     assert np.array_equal(bits(e.logits(ct[:33], 0)), bits(clog[0]))
     for i in (1, 2, 7, n_new - 1):

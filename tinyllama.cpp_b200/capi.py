@@ -27,7 +27,7 @@ SYMBOLS = [
     "gtb_qkv_attn", "gtb_engine_create", "gtb_engine_destroy", "gtb_engine_set_weight", "gtb_engine_load_gten",
     "gtb_engine_logits", "gtb_engine_generate", "gtb_engine_reset", "gtb_engine_prefill", "gtb_engine_decode",
     "gtb_engine_position", "gtb_engine_read_tokens", "gtb_engine_read_logits", "gtb_engine_acv",
-    "gtb_engine_set_option", "gtb_engine_weight_bytes",
+    "gtb_engine_set_option", "gtb_engine_weight_bytes", "gtb_engine_read_prof",
 ]
 
 
@@ -74,6 +74,7 @@ def lib():
             "gtb_engine_position": [vp, C.POINTER(i)], "gtb_engine_read_tokens": [vp, vp, i, i],
             "gtb_engine_read_logits": [vp, vp], "gtb_engine_acv": [vp, i, i, vp, C.POINTER(i)],
             "gtb_engine_set_option": [vp, C.c_char_p, i], "gtb_engine_weight_bytes": [vp, C.POINTER(sz)],
+            "gtb_engine_read_prof": [vp, vp, i],
         }
         for name, args in sigs.items():
             fn = getattr(L, name)
@@ -337,6 +338,11 @@ class Engine:
         w = C.c_int()
         check(lib().gtb_engine_acv(self.h, layer, aid, _hp(out), C.byref(w)))
         return out[: w.value].copy()
+
+    def read_prof(self, count: int) -> np.ndarray:
+        out = np.zeros(count, np.int64)
+        check(lib().gtb_engine_read_prof(self.h, _hp(out), count))
+        return out
 
     def weight_bytes(self) -> int:
         n = C.c_size_t()

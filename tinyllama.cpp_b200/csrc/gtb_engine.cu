@@ -11,17 +11,11 @@
 
 #include "gtb_internal.h"
 #include "gtb_kernels.cuh"
+#include "gtb_mega.cuh"
 
 namespace gtb {
 
 enum { PRO_ENCODE = 0, PRO_NORM = 1, PRO_SILU_MUL = 2 };
-
-struct DevState {
-    int pos;        // row to process next
-    int nctx_min;   // n_ctx of the current logits() call (P row length / P.V lane split), SURVEY App. A
-    int stop;       // set when eos was generated
-    int n_gen;
-};
 
 struct GemvMat {
     const void* data;
@@ -279,6 +273,17 @@ struct gtb_engine {
     int host_pos = 0;
     size_t weight_bytes = 0;
     int launches_body = 0, launches_head = 0;
+    // persistent megakernel (gtb_mega.cuh)
+    bool use_mega = true;
+    int pf_ahead = 4;
+    bool prof = false;
+    MegaLayer* d_layers = nullptr;
+    bool layers_valid = false;
+    unsigned long long *x_qkv = nullptr, *x_sc = nullptr, *x_attn = nullptr, *x_o = nullptr, *x_gu = nullptr, *x_act = nullptr,
+                       *x_down = nullptr, *x_arg = nullptr, *dbg = nullptr;
+    unsigned int* epoch = nullptr;
+    long long* d_prof = nullptr;
+    int sc_stride = 0;
 };
 
 namespace {
@@ -419,9 +424,71 @@ int build_graph(gtb_engine* e, bool with_head, int eos_id, cudaGraphExec_t* out,
     return GTB_OK;
 }
 
+constexpr int PROF_SLOTS = 4096;
+
+bool mega_ok(const gtb_engine* e) {
+    const int at = e->adtype;
+    return e->use_mega && !e->capture && e->grid >= e->cfg.n_heads * 4 && e->grid <= 1024 &&
+           attn_scratch_bytes(at, e->cfg.max_ctx) <= (size_t)PS_BYTES;
+}
+
+template <int WT>
+int launch_mega(gtb_engine* e, MegaParams& p) {
+    constexpr int AT = (WT == DT_F16) ? DT_F16 : DT_Q8;
+    const size_t smem = mega_smem_bytes(AT, p.E, p.F);
+    static bool attr_done = false;
+    if (!attr_done) {
+        GTB_CUDA(cudaFuncSetAttribute(k_mega<WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        GTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_mega<WT>, MT, smem));
+        if (nb < 1) return fail(GTB_ERR_CUDA, "megakernel does not fit on an SM (%zu B shared memory)", smem);
+        attr_done = true;
+    }
+    if (e->grid > ctx().sm_count) return fail(GTB_ERR_ARG, "cooperative grid (%d) exceeds the SM count (%d)", e->grid, ctx().sm_count);
+    void* args[] = {&p};
+    GTB_CUDA(cudaLaunchCooperativeKernel((const void*)k_mega<WT>, dim3(e->grid), dim3(MT), args, smem, ctx().stream));
+    GTB_LAUNCHED();
+    return GTB_OK;
+}
+
+int run_rows_mega(gtb_engine* e, int n_body, int n_head, int eos_id) {
+    const gtb_model_config& c = e->cfg;
+    if (!e->layers_valid) {
+        std::vector<MegaLayer> h(c.n_layers);
+        for (int i = 0; i < c.n_layers; i++) {
+            LayerW& l = e->L[i];
+            gtb_weight_t ws[7] = {l.q, l.k, l.v, l.o, l.gate, l.up, l.down};
+            for (int k = 0; k < 7; k++) { h[i].w[k] = ws[k]->data; h[i].s[k] = ws[k]->scales; }
+            h[i].attn_norm = l.attn_norm; h[i].ffn_norm = l.ffn_norm;
+            h[i].kq = l.kq; h[i].ks = l.ks; h[i].vq = l.vq; h[i].vs = l.vs;
+        }
+        GTB_CUDA(cudaMemcpyAsync(e->d_layers, h.data(), h.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice, ctx().stream));
+        GTB_CUDA(cudaStreamSynchronize(ctx().stream));
+        e->layers_valid = true;
+    }
+    MegaParams p{};
+    p.E = c.n_embd; p.F = c.n_ffn; p.KV = e->kv_dim; p.n_heads = c.n_heads; p.gsz = e->gsz; p.n_layers = c.n_layers;
+    p.n_vocab = c.n_vocab; p.max_ctx = c.max_ctx; p.sc_stride = e->sc_stride;
+    p.layers = e->d_layers;
+    p.emb_w = e->embed->data; p.emb_s = e->embed->scales; p.head_w = e->lm_head->data; p.head_s = e->lm_head->scales;
+    p.final_norm = e->final_norm; p.rope_cos = e->rope_cos; p.rope_sin = e->rope_sin;
+    p.x_qkv = e->x_qkv; p.x_sc = e->x_sc; p.x_attn = e->x_attn; p.x_o = e->x_o; p.x_gu = e->x_gu; p.x_act = e->x_act;
+    p.x_down = e->x_down; p.x_arg = e->x_arg;
+    p.logits = e->logits; p.tokens = e->tokens; p.st = e->st; p.epoch = e->epoch;
+    p.n_body = n_body; p.n_head = n_head; p.eos_id = eos_id; p.pf_ahead = e->pf_ahead;
+    p.dbg = e->dbg; p.prof = e->prof ? e->d_prof : nullptr;
+    switch (c.wdtype) {
+        case GTB_F16: return launch_mega<DT_F16>(e, p);
+        case GTB_Q8: return launch_mega<DT_Q8>(e, p);
+        default: return launch_mega<DT_Q4>(e, p);
+    }
+}
+
 // rows to run: `n_body` rows without lm_head, then `n_head` rows with lm_head + argmax
 int run_rows(gtb_engine* e, int n_body, int n_head, int eos_id) {
     cudaStream_t st = ctx().stream;
+    if (n_body + n_head <= 0) return GTB_OK;
+    if (mega_ok(e)) return run_rows_mega(e, n_body, n_head, eos_id);
     if (e->use_graph && !e->capture) {
         if (n_body > 0 && !e->g_body) { int r = build_graph(e, false, -1, &e->g_body, &e->launches_body); if (r) return r; }
         if (n_head > 0 && (!e->g_head || e->g_eos != eos_id)) {
@@ -501,6 +568,13 @@ int gtb_engine_create(gtb_engine_t* out, const gtb_model_config* cfg) {
     e->capw = (F > E) ? F : E;
     r |= dalloc((void**)&e->cap, ((size_t)cfg->n_layers * 12 + 2) * e->capw * 4);
     r |= dalloc((void**)&e->rope_cos, (size_t)MC * 32 * 4); r |= dalloc((void**)&e->rope_sin, (size_t)MC * 32 * 4);
+    // exchange buffers of the persistent kernel: 64-bit {tag | payload} words, zero = never written (tags start at 1)
+    e->sc_stride = (MC + 2) & ~1;
+    r |= dalloc((void**)&e->x_qkv, (size_t)(E + 2 * KV) * 8); r |= dalloc((void**)&e->x_sc, (size_t)cfg->n_heads * e->sc_stride * 8);
+    r |= dalloc((void**)&e->x_attn, (size_t)E * 8); r |= dalloc((void**)&e->x_o, (size_t)E * 8); r |= dalloc((void**)&e->x_gu, (size_t)2 * F * 8);
+    r |= dalloc((void**)&e->x_act, (size_t)(F / 32) * 16 * 8); r |= dalloc((void**)&e->x_down, (size_t)E * 8);
+    r |= dalloc((void**)&e->x_arg, (size_t)2 * 1024 * 8); r |= dalloc((void**)&e->dbg, 64); r |= dalloc((void**)&e->epoch, 16);
+    r |= dalloc((void**)&e->d_prof, (size_t)PROF_SLOTS * 8); r |= dalloc((void**)&e->d_layers, (size_t)cfg->n_layers * sizeof(MegaLayer));
     if (r) { return r; }
     {   // RoPE table with the reference's own expressions and libm (gten/ops.h:728-746; SURVEY §7 hard part 4)
         std::vector<float> cs((size_t)MC * 32), sn((size_t)MC * 32);
@@ -533,7 +607,8 @@ int gtb_engine_destroy(gtb_engine_t e) {
     }
     gtb_weight_free(e->embed); gtb_weight_free(e->lm_head);
     void* bufs[] = {e->final_norm, e->xres, e->hres, e->xfinal, e->rqkv, e->rattn, e->ro, e->rg, e->ru, e->rd, e->logits,
-                    e->tokens, e->st, e->cap, e->rope_cos, e->rope_sin};
+                    e->tokens, e->st, e->cap, e->rope_cos, e->rope_sin, e->x_qkv, e->x_sc, e->x_attn, e->x_o, e->x_gu, e->x_act,
+                    e->x_down, e->x_arg, e->dbg, e->epoch, e->d_prof, e->d_layers};
     for (void* b : bufs) cudaFree(b);
     delete e;
     return GTB_OK;
@@ -568,6 +643,7 @@ int gtb_engine_set_weight(gtb_engine_t e, int layer, int tensor_id, const void* 
         default: return fail(GTB_ERR_ARG, "bad tensor id %d", tensor_id);
     }
     if (*slot) { e->weight_bytes -= (*slot)->nbytes; gtb_weight_free(*slot); *slot = nullptr; drop_graphs(e); }
+    e->layers_valid = false;
     int r = gtb_weight_upload(slot, h_payload, dt, rows, cols);
     if (r == GTB_OK) e->weight_bytes += (*slot)->nbytes;
     return r;
@@ -674,9 +750,23 @@ int gtb_engine_generate(gtb_engine_t e, int32_t* h_tokens, int n_prompt, int n_n
     GTB_CUDA(cudaMemcpyAsync(e->tokens, h_tokens, (size_t)n_prompt * 4, cudaMemcpyHostToDevice, ctx().stream));
     r = set_state(e, 0, n_prompt);
     if (r) return r;
+    int produced = 1;
+    if (mega_ok(e)) {
+        // prefill rows, the first token and every further greedy step in ONE launch; an EOS ends the loop on the device
+        r = run_rows(e, n_prompt - 1, n_new, eos_id);
+        if (r) return r;
+        DevState s;
+        GTB_CUDA(cudaMemcpyAsync(&s, e->st, sizeof s, cudaMemcpyDeviceToHost, ctx().stream));
+        GTB_CUDA(cudaStreamSynchronize(ctx().stream));
+        produced = s.n_gen;
+        GTB_CUDA(cudaMemcpyAsync(h_tokens + n_prompt, e->tokens + n_prompt, (size_t)produced * 4, cudaMemcpyDeviceToHost, ctx().stream));
+        GTB_CUDA(cudaStreamSynchronize(ctx().stream));
+        e->host_pos = n_prompt + produced - 1;
+        if (n_generated) *n_generated = produced;
+        return GTB_OK;
+    }
     r = run_rows(e, n_prompt - 1, 1, eos_id);
     if (r) return r;
-    int produced = 1;
     if (eos_id < 0) {
         r = run_rows(e, 0, n_new - 1, eos_id);
         if (r) return r;
@@ -749,7 +839,18 @@ int gtb_engine_set_option(gtb_engine_t e, const char* name, int value) {
     if (!strcmp(name, "graph")) { e->use_graph = value != 0; return GTB_OK; }
     if (!strcmp(name, "capture_acv")) { e->capture = value != 0; drop_graphs(e); return GTB_OK; }
     if (!strcmp(name, "grid")) { GTB_ARG(value > 0); e->grid = value; drop_graphs(e); return GTB_OK; }
+    if (!strcmp(name, "mega")) { e->use_mega = value != 0; return GTB_OK; }
+    if (!strcmp(name, "pf_ahead")) { GTB_ARG(value >= 0 && value <= 64); e->pf_ahead = value; return GTB_OK; }
+    if (!strcmp(name, "prof")) { e->prof = value != 0; return GTB_OK; }
     return fail(GTB_ERR_ARG, "unknown option %s", name);
+}
+
+int gtb_engine_read_prof(gtb_engine_t e, long long* h_out, int count) {
+    GTB_CHECK_INIT();
+    GTB_ARG(e && h_out && count > 0 && count <= PROF_SLOTS);
+    GTB_CUDA(cudaMemcpyAsync(h_out, e->d_prof, (size_t)count * 8, cudaMemcpyDeviceToHost, ctx().stream));
+    GTB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return GTB_OK;
 }
 
 int gtb_engine_weight_bytes(gtb_engine_t e, size_t* nbytes) {

@@ -14,6 +14,13 @@
 
 namespace gtb {
 
+struct DevState {
+    int pos;        // row to process next
+    int nctx_min;   // n_ctx of the current logits() call (P row length / P.V lane split), SURVEY App. A
+    int stop;       // set when eos was generated
+    int n_gen;
+};
+
 constexpr int NT = 256;          // threads per CTA for every phase kernel
 constexpr int NWARP = NT / 32;
 constexpr int RPW = 4;           // weight rows per warp pass (Q4/Q8)
@@ -100,8 +107,8 @@ __device__ __forceinline__ float roundtrip(float x) {     // E(): what the next 
 // PRO_ENCODE: stage E(src0).
 template <int AT>
 __device__ void pro_encode(const ActView& av, const float* __restrict__ src, int n, float* cap) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int b = wid; b < n / 32; b += NWARP) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int b = wid; b < n / 32; b += nwarp) {
         const float d = stage_block<AT>(av, b, lane, src[b * 32 + lane]);
         if (cap) cap[b * 32 + lane] = d;
     }
@@ -113,8 +120,8 @@ template <int AT>
 __device__ void pro_norm(const ActView& av, const float* __restrict__ res, const float* __restrict__ delta,
                          const uint16_t* __restrict__ normw, int n, float* xbuf, ExactSumSmem& es,
                          float* res_out, float* cap_delta, float* cap_res, float* cap_norm) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int b = wid; b < n / 32; b += NWARP) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int b = wid; b < n / 32; b += nwarp) {
         const int e = b * 32 + lane;
         float x = res[e];
         if (delta) {
@@ -130,7 +137,7 @@ __device__ void pro_norm(const ActView& av, const float* __restrict__ res, const
     const float sq_sum = exact_sum_block([&](int i) { const float v = xbuf[i]; return __fmul_rn(v, v); }, n, es);
     const float rms = sqrtf(__fdiv_rn(sq_sum, (float)n));
     const float denom = __fadd_rn(rms, 1e-6f);
-    for (int b = wid; b < n / 32; b += NWARP) {
+    for (int b = wid; b < n / 32; b += nwarp) {
         const int e = b * 32 + lane;
         const float y = __fmul_rn(__fdiv_rn(xbuf[e], denom), h2f(normw[e]));
         const float d = stage_block<AT>(av, b, lane, y);
