@@ -240,55 +240,71 @@ int gtb_host_free(void* h_ptr) {
 }
 
 // ------------------------------------------------------------------ weights
-int gtb_weight_from_device(gtb_weight_t* out, const void* d_payload, int dtype, int rows, int cols) {
+static int weight_from_device_impl(gtb_weight_t* out, const void* d_payload, int dtype, int rows, int cols, void* d_data, uint16_t* d_scales) {
     GTB_CHECK_INIT();
     GTB_ARG(out && d_payload && rows > 0 && cols > 0);
     GTB_ARG(dtype == GTB_F16 || dtype == GTB_Q8 || dtype == GTB_Q4);
     GTB_ARG(dtype == GTB_F16 ? (cols % 64 == 0) : (cols % 32 == 0));
     auto* w = new gtb_weight();
     w->dtype = dtype; w->rows = rows; w->cols = cols;
+    w->owns = (d_data == nullptr);
     cudaStream_t st = ctx().stream;
     const int T = 256;
     if (dtype == GTB_F16) {
         const size_t nvec = (size_t)rows * cols / 8;
         w->nbytes = nvec * 16;
-        GTB_CUDA(cudaMalloc(&w->data, w->nbytes));
+        if (w->owns) GTB_CUDA(cudaMalloc(&w->data, w->nbytes)); else w->data = d_data;
         k_repack_f16<<<(unsigned)((nvec + T - 1) / T), T, 0, st>>>((const uint16_t*)d_payload, (uint4*)w->data, cols, nvec);
     } else {
         const size_t nblk = (size_t)rows * cols / 32;
         const size_t dbytes = nblk * (dtype == GTB_Q4 ? 16 : 32);
         w->nbytes = dbytes + nblk * 2;
-        GTB_CUDA(cudaMalloc(&w->data, dbytes));
-        GTB_CUDA(cudaMalloc((void**)&w->scales, nblk * 2));
+        if (w->owns) {
+            GTB_CUDA(cudaMalloc(&w->data, dbytes));
+            GTB_CUDA(cudaMalloc((void**)&w->scales, nblk * 2));
+        } else {
+            w->data = d_data; w->scales = d_scales;
+        }
         if (dtype == GTB_Q4) k_repack_q4<<<(unsigned)((nblk + T - 1) / T), T, 0, st>>>((const uint8_t*)d_payload, (uint4*)w->data, w->scales, nblk);
         else k_repack_q8<<<(unsigned)((nblk + T - 1) / T), T, 0, st>>>((const uint8_t*)d_payload, (uint4*)w->data, w->scales, nblk);
     }
     GTB_LAUNCHED();
-    ctx().mem += (int64_t)w->nbytes;
+    if (w->owns) ctx().mem += (int64_t)w->nbytes;
     *out = w;
     return GTB_OK;
 }
 
-int gtb_weight_upload(gtb_weight_t* out, const void* h_payload, int dtype, int rows, int cols) {
+int gtb_weight_from_device(gtb_weight_t* out, const void* d_payload, int dtype, int rows, int cols) {
+    return weight_from_device_impl(out, d_payload, dtype, rows, cols, nullptr, nullptr);
+}
+
+static int weight_upload_impl(gtb_weight_t* out, const void* h_payload, int dtype, int rows, int cols, void* d_data, uint16_t* d_scales) {
     GTB_CHECK_INIT();
     GTB_ARG(out && h_payload && rows > 0 && cols > 0);
     const size_t nb = (size_t)rows * row_nbytes(dtype, cols);
     void* tmp = nullptr;
     GTB_CUDA(cudaMalloc(&tmp, nb));
     cudaError_t e = cudaMemcpyAsync(tmp, h_payload, nb, cudaMemcpyHostToDevice, ctx().stream);
-    int r = (e == cudaSuccess) ? gtb_weight_from_device(out, tmp, dtype, rows, cols) : fail(GTB_ERR_CUDA, "weight H2D failed: %s", cudaGetErrorString(e));
+    int r = (e == cudaSuccess) ? weight_from_device_impl(out, tmp, dtype, rows, cols, d_data, d_scales)
+                               : fail(GTB_ERR_CUDA, "weight H2D failed: %s", cudaGetErrorString(e));
     cudaStreamSynchronize(ctx().stream);
     cudaFree(tmp);
     return r;
+}
+
+int gtb_weight_upload(gtb_weight_t* out, const void* h_payload, int dtype, int rows, int cols) {
+    return weight_upload_impl(out, h_payload, dtype, rows, cols, nullptr, nullptr);
 }
 
 int gtb_weight_free(gtb_weight_t w) {
     if (!w) return GTB_OK;
     GTB_CHECK_INIT();
     cudaStreamSynchronize(ctx().stream);
-    if (w->data) cudaFree(w->data);
-    if (w->scales) cudaFree(w->scales);
-    ctx().mem -= (int64_t)w->nbytes;
+    if (w->owns) {
+        if (w->data) cudaFree(w->data);
+        if (w->scales) cudaFree(w->scales);
+        ctx().mem -= (int64_t)w->nbytes;
+    }
     delete w;
     return GTB_OK;
 }
@@ -337,3 +353,10 @@ int gtb_read_rows_to_float(const void* d_in, int in_dtype, float* d_out, int row
 }
 
 }  // extern "C"
+
+namespace gtb {
+int weight_upload_view(gtb_weight_t* out, const void* h_payload, int dtype, int rows, int cols, void* d_data, uint16_t* d_scales) {
+    if (!d_data) return fail(GTB_ERR_ARG, "weight_upload_view: no destination");
+    return weight_upload_impl(out, h_payload, dtype, rows, cols, d_data, d_scales);
+}
+}  // namespace gtb

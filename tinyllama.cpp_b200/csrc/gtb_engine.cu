@@ -245,6 +245,9 @@ struct LayerW {
     uint16_t* ffn_norm = nullptr;
     uint8_t *kq = nullptr, *vq = nullptr;
     uint16_t *ks = nullptr, *vs = nullptr;
+    // q|k|v and gate|up live in one buffer each so that a GEMV phase of the persistent kernel streams ONE matrix
+    uint8_t *qkv_data = nullptr, *gu_data = nullptr;
+    uint16_t *qkv_sc = nullptr, *gu_sc = nullptr;
 };
 
 }  // namespace gtb
@@ -282,6 +285,7 @@ struct gtb_engine {
     unsigned long long *x_qkv = nullptr, *x_sc = nullptr, *x_attn = nullptr, *x_o = nullptr, *x_gu = nullptr, *x_act = nullptr,
                        *x_down = nullptr, *x_arg = nullptr, *dbg = nullptr;
     unsigned int* epoch = nullptr;
+    unsigned int* cnt = nullptr;
     long long* d_prof = nullptr;
     int sc_stride = 0;
 };
@@ -427,15 +431,17 @@ int build_graph(gtb_engine* e, bool with_head, int eos_id, cudaGraphExec_t* out,
 constexpr int PROF_SLOTS = 4096;
 
 bool mega_ok(const gtb_engine* e) {
-    const int at = e->adtype;
-    return e->use_mega && !e->capture && e->grid >= e->cfg.n_heads * 4 && e->grid <= 1024 &&
-           attn_scratch_bytes(at, e->cfg.max_ctx) <= (size_t)PS_BYTES;
+    const gtb_model_config& c = e->cfg;
+    // the persistent kernel is specialised for the TinyLlama dimensions (tinyllama.cpp:12-20); anything else takes
+    // the one-kernel-per-phase path
+    return e->use_mega && !e->capture && c.n_embd == ME && c.n_ffn == MF && c.n_heads == MH && c.n_groups * MGSZ == MH &&
+           e->grid >= MH * 4 && e->grid <= 1024 && attn_scratch_bytes(e->adtype, c.max_ctx) <= (size_t)PS_BYTES;
 }
 
 template <int WT>
 int launch_mega(gtb_engine* e, MegaParams& p) {
     constexpr int AT = (WT == DT_F16) ? DT_F16 : DT_Q8;
-    const size_t smem = mega_smem_bytes(AT, p.E, p.F);
+    const size_t smem = mega_smem_bytes(AT);
     static bool attr_done = false;
     if (!attr_done) {
         GTB_CUDA(cudaFuncSetAttribute(k_mega<WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -457,8 +463,10 @@ int run_rows_mega(gtb_engine* e, int n_body, int n_head, int eos_id) {
         std::vector<MegaLayer> h(c.n_layers);
         for (int i = 0; i < c.n_layers; i++) {
             LayerW& l = e->L[i];
-            gtb_weight_t ws[7] = {l.q, l.k, l.v, l.o, l.gate, l.up, l.down};
-            for (int k = 0; k < 7; k++) { h[i].w[k] = ws[k]->data; h[i].s[k] = ws[k]->scales; }
+            h[i].w[0] = (const uint4*)l.qkv_data; h[i].s[0] = l.qkv_sc;
+            h[i].w[1] = (const uint4*)l.o->data; h[i].s[1] = l.o->scales;
+            h[i].w[2] = (const uint4*)l.gu_data; h[i].s[2] = l.gu_sc;
+            h[i].w[3] = (const uint4*)l.down->data; h[i].s[3] = l.down->scales;
             h[i].attn_norm = l.attn_norm; h[i].ffn_norm = l.ffn_norm;
             h[i].kq = l.kq; h[i].ks = l.ks; h[i].vq = l.vq; h[i].vs = l.vs;
         }
@@ -467,13 +475,12 @@ int run_rows_mega(gtb_engine* e, int n_body, int n_head, int eos_id) {
         e->layers_valid = true;
     }
     MegaParams p{};
-    p.E = c.n_embd; p.F = c.n_ffn; p.KV = e->kv_dim; p.n_heads = c.n_heads; p.gsz = e->gsz; p.n_layers = c.n_layers;
-    p.n_vocab = c.n_vocab; p.max_ctx = c.max_ctx; p.sc_stride = e->sc_stride;
+    p.n_layers = c.n_layers; p.n_vocab = c.n_vocab; p.max_ctx = c.max_ctx; p.sc_stride = e->sc_stride;
     p.layers = e->d_layers;
-    p.emb_w = e->embed->data; p.emb_s = e->embed->scales; p.head_w = e->lm_head->data; p.head_s = e->lm_head->scales;
+    p.emb_w = e->embed->data; p.emb_s = e->embed->scales; p.head_w = (const uint4*)e->lm_head->data; p.head_s = e->lm_head->scales;
     p.final_norm = e->final_norm; p.rope_cos = e->rope_cos; p.rope_sin = e->rope_sin;
     p.x_qkv = e->x_qkv; p.x_sc = e->x_sc; p.x_attn = e->x_attn; p.x_o = e->x_o; p.x_gu = e->x_gu; p.x_act = e->x_act;
-    p.x_down = e->x_down; p.x_arg = e->x_arg;
+    p.x_down = e->x_down; p.x_arg = e->x_arg; p.cnt = e->cnt;
     p.logits = e->logits; p.tokens = e->tokens; p.st = e->st; p.epoch = e->epoch;
     p.n_body = n_body; p.n_head = n_head; p.eos_id = eos_id; p.pf_ahead = e->pf_ahead;
     p.dbg = e->dbg; p.prof = e->prof ? e->d_prof : nullptr;
@@ -557,6 +564,12 @@ int gtb_engine_create(gtb_engine_t* out, const gtb_model_config* cfg) {
         r |= dalloc((void**)&l.kq, code_bytes); r |= dalloc((void**)&l.vq, code_bytes);
         if (e->adtype == GTB_Q8) { r |= dalloc((void**)&l.ks, (size_t)MC * (KV / 32) * 2); r |= dalloc((void**)&l.vs, (size_t)MC * (KV / 32) * 2); }
         r |= dalloc((void**)&l.attn_norm, (size_t)E * 2); r |= dalloc((void**)&l.ffn_norm, (size_t)E * 2);
+        r |= dalloc((void**)&l.qkv_data, weight_data_bytes(cfg->wdtype, E + 2 * KV, E));
+        r |= dalloc((void**)&l.gu_data, weight_data_bytes(cfg->wdtype, 2 * F, E));
+        if (cfg->wdtype != GTB_F16) {
+            r |= dalloc((void**)&l.qkv_sc, weight_scale_bytes(cfg->wdtype, E + 2 * KV, E));
+            r |= dalloc((void**)&l.gu_sc, weight_scale_bytes(cfg->wdtype, 2 * F, E));
+        }
     }
     r |= dalloc((void**)&e->final_norm, (size_t)E * 2);
     r |= dalloc((void**)&e->xres, E * 4); r |= dalloc((void**)&e->hres, E * 4); r |= dalloc((void**)&e->xfinal, E * 4);
@@ -574,6 +587,7 @@ int gtb_engine_create(gtb_engine_t* out, const gtb_model_config* cfg) {
     r |= dalloc((void**)&e->x_attn, (size_t)E * 8); r |= dalloc((void**)&e->x_o, (size_t)E * 8); r |= dalloc((void**)&e->x_gu, (size_t)2 * F * 8);
     r |= dalloc((void**)&e->x_act, (size_t)(F / 32) * 16 * 8); r |= dalloc((void**)&e->x_down, (size_t)E * 8);
     r |= dalloc((void**)&e->x_arg, (size_t)2 * 1024 * 8); r |= dalloc((void**)&e->dbg, 64); r |= dalloc((void**)&e->epoch, 16);
+    r |= dalloc((void**)&e->cnt, (size_t)CNT_TOTAL * CNT_STRIDE * 4);
     r |= dalloc((void**)&e->d_prof, (size_t)PROF_SLOTS * 8); r |= dalloc((void**)&e->d_layers, (size_t)cfg->n_layers * sizeof(MegaLayer));
     if (r) { return r; }
     {   // RoPE table with the reference's own expressions and libm (gten/ops.h:728-746; SURVEY §7 hard part 4)
@@ -604,11 +618,12 @@ int gtb_engine_destroy(gtb_engine_t e) {
         gtb_weight_free(l.q); gtb_weight_free(l.k); gtb_weight_free(l.v); gtb_weight_free(l.o);
         gtb_weight_free(l.gate); gtb_weight_free(l.up); gtb_weight_free(l.down);
         cudaFree(l.attn_norm); cudaFree(l.ffn_norm); cudaFree(l.kq); cudaFree(l.vq); cudaFree(l.ks); cudaFree(l.vs);
+        cudaFree(l.qkv_data); cudaFree(l.gu_data); cudaFree(l.qkv_sc); cudaFree(l.gu_sc);
     }
     gtb_weight_free(e->embed); gtb_weight_free(e->lm_head);
     void* bufs[] = {e->final_norm, e->xres, e->hres, e->xfinal, e->rqkv, e->rattn, e->ro, e->rg, e->ru, e->rd, e->logits,
                     e->tokens, e->st, e->cap, e->rope_cos, e->rope_sin, e->x_qkv, e->x_sc, e->x_attn, e->x_o, e->x_gu, e->x_act,
-                    e->x_down, e->x_arg, e->dbg, e->epoch, e->d_prof, e->d_layers};
+                    e->x_down, e->x_arg, e->dbg, e->epoch, e->cnt, e->d_prof, e->d_layers};
     for (void* b : bufs) cudaFree(b);
     delete e;
     return GTB_OK;
@@ -644,7 +659,26 @@ int gtb_engine_set_weight(gtb_engine_t e, int layer, int tensor_id, const void* 
     }
     if (*slot) { e->weight_bytes -= (*slot)->nbytes; gtb_weight_free(*slot); *slot = nullptr; drop_graphs(e); }
     e->layers_valid = false;
-    int r = gtb_weight_upload(slot, h_payload, dt, rows, cols);
+    int r;
+    int row_off = -1;
+    uint8_t* fdata = nullptr;
+    uint16_t* fsc = nullptr;
+    if (per_layer) {
+        LayerW& l = e->L[layer];
+        switch (tensor_id) {
+            case GTB_T_Q: row_off = 0; fdata = l.qkv_data; fsc = l.qkv_sc; break;
+            case GTB_T_K: row_off = e->cfg.n_embd; fdata = l.qkv_data; fsc = l.qkv_sc; break;
+            case GTB_T_V: row_off = e->cfg.n_embd + e->kv_dim; fdata = l.qkv_data; fsc = l.qkv_sc; break;
+            case GTB_T_GATE: row_off = 0; fdata = l.gu_data; fsc = l.gu_sc; break;
+            case GTB_T_UP: row_off = e->cfg.n_ffn; fdata = l.gu_data; fsc = l.gu_sc; break;
+            default: break;
+        }
+    }
+    if (row_off >= 0)
+        r = weight_upload_view(slot, h_payload, dt, rows, cols, fdata + weight_data_bytes(dt, row_off, cols),
+                               fsc ? fsc + weight_scale_bytes(dt, row_off, cols) / 2 : nullptr);
+    else
+        r = gtb_weight_upload(slot, h_payload, dt, rows, cols);
     if (r == GTB_OK) e->weight_bytes += (*slot)->nbytes;
     return r;
 }

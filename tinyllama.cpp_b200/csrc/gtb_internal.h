@@ -61,4 +61,14 @@ struct gtb_weight {
     void* data = nullptr;
     uint16_t* scales = nullptr;
     size_t nbytes = 0;
+    bool owns = true;          // false: data/scales are slices of a buffer owned by someone else (fused q|k|v, gate|up)
 };
+
+namespace gtb {
+// repack a host payload into caller-provided device storage (slices of a fused buffer); *out is a non-owning view
+int weight_upload_view(gtb_weight_t* out, const void* h_payload, int dtype, int rows, int cols, void* d_data, uint16_t* d_scales);
+inline size_t weight_data_bytes(int dtype, int rows, int cols) {
+    return dtype == GTB_F16 ? (size_t)rows * cols * 2 : (size_t)rows * cols / 32 * (dtype == GTB_Q4 ? 16 : 32);
+}
+inline size_t weight_scale_bytes(int dtype, int rows, int cols) { return dtype == GTB_F16 ? 0 : (size_t)rows * cols / 32 * 2; }
+}

@@ -3,17 +3,22 @@
 // through L2 instead of a kernel boundary, rows and greedy steps looped inside the kernel.
 //
 // Why: batch-1 decode is ~155 dependent GEMVs per token; at 2-5 us per kernel boundary a graph of small
-// kernels cannot approach the HBM roofline (SURVEY.md §7 hard part 2).  Here a phase boundary costs one L2
-// round trip:
-//   * exchange = "LL" words: every produced fp32 value travels as one 64-bit store {tag:32 | bits:32};
-//     consumers poll the words themselves until the tag equals the phase's epoch, so data and flag arrive
-//     together (no separate barrier, no fence on the critical path).  Tags are a monotone epoch counter.
+// kernels cannot approach the HBM roofline (SURVEY.md §7 hard part 2).  Here a phase boundary costs a few L2
+// round trips:
+//   * exchange: every produced fp32 value travels as one 64-bit "LL" word {tag:32 | bits:32}; the tag is a
+//     monotone epoch, so a reader can never mistake stale data for fresh data and no fence sits on the
+//     critical path.  Readers do not spin on the data (148 CTAs polling 16 KB each saturate L2): one thread
+//     per CTA spins on a per-exchange arrival counter (a relaxed RED per producer CTA -- a hint, not a
+//     guarantee), the rest of the CTA sleeps in bar.sync, then every thread loads exactly the words it needs
+//     and re-reads the rare word whose tag is not there yet.
 //   * weights never depend on activations: each thread issues the 128-bit loads of its share of the NEXT
-//     phase's weight blocks into registers before it starts polling, and one thread per CTA pushes the same
-//     rows of a later phase into L2 with cp.async.bulk.prefetch -- HBM streaming is decoupled from the
-//     dependency chain.
-//   * the numeric contract is unchanged (gtb_dev.cuh / gtb_kernels.cuh): exact integer block dots, products
+//     phase's weight blocks into registers before it waits, and one thread per CTA pushes the same rows of a
+//     later phase into L2 with cp.async.bulk.prefetch -- HBM streaming is decoupled from the dependency chain.
+//   * the numeric contract is unchanged (gtb_dev.cuh): exact integer block dots, products
 //     parked in shared memory, then one thread per (row, lane) runs the reference's ordered fp32 adds.
+//   * the model dimensions are compile-time constants (tinyllama.cpp:12-20); vectors of n_embd elements are
+//     held 4 elements per thread ("quad": one staged 32-bit code word per thread, 8 threads per Q8 block), so
+//     the per-op re-encodes (App. A) cost ~70 instructions per thread and the residual stream lives in registers.
 //
 // Phases of one layer (all CTAs walk the same sequence; the tag of each exchange is the next epoch):
 //   P1   [x' = E(h + E(down)); E(rmsnorm(x'))] -> q|k|v rows                      -> x_qkv   (raw fp32)
@@ -33,27 +38,35 @@ typedef unsigned long long ull;
 
 constexpr int MT = 512;                    // threads per CTA
 constexpr int MWARP = MT / 32;
+constexpr int ME = 2048, MF = 5632, MKV = 256, MH = 32, MGSZ = 8;     // TinyLLamaParams, tinyllama.cpp:12-20
+constexpr int NBE = ME / 32, NBF = MF / 32;
 constexpr int PS_BYTES = 84 * 1024;        // product staging (also the attention scratch)
 constexpr int IT_Q4 = 10;                  // (row, block) items per thread per tile: MT*IT items in registers
 constexpr int IT_Q8 = 5;
 constexpr int SPIN_LIMIT = 1 << 24;        // ~ seconds; a stuck exchange traps instead of hanging the GPU
+static_assert(ME == MT * 4, "quad layout: 4 elements of an n_embd vector per thread");
+
+// arrival counters (one 128-byte line each)
+enum { CNT_ATTN = 0, CNT_O = 1, CNT_ACT = 2, CNT_DOWN = 3, CNT_ARG = 4, CNT_SC0 = 8, CNT_TOTAL = 8 + MH };
+constexpr int CNT_STRIDE = 32;             // in 32-bit words
 
 struct MegaLayer {
-    const void* w[7];                      // q k v o gate up down (device layout, gtb_internal.h)
-    const uint16_t* s[7];
+    const uint4* w[4];                     // q|k|v, o, gate|up, down (device layout, gtb_internal.h)
+    const uint16_t* s[4];
     const uint16_t* attn_norm;
     const uint16_t* ffn_norm;
     uint8_t* kq; uint16_t* ks; uint8_t* vq; uint16_t* vs;
 };
 
 struct MegaParams {
-    int E, F, KV, n_heads, gsz, n_layers, n_vocab, max_ctx, sc_stride;
+    int n_layers, n_vocab, max_ctx, sc_stride;
     const MegaLayer* layers;
     const void* emb_w; const uint16_t* emb_s;
-    const void* head_w; const uint16_t* head_s;
+    const uint4* head_w; const uint16_t* head_s;
     const uint16_t* final_norm;
     const float* rope_cos; const float* rope_sin;
     ull *x_qkv, *x_sc, *x_attn, *x_o, *x_gu, *x_act, *x_down, *x_arg;
+    unsigned int* cnt;
     float* logits;
     int32_t* tokens;
     DevState* st;
@@ -64,7 +77,7 @@ struct MegaParams {
     long long* prof;                       // optional: CTA 0 timestamps of the last row
 };
 
-// ---------------------------------------------------------------- LL words
+// ---------------------------------------------------------------- exchange primitives
 __device__ __forceinline__ void ll_store(ull* p, uint32_t payload, uint32_t tag) {
     const ull v = ((ull)tag << 32) | (ull)payload;
     asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -77,7 +90,7 @@ __device__ __forceinline__ ull ll_load1(const ull* p) {
     asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
     return a;
 }
-__device__ __noinline__ void ll_timeout(ull* dbg, uint32_t tag, const ull* p, ull seen) {
+__device__ __noinline__ void ll_timeout(ull* dbg, uint32_t tag, const void* p, ull seen) {
     if (dbg) {
         dbg[1] = tag; dbg[2] = (ull)p; dbg[3] = seen; dbg[4] = blockIdx.x; dbg[5] = threadIdx.x;
         __threadfence_system();
@@ -86,7 +99,7 @@ __device__ __noinline__ void ll_timeout(ull* dbg, uint32_t tag, const ull* p, ul
     }
     __trap();
 }
-// wait for words [i, i+1] of src
+// words [0, 1] at p (16-byte aligned)
 __device__ __forceinline__ void ll_wait2(const ull* p, uint32_t tag, uint32_t& a, uint32_t& b, ull* dbg) {
     ull x, y;
     int spins = 0;
@@ -107,32 +120,26 @@ __device__ __forceinline__ uint32_t ll_wait1(const ull* p, uint32_t tag, ull* db
     }
     return (uint32_t)x;
 }
-// CTA-wide gather of n words (n even or odd, src 16-byte aligned); sink(index, payload)
-template <typename Sink>
-__device__ __forceinline__ void ll_gather(const ull* src, int n, uint32_t tag, ull* dbg, Sink sink) {
-    const int n2 = n & ~1;
-    for (int i = threadIdx.x * 2; i < n2; i += MT * 4) {
-        // two pairs in flight per thread
-        const int i2 = i + MT * 2;
-        ull x0, y0, x1 = 0, y1 = 0;
-        const bool second = i2 < n2;
-        ll_load2(src + i, x0, y0);
-        if (second) ll_load2(src + i2, x1, y1);
+__device__ __forceinline__ void cnt_add(unsigned int* c, unsigned int v) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(c), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int cnt_load(const unsigned int* c) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+    return v;
+}
+// CTA-wide: (optionally) announce that this CTA's contribution to `sig` is on its way, then wait until counter
+// `cnt` has reached `expected`.  One thread spins; everybody else is parked in the barrier.
+__device__ __forceinline__ void xwait(unsigned int* sig, const unsigned int* cnt, unsigned int expected, ull* dbg) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (sig) cnt_add(sig, 1u);
         int spins = 0;
-        while ((uint32_t)(x0 >> 32) != tag || (uint32_t)(y0 >> 32) != tag) {
-            ll_load2(src + i, x0, y0);
-            if (++spins > SPIN_LIMIT) ll_timeout(dbg, tag, src + i, x0);
-        }
-        sink(i, (uint32_t)x0); sink(i + 1, (uint32_t)y0);
-        if (second) {
-            while ((uint32_t)(x1 >> 32) != tag || (uint32_t)(y1 >> 32) != tag) {
-                ll_load2(src + i2, x1, y1);
-                if (++spins > SPIN_LIMIT) ll_timeout(dbg, tag, src + i2, x1);
-            }
-            sink(i2, (uint32_t)x1); sink(i2 + 1, (uint32_t)y1);
+        while ((int)(cnt_load(cnt) - expected) < 0) {
+            if (++spins > SPIN_LIMIT) ll_timeout(dbg, expected, cnt, cnt_load(cnt));
         }
     }
-    if ((n & 1) && threadIdx.x == MT - 1) sink(n - 1, ll_wait1(src + n - 1, tag, dbg));
+    __syncthreads();
 }
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
@@ -157,20 +164,262 @@ __device__ __forceinline__ long long gtimer() {
     return t;
 }
 
-// ---------------------------------------------------------------- phase descriptors
-struct PhaseDesc {
-    const void* d[3];
-    const uint16_t* s[3];
-    int rows[3];
-    int nm;        // matrices whose rows are concatenated into one row space
-    int nb;        // K / 32
-    int R;         // total rows
+// ---------------------------------------------------------------- quad layout of an n_embd vector
+// thread t: block b = t >> 3, word j = t & 7 (half hh = j >> 2, lane l = j & 3) holds the four elements
+// e0 + {0, 1, 8, 9}, e0 = 32 b + 16 hh + 2 l: exactly the codes of staged word j of the block (gtb_kernels.cuh).
+__device__ __forceinline__ int quad_e0(int t) { return (t >> 3) * 32 + ((t >> 2) & 1) * 16 + (t & 3) * 2; }
+
+// roundf(): half away from zero, for |v| < 2^22 (quants.h:64)
+__device__ __forceinline__ float round_away(float v) {
+    const float M = 12582912.0f;
+    float r = __fsub_rn(__fadd_rn(v, M), M);                    // nearest-even
+    const float d = __fsub_rn(v, r);                            // exact
+    if (fabsf(d) == 0.5f) r = __fadd_rn(v, copysignf(0.5f, v));
+    return r;
+}
+// Q8 encode of a block held as 8 quads (quants.h:52-66): decoded values, the staged code word and the fp16 scale.
+__device__ __forceinline__ void q8_encode_quad(const float x[4], float d[4], uint32_t& word, float& deltaf) {
+    float am = fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3])));
+    am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 1));
+    am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 2));
+    am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 4));
+    const float delta = __fdiv_rn(am, 127.0f);
+    deltaf = __half2float(__float2half_rn(delta));
+    const float scale = (delta != 0.0f) ? __fdiv_rn(1.0f, delta) : 0.0f;     // from the UNROUNDED delta
+    uint32_t cb[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float r = round_away(__fmul_rn(x[i], scale));
+        d[i] = __fmul_rn(r, deltaf);
+        cb[i] = __float_as_uint(__fadd_rn(r, 12582912.0f));     // low byte = two's complement code
+    }
+    word = __byte_perm(__byte_perm(cb[0], cb[1], 0x0040), __byte_perm(cb[2], cb[3], 0x0040), 0x5410);
+}
+template <int AT>
+__device__ __forceinline__ void roundtrip_quad(const float x[4], float d[4]) {
+    if (AT == DT_F16) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) d[i] = f16_roundtrip(x[i]);
+    } else {
+        uint32_t w; float df;
+        q8_encode_quad(x, d, w, df);
+    }
+}
+__device__ __forceinline__ int xs_index(int e) { return (((e >> 6) * 8) + (e & 7)) * 8 + ((e >> 3) & 7); }
+// encode + write the staged GEMV input (the ActView layout of gtb_kernels.cuh)
+template <int AT, int WT>
+__device__ __forceinline__ void stage_quad(const ActView& av, const float x[4]) {
+    const int t = threadIdx.x;
+    if (AT == DT_F16) {
+        const int e0 = quad_e0(t);
+        av.xs[xs_index(e0)] = f16_roundtrip(x[0]);
+        av.xs[xs_index(e0 + 1)] = f16_roundtrip(x[1]);
+        av.xs[xs_index(e0 + 8)] = f16_roundtrip(x[2]);
+        av.xs[xs_index(e0 + 9)] = f16_roundtrip(x[3]);
+    } else {
+        float d[4]; uint32_t w; float df;
+        q8_encode_quad(x, d, w, df);
+        av.aw[t] = w;                                           // t == b * 8 + j
+        if ((t & 7) == 0) av.ad[t >> 3] = df;
+        if (WT == DT_Q4) {
+            int s = __dp4a((int)w, 0x01010101, 0);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            if ((t & 4) == 0) av.ns7[(t >> 3) * 4 + (t & 3)] = -7 * s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- exact in-order sum, 512 threads x 4 elements per pass
+// Same algorithm as exact_sum_block (gtb_dev.cuh), restructured: cross-warp prefixes are 16-lane shuffle scans,
+// four barriers per pass, the serial resolve reads its items with 128-bit loads.
+constexpr int ES2_MAXEXP = 96;
+struct ExactSum2Smem {
+    double wsum[MWARP];
+    PMap wtail[MWARP];
+    int wflag[MWARP];
+    int wcnt[MWARP];
+    uint4 item[2 * ES2_MAXEXP + 2];       // {a, b, type, -}
+    float result;
 };
 
-template <int WT> struct ItemsPerThread { static constexpr int v = (WT == DT_Q4) ? IT_Q4 : IT_Q8; };
+template <typename LoadT>
+__device__ __forceinline__ float exact_sum512(LoadT load4, int n, ExactSum2Smem& sm) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float s_run = 0.0f;
+    double carry = 0.0;
+    for (int p0 = 0; p0 < n; p0 += MT * 4) {
+        const int i0 = p0 + tid * 4;
+        float tv[4];
+        load4(i0, tv);                                     // elements >= n must come back as 0
+        const double loc = ((double)tv[0] + (double)tv[1]) + ((double)tv[2] + (double)tv[3]);
+        double inc = loc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+        if (lane == 31) sm.wsum[wid] = inc;
+        __syncthreads();                                   // (1)
+        double ws = (lane < MWARP) ? sm.wsum[lane] : 0.0;
+#pragma unroll
+        for (int o = 1; o < MWARP; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += v; }
+        const double wbase = __shfl_sync(0xffffffffu, ws, (wid + 31) & 31);      // inclusive total of warp wid-1
+        const double total_d = __shfl_sync(0xffffffffu, ws, MWARP - 1);
+        // A differs from a strictly sequential double sum only in its last bits: the drift allowance of the float
+        // chain below (2^-22 * index) dwarfs that.
+        double A = carry + ((wid > 0) ? wbase : 0.0) + (inc - loc);
+        PMap em[4];
+        uint32_t exmask = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const double An = A + (double)tv[j];
+            em[j] = PMap{0u, 0u};
+            if (tv[j] != 0.0f) {
+                const double rel = (double)(i0 + j + 8) * 0x1p-22;
+                const double lo = A - A * rel, hi = An + An * rel;
+                bool ex = !(lo > 0x1p-100);
+                if (!ex) {
+                    const int eL = dexp(lo), eU = dexp(hi);
+                    const uint32_t tb = __float_as_uint(tv[j]);
+                    if (eL != eU || (tb >> 23) == 0u || ((int)(tb >> 23) - 127) > eL) ex = true;
+                    else em[j] = pmap_of(tv[j], eL);
+                }
+                if (ex) exmask |= 1u << j;
+            }
+            A = An;
+        }
+        const int nexp = __popc(exmask);
+        // per-thread pieces: maps between explicit elements
+        PMap cur{0u, 0u}, head{0u, 0u};
+        PMap mids[3] = {PMap{0u, 0u}, PMap{0u, 0u}, PMap{0u, 0u}};
+        int ne = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (exmask & (1u << j)) {
+                if (ne == 0) head = cur;
+                else if (ne == 1) mids[0] = cur;
+                else if (ne == 2) mids[1] = cur;
+                else mids[2] = cur;
+                cur = PMap{0u, 0u};
+                ne++;
+            } else {
+                cur = pmap_compose(cur, em[j]);
+            }
+        }
+        // warp scans: explicit count (inclusive) and segmented composition of the tails
+        int cinc = nexp;
+        PMap sc = cur;
+        int fl = (ne > 0) ? 1 : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int cv = __shfl_up_sync(0xffffffffu, cinc, o);
+            const uint32_t pa = __shfl_up_sync(0xffffffffu, sc.a, o);
+            const uint32_t pb = __shfl_up_sync(0xffffffffu, sc.b, o);
+            const int pf = __shfl_up_sync(0xffffffffu, fl, o);
+            if (lane >= o) {
+                cinc += cv;
+                if (!fl) sc = pmap_compose(PMap{pa, pb}, sc);
+                fl |= pf;
+            }
+        }
+        if (lane == 31) { sm.wcnt[wid] = cinc; sm.wtail[wid] = sc; sm.wflag[wid] = fl; }
+        __syncthreads();                                   // (2)
+        int wc = (lane < MWARP) ? sm.wcnt[lane] : 0;
+        PMap wt = (lane < MWARP) ? sm.wtail[lane] : PMap{0u, 0u};
+        int wf = (lane < MWARP) ? sm.wflag[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < MWARP; o <<= 1) {
+            const int cv = __shfl_up_sync(0xffffffffu, wc, o);
+            const uint32_t pa = __shfl_up_sync(0xffffffffu, wt.a, o);
+            const uint32_t pb = __shfl_up_sync(0xffffffffu, wt.b, o);
+            const int pf = __shfl_up_sync(0xffffffffu, wf, o);
+            if (lane >= o) {
+                wc += cv;
+                if (!wf) wt = pmap_compose(PMap{pa, pb}, wt);
+                wf |= pf;
+            }
+        }
+        const int total = __shfl_sync(0xffffffffu, wc, MWARP - 1);
+        const int cb_w = __shfl_sync(0xffffffffu, wc, (wid + 31) & 31);
+        const uint32_t wpa = __shfl_sync(0xffffffffu, wt.a, (wid + 31) & 31);
+        const uint32_t wpb = __shfl_sync(0xffffffffu, wt.b, (wid + 31) & 31);
+        const int cbase = ((wid > 0) ? cb_w : 0) + cinc - nexp;
+        // composition of everything since the last explicit element before this warp
+        const PMap wpre = (wid > 0) ? PMap{wpa, wpb} : PMap{0u, 0u};
+        if (total > ES2_MAXEXP) {                          // pathological input: plain serial chain (still exact)
+            if (tid == 0) {
+                float s = s_run;
+                const int hi_i = min(n, p0 + MT * 4);
+                for (int i = p0; i < hi_i; i += 4) {
+                    float q[4];
+                    load4(i, q);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) s = __fadd_rn(s, q[j]);
+                }
+                sm.result = s;
+            }
+            __syncthreads();
+            s_run = sm.result;
+            carry += total_d;
+            __syncthreads();
+            continue;
+        }
+        const PMap incl = fl ? sc : pmap_compose(wpre, sc);
+        const uint32_t ea = __shfl_up_sync(0xffffffffu, incl.a, 1), eb = __shfl_up_sync(0xffffffffu, incl.b, 1);
+        const PMap excl = (lane == 0) ? wpre : PMap{ea, eb};
+        if (ne > 0) {
+            const PMap r = pmap_compose(excl, head);
+            sm.item[2 * cbase] = make_uint4(r.a, r.b, 0u, 0u);
+            int k = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (exmask & (1u << j)) {
+                    sm.item[2 * (cbase + k) + 1] = make_uint4(__float_as_uint(tv[j]), 0u, 1u, 0u);
+                    if (k == 1) sm.item[2 * (cbase + 1)] = make_uint4(mids[0].a, mids[0].b, 0u, 0u);
+                    else if (k == 2) sm.item[2 * (cbase + 2)] = make_uint4(mids[1].a, mids[1].b, 0u, 0u);
+                    else if (k == 3) sm.item[2 * (cbase + 3)] = make_uint4(mids[2].a, mids[2].b, 0u, 0u);
+                    k++;
+                }
+            }
+        }
+        if (tid == MT - 1) sm.item[2 * total] = make_uint4(incl.a, incl.b, 0u, 0u);
+        __syncthreads();                                   // (3)
+        if (tid == 0) {
+            uint32_t sb = __float_as_uint(s_run);
+            const int nq = 2 * total + 1;
+            int q = 0;
+            for (; q + 4 <= nq; q += 4) {
+                uint4 it[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) it[u] = sm.item[q + u];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (it[u].z) sb = __float_as_uint(__fadd_rn(__uint_as_float(sb), __uint_as_float(it[u].x)));
+                    else sb += (sb & 1u) ? it[u].y : it[u].x;
+                }
+            }
+            for (; q < nq; q++) {
+                const uint4 it = sm.item[q];
+                if (it.z) sb = __float_as_uint(__fadd_rn(__uint_as_float(sb), __uint_as_float(it.x)));
+                else sb += (sb & 1u) ? it.y : it.x;
+            }
+            sm.result = __uint_as_float(sb);
+        }
+        __syncthreads();                                   // (4)
+        s_run = sm.result;
+        carry += total_d;
+    }
+    return s_run;
+}
+
+// ---------------------------------------------------------------- GEMV phases
+struct PhaseDesc {
+    const uint4* d;
+    const uint16_t* s;
+    int nb;        // K / 32
+    int kind;      // 0 q|k|v, 1 o, 2 gate|up, 3 down, 4 lm_head
+};
 
 struct MegaSm {
-    ExactSumSmem es;
+    ExactSum2Smem es;
+    int rr[5][2];              // this CTA's row range per phase kind
     float raw[192];
     uint32_t qw[16]; float qd[2]; float qf[64];
     uint32_t kw[16]; float kd[2]; float kf[64];
@@ -181,26 +430,16 @@ struct MegaSm {
     float bestv[MWARP]; int besti[MWARP];
 };
 
-struct MCtx {
-    float* res;            // residual stream of the current row (every CTA keeps its own copy)
-    float* xbuf;           // scratch vector
-    ActView av;            // staged GEMV input
-    float* ps;             // product staging / attention scratch
-    MegaSm* sm;
-    unsigned int ep;       // epoch counter: identical sequence in every CTA
-    int cta, G;
-    int prof_i;
-};
-
-__host__ __device__ inline size_t mega_smem_bytes(int at, int E, int F) {
+__host__ __device__ inline size_t mega_smem_bytes(int at) {
     size_t s = 0;
-    s += (size_t)E * 4;                              // res
-    s += (size_t)((F > E ? F : E) + 64) * 4;          // xbuf
-    s += (act_bytes(at, F) + 15) & ~(size_t)15;      // act
+    s += (size_t)(MF + 64) * 4;                       // xbuf
+    s += (act_bytes(at, MF) + 15) & ~(size_t)15;      // staged GEMV input
     s += PS_BYTES;
     s += (sizeof(MegaSm) + 15) & ~(size_t)15;
     return s + 32;
 }
+
+template <int WT> struct ItemsPerThread { static constexpr int v = (WT == DT_Q4) ? IT_Q4 : IT_Q8; };
 
 template <int WT>
 struct WRegs {
@@ -212,59 +451,61 @@ struct WRegs {
 
 template <int WT>
 __device__ __forceinline__ int tile_rows(int nb) {
-    int tr = MT / 4;                                       // 4 chain threads per row
-    const int by_ps = PS_BYTES / (16 * (nb + 1));
-    if (by_ps < tr) tr = by_ps;
-    const int by_regs = (MT * ItemsPerThread<WT>::v) / nb;
-    if (by_regs < tr) tr = by_regs;
-    return tr;
-}
-
-// rows of the phase owned by this CTA: [r0, r1)
-__device__ __forceinline__ void cta_rows(const PhaseDesc& pd, int cta, int G, int& r0, int& r1) {
-    r0 = (int)(((long long)cta * pd.R) / G);
-    r1 = (int)(((long long)(cta + 1) * pd.R) / G);
-}
-
-// issue the weight loads of one tile: rows [row_begin, row_begin + nrows) of the concatenated row space
-template <int WT>
-__device__ __forceinline__ void load_tile(const PhaseDesc& pd, int row_begin, int nrows, WRegs<WT>& w) {
-    constexpr int IT = WRegs<WT>::IT;
-    const int nb = pd.nb;
-    int rl = threadIdx.x / nb, b = threadIdx.x - rl * nb;
-    const int drl = MT / nb, db = MT - drl * nb;
-    const int c1 = pd.rows[0], c2 = pd.rows[0] + pd.rows[1];
-#pragma unroll
-    for (int j = 0; j < IT; j++) {
-        if (rl < nrows) {
-            const int gr = row_begin + rl;
-            const int m = (pd.nm > 1 && gr >= c1) ? ((pd.nm > 2 && gr >= c2) ? 2 : 1) : 0;
-            const int lr = gr - (m == 0 ? 0 : (m == 1 ? c1 : c2));
-            const size_t blk = (size_t)lr * nb + b;
-            const uint4* dp = reinterpret_cast<const uint4*>(pd.d[m]);
-            if (WT == DT_Q4) {
-                w.a[j] = ldg_stream(dp + blk);
-            } else {
-                w.a[j] = ldg_stream(dp + 2 * blk);
-                w.b[j] = ldg_stream(dp + 2 * blk + 1);
-            }
-            w.sc[j] = ldg_stream_u16(pd.s[m] + blk);
-        }
-        b += db; rl += drl;
-        if (b >= nb) { b -= nb; rl++; }
+    if (nb == NBE) {
+        constexpr int by_ps = PS_BYTES / (16 * (NBE + 1));
+        constexpr int by_regs = (MT * ItemsPerThread<WT>::v) / NBE;
+        constexpr int a = (MT / 4 < by_ps) ? MT / 4 : by_ps;
+        return (a < by_regs) ? a : by_regs;
+    } else {
+        constexpr int by_ps = PS_BYTES / (16 * (NBF + 1));
+        constexpr int by_regs = (MT * ItemsPerThread<WT>::v) / NBF;
+        constexpr int a = (MT / 4 < by_ps) ? MT / 4 : by_ps;
+        return (a < by_regs) ? a : by_regs;
     }
 }
 
-// exact integer lane sums of one block from registers, scaled: p[l] = float(lane[l]) * (da * dw)  (ops.h:282-287)
+__device__ __forceinline__ PhaseDesc phase_desc(const MegaParams& P, int s) {
+    PhaseDesc pd;
+    if (s >= 4 * P.n_layers) {
+        pd.d = P.head_w; pd.s = P.head_s; pd.nb = NBE; pd.kind = 4;
+        return pd;
+    }
+    const MegaLayer& L = P.layers[s >> 2];
+    const int k = s & 3;
+    pd.d = L.w[k]; pd.s = L.s[k]; pd.nb = (k == 3) ? NBF : NBE; pd.kind = k;
+    return pd;
+}
+
+// issue the weight loads of one tile: rows [row_begin, row_begin + nrows) -- contiguous blocks, no index math
 template <int WT>
-__device__ __forceinline__ float4 block_products_r(const uint4& wa, const uint4& wb, uint32_t sc16, const ActView& av, int b) {
-    const float dw = h2f((uint16_t)sc16);
-    const uint4 ax = reinterpret_cast<const uint4*>(av.aw)[2 * b];
-    const uint4 ay = reinterpret_cast<const uint4*>(av.aw)[2 * b + 1];
-    const float s = __fmul_rn(av.ad[b], dw);
+__device__ __forceinline__ void load_tile(const PhaseDesc& pd, int row_begin, int nrows, WRegs<WT>& w) {
+    constexpr int IT = WRegs<WT>::IT;
+    const int nitems = nrows * pd.nb;
+    const size_t base = (size_t)row_begin * pd.nb;
+    const uint4* dp = pd.d + ((WT == DT_Q8) ? 2 * base : base);
+    const uint16_t* sp = pd.s + base;
+#pragma unroll
+    for (int j = 0; j < IT; j++) {
+        const int it = j * MT + threadIdx.x;
+        if (it < nitems) {
+            if (WT == DT_Q4) {
+                w.a[j] = ldg_stream(dp + it);
+            } else {
+                w.a[j] = ldg_stream(dp + 2 * it);
+                w.b[j] = ldg_stream(dp + 2 * it + 1);
+            }
+            w.sc[j] = ldg_stream_u16(sp + it);
+        }
+    }
+}
+
+// exact integer lane sums of one block, scaled: p[l] = float(lane[l]) * (da * dw)  (gten/ops.h:282-287, 339-378)
+template <int WT>
+__device__ __forceinline__ float4 block_products_r(const uint4& wa, const uint4& wb, uint32_t sc16, const uint4& ax, const uint4& ay,
+                                                   const int4& n7, float ad) {
+    const float s = __fmul_rn(ad, h2f((uint16_t)sc16));
     int l0, l1, l2, l3;
     if (WT == DT_Q4) {
-        const int4 n7 = reinterpret_cast<const int4*>(av.ns7)[b];
         l0 = __dp4a((int)(wa.x & 0x0f0f0f0fu), (int)ay.x, __dp4a((int)((wa.x >> 4) & 0x0f0f0f0fu), (int)ax.x, n7.x));
         l1 = __dp4a((int)(wa.y & 0x0f0f0f0fu), (int)ay.y, __dp4a((int)((wa.y >> 4) & 0x0f0f0f0fu), (int)ax.y, n7.y));
         l2 = __dp4a((int)(wa.z & 0x0f0f0f0fu), (int)ay.z, __dp4a((int)((wa.z >> 4) & 0x0f0f0f0fu), (int)ax.z, n7.z));
@@ -279,22 +520,40 @@ __device__ __forceinline__ float4 block_products_r(const uint4& wa, const uint4&
 }
 
 template <int WT>
-__device__ __forceinline__ void tile_products(const PhaseDesc& pd, int nrows, const WRegs<WT>& w, const ActView& av, float* ps) {
+__device__ __forceinline__ void tile_products(int nb, int nrows, const WRegs<WT>& w, const ActView& av, float* ps) {
     constexpr int IT = WRegs<WT>::IT;
-    const int nb = pd.nb;
-    int rl = threadIdx.x / nb, b = threadIdx.x - rl * nb;
-    const int drl = MT / nb, db = MT - drl * nb;
     float4* ps4 = reinterpret_cast<float4*>(ps);
+    const int nitems = nrows * nb;
+    if (nb == NBE) {
+        // K = 2048: the block index of a thread's items never changes -> its activation block stays in registers
+        const int b = threadIdx.x & (NBE - 1), rl0 = threadIdx.x >> 6;
+        const uint4 ax = reinterpret_cast<const uint4*>(av.aw)[2 * b];
+        const uint4 ay = reinterpret_cast<const uint4*>(av.aw)[2 * b + 1];
+        const int4 n7 = (WT == DT_Q4) ? reinterpret_cast<const int4*>(av.ns7)[b] : make_int4(0, 0, 0, 0);
+        const float ad = av.ad[b];
 #pragma unroll
-    for (int j = 0; j < IT; j++) {
-        if (rl < nrows) ps4[rl * (nb + 1) + b] = block_products_r<WT>(w.a[j], w.b[(WT == DT_Q8) ? j : 0], w.sc[j], av, b);
-        b += db; rl += drl;
-        if (b >= nb) { b -= nb; rl++; }
+        for (int j = 0; j < IT; j++) {
+            if (j * MT + (int)threadIdx.x < nitems)
+                ps4[(rl0 + j * (MT / NBE)) * (NBE + 1) + b] = block_products_r<WT>(w.a[j], w.b[(WT == DT_Q8) ? j : 0], w.sc[j], ax, ay, n7, ad);
+        }
+    } else {
+        int rl = threadIdx.x / NBF, b = threadIdx.x - rl * NBF;
+        constexpr int drl = MT / NBF, db = MT - drl * NBF;
+#pragma unroll
+        for (int j = 0; j < IT; j++) {
+            if (j * MT + (int)threadIdx.x < nitems) {
+                const uint4 ax = reinterpret_cast<const uint4*>(av.aw)[2 * b];
+                const uint4 ay = reinterpret_cast<const uint4*>(av.aw)[2 * b + 1];
+                const int4 n7 = (WT == DT_Q4) ? reinterpret_cast<const int4*>(av.ns7)[b] : make_int4(0, 0, 0, 0);
+                ps4[rl * (NBF + 1) + b] = block_products_r<WT>(w.a[j], w.b[(WT == DT_Q8) ? j : 0], w.sc[j], ax, ay, n7, av.ad[b]);
+            }
+            b += db; rl += drl;
+            if (b >= NBF) { b -= NBF; rl++; }
+        }
     }
 }
 
 // ordered adds: thread (row, l) sums its lane's products in ascending block order, then (a0+a1)+(a2+a3).
-// Returns the row result on the l == 0 thread of each row (valid when tid < nrows * 4).
 __device__ __forceinline__ float tile_chain(int nb, int nrows, const float* ps) {
     const int ct = threadIdx.x;
     float acc = 0.0f;
@@ -314,62 +573,24 @@ __device__ __forceinline__ float tile_chain(int nb, int nrows, const float* ps) 
     return __fadd_rn(v1, __shfl_xor_sync(0xffffffffu, v1, 2));
 }
 
-// L2 prefetch of this CTA's rows of a phase (one thread)
+// L2 prefetch of rows [r0, r1) of a phase (one thread)
 template <int WT>
-__device__ __forceinline__ void prefetch_phase(const PhaseDesc& pd, int cta, int G) {
-    int r0, r1;
-    cta_rows(pd, cta, G, r0, r1);
-    int base = 0;
-    for (int m = 0; m < pd.nm; m++) {
-        const int lo = max(r0, base) - base, hi = min(r1, base + pd.rows[m]) - base;
-        if (hi > lo) {
-            if (WT == DT_F16) {
-                l2_prefetch(reinterpret_cast<const uint8_t*>(pd.d[m]) + (size_t)lo * pd.nb * 64, (size_t)(hi - lo) * pd.nb * 64);
-            } else {
-                const size_t bb = (WT == DT_Q4) ? 16 : 32;
-                l2_prefetch(reinterpret_cast<const uint8_t*>(pd.d[m]) + (size_t)lo * pd.nb * bb, (size_t)(hi - lo) * pd.nb * bb);
-                l2_prefetch(pd.s[m] + (size_t)lo * pd.nb, (size_t)(hi - lo) * pd.nb * 2);
-            }
-        }
-        base += pd.rows[m];
+__device__ __forceinline__ void prefetch_rows(const PhaseDesc& pd, int r0, int r1) {
+    if (r1 <= r0) return;
+    if (WT == DT_F16) {
+        l2_prefetch(reinterpret_cast<const uint8_t*>(pd.d) + (size_t)r0 * pd.nb * 64, (size_t)(r1 - r0) * pd.nb * 64);
+    } else {
+        const size_t bb = (WT == DT_Q4) ? 16 : 32;
+        l2_prefetch(reinterpret_cast<const uint8_t*>(pd.d) + (size_t)r0 * pd.nb * bb, (size_t)(r1 - r0) * pd.nb * bb);
+        l2_prefetch(pd.s + (size_t)r0 * pd.nb, (size_t)(r1 - r0) * pd.nb * 2);
     }
-}
-
-// ---------------------------------------------------------------- the GEMV sequence of one row
-// index s: layer * 4 + {0: q|k|v, 1: o, 2: gate|up, 3: down}; s == 4 * n_layers: lm_head
-__device__ __forceinline__ PhaseDesc phase_desc(const MegaParams& P, int s) {
-    PhaseDesc pd;
-    pd.d[1] = pd.d[2] = nullptr; pd.s[1] = pd.s[2] = nullptr; pd.rows[1] = pd.rows[2] = 0;
-    if (s >= 4 * P.n_layers) {
-        pd.d[0] = P.head_w; pd.s[0] = P.head_s; pd.rows[0] = P.n_vocab; pd.nm = 1; pd.nb = P.E / 32; pd.R = P.n_vocab;
-        return pd;
-    }
-    const MegaLayer& L = P.layers[s >> 2];
-    switch (s & 3) {
-        case 0:
-            pd.d[0] = L.w[0]; pd.d[1] = L.w[1]; pd.d[2] = L.w[2]; pd.s[0] = L.s[0]; pd.s[1] = L.s[1]; pd.s[2] = L.s[2];
-            pd.rows[0] = P.E; pd.rows[1] = P.KV; pd.rows[2] = P.KV; pd.nm = 3; pd.nb = P.E / 32; pd.R = P.E + 2 * P.KV;
-            break;
-        case 1:
-            pd.d[0] = L.w[3]; pd.s[0] = L.s[3]; pd.rows[0] = P.E; pd.nm = 1; pd.nb = P.E / 32; pd.R = P.E;
-            break;
-        case 2:
-            pd.d[0] = L.w[4]; pd.d[1] = L.w[5]; pd.s[0] = L.s[4]; pd.s[1] = L.s[5];
-            pd.rows[0] = P.F; pd.rows[1] = P.F; pd.nm = 2; pd.nb = P.E / 32; pd.R = 2 * P.F;
-            break;
-        default:
-            pd.d[0] = L.w[6]; pd.s[0] = L.s[6]; pd.rows[0] = P.E; pd.nm = 1; pd.nb = P.F / 32; pd.R = P.E;
-            break;
-    }
-    return pd;
 }
 
 // F16 weights: direct streaming, thread (row, lane l of 8), no staging (gten/ops.h:140-160)
 __device__ __forceinline__ float f16_row_lane(const uint4* __restrict__ src, int cpr, int l, const ActView& av) {
     float acc = 0.0f;
     constexpr int UN = 8;
-    int c = 0;
-    for (; c + UN <= cpr; c += UN) {
+    for (int c = 0; c < cpr; c += UN) {                        // cpr is 32 or 88: multiples of 8
         uint4 w[UN];
 #pragma unroll
         for (int u = 0; u < UN; u++) w[u] = ldg_stream(src + (size_t)(c + u) * 8);
@@ -385,34 +606,21 @@ __device__ __forceinline__ float f16_row_lane(const uint4* __restrict__ src, int
             acc = fmaf(x1.x, d.x, acc); acc = fmaf(x1.y, d.y, acc); acc = fmaf(x1.z, e.x, acc); acc = fmaf(x1.w, e.y, acc);
         }
     }
-    for (; c < cpr; c++) {
-        const uint4 w = ldg_stream(src + (size_t)c * 8);
-        const float* x = av.xs + (c * 8 + l) * 8;
-        const __half* hw = reinterpret_cast<const __half*>(&w);
-#pragma unroll
-        for (int i = 0; i < 8; i++) acc = fmaf(x[i], __half2float(hw[i]), acc);
-    }
     return acc;
 }
 
-// One GEMV phase.  sink(row, value) is called by one thread per finished row (row = index in the phase's row space).
+// One GEMV phase over this CTA's rows [r0, r1).  sink(row, value) is called by one thread per finished row.
 // For Q4/Q8 `w` holds the first tile's weights on entry; on exit it holds the first tile of `next` (if next_valid).
 template <int WT, typename Sink>
-__device__ __forceinline__ void gemv_phase(const MegaParams& P, MCtx& c, const PhaseDesc& pd, WRegs<WT>& w,
-                                           const PhaseDesc& next, bool next_valid, Sink sink) {
-    int r0, r1;
-    cta_rows(pd, c.cta, c.G, r0, r1);
+__device__ __forceinline__ void gemv_phase(const PhaseDesc& pd, int r0, int r1, const ActView& av, float* ps, WRegs<WT>& w,
+                                           const PhaseDesc& next, int n0, int n1, bool next_valid, Sink sink) {
     if (WT == DT_F16) {
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, rl = lane >> 3, l = lane & 7;
         const int cpr = pd.nb / 2;                                   // 64-element chunks per row
-        const int c1 = pd.rows[0], c2 = pd.rows[0] + pd.rows[1];
         for (int row0 = r0 + wid * 4; row0 < r1; row0 += MWARP * 4) {
             const int gr = row0 + rl;
             const bool active = gr < r1;
-            const int grc = active ? gr : r0;
-            const int m = (pd.nm > 1 && grc >= c1) ? ((pd.nm > 2 && grc >= c2) ? 2 : 1) : 0;
-            const int lr = grc - (m == 0 ? 0 : (m == 1 ? c1 : c2));
-            const float acc = f16_row_lane(reinterpret_cast<const uint4*>(pd.d[m]) + (size_t)lr * cpr * 8 + l, cpr, l, c.av);
+            const float acc = f16_row_lane(pd.d + (size_t)(active ? gr : r0) * cpr * 8 + l, cpr, l, av);
             float v = __shfl_sync(0xffffffffu, acc, lane & ~7);
 #pragma unroll
             for (int j = 1; j < 8; j++) v = __fadd_rn(v, __shfl_sync(0xffffffffu, acc, (lane & ~7) + j));
@@ -424,30 +632,20 @@ __device__ __forceinline__ void gemv_phase(const MegaParams& P, MCtx& c, const P
     const int tr = tile_rows<WT>(nb);
     for (int t0 = r0; t0 < r1; t0 += tr) {
         const int nrows = min(tr, r1 - t0);
-        tile_products<WT>(pd, nrows, w, c.av, c.ps);
-        if (t0 + tr < r1) {
-            load_tile<WT>(pd, t0 + tr, min(tr, r1 - t0 - tr), w);
-        } else if (next_valid) {
-            int n0, n1;
-            cta_rows(next, c.cta, c.G, n0, n1);
-            const int ntr = tile_rows<WT>(next.nb);
-            load_tile<WT>(next, n0, min(ntr, n1 - n0), w);
-        }
+        tile_products<WT>(nb, nrows, w, av, ps);
+        if (t0 + tr < r1) load_tile<WT>(pd, t0 + tr, min(tr, r1 - t0 - tr), w);
+        else if (next_valid) load_tile<WT>(next, n0, min(tile_rows<WT>(next.nb), n1 - n0), w);
         __syncthreads();
-        const float v = tile_chain(nb, nrows, c.ps);
+        const float v = tile_chain(nb, nrows, ps);
         if ((threadIdx.x & 3) == 0 && threadIdx.x < nrows * 4) sink(t0 + (threadIdx.x >> 2), v);
         if (t0 + tr < r1) __syncthreads();
     }
-    if (r1 <= r0 && next_valid) {                     // no rows of this phase here: still fetch the next phase's first tile
-        int n0, n1;
-        cta_rows(next, c.cta, c.G, n0, n1);
-        load_tile<WT>(next, n0, min(tile_rows<WT>(next.nb), n1 - n0), w);
-    }
+    if (r1 <= r0 && next_valid) load_tile<WT>(next, n0, min(tile_rows<WT>(next.nb), n1 - n0), w);
 }
 
 // ---------------------------------------------------------------- attention, unit = (head h, quarter j)
 template <int AT>
-__device__ __forceinline__ float mega_score(const MegaSm& sm, const MegaLayer& L, int KV, int g, int kcol, int own) {
+__device__ __forceinline__ float mega_score(const MegaSm& sm, const MegaLayer& L, int g, int kcol, int own) {
     if (AT == DT_F16) {
         float acc[8];
 #pragma unroll
@@ -458,7 +656,7 @@ __device__ __forceinline__ float mega_score(const MegaSm& sm, const MegaLayer& L
 #pragma unroll
                 for (int l = 0; l < 8; l++) acc[l] = fmaf(sm.qf[8 * i + l], sm.kf[8 * i + l], acc[l]);
         } else {
-            const uint4* kp = reinterpret_cast<const uint4*>(L.kq + ((size_t)kcol * KV + g * 64) * 2);
+            const uint4* kp = reinterpret_cast<const uint4*>(L.kq + ((size_t)kcol * MKV + g * 64) * 2);
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const uint4 w = __ldcg(kp + i);
@@ -482,9 +680,9 @@ __device__ __forceinline__ float mega_score(const MegaSm& sm, const MegaLayer& L
                 ky = make_uint4(sm.kw[bi * 8 + 4], sm.kw[bi * 8 + 5], sm.kw[bi * 8 + 6], sm.kw[bi * 8 + 7]);
                 kdv = sm.kd[bi];
             } else {
-                const uint4* kp = reinterpret_cast<const uint4*>(L.kq + (size_t)kcol * KV + g * 64 + bi * 32);
+                const uint4* kp = reinterpret_cast<const uint4*>(L.kq + (size_t)kcol * MKV + g * 64 + bi * 32);
                 kx = __ldcg(kp); ky = __ldcg(kp + 1);
-                kdv = h2f(__ldcg(L.ks + (size_t)kcol * (KV / 32) + g * 2 + bi));
+                kdv = h2f(__ldcg(L.ks + (size_t)kcol * (MKV / 32) + g * 2 + bi));
             }
             const float s = __fmul_rn(sm.qd[bi], kdv);
             const uint32_t* q = sm.qw + bi * 8;
@@ -522,29 +720,29 @@ __host__ __device__ inline size_t attn_scratch_bytes(int at, int max_ctx) {
 
 // P2a: re-encode / RoPE the unit's q, k, v (gten/ops.h:645-646, 733-753), append K/V, publish the scores of quarter j
 template <int AT>
-__device__ __forceinline__ void mega_attn_a(const MegaParams& P, const MegaLayer& L, MCtx& c, int pos, uint32_t tag_qkv, uint32_t tag_sc) {
-    MegaSm& sm = *c.sm;
+__device__ __forceinline__ void mega_attn_a(const MegaParams& P, const MegaLayer& L, MegaSm& sm, float* ps, int cta, int pos,
+                                            uint32_t tag_qkv, uint32_t tag_sc) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int h = c.cta >> 2, j = c.cta & 3, g = h / P.gsz;
-    const bool writer = (h % P.gsz) == 0 && j == 0;
-    const AttnScratch as = attn_scratch(AT, c.ps, P.max_ctx);
+    const int h = cta >> 2, j = cta & 3, g = h / MGSZ;
+    const bool writer = (h % MGSZ) == 0 && j == 0;
+    const AttnScratch as = attn_scratch(AT, ps, P.max_ctx);
     // this unit's V slice (16 channels) of every cached position: independent of the exchange, issue first
     {
         const int ch0 = g * 64 + j * 16;
         for (int i = tid; i < pos; i += MT) {
             if (AT == DT_F16) {
-                const uint4* vp = reinterpret_cast<const uint4*>(L.vq + ((size_t)i * P.KV + ch0) * 2);
+                const uint4* vp = reinterpret_cast<const uint4*>(L.vq + ((size_t)i * MKV + ch0) * 2);
                 reinterpret_cast<uint4*>(as.vb)[i * 2] = __ldcg(vp);
                 reinterpret_cast<uint4*>(as.vb)[i * 2 + 1] = __ldcg(vp + 1);
             } else {
-                reinterpret_cast<uint4*>(as.vb)[i] = __ldcg(reinterpret_cast<const uint4*>(L.vq + (size_t)i * P.KV + ch0));
-                as.vd[i] = h2f(__ldcg(L.vs + (size_t)i * (P.KV / 32) + g * 2 + (j >> 1)));
+                reinterpret_cast<uint4*>(as.vb)[i] = __ldcg(reinterpret_cast<const uint4*>(L.vq + (size_t)i * MKV + ch0));
+                as.vd[i] = h2f(__ldcg(L.vs + (size_t)i * (MKV / 32) + g * 2 + (j >> 1)));
             }
         }
     }
     if (tid < 96) {
         const int seg = tid >> 5, o = (tid & 31) * 2;
-        const ull* src = P.x_qkv + (seg == 0 ? h * 64 : (seg == 1 ? P.E + g * 64 : P.E + P.KV + g * 64)) + o;
+        const ull* src = P.x_qkv + (seg == 0 ? h * 64 : (seg == 1 ? ME + g * 64 : ME + MKV + g * 64)) + o;
         uint32_t a, b;
         ll_wait2(src, tag_qkv, a, b, P.dbg);
         sm.raw[seg * 64 + o] = __uint_as_float(a);
@@ -562,7 +760,7 @@ __device__ __forceinline__ void mega_attn_a(const MegaParams& P, const MegaLayer
             const uint16_t hb = f2h(x);
             sm.vf[ch] = h2f(hb);
             if (sl >= 0 && sl < 16) reinterpret_cast<uint16_t*>(as.vb)[pos * 16 + sl] = hb;
-            if (writer) reinterpret_cast<uint16_t*>(L.vq)[(size_t)pos * P.KV + g * 64 + ch] = hb;
+            if (writer) reinterpret_cast<uint16_t*>(L.vq)[(size_t)pos * MKV + g * 64 + ch] = hb;
         } else {
             uint16_t dh;
             const int q = q8_encode_lane(x, &dh);
@@ -570,8 +768,8 @@ __device__ __forceinline__ void mega_attn_a(const MegaParams& P, const MegaLayer
             if (sl >= 0 && sl < 16) as.vb[pos * 16 + sl] = (uint8_t)(int8_t)q;
             if (lane == 0 && half == (j >> 1)) as.vd[pos] = h2f(dh);
             if (writer) {
-                L.vq[(size_t)pos * P.KV + g * 64 + ch] = (uint8_t)(int8_t)q;
-                if (lane == 0) L.vs[(size_t)pos * (P.KV / 32) + g * 2 + half] = dh;
+                L.vq[(size_t)pos * MKV + g * 64 + ch] = (uint8_t)(int8_t)q;
+                if (lane == 0) L.vs[(size_t)pos * (MKV / 32) + g * 2 + half] = dh;
             }
         }
     }
@@ -588,7 +786,7 @@ __device__ __forceinline__ void mega_attn_a(const MegaParams& P, const MegaLayer
             if (which == 0) sm.qf[half * 32 + lane] = d;
             else {
                 sm.kf[half * 32 + lane] = d;
-                if (writer) reinterpret_cast<uint16_t*>(L.kq)[(size_t)pos * P.KV + g * 64 + half * 32 + lane] = hb;
+                if (writer) reinterpret_cast<uint16_t*>(L.kq)[(size_t)pos * MKV + g * 64 + half * 32 + lane] = hb;
             }
         } else {
             uint16_t dh;
@@ -602,8 +800,8 @@ __device__ __forceinline__ void mega_attn_a(const MegaParams& P, const MegaLayer
                 reinterpret_cast<int8_t*>(sm.kw)[half * 32 + pb] = (int8_t)q;
                 if (lane == 0) sm.kd[half] = delta;
                 if (writer) {
-                    L.kq[(size_t)pos * P.KV + g * 64 + half * 32 + pb] = (uint8_t)(int8_t)q;
-                    if (lane == 0) L.ks[(size_t)pos * (P.KV / 32) + g * 2 + half] = dh;
+                    L.kq[(size_t)pos * MKV + g * 64 + half * 32 + pb] = (uint8_t)(int8_t)q;
+                    if (lane == 0) L.ks[(size_t)pos * (MKV / 32) + g * 2 + half] = dh;
                 }
             }
         }
@@ -614,20 +812,29 @@ __device__ __forceinline__ void mega_attn_a(const MegaParams& P, const MegaLayer
     const int lo = j * per, hi = min(pos + 1, lo + per);
     ull* dst = P.x_sc + (size_t)h * P.sc_stride;
     for (int k = lo + tid; k < hi; k += MT) {
-        const float s = __fmul_rn(mega_score<AT>(sm, L, P.KV, g, k, pos), 0.125f);
+        const float s = __fmul_rn(mega_score<AT>(sm, L, g, k, pos), 0.125f);
         ll_store(dst + k, __float_as_uint(s), tag_sc);
     }
 }
 
 // P2b: softmax over the whole row (gten/ops.h:967-996), then P.V for the unit's 16 channels (ops.h:1046-1087)
 template <int AT>
-__device__ __forceinline__ void mega_attn_b(const MegaParams& P, MCtx& c, int pos, int n_ctx, uint32_t tag_sc, uint32_t tag_attn) {
-    MegaSm& sm = *c.sm;
+__device__ __forceinline__ void mega_attn_b(const MegaParams& P, MegaSm& sm, float* ps, int cta, int pos, int n_ctx,
+                                            uint32_t tag_sc, uint32_t tag_attn) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int h = c.cta >> 2, j = c.cta & 3;
-    const AttnScratch as = attn_scratch(AT, c.ps, P.max_ctx);
+    const int h = cta >> 2, j = cta & 3;
+    const AttnScratch as = attn_scratch(AT, ps, P.max_ctx);
     float* sc = as.sc;
-    ll_gather(P.x_sc + (size_t)h * P.sc_stride, pos + 1, tag_sc, P.dbg, [&](int i, uint32_t v) { sc[i] = __uint_as_float(v); });
+    {
+        const ull* src = P.x_sc + (size_t)h * P.sc_stride;
+        const int n = pos + 1, n2 = n & ~1;
+        for (int i = tid * 2; i < n2; i += MT * 2) {
+            uint32_t a, b;
+            ll_wait2(src + i, tag_sc, a, b, P.dbg);
+            sc[i] = __uint_as_float(a); sc[i + 1] = __uint_as_float(b);
+        }
+        if ((n & 1) && tid == MT - 1) sc[n - 1] = __uint_as_float(ll_wait1(src + n - 1, tag_sc, P.dbg));
+    }
     __syncthreads();
     float mx = -INFINITY;
     for (int k = tid; k <= pos; k += MT) mx = fmaxf(mx, sc[k]);
@@ -639,7 +846,10 @@ __device__ __forceinline__ void mega_attn_b(const MegaParams& P, MCtx& c, int po
     for (int w = 1; w < MWARP; w++) mx = fmaxf(mx, sm.red[w]);
     for (int k = tid; k <= pos; k += MT) sc[k] = expf_glibc(__fsub_rn(sc[k], mx));
     __syncthreads();
-    const float sum = exact_sum_block([&](int i) { return sc[i]; }, pos + 1, sm.es);
+    const float sum = exact_sum512([&](int i, float q[4]) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) q[u] = (i + u <= pos) ? sc[i + u] : 0.0f;
+    }, pos + 1, sm.es);
     const int nblk = (pos + 32) / 32;
     for (int b = wid; b < nblk; b += MWARP) {
         const int i = b * 32 + lane;
@@ -680,15 +890,14 @@ __device__ __forceinline__ void mega_attn_b(const MegaParams& P, MCtx& c, int po
 }
 
 // P4b: one warp per block of 32 FFN channels: E(E(silu(E(gate))) * E(up)) (gten/modules.cpp:238-247), published as
-// packed words in the staged layout (Q8: 8 code words + the fp16 scale; F16: 16 half2 words)
+// packed words in the staged layout (Q8: pairs (X_l, Y_l), the fp16 scale, a pad; F16: 16 half2 words)
 template <int AT>
-__device__ __forceinline__ void mega_silu(const MegaParams& P, MCtx& c, uint32_t tag_gu, uint32_t tag_act) {
+__device__ __forceinline__ void mega_silu(const MegaParams& P, int cta, int G, uint32_t tag_gu, uint32_t tag_act) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int nblk = P.F / 32;
-    for (int b = c.cta + wid * c.G; b < nblk; b += c.G * MWARP) {
+    for (int b = cta + wid * G; b < NBF; b += G * MWARP) {
         const int e = b * 32 + lane;
         const float g0 = __uint_as_float(ll_wait1(P.x_gu + e, tag_gu, P.dbg));
-        const float u0 = __uint_as_float(ll_wait1(P.x_gu + P.F + e, tag_gu, P.dbg));
+        const float u0 = __uint_as_float(ll_wait1(P.x_gu + MF + e, tag_gu, P.dbg));
         const float g1 = roundtrip<AT>(g0);
         const float u1 = roundtrip<AT>(u0);
         const float g2 = roundtrip<AT>(silu_ref(g1));
@@ -701,278 +910,299 @@ __device__ __forceinline__ void mega_silu(const MegaParams& P, MCtx& c, uint32_t
         } else {
             uint16_t dh;
             const uint32_t q = (uint32_t)q8_encode_lane(y, &dh) & 0xffu;
-            // word w (0..7): half = w >> 2, l = w & 3: codes of elements 16*half + {2l, 2l+1, 2l+8, 2l+9}
+            // lane w < 8 assembles staged word w: half = w >> 2, l = w & 3: codes of elements 16*half + {2l, 2l+1, 2l+8, 2l+9}
             const int w = lane & 7, e0 = 16 * (w >> 2) + 2 * (w & 3);
             const uint32_t b0 = __shfl_sync(0xffffffffu, q, e0);
             const uint32_t b1 = __shfl_sync(0xffffffffu, q, e0 + 1);
             const uint32_t b2 = __shfl_sync(0xffffffffu, q, e0 + 8);
             const uint32_t b3 = __shfl_sync(0xffffffffu, q, e0 + 9);
-            if (lane < 8) ll_store(P.x_act + (size_t)b * 9 + lane, b0 | (b1 << 8) | (b2 << 16) | (b3 << 24), tag_act);
-            if (lane == 8) ll_store(P.x_act + (size_t)b * 9 + 8, (uint32_t)dh, tag_act);
+            if (lane < 8) ll_store(P.x_act + (size_t)b * 10 + (w & 3) * 2 + (w >> 2), b0 | (b1 << 8) | (b2 << 16) | (b3 << 24), tag_act);
+            if (lane == 8) ll_store(P.x_act + (size_t)b * 10 + 8, (uint32_t)dh, tag_act);
+            if (lane == 9) ll_store(P.x_act + (size_t)b * 10 + 9, 0u, tag_act);
         }
+        __syncwarp();
+        if (lane == 0) cnt_add(P.cnt + CNT_ACT * CNT_STRIDE, 1u);
     }
 }
 
 // P5 prologue: the staged GEMV input straight from the packed words
 template <int AT, int WT>
-__device__ __forceinline__ void mega_gather_act(const MegaParams& P, MCtx& c, uint32_t tag_act) {
-    const int nblk = P.F / 32;
+__device__ __forceinline__ void mega_gather_act(const MegaParams& P, const ActView& av, uint32_t tag_act) {
     if (AT == DT_F16) {
-        ll_gather(P.x_act, nblk * 16, tag_act, P.dbg, [&](int i, uint32_t v) {
-            const int e = 2 * i;
-            const float lo = h2f((uint16_t)(v & 0xffffu)), hi = h2f((uint16_t)(v >> 16));
-            c.av.xs[(((e >> 6) * 8) + (e & 7)) * 8 + ((e >> 3) & 7)] = lo;
-            c.av.xs[((((e + 1) >> 6) * 8) + ((e + 1) & 7)) * 8 + (((e + 1) >> 3) & 7)] = hi;
-        });
+        for (int p = threadIdx.x; p < NBF * 8; p += MT) {
+            uint32_t a, b;
+            ll_wait2(P.x_act + 2 * p, tag_act, a, b, P.dbg);
+            const int e = 4 * p;
+            av.xs[xs_index(e)] = h2f((uint16_t)(a & 0xffffu));
+            av.xs[xs_index(e + 1)] = h2f((uint16_t)(a >> 16));
+            av.xs[xs_index(e + 2)] = h2f((uint16_t)(b & 0xffffu));
+            av.xs[xs_index(e + 3)] = h2f((uint16_t)(b >> 16));
+        }
     } else {
-        ll_gather(P.x_act, nblk * 9, tag_act, P.dbg, [&](int i, uint32_t v) {
-            const int b = i / 9, k = i - b * 9;
-            if (k < 8) c.av.aw[b * 8 + k] = v;
-            else c.av.ad[b] = h2f((uint16_t)v);
-        });
-        if (WT == DT_Q4) {
-            __syncthreads();
-            for (int i = threadIdx.x; i < nblk * 4; i += MT) {
-                const int b = i >> 2, l = i & 3;
-                const int s = __dp4a((int)c.av.aw[b * 8 + l], 0x01010101, __dp4a((int)c.av.aw[b * 8 + 4 + l], 0x01010101, 0));
-                c.av.ns7[i] = -7 * s;
+        for (int p = threadIdx.x; p < NBF * 5; p += MT) {
+            uint32_t a, b;
+            ll_wait2(P.x_act + 2 * p, tag_act, a, b, P.dbg);
+            const int blk = p / 5, k = p - blk * 5;
+            if (k < 4) {
+                av.aw[blk * 8 + k] = a;             // X_k
+                av.aw[blk * 8 + 4 + k] = b;         // Y_k
+                if (WT == DT_Q4) av.ns7[blk * 4 + k] = -7 * __dp4a((int)a, 0x01010101, __dp4a((int)b, 0x01010101, 0));
+            } else {
+                av.ad[blk] = h2f((uint16_t)a);
             }
         }
     }
 }
 
-// token embedding into the residual stream (gten/ops.h:514-564)
+// token embedding into the residual registers (gten/ops.h:514-564)
 template <int WT>
-__device__ __forceinline__ void mega_embed(const MegaParams& P, MCtx& c, int tok) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int E = P.E;
+__device__ __forceinline__ void mega_embed(const MegaParams& P, int tok, float res[4]) {
+    const int t = threadIdx.x, b = t >> 3, j = t & 7;
     const size_t row = (size_t)tok;
-    for (int b = wid; b < E / 32; b += MWARP) {
-        const int e = b * 32 + lane;
-        float v;
-        if (WT == DT_F16) {
-            const int ch = e >> 6, r = e & 63, l = r & 7, ii = r >> 3;
-            v = h2f(reinterpret_cast<const uint16_t*>(P.emb_w)[((row * (E / 64) + ch) * 8 + l) * 8 + ii]);
+    if (WT == DT_F16) {
+        const int e0 = quad_e0(t);
+        const uint16_t* src = reinterpret_cast<const uint16_t*>(P.emb_w) + row * ME;
+        res[0] = h2f(src[xs_index(e0)]); res[1] = h2f(src[xs_index(e0 + 1)]);
+        res[2] = h2f(src[xs_index(e0 + 8)]); res[3] = h2f(src[xs_index(e0 + 9)]);
+    } else {
+        const size_t blk = row * NBE + b;
+        const float delta = h2f(P.emb_s[blk]);
+        if (WT == DT_Q8) {
+            const uint32_t w = reinterpret_cast<const uint32_t*>(P.emb_w)[blk * 8 + j];       // the row is copied: codes as they are
+#pragma unroll
+            for (int i = 0; i < 4; i++) res[i] = __fmul_rn((float)(int8_t)((w >> (8 * i)) & 0xffu), delta);
         } else {
-            const size_t blk = row * (E / 32) + b;
-            const float delta = h2f(P.emb_s[blk]);
-            if (WT == DT_Q8) {
-                v = __fmul_rn((float)reinterpret_cast<const int8_t*>(P.emb_w)[blk * 32 + perm_byte(lane)], delta);
-            } else {
-                const int jj = lane & 15;
-                const int l = (jj & 7) >> 1, ps = (jj & 1) + 2 * (jj >> 3);
-                const uint8_t byte = reinterpret_cast<const uint8_t*>(P.emb_w)[blk * 16 + l * 4 + ps];
-                const int q = (int)((lane < 16) ? (byte >> 4) : (byte & 0x0f)) - 7;
-                v = q8_roundtrip_lane(__fmul_rn((float)q, delta));
-            }
+            // Q4 row: dequantise, then re-encode as Q8 (ops.h:522-528)
+            const uint32_t w = reinterpret_cast<const uint32_t*>(P.emb_w)[blk * 4 + (j & 3)];
+            const uint32_t nib = (j < 4) ? ((w >> 4) & 0x0f0f0f0fu) : (w & 0x0f0f0f0fu);
+            float x[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) x[i] = __fmul_rn((float)((int)((nib >> (8 * i)) & 0xffu) - 7), delta);
+            uint32_t cw; float df;
+            q8_encode_quad(x, res, cw, df);
         }
-        c.res[e] = v;
     }
 }
 
 #define MEGA_PROF()                                                                   \
     do {                                                                              \
-        if (P.prof && c.cta == 0 && threadIdx.x == 0) P.prof[c.prof_i++] = gtimer();  \
+        if (P.prof && cta == 0 && threadIdx.x == 0) P.prof[prof_i++] = gtimer();      \
     } while (0)
 
 template <int WT>
 __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
     constexpr int AT = (WT == DT_F16) ? DT_F16 : DT_Q8;
     extern __shared__ __align__(16) unsigned char smem[];
-    MCtx c;
-    {
-        size_t off = 0;
-        c.res = reinterpret_cast<float*>(smem + off); off += (size_t)P.E * 4;
-        c.xbuf = reinterpret_cast<float*>(smem + off); off += (size_t)((P.F > P.E ? P.F : P.E) + 64) * 4;
-        c.av = act_carve(AT, P.F, smem + off); off += (act_bytes(AT, P.F) + 15) & ~(size_t)15;
-        c.ps = reinterpret_cast<float*>(smem + off); off += PS_BYTES;
-        c.sm = reinterpret_cast<MegaSm*>(smem + off);
+    float* xbuf = reinterpret_cast<float*>(smem);
+    const ActView av = act_carve(AT, MF, smem + (size_t)(MF + 64) * 4);
+    float* ps = reinterpret_cast<float*>(smem + (size_t)(MF + 64) * 4 + ((act_bytes(AT, MF) + 15) & ~(size_t)15));
+    MegaSm& sm = *reinterpret_cast<MegaSm*>(reinterpret_cast<unsigned char*>(ps) + PS_BYTES);
+    const int cta = blockIdx.x, G = gridDim.x, tid = threadIdx.x;
+    int prof_i = 0;
+    unsigned int ep = *reinterpret_cast<volatile unsigned int*>(P.epoch);
+    const int n_units = MH * 4;
+    const int nL4 = 4 * P.n_layers;                // GEMV phases of a row without the lm_head
+    if (tid < 5) {
+        const int R = (tid == 0) ? ME + 2 * MKV : ((tid == 2) ? 2 * MF : ((tid == 4) ? P.n_vocab : ME));
+        sm.rr[tid][0] = (int)(((long long)cta * R) / G);
+        sm.rr[tid][1] = (int)(((long long)(cta + 1) * R) / G);
     }
-    c.cta = blockIdx.x; c.G = gridDim.x; c.prof_i = 0;
-    c.ep = *reinterpret_cast<volatile unsigned int*>(P.epoch);
-    MegaSm& sm = *c.sm;
-    const int tid = threadIdx.x;
-    const int n_units = P.n_heads * 4;
-    const int n_seq = 4 * P.n_layers + 1;          // GEMV phases of a row that ends with the lm_head
+    // arrival counters only ever grow; what this launch waits for is relative to their value at its start
+    unsigned int exp_attn = cnt_load(P.cnt + CNT_ATTN * CNT_STRIDE), exp_o = cnt_load(P.cnt + CNT_O * CNT_STRIDE);
+    unsigned int exp_act = cnt_load(P.cnt + CNT_ACT * CNT_STRIDE), exp_down = cnt_load(P.cnt + CNT_DOWN * CNT_STRIDE);
+    unsigned int exp_arg = cnt_load(P.cnt + CNT_ARG * CNT_STRIDE);
+    unsigned int exp_sc = (cta < n_units) ? cnt_load(P.cnt + (CNT_SC0 + (cta >> 2)) * CNT_STRIDE) : 0u;
     int pos = P.st->pos;
     const int nctx_min = P.st->nctx_min;
     const int n_rows = P.n_body + P.n_head;
     int n_gen = 0, stop = 0, next_tok = -1;
+    __syncthreads();
     WRegs<WT> w;
     PhaseDesc pd = phase_desc(P, 0);
-    if (WT != DT_F16) {
-        int r0, r1;
-        cta_rows(pd, c.cta, c.G, r0, r1);
-        const int tr = tile_rows<WT>(pd.nb);
-        load_tile<WT>(pd, r0, min(tr, r1 - r0), w);
-    }
+    if (WT != DT_F16) load_tile<WT>(pd, sm.rr[0][0], min(tile_rows<WT>(pd.nb), sm.rr[0][1] - sm.rr[0][0]), w);
     if (tid == 0) {
-        for (int a = 1; a < P.pf_ahead && a < n_seq - 1; a++) prefetch_phase<WT>(phase_desc(P, a), c.cta, c.G);
+        for (int a = 1; a < P.pf_ahead && a < nL4; a++) prefetch_rows<WT>(phase_desc(P, a), sm.rr[a & 3][0], sm.rr[a & 3][1]);
     }
-    for (int r = 0; r < n_rows; r++, pos++) {
+    float res[4] = {0.0f, 0.0f, 0.0f, 0.0f};      // this thread's quad of the residual stream
+    const int e0 = quad_e0(tid);
+    // The whole row is ONE loop over GEMV phases with a single copy of every building block: a phase's code runs once
+    // per layer and is fetched through the instruction caches every time, so the loop body has to stay small.
+    for (int r = 0; r < n_rows && !stop; r++, pos++) {
         const bool with_head = r >= P.n_body;
         const bool last_row = (r == n_rows - 1);
         const int n_ctx = max(nctx_min, pos + 1);
         const int tok = (next_tok >= 0) ? next_tok : __ldcg(P.tokens + pos);
-        // L2 prefetch of this CTA's rows of the GEMV phase pf_ahead steps after phase s (wrapping into the next row)
-        auto prefetch_ahead = [&](int s) {
-            if (tid != 0 || P.pf_ahead <= 0) return;
-            int t = s + P.pf_ahead;
-            const int nrow = with_head ? n_seq : n_seq - 1;
-            if (t >= nrow) {
-                if (last_row) return;
-                t -= nrow;
-                if (t >= n_seq - 1) return;
-            }
-            prefetch_phase<WT>(phase_desc(P, t), c.cta, c.G);
-        };
-        c.prof_i = 0;
+        const int nphase = with_head ? nL4 + 1 : nL4;
+        next_tok = -1;
+        prof_i = 0;
         MEGA_PROF();
-        mega_embed<WT>(P, c, tok);
-        __syncthreads();
-        uint32_t tag_down = 0;
-        for (int li = 0; li < P.n_layers; li++) {
-            const MegaLayer& L = P.layers[li];
-            // ---------------- P1
-            if (li > 0) {
-                ll_gather(P.x_down, P.E, tag_down, P.dbg, [&](int i, uint32_t v) { c.xbuf[i] = __uint_as_float(v); });
-                __syncthreads();
+        mega_embed<WT>(P, tok, res);
+        uint32_t tag_in = 0;                        // tag of the exchange the next prologue consumes
+        for (int s = 0; s < nphase; s++) {
+            const int kind = pd.kind;
+            const MegaLayer& L = P.layers[min(s >> 2, P.n_layers - 1)];
+            // ---------------- prologue: wait for the input vector and stage it as this phase's GEMV input
+            if (kind == 3) {
+                exp_act += NBF;
+                xwait(nullptr, P.cnt + CNT_ACT * CNT_STRIDE, exp_act, P.dbg);
+                mega_gather_act<AT, WT>(P, av, tag_in);
+            } else {
+                float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                if (s > 0) {
+                    const ull* src;
+                    if (kind == 1) {
+                        exp_attn += n_units;
+                        xwait((cta < n_units) ? P.cnt + CNT_ATTN * CNT_STRIDE : nullptr, P.cnt + CNT_ATTN * CNT_STRIDE, exp_attn, P.dbg);
+                        src = P.x_attn;
+                    } else if (kind == 2) {
+                        exp_o += G;
+                        xwait(P.cnt + CNT_O * CNT_STRIDE, P.cnt + CNT_O * CNT_STRIDE, exp_o, P.dbg);
+                        src = P.x_o;
+                    } else {
+                        exp_down += G;
+                        xwait(P.cnt + CNT_DOWN * CNT_STRIDE, P.cnt + CNT_DOWN * CNT_STRIDE, exp_down, P.dbg);
+                        src = P.x_down;
+                    }
+                    uint32_t a0, a1, a2, a3;
+                    ll_wait2(src + e0, tag_in, a0, a1, P.dbg);
+                    ll_wait2(src + e0 + 8, tag_in, a2, a3, P.dbg);
+                    x[0] = __uint_as_float(a0); x[1] = __uint_as_float(a1); x[2] = __uint_as_float(a2); x[3] = __uint_as_float(a3);
+                }
+                if (kind == 1) {
+                    stage_quad<AT, WT>(av, x);                                   // E(attention output)
+                } else {
+                    // residual add (gten/ops.h:870-898) + RMSNorm (ops.h:762-804)
+                    const uint16_t* nw = (kind == 0) ? L.attn_norm : ((kind == 2) ? L.ffn_norm : P.final_norm);
+                    const uint32_t nw01 = __ldg(reinterpret_cast<const uint32_t*>(nw + e0));
+                    const uint32_t nw23 = __ldg(reinterpret_cast<const uint32_t*>(nw + e0 + 8));
+                    if (s > 0) {
+                        float d1[4], y[4];
+                        roundtrip_quad<AT>(x, d1);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) y[i] = __fadd_rn(res[i], d1[i]);
+                        roundtrip_quad<AT>(y, res);
+                    }
+                    *reinterpret_cast<float2*>(xbuf + e0) = make_float2(__fmul_rn(res[0], res[0]), __fmul_rn(res[1], res[1]));
+                    *reinterpret_cast<float2*>(xbuf + e0 + 8) = make_float2(__fmul_rn(res[2], res[2]), __fmul_rn(res[3], res[3]));
+                    __syncthreads();
+                    const float sq_sum = exact_sum512([&](int i, float q[4]) {
+                        const float4 v = *reinterpret_cast<const float4*>(xbuf + i);
+                        q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
+                    }, ME, sm.es);
+                    const float denom = __fadd_rn(sqrtf(__fdiv_rn(sq_sum, (float)ME)), 1e-6f);
+                    float y[4];
+                    y[0] = __fmul_rn(__fdiv_rn(res[0], denom), h2f((uint16_t)(nw01 & 0xffffu)));
+                    y[1] = __fmul_rn(__fdiv_rn(res[1], denom), h2f((uint16_t)(nw01 >> 16)));
+                    y[2] = __fmul_rn(__fdiv_rn(res[2], denom), h2f((uint16_t)(nw23 & 0xffffu)));
+                    y[3] = __fmul_rn(__fdiv_rn(res[3], denom), h2f((uint16_t)(nw23 >> 16)));
+                    stage_quad<AT, WT>(av, y);
+                }
             }
-            pro_norm<AT>(c.av, c.res, (li > 0) ? c.xbuf : nullptr, L.attn_norm, P.E, c.xbuf, sm.es, c.res, nullptr, nullptr, nullptr);
             __syncthreads();
             MEGA_PROF();
-            const uint32_t tag_qkv = ++c.ep;
-            prefetch_ahead(li * 4 + 0);
-            PhaseDesc nx = phase_desc(P, li * 4 + 1);
-            gemv_phase<WT>(P, c, pd, w, nx, true, [&](int row, float v) { ll_store(P.x_qkv + row, __float_as_uint(v), tag_qkv); });
-            pd = nx;
-            MEGA_PROF();
-            // ---------------- P2
-            const uint32_t tag_sc = ++c.ep;
-            const uint32_t tag_attn = ++c.ep;
-            if (c.cta < n_units) {
-                __syncthreads();                                   // product staging is reused as attention scratch
-                mega_attn_a<AT>(P, L, c, pos, tag_qkv, tag_sc);
-                MEGA_PROF();
-                mega_attn_b<AT>(P, c, pos, n_ctx, tag_sc, tag_attn);
-                __threadfence();                                   // K/V appends visible before anything later is published
+            // ---------------- GEMV
+            const uint32_t tag = ++ep;
+            const int r0 = sm.rr[kind][0], r1 = sm.rr[kind][1];
+            if (tid == 0 && P.pf_ahead > 0) {       // L2 prefetch of this CTA's rows, pf_ahead phases ahead (wraps into the next row)
+                int t = s + P.pf_ahead;
+                bool ok = true;
+                if (t >= nphase) { t -= nphase; ok = !last_row && t < nL4; }
+                if (ok) {
+                    const PhaseDesc pf = phase_desc(P, t);
+                    prefetch_rows<WT>(pf, sm.rr[pf.kind][0], sm.rr[pf.kind][1]);
+                }
             }
-            MEGA_PROF();
-            // ---------------- P3
-            ll_gather(P.x_attn, P.E, tag_attn, P.dbg, [&](int i, uint32_t v) { c.xbuf[i] = __uint_as_float(v); });
-            __syncthreads();
-            pro_encode<AT>(c.av, c.xbuf, P.E, nullptr);
-            __syncthreads();
-            MEGA_PROF();
-            const uint32_t tag_o = ++c.ep;
-            prefetch_ahead(li * 4 + 1);
-            nx = phase_desc(P, li * 4 + 2);
-            gemv_phase<WT>(P, c, pd, w, nx, true, [&](int row, float v) { ll_store(P.x_o + row, __float_as_uint(v), tag_o); });
-            pd = nx;
-            MEGA_PROF();
-            // ---------------- P4
-            ll_gather(P.x_o, P.E, tag_o, P.dbg, [&](int i, uint32_t v) { c.xbuf[i] = __uint_as_float(v); });
-            __syncthreads();
-            pro_norm<AT>(c.av, c.res, c.xbuf, L.ffn_norm, P.E, c.xbuf, sm.es, c.res, nullptr, nullptr, nullptr);
-            __syncthreads();
-            MEGA_PROF();
-            const uint32_t tag_gu = ++c.ep;
-            prefetch_ahead(li * 4 + 2);
-            nx = phase_desc(P, li * 4 + 3);
-            gemv_phase<WT>(P, c, pd, w, nx, true, [&](int row, float v) { ll_store(P.x_gu + row, __float_as_uint(v), tag_gu); });
-            pd = nx;
-            MEGA_PROF();
-            // ---------------- P4b
-            const uint32_t tag_act = ++c.ep;
-            mega_silu<AT>(P, c, tag_gu, tag_act);
-            MEGA_PROF();
-            // ---------------- P5
-            __syncthreads();
-            mega_gather_act<AT, WT>(P, c, tag_act);
-            __syncthreads();
-            MEGA_PROF();
-            tag_down = ++c.ep;
-            prefetch_ahead(li * 4 + 3);
-            const bool more = (li + 1 < P.n_layers) || with_head || !last_row;
-            nx = (li + 1 < P.n_layers) ? phase_desc(P, li * 4 + 4) : (with_head ? phase_desc(P, 4 * P.n_layers) : phase_desc(P, 0));
-            gemv_phase<WT>(P, c, pd, w, nx, more, [&](int row, float v) { ll_store(P.x_down + row, __float_as_uint(v), tag_down); });
-            pd = nx;
-            MEGA_PROF();
-        }
-        if (with_head) {
-            // final residual + norm + lm_head (tinyllama.cpp:57-58), then argmax (tinyllama.cpp:416-424)
-            ll_gather(P.x_down, P.E, tag_down, P.dbg, [&](int i, uint32_t v) { c.xbuf[i] = __uint_as_float(v); });
-            __syncthreads();
-            pro_norm<AT>(c.av, c.res, c.xbuf, P.final_norm, P.E, c.xbuf, sm.es, c.res, nullptr, nullptr, nullptr);
-            __syncthreads();
-            MEGA_PROF();
-            const uint32_t tag_arg = ++c.ep;
-            prefetch_ahead(4 * P.n_layers);
+            const bool more = (s + 1 < nphase) || !last_row;
+            const PhaseDesc nx = phase_desc(P, (s + 1 < nphase) ? s + 1 : 0);
+            ull* outp = (kind == 0) ? P.x_qkv : ((kind == 1) ? P.x_o : ((kind == 2) ? P.x_gu : P.x_down));
             float best = -INFINITY;
             int arg = 0x7fffffff;
-            PhaseDesc nx = phase_desc(P, 0);
-            gemv_phase<WT>(P, c, pd, w, nx, !last_row, [&](int row, float v) {
-                P.logits[row] = v;
-                if (v > best) { best = v; arg = row; }              // rows ascend per thread: first maximum wins
+            gemv_phase<WT>(pd, r0, r1, av, ps, w, nx, sm.rr[nx.kind][0], sm.rr[nx.kind][1], more, [&](int row, float v) {
+                if (kind == 4) {
+                    P.logits[row] = v;
+                    if (v > best) { best = v; arg = row; }          // rows ascend per thread: first maximum wins
+                } else {
+                    ll_store(outp + row, __float_as_uint(v), tag);
+                }
             });
             pd = nx;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
-                if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
-            }
-            if ((tid & 31) == 0) { sm.bestv[tid >> 5] = best; sm.besti[tid >> 5] = arg; }
-            __syncthreads();
-            if (tid == 0) {
-                for (int q = 1; q < MWARP; q++) {
-                    const float ov = sm.bestv[q];
-                    const int oi = sm.besti[q];
-                    if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
+            tag_in = tag;
+            MEGA_PROF();
+            // ---------------- what follows the GEMV
+            if (kind == 0) {
+                const uint32_t tag_sc = ++ep;
+                const uint32_t tag_attn = ++ep;
+                if (cta < n_units) {
+                    __syncthreads();                               // product staging is reused as attention scratch
+                    mega_attn_a<AT>(P, L, sm, ps, cta, pos, tag, tag_sc);
+                    MEGA_PROF();
+                    exp_sc += 4;
+                    xwait(P.cnt + (CNT_SC0 + (cta >> 2)) * CNT_STRIDE, P.cnt + (CNT_SC0 + (cta >> 2)) * CNT_STRIDE, exp_sc, P.dbg);
+                    mega_attn_b<AT>(P, sm, ps, cta, pos, n_ctx, tag_sc, tag_attn);
+                    __threadfence();                               // K/V appends visible before anything later is published
                 }
-                ll_store(P.x_arg + 2 * c.cta, __float_as_uint(best), tag_arg);
-                ll_store(P.x_arg + 2 * c.cta + 1, (uint32_t)arg, tag_arg);
-            }
-            // every CTA reduces the per-CTA candidates the same way
-            float* cv = c.xbuf;
-            int* ci = reinterpret_cast<int*>(c.xbuf) + c.G;
-            __syncthreads();
-            ll_gather(P.x_arg, 2 * c.G, tag_arg, P.dbg, [&](int i, uint32_t v) {
-                if (i & 1) ci[i >> 1] = (int)v; else cv[i >> 1] = __uint_as_float(v);
-            });
-            __syncthreads();
-            if (tid < 32) {
-                float bv = -INFINITY;
-                int bi = 0x7fffffff;
-                for (int q = tid; q < c.G; q += 32) {
-                    const float ov = cv[q];
-                    const int oi = ci[q];
-                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-                }
+                tag_in = tag_attn;
+                MEGA_PROF();
+            } else if (kind == 2) {
+                const uint32_t tag_act = ++ep;
+                mega_silu<AT>(P, cta, G, tag, tag_act);
+                tag_in = tag_act;
+                MEGA_PROF();
+            } else if (kind == 4) {
+                // argmax (tinyllama.cpp:416-424): per-CTA first maximum, exchanged, reduced identically by every CTA
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
-                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+                    if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
                 }
-                if (tid == 0) sm.besti[0] = (bi == 0x7fffffff) ? 0 : bi;   // all -inf/NaN: the reference leaves index 0
+                if ((tid & 31) == 0) { sm.bestv[tid >> 5] = best; sm.besti[tid >> 5] = arg; }
+                __syncthreads();
+                const uint32_t tag_arg = ++ep;
+                if (tid == 0) {
+                    for (int q = 1; q < MWARP; q++) {
+                        const float ov = sm.bestv[q];
+                        const int oi = sm.besti[q];
+                        if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
+                    }
+                    ll_store(P.x_arg + 2 * cta, __float_as_uint(best), tag_arg);
+                    ll_store(P.x_arg + 2 * cta + 1, (uint32_t)arg, tag_arg);
+                }
+                exp_arg += G;
+                xwait(P.cnt + CNT_ARG * CNT_STRIDE, P.cnt + CNT_ARG * CNT_STRIDE, exp_arg, P.dbg);
+                if (tid < 32) {
+                    float bv = -INFINITY;
+                    int bi = 0x7fffffff;
+                    for (int q = tid; q < G; q += 32) {
+                        uint32_t a, b;
+                        ll_wait2(P.x_arg + 2 * q, tag_arg, a, b, P.dbg);
+                        const float ov = __uint_as_float(a);
+                        const int oi = (int)b;
+                        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                    }
+                    if (tid == 0) sm.besti[0] = (bi == 0x7fffffff) ? 0 : bi;   // all -inf/NaN: the reference leaves index 0
+                }
+                __syncthreads();
+                next_tok = sm.besti[0];
+                __syncthreads();
+                n_gen++;
+                if (cta == 0 && tid == 0) P.tokens[pos + 1] = next_tok;
+                if (next_tok == P.eos_id) stop = 1;
+                MEGA_PROF();
             }
-            __syncthreads();
-            next_tok = sm.besti[0];
-            __syncthreads();
-            n_gen++;
-            if (c.cta == 0 && tid == 0) P.tokens[pos + 1] = next_tok;
-            if (next_tok == P.eos_id) { stop = 1; pos++; break; }
-            MEGA_PROF();
-        } else {
-            next_tok = -1;
         }
     }
-    if (c.cta == 0 && tid == 0) {
+    if (cta == 0 && tid == 0) {
         P.st->pos = pos;
         P.st->n_gen += n_gen;
         if (stop) P.st->stop = 1;
-        *P.epoch = c.ep;
+        *P.epoch = ep;
     }
 }
 
