@@ -189,7 +189,8 @@ def main():
         n_prompt = 128
         max_ctx = n_prompt + K + Wm - 1
     t_setup = time.time()
-    eng = capi.Engine(cfg, max_ctx + 1, wdt).load(W.synth_weights(cfg, wdt, seed=1))
+    eng = capi.Engine(cfg, max_ctx, wdt).load(W.synth_weights(cfg, wdt, seed=1))
+    assert eng.uses_megakernel(), "bench must run the persistent-kernel path"
     prompt = W.synth_prompt(7 + rank, n_prompt, cfg.n_vocab)       # disjoint sequences per replica
     stream = torch.cuda.ExternalStream(capi.stream_handle(), device=torch.device("cuda", local))
     hbm_peak, peak_src = measured_peaks()

@@ -122,7 +122,13 @@ int gtb_engine_acv(gtb_engine_t e, int layer, int acv_id, float* h_out, int* wid
 int gtb_engine_set_option(gtb_engine_t e, const char* name, int value);
 /* "prof": globaltimer stamps (ns) taken by CTA 0 at every phase boundary of the last processed row */
 int gtb_engine_read_prof(gtb_engine_t e, long long* h_out, int count);
+/* 1 if rows run in the persistent kernel (TinyLlama dimensions, max_ctx <= 2048, grid >= 128), 0 if one kernel per phase */
+int gtb_engine_uses_megakernel(gtb_engine_t e, int* yes);
 int gtb_engine_weight_bytes(gtb_engine_t e, size_t* nbytes);
+/* self-test: the persistent kernel's parallel emulation of the reference's strictly in-order fp32 sum
+ * (gten/ops.h:765-767, 982-988) on n non-negative host terms; h_out[0] must equal the sequential sum bit for bit,
+ * h_out[1..4] receive the SM cycles of four back-to-back evaluations (cold and warm instruction cache) */
+int gtb_selftest_exact_sum(const float* h_terms, int n, float* h_out);
 
 #ifdef __cplusplus
 }

@@ -149,6 +149,33 @@ def test_rms_norm_exact_sum_adversarial(capi, checker):
         assert not bad, (adt, bad)
 
 
+def test_megakernel_exact_sum_adversarial(capi):
+    """The persistent kernel's own parallel exact sum against numpy's sequential float32 accumulation."""
+    rng = np.random.default_rng(11)
+    cases = []
+    for n in (1, 3, 4, 5, 31, 64, 129, 300, 1000, 2047, 2048, 2049, 4096, 5000):
+        cases.append(np.abs(rng.standard_normal(n)).astype(np.float32) ** 2)
+        cases.append(np.exp(rng.standard_normal(n) * 3 - 4).astype(np.float32))
+    n = 2048
+    for _ in range(6):
+        cases.append(np.ldexp(rng.integers(1, 5, n).astype(np.float64), -rng.integers(0, 6, n)).astype(np.float32))       # ties
+        cases.append(np.where(rng.random(n) < 0.3, 0.0, np.abs(rng.standard_normal(n)) * np.ldexp(1.0, rng.integers(-20, 20, n))).astype(np.float32))
+        cases.append((np.abs(rng.standard_normal(n)) * np.ldexp(1.0, rng.integers(-8, 8))).astype(np.float32))
+        q = rng.integers(-127, 128, n).astype(np.float32) * np.float32(np.float16(rng.random() * 0.05))
+        cases.append((q * q).astype(np.float32))                                                                           # squares of Q8 values
+    cases += [np.full(n, 1.0, np.float32), np.concatenate([np.full(1, 300.0), np.full(n - 1, 1e-3)]).astype(np.float32),
+              np.concatenate([np.full(n - 1, 1e-3), np.full(1, 300.0)]).astype(np.float32), np.zeros(n, np.float32),
+              np.full(n, 1e-40, np.float32), np.full(n, 3e38 / n, np.float32)]
+    z = np.zeros(n, np.float32); z[rng.integers(0, n, 5)] = np.abs(rng.standard_normal(5)) * 10
+    cases.append(z)
+    for i, t in enumerate(cases):
+        want = np.float32(0.0)
+        for v in t:
+            want = np.float32(want + v)
+        got = capi.selftest_exact_sum(t)
+        assert got.view(np.uint32) == want.view(np.uint32), (i, t.size, got, want)
+
+
 @pytest.mark.parametrize("wdt", [Q4, Q8, F16])
 def test_token_embed(capi, checker, wdt):
     rng = np.random.default_rng(9)

@@ -27,7 +27,7 @@ SYMBOLS = [
     "gtb_qkv_attn", "gtb_engine_create", "gtb_engine_destroy", "gtb_engine_set_weight", "gtb_engine_load_gten",
     "gtb_engine_logits", "gtb_engine_generate", "gtb_engine_reset", "gtb_engine_prefill", "gtb_engine_decode",
     "gtb_engine_position", "gtb_engine_read_tokens", "gtb_engine_read_logits", "gtb_engine_acv",
-    "gtb_engine_set_option", "gtb_engine_weight_bytes", "gtb_engine_read_prof",
+    "gtb_engine_set_option", "gtb_engine_weight_bytes", "gtb_engine_read_prof", "gtb_selftest_exact_sum", "gtb_engine_uses_megakernel",
 ]
 
 
@@ -74,7 +74,7 @@ def lib():
             "gtb_engine_position": [vp, C.POINTER(i)], "gtb_engine_read_tokens": [vp, vp, i, i],
             "gtb_engine_read_logits": [vp, vp], "gtb_engine_acv": [vp, i, i, vp, C.POINTER(i)],
             "gtb_engine_set_option": [vp, C.c_char_p, i], "gtb_engine_weight_bytes": [vp, C.POINTER(sz)],
-            "gtb_engine_read_prof": [vp, vp, i],
+            "gtb_engine_read_prof": [vp, vp, i], "gtb_selftest_exact_sum": [vp, i, vp], "gtb_engine_uses_megakernel": [vp, C.POINTER(C.c_int)],
         }
         for name, args in sigs.items():
             fn = getattr(L, name)
@@ -261,6 +261,15 @@ def qkv_attn(q, k, v, dtype, n_ctx, n_heads, n_kv, d_head, max_ctx, start_pos=0)
 
 
 # ---- engine -----------------------------------------------------------------------------------------
+def selftest_exact_sum(terms, cycles: bool = False):
+    terms = np.ascontiguousarray(terms, np.float32)
+    out = np.zeros(8, np.float32)
+    check(lib().gtb_selftest_exact_sum(_hp(terms), terms.size, _hp(out)))
+    if cycles:
+        return out[0], out[1:5].copy()
+    return out[0]
+
+
 class Engine:
     """TinyLlama{max_ctx, dtype} resident on the GPU (tinyllama.cpp:23-76)."""
 
@@ -338,6 +347,11 @@ class Engine:
         w = C.c_int()
         check(lib().gtb_engine_acv(self.h, layer, aid, _hp(out), C.byref(w)))
         return out[: w.value].copy()
+
+    def uses_megakernel(self) -> bool:
+        y = C.c_int()
+        check(lib().gtb_engine_uses_megakernel(self.h, C.byref(y)))
+        return bool(y.value)
 
     def read_prof(self, count: int) -> np.ndarray:
         out = np.zeros(count, np.int64)

@@ -4,6 +4,7 @@
 // the library stream; position / token live in device memory so a captured CUDA graph replays every row
 // and the greedy loop (tinyllama.cpp:395-440) never returns to the host between tokens.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <fstream>
@@ -239,6 +240,23 @@ __global__ void __launch_bounds__(1024) k_argmax_advance(const float* __restrict
 __global__ void k_advance(DevState* st) { st->pos += 1; }
 
 // ---------------------------------------------------------------- host side
+// self-test of the megakernel's exact in-order sum on arbitrary terms (one CTA of MT threads)
+__global__ void __launch_bounds__(MT) k_selftest_exact_sum(const float* __restrict__ terms, int n, float* out) {
+    __shared__ ExactSum2Smem es;
+    float r = 0.0f;
+    for (int rep = 0; rep < 4; rep++) {          // repetitions 1..3 run with warm instruction caches: out[1 + rep] = cycles
+        __syncthreads();
+        const long long t0 = clock64();
+        r = exact_sum512([&](int i, float q[4]) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) q[u] = (i + u < n) ? terms[i + u] : 0.0f;
+        }, n, es);
+        const long long t1 = clock64();
+        if (threadIdx.x == 0) out[1 + rep] = (float)(t1 - t0);
+    }
+    if (threadIdx.x == 0) *out = r;
+}
+
 struct LayerW {
     gtb_weight_t q = nullptr, k = nullptr, v = nullptr, o = nullptr, gate = nullptr, up = nullptr, down = nullptr;
     uint16_t* attn_norm = nullptr;
@@ -435,7 +453,7 @@ bool mega_ok(const gtb_engine* e) {
     // the persistent kernel is specialised for the TinyLlama dimensions (tinyllama.cpp:12-20); anything else takes
     // the one-kernel-per-phase path
     return e->use_mega && !e->capture && c.n_embd == ME && c.n_ffn == MF && c.n_heads == MH && c.n_groups * MGSZ == MH &&
-           e->grid >= MH * 4 && e->grid <= 1024 && attn_scratch_bytes(e->adtype, c.max_ctx) <= (size_t)PS_BYTES;
+           e->grid >= MH * 4 && e->grid <= 1024 && c.max_ctx <= 4 * MT && attn_scratch_bytes(c.max_ctx) <= (size_t)PS_BYTES;
 }
 
 template <int WT>
@@ -879,11 +897,35 @@ int gtb_engine_set_option(gtb_engine_t e, const char* name, int value) {
     return fail(GTB_ERR_ARG, "unknown option %s", name);
 }
 
+int gtb_engine_uses_megakernel(gtb_engine_t e, int* yes) {
+    GTB_ARG(e && yes);
+    *yes = mega_ok(e) ? 1 : 0;
+    return GTB_OK;
+}
+
 int gtb_engine_read_prof(gtb_engine_t e, long long* h_out, int count) {
     GTB_CHECK_INIT();
     GTB_ARG(e && h_out && count > 0 && count <= PROF_SLOTS);
     GTB_CUDA(cudaMemcpyAsync(h_out, e->d_prof, (size_t)count * 8, cudaMemcpyDeviceToHost, ctx().stream));
     GTB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return GTB_OK;
+}
+
+int gtb_selftest_exact_sum(const float* h_terms, int n, float* h_out) {
+    GTB_CHECK_INIT();
+    GTB_ARG(h_terms && h_out && n > 0 && n <= (1 << 20));
+    float *d = nullptr, *o = nullptr;
+    GTB_CUDA(cudaMalloc((void**)&d, (size_t)n * 4));
+    GTB_CUDA(cudaMalloc((void**)&o, 32));
+    cudaError_t ce = cudaMemcpyAsync(d, h_terms, (size_t)n * 4, cudaMemcpyHostToDevice, ctx().stream);
+    if (ce == cudaSuccess) {
+        k_selftest_exact_sum<<<1, MT, 0, ctx().stream>>>(d, n, o);
+        ctx().launches++;
+        ce = cudaMemcpyAsync(h_out, o, 20, cudaMemcpyDeviceToHost, ctx().stream);
+    }
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx().stream);
+    cudaFree(d); cudaFree(o);
+    if (ce != cudaSuccess) return fail(GTB_ERR_CUDA, "exact-sum self-test failed: %s", cudaGetErrorString(ce));
     return GTB_OK;
 }
 

@@ -40,7 +40,7 @@ constexpr int MT = 512;                    // threads per CTA
 constexpr int MWARP = MT / 32;
 constexpr int ME = 2048, MF = 5632, MKV = 256, MH = 32, MGSZ = 8;     // TinyLLamaParams, tinyllama.cpp:12-20
 constexpr int NBE = ME / 32, NBF = MF / 32;
-constexpr int PS_BYTES = 84 * 1024;        // product staging (also the attention scratch)
+constexpr int PS_BYTES = 140 * 1024;       // product staging; during attention: scores + the unit's V slice as fp32
 constexpr int IT_Q4 = 10;                  // (row, block) items per thread per tile: MT*IT items in registers
 constexpr int IT_Q8 = 5;
 constexpr int SPIN_LIMIT = 1 << 24;        // ~ seconds; a stuck exchange traps instead of hanging the GPU
@@ -232,9 +232,23 @@ __device__ __forceinline__ void stage_quad(const ActView& av, const float x[4]) 
 // ---------------------------------------------------------------- exact in-order sum, 512 threads x 4 elements per pass
 // Same algorithm as exact_sum_block (gtb_dev.cuh), restructured: cross-warp prefixes are 16-lane shuffle scans,
 // four barriers per pass, the serial resolve reads its items with 128-bit loads.
+// branch-free map of "add t to a running sum whose binade is e" (e >= exponent of t; t normal, or zero -> identity)
+__device__ __forceinline__ PMap pmap_of2(float tv, int e) {
+    const uint32_t tb = __float_as_uint(tv);
+    const int sh = min(e - ((int)(tb >> 23) - 127), 25);
+    const uint32_t mt = (tb & 0x7fffffu) | 0x800000u;
+    const uint32_t k = mt >> sh;
+    const uint32_t rem2 = (mt & ((1u << sh) - 1u)) << 1, full = 1u << sh;
+    const uint32_t up = rem2 > full ? 1u : 0u, tie = rem2 == full ? 1u : 0u;
+    PMap m;
+    m.a = k + (up | (tie & k & 1u));
+    m.b = k + (up | (tie & ~k & 1u));
+    return m;
+}
+
 constexpr int ES2_MAXEXP = 96;
 struct ExactSum2Smem {
-    double wsum[MWARP];
+    float wsum[MWARP];
     PMap wtail[MWARP];
     int wflag[MWARP];
     int wcnt[MWARP];
@@ -242,48 +256,71 @@ struct ExactSum2Smem {
     float result;
 };
 
-template <typename LoadT>
-__device__ __forceinline__ float exact_sum512(LoadT load4, int n, ExactSum2Smem& sm) {
+struct NoSpill { __device__ __forceinline__ void operator()() const {} };
+
+// load4(i, q): the four terms starting at element i (i % 4 == 0; elements >= n come back as 0).  In the normal path
+// every thread asks only for its own i = 4 * tid (+ pass offset); the serial fallback makes thread 0 ask for every i,
+// so a caller that keeps its terms in registers passes `spill`, which writes them where load4 can find them.
+template <typename LoadT, typename SpillT = NoSpill>
+__device__ __forceinline__ float exact_sum512(LoadT load4, int n, ExactSum2Smem& sm, SpillT spill = SpillT()) {
+    // No FP64 here: the prefix sums that locate the running sum's binade are plain fp32 scans.  Terms are
+    // non-negative, so a sum taken through any addition tree of depth d is within d * 2^-24 (relative) of the exact
+    // one (d <= 16 here), and the strictly sequential chain being emulated is within k * 2^-24 of exact after k
+    // terms; the allowance below, (4k + 64) * 2^-24, covers both with room to spare.
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     float s_run = 0.0f;
-    double carry = 0.0;
+    float carry = 0.0f;
     for (int p0 = 0; p0 < n; p0 += MT * 4) {
         const int i0 = p0 + tid * 4;
         float tv[4];
         load4(i0, tv);                                     // elements >= n must come back as 0
-        const double loc = ((double)tv[0] + (double)tv[1]) + ((double)tv[2] + (double)tv[3]);
-        double inc = loc;
+        const float loc = __fadd_rn(__fadd_rn(tv[0], tv[1]), __fadd_rn(tv[2], tv[3]));
+        float inc = loc;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+        for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = __fadd_rn(inc, v); }
+        const float lane_pre = __shfl_up_sync(0xffffffffu, inc, 1);   // prefix of the lanes before this one
         if (lane == 31) sm.wsum[wid] = inc;
         __syncthreads();                                   // (1)
-        double ws = (lane < MWARP) ? sm.wsum[lane] : 0.0;
+        float ws = (lane < MWARP) ? sm.wsum[lane] : 0.0f;
 #pragma unroll
-        for (int o = 1; o < MWARP; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += v; }
-        const double wbase = __shfl_sync(0xffffffffu, ws, (wid + 31) & 31);      // inclusive total of warp wid-1
-        const double total_d = __shfl_sync(0xffffffffu, ws, MWARP - 1);
-        // A differs from a strictly sequential double sum only in its last bits: the drift allowance of the float
-        // chain below (2^-22 * index) dwarfs that.
-        double A = carry + ((wid > 0) ? wbase : 0.0) + (inc - loc);
+        for (int o = 1; o < MWARP; o <<= 1) { const float v = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws = __fadd_rn(ws, v); }
+        const float wbase = __shfl_sync(0xffffffffu, ws, (wid + 31) & 31);       // inclusive total of warp wid-1
+        const float total_f = __shfl_sync(0xffffffffu, ws, MWARP - 1);
+        float A = __fadd_rn(__fadd_rn(carry, (wid > 0) ? wbase : 0.0f), (lane > 0) ? lane_pre : 0.0f);
         PMap em[4];
         uint32_t exmask = 0;
+        {
+            // fast path: the running sum stays inside one binade from before the first to after the last of the four
+            const float rel4 = (float)(i0 + 20) * 0x1p-22f;
+            const float A4 = __fadd_rn(A, loc);
+            const float lo4 = __fsub_rn(A, __fmul_rn(A, rel4)), hi4 = __fadd_rn(A4, __fmul_rn(A4, rel4));
+            const int eL4 = (int)(__float_as_uint(lo4) >> 23) - 127;
+            bool fast = (lo4 > 0x1p-100f) && (eL4 == (int)(__float_as_uint(hi4) >> 23) - 127);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const double An = A + (double)tv[j];
-            em[j] = PMap{0u, 0u};
-            if (tv[j] != 0.0f) {
-                const double rel = (double)(i0 + j + 8) * 0x1p-22;
-                const double lo = A - A * rel, hi = An + An * rel;
-                bool ex = !(lo > 0x1p-100);
-                if (!ex) {
-                    const int eL = dexp(lo), eU = dexp(hi);
-                    const uint32_t tb = __float_as_uint(tv[j]);
-                    if (eL != eU || (tb >> 23) == 0u || ((int)(tb >> 23) - 127) > eL) ex = true;
-                    else em[j] = pmap_of(tv[j], eL);
-                }
-                if (ex) exmask |= 1u << j;
+            for (int j = 0; j < 4; j++) {
+                const uint32_t tb = __float_as_uint(tv[j]);
+                if (tv[j] != 0.0f && ((tb >> 23) == 0u || ((int)(tb >> 23) - 127) > eL4)) fast = false;
             }
-            A = An;
+            if (fast) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) em[j] = pmap_of2(tv[j], eL4);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float An = __fadd_rn(A, tv[j]);
+                    em[j] = PMap{0u, 0u};
+                    if (tv[j] != 0.0f) {
+                        const float rel = (float)(i0 + j + 16) * 0x1p-22f;
+                        const float lo = __fsub_rn(A, __fmul_rn(A, rel)), hi = __fadd_rn(An, __fmul_rn(An, rel));
+                        const int eL = (int)(__float_as_uint(lo) >> 23) - 127, eU = (int)(__float_as_uint(hi) >> 23) - 127;
+                        const uint32_t tb = __float_as_uint(tv[j]);
+                        const bool ex = !(lo > 0x1p-100f) || eL != eU || (tb >> 23) == 0u || ((int)(tb >> 23) - 127) > eL;
+                        if (ex) exmask |= 1u << j;
+                        else em[j] = pmap_of2(tv[j], eL);
+                    }
+                    A = An;
+                }
+            }
         }
         const int nexp = __popc(exmask);
         // per-thread pieces: maps between explicit elements
@@ -344,6 +381,8 @@ __device__ __forceinline__ float exact_sum512(LoadT load4, int n, ExactSum2Smem&
         // composition of everything since the last explicit element before this warp
         const PMap wpre = (wid > 0) ? PMap{wpa, wpb} : PMap{0u, 0u};
         if (total > ES2_MAXEXP) {                          // pathological input: plain serial chain (still exact)
+            spill();
+            __syncthreads();
             if (tid == 0) {
                 float s = s_run;
                 const int hi_i = min(n, p0 + MT * 4);
@@ -357,7 +396,7 @@ __device__ __forceinline__ float exact_sum512(LoadT load4, int n, ExactSum2Smem&
             }
             __syncthreads();
             s_run = sm.result;
-            carry += total_d;
+            carry = __fadd_rn(carry, total_f);
             __syncthreads();
             continue;
         }
@@ -382,29 +421,39 @@ __device__ __forceinline__ float exact_sum512(LoadT load4, int n, ExactSum2Smem&
         if (tid == MT - 1) sm.item[2 * total] = make_uint4(incl.a, incl.b, 0u, 0u);
         __syncthreads();                                   // (3)
         if (tid == 0) {
+            // items alternate: map, explicit element, map, ..., map
             uint32_t sb = __float_as_uint(s_run);
-            const int nq = 2 * total + 1;
-            int q = 0;
-            for (; q + 4 <= nq; q += 4) {
-                uint4 it[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) it[u] = sm.item[q + u];
+            {
+                const uint4 m0 = sm.item[0];
+                sb += (sb & 1u) ? m0.y : m0.x;
+            }
+            int k = 0;
+            for (; k + 4 <= total; k += 4) {
+                uint32_t tt[4];
+                uint2 mm[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    if (it[u].z) sb = __float_as_uint(__fadd_rn(__uint_as_float(sb), __uint_as_float(it[u].x)));
-                    else sb += (sb & 1u) ? it[u].y : it[u].x;
+                    tt[u] = sm.item[2 * (k + u) + 1].x;
+                    const uint4 m = sm.item[2 * (k + u) + 2];
+                    mm[u] = make_uint2(m.x, m.y);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    sb = __float_as_uint(__fadd_rn(__uint_as_float(sb), __uint_as_float(tt[u])));
+                    sb += (sb & 1u) ? mm[u].y : mm[u].x;
                 }
             }
-            for (; q < nq; q++) {
-                const uint4 it = sm.item[q];
-                if (it.z) sb = __float_as_uint(__fadd_rn(__uint_as_float(sb), __uint_as_float(it.x)));
-                else sb += (sb & 1u) ? it.y : it.x;
+            for (; k < total; k++) {
+                const uint32_t t1 = sm.item[2 * k + 1].x;
+                const uint4 m = sm.item[2 * k + 2];
+                sb = __float_as_uint(__fadd_rn(__uint_as_float(sb), __uint_as_float(t1)));
+                sb += (sb & 1u) ? m.y : m.x;
             }
             sm.result = __uint_as_float(sb);
         }
         __syncthreads();                                   // (4)
         s_run = sm.result;
-        carry += total_d;
+        carry = __fadd_rn(carry, total_f);
     }
     return s_run;
 }
@@ -516,7 +565,10 @@ __device__ __forceinline__ float4 block_products_r(const uint4& wa, const uint4&
         l2 = __dp4a((int)wb.z, (int)ay.z, __dp4a((int)wa.z, (int)ax.z, 0));
         l3 = __dp4a((int)wb.w, (int)ay.w, __dp4a((int)wa.w, (int)ax.w, 0));
     }
-    return make_float4(__fmul_rn((float)l0, s), __fmul_rn((float)l1, s), __fmul_rn((float)l2, s), __fmul_rn((float)l3, s));
+    // int -> float without the conversion pipe (|lane sum| < 2^22): bits(1.5 * 2^23) + l, minus 1.5 * 2^23
+    const float f0 = __fsub_rn(__int_as_float(0x4b400000 + l0), 12582912.0f), f1 = __fsub_rn(__int_as_float(0x4b400000 + l1), 12582912.0f);
+    const float f2 = __fsub_rn(__int_as_float(0x4b400000 + l2), 12582912.0f), f3 = __fsub_rn(__int_as_float(0x4b400000 + l3), 12582912.0f);
+    return make_float4(__fmul_rn(f0, s), __fmul_rn(f1, s), __fmul_rn(f2, s), __fmul_rn(f3, s));
 }
 
 template <int WT>
@@ -701,22 +753,21 @@ __device__ __forceinline__ float mega_score(const MegaSm& sm, const MegaLayer& L
 
 // attention scratch carved from the product staging area
 struct AttnScratch {
-    float* sc;          // [max_ctx + 32] scores / probabilities
-    uint8_t* vb;        // Q8: int8 [max_ctx][16]; F16: half [max_ctx][16]
-    float* vd;          // Q8: block scale of the slice per position
+    float* sc;          // [max_ctx + 32] probabilities
+    float* vf;          // [max_ctx][16] the unit's V slice, decoded (exact: 7-bit code x fp16 scale, or fp16)
 };
-__device__ __forceinline__ AttnScratch attn_scratch(int at, float* ps, int max_ctx) {
+__device__ __forceinline__ AttnScratch attn_scratch(float* ps, int max_ctx) {
     AttnScratch a;
     a.sc = ps;
-    const size_t o1 = (size_t)((max_ctx + 32 + 3) & ~3) * 4;
-    a.vb = reinterpret_cast<uint8_t*>(ps) + o1;
-    const size_t o2 = o1 + (size_t)max_ctx * (at == DT_F16 ? 32 : 16);
-    a.vd = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ps) + o2);
+    a.vf = ps + ((max_ctx + 32 + 3) & ~3);
     return a;
 }
-__host__ __device__ inline size_t attn_scratch_bytes(int at, int max_ctx) {
-    return (size_t)((max_ctx + 32 + 3) & ~3) * 4 + (size_t)max_ctx * (at == DT_F16 ? 32 : 16) + (size_t)max_ctx * 4 + 64;
+__host__ __device__ inline size_t attn_scratch_bytes(int max_ctx) {
+    return (size_t)((max_ctx + 32 + 3) & ~3) * 4 + (size_t)max_ctx * 64 + 64;
 }
+
+// K row of one cached position for group g, as loaded from the cache (Q8: 64 permuted codes + 2 scales)
+struct KRow { uint4 x0, y0, x1, y1; uint32_t s0, s1; };
 
 // P2a: re-encode / RoPE the unit's q, k, v (gten/ops.h:645-646, 733-753), append K/V, publish the scores of quarter j
 template <int AT>
@@ -725,18 +776,48 @@ __device__ __forceinline__ void mega_attn_a(const MegaParams& P, const MegaLayer
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int h = cta >> 2, j = cta & 3, g = h / MGSZ;
     const bool writer = (h % MGSZ) == 0 && j == 0;
-    const AttnScratch as = attn_scratch(AT, ps, P.max_ctx);
-    // this unit's V slice (16 channels) of every cached position: independent of the exchange, issue first
+    const AttnScratch as = attn_scratch(ps, P.max_ctx);
+    const int per = (pos + 4) >> 2;
+    const int lo = j * per, hi = min(pos + 1, lo + per);
+    // Everything that does not depend on this row's q/k/v is issued before the exchange is waited for:
+    // (1) the K row of this thread's score position (registers), (2) the unit's V slice, decoded into shared memory.
+    const int k0 = lo + tid;
+    KRow kr;
+    if (AT != DT_F16 && k0 < hi && k0 != pos) {
+        const uint4* kp = reinterpret_cast<const uint4*>(L.kq + (size_t)k0 * MKV + g * 64);
+        kr.x0 = __ldcg(kp); kr.y0 = __ldcg(kp + 1); kr.x1 = __ldcg(kp + 2); kr.y1 = __ldcg(kp + 3);
+        kr.s0 = __ldcg(L.ks + (size_t)k0 * (MKV / 32) + g * 2);
+        kr.s1 = __ldcg(L.ks + (size_t)k0 * (MKV / 32) + g * 2 + 1);
+    }
     {
         const int ch0 = g * 64 + j * 16;
         for (int i = tid; i < pos; i += MT) {
+            float4* dst = reinterpret_cast<float4*>(as.vf + (size_t)i * 16);
             if (AT == DT_F16) {
                 const uint4* vp = reinterpret_cast<const uint4*>(L.vq + ((size_t)i * MKV + ch0) * 2);
-                reinterpret_cast<uint4*>(as.vb)[i * 2] = __ldcg(vp);
-                reinterpret_cast<uint4*>(as.vb)[i * 2 + 1] = __ldcg(vp + 1);
+                const uint4 a = __ldcg(vp), b = __ldcg(vp + 1);
+                const __half2* ha = reinterpret_cast<const __half2*>(&a);
+                const __half2* hb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const float2 p0 = __half22float2(ha[2 * u]), p1 = __half22float2(ha[2 * u + 1]);
+                    const float2 q0 = __half22float2(hb[2 * u]), q1 = __half22float2(hb[2 * u + 1]);
+                    dst[u] = make_float4(p0.x, p0.y, p1.x, p1.y);
+                    dst[2 + u] = make_float4(q0.x, q0.y, q1.x, q1.y);
+                }
             } else {
-                reinterpret_cast<uint4*>(as.vb)[i] = __ldcg(reinterpret_cast<const uint4*>(L.vq + (size_t)i * MKV + ch0));
-                as.vd[i] = h2f(__ldcg(L.vs + (size_t)i * (MKV / 32) + g * 2 + (j >> 1)));
+                const uint4 c = __ldcg(reinterpret_cast<const uint4*>(L.vq + (size_t)i * MKV + ch0));
+                const float d = h2f(__ldcg(L.vs + (size_t)i * (MKV / 32) + g * 2 + (j >> 1)));
+                const uint32_t cw[4] = {c.x ^ 0x80808080u, c.y ^ 0x80808080u, c.z ^ 0x80808080u, c.w ^ 0x80808080u};
+#pragma unroll
+                for (int u = 0; u < 4; u++) {                      // value = code * delta (ops.h:1026), exact in fp32
+                    // int8 -> float without the conversion pipe: (2^23 + 128 + code) - (2^23 + 128)
+                    const float f0 = __fsub_rn(__uint_as_float(__byte_perm(cw[u], 0x4b000000u, 0x7650)), 8388736.0f);
+                    const float f1 = __fsub_rn(__uint_as_float(__byte_perm(cw[u], 0x4b000000u, 0x7651)), 8388736.0f);
+                    const float f2 = __fsub_rn(__uint_as_float(__byte_perm(cw[u], 0x4b000000u, 0x7652)), 8388736.0f);
+                    const float f3 = __fsub_rn(__uint_as_float(__byte_perm(cw[u], 0x4b000000u, 0x7653)), 8388736.0f);
+                    dst[u] = make_float4(__fmul_rn(f0, d), __fmul_rn(f1, d), __fmul_rn(f2, d), __fmul_rn(f3, d));
+                }
             }
         }
     }
@@ -756,21 +837,22 @@ __device__ __forceinline__ void mega_attn_a(const MegaParams& P, const MegaLayer
         const int sl = ch - j * 16;                            // channel inside this unit's P.V slice
         if (which < 2) {
             sm.tmp[wid][lane] = roundtrip<AT>(x);
-        } else if (AT == DT_F16) {
-            const uint16_t hb = f2h(x);
-            sm.vf[ch] = h2f(hb);
-            if (sl >= 0 && sl < 16) reinterpret_cast<uint16_t*>(as.vb)[pos * 16 + sl] = hb;
-            if (writer) reinterpret_cast<uint16_t*>(L.vq)[(size_t)pos * MKV + g * 64 + ch] = hb;
         } else {
-            uint16_t dh;
-            const int q = q8_encode_lane(x, &dh);
-            sm.vf[ch] = __fmul_rn((float)q, h2f(dh));
-            if (sl >= 0 && sl < 16) as.vb[pos * 16 + sl] = (uint8_t)(int8_t)q;
-            if (lane == 0 && half == (j >> 1)) as.vd[pos] = h2f(dh);
-            if (writer) {
-                L.vq[(size_t)pos * MKV + g * 64 + ch] = (uint8_t)(int8_t)q;
-                if (lane == 0) L.vs[(size_t)pos * (MKV / 32) + g * 2 + half] = dh;
+            float d;
+            if (AT == DT_F16) {
+                const uint16_t hb = f2h(x);
+                d = h2f(hb);
+                if (writer) reinterpret_cast<uint16_t*>(L.vq)[(size_t)pos * MKV + g * 64 + ch] = hb;
+            } else {
+                uint16_t dh;
+                const int q = q8_encode_lane(x, &dh);
+                d = __fmul_rn((float)q, h2f(dh));
+                if (writer) {
+                    L.vq[(size_t)pos * MKV + g * 64 + ch] = (uint8_t)(int8_t)q;
+                    if (lane == 0) L.vs[(size_t)pos * (MKV / 32) + g * 2 + half] = dh;
+                }
             }
+            if (sl >= 0 && sl < 16) as.vf[(size_t)pos * 16 + sl] = d;      // this row's own v is not read back from the cache
         }
     }
     __syncthreads();
@@ -808,75 +890,92 @@ __device__ __forceinline__ void mega_attn_a(const MegaParams& P, const MegaLayer
     }
     __syncthreads();
     // scores of this unit's quarter of the positions, scaled by 1/sqrt(64) (exactly 0.125)
-    const int per = (pos + 4) >> 2;
-    const int lo = j * per, hi = min(pos + 1, lo + per);
     ull* dst = P.x_sc + (size_t)h * P.sc_stride;
-    for (int k = lo + tid; k < hi; k += MT) {
-        const float s = __fmul_rn(mega_score<AT>(sm, L, g, k, pos), 0.125f);
-        ll_store(dst + k, __float_as_uint(s), tag_sc);
+    for (int k = k0; k < hi; k += MT) {
+        float d;
+        if (AT != DT_F16 && k == k0 && k != pos) {
+            // gten/ops.h:224-292 on the prefetched row
+            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int bi = 0; bi < 2; bi++) {
+                const uint4 kx = bi ? kr.x1 : kr.x0, ky = bi ? kr.y1 : kr.y0;
+                const float s = __fmul_rn(sm.qd[bi], h2f((uint16_t)(bi ? kr.s1 : kr.s0)));
+                const uint32_t* q = sm.qw + bi * 8;
+                const int l0 = __dp4a((int)ky.x, (int)q[4], __dp4a((int)kx.x, (int)q[0], 0));
+                const int l1 = __dp4a((int)ky.y, (int)q[5], __dp4a((int)kx.y, (int)q[1], 0));
+                const int l2 = __dp4a((int)ky.z, (int)q[6], __dp4a((int)kx.z, (int)q[2], 0));
+                const int l3 = __dp4a((int)ky.w, (int)q[7], __dp4a((int)kx.w, (int)q[3], 0));
+                acc[0] = __fadd_rn(acc[0], __fmul_rn((float)l0, s));
+                acc[1] = __fadd_rn(acc[1], __fmul_rn((float)l1, s));
+                acc[2] = __fadd_rn(acc[2], __fmul_rn((float)l2, s));
+                acc[3] = __fadd_rn(acc[3], __fmul_rn((float)l3, s));
+            }
+            d = __fadd_rn(__fadd_rn(acc[0], acc[1]), __fadd_rn(acc[2], acc[3]));
+        } else {
+            d = mega_score<AT>(sm, L, g, k, pos);
+        }
+        ll_store(dst + k, __float_as_uint(__fmul_rn(d, 0.125f)), tag_sc);
     }
 }
 
-// P2b: softmax over the whole row (gten/ops.h:967-996), then P.V for the unit's 16 channels (ops.h:1046-1087)
+// P2b: softmax over the whole row (gten/ops.h:967-996), then P.V for the unit's 16 channels (ops.h:1046-1087).
+// Thread t owns positions 4t .. 4t+3 (max_ctx <= 4 * MT): scores, exponentials and probabilities stay in registers.
 template <int AT>
-__device__ __forceinline__ void mega_attn_b(const MegaParams& P, MegaSm& sm, float* ps, int cta, int pos, int n_ctx,
+__device__ __forceinline__ void mega_attn_b(const MegaParams& P, MegaSm& sm, float* ps, float* xbuf, int cta, int pos, int n_ctx,
                                             uint32_t tag_sc, uint32_t tag_attn) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int h = cta >> 2, j = cta & 3;
-    const AttnScratch as = attn_scratch(AT, ps, P.max_ctx);
+    const AttnScratch as = attn_scratch(ps, P.max_ctx);
     float* sc = as.sc;
+    const int i0 = tid * 4;
+    float s[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};            // masked / non-existent positions (ops.h:962-964)
     {
         const ull* src = P.x_sc + (size_t)h * P.sc_stride;
-        const int n = pos + 1, n2 = n & ~1;
-        for (int i = tid * 2; i < n2; i += MT * 2) {
-            uint32_t a, b;
-            ll_wait2(src + i, tag_sc, a, b, P.dbg);
-            sc[i] = __uint_as_float(a); sc[i + 1] = __uint_as_float(b);
-        }
-        if ((n & 1) && tid == MT - 1) sc[n - 1] = __uint_as_float(ll_wait1(src + n - 1, tag_sc, P.dbg));
+        uint32_t a, b;
+        if (i0 + 1 <= pos) { ll_wait2(src + i0, tag_sc, a, b, P.dbg); s[0] = __uint_as_float(a); s[1] = __uint_as_float(b); }
+        else if (i0 == pos) s[0] = __uint_as_float(ll_wait1(src + i0, tag_sc, P.dbg));
+        if (i0 + 3 <= pos) { ll_wait2(src + i0 + 2, tag_sc, a, b, P.dbg); s[2] = __uint_as_float(a); s[3] = __uint_as_float(b); }
+        else if (i0 + 2 == pos) s[2] = __uint_as_float(ll_wait1(src + i0 + 2, tag_sc, P.dbg));
     }
-    __syncthreads();
-    float mx = -INFINITY;
-    for (int k = tid; k <= pos; k += MT) mx = fmaxf(mx, sc[k]);
-    mx = warp_max(mx);
+    float mx = warp_max(fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3])));
     if (lane == 0) sm.red[wid] = mx;
     __syncthreads();
     mx = sm.red[0];
 #pragma unroll
     for (int w = 1; w < MWARP; w++) mx = fmaxf(mx, sm.red[w]);
-    for (int k = tid; k <= pos; k += MT) sc[k] = expf_glibc(__fsub_rn(sc[k], mx));
-    __syncthreads();
-    const float sum = exact_sum512([&](int i, float q[4]) {
+    float e[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) q[u] = (i + u <= pos) ? sc[i + u] : 0.0f;
-    }, pos + 1, sm.es);
-    const int nblk = (pos + 32) / 32;
-    for (int b = wid; b < nblk; b += MWARP) {
-        const int i = b * 32 + lane;
-        const float p = (i <= pos) ? __fdiv_rn(sc[i], sum) : 0.0f;
-        const float ph = roundtrip<AT>(p);
-        __syncwarp();
-        if (i <= pos) sc[i] = ph;
-    }
+    for (int u = 0; u < 4; u++) e[u] = (i0 + u <= pos) ? expf_glibc(__fsub_rn(s[u], mx)) : 0.0f;
+    const float sum = exact_sum512([&](int i, float q[4]) {
+        if (i == i0) { q[0] = e[0]; q[1] = e[1]; q[2] = e[2]; q[3] = e[3]; }
+        else {                                               // serial fallback: thread 0 walks every element
+#pragma unroll
+            for (int u = 0; u < 4; u++) q[u] = xbuf[i + u];
+        }
+    }, pos + 1, sm.es, [&]() { *reinterpret_cast<float4*>(xbuf + i0) = make_float4(e[0], e[1], e[2], e[3]); });
+    // probabilities, re-encoded as a row (blocks of 32 positions = 8 consecutive threads); masked entries are exact zeros
+    float p[4], ph[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) p[u] = (i0 + u <= pos) ? __fdiv_rn(e[u], sum) : 0.0f;
+    roundtrip_quad<AT>(p, ph);
+    if (i0 <= pos) *reinterpret_cast<float4*>(sc + i0) = make_float4(ph[0], ph[1], ph[2], ph[3]);      // sc holds max_ctx + 32 entries
     __syncthreads();
+    // P.V: eight position-lanes (i mod 8) per channel over [0, n8), lanes summed left to right, then the tail
     const int n8 = (n_ctx / 8) * 8;
-    auto v_of = [&](int i, int cc) -> float {
-        if (AT == DT_F16) return h2f(reinterpret_cast<const uint16_t*>(as.vb)[i * 16 + cc]);
-        return __fmul_rn((float)(int8_t)as.vb[i * 16 + cc], as.vd[i]);                       // ops.h:1026
-    };
+    const float* vf = as.vf;
     if (tid < 128) {
         const int l = tid >> 4, cc = tid & 15;
         const int hi = min(n8, pos + 1);
         float a = 0.0f;
         int i = l;
-        for (; i + 24 < hi; i += 32) {
-            float p[4], v[4];
+        for (; i + 56 < hi; i += 64) {
+            float pp[8], vv[8];
 #pragma unroll
-            for (int u = 0; u < 4; u++) { p[u] = sc[i + 8 * u]; v[u] = v_of(i + 8 * u, cc); }
+            for (int u = 0; u < 8; u++) { pp[u] = sc[i + 8 * u]; vv[u] = vf[(size_t)(i + 8 * u) * 16 + cc]; }
 #pragma unroll
-            for (int u = 0; u < 4; u++) a = __fadd_rn(__fmul_rn(p[u], v[u]), a);
+            for (int u = 0; u < 8; u++) a = __fadd_rn(__fmul_rn(pp[u], vv[u]), a);
         }
-        for (; i < hi; i += 8) a = __fadd_rn(__fmul_rn(sc[i], v_of(i, cc)), a);
+        for (; i < hi; i += 8) a = __fadd_rn(__fmul_rn(sc[i], vf[(size_t)i * 16 + cc]), a);
         sm.part[l][cc] = a;
     }
     __syncthreads();
@@ -884,7 +983,7 @@ __device__ __forceinline__ void mega_attn_b(const MegaParams& P, MegaSm& sm, flo
         float d = __fadd_rn(sm.part[0][tid], sm.part[1][tid]);
 #pragma unroll
         for (int l = 2; l < 8; l++) d = __fadd_rn(d, sm.part[l][tid]);
-        for (int i = n8; i < n_ctx && i <= pos; i++) d = __fadd_rn(d, __fmul_rn(sc[i], v_of(i, tid)));
+        for (int i = n8; i < n_ctx && i <= pos; i++) d = __fadd_rn(d, __fmul_rn(sc[i], vf[(size_t)i * 16 + tid]));
         ll_store(P.x_attn + h * 64 + j * 16 + tid, __float_as_uint(d), tag_attn);
     }
 }
@@ -984,9 +1083,10 @@ __device__ __forceinline__ void mega_embed(const MegaParams& P, int tok, float r
     }
 }
 
-#define MEGA_PROF()                                                                   \
-    do {                                                                              \
-        if (P.prof && cta == 0 && threadIdx.x == 0) P.prof[prof_i++] = gtimer();      \
+// profiling stamps of CTA 0: (code, globaltimer) pairs; code = phase kind * 16 + step
+#define MEGA_PROF(code)                                                                                   \
+    do {                                                                                                  \
+        if (P.prof && cta == 0 && threadIdx.x == 0) { P.prof[prof_i++] = (code); P.prof[prof_i++] = gtimer(); } \
     } while (0)
 
 template <int WT>
@@ -1035,7 +1135,7 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
         const int nphase = with_head ? nL4 + 1 : nL4;
         next_tok = -1;
         prof_i = 0;
-        MEGA_PROF();
+        MEGA_PROF(255);
         mega_embed<WT>(P, tok, res);
         uint32_t tag_in = 0;                        // tag of the exchange the next prologue consumes
         for (int s = 0; s < nphase; s++) {
@@ -1045,6 +1145,7 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
             if (kind == 3) {
                 exp_act += NBF;
                 xwait(nullptr, P.cnt + CNT_ACT * CNT_STRIDE, exp_act, P.dbg);
+                MEGA_PROF(kind * 16 + 0);
                 mega_gather_act<AT, WT>(P, av, tag_in);
             } else {
                 float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -1063,6 +1164,7 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
                         xwait(P.cnt + CNT_DOWN * CNT_STRIDE, P.cnt + CNT_DOWN * CNT_STRIDE, exp_down, P.dbg);
                         src = P.x_down;
                     }
+                    MEGA_PROF(kind * 16 + 0);
                     uint32_t a0, a1, a2, a3;
                     ll_wait2(src + e0, tag_in, a0, a1, P.dbg);
                     ll_wait2(src + e0 + 8, tag_in, a2, a3, P.dbg);
@@ -1085,10 +1187,12 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
                     *reinterpret_cast<float2*>(xbuf + e0) = make_float2(__fmul_rn(res[0], res[0]), __fmul_rn(res[1], res[1]));
                     *reinterpret_cast<float2*>(xbuf + e0 + 8) = make_float2(__fmul_rn(res[2], res[2]), __fmul_rn(res[3], res[3]));
                     __syncthreads();
+                    MEGA_PROF(kind * 16 + 1);
                     const float sq_sum = exact_sum512([&](int i, float q[4]) {
                         const float4 v = *reinterpret_cast<const float4*>(xbuf + i);
                         q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
                     }, ME, sm.es);
+                    MEGA_PROF(kind * 16 + 2);
                     const float denom = __fadd_rn(sqrtf(__fdiv_rn(sq_sum, (float)ME)), 1e-6f);
                     float y[4];
                     y[0] = __fmul_rn(__fdiv_rn(res[0], denom), h2f((uint16_t)(nw01 & 0xffffu)));
@@ -1099,7 +1203,7 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
                 }
             }
             __syncthreads();
-            MEGA_PROF();
+            MEGA_PROF(kind * 16 + 3);
             // ---------------- GEMV
             const uint32_t tag = ++ep;
             const int r0 = sm.rr[kind][0], r1 = sm.rr[kind][1];
@@ -1127,7 +1231,7 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
             });
             pd = nx;
             tag_in = tag;
-            MEGA_PROF();
+            MEGA_PROF(kind * 16 + 4);
             // ---------------- what follows the GEMV
             if (kind == 0) {
                 const uint32_t tag_sc = ++ep;
@@ -1135,19 +1239,20 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
                 if (cta < n_units) {
                     __syncthreads();                               // product staging is reused as attention scratch
                     mega_attn_a<AT>(P, L, sm, ps, cta, pos, tag, tag_sc);
-                    MEGA_PROF();
+                    MEGA_PROF(kind * 16 + 5);
                     exp_sc += 4;
                     xwait(P.cnt + (CNT_SC0 + (cta >> 2)) * CNT_STRIDE, P.cnt + (CNT_SC0 + (cta >> 2)) * CNT_STRIDE, exp_sc, P.dbg);
-                    mega_attn_b<AT>(P, sm, ps, cta, pos, n_ctx, tag_sc, tag_attn);
+                    MEGA_PROF(kind * 16 + 6);
+                    mega_attn_b<AT>(P, sm, ps, xbuf, cta, pos, n_ctx, tag_sc, tag_attn);
                     __threadfence();                               // K/V appends visible before anything later is published
                 }
                 tag_in = tag_attn;
-                MEGA_PROF();
+                MEGA_PROF(kind * 16 + 7);
             } else if (kind == 2) {
                 const uint32_t tag_act = ++ep;
                 mega_silu<AT>(P, cta, G, tag, tag_act);
                 tag_in = tag_act;
-                MEGA_PROF();
+                MEGA_PROF(kind * 16 + 8);
             } else if (kind == 4) {
                 // argmax (tinyllama.cpp:416-424): per-CTA first maximum, exchanged, reduced identically by every CTA
 #pragma unroll
@@ -1194,7 +1299,7 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
                 n_gen++;
                 if (cta == 0 && tid == 0) P.tokens[pos + 1] = next_tok;
                 if (next_tok == P.eos_id) stop = 1;
-                MEGA_PROF();
+                MEGA_PROF(kind * 16 + 9);
             }
         }
     }

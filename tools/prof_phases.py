@@ -17,8 +17,10 @@ sys.path.insert(0, str(ROOT))
 import gtb  # noqa: E402,F401
 from tinyllama_cpp_b200 import capi, weights as W  # noqa: E402
 
-LABELS = ["P1 gather+norm (+embed)", "P1 gemv q|k|v", "P2a rope+scores", "P2b softmax+P.V", "P3 gather+encode", "P3 gemv o",
-          "P4 gather+norm", "P4 gemv gate|up", "P4b silu*up", "P5 gather act", "P5 gemv down"]
+KIND = {0: "P1 q|k|v", 1: "P3 o", 2: "P4 gate|up", 3: "P5 down", 4: "head"}
+STEP = {0: "wait for input (exchange)", 1: "LL loads + residual/encodes + squares", 2: "exact in-order sum", 3: "normalise/encode/stage (prologue done)",
+        4: "gemv (products, chain, publish)", 5: "P2a: q/k/v encode, rope, scores", 6: "P2: wait scores", 7: "P2b: softmax, P.V",
+        8: "P4b: silu*up", 9: "argmax exchange"}
 
 
 def main():
@@ -39,25 +41,27 @@ def main():
     eng.decode(4)
     eng.set_option("prof", 1)
     L = cfg.n_layers
-    n = 1 + 11 * L + 2
-    acc = np.zeros(11)
-    head = np.zeros(2)
+    agg = {}
     tot = 0.0
     for _ in range(a.steps):
         eng.decode(1)
-        t = eng.read_prof(n).astype(np.float64)
-        d = np.diff(t)
-        acc += d[: 11 * L].reshape(L, 11).mean(axis=0)
-        head += d[11 * L: 11 * L + 2]
-        tot += t[n - 1] - t[0]
-    acc /= a.steps
-    head /= a.steps
+        t = eng.read_prof(4096)
+        codes, times = t[0::2], t[1::2].astype(np.float64)
+        n = 1
+        while n < codes.size and codes[n] != 255 and times[n] >= times[n - 1] and times[n] > 0:
+            n += 1
+        for i in range(1, n):
+            agg.setdefault(int(codes[i]), []).append(times[i] - times[i - 1])
+        tot += times[n - 1] - times[0]
     tot /= a.steps
-    print(f"workload {a.workload} ctx {a.ctx}: row {tot / 1e3:.1f} us (with prof stamps)")
-    for i, nm in enumerate(LABELS):
-        print(f"  {nm:26s} {acc[i]:9.0f} ns/layer")
-    print(f"  per-layer sum              {acc.sum():9.0f} ns  x {L} = {acc.sum() * L / 1e3:.1f} us")
-    print(f"  head prologue {head[0]:.0f} ns, lm_head+argmax {head[1]:.0f} ns")
+    print(f"workload {a.workload} ctx {a.ctx}: row {tot / 1e3:.1f} us (with prof stamps), {L} layers")
+    total = 0.0
+    for code in sorted(agg):
+        v = np.array(agg[code])
+        per_row = v.sum() / a.steps
+        total += per_row
+        print(f"  {KIND[code >> 4]:11s} {STEP[code & 15]:46s} mean {v.mean():8.0f} ns  x{len(v) // a.steps:3d} = {per_row / 1e3:7.1f} us/row")
+    print(f"  sum {total / 1e3:.1f} us")
 
 
 if __name__ == "__main__":
