@@ -55,6 +55,16 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(workload: str, steps: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the kernel from the committed `ncu --set full` capture, scaled to the
+    K steps one launch of this run processes (profiles/roofline_traffic.json: bytes per step), or None."""
+    p = ROOT / "profiles" / "roofline_traffic.json"
+    if not p.exists():
+        return None
+    d = json.loads(p.read_text()).get(workload)
+    return None if d is None else d["dram_bytes_per_step"] * steps
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -168,14 +178,12 @@ def main():
         return run_reference(args, wdt, desc)
 
     import torch
-    from tinyllama_cpp_b200 import capi
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from tinyllama_cpp_b200 import capi, replicas as R
+    env = R.ReplicaEnv.from_env()
+    rank, world, local = env.rank, env.world, env.local_rank
     if world > 1:
-        import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        R.init(env, "nccl", device_id=torch.device("cuda", local))
     capi.init(local)
     torch.cuda.set_device(local)
     cfg = W.TINYLLAMA
@@ -198,8 +206,7 @@ def main():
     def barrier():
         capi.sync()
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        R.barrier(env)
 
     # ---- resident path: prefill (untimed, exact row-by-row path), W warm-up steps, K timed steps
     eng.prefill(prompt)
@@ -240,16 +247,10 @@ def main():
     else:
         e2e_local = float("nan")
 
-    if world > 1:
-        t = torch.tensor([ms, e2e_local * 1e3], device=f"cuda:{local}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0]), float(t[1])
-        lt = torch.tensor([launches], device=f"cuda:{local}", dtype=torch.int64)
-        dist.all_reduce(lt)
-        launches = int(lt[0])
-    else:
-        e2e_ms = e2e_local * 1e3
-    value = world * K / (ms * 1e-3)
+    # replicas: the job is done when the slowest replica is; units (tokens) and launches add up
+    ms, units, (e2e_ms,), (launches,) = R.aggregate(env, ms, K, extra_max=[e2e_local * 1e3], extra_sum=[launches], device=f"cuda:{local}")
+    launches = int(launches)
+    value = R.throughput(units, ms)
     t_mean = n_prompt + Wm + (K - 1) / 2.0                 # mean sequence length over the timed steps
     bytes_per_tok = cfg.decode_bytes(wdt, int(round(t_mean)))
     achieved = bytes_per_tok * (K / (ms * 1e-3)) / 1e9     # per GPU
@@ -265,12 +266,13 @@ def main():
                        "weights": "random-init, seeded, gten format", "l2": "inputs larger than L2: every step streams "
                        f"{cfg.weight_bytes_per_token(wdt) / 1e6:.0f} MB of weights (L2 = 126 MB)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "one decode step (all kernels of one token)",
+                         "traffic": measured_traffic(args.workload, K), "peak_source": peak_src,
+                         "kernel": "k_mega<%s>: one persistent cooperative launch runs all K steps (achieved = bytes of K steps / launch time)" % args.workload,
                          "algorithmic_bytes_per_step": bytes_per_tok},
             "gpu_launches": launches, "clocks": clocks,
         }
         if not args.no_e2e:
-            out["e2e"] = {"value": world * K / (e2e_ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": 4,
+            out["e2e"] = {"value": units / (e2e_ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": 4,
                           "d2h_bytes_per_step": cfg.n_vocab * 4}
         if world == 1 and not args.no_cpu_baseline:
             eng.close()
@@ -278,6 +280,7 @@ def main():
         out["setup_s"] = round(time.time() - t_setup, 1)
         print(json.dumps(out), flush=True)
     if world > 1:
+        import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
 

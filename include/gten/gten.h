@@ -1,0 +1,54 @@
+// gten/gten.h -- umbrella header of the gten API on B200 (the reference's gten/gten.h:3-8 is a unity include of .cpp files;
+// these are ordinary headers over libgten_b200.so).  `#include "gten/gten.h"` + `-lgten_b200` replaces the reference's gten/.
+#pragma once
+// the reference's unity include drags these in for the application (tensor.cpp, ops.h); keep them so it compiles unchanged
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <limits>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "log.h"
+#include "gten_types.h"
+#include "quants.h"
+#include "tensor.h"
+#include "ops.h"
+#include "modules.h"
+
+namespace gten {
+
+/// The whole TinyLlama::logits graph (tinyllama.cpp:45-61) resident on the GPU: one persistent kernel per call instead of
+/// one kernel per op.  Same calling protocol as the reference class: logits(tokens, start_pos) takes ALL token ids so far.
+class FusedTinyLlama {
+public:
+    FusedTinyLlama(const int n_ctx, ModuleDtype dtype, int n_vocab = 32003, int n_embd = 2048, int n_ffn = 5632, int n_layers = 22,
+                   int n_heads = 32, int n_query_groups = 4)
+        : n_ctx_{n_ctx}, logits_{Tensor({n_vocab}, kFloat32)} {
+        gtb_model_config c{n_vocab, n_embd, n_ffn, n_layers, n_heads, n_query_groups, n_ctx, (int)dtype.wdtype};
+        GTEN_CUDA_OK(gtb_engine_create(&eng_, &c));
+    }
+    ~FusedTinyLlama() { if (eng_) gtb_engine_destroy(eng_); }
+    FusedTinyLlama(const FusedTinyLlama&) = delete;
+    FusedTinyLlama& operator=(const FusedTinyLlama&) = delete;
+    void load_from_ckpt(const char* path) { GTEN_CUDA_OK(gtb_engine_load_gten(eng_, path)); }
+    Tensor logits(const Tensor& tokens, const int start_pos = 0) {
+        if (tokens.numel() > n_ctx_) {
+            std::cerr << "Number of prompt tokens (" << tokens.numel() << ") exceed provided maximum ctx size (" << n_ctx_ << ")\n";
+            std::exit(EXIT_FAILURE);
+        }
+        GTEN_CUDA_OK(gtb_engine_logits(eng_, tokens.data_ptr<int32_t>(), tokens.numel(), start_pos, logits_.data_ptr<float>()));
+        return logits_;
+    }
+    gtb_engine_t engine() { return eng_; }
+private:
+    int n_ctx_;
+    gtb_engine_t eng_ = nullptr;
+    Tensor logits_;
+};
+
+}  // namespace gten

@@ -1,0 +1,39 @@
+"""Drop-in acceptance test: the UNMODIFIED reference application source (TinyLlama class, load_from_ckpt,
+greedy_sample, print_perf) compiled against include/gten -- oracle/_ref/libdropin_refapp.so, built where /root/reference
+exists -- loads a gten checkpoint and generates through the C++ module / op API on the GPU.  Its tokens and first logits
+must equal the engine's (which the other tests pin bit-exactly to the reference CPU build)."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from tinyllama_cpp_b200 import weights as W
+
+pytestmark = pytest.mark.gpu
+LIB = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "libdropin_refapp.so"
+
+
+@pytest.mark.skipif(not LIB.exists(), reason="oracle/_ref/libdropin_refapp.so not built (needs /root/reference at build time)")
+def test_reference_app_over_dropin_headers(tmp_path):
+    from tinyllama_cpp_b200 import capi
+    capi.init(0)
+    cfg = W.TINYLLAMA                                   # the reference class hard-codes these dimensions (tinyllama.cpp:12-20)
+    wdt = W.Q4
+    wl = list(W.synth_weights(cfg, wdt, seed=1))
+    path = tmp_path / "tinyllama.q4.gten"
+    W.write_gten(path, cfg, wdt, wl)
+    prompt = W.synth_prompt(11, 9, cfg.n_vocab).astype(np.int32)
+    n_new, max_ctx = 5, 32
+    L = C.CDLL(str(LIB))
+    L.dropin_generate.restype = C.c_int
+    toks = np.zeros(n_new, np.int32)
+    logits = np.zeros(cfg.n_vocab, np.float32)
+    rc = L.dropin_generate(str(path).encode(), wdt, max_ctx, prompt.ctypes.data_as(C.c_void_p), prompt.size, n_new,
+                           toks.ctypes.data_as(C.c_void_p), logits.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    e = capi.Engine(cfg, max_ctx, wdt).load(wl)
+    want = e.generate(prompt, n_new)
+    assert np.array_equal(toks, want[prompt.size:])
+    assert np.array_equal(logits.view(np.uint32), e.logits(prompt, 0).view(np.uint32))
+    e.close()
