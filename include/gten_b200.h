@@ -112,13 +112,25 @@ int gtb_engine_generate(gtb_engine_t e, int32_t* h_tokens, int n_prompt, int n_n
 int gtb_engine_reset(gtb_engine_t e);
 int gtb_engine_prefill(gtb_engine_t e, const int32_t* h_tokens, int n_tokens);     /* exact path, rows [0,n) */
 int gtb_engine_decode(gtb_engine_t e, int n_steps);                                /* n greedy steps, device-resident */
+/* Batched prefill of rows [0,n): every Linear of the n rows (ops.h:613-670) is one tcgen05/TMEM GEMM fed by TMA
+ * (fp16 operands dequantised from the Q8/Q4 blocks), the reference's re-encode points are applied in the epilogues,
+ * causal GQA attention runs on the tensor cores; K/V land in the cache and the last row's logits / first greedy
+ * token come from the order-exact lm_head phase, so gtb_engine_decode continues from here.  Summation order differs
+ * from ops.h:224-391: results match the reference within a tolerance (tests/test_prefill_gpu.py), not bit for bit.
+ * Q8-activation models only (Q8 and Q4 weights, tinyllama.cpp:258-265). */
+int gtb_engine_prefill_fast(gtb_engine_t e, const int32_t* h_tokens, int n_tokens);
+/* decoded fp32 row `row` of a module activation of the last gtb_engine_prefill_fast call ("capture_acv" on) */
+int gtb_engine_pf_acv(gtb_engine_t e, int layer, int acv_id, int row, float* h_out, int* width);
+/* self-test of the tcgen05 GEMM: C[M][N] = A[M][K] . W[N][K]^T, fp16 host inputs, fp32 host output; bn = 128 or 256 */
+int gtb_pf_gemm_f32(const void* h_A16, const void* h_W16, int M, int N, int K, int bn, float* h_C);
 int gtb_engine_position(gtb_engine_t e, int* pos);
 int gtb_engine_read_tokens(gtb_engine_t e, int32_t* h_tokens, int first, int count);
 int gtb_engine_read_logits(gtb_engine_t e, float* h_logits);
 /* decoded fp32 row of a module activation for the LAST processed row (debug/parity) */
 int gtb_engine_acv(gtb_engine_t e, int layer, int acv_id, float* h_out, int* width);
 /* options: "mega" (1: persistent cooperative kernel, default; 0: one kernel per phase), "graph" (CUDA-graph replay of
- * the per-phase path), "capture_acv", "grid", "pf_ahead" (L2 prefetch distance in GEMV phases), "prof" */
+ * the per-phase path), "capture_acv", "grid", "pf_ahead" (L2 prefetch distance in GEMV phases), "prof",
+ * "pf_layers" (debug: batched prefill stops after this many layers) */
 int gtb_engine_set_option(gtb_engine_t e, const char* name, int value);
 /* "prof": globaltimer stamps (ns) taken by CTA 0 at every phase boundary of the last processed row */
 int gtb_engine_read_prof(gtb_engine_t e, long long* h_out, int count);

@@ -28,6 +28,7 @@ SYMBOLS = [
     "gtb_engine_logits", "gtb_engine_generate", "gtb_engine_reset", "gtb_engine_prefill", "gtb_engine_decode",
     "gtb_engine_position", "gtb_engine_read_tokens", "gtb_engine_read_logits", "gtb_engine_acv",
     "gtb_engine_set_option", "gtb_engine_weight_bytes", "gtb_engine_read_prof", "gtb_selftest_exact_sum", "gtb_engine_uses_megakernel",
+    "gtb_engine_prefill_fast", "gtb_engine_pf_acv", "gtb_pf_gemm_f32",
 ]
 
 
@@ -75,6 +76,8 @@ def lib():
             "gtb_engine_read_logits": [vp, vp], "gtb_engine_acv": [vp, i, i, vp, C.POINTER(i)],
             "gtb_engine_set_option": [vp, C.c_char_p, i], "gtb_engine_weight_bytes": [vp, C.POINTER(sz)],
             "gtb_engine_read_prof": [vp, vp, i], "gtb_selftest_exact_sum": [vp, i, vp], "gtb_engine_uses_megakernel": [vp, C.POINTER(C.c_int)],
+            "gtb_engine_prefill_fast": [vp, vp, i], "gtb_engine_pf_acv": [vp, i, i, i, vp, C.POINTER(i)],
+            "gtb_pf_gemm_f32": [vp, vp, i, i, i, i, vp],
         }
         for name, args in sigs.items():
             fn = getattr(L, name)
@@ -114,6 +117,17 @@ def stream_handle() -> int:
 def _hp(a: np.ndarray):
     assert a.flags["C_CONTIGUOUS"]
     return a.ctypes.data_as(C.c_void_p)
+
+
+def pf_gemm_f32(a16: np.ndarray, w16: np.ndarray, bn: int = 256) -> np.ndarray:
+    """C = A . W^T on the tcgen05 path (self-test entry): A [M,K] fp16, W [N,K] fp16 -> C [M,N] fp32."""
+    a16 = np.ascontiguousarray(a16, np.float16)
+    w16 = np.ascontiguousarray(w16, np.float16)
+    m, k = a16.shape
+    n = w16.shape[0]
+    out = np.empty((m, n), np.float32)
+    check(lib().gtb_pf_gemm_f32(_hp(a16), _hp(w16), m, n, k, bn, _hp(out)))
+    return out
 
 
 class DeviceBuffer:
@@ -323,6 +337,17 @@ class Engine:
     def prefill(self, tokens):
         tokens = np.ascontiguousarray(tokens, np.int32)
         check(lib().gtb_engine_prefill(self.h, _hp(tokens), tokens.size))
+
+    def prefill_fast(self, tokens):
+        """Batched prefill (tcgen05 GEMMs); tolerance-level parity, K/V cache and first token left for decode()."""
+        tokens = np.ascontiguousarray(tokens, np.int32)
+        check(lib().gtb_engine_prefill_fast(self.h, _hp(tokens), tokens.size))
+
+    def pf_acv(self, layer: int, aid: int, row: int) -> np.ndarray:
+        out = np.empty(max(self.cfg.n_ffn, self.cfg.n_embd), np.float32)
+        w = C.c_int()
+        check(lib().gtb_engine_pf_acv(self.h, layer, aid, row, _hp(out), C.byref(w)))
+        return out[: w.value].copy()
 
     def decode(self, n_steps: int):
         check(lib().gtb_engine_decode(self.h, n_steps))

@@ -13,6 +13,7 @@
 #include "gtb_internal.h"
 #include "gtb_kernels.cuh"
 #include "gtb_mega.cuh"
+#include "gtb_prefill.h"
 
 namespace gtb {
 
@@ -306,6 +307,11 @@ struct gtb_engine {
     unsigned int* cnt = nullptr;
     long long* d_prof = nullptr;
     int sc_stride = 0;
+    // batched prefill (gtb_prefill.cu): fp16 weight copies + activation workspace, built on first use
+    gtb::PfPlan* pf = nullptr;
+    float* pf_cap = nullptr;         // [n_layers*12 + 1][pf_cap_T][capw] when capture_acv is on
+    int pf_cap_T = 0;
+    int pf_layers = 0;               // debug: run only the first pf_layers layers (0 = all)
 };
 
 namespace {
@@ -643,6 +649,8 @@ int gtb_engine_destroy(gtb_engine_t e) {
                     e->tokens, e->st, e->cap, e->rope_cos, e->rope_sin, e->x_qkv, e->x_sc, e->x_attn, e->x_o, e->x_gu, e->x_act,
                     e->x_down, e->x_arg, e->dbg, e->epoch, e->cnt, e->d_prof, e->d_layers};
     for (void* b : bufs) cudaFree(b);
+    if (e->pf) pf_destroy(e->pf);
+    cudaFree(e->pf_cap);
     delete e;
     return GTB_OK;
 }
@@ -677,6 +685,7 @@ int gtb_engine_set_weight(gtb_engine_t e, int layer, int tensor_id, const void* 
     }
     if (*slot) { e->weight_bytes -= (*slot)->nbytes; gtb_weight_free(*slot); *slot = nullptr; drop_graphs(e); }
     e->layers_valid = false;
+    if (e->pf) { pf_destroy(e->pf); e->pf = nullptr; }     // the fp16 copies are rebuilt on the next batched prefill
     int r;
     int row_off = -1;
     uint8_t* fdata = nullptr;
@@ -780,6 +789,114 @@ int gtb_engine_prefill(gtb_engine_t e, const int32_t* h_tokens, int n_tokens) {
     r = run_rows(e, n_tokens - 1, 1, -1);
     if (r) return r;
     e->host_pos = n_tokens;
+    return GTB_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- batched prefill (gtb_prefill.cu)
+template <int WT>
+static int pf_head(gtb_engine* e) {
+    // final residual + RMSNorm + lm_head of the last prompt row through the order-exact phase kernel (tinyllama.cpp:57-58)
+    PhaseArgs a{};
+    a.K = e->cfg.n_embd; a.n_mats = 1;
+    a.mat[0] = matof(e->lm_head, e->logits);
+    a.src0 = e->hres; a.src1 = e->rd; a.normw = e->final_norm; a.res_out = e->xfinal;
+    int r = launch_phase<WT, PRO_NORM>(e, a);
+    if (r) return r;
+    k_argmax_advance<<<1, 1024, 0, ctx().stream>>>(e->logits, e->cfg.n_vocab, e->tokens, e->st, -1);
+    GTB_LAUNCHED();
+    return GTB_OK;
+}
+
+extern "C" {
+
+int gtb_engine_prefill_fast(gtb_engine_t e, const int32_t* h_tokens, int n_tokens) {
+    GTB_CHECK_INIT();
+    GTB_ARG(e && h_tokens && n_tokens > 0 && n_tokens < e->cfg.max_ctx);
+    const gtb_model_config& c = e->cfg;
+    if (c.wdtype != GTB_Q8 && c.wdtype != GTB_Q4)
+        return fail(GTB_ERR_STATE, "batched prefill is built for Q8-activation models (Q8, Q4 weights); use gtb_engine_prefill");
+    int r = check_loaded(e);
+    if (r) return r;
+    const int E = c.n_embd, F = c.n_ffn, KV = e->kv_dim;
+    if (!e->pf) { r = pf_create(&e->pf, c); if (r) return r; }
+    if (!pf_weights_ready(e->pf)) {
+        for (int li = 0; li < c.n_layers; li++) {
+            LayerW& l = e->L[li];
+            r = pf_set_weight(e->pf, li, 0, c.wdtype, l.qkv_data, l.qkv_sc, E + 2 * KV, E);
+            if (!r) r = pf_set_weight(e->pf, li, 1, c.wdtype, l.o->data, l.o->scales, E, E);
+            if (!r) r = pf_set_weight(e->pf, li, 2, c.wdtype, l.gu_data, l.gu_sc, 2 * F, E);
+            if (!r) r = pf_set_weight(e->pf, li, 3, c.wdtype, l.down->data, l.down->scales, E, F);
+            if (r) return r;
+        }
+    }
+    if (e->capture && e->pf_cap_T != n_tokens) {
+        cudaFree(e->pf_cap);
+        e->pf_cap = nullptr;
+        GTB_CUDA(cudaMalloc((void**)&e->pf_cap, ((size_t)c.n_layers * 12 + 1) * n_tokens * e->capw * 4));
+        e->pf_cap_T = n_tokens;
+    }
+    GTB_CUDA(cudaMemcpyAsync(e->tokens, h_tokens, (size_t)n_tokens * 4, cudaMemcpyHostToDevice, ctx().stream));
+    std::vector<PfLayerIO> io(c.n_layers);
+    for (int li = 0; li < c.n_layers; li++) {
+        LayerW& l = e->L[li];
+        io[li] = PfLayerIO{l.attn_norm, l.ffn_norm, l.kq, l.ks, l.vq, l.vs};
+    }
+    PfRun run{};
+    run.d_tokens = e->tokens; run.T = n_tokens; run.embed = e->embed; run.layers = io.data();
+    run.rope_cos = e->rope_cos; run.rope_sin = e->rope_sin; run.last_res = e->hres; run.last_down = e->rd;
+    run.cap = e->capture ? e->pf_cap : nullptr; run.capw = e->capw;
+    run.n_layers_run = (e->pf_layers > 0 && e->pf_layers < c.n_layers) ? e->pf_layers : c.n_layers;
+    if (e->capture && e->pf_cap) GTB_CUDA(cudaMemsetAsync(e->pf_cap, 0, ((size_t)c.n_layers * 12 + 1) * n_tokens * e->capw * 4, ctx().stream));
+    r = pf_run(e->pf, run);
+    if (r) return r;
+    r = set_state(e, n_tokens - 1, n_tokens);
+    if (r) return r;
+    r = (c.wdtype == GTB_Q8) ? pf_head<DT_Q8>(e) : pf_head<DT_Q4>(e);
+    if (r) return r;
+    e->host_pos = n_tokens;
+    return GTB_OK;
+}
+
+int gtb_engine_pf_acv(gtb_engine_t e, int layer, int acv_id, int row, float* h_out, int* width) {
+    GTB_CHECK_INIT();
+    GTB_ARG(e && h_out);
+    if (!e->capture || !e->pf_cap) return fail(GTB_ERR_STATE, "no batched-prefill capture: set capture_acv and call gtb_engine_prefill_fast");
+    GTB_ARG(row >= 0 && row < e->pf_cap_T);
+    int w = e->cfg.n_embd;
+    if (acv_id == GTB_A_K || acv_id == GTB_A_V) w = e->kv_dim;
+    if (acv_id == GTB_A_GATE || acv_id == GTB_A_UP) w = e->cfg.n_ffn;
+    GTB_ARG(acv_id == GTB_A_EMB || (acv_id >= GTB_A_ATTN_NORM && acv_id <= GTB_A_ATTN_RES && layer >= 0 && layer < e->cfg.n_layers));
+    const size_t T = (size_t)e->pf_cap_T;
+    const size_t slot = (acv_id == GTB_A_EMB) ? (size_t)e->cfg.n_layers * 12 : (size_t)layer * 12 + (acv_id - GTB_A_ATTN_NORM);
+    const float* src = e->pf_cap + (slot * T + row) * e->capw;
+    GTB_CUDA(cudaMemcpyAsync(h_out, src, (size_t)w * 4, cudaMemcpyDeviceToHost, ctx().stream));
+    GTB_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (width) *width = w;
+    return GTB_OK;
+}
+
+int gtb_pf_gemm_f32(const void* h_A16, const void* h_W16, int M, int N, int K, int bn, float* h_C) {
+    GTB_CHECK_INIT();
+    GTB_ARG(h_A16 && h_W16 && h_C && M > 0 && N > 0 && K > 0);
+    void *dA = nullptr, *dW = nullptr;
+    float* dC = nullptr;
+    const int Ma = M < 128 ? 128 : M, Na = N < bn ? bn : N;
+    GTB_CUDA(cudaMalloc(&dA, (size_t)Ma * K * 2));
+    GTB_CUDA(cudaMalloc(&dW, (size_t)Na * K * 2));
+    GTB_CUDA(cudaMalloc((void**)&dC, (size_t)M * N * 4));
+    cudaMemsetAsync(dA, 0, (size_t)Ma * K * 2, ctx().stream);
+    cudaMemsetAsync(dW, 0, (size_t)Na * K * 2, ctx().stream);
+    cudaMemcpyAsync(dA, h_A16, (size_t)M * K * 2, cudaMemcpyHostToDevice, ctx().stream);
+    cudaMemcpyAsync(dW, h_W16, (size_t)N * K * 2, cudaMemcpyHostToDevice, ctx().stream);
+    int r = pf_gemm_f32(dA, dW, dC, M, N, K, bn);
+    cudaError_t ce = cudaSuccess;
+    if (!r) ce = cudaMemcpyAsync(h_C, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost, ctx().stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx().stream);
+    cudaFree(dA); cudaFree(dW); cudaFree(dC);
+    if (r) return r;
+    if (ce != cudaSuccess) return fail(GTB_ERR_CUDA, "tcgen05 GEMM self-test failed: %s", cudaGetErrorString(ce));
     return GTB_OK;
 }
 
@@ -894,6 +1011,7 @@ int gtb_engine_set_option(gtb_engine_t e, const char* name, int value) {
     if (!strcmp(name, "mega")) { e->use_mega = value != 0; return GTB_OK; }
     if (!strcmp(name, "pf_ahead")) { GTB_ARG(value >= 0 && value <= 64); e->pf_ahead = value; return GTB_OK; }
     if (!strcmp(name, "prof")) { e->prof = value != 0; return GTB_OK; }
+    if (!strcmp(name, "pf_layers")) { GTB_ARG(value >= 0); e->pf_layers = value; return GTB_OK; }
     return fail(GTB_ERR_ARG, "unknown option %s", name);
 }
 

@@ -1,0 +1,945 @@
+// gtb_prefill.cu -- batched prefill: all T prompt rows of TinyLlama::logits (tinyllama.cpp:45-61) at once.
+//
+// Every Linear (gten/modules.cpp:44-62 -> ops.h:613-670) of the T rows is ONE GEMM
+//     C[T][N] = A[T][K] . W[N][K]^T
+// on the tcgen05 tensor cores: A and W tiles (fp16, K-major, 128-byte swizzle) are staged in shared memory by TMA
+// through a 4-stage mbarrier ring, one elected thread issues tcgen05.mma (M128 x N256 x K16, fp32 accumulate) into a
+// double-buffered TMEM accumulator, and four epilogue warps read it back with tcgen05.ld and apply the reference's
+// output re-encode (Q8 blocks, quants.h:52-66) before anything reaches HBM.  The row-wise ops between the GEMMs
+// (token_embed, add, rms_norm, rotary_emb, silu, mul: ops.h:514-910) work on "Q8 planar" activations
+// (int8 codes [T][D] + fp16 block scales [T][D/32]) with the reference's arithmetic and rounding points, and the
+// causal GQA attention (ops.h:930-1133) is a two-pass tensor-core kernel that reproduces the Q8 re-encode of the
+// probability rows.  K and V land in the engine's cache layout so that decode continues from position T.
+//
+// fp16 operands are the dequantised Q8/Q4 values rounded to fp16 (relative error <= 2^-12 per element) and the
+// summation order of a dot differs from ops.h:224-391, so this path is tolerance-checked, not bit-checked.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <string.h>
+
+#include <vector>
+
+#include "gtb_prefill.h"
+
+namespace gtb {
+
+// =================================================================================================== PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// A wait that cannot hang the GPU: a broken pipeline traps (the launch fails) after ~2 s instead of spinning forever.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, fp16 operands, fp32 accumulate; issued by ONE thread for the whole CTA
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrive once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread `lane` of the warp receives row (lane_base + lane), columns col..col+31
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// =================================================================================================== block codecs
+// One Q8 block (32 values) held by ONE thread: same operations as quants.h:52-66 / gtb_dev.cuh q8_encode_lane.
+__device__ __forceinline__ uint16_t q8_encode32(const float (&x)[32], int (&q)[32]) {
+    float amax = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; i++) amax = fmaxf(amax, fabsf(x[i]));
+    const float delta = __fdiv_rn(amax, 127.0f);
+    const float scale = (delta != 0.0f) ? __fdiv_rn(1.0f, delta) : 0.0f;       // from the UNROUNDED delta
+#pragma unroll
+    for (int i = 0; i < 32; i++) q[i] = (int)roundf(__fmul_rn(x[i], scale));   // half away from zero
+    return f2h(delta);
+}
+__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
+    return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);
+}
+// natural order (planar activations, V cache)
+__device__ __forceinline__ void store_codes32(int8_t* dst, const int (&q)[32]) {
+    uint4 lo, hi;
+    lo.x = pack4(q[0], q[1], q[2], q[3]);     lo.y = pack4(q[4], q[5], q[6], q[7]);
+    lo.z = pack4(q[8], q[9], q[10], q[11]);   lo.w = pack4(q[12], q[13], q[14], q[15]);
+    hi.x = pack4(q[16], q[17], q[18], q[19]); hi.y = pack4(q[20], q[21], q[22], q[23]);
+    hi.z = pack4(q[24], q[25], q[26], q[27]); hi.w = pack4(q[28], q[29], q[30], q[31]);
+    reinterpret_cast<uint4*>(dst)[0] = lo;
+    reinterpret_cast<uint4*>(dst)[1] = hi;
+}
+// staged order of the K cache (gtb_kernels.cuh perm_byte): word l of a half = elements (2l, 2l+1, 2l+8, 2l+9)
+__device__ __forceinline__ void store_codes32_perm(uint8_t* dst, const int (&q)[32]) {
+    uint4 lo, hi;
+    lo.x = pack4(q[0], q[1], q[8], q[9]);     lo.y = pack4(q[2], q[3], q[10], q[11]);
+    lo.z = pack4(q[4], q[5], q[12], q[13]);   lo.w = pack4(q[6], q[7], q[14], q[15]);
+    hi.x = pack4(q[16], q[17], q[24], q[25]); hi.y = pack4(q[18], q[19], q[26], q[27]);
+    hi.z = pack4(q[20], q[21], q[28], q[29]); hi.w = pack4(q[22], q[23], q[30], q[31]);
+    reinterpret_cast<uint4*>(dst)[0] = lo;
+    reinterpret_cast<uint4*>(dst)[1] = hi;
+}
+__device__ __forceinline__ int sbyte(uint32_t w, int j) { return (int)(int8_t)((w >> (8 * j)) & 0xffu); }
+__device__ __forceinline__ void load_codes32(const int8_t* src, int (&q)[32]) {
+    const uint4 lo = reinterpret_cast<const uint4*>(src)[0], hi = reinterpret_cast<const uint4*>(src)[1];
+    const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int i = 0; i < 32; i++) q[i] = sbyte(w[i >> 2], i & 3);
+}
+// dequantised block of a planar activation: value = code * fp32(delta) (exact in fp32, quants.h:69-76)
+__device__ __forceinline__ void load_deq32(const int8_t* q, const uint16_t* s, size_t row, int D, int b, float (&v)[32]) {
+    int c[32];
+    load_codes32(q + row * D + (size_t)b * 32, c);
+    const float d = h2f(s[row * (D / 32) + b]);
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __fmul_rn((float)c[i], d);
+}
+__device__ __forceinline__ void store_half32(__half* dst, const float (&v)[32]) {
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) reinterpret_cast<uint4*>(dst)[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+}
+__device__ __forceinline__ void store_f32x32(float* dst, const float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+
+// =================================================================================================== GEMM (tcgen05)
+constexpr int PF_BM = 128;          // rows of A (prompt positions) per tile = UMMA M
+constexpr int PF_BK = 64;           // fp16 elements per k-block = one 128-byte swizzle atom
+constexpr int PF_THREADS = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+enum { EPI_F32 = 0, EPI_Q8 = 1 };
+
+template <int BN> struct PfGemmCfg {
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr uint32_t A_BYTES = PF_BM * PF_BK * 2;
+    static constexpr uint32_t B_BYTES = BN * PF_BK * 2;
+    static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers + tmem slot*/;
+    // kind::f16 instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D = fp32 (bits 4-5 = 1),
+    // A = B = fp16 (0), both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28
+    static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(PF_BM >> 4) << 24);
+};
+
+// shared-memory matrix descriptor of a K-major tile with 128-byte swizzle: rows are 128 B apart, 8-row groups 1024 B
+// apart (SBO), LBO unused (1), descriptor version 1, layout type 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(PF_THREADS, 1)
+k_pf_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+          void* __restrict__ out0, void* __restrict__ out1) {
+    using Cfg = PfGemmCfg<BN>;
+    constexpr int ST = Cfg::STAGES;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ST * Cfg::STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ST + 4);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_u32(bars);
+    auto bar_full = [&](int s) { return bar_base + 8u * s; };
+    auto bar_empty = [&](int s) { return bar_base + 8u * (ST + s); };
+    auto bar_tfull = [&](int a) { return bar_base + 8u * (2 * ST + a); };
+    auto bar_tempty = [&](int a) { return bar_base + 8u * (2 * ST + 2 + a); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_mt = (M + PF_BM - 1) / PF_BM, n_nt = (N + BN - 1) / BN;
+    const int n_tiles = n_mt * n_nt, nkb = K / PF_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < ST; s++) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {        // ---------------- TMA producer
+            tma_prefetch_desc(&tmA);
+            tma_prefetch_desc(&tmB);
+            uint32_t s = 0, ph = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int mt = tile % n_mt, nt = tile / n_mt;         // consecutive CTAs share one slice of W
+                for (int kb = 0; kb < nkb; kb++) {
+                    mbar_wait(bar_empty(s), ph ^ 1);
+                    mbar_expect_tx(bar_full(s), Cfg::STAGE_BYTES);
+                    const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
+                    tma_load_2d(sa, &tmA, bar_full(s), kb * PF_BK, mt * PF_BM);
+                    tma_load_2d(sa + Cfg::A_BYTES, &tmB, bar_full(s), kb * PF_BK, nt * BN);
+                    if (++s == ST) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {        // ---------------- MMA issuer
+            uint32_t s = 0, ph = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+                const int as = it & 1;
+                mbar_wait(bar_tempty(as), ((it >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < nkb; kb++) {
+                    mbar_wait(bar_full(s), ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
+                    const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < PF_BK / 16; k++)          // UMMA K = 16 fp16 = 32 bytes inside the swizzle atom
+                        umma_f16(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), Cfg::IDESC, (kb | k) != 0);
+                    umma_commit(bar_empty(s));                      // frees the stage when these MMAs have read it
+                    if (kb == nkb - 1) umma_commit(bar_tfull(as));  // accumulator complete
+                    if (++s == ST) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else {                    // ---------------- epilogue warps: TMEM -> registers -> re-encode -> HBM
+        const int lg = warp & 3;                                    // a warp may only touch TMEM lanes 32*(warp%4)..+31
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+            const int mt = tile % n_mt, nt = tile / n_mt;
+            const int as = it & 1;
+            mbar_wait(bar_tfull(as), (it >> 1) & 1);
+            tc_fence_after();
+            const int row = mt * PF_BM + lg * 32 + lane;
+            const bool row_ok = row < M;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; c++) {
+                const int col = nt * BN + c * 32;
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + c * 32), v);
+                if (row_ok && col < N) {
+                    if (EPI == EPI_F32) {
+                        store_f32x32(reinterpret_cast<float*>(out0) + (size_t)row * N + col, v);
+                    } else {
+                        int q[32];
+                        const uint16_t dh = q8_encode32(v, q);        // write_row_from_float, ops.h:645-646
+                        store_codes32(reinterpret_cast<int8_t*>(out0) + (size_t)row * N + col, q);
+                        reinterpret_cast<uint16_t*>(out1)[(size_t)row * (N / 32) + (col >> 5)] = dh;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_tempty(as));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// =================================================================================================== row-wise kernels
+// weights: device layout (gtb_internal.h) -> fp16 [rows][cols], value = fp16(code * delta)
+__global__ void k_pf_w16(const void* __restrict__ data, const uint16_t* __restrict__ scales, int wdtype, size_t nblocks,
+                         __half* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nblocks) return;
+    const float d = h2f(scales[i]);
+    float v[32];
+    if (wdtype == DT_Q4) {
+        const uint4 w4 = reinterpret_cast<const uint4*>(data)[i];
+        const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int e = 0; e < 16; e++) {                    // payload byte j = e: word (j&7)>>1, position (j&1) + 2*(j>>3)
+            const int l = (e & 7) >> 1, pos = (e & 1) + 2 * (e >> 3);
+            const uint32_t byte = (w[l] >> (8 * pos)) & 0xffu;
+            v[e] = __fmul_rn((float)((int)(byte >> 4) - 7), d);
+            v[e + 16] = __fmul_rn((float)((int)(byte & 0x0fu) - 7), d);
+        }
+    } else {
+        const uint4 x4 = reinterpret_cast<const uint4*>(data)[2 * i], y4 = reinterpret_cast<const uint4*>(data)[2 * i + 1];
+        const uint32_t w[8] = {x4.x, x4.y, x4.z, x4.w, y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+            const int half = e >> 4, j = e & 15, l = (j & 7) >> 1, pos = (j & 1) + 2 * (j >> 3);
+            v[e] = __fmul_rn((float)sbyte(w[half * 4 + l], pos), d);
+        }
+    }
+    store_half32(out + i * 32, v);
+}
+
+// token_embed (ops.h:514-564): Q8 rows are copied, Q4 rows are dequantised and re-encoded as Q8
+__global__ void k_pf_embed(const void* __restrict__ wdata, const uint16_t* __restrict__ wsc, int wdtype, const int32_t* __restrict__ tokens,
+                           int T, int D, int8_t* __restrict__ xq, uint16_t* __restrict__ xs, float* cap, int capw) {
+    const int nb = D / 32;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)T * nb) return;
+    const int row = (int)(i / nb), b = (int)(i % nb);
+    const size_t blk = (size_t)tokens[row] * nb + b;
+    const float d = h2f(wsc[blk]);
+    int q[32];
+    uint16_t dh;
+    if (wdtype == DT_Q4) {
+        const uint4 w4 = reinterpret_cast<const uint4*>(wdata)[blk];
+        const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+        float v[32];
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const int l = (e & 7) >> 1, pos = (e & 1) + 2 * (e >> 3);
+            const uint32_t byte = (w[l] >> (8 * pos)) & 0xffu;
+            v[e] = __fmul_rn((float)((int)(byte >> 4) - 7), d);
+            v[e + 16] = __fmul_rn((float)((int)(byte & 0x0fu) - 7), d);
+        }
+        dh = q8_encode32(v, q);
+    } else {
+        const uint4 x4 = reinterpret_cast<const uint4*>(wdata)[2 * blk], y4 = reinterpret_cast<const uint4*>(wdata)[2 * blk + 1];
+        const uint32_t w[8] = {x4.x, x4.y, x4.z, x4.w, y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+            const int half = e >> 4, j = e & 15, l = (j & 7) >> 1, pos = (j & 1) + 2 * (j >> 3);
+            q[e] = sbyte(w[half * 4 + l], pos);
+        }
+        dh = wsc[blk];
+    }
+    store_codes32(xq + (size_t)row * D + (size_t)b * 32, q);
+    xs[(size_t)row * nb + b] = dh;
+    if (cap) {
+        const float dd = h2f(dh);
+        for (int e = 0; e < 32; e++) cap[(size_t)row * capw + b * 32 + e] = __fmul_rn((float)q[e], dd);
+    }
+}
+
+// Residual (ops.h:870-910) + RMSNorm (ops.h:762-814), one warp per row:
+//   x <- E(x + y)        (skipped when y == nullptr)
+//   xn <- fp16( E( x / (rms(x) + 1e-6) * w ) )       the A operand of the next GEMM
+// The sum of squares is a plain parallel fp32 sum (the reference sums in element order): its relative error of ~1e-7
+// is three orders of magnitude below the fp16 operand rounding of the GEMMs of this path.
+__global__ void __launch_bounds__(128) k_pf_add_norm(int8_t* __restrict__ xq, uint16_t* __restrict__ xs, const int8_t* __restrict__ yq,
+                                                      const uint16_t* __restrict__ ys, const uint16_t* __restrict__ normw,
+                                                      __half* __restrict__ xn16, int T, int D, float* cap_y, float* cap_x, float* cap_n, int capw) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= T) return;
+    const int nb = D / 32;
+    float ssq = 0.0f;
+    for (int b = lane; b < nb; b += 32) {
+        float v[32];
+        load_deq32(xq, xs, row, D, b, v);
+        if (yq) {
+            float y[32];
+            load_deq32(yq, ys, row, D, b, y);
+            if (cap_y) for (int i = 0; i < 32; i++) cap_y[(size_t)row * capw + b * 32 + i] = y[i];
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = __fadd_rn(v[i], y[i]);
+            int q[32];
+            const uint16_t dh = q8_encode32(v, q);
+            store_codes32(xq + (size_t)row * D + (size_t)b * 32, q);
+            xs[(size_t)row * nb + b] = dh;
+            const float dd = h2f(dh);
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = __fmul_rn((float)q[i], dd);
+        }
+        if (cap_x) for (int i = 0; i < 32; i++) cap_x[(size_t)row * capw + b * 32 + i] = v[i];
+#pragma unroll
+        for (int i = 0; i < 32; i++) ssq = __fadd_rn(ssq, __fmul_rn(v[i], v[i]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ssq = __fadd_rn(ssq, __shfl_xor_sync(0xffffffffu, ssq, o));
+    const float rms = sqrtf(__fdiv_rn(ssq, (float)D));
+    const float denom = __fadd_rn(rms, 1e-6f);
+    for (int b = lane; b < nb; b += 32) {
+        float v[32];
+        load_deq32(xq, xs, row, D, b, v);
+        const uint4* wp = reinterpret_cast<const uint4*>(normw + b * 32);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint4 w4 = wp[k];
+            const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float wf = h2f((uint16_t)((w[j >> 1] >> (16 * (j & 1))) & 0xffffu));
+                v[k * 8 + j] = __fmul_rn(__fdiv_rn(v[k * 8 + j], denom), wf);
+            }
+        }
+        int q[32];
+        const uint16_t dh = q8_encode32(v, q);
+        const float dd = h2f(dh);
+#pragma unroll
+        for (int i = 0; i < 32; i++) v[i] = __fmul_rn((float)q[i], dd);
+        if (cap_n) for (int i = 0; i < 32; i++) cap_n[(size_t)row * capw + b * 32 + i] = v[i];
+        store_half32(xn16 + (size_t)row * D + (size_t)b * 32, v);
+    }
+}
+
+// RoPE (ops.h:714-760) on the q and k heads of the fused q|k|v GEMM output, K/V append in the engine's cache layout,
+// and the fp16 operands of the attention kernel.  One thread per (row, head slot): slots [0,nh) = q heads,
+// [nh, nh+ng) = k heads, [nh+ng, nh+2ng) = v heads.
+__global__ void __launch_bounds__(128) k_pf_rope_kv(const int8_t* __restrict__ cq, const uint16_t* __restrict__ cs, int T, int nh, int ng,
+                                                     const float* __restrict__ rope_cos, const float* __restrict__ rope_sin,
+                                                     __half* __restrict__ q16, __half* __restrict__ k16, __half* __restrict__ v16,
+                                                     uint8_t* __restrict__ kq, uint16_t* __restrict__ ks, uint8_t* __restrict__ vq, uint16_t* __restrict__ vs,
+                                                     float* cap_q, float* cap_k, float* cap_v, int capw) {
+    const int nslots = nh + 2 * ng;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)T * nslots) return;
+    const int row = (int)(idx / nslots), slot = (int)(idx % nslots);
+    const int E = nh * 64, KV = ng * 64, D = E + 2 * KV;
+    float x0[32], x1[32];
+    load_deq32(cq, cs, row, D, slot * 2, x0);
+    load_deq32(cq, cs, row, D, slot * 2 + 1, x1);
+    const bool is_v = slot >= nh + ng;
+    int q0[32], q1[32];
+    uint16_t dh0, dh1;
+    if (!is_v) {
+        const float4* cp = reinterpret_cast<const float4*>(rope_cos + (size_t)row * 32);
+        const float4* sp = reinterpret_cast<const float4*>(rope_sin + (size_t)row * 32);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float4 c4 = cp[k], s4 = sp[k];
+            const float c[4] = {c4.x, c4.y, c4.z, c4.w}, s[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float a = x0[4 * k + j], b = x1[4 * k + j];
+                x0[4 * k + j] = __fsub_rn(__fmul_rn(a, c[j]), __fmul_rn(b, s[j]));
+                x1[4 * k + j] = __fadd_rn(__fmul_rn(a, s[j]), __fmul_rn(b, c[j]));
+            }
+        }
+        dh0 = q8_encode32(x0, q0);
+        dh1 = q8_encode32(x1, q1);
+        const float d0 = h2f(dh0), d1 = h2f(dh1);
+#pragma unroll
+        for (int i = 0; i < 32; i++) { x0[i] = __fmul_rn((float)q0[i], d0); x1[i] = __fmul_rn((float)q1[i], d1); }
+    } else {
+        // V is the Linear output itself: codes and scales pass through unchanged
+        load_codes32(cq + (size_t)row * D + (size_t)slot * 64, q0);
+        load_codes32(cq + (size_t)row * D + (size_t)slot * 64 + 32, q1);
+        dh0 = cs[(size_t)row * (D / 32) + slot * 2];
+        dh1 = cs[(size_t)row * (D / 32) + slot * 2 + 1];
+    }
+    if (slot < nh) {
+        store_half32(q16 + (size_t)row * E + slot * 64, x0);
+        store_half32(q16 + (size_t)row * E + slot * 64 + 32, x1);
+        if (cap_q) for (int i = 0; i < 32; i++) { cap_q[(size_t)row * capw + slot * 64 + i] = x0[i]; cap_q[(size_t)row * capw + slot * 64 + 32 + i] = x1[i]; }
+    } else if (!is_v) {
+        const int g = slot - nh;
+        store_half32(k16 + (size_t)row * KV + g * 64, x0);
+        store_half32(k16 + (size_t)row * KV + g * 64 + 32, x1);
+        store_codes32_perm(kq + (size_t)row * KV + g * 64, q0);
+        store_codes32_perm(kq + (size_t)row * KV + g * 64 + 32, q1);
+        ks[(size_t)row * (KV / 32) + g * 2] = dh0;
+        ks[(size_t)row * (KV / 32) + g * 2 + 1] = dh1;
+        if (cap_k) for (int i = 0; i < 32; i++) { cap_k[(size_t)row * capw + g * 64 + i] = x0[i]; cap_k[(size_t)row * capw + g * 64 + 32 + i] = x1[i]; }
+    } else {
+        const int g = slot - nh - ng;
+        store_half32(v16 + (size_t)row * KV + g * 64, x0);
+        store_half32(v16 + (size_t)row * KV + g * 64 + 32, x1);
+        store_codes32(reinterpret_cast<int8_t*>(vq) + (size_t)row * KV + g * 64, q0);
+        store_codes32(reinterpret_cast<int8_t*>(vq) + (size_t)row * KV + g * 64 + 32, q1);
+        vs[(size_t)row * (KV / 32) + g * 2] = dh0;
+        vs[(size_t)row * (KV / 32) + g * 2 + 1] = dh1;
+        if (cap_v) for (int i = 0; i < 32; i++) { cap_v[(size_t)row * capw + g * 64 + i] = x0[i]; cap_v[(size_t)row * capw + g * 64 + 32 + i] = x1[i]; }
+    }
+}
+
+// SiLU (ops.h:673-711) and Multiply (ops.h:816-867) on the fused gate|up GEMM output: E(E(silu(gate)) * up) -> fp16
+__device__ __forceinline__ float pf_silu(float x) { return __fdiv_rn(x, __fadd_rn(1.0f, expf_glibc(-x))); }
+
+__global__ void __launch_bounds__(128) k_pf_silu_mul(const int8_t* __restrict__ gq, const uint16_t* __restrict__ gs, int T, int F,
+                                                      __half* __restrict__ act16, float* cap_g, float* cap_u, int capw) {
+    const int nb = F / 32;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)T * nb) return;
+    const int row = (int)(i / nb), b = (int)(i % nb);
+    float g[32], u[32];
+    load_deq32(gq, gs, row, 2 * F, b, g);
+    load_deq32(gq, gs, row, 2 * F, nb + b, u);
+#pragma unroll
+    for (int k = 0; k < 32; k++) g[k] = pf_silu(g[k]);
+    int q[32];
+    uint16_t dh = q8_encode32(g, q);
+    float dd = h2f(dh);
+#pragma unroll
+    for (int k = 0; k < 32; k++) g[k] = __fmul_rn(__fmul_rn((float)q[k], dd), u[k]);
+    dh = q8_encode32(g, q);
+    dd = h2f(dh);
+#pragma unroll
+    for (int k = 0; k < 32; k++) g[k] = __fmul_rn((float)q[k], dd);
+    store_half32(act16 + (size_t)row * F + (size_t)b * 32, g);
+    if (cap_g) for (int k = 0; k < 32; k++) { cap_g[(size_t)row * capw + b * 32 + k] = g[k]; cap_u[(size_t)row * capw + b * 32 + k] = u[k]; }
+}
+
+// dequantised fp32 copies of row `row` for the exact final-norm + lm_head phase of the engine
+__global__ void k_pf_tail(const int8_t* __restrict__ xq, const uint16_t* __restrict__ xs, const int8_t* __restrict__ dq, const uint16_t* __restrict__ ds,
+                          int row, int D, float* __restrict__ res, float* __restrict__ down, float* cap_down, int T, int capw) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= D) return;
+    const size_t o = (size_t)row * D + e, so = (size_t)row * (D / 32) + (e >> 5);
+    res[e] = __fmul_rn((float)xq[o], h2f(xs[so]));
+    down[e] = __fmul_rn((float)dq[o], h2f(ds[so]));
+    if (cap_down)
+        for (int r = 0; r < T; r++)
+            cap_down[(size_t)r * capw + e] = __fmul_rn((float)dq[(size_t)r * D + e], h2f(ds[(size_t)r * (D / 32) + (e >> 5)]));
+}
+
+// =================================================================================================== attention
+// Causal GQA attention of all T rows (ops.h:930-1133).  One CTA = 64 query rows of one head, 4 warps x 16 rows,
+// keys in tiles of 64, mma.sync m16n8k16 (fp16 in, fp32 accumulate).  Pass A: row maximum and sum of exp.  Pass B:
+// p = exp(s - max) / sum, the Q8 re-encode of the probability row in 32-key blocks (ops.h:996), then the integer
+// codes (exact in fp16) go through the tensor cores against V and the block's fp16 scale is applied to the partial
+// sum, so the only operand rounding on this side is V's.  The output row is re-encoded per 32 channels (ops.h:1084).
+constexpr int PA_LD = 72;           // shared-memory row stride in halves (64 + 8: conflict-free ldmatrix)
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float quad_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// 64 x 64 fp16 tile (rows r0.., 64 columns starting at column c0 of a [T][ld] matrix) -> shared [64][PA_LD]; rows >= T are zero
+__device__ __forceinline__ void pa_load_tile(__half* dst, const __half* __restrict__ src, int r0, int T, int ld, int c0) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int idx = threadIdx.x + 128 * i, r = idx >> 3, ch = idx & 7;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r0 + r < T) v = *reinterpret_cast<const uint4*>(src + (size_t)(r0 + r) * ld + c0 + ch * 8);
+        *reinterpret_cast<uint4*>(dst + r * PA_LD + ch * 8) = v;
+    }
+}
+
+// S[j][*] = (Q_warp . K_tile^T) * 0.125 for the 8 key octets j of the tile, masked on the diagonal tile
+__device__ __forceinline__ void pa_scores(float (&S)[8][4], const uint32_t (&qa)[4][4], uint32_t ks_addr, int lane, bool diag, int qrow0, int key0) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        S[j][0] = S[j][1] = S[j][2] = S[j][3] = 0.0f;
+#pragma unroll
+        for (int kp = 0; kp < 2; kp++) {
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4(ks_addr + (uint32_t)(((8 * j + (lane & 7)) * PA_LD + 32 * kp + (lane >> 3) * 8) * 2), b0, b1, b2, b3);
+            mma_16816(S[j], qa[2 * kp], b0, b1);
+            mma_16816(S[j], qa[2 * kp + 1], b2, b3);
+        }
+    }
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            float s = S[j][c] * 0.125f;                               // scale = 1/sqrt(64), ops.h:1098
+            if (diag) {
+                const int key = key0 + 8 * j + 2 * t + (c & 1), qrow = qrow0 + g + ((c >> 1) << 3);
+                if (key > qrow) s = -INFINITY;                        // ops.h:966-969
+            }
+            S[j][c] = s;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_pf_attn(const __half* __restrict__ q16, const __half* __restrict__ k16, const __half* __restrict__ v16,
+                                                  __half* __restrict__ out16, int T, int n_heads, int gsz, float* cap, int capw) {
+    __shared__ __align__(16) __half Qs[64 * PA_LD];
+    __shared__ __align__(16) __half Ks[64 * PA_LD];
+    __shared__ __align__(16) __half Vs[64 * PA_LD];
+    const int n_qt = (T + 63) / 64;
+    const int qt = n_qt - 1 - (int)(blockIdx.x / n_heads);          // longest rows first
+    const int h = blockIdx.x % n_heads, grp = h / gsz;
+    const int E = n_heads * 64, KV = (n_heads / gsz) * 64;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int q0 = qt * 64;
+
+    pa_load_tile(Qs, q16, q0, T, E, h * 64);
+    __syncthreads();
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++)
+        ldsm_x4(smem_u32(Qs) + (uint32_t)(((16 * warp + (lane & 15)) * PA_LD + 16 * kk + (lane >> 4) * 8) * 2), qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3]);
+    const uint32_t ks_addr = smem_u32(Ks), vs_addr = smem_u32(Vs);
+    const int qrow0 = q0 + 16 * warp;
+
+    // ---- pass A: running maximum and sum (ops.h:972-988)
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+    for (int kt = 0; kt <= qt; kt++) {
+        __syncthreads();
+        pa_load_tile(Ks, k16, kt * 64, T, KV, grp * 64);
+        __syncthreads();
+        float S[8][4];
+        pa_scores(S, qa, ks_addr, lane, kt == qt, qrow0, kt * 64);
+        float t0 = -INFINITY, t1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { t0 = fmaxf(t0, fmaxf(S[j][0], S[j][1])); t1 = fmaxf(t1, fmaxf(S[j][2], S[j][3])); }
+        t0 = quad_max(t0); t1 = quad_max(t1);
+        const float n0 = fmaxf(m0, t0), n1 = fmaxf(m1, t1);
+        l0 *= __expf(m0 - n0); l1 *= __expf(m1 - n1);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            l0 += __expf(S[j][0] - n0) + __expf(S[j][1] - n0);
+            l1 += __expf(S[j][2] - n1) + __expf(S[j][3] - n1);
+        }
+        m0 = n0; m1 = n1;
+    }
+    l0 = quad_sum(l0); l1 = quad_sum(l1);
+
+    // ---- pass B: probabilities, Q8 re-encode per 32 keys, P.V
+    float O[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; j++) O[j][0] = O[j][1] = O[j][2] = O[j][3] = 0.0f;
+    for (int kt = 0; kt <= qt; kt++) {
+        __syncthreads();
+        pa_load_tile(Ks, k16, kt * 64, T, KV, grp * 64);
+        pa_load_tile(Vs, v16, kt * 64, T, KV, grp * 64);
+        __syncthreads();
+        float S[8][4];
+        pa_scores(S, qa, ks_addr, lane, kt == qt, qrow0, kt * 64);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            S[j][0] = __fdiv_rn(__expf(S[j][0] - m0), l0); S[j][1] = __fdiv_rn(__expf(S[j][1] - m0), l0);
+            S[j][2] = __fdiv_rn(__expf(S[j][2] - m1), l1); S[j][3] = __fdiv_rn(__expf(S[j][3] - m1), l1);
+        }
+#pragma unroll
+        for (int bb = 0; bb < 2; bb++) {                              // one Q8 block = 32 keys = 4 octets
+            float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+            for (int j = 4 * bb; j < 4 * bb + 4; j++) { a0 = fmaxf(a0, fmaxf(S[j][0], S[j][1])); a1 = fmaxf(a1, fmaxf(S[j][2], S[j][3])); }
+            a0 = quad_max(a0); a1 = quad_max(a1);
+            const float de0 = __fdiv_rn(a0, 127.0f), de1 = __fdiv_rn(a1, 127.0f);
+            const float sc0 = (de0 != 0.0f) ? __fdiv_rn(1.0f, de0) : 0.0f, sc1 = (de1 != 0.0f) ? __fdiv_rn(1.0f, de1) : 0.0f;
+            const float dq0 = h2f(f2h(de0)), dq1 = h2f(f2h(de1));
+            float Ob[8][4];
+#pragma unroll
+            for (int j = 0; j < 8; j++) Ob[j][0] = Ob[j][1] = Ob[j][2] = Ob[j][3] = 0.0f;
+#pragma unroll
+            for (int kk = 2 * bb; kk < 2 * bb + 2; kk++) {            // 16 keys per MMA k-step
+                uint32_t pa[4];
+                pa[0] = pack_h2(roundf(__fmul_rn(S[2 * kk][0], sc0)), roundf(__fmul_rn(S[2 * kk][1], sc0)));
+                pa[1] = pack_h2(roundf(__fmul_rn(S[2 * kk][2], sc1)), roundf(__fmul_rn(S[2 * kk][3], sc1)));
+                pa[2] = pack_h2(roundf(__fmul_rn(S[2 * kk + 1][0], sc0)), roundf(__fmul_rn(S[2 * kk + 1][1], sc0)));
+                pa[3] = pack_h2(roundf(__fmul_rn(S[2 * kk + 1][2], sc1)), roundf(__fmul_rn(S[2 * kk + 1][3], sc1)));
+#pragma unroll
+                for (int jp = 0; jp < 4; jp++) {
+                    uint32_t b0, b1, b2, b3;
+                    ldsm_x4_t(vs_addr + (uint32_t)(((16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8) * PA_LD + 16 * jp + (lane >> 4) * 8) * 2), b0, b1, b2, b3);
+                    mma_16816(Ob[2 * jp], pa, b0, b1);
+                    mma_16816(Ob[2 * jp + 1], pa, b2, b3);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                O[j][0] = fmaf(dq0, Ob[j][0], O[j][0]); O[j][1] = fmaf(dq0, Ob[j][1], O[j][1]);
+                O[j][2] = fmaf(dq1, Ob[j][2], O[j][2]); O[j][3] = fmaf(dq1, Ob[j][3], O[j][3]);
+            }
+        }
+    }
+
+    // ---- output row: Q8 re-encode per 32 channels (ops.h:1084), fp16 operand of the o-projection
+    const int r0 = qrow0 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int cb = 0; cb < 2; cb++) {
+        float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+        for (int j = 4 * cb; j < 4 * cb + 4; j++) { a0 = fmaxf(a0, fmaxf(fabsf(O[j][0]), fabsf(O[j][1]))); a1 = fmaxf(a1, fmaxf(fabsf(O[j][2]), fabsf(O[j][3]))); }
+        a0 = quad_max(a0); a1 = quad_max(a1);
+        const float de0 = __fdiv_rn(a0, 127.0f), de1 = __fdiv_rn(a1, 127.0f);
+        const float sc0 = (de0 != 0.0f) ? __fdiv_rn(1.0f, de0) : 0.0f, sc1 = (de1 != 0.0f) ? __fdiv_rn(1.0f, de1) : 0.0f;
+        const float dq0 = h2f(f2h(de0)), dq1 = h2f(f2h(de1));
+#pragma unroll
+        for (int j = 4 * cb; j < 4 * cb + 4; j++) {
+            const int col = h * 64 + 8 * j + 2 * t;
+            const float y0 = __fmul_rn(roundf(__fmul_rn(O[j][0], sc0)), dq0), y1 = __fmul_rn(roundf(__fmul_rn(O[j][1], sc0)), dq0);
+            const float y2 = __fmul_rn(roundf(__fmul_rn(O[j][2], sc1)), dq1), y3 = __fmul_rn(roundf(__fmul_rn(O[j][3], sc1)), dq1);
+            if (r0 < T) {
+                *reinterpret_cast<uint32_t*>(out16 + (size_t)r0 * E + col) = pack_h2(y0, y1);
+                if (cap) { cap[(size_t)r0 * capw + col] = y0; cap[(size_t)r0 * capw + col + 1] = y1; }
+            }
+            if (r1 < T) {
+                *reinterpret_cast<uint32_t*>(out16 + (size_t)r1 * E + col) = pack_h2(y2, y3);
+                if (cap) { cap[(size_t)r1 * capw + col] = y2; cap[(size_t)r1 * capw + col + 1] = y3; }
+            }
+        }
+    }
+}
+
+// =================================================================================================== host side
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled tmap_encoder() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+    }
+    return fn;
+}
+
+// fp16 matrix [rows][cols] (cols contiguous) -> tensor map with a [box_rows][64] box, 128-byte swizzle, zero fill out of bounds
+static int make_tmap(CUtensorMap* m, const void* base, int rows, int cols, int box_rows) {
+    PFN_tmapEncodeTiled enc = tmap_encoder();
+    if (!enc) return fail(GTB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)cols * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)PF_BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(GTB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %d x %d matrix", (int)r, rows, cols);
+    return GTB_OK;
+}
+
+template <int BN, int EPI>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, void* out0, void* out1) {
+    using Cfg = PfGemmCfg<BN>;
+    static bool attr = false;
+    if (!attr) {
+        GTB_CUDA(cudaFuncSetAttribute(k_pf_gemm<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr = true;
+    }
+    const int n_tiles = ((M + PF_BM - 1) / PF_BM) * ((N + BN - 1) / BN);
+    const int grid = n_tiles < ctx().sm_count ? n_tiles : ctx().sm_count;
+    k_pf_gemm<BN, EPI><<<grid, PF_THREADS, Cfg::SMEM, ctx().stream>>>(ta, tb, M, N, K, out0, out1);
+    GTB_LAUNCHED();
+    return GTB_OK;
+}
+
+static int gemm_q8(const CUtensorMap& ta, const CUtensorMap& tb, int bn, int M, int N, int K, int8_t* oq, uint16_t* os) {
+    return bn == 256 ? launch_gemm<256, EPI_Q8>(ta, tb, M, N, K, oq, os) : launch_gemm<128, EPI_Q8>(ta, tb, M, N, K, oq, os);
+}
+
+int pf_gemm_f32(const void* d_A16, const void* d_W16, float* d_C, int M, int N, int K, int bn) {
+    GTB_ARG(M > 0 && N > 0 && K > 0 && K % PF_BK == 0 && N % 32 == 0 && (bn == 128 || bn == 256));
+    CUtensorMap ta, tb;
+    int r = make_tmap(&ta, d_A16, M, K, PF_BM);
+    if (r) return r;
+    r = make_tmap(&tb, d_W16, N, K, bn);
+    if (r) return r;
+    return bn == 256 ? launch_gemm<256, EPI_F32>(ta, tb, M, N, K, d_C, nullptr) : launch_gemm<128, EPI_F32>(ta, tb, M, N, K, d_C, nullptr);
+}
+
+struct PfLayerW {
+    __half* w[4] = {nullptr, nullptr, nullptr, nullptr};      // q|k|v, o, gate|up, down as fp16 [N][K]
+    CUtensorMap tm[4];
+    bool set[4] = {false, false, false, false};
+};
+
+struct PfPlan {
+    gtb_model_config cfg{};
+    int E = 0, F = 0, KV = 0, NQKV = 0, Tcap = 0;
+    int bn[4] = {256, 256, 256, 256};
+    std::vector<PfLayerW> L;
+    // activations for up to Tcap rows
+    int8_t *xq = nullptr, *qkvq = nullptr, *oq = nullptr, *guq = nullptr;
+    uint16_t *xs = nullptr, *qkvs = nullptr, *os = nullptr, *gus = nullptr;
+    __half *xn16 = nullptr, *q16 = nullptr, *k16 = nullptr, *v16 = nullptr, *attn16 = nullptr, *act16 = nullptr;
+    size_t bytes = 0;
+    int64_t launches_last = 0;
+};
+
+static int pf_alloc(PfPlan* p, void** ptr, size_t n) {
+    GTB_CUDA(cudaMalloc(ptr, n));
+    p->bytes += n;
+    ctx().mem += (int64_t)n;
+    return GTB_OK;
+}
+
+int pf_create(PfPlan** out, const gtb_model_config& cfg) {
+    GTB_ARG(cfg.wdtype == GTB_Q8 || cfg.wdtype == GTB_Q4);
+    auto* p = new PfPlan();
+    p->cfg = cfg;
+    p->E = cfg.n_embd; p->F = cfg.n_ffn; p->KV = 64 * cfg.n_groups; p->NQKV = p->E + 2 * p->KV;
+    p->Tcap = cfg.max_ctx < PF_BM ? PF_BM : cfg.max_ctx;      // TMA boxes are 128 rows tall
+    p->L.resize(cfg.n_layers);
+    const int N[4] = {p->NQKV, p->E, 2 * p->F, p->E};
+    for (int w = 0; w < 4; w++) p->bn[w] = (N[w] >= 1024) ? 256 : 128;
+    const size_t T = (size_t)p->Tcap;
+    int r = 0;
+    r |= pf_alloc(p, (void**)&p->xq, T * p->E); r |= pf_alloc(p, (void**)&p->xs, T * (p->E / 32) * 2);
+    r |= pf_alloc(p, (void**)&p->qkvq, T * p->NQKV); r |= pf_alloc(p, (void**)&p->qkvs, T * (p->NQKV / 32) * 2);
+    r |= pf_alloc(p, (void**)&p->oq, T * p->E); r |= pf_alloc(p, (void**)&p->os, T * (p->E / 32) * 2);
+    r |= pf_alloc(p, (void**)&p->guq, T * 2 * p->F); r |= pf_alloc(p, (void**)&p->gus, T * (2 * p->F / 32) * 2);
+    r |= pf_alloc(p, (void**)&p->xn16, T * p->E * 2); r |= pf_alloc(p, (void**)&p->q16, T * p->E * 2);
+    r |= pf_alloc(p, (void**)&p->k16, T * p->KV * 2); r |= pf_alloc(p, (void**)&p->v16, T * p->KV * 2);
+    r |= pf_alloc(p, (void**)&p->attn16, T * p->E * 2); r |= pf_alloc(p, (void**)&p->act16, T * p->F * 2);
+    if (r) { pf_destroy(p); return r; }
+    // rows beyond T are read by the last row tile (their results are never stored): keep them finite
+    cudaMemsetAsync(p->xn16, 0, T * p->E * 2, ctx().stream);
+    cudaMemsetAsync(p->attn16, 0, T * p->E * 2, ctx().stream);
+    cudaMemsetAsync(p->act16, 0, T * p->F * 2, ctx().stream);
+    *out = p;
+    return GTB_OK;
+}
+
+void pf_destroy(PfPlan* p) {
+    if (!p) return;
+    for (auto& l : p->L) for (int w = 0; w < 4; w++) cudaFree(l.w[w]);
+    void* bufs[] = {p->xq, p->xs, p->qkvq, p->qkvs, p->oq, p->os, p->guq, p->gus, p->xn16, p->q16, p->k16, p->v16, p->attn16, p->act16};
+    for (void* b : bufs) cudaFree(b);
+    ctx().mem -= (int64_t)p->bytes;
+    delete p;
+}
+
+int pf_set_weight(PfPlan* p, int layer, int which, int wdtype, const void* d_data, const uint16_t* d_scales, int rows, int cols) {
+    GTB_ARG(p && layer >= 0 && layer < (int)p->L.size() && which >= 0 && which < 4 && (wdtype == GTB_Q8 || wdtype == GTB_Q4));
+    const int N[4] = {p->NQKV, p->E, 2 * p->F, p->E}, K[4] = {p->E, p->E, p->E, p->F};
+    GTB_ARG(rows == N[which] && cols == K[which]);
+    PfLayerW& l = p->L[layer];
+    const size_t n = (size_t)rows * cols;
+    if (!l.w[which]) { int r = pf_alloc(p, (void**)&l.w[which], n * 2); if (r) return r; }
+    const size_t nblk = n / 32;
+    k_pf_w16<<<(unsigned)((nblk + 255) / 256), 256, 0, ctx().stream>>>(d_data, d_scales, wdtype, nblk, l.w[which]);
+    GTB_LAUNCHED();
+    int r = make_tmap(&l.tm[which], l.w[which], rows, cols, p->bn[which]);
+    if (r) return r;
+    l.set[which] = true;
+    return GTB_OK;
+}
+
+bool pf_weights_ready(const PfPlan* p) {
+    for (auto& l : p->L) for (int w = 0; w < 4; w++) if (!l.set[w]) return false;
+    return true;
+}
+size_t pf_bytes(const PfPlan* p) { return p->bytes; }
+int64_t pf_launches_last(const PfPlan* p) { return p->launches_last; }
+
+int pf_run(PfPlan* p, const PfRun& r) {
+    GTB_ARG(p && r.T > 0 && r.T <= p->cfg.max_ctx && r.n_layers_run > 0 && r.n_layers_run <= p->cfg.n_layers);
+    if (!pf_weights_ready(p)) return fail(GTB_ERR_STATE, "fast prefill: fp16 weight copies are not built");
+    cudaStream_t st = ctx().stream;
+    const int T = r.T, E = p->E, F = p->F, KV = p->KV, NQKV = p->NQKV;
+    const int nh = p->cfg.n_heads, ng = p->cfg.n_groups, nl = p->cfg.n_layers;
+    const int64_t l0 = ctx().launches;
+    CUtensorMap ta_xn, ta_attn, ta_act;
+    const int Tm = T < PF_BM ? PF_BM : T;
+    int rc = make_tmap(&ta_xn, p->xn16, Tm, E, PF_BM);
+    if (!rc) rc = make_tmap(&ta_attn, p->attn16, Tm, E, PF_BM);
+    if (!rc) rc = make_tmap(&ta_act, p->act16, Tm, F, PF_BM);
+    if (rc) return rc;
+    auto capp = [&](int layer, int aid) -> float* {
+        if (!r.cap) return nullptr;
+        if (aid == GTB_A_EMB) return r.cap + (size_t)nl * 12 * T * r.capw;
+        return r.cap + ((size_t)layer * 12 + (aid - GTB_A_ATTN_NORM)) * T * r.capw;
+    };
+    const int nbE = E / 32;
+    {
+        const size_t n = (size_t)T * nbE;
+        k_pf_embed<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(r.embed->data, r.embed->scales, r.embed->dtype, r.d_tokens, T, E, p->xq, p->xs,
+                                                                 capp(0, GTB_A_EMB), r.capw);
+        GTB_LAUNCHED();
+    }
+    const unsigned row_grid = (unsigned)((T + 3) / 4);
+    k_pf_add_norm<<<row_grid, 128, 0, st>>>(p->xq, p->xs, nullptr, nullptr, r.layers[0].attn_norm, p->xn16, T, E, nullptr, nullptr,
+                                            capp(0, GTB_A_ATTN_NORM), r.capw);
+    GTB_LAUNCHED();
+    for (int li = 0; li < r.n_layers_run; li++) {
+        const PfLayerIO& io = r.layers[li];
+        PfLayerW& w = p->L[li];
+        rc = gemm_q8(ta_xn, w.tm[0], p->bn[0], T, NQKV, E, p->qkvq, p->qkvs);
+        if (rc) return rc;
+        {
+            const size_t n = (size_t)T * (nh + 2 * ng);
+            k_pf_rope_kv<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p->qkvq, p->qkvs, T, nh, ng, r.rope_cos, r.rope_sin, p->q16, p->k16, p->v16,
+                                                                       io.kq, io.ks, io.vq, io.vs, capp(li, GTB_A_Q), capp(li, GTB_A_K), capp(li, GTB_A_V), r.capw);
+            GTB_LAUNCHED();
+        }
+        k_pf_attn<<<(unsigned)(((T + 63) / 64) * nh), 128, 0, st>>>(p->q16, p->k16, p->v16, p->attn16, T, nh, nh / ng, capp(li, GTB_A_ATTN_OUT), r.capw);
+        GTB_LAUNCHED();
+        rc = gemm_q8(ta_attn, w.tm[1], p->bn[1], T, E, E, p->oq, p->os);
+        if (rc) return rc;
+        k_pf_add_norm<<<row_grid, 128, 0, st>>>(p->xq, p->xs, p->oq, p->os, io.ffn_norm, p->xn16, T, E, capp(li, GTB_A_O), capp(li, GTB_A_INP_RES),
+                                                capp(li, GTB_A_FFN_NORM), r.capw);
+        GTB_LAUNCHED();
+        rc = gemm_q8(ta_xn, w.tm[2], p->bn[2], T, 2 * F, E, p->guq, p->gus);
+        if (rc) return rc;
+        {
+            const size_t n = (size_t)T * (F / 32);
+            k_pf_silu_mul<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p->guq, p->gus, T, F, p->act16, capp(li, GTB_A_GATE), capp(li, GTB_A_UP), r.capw);
+            GTB_LAUNCHED();
+        }
+        rc = gemm_q8(ta_act, w.tm[3], p->bn[3], T, E, F, p->oq, p->os);
+        if (rc) return rc;
+        if (li + 1 < r.n_layers_run) {
+            k_pf_add_norm<<<row_grid, 128, 0, st>>>(p->xq, p->xs, p->oq, p->os, r.layers[li + 1].attn_norm, p->xn16, T, E, capp(li, GTB_A_DOWN),
+                                                    capp(li, GTB_A_ATTN_RES), capp(li + 1, GTB_A_ATTN_NORM), r.capw);
+            GTB_LAUNCHED();
+        } else {
+            k_pf_tail<<<(E + 255) / 256, 256, 0, st>>>(p->xq, p->xs, p->oq, p->os, T - 1, E, r.last_res, r.last_down, capp(li, GTB_A_DOWN), T, r.capw);
+            GTB_LAUNCHED();
+        }
+    }
+    p->launches_last = ctx().launches - l0;
+    return GTB_OK;
+}
+
+}  // namespace gtb
