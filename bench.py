@@ -162,6 +162,64 @@ def cpu_baseline(wdt, seconds_budget=20.0):
             "sample": f"{done} decode steps after a {n_prompt}-token prompt (t = {n_prompt + 1}..{n_prompt + done}), same synthetic weights"}
 
 
+def prefill_flops(cfg, T):
+    """layer linears of T rows + lm_head of the last row + causal attention (QK^T and P.V)."""
+    per_layer = 2 * cfg.n_embd * cfg.n_embd + 2 * cfg.kv_dim * cfg.n_embd + 3 * cfg.n_ffn * cfg.n_embd
+    return (2.0 * cfg.n_layers * per_layer * T + 2.0 * cfg.n_vocab * cfg.n_embd
+            + cfg.n_layers * cfg.n_heads * 2.0 * 2 * cfg.d_head * T * (T + 1) / 2)
+
+
+def prefill_section(capi, torch, stream, iters=5, warmup=3, T=2048, cpu=True):
+    """BASELINE.json configs[3]: Q8 prefill of a 2048-token synthetic prompt through the batched tcgen05 path
+    (gtb_engine_prefill_fast).  Token ids start on the host in both numbers; e2e also reads the logits back."""
+    cfg = W.TINYLLAMA
+    eng = capi.Engine(cfg, T + 128, W.Q8).load(W.synth_weights(cfg, W.Q8, seed=1))
+    prompt = W.synth_prompt(7, T, cfg.n_vocab)
+    for _ in range(warmup):
+        eng.prefill_fast(prompt)
+    capi.sync()
+    l0 = capi.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    ev[0].record(stream)
+    for i in range(iters):
+        eng.prefill_fast(prompt)
+        ev[i + 1].record(stream)
+    capi.sync()
+    torch.cuda.synchronize()
+    ms = float(np.median([ev[i].elapsed_time(ev[i + 1]) for i in range(iters)]))
+    launches = (capi.launch_count() - l0) // iters
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        eng.prefill_fast(prompt)
+        lg = eng.read_logits()
+    e2e_s = (time.perf_counter() - t0) / iters
+    eng.close()
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    peak = float(peaks.get("bf16_tflops", 1590.0))
+    fl = prefill_flops(cfg, T)
+    out = {"metric": "prefill_tokens_per_s", "value": T / (ms * 1e-3), "unit": "tokens/s", "ms_per_prefill": ms,
+           "config": {"workload": f"TinyLlama-1.1B Q8 (-q8) prefill of a {T}-token synthetic prompt (BASELINE.json configs[3])",
+                      "path": "gtb_engine_prefill_fast: tcgen05/TMEM GEMMs fed by TMA + tensor-core causal GQA attention; tolerance-checked "
+                              "against the reference (tests/test_prefill_gpu.py), the order-exact row-by-row path stays available"},
+           "roofline": {"bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                        "frac": fl / (ms * 1e-3) / 1e12 / peak, "flops_per_prefill": fl,
+                        "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if peaks else "fallback (B200_PROFILING.md)"},
+           "e2e": {"value": T / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": T * 4, "d2h_bytes_per_step": cfg.n_vocab * 4},
+           "gpu_launches": int(launches), "argmax_last_row": int(np.argmax(lg))}
+    if cpu:
+        import oracle
+        lib = oracle.best()
+        n = 24
+        m = lib.model(cfg, 2 * n + 64, W.Q8).load(W.synth_weights(cfg, W.Q8, seed=1))
+        t0 = time.perf_counter()
+        m.logits(prompt[:n], 0)
+        dt = time.perf_counter() - t0
+        m.close()
+        out["cpu_baseline"] = {"value": n / dt, "unit": "tokens/s", "cores": os.cpu_count() or 1, "kind": lib.kind,
+                               "sample": f"prefill of the first {n} prompt tokens (the reference's prefill is row-by-row GEMV, ops.h:632)"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -171,6 +229,7 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-prefill", action="store_true", help="skip the configs[3] prefill measurement appended to the N=1 line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     wdt, cfg_idx, desc = WORKLOADS[args.workload]
@@ -274,6 +333,9 @@ def main():
         if not args.no_e2e:
             out["e2e"] = {"value": units / (e2e_ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": 4,
                           "d2h_bytes_per_step": cfg.n_vocab * 4}
+        if world == 1 and not args.no_prefill:
+            eng.close()
+            out["prefill"] = prefill_section(capi, torch, stream, cpu=not args.no_cpu_baseline)
         if world == 1 and not args.no_cpu_baseline:
             eng.close()
             out["cpu_baseline"] = cpu_baseline(wdt)

@@ -497,7 +497,9 @@ __global__ void __launch_bounds__(128) k_pf_rope_kv(const int8_t* __restrict__ c
 }
 
 // SiLU (ops.h:673-711) and Multiply (ops.h:816-867) on the fused gate|up GEMM output: E(E(silu(gate)) * up) -> fp16
-__device__ __forceinline__ float pf_silu(float x) { return __fdiv_rn(x, __fadd_rn(1.0f, expf_glibc(-x))); }
+// __expf is within 2 ulp of the reference's correctly rounded expf: a 1e-7 relative change of silu(x), far below the
+// fp16 operand rounding of this path (the exact path keeps glibc's algorithm, gtb_dev.cuh expf_glibc)
+__device__ __forceinline__ float pf_silu(float x) { return __fdiv_rn(x, __fadd_rn(1.0f, __expf(-x))); }
 
 __global__ void __launch_bounds__(128) k_pf_silu_mul(const int8_t* __restrict__ gq, const uint16_t* __restrict__ gs, int T, int F,
                                                       __half* __restrict__ act16, float* cap_g, float* cap_u, int capw) {
@@ -567,18 +569,34 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// 64 x 64 fp16 tile (rows r0.., 64 columns starting at column c0 of a [T][ld] matrix) -> shared [64][PA_LD]; rows >= T are zero
-__device__ __forceinline__ void pa_load_tile(__half* dst, const __half* __restrict__ src, int r0, int T, int ld, int c0) {
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rne_int(float x) {        // nearest integer for 0 <= x < 2^22 (ties to even)
+    return __fsub_rn(__fadd_rn(x, 12582912.0f), 12582912.0f);
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;                          // 0: the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// 64 x 64 fp16 tile (rows r0.., 64 columns starting at column c0 of a [T][ld] matrix) -> shared [64][PA_LD], asynchronously;
+// rows >= T are zero
+__device__ __forceinline__ void pa_load_tile_async(uint32_t dst, const __half* __restrict__ src, int r0, int T, int ld, int c0) {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int idx = threadIdx.x + 128 * i, r = idx >> 3, ch = idx & 7;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (r0 + r < T) v = *reinterpret_cast<const uint4*>(src + (size_t)(r0 + r) * ld + c0 + ch * 8);
-        *reinterpret_cast<uint4*>(dst + r * PA_LD + ch * 8) = v;
+        const bool ok = r0 + r < T;
+        const int rr = ok ? r0 + r : T - 1;
+        cp_async16(dst + (uint32_t)((r * PA_LD + ch * 8) * 2), src + (size_t)rr * ld + c0 + ch * 8, ok);
     }
 }
 
-// S[j][*] = (Q_warp . K_tile^T) * 0.125 for the 8 key octets j of the tile, masked on the diagonal tile
+// raw S[j][*] = Q_warp . K_tile^T for the 8 key octets j of the tile, -inf above the diagonal (ops.h:966-969)
 __device__ __forceinline__ void pa_scores(float (&S)[8][4], const uint32_t (&qa)[4][4], uint32_t ks_addr, int lane, bool diag, int qrow0, int key0) {
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -591,104 +609,119 @@ __device__ __forceinline__ void pa_scores(float (&S)[8][4], const uint32_t (&qa)
             mma_16816(S[j], qa[2 * kp + 1], b2, b3);
         }
     }
-    const int g = lane >> 2, t = lane & 3;
+    if (diag) {
+        const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < 8; j++)
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            float s = S[j][c] * 0.125f;                               // scale = 1/sqrt(64), ops.h:1098
-            if (diag) {
+            for (int c = 0; c < 4; c++) {
                 const int key = key0 + 8 * j + 2 * t + (c & 1), qrow = qrow0 + g + ((c >> 1) << 3);
-                if (key > qrow) s = -INFINITY;                        // ops.h:966-969
+                if (key > qrow) S[j][c] = -INFINITY;
             }
-            S[j][c] = s;
-        }
     }
 }
+
+// scores are kept unscaled; exp(0.125 * (s - max)) = 2^((s - max) * PA_C)    (scale = 1/sqrt(64), ops.h:1098)
+#define PA_C (0.125f * 1.4426950408889634f)
 
 __global__ void __launch_bounds__(128) k_pf_attn(const __half* __restrict__ q16, const __half* __restrict__ k16, const __half* __restrict__ v16,
                                                   __half* __restrict__ out16, int T, int n_heads, int gsz, float* cap, int capw) {
     __shared__ __align__(16) __half Qs[64 * PA_LD];
-    __shared__ __align__(16) __half Ks[64 * PA_LD];
-    __shared__ __align__(16) __half Vs[64 * PA_LD];
+    __shared__ __align__(16) __half Ks[2][64 * PA_LD];
+    __shared__ __align__(16) __half Vs[2][64 * PA_LD];
     const int n_qt = (T + 63) / 64;
     const int qt = n_qt - 1 - (int)(blockIdx.x / n_heads);          // longest rows first
     const int h = blockIdx.x % n_heads, grp = h / gsz;
     const int E = n_heads * 64, KV = (n_heads / gsz) * 64;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int q0 = qt * 64;
+    const uint32_t ks_base = smem_u32(Ks[0]), vs_base = smem_u32(Vs[0]);
+    auto ks_addr = [&](int b) { return ks_base + (uint32_t)(b * 64 * PA_LD * 2); };
+    auto vs_addr = [&](int b) { return vs_base + (uint32_t)(b * 64 * PA_LD * 2); };
 
-    pa_load_tile(Qs, q16, q0, T, E, h * 64);
+    pa_load_tile_async(smem_u32(Qs), q16, q0, T, E, h * 64);
+    pa_load_tile_async(ks_addr(0), k16, 0, T, KV, grp * 64);
+    cp_async_commit();
+    cp_async_wait_all();
     __syncthreads();
     uint32_t qa[4][4];
 #pragma unroll
     for (int kk = 0; kk < 4; kk++)
         ldsm_x4(smem_u32(Qs) + (uint32_t)(((16 * warp + (lane & 15)) * PA_LD + 16 * kk + (lane >> 4) * 8) * 2), qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3]);
-    const uint32_t ks_addr = smem_u32(Ks), vs_addr = smem_u32(Vs);
     const int qrow0 = q0 + 16 * warp;
 
-    // ---- pass A: running maximum and sum (ops.h:972-988)
+    // ---- pass A: row maximum and sum of exp (ops.h:972-988); K tiles double-buffered with cp.async
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
     for (int kt = 0; kt <= qt; kt++) {
-        __syncthreads();
-        pa_load_tile(Ks, k16, kt * 64, T, KV, grp * 64);
-        __syncthreads();
+        const int cur = kt & 1;
+        if (kt > 0) { cp_async_wait_all(); __syncthreads(); }
+        // the last prefetch of pass A brings tile 0 of pass B (K again, plus V)
+        const int nk = (kt < qt) ? kt + 1 : 0;
+        pa_load_tile_async(ks_addr(cur ^ 1), k16, nk * 64, T, KV, grp * 64);
+        if (kt == qt) pa_load_tile_async(vs_addr(cur ^ 1), v16, 0, T, KV, grp * 64);
+        cp_async_commit();
         float S[8][4];
-        pa_scores(S, qa, ks_addr, lane, kt == qt, qrow0, kt * 64);
+        pa_scores(S, qa, ks_addr(cur), lane, kt == qt, qrow0, kt * 64);
         float t0 = -INFINITY, t1 = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 8; j++) { t0 = fmaxf(t0, fmaxf(S[j][0], S[j][1])); t1 = fmaxf(t1, fmaxf(S[j][2], S[j][3])); }
         t0 = quad_max(t0); t1 = quad_max(t1);
         const float n0 = fmaxf(m0, t0), n1 = fmaxf(m1, t1);
-        l0 *= __expf(m0 - n0); l1 *= __expf(m1 - n1);
+        l0 *= ex2_approx((m0 - n0) * PA_C); l1 *= ex2_approx((m1 - n1) * PA_C);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            l0 += __expf(S[j][0] - n0) + __expf(S[j][1] - n0);
-            l1 += __expf(S[j][2] - n1) + __expf(S[j][3] - n1);
+            l0 += ex2_approx((S[j][0] - n0) * PA_C) + ex2_approx((S[j][1] - n0) * PA_C);
+            l1 += ex2_approx((S[j][2] - n1) * PA_C) + ex2_approx((S[j][3] - n1) * PA_C);
         }
         m0 = n0; m1 = n1;
     }
     l0 = quad_sum(l0); l1 = quad_sum(l1);
+    const float pinv0 = __fdiv_rn(1.0f, l0), pinv1 = __fdiv_rn(1.0f, l1);
 
-    // ---- pass B: probabilities, Q8 re-encode per 32 keys, P.V
+    // ---- pass B: probabilities, Q8 re-encode per 32 keys, P.V.  Tile kt of pass B sits in buffer (qt + 1 + kt) & 1.
     float O[8][4];
 #pragma unroll
     for (int j = 0; j < 8; j++) O[j][0] = O[j][1] = O[j][2] = O[j][3] = 0.0f;
     for (int kt = 0; kt <= qt; kt++) {
+        const int cur = (qt + 1 + kt) & 1;
+        cp_async_wait_all();
         __syncthreads();
-        pa_load_tile(Ks, k16, kt * 64, T, KV, grp * 64);
-        pa_load_tile(Vs, v16, kt * 64, T, KV, grp * 64);
-        __syncthreads();
+        if (kt < qt) {
+            pa_load_tile_async(ks_addr(cur ^ 1), k16, (kt + 1) * 64, T, KV, grp * 64);
+            pa_load_tile_async(vs_addr(cur ^ 1), v16, (kt + 1) * 64, T, KV, grp * 64);
+            cp_async_commit();
+        }
         float S[8][4];
-        pa_scores(S, qa, ks_addr, lane, kt == qt, qrow0, kt * 64);
+        pa_scores(S, qa, ks_addr(cur), lane, kt == qt, qrow0, kt * 64);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            S[j][0] = __fdiv_rn(__expf(S[j][0] - m0), l0); S[j][1] = __fdiv_rn(__expf(S[j][1] - m0), l0);
-            S[j][2] = __fdiv_rn(__expf(S[j][2] - m1), l1); S[j][3] = __fdiv_rn(__expf(S[j][3] - m1), l1);
+        for (int j = 0; j < 8; j++) {                                 // e = exp(s - max), ops.h:982-988
+            S[j][0] = ex2_approx((S[j][0] - m0) * PA_C); S[j][1] = ex2_approx((S[j][1] - m0) * PA_C);
+            S[j][2] = ex2_approx((S[j][2] - m1) * PA_C); S[j][3] = ex2_approx((S[j][3] - m1) * PA_C);
         }
 #pragma unroll
-        for (int bb = 0; bb < 2; bb++) {                              // one Q8 block = 32 keys = 4 octets
+        for (int bb = 0; bb < 2; bb++) {                              // one Q8 block = 32 keys = 4 octets (ops.h:996)
             float a0 = 0.0f, a1 = 0.0f;
 #pragma unroll
             for (int j = 4 * bb; j < 4 * bb + 4; j++) { a0 = fmaxf(a0, fmaxf(S[j][0], S[j][1])); a1 = fmaxf(a1, fmaxf(S[j][2], S[j][3])); }
-            a0 = quad_max(a0); a1 = quad_max(a1);
+            a0 = quad_max(a0) * pinv0; a1 = quad_max(a1) * pinv1;     // largest probability of the block (p = e / sum, ops.h:991-994)
             const float de0 = __fdiv_rn(a0, 127.0f), de1 = __fdiv_rn(a1, 127.0f);
-            const float sc0 = (de0 != 0.0f) ? __fdiv_rn(1.0f, de0) : 0.0f, sc1 = (de1 != 0.0f) ? __fdiv_rn(1.0f, de1) : 0.0f;
+            // code = round(p * (1 / delta)) with p = e * pinv: one multiply per element
+            const float f0 = (de0 != 0.0f) ? __fdiv_rn(1.0f, de0) * pinv0 : 0.0f, f1 = (de1 != 0.0f) ? __fdiv_rn(1.0f, de1) * pinv1 : 0.0f;
             const float dq0 = h2f(f2h(de0)), dq1 = h2f(f2h(de1));
             float Ob[8][4];
 #pragma unroll
             for (int j = 0; j < 8; j++) Ob[j][0] = Ob[j][1] = Ob[j][2] = Ob[j][3] = 0.0f;
 #pragma unroll
-            for (int kk = 2 * bb; kk < 2 * bb + 2; kk++) {            // 16 keys per MMA k-step
+            for (int kk = 2 * bb; kk < 2 * bb + 2; kk++) {            // 16 keys per MMA k-step; the integer codes are exact in fp16
                 uint32_t pa[4];
-                pa[0] = pack_h2(roundf(__fmul_rn(S[2 * kk][0], sc0)), roundf(__fmul_rn(S[2 * kk][1], sc0)));
-                pa[1] = pack_h2(roundf(__fmul_rn(S[2 * kk][2], sc1)), roundf(__fmul_rn(S[2 * kk][3], sc1)));
-                pa[2] = pack_h2(roundf(__fmul_rn(S[2 * kk + 1][0], sc0)), roundf(__fmul_rn(S[2 * kk + 1][1], sc0)));
-                pa[3] = pack_h2(roundf(__fmul_rn(S[2 * kk + 1][2], sc1)), roundf(__fmul_rn(S[2 * kk + 1][3], sc1)));
+                pa[0] = pack_h2(rne_int(S[2 * kk][0] * f0), rne_int(S[2 * kk][1] * f0));
+                pa[1] = pack_h2(rne_int(S[2 * kk][2] * f1), rne_int(S[2 * kk][3] * f1));
+                pa[2] = pack_h2(rne_int(S[2 * kk + 1][0] * f0), rne_int(S[2 * kk + 1][1] * f0));
+                pa[3] = pack_h2(rne_int(S[2 * kk + 1][2] * f1), rne_int(S[2 * kk + 1][3] * f1));
 #pragma unroll
                 for (int jp = 0; jp < 4; jp++) {
                     uint32_t b0, b1, b2, b3;
-                    ldsm_x4_t(vs_addr + (uint32_t)(((16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8) * PA_LD + 16 * jp + (lane >> 4) * 8) * 2), b0, b1, b2, b3);
+                    ldsm_x4_t(vs_addr(cur) + (uint32_t)(((16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8) * PA_LD + 16 * jp + (lane >> 4) * 8) * 2), b0, b1, b2, b3);
                     mma_16816(Ob[2 * jp], pa, b0, b1);
                     mma_16816(Ob[2 * jp + 1], pa, b2, b3);
                 }
@@ -877,7 +910,7 @@ int pf_run(PfPlan* p, const PfRun& r) {
     GTB_ARG(p && r.T > 0 && r.T <= p->cfg.max_ctx && r.n_layers_run > 0 && r.n_layers_run <= p->cfg.n_layers);
     if (!pf_weights_ready(p)) return fail(GTB_ERR_STATE, "fast prefill: fp16 weight copies are not built");
     cudaStream_t st = ctx().stream;
-    const int T = r.T, E = p->E, F = p->F, KV = p->KV, NQKV = p->NQKV;
+    const int T = r.T, E = p->E, F = p->F, NQKV = p->NQKV;
     const int nh = p->cfg.n_heads, ng = p->cfg.n_groups, nl = p->cfg.n_layers;
     const int64_t l0 = ctx().launches;
     CUtensorMap ta_xn, ta_attn, ta_act;
