@@ -44,7 +44,7 @@ def rel(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
-@pytest.mark.parametrize("bn", [128, 256])
+@pytest.mark.parametrize("bn", [128, 256, 512])        # 512 = the CTA-pair kernel (256 x 256 tiles, tcgen05 cta_group::2)
 @pytest.mark.parametrize("shape", [(128, 256, 64), (1, 256, 128), (200, 2560, 2048), (333, 2048, 5632), (2048, 512, 2048)])
 def test_tcgen05_gemm_exact_on_integers(capi, shape, bn):
     """Small integers: every product and every partial sum is exact in fp32, so any summation order gives the same bits."""
@@ -134,6 +134,25 @@ def test_batched_prefill_then_decode_runs_in_megakernel(capi):
     if top2[1] - top2[0] > 0.05:
         assert e2.read_tokens(130, 1)[0] == toks[130]
     e.close(); e2.close()
+
+
+def test_fused_epilogues_equal_unfused_kernels(capi):
+    """RoPE/KV-append and SiLU*up run inside the GEMM epilogues; the stand-alone kernels share their arithmetic, so both
+    routes must give the same bits (logits, K/V cache via the next exact row)."""
+    cfg = W.mini_config(n_layers=2, n_vocab=300)
+    wl = list(W.synth_weights(cfg, Q4, seed=8))
+    prompt = W.synth_prompt(9, 150, cfg.n_vocab)
+    outs = []
+    for fused in (1, 0):
+        e = capi.Engine(cfg, 192, Q4).load(wl)
+        e.set_option("pf_fused", fused)
+        e.prefill_fast(prompt)
+        lg = e.read_logits()
+        nxt = e.logits(np.concatenate([prompt, [int(np.argmax(lg))]]).astype(np.int32), 150)
+        outs.append((lg, nxt))
+        e.close()
+    assert np.array_equal(outs[0][0].view(np.uint32), outs[1][0].view(np.uint32))
+    assert np.array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32))
 
 
 def test_batched_prefill_rejects_f16_models(capi):

@@ -312,6 +312,8 @@ struct gtb_engine {
     float* pf_cap = nullptr;         // [n_layers*12 + 1][pf_cap_T][capw] when capture_acv is on
     int pf_cap_T = 0;
     int pf_layers = 0;               // debug: run only the first pf_layers layers (0 = all)
+    int pf_fused = 1;                // RoPE/KV append and SiLU*up inside the GEMM epilogues
+    int pf_2cta = 0;                 // CTA-pair GEMM kernel
 };
 
 namespace {
@@ -821,6 +823,8 @@ int gtb_engine_prefill_fast(gtb_engine_t e, const int32_t* h_tokens, int n_token
     if (r) return r;
     const int E = c.n_embd, F = c.n_ffn, KV = e->kv_dim;
     if (!e->pf) { r = pf_create(&e->pf, c); if (r) return r; }
+    pf_set_fused(e->pf, e->pf_fused != 0);
+    pf_set_two_cta(e->pf, e->pf_2cta != 0);
     if (!pf_weights_ready(e->pf)) {
         for (int li = 0; li < c.n_layers; li++) {
             LayerW& l = e->L[li];
@@ -1012,6 +1016,8 @@ int gtb_engine_set_option(gtb_engine_t e, const char* name, int value) {
     if (!strcmp(name, "pf_ahead")) { GTB_ARG(value >= 0 && value <= 64); e->pf_ahead = value; return GTB_OK; }
     if (!strcmp(name, "prof")) { e->prof = value != 0; return GTB_OK; }
     if (!strcmp(name, "pf_layers")) { GTB_ARG(value >= 0); e->pf_layers = value; return GTB_OK; }
+    if (!strcmp(name, "pf_fused")) { e->pf_fused = value != 0; return GTB_OK; }
+    if (!strcmp(name, "pf_2cta")) { e->pf_2cta = value != 0; return GTB_OK; }
     return fail(GTB_ERR_ARG, "unknown option %s", name);
 }
 

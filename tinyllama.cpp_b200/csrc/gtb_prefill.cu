@@ -162,11 +162,104 @@ __device__ __forceinline__ void store_f32x32(float* dst, const float (&v)[32]) {
     for (int i = 0; i < 8; i++) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
 
+
+// =================================================================================================== fused row-wise cores
+// Arguments of the GEMM epilogues (and of the stand-alone row-wise kernels that share their arithmetic).
+struct PfEpi {
+    void* out0 = nullptr;            // EPI_F32: float C[M][N];  EPI_Q8: int8 codes [M][N]
+    void* out1 = nullptr;            // EPI_Q8: fp16 block scales [M][N/32]
+    // EPI_ROPE (q|k|v projection)
+    const float* rope_cos = nullptr; const float* rope_sin = nullptr;
+    __half *q16 = nullptr, *k16 = nullptr, *v16 = nullptr;
+    uint8_t* kq = nullptr; uint16_t* ks = nullptr; uint8_t* vq = nullptr; uint16_t* vs = nullptr;
+    int nh = 0, ng = 0;
+    // EPI_SILU (gate|up projection, rows interleaved in groups of 32)
+    __half* act16 = nullptr; int F = 0;
+    float *cap0 = nullptr, *cap1 = nullptr, *cap2 = nullptr; int capw = 0;
+};
+
+// __expf is within 2 ulp of the reference's correctly rounded expf: a 1e-7 relative change of silu(x), far below the
+// fp16 operand rounding of this path (the exact path keeps glibc's algorithm, gtb_dev.cuh expf_glibc)
+__device__ __forceinline__ float pf_silu(float x) { return __fdiv_rn(x, __fadd_rn(1.0f, __expf(-x))); }
+
+// encode a raw block and leave its decoded value in place (write_row_from_float + read_row_to_float, ops.h:40-96)
+__device__ __forceinline__ uint16_t pf_roundtrip32(float (&x)[32], int (&q)[32]) {
+    const uint16_t dh = q8_encode32(x, q);
+    const float d = h2f(dh);
+#pragma unroll
+    for (int i = 0; i < 32; i++) x[i] = __fmul_rn((float)q[i], d);
+    return dh;
+}
+
+// One head slot of the q|k|v Linear output of row `row`: x0/x1 = the two decoded Q8 blocks, (q0,dh0)/(q1,dh1) their codes.
+// q and k heads: RoPE (ops.h:714-760) and the second re-encode; k and v: append to the cache in the engine's layout.
+__device__ __forceinline__ void pf_rope_store(const PfEpi& ep, int row, int slot, float (&x0)[32], float (&x1)[32],
+                                              int (&q0)[32], int (&q1)[32], uint16_t dh0, uint16_t dh1) {
+    const int nh = ep.nh, ng = ep.ng, E = nh * 64, KV = ng * 64;
+    const bool is_v = slot >= nh + ng;
+    if (!is_v) {
+        const float4* cp = reinterpret_cast<const float4*>(ep.rope_cos + (size_t)row * 32);
+        const float4* sp = reinterpret_cast<const float4*>(ep.rope_sin + (size_t)row * 32);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float4 c4 = cp[k], s4 = sp[k];
+            const float c[4] = {c4.x, c4.y, c4.z, c4.w}, s[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float a = x0[4 * k + j], b = x1[4 * k + j];
+                x0[4 * k + j] = __fsub_rn(__fmul_rn(a, c[j]), __fmul_rn(b, s[j]));
+                x1[4 * k + j] = __fadd_rn(__fmul_rn(a, s[j]), __fmul_rn(b, c[j]));
+            }
+        }
+        dh0 = pf_roundtrip32(x0, q0);
+        dh1 = pf_roundtrip32(x1, q1);
+    }
+    const int capw = ep.capw;
+    if (slot < nh) {
+        store_half32(ep.q16 + (size_t)row * E + slot * 64, x0);
+        store_half32(ep.q16 + (size_t)row * E + slot * 64 + 32, x1);
+        if (ep.cap0) for (int i = 0; i < 32; i++) { ep.cap0[(size_t)row * capw + slot * 64 + i] = x0[i]; ep.cap0[(size_t)row * capw + slot * 64 + 32 + i] = x1[i]; }
+    } else if (!is_v) {
+        const int g = slot - nh;
+        store_half32(ep.k16 + (size_t)row * KV + g * 64, x0);
+        store_half32(ep.k16 + (size_t)row * KV + g * 64 + 32, x1);
+        store_codes32_perm(ep.kq + (size_t)row * KV + g * 64, q0);
+        store_codes32_perm(ep.kq + (size_t)row * KV + g * 64 + 32, q1);
+        ep.ks[(size_t)row * (KV / 32) + g * 2] = dh0;
+        ep.ks[(size_t)row * (KV / 32) + g * 2 + 1] = dh1;
+        if (ep.cap1) for (int i = 0; i < 32; i++) { ep.cap1[(size_t)row * capw + g * 64 + i] = x0[i]; ep.cap1[(size_t)row * capw + g * 64 + 32 + i] = x1[i]; }
+    } else {
+        const int g = slot - nh - ng;
+        store_half32(ep.v16 + (size_t)row * KV + g * 64, x0);
+        store_half32(ep.v16 + (size_t)row * KV + g * 64 + 32, x1);
+        store_codes32(reinterpret_cast<int8_t*>(ep.vq) + (size_t)row * KV + g * 64, q0);
+        store_codes32(reinterpret_cast<int8_t*>(ep.vq) + (size_t)row * KV + g * 64 + 32, q1);
+        ep.vs[(size_t)row * (KV / 32) + g * 2] = dh0;
+        ep.vs[(size_t)row * (KV / 32) + g * 2 + 1] = dh1;
+        if (ep.cap2) for (int i = 0; i < 32; i++) { ep.cap2[(size_t)row * capw + g * 64 + i] = x0[i]; ep.cap2[(size_t)row * capw + g * 64 + 32 + i] = x1[i]; }
+    }
+}
+
+// One 32-block of the FFN: g/u = decoded gate and up Linear outputs; SiLU (ops.h:673-711), re-encode, Multiply
+// (ops.h:816-867), re-encode -> fp16 operand of the down projection
+__device__ __forceinline__ void pf_silu_store(const PfEpi& ep, int row, int b, float (&g)[32], const float (&u)[32]) {
+#pragma unroll
+    for (int k = 0; k < 32; k++) g[k] = pf_silu(g[k]);
+    int q[32];
+    pf_roundtrip32(g, q);
+#pragma unroll
+    for (int k = 0; k < 32; k++) g[k] = __fmul_rn(g[k], u[k]);
+    pf_roundtrip32(g, q);
+    store_half32(ep.act16 + (size_t)row * ep.F + (size_t)b * 32, g);
+    if (ep.cap0) for (int k = 0; k < 32; k++) { ep.cap0[(size_t)row * ep.capw + b * 32 + k] = g[k]; ep.cap1[(size_t)row * ep.capw + b * 32 + k] = u[k]; }
+}
+
 // =================================================================================================== GEMM (tcgen05)
 constexpr int PF_BM = 128;          // rows of A (prompt positions) per tile = UMMA M
 constexpr int PF_BK = 64;           // fp16 elements per k-block = one 128-byte swizzle atom
-constexpr int PF_THREADS = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
-enum { EPI_F32 = 0, EPI_Q8 = 1 };
+constexpr int PF_THREADS = 320;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
+constexpr int PF_EPI_THREADS = 256; // two epilogue warps per TMEM lane quarter, each takes half of the tile's columns
+enum { EPI_F32 = 0, EPI_Q8 = 1, EPI_ROPE = 2, EPI_SILU = 3 };
 
 template <int BN> struct PfGemmCfg {
     static constexpr int STAGES = (BN == 256) ? 4 : 6;
@@ -185,10 +278,48 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// Epilogue of one accumulator tile for one thread: `tacc` = TMEM address of this thread's row (lane) at the tile's first
+// column; the two epilogue warps of a lane quarter split the columns (chalf = 0/1).
+template <int BN, int EPI>
+__device__ __forceinline__ void pf_epilogue(const PfEpi& ep, uint32_t tacc, int row, bool row_ok, int col0, int N, int chalf) {
+    if (EPI == EPI_F32 || EPI == EPI_Q8) {
+#pragma unroll 1
+        for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); c++) {
+            const int col = col0 + c * 32;
+            float v[32];
+            tmem_ld32(tacc + (uint32_t)(c * 32), v);
+            if (row_ok && col < N) {
+                if (EPI == EPI_F32) {
+                    store_f32x32(reinterpret_cast<float*>(ep.out0) + (size_t)row * N + col, v);
+                } else {
+                    int q[32];
+                    const uint16_t dh = q8_encode32(v, q);        // write_row_from_float, ops.h:645-646
+                    store_codes32(reinterpret_cast<int8_t*>(ep.out0) + (size_t)row * N + col, q);
+                    reinterpret_cast<uint16_t*>(ep.out1)[(size_t)row * (N / 32) + (col >> 5)] = dh;
+                }
+            }
+        }
+    } else {
+        // 64 output columns at a time: one head of q|k|v (EPI_ROPE) or one gate block + its up block (EPI_SILU)
+#pragma unroll 1
+        for (int c2 = chalf * (BN / 128); c2 < (chalf + 1) * (BN / 128); c2++) {
+            const int col = col0 + c2 * 64;
+            float a[32], b[32];
+            tmem_ld32(tacc + (uint32_t)(c2 * 64), a);
+            tmem_ld32(tacc + (uint32_t)(c2 * 64 + 32), b);
+            if (row_ok && col < N) {
+                int q0[32], q1[32];
+                const uint16_t dh0 = pf_roundtrip32(a, q0), dh1 = pf_roundtrip32(b, q1);   // the Linear's own re-encode
+                if (EPI == EPI_ROPE) pf_rope_store(ep, row, col >> 6, a, b, q0, q1, dh0, dh1);
+                else pf_silu_store(ep, row, col >> 6, a, b);
+            }
+        }
+    }
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(PF_THREADS, 1)
-k_pf_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-          void* __restrict__ out0, void* __restrict__ out1) {
+k_pf_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, const PfEpi ep) {
     using Cfg = PfGemmCfg<BN>;
     constexpr int ST = Cfg::STAGES;
     extern __shared__ unsigned char smem_raw[];
@@ -208,7 +339,7 @@ k_pf_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < ST; s++) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 128); }
+        for (int a = 0; a < 2; a++) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), PF_EPI_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
@@ -260,6 +391,7 @@ k_pf_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         __syncwarp();
     } else {                    // ---------------- epilogue warps: TMEM -> registers -> re-encode -> HBM
         const int lg = warp & 3;                                    // a warp may only touch TMEM lanes 32*(warp%4)..+31
+        const int chalf = (warp - 2) >> 2;                          // which half of the tile's columns this warp re-encodes
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
             const int mt = tile % n_mt, nt = tile / n_mt;
@@ -268,22 +400,7 @@ k_pf_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             tc_fence_after();
             const int row = mt * PF_BM + lg * 32 + lane;
             const bool row_ok = row < M;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; c++) {
-                const int col = nt * BN + c * 32;
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + c * 32), v);
-                if (row_ok && col < N) {
-                    if (EPI == EPI_F32) {
-                        store_f32x32(reinterpret_cast<float*>(out0) + (size_t)row * N + col, v);
-                    } else {
-                        int q[32];
-                        const uint16_t dh = q8_encode32(v, q);        // write_row_from_float, ops.h:645-646
-                        store_codes32(reinterpret_cast<int8_t*>(out0) + (size_t)row * N + col, q);
-                        reinterpret_cast<uint16_t*>(out1)[(size_t)row * (N / 32) + (col >> 5)] = dh;
-                    }
-                }
-            }
+            pf_epilogue<BN, EPI>(ep, tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN), row, row_ok, nt * BN, N, chalf);
             tc_fence_before();
             mbar_arrive(bar_tempty(as));
         }
@@ -293,12 +410,152 @@ k_pf_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same GEMM on CTA PAIRS (tcgen05 cta_group::2).  One M128 x N256 MMA per SM reads 12 KB of shared memory per K=16
+// step while TMA writes another 12 KB: 182 B/clk against the 128 B/clk an SM's shared memory delivers -- the measured
+// 70 % tensor-pipe ceiling of k_pf_gemm (profiles/r01_02_prefill.md).  A pair computes a 256 x 256 tile: each CTA
+// stages its own 128 rows of A and HALF of the W tile, the leader CTA issues M256 MMAs that read both halves, and each
+// CTA's TMEM receives its 128 rows.  Shared-memory traffic per SM drops to 121 B/clk and L2 traffic per flop by a third.
+//   full[s]   (leader only, 2 arrivals): both producers arrive; both CTAs' TMA bytes complete_tx on the LEADER's barrier
+//   empty[s]  (each CTA, 1 arrival)    : the leader's tcgen05.commit multicasts to both CTAs
+//   tfull[a]  (each CTA, 1 arrival)    : commit multicast after the last k-block of a tile
+//   tempty[a] (leader only, 512)       : the epilogue threads of BOTH CTAs arrive on the leader's barrier
+constexpr int PF2_STAGES = 6;
+constexpr uint32_t PF2_STAGE_BYTES = PF_BM * PF_BK * 2 + 128 * PF_BK * 2;
+constexpr uint32_t PF2_SMEM = PF2_STAGES * PF2_STAGE_BYTES + 1024 + 256;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PF_THREADS, 1)
+k_pf_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, const PfEpi ep) {
+    constexpr int BN = 256;
+    constexpr int ST = PF2_STAGES;
+    constexpr uint32_t A_BYTES = PF_BM * PF_BK * 2, STAGE_BYTES = PF2_STAGE_BYTES;
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);      // M = 256 across the pair
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ST * STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ST + 4);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_u32(bars);
+    auto bar_full = [&](int s) { return bar_base + 8u * s; };
+    auto bar_empty = [&](int s) { return bar_base + 8u * (ST + s); };
+    auto bar_tfull = [&](int a) { return bar_base + 8u * (2 * ST + a); };
+    auto bar_tempty = [&](int a) { return bar_base + 8u * (2 * ST + 2 + a); };
+
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const bool leader = rank == 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_mt = (M + 255) / 256, n_nt = (N + BN - 1) / BN;
+    const int n_tiles = n_mt * n_nt, nkb = K / PF_BK;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < ST; s++) { mbar_init(bar_full(s), 2); mbar_init(bar_empty(s), 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 2 * PF_EPI_THREADS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {        // ---------------- TMA producer (both CTAs): own rows of A, own half of the W tile
+            tma_prefetch_desc(&tmA);
+            tma_prefetch_desc(&tmB);
+            uint32_t s = 0, ph = 0;
+            for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+                const int mt = tile % n_mt, nt = tile / n_mt;
+                for (int kb = 0; kb < nkb; kb++) {
+                    mbar_wait(bar_empty(s), ph ^ 1);
+                    const uint32_t lbar = bar_full(s) & 0xFEFFFFFFu;            // the leader CTA's barrier (peer bit cleared)
+                    if (leader) {
+                        mbar_expect_tx(bar_full(s), 2 * STAGE_BYTES);
+                    } else {
+                        asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, 0;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+                                     ::"r"(bar_full(s)) : "memory");
+                    }
+                    const uint32_t sa = smem_base + s * STAGE_BYTES;
+                    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                                 ::"r"(sa), "l"(&tmA), "r"(lbar), "r"(kb * PF_BK), "r"(mt * 256 + (int)rank * PF_BM) : "memory");
+                    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                                 ::"r"(sa + A_BYTES), "l"(&tmB), "r"(lbar), "r"(kb * PF_BK), "r"(nt * BN + (int)rank * (BN / 2)) : "memory");
+                    if (++s == ST) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {   // ---------------- MMA issuer (leader CTA only)
+            uint32_t s = 0, ph = 0;
+            int it = 0;
+            for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
+                const int as = it & 1;
+                mbar_wait(bar_tempty(as), ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < nkb; kb++) {
+                    mbar_wait(bar_full(s), ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + s * STAGE_BYTES;
+                    const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < PF_BK / 16; k++) {
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\t"
+                            "setp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                            ::"r"(d_tmem), "l"(umma_desc_sw128(sa + k * 32)), "l"(umma_desc_sw128(sb + k * 32)), "r"(IDESC), "r"((uint32_t)((kb | k) != 0)) : "memory");
+                    }
+                    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                 ::"r"(bar_empty(s)), "h"((uint16_t)3) : "memory");
+                    if (kb == nkb - 1)
+                        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                     ::"r"(bar_tfull(as)), "h"((uint16_t)3) : "memory");
+                    if (++s == ST) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else {                    // ---------------- epilogue warps (both CTAs): own 128 rows
+        const int lg = warp & 3;
+        const int chalf = (warp - 2) >> 2;
+        int it = 0;
+        for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
+            const int mt = tile % n_mt, nt = tile / n_mt;
+            const int as = it & 1;
+            mbar_wait(bar_tfull(as), (it >> 1) & 1);
+            tc_fence_after();
+            const int row = mt * 256 + (int)rank * PF_BM + lg * 32 + lane;
+            pf_epilogue<BN, EPI>(ep, tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN), row, row < M, nt * BN, N, chalf);
+            tc_fence_before();
+            asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, 0;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+                         ::"r"(bar_tempty(as)) : "memory");
+        }
+    }
+    tc_fence_before();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+}
+
 // =================================================================================================== row-wise kernels
 // weights: device layout (gtb_internal.h) -> fp16 [rows][cols], value = fp16(code * delta)
+// interleave_half > 0 (gate|up, = n_ffn): source row r of the first half goes to row (r/32)*64 + r%32, row r of the second
+// half to (r/32)*64 + 32 + r%32, so that 64 consecutive output columns of the GEMM hold one gate block and its up block
 __global__ void k_pf_w16(const void* __restrict__ data, const uint16_t* __restrict__ scales, int wdtype, size_t nblocks,
-                         __half* __restrict__ out) {
+                         __half* __restrict__ out, int bpr, int interleave_half) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nblocks) return;
+    size_t o = i;
+    if (interleave_half > 0) {
+        const size_t row = i / bpr, kb = i % bpr;
+        const size_t r = row % interleave_half, up = row / interleave_half;
+        o = ((r / 32) * 64 + up * 32 + (r % 32)) * bpr + kb;
+    }
     const float d = h2f(scales[i]);
     float v[32];
     if (wdtype == DT_Q4) {
@@ -320,7 +577,7 @@ __global__ void k_pf_w16(const void* __restrict__ data, const uint16_t* __restri
             v[e] = __fmul_rn((float)sbyte(w[half * 4 + l], pos), d);
         }
     }
-    store_half32(out + i * 32, v);
+    store_half32(out + o * 32, v);
 }
 
 // token_embed (ops.h:514-564): Q8 rows are copied, Q4 rows are dequantised and re-encoded as Q8
@@ -364,21 +621,21 @@ __global__ void k_pf_embed(const void* __restrict__ wdata, const uint16_t* __res
     }
 }
 
-// Residual (ops.h:870-910) + RMSNorm (ops.h:762-814), one warp per row:
+// Residual (ops.h:870-910) + RMSNorm (ops.h:762-814), one 64-thread CTA per row, one 32-block per thread and pass:
 //   x <- E(x + y)        (skipped when y == nullptr)
 //   xn <- fp16( E( x / (rms(x) + 1e-6) * w ) )       the A operand of the next GEMM
 // The sum of squares is a plain parallel fp32 sum (the reference sums in element order): its relative error of ~1e-7
 // is three orders of magnitude below the fp16 operand rounding of the GEMMs of this path.
-__global__ void __launch_bounds__(128) k_pf_add_norm(int8_t* __restrict__ xq, uint16_t* __restrict__ xs, const int8_t* __restrict__ yq,
-                                                      const uint16_t* __restrict__ ys, const uint16_t* __restrict__ normw,
-                                                      __half* __restrict__ xn16, int T, int D, float* cap_y, float* cap_x, float* cap_n, int capw) {
-    const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= T) return;
+__global__ void __launch_bounds__(64) k_pf_add_norm(int8_t* __restrict__ xq, uint16_t* __restrict__ xs, const int8_t* __restrict__ yq,
+                                                     const uint16_t* __restrict__ ys, const uint16_t* __restrict__ normw,
+                                                     __half* __restrict__ xn16, int T, int D, float* cap_y, float* cap_x, float* cap_n, int capw) {
+    __shared__ float red[2];
+    const int row = blockIdx.x, tid = threadIdx.x;
     const int nb = D / 32;
+    const bool single = nb <= 64;                     // n_embd <= 2048: the block stays in registers between the passes
     float ssq = 0.0f;
-    for (int b = lane; b < nb; b += 32) {
-        float v[32];
+    float v[32];
+    for (int b = tid; b < nb; b += 64) {
         load_deq32(xq, xs, row, D, b, v);
         if (yq) {
             float y[32];
@@ -387,12 +644,9 @@ __global__ void __launch_bounds__(128) k_pf_add_norm(int8_t* __restrict__ xq, ui
 #pragma unroll
             for (int i = 0; i < 32; i++) v[i] = __fadd_rn(v[i], y[i]);
             int q[32];
-            const uint16_t dh = q8_encode32(v, q);
+            const uint16_t dh = pf_roundtrip32(v, q);
             store_codes32(xq + (size_t)row * D + (size_t)b * 32, q);
             xs[(size_t)row * nb + b] = dh;
-            const float dd = h2f(dh);
-#pragma unroll
-            for (int i = 0; i < 32; i++) v[i] = __fmul_rn((float)q[i], dd);
         }
         if (cap_x) for (int i = 0; i < 32; i++) cap_x[(size_t)row * capw + b * 32 + i] = v[i];
 #pragma unroll
@@ -400,11 +654,13 @@ __global__ void __launch_bounds__(128) k_pf_add_norm(int8_t* __restrict__ xq, ui
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ssq = __fadd_rn(ssq, __shfl_xor_sync(0xffffffffu, ssq, o));
+    if ((tid & 31) == 0) red[tid >> 5] = ssq;
+    __syncthreads();
+    ssq = __fadd_rn(red[0], red[1]);
     const float rms = sqrtf(__fdiv_rn(ssq, (float)D));
     const float denom = __fadd_rn(rms, 1e-6f);
-    for (int b = lane; b < nb; b += 32) {
-        float v[32];
-        load_deq32(xq, xs, row, D, b, v);
+    for (int b = tid; b < nb; b += 64) {
+        if (!single) load_deq32(xq, xs, row, D, b, v);
         const uint4* wp = reinterpret_cast<const uint4*>(normw + b * 32);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -417,112 +673,39 @@ __global__ void __launch_bounds__(128) k_pf_add_norm(int8_t* __restrict__ xq, ui
             }
         }
         int q[32];
-        const uint16_t dh = q8_encode32(v, q);
-        const float dd = h2f(dh);
-#pragma unroll
-        for (int i = 0; i < 32; i++) v[i] = __fmul_rn((float)q[i], dd);
+        pf_roundtrip32(v, q);
         if (cap_n) for (int i = 0; i < 32; i++) cap_n[(size_t)row * capw + b * 32 + i] = v[i];
         store_half32(xn16 + (size_t)row * D + (size_t)b * 32, v);
     }
 }
 
-// RoPE (ops.h:714-760) on the q and k heads of the fused q|k|v GEMM output, K/V append in the engine's cache layout,
-// and the fp16 operands of the attention kernel.  One thread per (row, head slot): slots [0,nh) = q heads,
-// [nh, nh+ng) = k heads, [nh+ng, nh+2ng) = v heads.
-__global__ void __launch_bounds__(128) k_pf_rope_kv(const int8_t* __restrict__ cq, const uint16_t* __restrict__ cs, int T, int nh, int ng,
-                                                     const float* __restrict__ rope_cos, const float* __restrict__ rope_sin,
-                                                     __half* __restrict__ q16, __half* __restrict__ k16, __half* __restrict__ v16,
-                                                     uint8_t* __restrict__ kq, uint16_t* __restrict__ ks, uint8_t* __restrict__ vq, uint16_t* __restrict__ vs,
-                                                     float* cap_q, float* cap_k, float* cap_v, int capw) {
-    const int nslots = nh + 2 * ng;
+// Unfused fallbacks of the two fused epilogues ("pf_fused" = 0): same arithmetic on the planar GEMM output.
+// One thread per (row, head slot): slots [0,nh) = q heads, [nh, nh+ng) = k heads, [nh+ng, nh+2ng) = v heads.
+__global__ void __launch_bounds__(128) k_pf_rope_kv(const int8_t* __restrict__ cq, const uint16_t* __restrict__ cs, int T, const PfEpi ep) {
+    const int nslots = ep.nh + 2 * ep.ng;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)T * nslots) return;
     const int row = (int)(idx / nslots), slot = (int)(idx % nslots);
-    const int E = nh * 64, KV = ng * 64, D = E + 2 * KV;
+    const int D = nslots * 64;
     float x0[32], x1[32];
+    int q0[32], q1[32];
     load_deq32(cq, cs, row, D, slot * 2, x0);
     load_deq32(cq, cs, row, D, slot * 2 + 1, x1);
-    const bool is_v = slot >= nh + ng;
-    int q0[32], q1[32];
-    uint16_t dh0, dh1;
-    if (!is_v) {
-        const float4* cp = reinterpret_cast<const float4*>(rope_cos + (size_t)row * 32);
-        const float4* sp = reinterpret_cast<const float4*>(rope_sin + (size_t)row * 32);
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const float4 c4 = cp[k], s4 = sp[k];
-            const float c[4] = {c4.x, c4.y, c4.z, c4.w}, s[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float a = x0[4 * k + j], b = x1[4 * k + j];
-                x0[4 * k + j] = __fsub_rn(__fmul_rn(a, c[j]), __fmul_rn(b, s[j]));
-                x1[4 * k + j] = __fadd_rn(__fmul_rn(a, s[j]), __fmul_rn(b, c[j]));
-            }
-        }
-        dh0 = q8_encode32(x0, q0);
-        dh1 = q8_encode32(x1, q1);
-        const float d0 = h2f(dh0), d1 = h2f(dh1);
-#pragma unroll
-        for (int i = 0; i < 32; i++) { x0[i] = __fmul_rn((float)q0[i], d0); x1[i] = __fmul_rn((float)q1[i], d1); }
-    } else {
-        // V is the Linear output itself: codes and scales pass through unchanged
-        load_codes32(cq + (size_t)row * D + (size_t)slot * 64, q0);
-        load_codes32(cq + (size_t)row * D + (size_t)slot * 64 + 32, q1);
-        dh0 = cs[(size_t)row * (D / 32) + slot * 2];
-        dh1 = cs[(size_t)row * (D / 32) + slot * 2 + 1];
-    }
-    if (slot < nh) {
-        store_half32(q16 + (size_t)row * E + slot * 64, x0);
-        store_half32(q16 + (size_t)row * E + slot * 64 + 32, x1);
-        if (cap_q) for (int i = 0; i < 32; i++) { cap_q[(size_t)row * capw + slot * 64 + i] = x0[i]; cap_q[(size_t)row * capw + slot * 64 + 32 + i] = x1[i]; }
-    } else if (!is_v) {
-        const int g = slot - nh;
-        store_half32(k16 + (size_t)row * KV + g * 64, x0);
-        store_half32(k16 + (size_t)row * KV + g * 64 + 32, x1);
-        store_codes32_perm(kq + (size_t)row * KV + g * 64, q0);
-        store_codes32_perm(kq + (size_t)row * KV + g * 64 + 32, q1);
-        ks[(size_t)row * (KV / 32) + g * 2] = dh0;
-        ks[(size_t)row * (KV / 32) + g * 2 + 1] = dh1;
-        if (cap_k) for (int i = 0; i < 32; i++) { cap_k[(size_t)row * capw + g * 64 + i] = x0[i]; cap_k[(size_t)row * capw + g * 64 + 32 + i] = x1[i]; }
-    } else {
-        const int g = slot - nh - ng;
-        store_half32(v16 + (size_t)row * KV + g * 64, x0);
-        store_half32(v16 + (size_t)row * KV + g * 64 + 32, x1);
-        store_codes32(reinterpret_cast<int8_t*>(vq) + (size_t)row * KV + g * 64, q0);
-        store_codes32(reinterpret_cast<int8_t*>(vq) + (size_t)row * KV + g * 64 + 32, q1);
-        vs[(size_t)row * (KV / 32) + g * 2] = dh0;
-        vs[(size_t)row * (KV / 32) + g * 2 + 1] = dh1;
-        if (cap_v) for (int i = 0; i < 32; i++) { cap_v[(size_t)row * capw + g * 64 + i] = x0[i]; cap_v[(size_t)row * capw + g * 64 + 32 + i] = x1[i]; }
-    }
+    load_codes32(cq + (size_t)row * D + (size_t)slot * 64, q0);
+    load_codes32(cq + (size_t)row * D + (size_t)slot * 64 + 32, q1);
+    pf_rope_store(ep, row, slot, x0, x1, q0, q1, cs[(size_t)row * (D / 32) + slot * 2], cs[(size_t)row * (D / 32) + slot * 2 + 1]);
 }
 
-// SiLU (ops.h:673-711) and Multiply (ops.h:816-867) on the fused gate|up GEMM output: E(E(silu(gate)) * up) -> fp16
-// __expf is within 2 ulp of the reference's correctly rounded expf: a 1e-7 relative change of silu(x), far below the
-// fp16 operand rounding of this path (the exact path keeps glibc's algorithm, gtb_dev.cuh expf_glibc)
-__device__ __forceinline__ float pf_silu(float x) { return __fdiv_rn(x, __fadd_rn(1.0f, __expf(-x))); }
-
-__global__ void __launch_bounds__(128) k_pf_silu_mul(const int8_t* __restrict__ gq, const uint16_t* __restrict__ gs, int T, int F,
-                                                      __half* __restrict__ act16, float* cap_g, float* cap_u, int capw) {
-    const int nb = F / 32;
+// gate|up planar output with the rows of the two matrices interleaved in groups of 32: block 2b = gate block b, 2b+1 = up block b
+__global__ void __launch_bounds__(128) k_pf_silu_mul(const int8_t* __restrict__ gq, const uint16_t* __restrict__ gs, int T, const PfEpi ep) {
+    const int nb = ep.F / 32;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)T * nb) return;
     const int row = (int)(i / nb), b = (int)(i % nb);
     float g[32], u[32];
-    load_deq32(gq, gs, row, 2 * F, b, g);
-    load_deq32(gq, gs, row, 2 * F, nb + b, u);
-#pragma unroll
-    for (int k = 0; k < 32; k++) g[k] = pf_silu(g[k]);
-    int q[32];
-    uint16_t dh = q8_encode32(g, q);
-    float dd = h2f(dh);
-#pragma unroll
-    for (int k = 0; k < 32; k++) g[k] = __fmul_rn(__fmul_rn((float)q[k], dd), u[k]);
-    dh = q8_encode32(g, q);
-    dd = h2f(dh);
-#pragma unroll
-    for (int k = 0; k < 32; k++) g[k] = __fmul_rn((float)q[k], dd);
-    store_half32(act16 + (size_t)row * F + (size_t)b * 32, g);
-    if (cap_g) for (int k = 0; k < 32; k++) { cap_g[(size_t)row * capw + b * 32 + k] = g[k]; cap_u[(size_t)row * capw + b * 32 + k] = u[k]; }
+    load_deq32(gq, gs, row, 2 * ep.F, 2 * b, g);
+    load_deq32(gq, gs, row, 2 * ep.F, 2 * b + 1, u);
+    pf_silu_store(ep, row, b, g, u);
 }
 
 // dequantised fp32 copies of row `row` for the exact final-norm + lm_head phase of the engine
@@ -793,7 +976,7 @@ static int make_tmap(CUtensorMap* m, const void* base, int rows, int cols, int b
 }
 
 template <int BN, int EPI>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, void* out0, void* out1) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const PfEpi& ep) {
     using Cfg = PfGemmCfg<BN>;
     static bool attr = false;
     if (!attr) {
@@ -802,35 +985,66 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int 
     }
     const int n_tiles = ((M + PF_BM - 1) / PF_BM) * ((N + BN - 1) / BN);
     const int grid = n_tiles < ctx().sm_count ? n_tiles : ctx().sm_count;
-    k_pf_gemm<BN, EPI><<<grid, PF_THREADS, Cfg::SMEM, ctx().stream>>>(ta, tb, M, N, K, out0, out1);
+    k_pf_gemm<BN, EPI><<<grid, PF_THREADS, Cfg::SMEM, ctx().stream>>>(ta, tb, M, N, K, ep);
     GTB_LAUNCHED();
     return GTB_OK;
 }
 
-static int gemm_q8(const CUtensorMap& ta, const CUtensorMap& tb, int bn, int M, int N, int K, int8_t* oq, uint16_t* os) {
-    return bn == 256 ? launch_gemm<256, EPI_Q8>(ta, tb, M, N, K, oq, os) : launch_gemm<128, EPI_Q8>(ta, tb, M, N, K, oq, os);
+template <int EPI>
+static int gemm_epi(const CUtensorMap& ta, const CUtensorMap& tb, int bn, int M, int N, int K, const PfEpi& ep) {
+    return bn == 256 ? launch_gemm<256, EPI>(ta, tb, M, N, K, ep) : launch_gemm<128, EPI>(ta, tb, M, N, K, ep);
+}
+
+// CTA-pair variant: 256 x 256 tiles; tb128 = tensor map of W with a 128-row box (each CTA stages half of the W tile)
+template <int EPI>
+static int gemm_epi2(const CUtensorMap& ta, const CUtensorMap& tb128, int M, int N, int K, const PfEpi& ep) {
+    static bool attr = false;
+    if (!attr) {
+        GTB_CUDA(cudaFuncSetAttribute(k_pf_gemm2<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF2_SMEM));
+        attr = true;
+    }
+    const int n_tiles = ((M + 255) / 256) * ((N + 255) / 256);
+    const int max_clusters = ctx().sm_count / 2;
+    const int clusters = n_tiles < max_clusters ? n_tiles : max_clusters;
+    k_pf_gemm2<EPI><<<2 * clusters, PF_THREADS, PF2_SMEM, ctx().stream>>>(ta, tb128, M, N, K, ep);
+    GTB_LAUNCHED();
+    return GTB_OK;
+}
+
+// N-tile width.  cost = waves x tile width; a 128-wide tile runs the tensor pipe at about half rate (per K=16 step it moves
+// 16 KB through shared memory in 67 clocks, twice what an SM delivers; measured 41.7 us vs 20.3 us on the q|k|v shape).
+static int pick_bn(int M, int N) {
+    const int sms = ctx().sm_count > 0 ? ctx().sm_count : 148;
+    const int n_mt = (M + PF_BM - 1) / PF_BM;
+    const long t256 = (long)n_mt * ((N + 255) / 256), t128 = (long)n_mt * ((N + 127) / 128);
+    const double c256 = (double)((t256 + sms - 1) / sms) * 256.0, c128 = (double)((t128 + sms - 1) / sms) * 128.0 * 1.9;
+    return c128 < c256 ? 128 : 256;
 }
 
 int pf_gemm_f32(const void* d_A16, const void* d_W16, float* d_C, int M, int N, int K, int bn) {
-    GTB_ARG(M > 0 && N > 0 && K > 0 && K % PF_BK == 0 && N % 32 == 0 && (bn == 128 || bn == 256));
+    GTB_ARG(M > 0 && N > 0 && K > 0 && K % PF_BK == 0 && N % 32 == 0 && (bn == 128 || bn == 256 || bn == 512));
     CUtensorMap ta, tb;
     int r = make_tmap(&ta, d_A16, M, K, PF_BM);
     if (r) return r;
-    r = make_tmap(&tb, d_W16, N, K, bn);
+    r = make_tmap(&tb, d_W16, N, K, bn == 512 ? 128 : bn);
     if (r) return r;
-    return bn == 256 ? launch_gemm<256, EPI_F32>(ta, tb, M, N, K, d_C, nullptr) : launch_gemm<128, EPI_F32>(ta, tb, M, N, K, d_C, nullptr);
+    PfEpi ep;
+    ep.out0 = d_C;
+    if (bn == 512) return gemm_epi2<EPI_F32>(ta, tb, M, N, K, ep);      // bn = 512 selects the CTA-pair kernel (256 x 256 tiles)
+    return gemm_epi<EPI_F32>(ta, tb, bn, M, N, K, ep);
 }
 
 struct PfLayerW {
-    __half* w[4] = {nullptr, nullptr, nullptr, nullptr};      // q|k|v, o, gate|up, down as fp16 [N][K]
-    CUtensorMap tm[4];
+    __half* w[4] = {nullptr, nullptr, nullptr, nullptr};      // q|k|v, o, gate|up (rows interleaved by 32), down as fp16 [N][K]
+    CUtensorMap tm[4][2];                                     // [..][0]: 128-row box, [..][1]: 256-row box
     bool set[4] = {false, false, false, false};
 };
 
 struct PfPlan {
     gtb_model_config cfg{};
     int E = 0, F = 0, KV = 0, NQKV = 0, Tcap = 0;
-    int bn[4] = {256, 256, 256, 256};
+    bool fused = true;               // RoPE/KV-append and SiLU*up inside the GEMM epilogues
+    bool two_cta = false;            // CTA-pair GEMM (k_pf_gemm2) wherever the tile is 256 wide
     std::vector<PfLayerW> L;
     // activations for up to Tcap rows
     int8_t *xq = nullptr, *qkvq = nullptr, *oq = nullptr, *guq = nullptr;
@@ -854,8 +1068,6 @@ int pf_create(PfPlan** out, const gtb_model_config& cfg) {
     p->E = cfg.n_embd; p->F = cfg.n_ffn; p->KV = 64 * cfg.n_groups; p->NQKV = p->E + 2 * p->KV;
     p->Tcap = cfg.max_ctx < PF_BM ? PF_BM : cfg.max_ctx;      // TMA boxes are 128 rows tall
     p->L.resize(cfg.n_layers);
-    const int N[4] = {p->NQKV, p->E, 2 * p->F, p->E};
-    for (int w = 0; w < 4; w++) p->bn[w] = (N[w] >= 1024) ? 256 : 128;
     const size_t T = (size_t)p->Tcap;
     int r = 0;
     r |= pf_alloc(p, (void**)&p->xq, T * p->E); r |= pf_alloc(p, (void**)&p->xs, T * (p->E / 32) * 2);
@@ -891,9 +1103,10 @@ int pf_set_weight(PfPlan* p, int layer, int which, int wdtype, const void* d_dat
     const size_t n = (size_t)rows * cols;
     if (!l.w[which]) { int r = pf_alloc(p, (void**)&l.w[which], n * 2); if (r) return r; }
     const size_t nblk = n / 32;
-    k_pf_w16<<<(unsigned)((nblk + 255) / 256), 256, 0, ctx().stream>>>(d_data, d_scales, wdtype, nblk, l.w[which]);
+    k_pf_w16<<<(unsigned)((nblk + 255) / 256), 256, 0, ctx().stream>>>(d_data, d_scales, wdtype, nblk, l.w[which], cols / 32, which == 2 ? p->F : 0);
     GTB_LAUNCHED();
-    int r = make_tmap(&l.tm[which], l.w[which], rows, cols, p->bn[which]);
+    int r = make_tmap(&l.tm[which][0], l.w[which], rows, cols, 128);
+    if (!r) r = make_tmap(&l.tm[which][1], l.w[which], rows, cols, 256);
     if (r) return r;
     l.set[which] = true;
     return GTB_OK;
@@ -905,6 +1118,15 @@ bool pf_weights_ready(const PfPlan* p) {
 }
 size_t pf_bytes(const PfPlan* p) { return p->bytes; }
 int64_t pf_launches_last(const PfPlan* p) { return p->launches_last; }
+
+void pf_set_fused(PfPlan* p, bool on) { p->fused = on; }
+void pf_set_two_cta(PfPlan* p, bool on) { p->two_cta = on; }
+
+template <int EPI>
+static int gemm_any(bool two_cta, const CUtensorMap& ta, const CUtensorMap (&tb)[2], int bn, int M, int N, int K, const PfEpi& ep) {
+    if (two_cta && bn == 256) return gemm_epi2<EPI>(ta, tb[0], M, N, K, ep);
+    return gemm_epi<EPI>(ta, tb[bn == 256], bn, M, N, K, ep);
+}
 
 int pf_run(PfPlan* p, const PfRun& r) {
     GTB_ARG(p && r.T > 0 && r.T <= p->cfg.max_ctx && r.n_layers_run > 0 && r.n_layers_run <= p->cfg.n_layers);
@@ -931,40 +1153,55 @@ int pf_run(PfPlan* p, const PfRun& r) {
                                                                  capp(0, GTB_A_EMB), r.capw);
         GTB_LAUNCHED();
     }
-    const unsigned row_grid = (unsigned)((T + 3) / 4);
-    k_pf_add_norm<<<row_grid, 128, 0, st>>>(p->xq, p->xs, nullptr, nullptr, r.layers[0].attn_norm, p->xn16, T, E, nullptr, nullptr,
+    k_pf_add_norm<<<T, 64, 0, st>>>(p->xq, p->xs, nullptr, nullptr, r.layers[0].attn_norm, p->xn16, T, E, nullptr, nullptr,
                                             capp(0, GTB_A_ATTN_NORM), r.capw);
     GTB_LAUNCHED();
+    const int bn_qkv = pick_bn(T, NQKV), bn_o = pick_bn(T, E), bn_gu = pick_bn(T, 2 * F), bn_d = pick_bn(T, E);
     for (int li = 0; li < r.n_layers_run; li++) {
         const PfLayerIO& io = r.layers[li];
         PfLayerW& w = p->L[li];
-        rc = gemm_q8(ta_xn, w.tm[0], p->bn[0], T, NQKV, E, p->qkvq, p->qkvs);
-        if (rc) return rc;
-        {
+        PfEpi eq;                                   // q|k|v: Linear re-encode, RoPE, K/V append
+        eq.out0 = p->qkvq; eq.out1 = p->qkvs;
+        eq.rope_cos = r.rope_cos; eq.rope_sin = r.rope_sin; eq.q16 = p->q16; eq.k16 = p->k16; eq.v16 = p->v16;
+        eq.kq = io.kq; eq.ks = io.ks; eq.vq = io.vq; eq.vs = io.vs; eq.nh = nh; eq.ng = ng;
+        eq.cap0 = capp(li, GTB_A_Q); eq.cap1 = capp(li, GTB_A_K); eq.cap2 = capp(li, GTB_A_V); eq.capw = r.capw;
+        if (p->fused) {
+            rc = gemm_any<EPI_ROPE>(p->two_cta, ta_xn, w.tm[0], bn_qkv, T, NQKV, E, eq);
+            if (rc) return rc;
+        } else {
+            rc = gemm_any<EPI_Q8>(p->two_cta, ta_xn, w.tm[0], bn_qkv, T, NQKV, E, eq);
+            if (rc) return rc;
             const size_t n = (size_t)T * (nh + 2 * ng);
-            k_pf_rope_kv<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p->qkvq, p->qkvs, T, nh, ng, r.rope_cos, r.rope_sin, p->q16, p->k16, p->v16,
-                                                                       io.kq, io.ks, io.vq, io.vs, capp(li, GTB_A_Q), capp(li, GTB_A_K), capp(li, GTB_A_V), r.capw);
+            k_pf_rope_kv<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p->qkvq, p->qkvs, T, eq);
             GTB_LAUNCHED();
         }
         k_pf_attn<<<(unsigned)(((T + 63) / 64) * nh), 128, 0, st>>>(p->q16, p->k16, p->v16, p->attn16, T, nh, nh / ng, capp(li, GTB_A_ATTN_OUT), r.capw);
         GTB_LAUNCHED();
-        rc = gemm_q8(ta_attn, w.tm[1], p->bn[1], T, E, E, p->oq, p->os);
+        PfEpi eo;
+        eo.out0 = p->oq; eo.out1 = p->os;
+        rc = gemm_any<EPI_Q8>(p->two_cta, ta_attn, w.tm[1], bn_o, T, E, E, eo);
         if (rc) return rc;
-        k_pf_add_norm<<<row_grid, 128, 0, st>>>(p->xq, p->xs, p->oq, p->os, io.ffn_norm, p->xn16, T, E, capp(li, GTB_A_O), capp(li, GTB_A_INP_RES),
-                                                capp(li, GTB_A_FFN_NORM), r.capw);
+        k_pf_add_norm<<<T, 64, 0, st>>>(p->xq, p->xs, p->oq, p->os, io.ffn_norm, p->xn16, T, E, capp(li, GTB_A_O), capp(li, GTB_A_INP_RES),
+                                        capp(li, GTB_A_FFN_NORM), r.capw);
         GTB_LAUNCHED();
-        rc = gemm_q8(ta_xn, w.tm[2], p->bn[2], T, 2 * F, E, p->guq, p->gus);
-        if (rc) return rc;
-        {
+        PfEpi eg;                                   // gate|up: Linear re-encode, SiLU, Multiply
+        eg.out0 = p->guq; eg.out1 = p->gus; eg.act16 = p->act16; eg.F = F;
+        eg.cap0 = capp(li, GTB_A_GATE); eg.cap1 = capp(li, GTB_A_UP); eg.capw = r.capw;
+        if (p->fused) {
+            rc = gemm_any<EPI_SILU>(p->two_cta, ta_xn, w.tm[2], bn_gu, T, 2 * F, E, eg);
+            if (rc) return rc;
+        } else {
+            rc = gemm_any<EPI_Q8>(p->two_cta, ta_xn, w.tm[2], bn_gu, T, 2 * F, E, eg);
+            if (rc) return rc;
             const size_t n = (size_t)T * (F / 32);
-            k_pf_silu_mul<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p->guq, p->gus, T, F, p->act16, capp(li, GTB_A_GATE), capp(li, GTB_A_UP), r.capw);
+            k_pf_silu_mul<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p->guq, p->gus, T, eg);
             GTB_LAUNCHED();
         }
-        rc = gemm_q8(ta_act, w.tm[3], p->bn[3], T, E, F, p->oq, p->os);
+        rc = gemm_any<EPI_Q8>(p->two_cta, ta_act, w.tm[3], bn_d, T, E, F, eo);
         if (rc) return rc;
         if (li + 1 < r.n_layers_run) {
-            k_pf_add_norm<<<row_grid, 128, 0, st>>>(p->xq, p->xs, p->oq, p->os, r.layers[li + 1].attn_norm, p->xn16, T, E, capp(li, GTB_A_DOWN),
-                                                    capp(li, GTB_A_ATTN_RES), capp(li + 1, GTB_A_ATTN_NORM), r.capw);
+            k_pf_add_norm<<<T, 64, 0, st>>>(p->xq, p->xs, p->oq, p->os, r.layers[li + 1].attn_norm, p->xn16, T, E, capp(li, GTB_A_DOWN),
+                                            capp(li, GTB_A_ATTN_RES), capp(li + 1, GTB_A_ATTN_NORM), r.capw);
             GTB_LAUNCHED();
         } else {
             k_pf_tail<<<(E + 255) / 256, 256, 0, st>>>(p->xq, p->xs, p->oq, p->os, T - 1, E, r.last_res, r.last_down, capp(li, GTB_A_DOWN), T, r.capw);

@@ -42,6 +42,8 @@ void pf_destroy(PfPlan* p);
 int pf_set_weight(PfPlan* p, int layer, int which, int wdtype, const void* d_data, const uint16_t* d_scales, int rows, int cols);
 bool pf_weights_ready(const PfPlan* p);
 int pf_run(PfPlan* p, const PfRun& r);
+void pf_set_two_cta(PfPlan* p, bool on);   // CTA-pair (tcgen05 cta_group::2) GEMM for the 256-wide tiles
+void pf_set_fused(PfPlan* p, bool on);     // false: RoPE/KV append and SiLU*up as separate kernels after plain GEMMs (debug)
 size_t pf_bytes(const PfPlan* p);
 int64_t pf_launches_last(const PfPlan* p);
 

@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--exact-rows", type=int, default=0)
     ap.add_argument("--layers", type=int, default=0, help="debug: smaller model")
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (e.g. pf_2cta=1)")
     args = ap.parse_args()
     import torch
     from tinyllama_cpp_b200 import capi
@@ -46,6 +47,9 @@ def main():
     cfg = W.TINYLLAMA if not args.layers else W.mini_config(n_layers=args.layers, n_vocab=32003)
     T = args.tokens
     eng = capi.Engine(cfg, T + 128, wdt).load(W.synth_weights(cfg, wdt, seed=1))
+    for o in args.opt:
+        k, v = o.split("=")
+        eng.set_option(k, int(v))
     prompt = W.synth_prompt(7, T, cfg.n_vocab)
     stream = torch.cuda.ExternalStream(capi.stream_handle(), device=torch.device("cuda", 0))
     for _ in range(args.warmup):
