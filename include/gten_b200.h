@@ -130,7 +130,9 @@ int gtb_engine_read_logits(gtb_engine_t e, float* h_logits);
 int gtb_engine_acv(gtb_engine_t e, int layer, int acv_id, float* h_out, int* width);
 /* options: "mega" (1: persistent cooperative kernel, default; 0: one kernel per phase), "graph" (CUDA-graph replay of
  * the per-phase path), "capture_acv", "grid", "pf_ahead" (L2 prefetch distance in GEMV phases), "prof",
- * "pf_layers" (debug: batched prefill stops after this many layers) */
+ * "pf_layers" (debug: batched prefill stops after this many layers), "pf_fused" (RoPE/KV append and SiLU*up inside the
+ * GEMM epilogues, default 1), "pf_pdl" (programmatic dependent launch, default 1), "pf_2cta" (CTA-pair tcgen05 GEMM, default 0),
+ * "pf_attn2" (second attention sweep that also reproduces the fp16 rounding of the probability-row block scales, default 0) */
 int gtb_engine_set_option(gtb_engine_t e, const char* name, int value);
 /* "prof": globaltimer stamps (ns) taken by CTA 0 at every phase boundary of the last processed row */
 int gtb_engine_read_prof(gtb_engine_t e, long long* h_out, int count);

@@ -70,11 +70,25 @@ def test_tcgen05_gemm_random(capi):
 @pytest.mark.parametrize("wdt", [Q8, Q4])
 @pytest.mark.parametrize("n_prompt", [100, 64, 7])
 def test_batched_prefill_mini(capi, checker, wdt, n_prompt):
+    _mini_case(capi, checker, wdt, n_prompt, {})
+
+
+@pytest.mark.parametrize("opts", [{"pf_attn2": 1}, {"pf_2cta": 1}, {"pf_pdl": 0, "pf_fused": 0}], ids=["two-sweep-attn", "cta-pairs", "unfused-no-pdl"])
+def test_batched_prefill_variants(capi, checker, opts):
+    """The optional code paths meet the same bound: two-sweep attention (also reproduces the fp16 rounding of the block
+    scales of the probability rows; the default online-softmax sweep applies them unrounded), the CTA-pair GEMM kernel,
+    and the unfused epilogues without programmatic dependent launch."""
+    _mini_case(capi, checker, Q8, 100, opts)
+
+
+def _mini_case(capi, checker, wdt, n_prompt, opts):
     cfg = W.mini_config(n_layers=3, n_vocab=300)
     wl = list(W.synth_weights(cfg, wdt, seed=21))
     max_ctx = 192
     cm = checker.model(cfg, max_ctx, wdt).load(wl)
     e = capi.Engine(cfg, max_ctx, wdt).load(wl)
+    for k, v in opts.items():
+        e.set_option(k, v)
     prompt = W.synth_prompt(5, n_prompt, cfg.n_vocab)
     want_logits = cm.logits(prompt, 0)
     e.set_option("capture_acv", 1)
@@ -94,7 +108,7 @@ def test_batched_prefill_mini(capi, checker, wdt, n_prompt):
     sens_logits = float(SENS[f"mini_{wn}_{n_prompt}_logits"])
     ours = [max(v for (l, _), v in worst.items() if l == layer) for layer in range(cfg.n_layers)]
     lerr = rel(got_logits, want_logits)
-    print(f"\nwdt={wn} T={n_prompt}: logits rel {lerr:.2e} (reference scalar-vs-AVX {sens_logits:.2e}); per layer "
+    print(f"\nwdt={wn} T={n_prompt} {opts}: logits rel {lerr:.2e} (reference scalar-vs-AVX {sens_logits:.2e}); per layer "
           + ", ".join(f"{o:.1e} ({s:.1e})" for o, s in zip(ours, sens_acv)))
     for row in rows:
         assert np.array_equal(e.pf_acv(0, oracle.A_EMB, row), cm.acv(0, oracle.A_EMB, row))     # the embedding gather is exact

@@ -314,6 +314,8 @@ struct gtb_engine {
     int pf_layers = 0;               // debug: run only the first pf_layers layers (0 = all)
     int pf_fused = 1;                // RoPE/KV append and SiLU*up inside the GEMM epilogues
     int pf_2cta = 0;                 // CTA-pair GEMM kernel
+    int pf_pdl = 1;                  // programmatic dependent launch inside the batched prefill
+    int pf_attn2 = 0;                // 1: two-sweep attention (also reproduces the fp16 rounding of the P-row block scales)
 };
 
 namespace {
@@ -825,6 +827,8 @@ int gtb_engine_prefill_fast(gtb_engine_t e, const int32_t* h_tokens, int n_token
     if (!e->pf) { r = pf_create(&e->pf, c); if (r) return r; }
     pf_set_fused(e->pf, e->pf_fused != 0);
     pf_set_two_cta(e->pf, e->pf_2cta != 0);
+    pf_set_pdl(e->pf_pdl != 0);
+    pf_set_attn_two_pass(e->pf, e->pf_attn2 != 0);
     if (!pf_weights_ready(e->pf)) {
         for (int li = 0; li < c.n_layers; li++) {
             LayerW& l = e->L[li];
@@ -1018,6 +1022,8 @@ int gtb_engine_set_option(gtb_engine_t e, const char* name, int value) {
     if (!strcmp(name, "pf_layers")) { GTB_ARG(value >= 0); e->pf_layers = value; return GTB_OK; }
     if (!strcmp(name, "pf_fused")) { e->pf_fused = value != 0; return GTB_OK; }
     if (!strcmp(name, "pf_2cta")) { e->pf_2cta = value != 0; return GTB_OK; }
+    if (!strcmp(name, "pf_pdl")) { e->pf_pdl = value != 0; return GTB_OK; }
+    if (!strcmp(name, "pf_attn2")) { e->pf_attn2 = value != 0; return GTB_OK; }
     return fail(GTB_ERR_ARG, "unknown option %s", name);
 }
 

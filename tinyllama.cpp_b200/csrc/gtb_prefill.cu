@@ -97,6 +97,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
+// Programmatic dependent launch: every kernel of the prefill chain lets its successor start launching as soon as all of its
+// own CTAs are running (the successor's prologue -- barrier init, TMEM allocation, descriptor prefetch -- then overlaps this
+// kernel's tail), and waits for its predecessor to complete and flush before touching global memory.
+__device__ __forceinline__ void pdl_trigger_and_wait() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // =================================================================================================== block codecs
 // One Q8 block (32 values) held by ONE thread: same operations as quants.h:52-66 / gtb_dev.cuh q8_encode_lane.
 __device__ __forceinline__ uint16_t q8_encode32(const float (&x)[32], int (&q)[32]) {
@@ -347,6 +355,7 @@ k_pf_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger_and_wait();
 
     if (warp == 0) {
         if (lane == 0) {        // ---------------- TMA producer
@@ -463,6 +472,7 @@ k_pf_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger_and_wait();
 
     if (warp == 0) {
         if (lane == 0) {        // ---------------- TMA producer (both CTAs): own rows of A, own half of the W tile
@@ -583,6 +593,7 @@ __global__ void k_pf_w16(const void* __restrict__ data, const uint16_t* __restri
 // token_embed (ops.h:514-564): Q8 rows are copied, Q4 rows are dequantised and re-encoded as Q8
 __global__ void k_pf_embed(const void* __restrict__ wdata, const uint16_t* __restrict__ wsc, int wdtype, const int32_t* __restrict__ tokens,
                            int T, int D, int8_t* __restrict__ xq, uint16_t* __restrict__ xs, float* cap, int capw) {
+    pdl_trigger_and_wait();
     const int nb = D / 32;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)T * nb) return;
@@ -629,6 +640,7 @@ __global__ void k_pf_embed(const void* __restrict__ wdata, const uint16_t* __res
 __global__ void __launch_bounds__(64) k_pf_add_norm(int8_t* __restrict__ xq, uint16_t* __restrict__ xs, const int8_t* __restrict__ yq,
                                                      const uint16_t* __restrict__ ys, const uint16_t* __restrict__ normw,
                                                      __half* __restrict__ xn16, int T, int D, float* cap_y, float* cap_x, float* cap_n, int capw) {
+    pdl_trigger_and_wait();
     __shared__ float red[2];
     const int row = blockIdx.x, tid = threadIdx.x;
     const int nb = D / 32;
@@ -682,6 +694,7 @@ __global__ void __launch_bounds__(64) k_pf_add_norm(int8_t* __restrict__ xq, uin
 // Unfused fallbacks of the two fused epilogues ("pf_fused" = 0): same arithmetic on the planar GEMM output.
 // One thread per (row, head slot): slots [0,nh) = q heads, [nh, nh+ng) = k heads, [nh+ng, nh+2ng) = v heads.
 __global__ void __launch_bounds__(128) k_pf_rope_kv(const int8_t* __restrict__ cq, const uint16_t* __restrict__ cs, int T, const PfEpi ep) {
+    pdl_trigger_and_wait();
     const int nslots = ep.nh + 2 * ep.ng;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)T * nslots) return;
@@ -698,6 +711,7 @@ __global__ void __launch_bounds__(128) k_pf_rope_kv(const int8_t* __restrict__ c
 
 // gate|up planar output with the rows of the two matrices interleaved in groups of 32: block 2b = gate block b, 2b+1 = up block b
 __global__ void __launch_bounds__(128) k_pf_silu_mul(const int8_t* __restrict__ gq, const uint16_t* __restrict__ gs, int T, const PfEpi ep) {
+    pdl_trigger_and_wait();
     const int nb = ep.F / 32;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)T * nb) return;
@@ -711,6 +725,7 @@ __global__ void __launch_bounds__(128) k_pf_silu_mul(const int8_t* __restrict__ 
 // dequantised fp32 copies of row `row` for the exact final-norm + lm_head phase of the engine
 __global__ void k_pf_tail(const int8_t* __restrict__ xq, const uint16_t* __restrict__ xs, const int8_t* __restrict__ dq, const uint16_t* __restrict__ ds,
                           int row, int D, float* __restrict__ res, float* __restrict__ down, float* cap_down, int T, int capw) {
+    pdl_trigger_and_wait();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= D) return;
     const size_t o = (size_t)row * D + e, so = (size_t)row * (D / 32) + (e >> 5);
@@ -807,8 +822,19 @@ __device__ __forceinline__ void pa_scores(float (&S)[8][4], const uint32_t (&qa)
 // scores are kept unscaled; exp(0.125 * (s - max)) = 2^((s - max) * PA_C)    (scale = 1/sqrt(64), ops.h:1098)
 #define PA_C (0.125f * 1.4426950408889634f)
 
+// One kernel, two variants:
+//  TWO_PASS = true : pass A computes each row's maximum and sum of exp, pass B the probabilities p = e / sum, the Q8 re-encode
+//                    of the probability row per 32 keys INCLUDING the fp16 rounding of each block scale (ops.h:996), and P.V.
+//  TWO_PASS = false: one sweep with a running maximum (the flash-attention recurrence).  The integer codes of a block depend
+//                    only on e / max(e of the block), so they are the same; the block scale is applied unrounded
+//                    (max_e / 127, rescaled with the running maximum, divided by the final sum at the end), i.e. the one
+//                    rounding point this variant does not reproduce is the fp16 rounding of the P-row block scales
+//                    (relative 2^-11 per block, averaging out over the blocks of a row -- the same size as the fp16 rounding
+//                    of the V operand).  QK^T and the exps run once instead of twice.
+template <bool TWO_PASS>
 __global__ void __launch_bounds__(128) k_pf_attn(const __half* __restrict__ q16, const __half* __restrict__ k16, const __half* __restrict__ v16,
                                                   __half* __restrict__ out16, int T, int n_heads, int gsz, float* cap, int capw) {
+    pdl_trigger_and_wait();
     __shared__ __align__(16) __half Qs[64 * PA_LD];
     __shared__ __align__(16) __half Ks[2][64 * PA_LD];
     __shared__ __align__(16) __half Vs[2][64 * PA_LD];
@@ -824,6 +850,7 @@ __global__ void __launch_bounds__(128) k_pf_attn(const __half* __restrict__ q16,
 
     pa_load_tile_async(smem_u32(Qs), q16, q0, T, E, h * 64);
     pa_load_tile_async(ks_addr(0), k16, 0, T, KV, grp * 64);
+    if (!TWO_PASS) pa_load_tile_async(vs_addr(0), v16, 0, T, KV, grp * 64);
     cp_async_commit();
     cp_async_wait_all();
     __syncthreads();
@@ -833,42 +860,44 @@ __global__ void __launch_bounds__(128) k_pf_attn(const __half* __restrict__ q16,
         ldsm_x4(smem_u32(Qs) + (uint32_t)(((16 * warp + (lane & 15)) * PA_LD + 16 * kk + (lane >> 4) * 8) * 2), qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3]);
     const int qrow0 = q0 + 16 * warp;
 
-    // ---- pass A: row maximum and sum of exp (ops.h:972-988); K tiles double-buffered with cp.async
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
-    for (int kt = 0; kt <= qt; kt++) {
-        const int cur = kt & 1;
-        if (kt > 0) { cp_async_wait_all(); __syncthreads(); }
-        // the last prefetch of pass A brings tile 0 of pass B (K again, plus V)
-        const int nk = (kt < qt) ? kt + 1 : 0;
-        pa_load_tile_async(ks_addr(cur ^ 1), k16, nk * 64, T, KV, grp * 64);
-        if (kt == qt) pa_load_tile_async(vs_addr(cur ^ 1), v16, 0, T, KV, grp * 64);
-        cp_async_commit();
-        float S[8][4];
-        pa_scores(S, qa, ks_addr(cur), lane, kt == qt, qrow0, kt * 64);
-        float t0 = -INFINITY, t1 = -INFINITY;
+    if (TWO_PASS) {
+        // ---- pass A: row maximum and sum of exp (ops.h:972-988); K tiles double-buffered with cp.async
+        for (int kt = 0; kt <= qt; kt++) {
+            const int cur = kt & 1;
+            if (kt > 0) { cp_async_wait_all(); __syncthreads(); }
+            const int nk = (kt < qt) ? kt + 1 : 0;                    // the last prefetch brings tile 0 of pass B (K again, plus V)
+            pa_load_tile_async(ks_addr(cur ^ 1), k16, nk * 64, T, KV, grp * 64);
+            if (kt == qt) pa_load_tile_async(vs_addr(cur ^ 1), v16, 0, T, KV, grp * 64);
+            cp_async_commit();
+            float S[8][4];
+            pa_scores(S, qa, ks_addr(cur), lane, kt == qt, qrow0, kt * 64);
+            float t0 = -INFINITY, t1 = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 8; j++) { t0 = fmaxf(t0, fmaxf(S[j][0], S[j][1])); t1 = fmaxf(t1, fmaxf(S[j][2], S[j][3])); }
-        t0 = quad_max(t0); t1 = quad_max(t1);
-        const float n0 = fmaxf(m0, t0), n1 = fmaxf(m1, t1);
-        l0 *= ex2_approx((m0 - n0) * PA_C); l1 *= ex2_approx((m1 - n1) * PA_C);
+            for (int j = 0; j < 8; j++) { t0 = fmaxf(t0, fmaxf(S[j][0], S[j][1])); t1 = fmaxf(t1, fmaxf(S[j][2], S[j][3])); }
+            t0 = quad_max(t0); t1 = quad_max(t1);
+            const float n0 = fmaxf(m0, t0), n1 = fmaxf(m1, t1);
+            l0 *= ex2_approx((m0 - n0) * PA_C); l1 *= ex2_approx((m1 - n1) * PA_C);
+            const float nc0 = -n0 * PA_C, nc1 = -n1 * PA_C;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            l0 += ex2_approx((S[j][0] - n0) * PA_C) + ex2_approx((S[j][1] - n0) * PA_C);
-            l1 += ex2_approx((S[j][2] - n1) * PA_C) + ex2_approx((S[j][3] - n1) * PA_C);
+            for (int j = 0; j < 8; j++) {
+                l0 += ex2_approx(fmaf(S[j][0], PA_C, nc0)) + ex2_approx(fmaf(S[j][1], PA_C, nc0));
+                l1 += ex2_approx(fmaf(S[j][2], PA_C, nc1)) + ex2_approx(fmaf(S[j][3], PA_C, nc1));
+            }
+            m0 = n0; m1 = n1;
         }
-        m0 = n0; m1 = n1;
+        l0 = quad_sum(l0); l1 = quad_sum(l1);
     }
-    l0 = quad_sum(l0); l1 = quad_sum(l1);
-    const float pinv0 = __fdiv_rn(1.0f, l0), pinv1 = __fdiv_rn(1.0f, l1);
+    const float pinv0 = TWO_PASS ? __fdiv_rn(1.0f, l0) : 1.0f, pinv1 = TWO_PASS ? __fdiv_rn(1.0f, l1) : 1.0f;
 
-    // ---- pass B: probabilities, Q8 re-encode per 32 keys, P.V.  Tile kt of pass B sits in buffer (qt + 1 + kt) & 1.
+    // ---- main sweep: probabilities, Q8 re-encode per 32 keys, P.V
     float O[8][4];
 #pragma unroll
     for (int j = 0; j < 8; j++) O[j][0] = O[j][1] = O[j][2] = O[j][3] = 0.0f;
+    const int buf0 = TWO_PASS ? (qt + 1) & 1 : 0;                     // buffer holding tile 0 of this sweep
     for (int kt = 0; kt <= qt; kt++) {
-        const int cur = (qt + 1 + kt) & 1;
-        cp_async_wait_all();
-        __syncthreads();
+        const int cur = (buf0 + kt) & 1;
+        if (TWO_PASS || kt > 0) { cp_async_wait_all(); __syncthreads(); }
         if (kt < qt) {
             pa_load_tile_async(ks_addr(cur ^ 1), k16, (kt + 1) * 64, T, KV, grp * 64);
             pa_load_tile_async(vs_addr(cur ^ 1), v16, (kt + 1) * 64, T, KV, grp * 64);
@@ -876,31 +905,55 @@ __global__ void __launch_bounds__(128) k_pf_attn(const __half* __restrict__ q16,
         }
         float S[8][4];
         pa_scores(S, qa, ks_addr(cur), lane, kt == qt, qrow0, kt * 64);
+        if (!TWO_PASS) {
+            float t0 = -INFINITY, t1 = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 8; j++) { t0 = fmaxf(t0, fmaxf(S[j][0], S[j][1])); t1 = fmaxf(t1, fmaxf(S[j][2], S[j][3])); }
+            t0 = quad_max(t0); t1 = quad_max(t1);
+            const float n0 = fmaxf(m0, t0), n1 = fmaxf(m1, t1);
+            if (__any_sync(0xffffffffu, n0 != m0 || n1 != m1)) {      // a new maximum: rescale what has been accumulated
+                const float c0 = ex2_approx((m0 - n0) * PA_C), c1 = ex2_approx((m1 - n1) * PA_C);
+                l0 *= c0; l1 *= c1;
+#pragma unroll
+                for (int j = 0; j < 8; j++) { O[j][0] *= c0; O[j][1] *= c0; O[j][2] *= c1; O[j][3] *= c1; }
+                m0 = n0; m1 = n1;
+            }
+        }
+        const float nc0 = -m0 * PA_C, nc1 = -m1 * PA_C;
 #pragma unroll
         for (int j = 0; j < 8; j++) {                                 // e = exp(s - max), ops.h:982-988
-            S[j][0] = ex2_approx((S[j][0] - m0) * PA_C); S[j][1] = ex2_approx((S[j][1] - m0) * PA_C);
-            S[j][2] = ex2_approx((S[j][2] - m1) * PA_C); S[j][3] = ex2_approx((S[j][3] - m1) * PA_C);
+            S[j][0] = ex2_approx(fmaf(S[j][0], PA_C, nc0)); S[j][1] = ex2_approx(fmaf(S[j][1], PA_C, nc0));
+            S[j][2] = ex2_approx(fmaf(S[j][2], PA_C, nc1)); S[j][3] = ex2_approx(fmaf(S[j][3], PA_C, nc1));
+            if (!TWO_PASS) { l0 += S[j][0] + S[j][1]; l1 += S[j][2] + S[j][3]; }
         }
 #pragma unroll
         for (int bb = 0; bb < 2; bb++) {                              // one Q8 block = 32 keys = 4 octets (ops.h:996)
             float a0 = 0.0f, a1 = 0.0f;
 #pragma unroll
             for (int j = 4 * bb; j < 4 * bb + 4; j++) { a0 = fmaxf(a0, fmaxf(S[j][0], S[j][1])); a1 = fmaxf(a1, fmaxf(S[j][2], S[j][3])); }
-            a0 = quad_max(a0) * pinv0; a1 = quad_max(a1) * pinv1;     // largest probability of the block (p = e / sum, ops.h:991-994)
-            const float de0 = __fdiv_rn(a0, 127.0f), de1 = __fdiv_rn(a1, 127.0f);
-            // code = round(p * (1 / delta)) with p = e * pinv: one multiply per element
-            const float f0 = (de0 != 0.0f) ? __fdiv_rn(1.0f, de0) * pinv0 : 0.0f, f1 = (de1 != 0.0f) ? __fdiv_rn(1.0f, de1) * pinv1 : 0.0f;
-            const float dq0 = h2f(f2h(de0)), dq1 = h2f(f2h(de1));
+            a0 = quad_max(a0); a1 = quad_max(a1);
+            float f0, f1, dq0, dq1;
+            if (TWO_PASS) {
+                a0 *= pinv0; a1 *= pinv1;                             // largest probability of the block (p = e / sum, ops.h:991-994)
+                const float de0 = __fdiv_rn(a0, 127.0f), de1 = __fdiv_rn(a1, 127.0f);
+                f0 = (de0 != 0.0f) ? __fdiv_rn(1.0f, de0) * pinv0 : 0.0f;     // code = round(p / delta), p = e * pinv
+                f1 = (de1 != 0.0f) ? __fdiv_rn(1.0f, de1) * pinv1 : 0.0f;
+                dq0 = h2f(f2h(de0)); dq1 = h2f(f2h(de1));
+            } else {
+                f0 = (a0 != 0.0f) ? __fdiv_rn(127.0f, a0) : 0.0f; f1 = (a1 != 0.0f) ? __fdiv_rn(127.0f, a1) : 0.0f;
+                dq0 = a0 * (1.0f / 127.0f); dq1 = a1 * (1.0f / 127.0f);
+            }
             float Ob[8][4];
 #pragma unroll
             for (int j = 0; j < 8; j++) Ob[j][0] = Ob[j][1] = Ob[j][2] = Ob[j][3] = 0.0f;
 #pragma unroll
             for (int kk = 2 * bb; kk < 2 * bb + 2; kk++) {            // 16 keys per MMA k-step; the integer codes are exact in fp16
+                const float M = 12582912.0f;                          // (x + 1.5 * 2^23) - 1.5 * 2^23 = nearest integer
                 uint32_t pa[4];
-                pa[0] = pack_h2(rne_int(S[2 * kk][0] * f0), rne_int(S[2 * kk][1] * f0));
-                pa[1] = pack_h2(rne_int(S[2 * kk][2] * f1), rne_int(S[2 * kk][3] * f1));
-                pa[2] = pack_h2(rne_int(S[2 * kk + 1][0] * f0), rne_int(S[2 * kk + 1][1] * f0));
-                pa[3] = pack_h2(rne_int(S[2 * kk + 1][2] * f1), rne_int(S[2 * kk + 1][3] * f1));
+                pa[0] = pack_h2(fmaf(S[2 * kk][0], f0, M) - M, fmaf(S[2 * kk][1], f0, M) - M);
+                pa[1] = pack_h2(fmaf(S[2 * kk][2], f1, M) - M, fmaf(S[2 * kk][3], f1, M) - M);
+                pa[2] = pack_h2(fmaf(S[2 * kk + 1][0], f0, M) - M, fmaf(S[2 * kk + 1][1], f0, M) - M);
+                pa[3] = pack_h2(fmaf(S[2 * kk + 1][2], f1, M) - M, fmaf(S[2 * kk + 1][3], f1, M) - M);
 #pragma unroll
                 for (int jp = 0; jp < 4; jp++) {
                     uint32_t b0, b1, b2, b3;
@@ -915,6 +968,11 @@ __global__ void __launch_bounds__(128) k_pf_attn(const __half* __restrict__ q16,
                 O[j][2] = fmaf(dq1, Ob[j][2], O[j][2]); O[j][3] = fmaf(dq1, Ob[j][3], O[j][3]);
             }
         }
+    }
+    if (!TWO_PASS) {
+        const float i0 = __fdiv_rn(1.0f, quad_sum(l0)), i1 = __fdiv_rn(1.0f, quad_sum(l1));
+#pragma unroll
+        for (int j = 0; j < 8; j++) { O[j][0] *= i0; O[j][1] *= i0; O[j][2] *= i1; O[j][3] *= i1; }
     }
 
     // ---- output row: Q8 re-encode per 32 channels (ops.h:1084), fp16 operand of the o-projection
@@ -975,6 +1033,21 @@ static int make_tmap(CUtensorMap* m, const void* base, int rows, int cols, int b
     return GTB_OK;
 }
 
+static bool g_pdl = true;
+
+// launch on the library stream; with `g_pdl` the launch carries the programmatic-stream-serialization attribute (the kernel
+// itself orders its global accesses after the previous kernel with griddepcontrol.wait)
+template <typename... KArgs, typename... Args>
+static cudaError_t pf_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = ctx().stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 template <int BN, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const PfEpi& ep) {
     using Cfg = PfGemmCfg<BN>;
@@ -985,7 +1058,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int 
     }
     const int n_tiles = ((M + PF_BM - 1) / PF_BM) * ((N + BN - 1) / BN);
     const int grid = n_tiles < ctx().sm_count ? n_tiles : ctx().sm_count;
-    k_pf_gemm<BN, EPI><<<grid, PF_THREADS, Cfg::SMEM, ctx().stream>>>(ta, tb, M, N, K, ep);
+    GTB_CUDA(pf_launch(k_pf_gemm<BN, EPI>, dim3(grid), dim3(PF_THREADS), Cfg::SMEM, ta, tb, M, N, K, ep));
     GTB_LAUNCHED();
     return GTB_OK;
 }
@@ -1006,7 +1079,7 @@ static int gemm_epi2(const CUtensorMap& ta, const CUtensorMap& tb128, int M, int
     const int n_tiles = ((M + 255) / 256) * ((N + 255) / 256);
     const int max_clusters = ctx().sm_count / 2;
     const int clusters = n_tiles < max_clusters ? n_tiles : max_clusters;
-    k_pf_gemm2<EPI><<<2 * clusters, PF_THREADS, PF2_SMEM, ctx().stream>>>(ta, tb128, M, N, K, ep);
+    GTB_CUDA(pf_launch(k_pf_gemm2<EPI>, dim3(2 * clusters), dim3(PF_THREADS), PF2_SMEM, ta, tb128, M, N, K, ep));
     GTB_LAUNCHED();
     return GTB_OK;
 }
@@ -1045,6 +1118,7 @@ struct PfPlan {
     int E = 0, F = 0, KV = 0, NQKV = 0, Tcap = 0;
     bool fused = true;               // RoPE/KV-append and SiLU*up inside the GEMM epilogues
     bool two_cta = false;            // CTA-pair GEMM (k_pf_gemm2) wherever the tile is 256 wide
+    bool attn_two_pass = false;      // true: a second QK^T sweep so that the fp16 rounding of the P-row block scales is reproduced too
     std::vector<PfLayerW> L;
     // activations for up to Tcap rows
     int8_t *xq = nullptr, *qkvq = nullptr, *oq = nullptr, *guq = nullptr;
@@ -1120,6 +1194,8 @@ size_t pf_bytes(const PfPlan* p) { return p->bytes; }
 int64_t pf_launches_last(const PfPlan* p) { return p->launches_last; }
 
 void pf_set_fused(PfPlan* p, bool on) { p->fused = on; }
+void pf_set_pdl(bool on) { g_pdl = on; }
+void pf_set_attn_two_pass(PfPlan* p, bool on) { p->attn_two_pass = on; }
 void pf_set_two_cta(PfPlan* p, bool on) { p->two_cta = on; }
 
 template <int EPI>
@@ -1149,12 +1225,12 @@ int pf_run(PfPlan* p, const PfRun& r) {
     const int nbE = E / 32;
     {
         const size_t n = (size_t)T * nbE;
-        k_pf_embed<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(r.embed->data, r.embed->scales, r.embed->dtype, r.d_tokens, T, E, p->xq, p->xs,
-                                                                 capp(0, GTB_A_EMB), r.capw);
+        GTB_CUDA(pf_launch(k_pf_embed, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, r.embed->data, r.embed->scales, r.embed->dtype, r.d_tokens, T, E, p->xq, p->xs,
+                                                                 capp(0, GTB_A_EMB), r.capw));
         GTB_LAUNCHED();
     }
-    k_pf_add_norm<<<T, 64, 0, st>>>(p->xq, p->xs, nullptr, nullptr, r.layers[0].attn_norm, p->xn16, T, E, nullptr, nullptr,
-                                            capp(0, GTB_A_ATTN_NORM), r.capw);
+    GTB_CUDA(pf_launch(k_pf_add_norm, dim3(T), dim3(64), 0, p->xq, p->xs, nullptr, nullptr, r.layers[0].attn_norm, p->xn16, T, E, nullptr, nullptr,
+                                            capp(0, GTB_A_ATTN_NORM), r.capw));
     GTB_LAUNCHED();
     const int bn_qkv = pick_bn(T, NQKV), bn_o = pick_bn(T, E), bn_gu = pick_bn(T, 2 * F), bn_d = pick_bn(T, E);
     for (int li = 0; li < r.n_layers_run; li++) {
@@ -1172,17 +1248,18 @@ int pf_run(PfPlan* p, const PfRun& r) {
             rc = gemm_any<EPI_Q8>(p->two_cta, ta_xn, w.tm[0], bn_qkv, T, NQKV, E, eq);
             if (rc) return rc;
             const size_t n = (size_t)T * (nh + 2 * ng);
-            k_pf_rope_kv<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p->qkvq, p->qkvs, T, eq);
+            GTB_CUDA(pf_launch(k_pf_rope_kv, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, p->qkvq, p->qkvs, T, eq));
             GTB_LAUNCHED();
         }
-        k_pf_attn<<<(unsigned)(((T + 63) / 64) * nh), 128, 0, st>>>(p->q16, p->k16, p->v16, p->attn16, T, nh, nh / ng, capp(li, GTB_A_ATTN_OUT), r.capw);
+        if (p->attn_two_pass) GTB_CUDA(pf_launch(k_pf_attn<true>, dim3((unsigned)(((T + 63) / 64) * nh)), dim3(128), 0, p->q16, p->k16, p->v16, p->attn16, T, nh, nh / ng, capp(li, GTB_A_ATTN_OUT), r.capw));
+        else GTB_CUDA(pf_launch(k_pf_attn<false>, dim3((unsigned)(((T + 63) / 64) * nh)), dim3(128), 0, p->q16, p->k16, p->v16, p->attn16, T, nh, nh / ng, capp(li, GTB_A_ATTN_OUT), r.capw));
         GTB_LAUNCHED();
         PfEpi eo;
         eo.out0 = p->oq; eo.out1 = p->os;
         rc = gemm_any<EPI_Q8>(p->two_cta, ta_attn, w.tm[1], bn_o, T, E, E, eo);
         if (rc) return rc;
-        k_pf_add_norm<<<T, 64, 0, st>>>(p->xq, p->xs, p->oq, p->os, io.ffn_norm, p->xn16, T, E, capp(li, GTB_A_O), capp(li, GTB_A_INP_RES),
-                                        capp(li, GTB_A_FFN_NORM), r.capw);
+        GTB_CUDA(pf_launch(k_pf_add_norm, dim3(T), dim3(64), 0, p->xq, p->xs, p->oq, p->os, io.ffn_norm, p->xn16, T, E, capp(li, GTB_A_O), capp(li, GTB_A_INP_RES),
+                                        capp(li, GTB_A_FFN_NORM), r.capw));
         GTB_LAUNCHED();
         PfEpi eg;                                   // gate|up: Linear re-encode, SiLU, Multiply
         eg.out0 = p->guq; eg.out1 = p->gus; eg.act16 = p->act16; eg.F = F;
@@ -1194,17 +1271,17 @@ int pf_run(PfPlan* p, const PfRun& r) {
             rc = gemm_any<EPI_Q8>(p->two_cta, ta_xn, w.tm[2], bn_gu, T, 2 * F, E, eg);
             if (rc) return rc;
             const size_t n = (size_t)T * (F / 32);
-            k_pf_silu_mul<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p->guq, p->gus, T, eg);
+            GTB_CUDA(pf_launch(k_pf_silu_mul, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, p->guq, p->gus, T, eg));
             GTB_LAUNCHED();
         }
         rc = gemm_any<EPI_Q8>(p->two_cta, ta_act, w.tm[3], bn_d, T, E, F, eo);
         if (rc) return rc;
         if (li + 1 < r.n_layers_run) {
-            k_pf_add_norm<<<T, 64, 0, st>>>(p->xq, p->xs, p->oq, p->os, r.layers[li + 1].attn_norm, p->xn16, T, E, capp(li, GTB_A_DOWN),
-                                            capp(li, GTB_A_ATTN_RES), capp(li + 1, GTB_A_ATTN_NORM), r.capw);
+            GTB_CUDA(pf_launch(k_pf_add_norm, dim3(T), dim3(64), 0, p->xq, p->xs, p->oq, p->os, r.layers[li + 1].attn_norm, p->xn16, T, E, capp(li, GTB_A_DOWN),
+                                            capp(li, GTB_A_ATTN_RES), capp(li + 1, GTB_A_ATTN_NORM), r.capw));
             GTB_LAUNCHED();
         } else {
-            k_pf_tail<<<(E + 255) / 256, 256, 0, st>>>(p->xq, p->xs, p->oq, p->os, T - 1, E, r.last_res, r.last_down, capp(li, GTB_A_DOWN), T, r.capw);
+            GTB_CUDA(pf_launch(k_pf_tail, dim3((E + 255) / 256), dim3(256), 0, p->xq, p->xs, p->oq, p->os, T - 1, E, r.last_res, r.last_down, capp(li, GTB_A_DOWN), T, r.capw));
             GTB_LAUNCHED();
         }
     }

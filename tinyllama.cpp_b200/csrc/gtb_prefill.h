@@ -43,6 +43,8 @@ int pf_set_weight(PfPlan* p, int layer, int which, int wdtype, const void* d_dat
 bool pf_weights_ready(const PfPlan* p);
 int pf_run(PfPlan* p, const PfRun& r);
 void pf_set_two_cta(PfPlan* p, bool on);   // CTA-pair (tcgen05 cta_group::2) GEMM for the 256-wide tiles
+void pf_set_pdl(bool on);                  // programmatic dependent launch between the kernels of the chain (default on)
+void pf_set_attn_two_pass(PfPlan* p, bool on);   // false: single-sweep attention (P-row block scales applied unrounded)
 void pf_set_fused(PfPlan* p, bool on);     // false: RoPE/KV append and SiLU*up as separate kernels after plain GEMMs (debug)
 size_t pf_bytes(const PfPlan* p);
 int64_t pf_launches_last(const PfPlan* p);
