@@ -117,11 +117,12 @@ __device__ __forceinline__ uint16_t q8_encode32(const float (&x)[32], int (&q)[3
     for (int i = 0; i < 32; i++) q[i] = (int)roundf(__fmul_rn(x[i], scale));   // half away from zero
     return f2h(delta);
 }
-__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
-    return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);
+// four codes -> one word; only the low byte of each argument is used (two's complement code)
+__device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
 // natural order (planar activations, V cache)
-__device__ __forceinline__ void store_codes32(int8_t* dst, const int (&q)[32]) {
+__device__ __forceinline__ void store_codes32(int8_t* dst, const uint32_t (&q)[32]) {
     uint4 lo, hi;
     lo.x = pack4(q[0], q[1], q[2], q[3]);     lo.y = pack4(q[4], q[5], q[6], q[7]);
     lo.z = pack4(q[8], q[9], q[10], q[11]);   lo.w = pack4(q[12], q[13], q[14], q[15]);
@@ -131,7 +132,7 @@ __device__ __forceinline__ void store_codes32(int8_t* dst, const int (&q)[32]) {
     reinterpret_cast<uint4*>(dst)[1] = hi;
 }
 // staged order of the K cache (gtb_kernels.cuh perm_byte): word l of a half = elements (2l, 2l+1, 2l+8, 2l+9)
-__device__ __forceinline__ void store_codes32_perm(uint8_t* dst, const int (&q)[32]) {
+__device__ __forceinline__ void store_codes32_perm(uint8_t* dst, const uint32_t (&q)[32]) {
     uint4 lo, hi;
     lo.x = pack4(q[0], q[1], q[8], q[9]);     lo.y = pack4(q[2], q[3], q[10], q[11]);
     lo.z = pack4(q[4], q[5], q[12], q[13]);   lo.w = pack4(q[6], q[7], q[14], q[15]);
@@ -146,6 +147,12 @@ __device__ __forceinline__ void load_codes32(const int8_t* src, int (&q)[32]) {
     const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
     for (int i = 0; i < 32; i++) q[i] = sbyte(w[i >> 2], i & 3);
+}
+__device__ __forceinline__ void load_codes32(const int8_t* src, uint32_t (&q)[32]) {
+    const uint4 lo = reinterpret_cast<const uint4*>(src)[0], hi = reinterpret_cast<const uint4*>(src)[1];
+    const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int i = 0; i < 32; i++) q[i] = w[i >> 2] >> (8 * (i & 3));
 }
 // dequantised block of a planar activation: value = code * fp32(delta) (exact in fp32, quants.h:69-76)
 __device__ __forceinline__ void load_deq32(const int8_t* q, const uint16_t* s, size_t row, int D, int b, float (&v)[32]) {
@@ -186,23 +193,35 @@ struct PfEpi {
     float *cap0 = nullptr, *cap1 = nullptr, *cap2 = nullptr; int capw = 0;
 };
 
-// __expf is within 2 ulp of the reference's correctly rounded expf: a 1e-7 relative change of silu(x), far below the
+// __expf and the fast division are each within 2 ulp of the reference's expf and '/': a 1e-7 relative change of silu(x), far below the
 // fp16 operand rounding of this path (the exact path keeps glibc's algorithm, gtb_dev.cuh expf_glibc)
-__device__ __forceinline__ float pf_silu(float x) { return __fdiv_rn(x, __fadd_rn(1.0f, __expf(-x))); }
+__device__ __forceinline__ float pf_silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
-// encode a raw block and leave its decoded value in place (write_row_from_float + read_row_to_float, ops.h:40-96)
-__device__ __forceinline__ uint16_t pf_roundtrip32(float (&x)[32], int (&q)[32]) {
-    const uint16_t dh = q8_encode32(x, q);
-    const float d = h2f(dh);
+// Q8 encode of a block held by one thread, decoded value left in place (write_row_from_float + read_row_to_float,
+// ops.h:40-96; quants.h:52-66).  Rounding is to nearest via the 1.5 * 2^23 magic number: the code sits in the low byte of
+// the biased sum.  This differs from the reference's roundf (half away from zero) only when x * scale lands exactly on
+// k + 0.5; the bit-exact path (gtb_dev.cuh) keeps roundf.
+__device__ __forceinline__ uint16_t pf_roundtrip32(float (&x)[32], uint32_t (&q)[32]) {
+    float amax = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 32; i++) x[i] = __fmul_rn((float)q[i], d);
+    for (int i = 0; i < 32; i++) amax = fmaxf(amax, fabsf(x[i]));
+    const float delta = __fdiv_rn(amax, 127.0f);
+    const uint16_t dh = f2h(delta);
+    const float d = h2f(dh);
+    const float scale = (delta != 0.0f) ? __fdiv_rn(1.0f, delta) : 0.0f;       // from the UNROUNDED delta
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        const float t = fmaf(x[i], scale, 12582912.0f);
+        q[i] = __float_as_uint(t);
+        x[i] = __fmul_rn(__fsub_rn(t, 12582912.0f), d);
+    }
     return dh;
 }
 
 // One head slot of the q|k|v Linear output of row `row`: x0/x1 = the two decoded Q8 blocks, (q0,dh0)/(q1,dh1) their codes.
 // q and k heads: RoPE (ops.h:714-760) and the second re-encode; k and v: append to the cache in the engine's layout.
 __device__ __forceinline__ void pf_rope_store(const PfEpi& ep, int row, int slot, float (&x0)[32], float (&x1)[32],
-                                              int (&q0)[32], int (&q1)[32], uint16_t dh0, uint16_t dh1) {
+                                              uint32_t (&q0)[32], uint32_t (&q1)[32], uint16_t dh0, uint16_t dh1) {
     const int nh = ep.nh, ng = ep.ng, E = nh * 64, KV = ng * 64;
     const bool is_v = slot >= nh + ng;
     if (!is_v) {
@@ -253,7 +272,7 @@ __device__ __forceinline__ void pf_rope_store(const PfEpi& ep, int row, int slot
 __device__ __forceinline__ void pf_silu_store(const PfEpi& ep, int row, int b, float (&g)[32], const float (&u)[32]) {
 #pragma unroll
     for (int k = 0; k < 32; k++) g[k] = pf_silu(g[k]);
-    int q[32];
+    uint32_t q[32];
     pf_roundtrip32(g, q);
 #pragma unroll
     for (int k = 0; k < 32; k++) g[k] = __fmul_rn(g[k], u[k]);
@@ -300,8 +319,8 @@ __device__ __forceinline__ void pf_epilogue(const PfEpi& ep, uint32_t tacc, int 
                 if (EPI == EPI_F32) {
                     store_f32x32(reinterpret_cast<float*>(ep.out0) + (size_t)row * N + col, v);
                 } else {
-                    int q[32];
-                    const uint16_t dh = q8_encode32(v, q);        // write_row_from_float, ops.h:645-646
+                    uint32_t q[32];
+                    const uint16_t dh = pf_roundtrip32(v, q);     // write_row_from_float, ops.h:645-646
                     store_codes32(reinterpret_cast<int8_t*>(ep.out0) + (size_t)row * N + col, q);
                     reinterpret_cast<uint16_t*>(ep.out1)[(size_t)row * (N / 32) + (col >> 5)] = dh;
                 }
@@ -316,7 +335,7 @@ __device__ __forceinline__ void pf_epilogue(const PfEpi& ep, uint32_t tacc, int 
             tmem_ld32(tacc + (uint32_t)(c2 * 64), a);
             tmem_ld32(tacc + (uint32_t)(c2 * 64 + 32), b);
             if (row_ok && col < N) {
-                int q0[32], q1[32];
+                uint32_t q0[32], q1[32];
                 const uint16_t dh0 = pf_roundtrip32(a, q0), dh1 = pf_roundtrip32(b, q1);   // the Linear's own re-encode
                 if (EPI == EPI_ROPE) pf_rope_store(ep, row, col >> 6, a, b, q0, q1, dh0, dh1);
                 else pf_silu_store(ep, row, col >> 6, a, b);
@@ -624,7 +643,10 @@ __global__ void k_pf_embed(const void* __restrict__ wdata, const uint16_t* __res
         }
         dh = wsc[blk];
     }
-    store_codes32(xq + (size_t)row * D + (size_t)b * 32, q);
+    uint32_t qb[32];
+#pragma unroll
+    for (int e = 0; e < 32; e++) qb[e] = (uint32_t)q[e];
+    store_codes32(xq + (size_t)row * D + (size_t)b * 32, qb);
     xs[(size_t)row * nb + b] = dh;
     if (cap) {
         const float dd = h2f(dh);
@@ -655,7 +677,7 @@ __global__ void __launch_bounds__(64) k_pf_add_norm(int8_t* __restrict__ xq, uin
             if (cap_y) for (int i = 0; i < 32; i++) cap_y[(size_t)row * capw + b * 32 + i] = y[i];
 #pragma unroll
             for (int i = 0; i < 32; i++) v[i] = __fadd_rn(v[i], y[i]);
-            int q[32];
+            uint32_t q[32];
             const uint16_t dh = pf_roundtrip32(v, q);
             store_codes32(xq + (size_t)row * D + (size_t)b * 32, q);
             xs[(size_t)row * nb + b] = dh;
@@ -684,7 +706,7 @@ __global__ void __launch_bounds__(64) k_pf_add_norm(int8_t* __restrict__ xq, uin
                 v[k * 8 + j] = __fmul_rn(__fdiv_rn(v[k * 8 + j], denom), wf);
             }
         }
-        int q[32];
+        uint32_t q[32];
         pf_roundtrip32(v, q);
         if (cap_n) for (int i = 0; i < 32; i++) cap_n[(size_t)row * capw + b * 32 + i] = v[i];
         store_half32(xn16 + (size_t)row * D + (size_t)b * 32, v);
@@ -701,7 +723,7 @@ __global__ void __launch_bounds__(128) k_pf_rope_kv(const int8_t* __restrict__ c
     const int row = (int)(idx / nslots), slot = (int)(idx % nslots);
     const int D = nslots * 64;
     float x0[32], x1[32];
-    int q0[32], q1[32];
+    uint32_t q0[32], q1[32];
     load_deq32(cq, cs, row, D, slot * 2, x0);
     load_deq32(cq, cs, row, D, slot * 2 + 1, x1);
     load_codes32(cq + (size_t)row * D + (size_t)slot * 64, q0);
@@ -832,7 +854,7 @@ __device__ __forceinline__ void pa_scores(float (&S)[8][4], const uint32_t (&qa)
 //                    (relative 2^-11 per block, averaging out over the blocks of a row -- the same size as the fp16 rounding
 //                    of the V operand).  QK^T and the exps run once instead of twice.
 template <bool TWO_PASS>
-__global__ void __launch_bounds__(128) k_pf_attn(const __half* __restrict__ q16, const __half* __restrict__ k16, const __half* __restrict__ v16,
+__global__ void __launch_bounds__(128, TWO_PASS ? 3 : 4) k_pf_attn(const __half* __restrict__ q16, const __half* __restrict__ k16, const __half* __restrict__ v16,
                                                   __half* __restrict__ out16, int T, int n_heads, int gsz, float* cap, int capw) {
     pdl_trigger_and_wait();
     __shared__ __align__(16) __half Qs[64 * PA_LD];
