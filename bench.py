@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- batch-1 greedy decode throughput of the tinyllama.cpp forward hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload q4|q8|f16] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload q4|q8|f16|prefill_q8] [--impl b200|reference]
 
 One "step" = one decoded token = one pass of the hot path (TinyLlama::logits for one new row + argmax).
 Default workload = BASELINE.json configs[2], the configuration north_star's target is quoted on:
@@ -36,6 +36,7 @@ sys.path.insert(0, str(ROOT))
 import gtb  # noqa: E402,F401
 from tinyllama_cpp_b200 import weights as W  # noqa: E402
 
+PREFILL_DESC = "TinyLlama-1.1B Q8 (-q8) prefill of a 2048-token synthetic prompt (BASELINE.json configs[3])"
 WORKLOADS = {
     # name: (wdtype, BASELINE.json config index, description)
     "q4": (W.Q4, 2, "TinyLlama-1.1B Q4 (-q4) batch-1 greedy decode ending at the full 2048-token KV cache (BASELINE.json configs[2])"),
@@ -220,18 +221,67 @@ def prefill_section(capi, torch, stream, iters=5, warmup=3, T=2048, cpu=True):
     return out
 
 
+def run_prefill(args):
+    """`--workload prefill_q8`: the whole line is BASELINE.json configs[3]; a "step" is one 2048-token prefill (N = 1 only:
+    the prompt is one sequence).  `--impl reference` times the reference CPU build on a bounded sample of the same prompt."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cfg = W.TINYLLAMA
+    T = 2048
+    if args.impl == "reference":
+        import oracle
+        lib = oracle.best()
+        cores = os.cpu_count() or 1
+        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+        n = 32
+        m = lib.model(cfg, 2 * n + 64, W.Q8).load(W.synth_weights(cfg, W.Q8, seed=1))
+        prompt = W.synth_prompt(7, T, cfg.n_vocab)
+        steps = max(1, min(args.steps, 4))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            m.logits(prompt[:n], 0)
+        dt = (time.perf_counter() - t0) / steps
+        v = n / dt
+        sample = f"prefill of the first {n} tokens of the prompt, {steps} times (row-by-row GEMV, ops.h:632: cost per row is flat in the prompt length at this size)"
+        print(json.dumps({"impl": "reference", "metric": "prefill_tokens_per_s", "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps,
+                          "warmup": 0, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": DTYPE_STR[W.Q8], "data": "synthetic", "config": {"workload": PREFILL_DESC, "sample": sample},
+                          "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": lib.kind, "sample": sample},
+                          "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    import torch
+    from tinyllama_cpp_b200 import capi
+    capi.init(0)
+    torch.cuda.set_device(0)
+    stream = torch.cuda.ExternalStream(capi.stream_handle(), device=torch.device("cuda", 0))
+    with ClockSampler(0) as clk:
+        p = prefill_section(capi, torch, stream, iters=max(args.steps if args.steps != 512 else 8, 3), warmup=args.warmup, T=T,
+                            cpu=not args.no_cpu_baseline)
+    out = {"metric": p["metric"], "value": p["value"], "unit": p["unit"], "n_gpus": 1, "steps": max(args.steps if args.steps != 512 else 8, 3),
+           "warmup": args.warmup, "ms_per_step": p["ms_per_prefill"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "fp16 operands (dequantised q8 blocks) x fp16, fp32 accumulate in TMEM; q8 re-encode in the epilogues", "data": "synthetic",
+           "config": dict(p["config"], l2="operands larger than L2: 2.07 GB of fp16 weight copies per prefill"),
+           "roofline": dict(p["roofline"], traffic=None, kernel="k_pf_gemm<256,*> (58 % of the step; the roofline is quoted on the whole prefill)"),
+           "e2e": p["e2e"], "gpu_launches": p["gpu_launches"], "clocks": clk.summary()}
+    if "cpu_baseline" in p:
+        out["cpu_baseline"] = p["cpu_baseline"]
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=512)
     ap.add_argument("--warmup", type=int, default=16)
-    ap.add_argument("--workload", choices=list(WORKLOADS), default="q4")
+    ap.add_argument("--workload", choices=list(WORKLOADS) + ["prefill_q8"], default="q4")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-prefill", action="store_true", help="skip the configs[3] prefill measurement appended to the N=1 line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.workload == "prefill_q8":
+        return run_prefill(args)
     wdt, cfg_idx, desc = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, wdt, desc)

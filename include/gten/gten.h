@@ -36,10 +36,19 @@ public:
     FusedTinyLlama(const FusedTinyLlama&) = delete;
     FusedTinyLlama& operator=(const FusedTinyLlama&) = delete;
     void load_from_ckpt(const char* path) { GTEN_CUDA_OK(gtb_engine_load_gten(eng_, path)); }
+    // Opt in to the batched tensor-core prefill (gtb_engine_prefill_fast) for the prompt call logits(tokens, 0): every Linear
+    // of the prompt rows becomes one tcgen05 GEMM.  Its results match the reference within a tolerance, not bit for bit
+    // (DESIGN.md 4.4); later calls (start_pos > 0) always take the order-exact path.  Q8 and Q4 models; prompts of >= 2 tokens.
+    void set_batched_prefill(bool on) { batched_prefill_ = on; }
     Tensor logits(const Tensor& tokens, const int start_pos = 0) {
         if (tokens.numel() > n_ctx_) {
             std::cerr << "Number of prompt tokens (" << tokens.numel() << ") exceed provided maximum ctx size (" << n_ctx_ << ")\n";
             std::exit(EXIT_FAILURE);
+        }
+        if (batched_prefill_ && start_pos == 0 && tokens.numel() >= 2 && tokens.numel() < n_ctx_) {
+            GTEN_CUDA_OK(gtb_engine_prefill_fast(eng_, tokens.data_ptr<int32_t>(), tokens.numel()));
+            GTEN_CUDA_OK(gtb_engine_read_logits(eng_, logits_.data_ptr<float>()));
+            return logits_;
         }
         GTEN_CUDA_OK(gtb_engine_logits(eng_, tokens.data_ptr<int32_t>(), tokens.numel(), start_pos, logits_.data_ptr<float>()));
         return logits_;
@@ -49,6 +58,7 @@ private:
     int n_ctx_;
     gtb_engine_t eng_ = nullptr;
     Tensor logits_;
+    bool batched_prefill_ = false;
 };
 
 }  // namespace gten

@@ -150,6 +150,38 @@ def test_batched_prefill_then_decode_runs_in_megakernel(capi):
     e.close(); e2.close()
 
 
+@pytest.mark.parametrize("n_prompt", [1, 2, 33, 129, 190])
+def test_batched_prefill_ragged_lengths(capi, checker, n_prompt):
+    """Lengths that are not multiples of the 128-row GEMM tile / 64-row attention tile / 32-key block, the single-row
+    prompt and the longest prompt max_ctx allows (n < max_ctx); bound = the worst spread the reference shows on this model."""
+    cfg = W.mini_config(n_layers=2, n_vocab=300)
+    wl = list(W.synth_weights(cfg, Q4, seed=12))
+    max_ctx = 191
+    cm = checker.model(cfg, max_ctx + 1, Q4).load(wl)          # Q8 P rows: the oracle needs ceil(n/32)*34 <= max_ctx (SURVEY App. B1)
+    e = capi.Engine(cfg, max_ctx, Q4).load(wl)
+    prompt = W.synth_prompt(31, n_prompt, cfg.n_vocab)
+    want = cm.logits(prompt, 0)
+    e.prefill_fast(prompt)
+    assert e.position() == n_prompt
+    bound = SLACK * max(float(SENS[k]) for k in SENS.files if k.startswith("mini_") and k.endswith("_logits")) + ABS
+    err = rel(e.read_logits(), want)
+    assert err <= bound, (n_prompt, err, bound)
+    e.close(); cm.close()
+
+
+def test_batched_prefill_argument_errors(capi):
+    cfg = W.mini_config(n_layers=1, n_vocab=64)
+    e = capi.Engine(cfg, 32, Q8)
+    with pytest.raises(capi.GtbError, match="not loaded"):
+        e.prefill_fast(np.zeros(4, np.int32))
+    e.load(W.synth_weights(cfg, Q8, seed=2))
+    with pytest.raises(capi.GtbError, match="argument check failed"):
+        e.prefill_fast(np.zeros(32, np.int32))              # n must leave room for the first generated token
+    with pytest.raises(capi.GtbError, match="argument check failed"):
+        e.prefill_fast(np.zeros(0, np.int32))
+    e.close()
+
+
 def test_fused_epilogues_equal_unfused_kernels(capi):
     """RoPE/KV-append and SiLU*up run inside the GEMM epilogues; the stand-alone kernels share their arithmetic, so both
     routes must give the same bits (logits, K/V cache via the next exact row)."""
