@@ -157,7 +157,7 @@ def test_batched_prefill_ragged_lengths(capi, checker, n_prompt):
     cfg = W.mini_config(n_layers=2, n_vocab=300)
     wl = list(W.synth_weights(cfg, Q4, seed=12))
     max_ctx = 191
-    cm = checker.model(cfg, max_ctx + 1, Q4).load(wl)          # Q8 P rows: the oracle needs ceil(n/32)*34 <= max_ctx
+    cm = checker.model(cfg, 256, Q4).load(wl)                  # Q8 P rows: the reference needs ceil(n/32)*34 <= max_ctx
     e = capi.Engine(cfg, max_ctx, Q4).load(wl)
     prompt = W.synth_prompt(31, n_prompt, cfg.n_vocab)
     want = cm.logits(prompt, 0)
