@@ -852,7 +852,8 @@ __device__ __forceinline__ void pa_scores(float (&S)[8][4], const uint32_t (&qa)
 //                    (max_e / 127, rescaled with the running maximum, divided by the final sum at the end), i.e. the one
 //                    rounding point this variant does not reproduce is the fp16 rounding of the P-row block scales
 //                    (relative 2^-11 per block, averaging out over the blocks of a row -- the same size as the fp16 rounding
-//                    of the V operand).  QK^T and the exps run once instead of twice.
+//                    of the V operand).  QK^T and the exps run once instead of twice; the decoded probabilities
+//                    (code x scale) are the fp16 A operand of P.V, accumulated in one set of registers.
 template <bool TWO_PASS>
 __global__ void __launch_bounds__(128, TWO_PASS ? 3 : 4) k_pf_attn(const __half* __restrict__ q16, const __half* __restrict__ k16, const __half* __restrict__ v16,
                                                   __half* __restrict__ out16, int T, int n_heads, int gsz, float* cap, int capw) {
@@ -965,29 +966,50 @@ __global__ void __launch_bounds__(128, TWO_PASS ? 3 : 4) k_pf_attn(const __half*
                 f0 = (a0 != 0.0f) ? __fdiv_rn(127.0f, a0) : 0.0f; f1 = (a1 != 0.0f) ? __fdiv_rn(127.0f, a1) : 0.0f;
                 dq0 = a0 * (1.0f / 127.0f); dq1 = a1 * (1.0f / 127.0f);
             }
-            float Ob[8][4];
+            const float M = 12582912.0f;                              // (x + 1.5 * 2^23) - 1.5 * 2^23 = nearest integer
+            if (TWO_PASS) {
+                // the integer codes (exact in fp16) go through the tensor cores; the block scale multiplies the partial sum
+                float Ob[8][4];
 #pragma unroll
-            for (int j = 0; j < 8; j++) Ob[j][0] = Ob[j][1] = Ob[j][2] = Ob[j][3] = 0.0f;
+                for (int j = 0; j < 8; j++) Ob[j][0] = Ob[j][1] = Ob[j][2] = Ob[j][3] = 0.0f;
 #pragma unroll
-            for (int kk = 2 * bb; kk < 2 * bb + 2; kk++) {            // 16 keys per MMA k-step; the integer codes are exact in fp16
-                const float M = 12582912.0f;                          // (x + 1.5 * 2^23) - 1.5 * 2^23 = nearest integer
-                uint32_t pa[4];
-                pa[0] = pack_h2(fmaf(S[2 * kk][0], f0, M) - M, fmaf(S[2 * kk][1], f0, M) - M);
-                pa[1] = pack_h2(fmaf(S[2 * kk][2], f1, M) - M, fmaf(S[2 * kk][3], f1, M) - M);
-                pa[2] = pack_h2(fmaf(S[2 * kk + 1][0], f0, M) - M, fmaf(S[2 * kk + 1][1], f0, M) - M);
-                pa[3] = pack_h2(fmaf(S[2 * kk + 1][2], f1, M) - M, fmaf(S[2 * kk + 1][3], f1, M) - M);
+                for (int kk = 2 * bb; kk < 2 * bb + 2; kk++) {        // 16 keys per MMA k-step
+                    uint32_t pa[4];
+                    pa[0] = pack_h2(fmaf(S[2 * kk][0], f0, M) - M, fmaf(S[2 * kk][1], f0, M) - M);
+                    pa[1] = pack_h2(fmaf(S[2 * kk][2], f1, M) - M, fmaf(S[2 * kk][3], f1, M) - M);
+                    pa[2] = pack_h2(fmaf(S[2 * kk + 1][0], f0, M) - M, fmaf(S[2 * kk + 1][1], f0, M) - M);
+                    pa[3] = pack_h2(fmaf(S[2 * kk + 1][2], f1, M) - M, fmaf(S[2 * kk + 1][3], f1, M) - M);
 #pragma unroll
-                for (int jp = 0; jp < 4; jp++) {
-                    uint32_t b0, b1, b2, b3;
-                    ldsm_x4_t(vs_addr(cur) + (uint32_t)(((16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8) * PA_LD + 16 * jp + (lane >> 4) * 8) * 2), b0, b1, b2, b3);
-                    mma_16816(Ob[2 * jp], pa, b0, b1);
-                    mma_16816(Ob[2 * jp + 1], pa, b2, b3);
+                    for (int jp = 0; jp < 4; jp++) {
+                        uint32_t b0, b1, b2, b3;
+                        ldsm_x4_t(vs_addr(cur) + (uint32_t)(((16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8) * PA_LD + 16 * jp + (lane >> 4) * 8) * 2), b0, b1, b2, b3);
+                        mma_16816(Ob[2 * jp], pa, b0, b1);
+                        mma_16816(Ob[2 * jp + 1], pa, b2, b3);
+                    }
                 }
-            }
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                O[j][0] = fmaf(dq0, Ob[j][0], O[j][0]); O[j][1] = fmaf(dq0, Ob[j][1], O[j][1]);
-                O[j][2] = fmaf(dq1, Ob[j][2], O[j][2]); O[j][3] = fmaf(dq1, Ob[j][3], O[j][3]);
+                for (int j = 0; j < 8; j++) {
+                    O[j][0] = fmaf(dq0, Ob[j][0], O[j][0]); O[j][1] = fmaf(dq0, Ob[j][1], O[j][1]);
+                    O[j][2] = fmaf(dq1, Ob[j][2], O[j][2]); O[j][3] = fmaf(dq1, Ob[j][3], O[j][3]);
+                }
+            } else {
+                // decoded probabilities code * scale as the fp16 A operand (7-bit code x scale rounded to 11 bits, like every
+                // other fp16 operand of this path): one accumulator, no per-block partial sums
+#pragma unroll
+                for (int kk = 2 * bb; kk < 2 * bb + 2; kk++) {
+                    uint32_t pa[4];
+                    pa[0] = pack_h2((fmaf(S[2 * kk][0], f0, M) - M) * dq0, (fmaf(S[2 * kk][1], f0, M) - M) * dq0);
+                    pa[1] = pack_h2((fmaf(S[2 * kk][2], f1, M) - M) * dq1, (fmaf(S[2 * kk][3], f1, M) - M) * dq1);
+                    pa[2] = pack_h2((fmaf(S[2 * kk + 1][0], f0, M) - M) * dq0, (fmaf(S[2 * kk + 1][1], f0, M) - M) * dq0);
+                    pa[3] = pack_h2((fmaf(S[2 * kk + 1][2], f1, M) - M) * dq1, (fmaf(S[2 * kk + 1][3], f1, M) - M) * dq1);
+#pragma unroll
+                    for (int jp = 0; jp < 4; jp++) {
+                        uint32_t b0, b1, b2, b3;
+                        ldsm_x4_t(vs_addr(cur) + (uint32_t)(((16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8) * PA_LD + 16 * jp + (lane >> 4) * 8) * 2), b0, b1, b2, b3);
+                        mma_16816(O[2 * jp], pa, b0, b1);
+                        mma_16816(O[2 * jp + 1], pa, b2, b3);
+                    }
+                }
             }
         }
     }
