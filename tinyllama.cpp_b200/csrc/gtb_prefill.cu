@@ -15,6 +15,7 @@
 // summation order of a dot differs from ops.h:224-391, so this path is tolerance-checked, not bit-checked.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -191,6 +192,7 @@ struct PfEpi {
     // EPI_SILU (gate|up projection, rows interleaved in groups of 32)
     __half* act16 = nullptr; int F = 0;
     float *cap0 = nullptr, *cap1 = nullptr, *cap2 = nullptr; int capw = 0;
+    int dbg_same_tile = 0;           // experiment: every TMA load fetches tile (0,0) (L2-resident operands, same shared-memory/MMA work)
 };
 
 // __expf and the fast division are each within 2 ulp of the reference's expf and '/': a 1e-7 relative change of silu(x), far below the
@@ -387,8 +389,9 @@ k_pf_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     mbar_wait(bar_empty(s), ph ^ 1);
                     mbar_expect_tx(bar_full(s), Cfg::STAGE_BYTES);
                     const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
-                    tma_load_2d(sa, &tmA, bar_full(s), kb * PF_BK, mt * PF_BM);
-                    tma_load_2d(sa + Cfg::A_BYTES, &tmB, bar_full(s), kb * PF_BK, nt * BN);
+                    const int zz = ep.dbg_same_tile ? 0 : 1;
+                    tma_load_2d(sa, &tmA, bar_full(s), zz * kb * PF_BK, zz * mt * PF_BM);
+                    tma_load_2d(sa + Cfg::A_BYTES, &tmB, bar_full(s), zz * kb * PF_BK, zz * nt * BN);
                     if (++s == ST) { s = 0; ph ^= 1; }
                 }
             }
@@ -1147,6 +1150,7 @@ int pf_gemm_f32(const void* d_A16, const void* d_W16, float* d_C, int M, int N, 
     if (r) return r;
     PfEpi ep;
     ep.out0 = d_C;
+    if (getenv("GTB_PF_SAME_TILE")) ep.dbg_same_tile = 1;
     if (bn == 512) return gemm_epi2<EPI_F32>(ta, tb, M, N, K, ep);      // bn = 512 selects the CTA-pair kernel (256 x 256 tiles)
     return gemm_epi<EPI_F32>(ta, tb, bn, M, N, K, ep);
 }
