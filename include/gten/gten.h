@@ -38,7 +38,7 @@ public:
     void load_from_ckpt(const char* path) { GTEN_CUDA_OK(gtb_engine_load_gten(eng_, path)); }
     // Opt in to the batched tensor-core prefill (gtb_engine_prefill_fast) for the prompt call logits(tokens, 0): every Linear
     // of the prompt rows becomes one tcgen05 GEMM.  Its results match the reference within a tolerance, not bit for bit
-    // (DESIGN.md 4.4); later calls (start_pos > 0) always take the order-exact path.  Q8 and Q4 models; prompts of >= 2 tokens.
+    // (DESIGN.md 4.4); later calls (start_pos > 0) always take the order-exact path.  Prompts of >= 2 tokens.
     void set_batched_prefill(bool on) { batched_prefill_ = on; }
     Tensor logits(const Tensor& tokens, const int start_pos = 0) {
         if (tokens.numel() > n_ctx_) {

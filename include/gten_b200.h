@@ -117,7 +117,7 @@ int gtb_engine_decode(gtb_engine_t e, int n_steps);                             
  * causal GQA attention runs on the tensor cores; K/V land in the cache and the last row's logits / first greedy
  * token come from the order-exact lm_head phase, so gtb_engine_decode continues from here.  Summation order differs
  * from ops.h:224-391: results match the reference within a tolerance (tests/test_prefill_gpu.py), not bit for bit.
- * Q8-activation models only (Q8 and Q4 weights, tinyllama.cpp:258-265). */
+ * All three formats: Q8 and Q4 weights with Q8 activations, FP16 weights with FP16 activations (tinyllama.cpp:258-265). */
 int gtb_engine_prefill_fast(gtb_engine_t e, const int32_t* h_tokens, int n_tokens);
 /* decoded fp32 row `row` of a module activation of the last gtb_engine_prefill_fast call ("capture_acv" on) */
 int gtb_engine_pf_acv(gtb_engine_t e, int layer, int acv_id, int row, float* h_out, int* width);

@@ -20,7 +20,7 @@ ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 import gtb  # noqa: E402,F401
 import oracle  # noqa: E402
-from oracle import Q4, Q8  # noqa: E402
+from oracle import F16, Q4, Q8  # noqa: E402
 from tinyllama_cpp_b200 import weights as W  # noqa: E402
 
 OUT = Path(__file__).resolve().parent
@@ -41,11 +41,13 @@ def scalar_lib():
 def mini(out):
     avx, sca = oracle.ref(), scalar_lib()
     cfg = W.mini_config(n_layers=MINI["n_layers"], n_vocab=MINI["n_vocab"])
-    for wn, wdt in (("q8", Q8), ("q4", Q4)):
+    for wn, wdt in (("q8", Q8), ("q4", Q4), ("f16", F16)):
         wl = list(W.synth_weights(cfg, wdt, seed=MINI["seed"]))
         for T in MINI["n_prompts"]:
-            a = avx.model(cfg, MINI["max_ctx"], wdt).load(wl)
-            s = sca.model(cfg, MINI["max_ctx"], wdt).load(wl)
+            if f"mini_{wn}_{T}_logits" in out:
+                continue
+            a = avx.model(cfg, MINI["max_ctx"] if wdt != F16 else 2 * MINI["max_ctx"], wdt).load(wl)     # FP16 P rows: 2 n <= max_ctx
+            s = sca.model(cfg, MINI["max_ctx"] if wdt != F16 else 2 * MINI["max_ctx"], wdt).load(wl)
             prompt = W.synth_prompt(MINI["prompt_seed"], T, cfg.n_vocab)
             la, ls = a.logits(prompt, 0), s.logits(prompt, 0)
             rows = sorted({0, 1, T // 2, T - 2, T - 1} & set(range(T)))

@@ -1,7 +1,8 @@
 """Batched (tcgen05) prefill against the CPU checker.
 
 The batched path sums each dot product in a different order than ops.h:224-391 and feeds the tensor cores fp16
-operands (dequantised Q8/Q4 values rounded to 11 bits), so parity here is a STATED TOLERANCE, not bit equality:
+operands (dequantised Q8/Q4 values rounded to 11 bits; FP16 models: the fp16 values themselves), so parity here is a
+STATED TOLERANCE, not bit equality:
 
 * the tcgen05 GEMM itself is exact on integer-valued inputs (every product and partial sum is representable);
 * the yardstick for everything else is the reference ITSELF: its two documented builds (README.md:18 scalar,
@@ -21,14 +22,14 @@ import numpy as np
 import pytest
 
 import oracle
-from oracle import Q4, Q8
+from oracle import F16, Q4, Q8
 from tinyllama_cpp_b200 import weights as W
 
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).resolve().parent / "golden"
 
 SLACK = 2.0           # x the reference's own scalar-vs-AVX distance
-ABS = 5e-3            # floor (a layer where the two reference builds happen to agree almost exactly)
+ABS = 5e-3            # floor (a layer where the two reference builds happen to agree almost exactly), never more than half the spread
 SENS = np.load(GOLD / "order_sensitivity.npz")
 
 
@@ -67,7 +68,7 @@ def test_tcgen05_gemm_random(capi):
     assert rel(got, want) < 1e-5        # measured 2.5e-6: the tensor-core accumulator keeps fewer guard bits than an fp32 FMA chain
 
 
-@pytest.mark.parametrize("wdt", [Q8, Q4])
+@pytest.mark.parametrize("wdt", [Q8, Q4, F16])
 @pytest.mark.parametrize("n_prompt", [100, 64, 7])
 def test_batched_prefill_mini(capi, checker, wdt, n_prompt):
     _mini_case(capi, checker, wdt, n_prompt, {})
@@ -85,7 +86,7 @@ def _mini_case(capi, checker, wdt, n_prompt, opts):
     cfg = W.mini_config(n_layers=3, n_vocab=300)
     wl = list(W.synth_weights(cfg, wdt, seed=21))
     max_ctx = 192
-    cm = checker.model(cfg, max_ctx, wdt).load(wl)
+    cm = checker.model(cfg, max_ctx if wdt != F16 else 2 * max_ctx, wdt).load(wl)     # FP16 P rows: 2 n <= max_ctx
     e = capi.Engine(cfg, max_ctx, wdt).load(wl)
     for k, v in opts.items():
         e.set_option(k, v)
@@ -103,7 +104,7 @@ def _mini_case(capi, checker, wdt, n_prompt, opts):
             for row in rows:
                 err = rel(e.pf_acv(layer, aid, row), cm.acv(layer, aid, row))
                 worst[(layer, name)] = max(worst.get((layer, name), 0.0), err)
-    wn = {Q8: "q8", Q4: "q4"}[wdt]
+    wn = {Q8: "q8", Q4: "q4", F16: "f16"}[wdt]
     sens_acv = SENS[f"mini_{wn}_{n_prompt}_acv"].max(axis=1)          # the reference's own spread, worst activation per layer
     sens_logits = float(SENS[f"mini_{wn}_{n_prompt}_logits"])
     ours = [max(v for (l, _), v in worst.items() if l == layer) for layer in range(cfg.n_layers)]
@@ -115,8 +116,8 @@ def _mini_case(capi, checker, wdt, n_prompt, opts):
     # whether an early layer already shows a flipped code is luck (T=7: the two reference builds agree to 1e-3 in layer 0,
     # to 2e-2 one layer later), so every layer is held to the reference's worst layer
     for layer in range(cfg.n_layers):
-        assert ours[layer] <= SLACK * sens_acv.max() + ABS, (layer, ours[layer], sens_acv)
-    LOGIT_REL = SLACK * sens_logits + ABS
+        assert ours[layer] <= SLACK * sens_acv.max() + min(ABS, 0.5 * sens_acv.max()), (layer, ours[layer], sens_acv)
+    LOGIT_REL = SLACK * sens_logits + min(ABS, 0.5 * sens_logits)
     assert lerr <= LOGIT_REL, (lerr, sens_logits)
     # the next row through the ORDER-EXACT kernels, on top of the K/V cache the batched path wrote
     nxt = int(np.argmax(want_logits))
@@ -201,13 +202,9 @@ def test_fused_epilogues_equal_unfused_kernels(capi):
     assert np.array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32))
 
 
-def test_batched_prefill_rejects_f16_models(capi):
-    from oracle import F16
-    cfg = W.mini_config(n_layers=1, n_vocab=64)
-    e = capi.Engine(cfg, 64, F16).load(W.synth_weights(cfg, F16, seed=2))
-    with pytest.raises(capi.GtbError, match="Q8-activation"):
-        e.prefill_fast(np.zeros(4, np.int32))
-    e.close()
+def test_batched_prefill_f16_two_sweep_attention(capi, checker):
+    """FP16 activations: the two-sweep attention rounds p = e / sum to fp16 like ops.h:996 does; same bound."""
+    _mini_case(capi, checker, F16, 64, {"pf_attn2": 1})
 
 
 def test_batched_prefill_full_size_q8_2048_vs_golden(capi):

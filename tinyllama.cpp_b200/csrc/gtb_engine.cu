@@ -819,8 +819,6 @@ int gtb_engine_prefill_fast(gtb_engine_t e, const int32_t* h_tokens, int n_token
     GTB_CHECK_INIT();
     GTB_ARG(e && h_tokens && n_tokens > 0 && n_tokens < e->cfg.max_ctx);
     const gtb_model_config& c = e->cfg;
-    if (c.wdtype != GTB_Q8 && c.wdtype != GTB_Q4)
-        return fail(GTB_ERR_STATE, "batched prefill is built for Q8-activation models (Q8, Q4 weights); use gtb_engine_prefill");
     int r = check_loaded(e);
     if (r) return r;
     const int E = c.n_embd, F = c.n_ffn, KV = e->kv_dim;
@@ -861,7 +859,7 @@ int gtb_engine_prefill_fast(gtb_engine_t e, const int32_t* h_tokens, int n_token
     if (r) return r;
     r = set_state(e, n_tokens - 1, n_tokens);
     if (r) return r;
-    r = (c.wdtype == GTB_Q8) ? pf_head<DT_Q8>(e) : pf_head<DT_Q4>(e);
+    r = (c.wdtype == GTB_Q8) ? pf_head<DT_Q8>(e) : (c.wdtype == GTB_Q4) ? pf_head<DT_Q4>(e) : pf_head<DT_F16>(e);
     if (r) return r;
     e->host_pos = n_tokens;
     return GTB_OK;

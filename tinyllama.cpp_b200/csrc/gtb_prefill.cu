@@ -11,7 +11,7 @@
 // causal GQA attention (ops.h:930-1133) is a two-pass tensor-core kernel that reproduces the Q8 re-encode of the
 // probability rows.  K and V land in the engine's cache layout so that decode continues from position T.
 //
-// fp16 operands are the dequantised Q8/Q4 values rounded to fp16 (relative error <= 2^-12 per element) and the
+// fp16 operands are the dequantised Q8/Q4 values rounded to fp16 (relative error <= 2^-12 per element; FP16 models: exact) and the
 // summation order of a dot differs from ops.h:224-391, so this path is tolerance-checked, not bit-checked.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -163,6 +163,20 @@ __device__ __forceinline__ void load_deq32(const int8_t* q, const uint16_t* s, s
 #pragma unroll
     for (int i = 0; i < 32; i++) v[i] = __fmul_rn((float)c[i], d);
 }
+__device__ __forceinline__ void load_half32(const __half* src, float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint4 w4 = reinterpret_cast<const uint4*>(src)[i];
+        const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+            v[8 * i + 2 * j] = f.x; v[8 * i + 2 * j + 1] = f.y;
+        }
+    }
+}
+// block b of row `row` of an activation matrix: Q8 planar (codes + scales) or fp16 [T][D] stored in the same buffer
+__device__ __forceinline__ void load_act32(int at, const int8_t* q, const uint16_t* s, size_t row, int D, int b, float (&v)[32]);
 __device__ __forceinline__ void store_half32(__half* dst, const float (&v)[32]) {
     uint32_t w[16];
 #pragma unroll
@@ -172,6 +186,10 @@ __device__ __forceinline__ void store_half32(__half* dst, const float (&v)[32]) 
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) reinterpret_cast<uint4*>(dst)[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+}
+__device__ __forceinline__ void load_act32(int at, const int8_t* q, const uint16_t* s, size_t row, int D, int b, float (&v)[32]) {
+    if (at == DT_F16) load_half32(reinterpret_cast<const __half*>(q) + row * D + (size_t)b * 32, v);
+    else load_deq32(q, s, row, D, b, v);
 }
 __device__ __forceinline__ void store_f32x32(float* dst, const float (&v)[32]) {
 #pragma unroll
@@ -192,6 +210,7 @@ struct PfEpi {
     // EPI_SILU (gate|up projection, rows interleaved in groups of 32)
     __half* act16 = nullptr; int F = 0;
     float *cap0 = nullptr, *cap1 = nullptr, *cap2 = nullptr; int capw = 0;
+    int at = DT_Q8;                  // activation dtype of the model: DT_Q8 (Q8/Q4 weights) or DT_F16 (tinyllama.cpp:258-265)
     int dbg_same_tile = 0;           // experiment: every TMA load fetches tile (0,0) (L2-resident operands, same shared-memory/MMA work)
 };
 
@@ -203,7 +222,12 @@ __device__ __forceinline__ float pf_silu(float x) { return __fdividef(x, 1.0f + 
 // ops.h:40-96; quants.h:52-66).  Rounding is to nearest via the 1.5 * 2^23 magic number: the code sits in the low byte of
 // the biased sum.  This differs from the reference's roundf (half away from zero) only when x * scale lands exactly on
 // k + 0.5; the bit-exact path (gtb_dev.cuh) keeps roundf.
-__device__ __forceinline__ uint16_t pf_roundtrip32(float (&x)[32], uint32_t (&q)[32]) {
+__device__ __forceinline__ uint16_t pf_roundtrip32(float (&x)[32], uint32_t (&q)[32], int at = DT_Q8) {
+    if (at == DT_F16) {                 // FP16 activations: every element is rounded to fp16 on its own (ops.h:83-90)
+#pragma unroll
+        for (int i = 0; i < 32; i++) x[i] = f16_roundtrip(x[i]);
+        return 0;
+    }
     float amax = 0.0f;
 #pragma unroll
     for (int i = 0; i < 32; i++) amax = fmaxf(amax, fabsf(x[i]));
@@ -240,10 +264,11 @@ __device__ __forceinline__ void pf_rope_store(const PfEpi& ep, int row, int slot
                 x1[4 * k + j] = __fadd_rn(__fmul_rn(a, s[j]), __fmul_rn(b, c[j]));
             }
         }
-        dh0 = pf_roundtrip32(x0, q0);
-        dh1 = pf_roundtrip32(x1, q1);
+        dh0 = pf_roundtrip32(x0, q0, ep.at);
+        dh1 = pf_roundtrip32(x1, q1, ep.at);
     }
     const int capw = ep.capw;
+    const bool f16 = ep.at == DT_F16;
     if (slot < nh) {
         store_half32(ep.q16 + (size_t)row * E + slot * 64, x0);
         store_half32(ep.q16 + (size_t)row * E + slot * 64 + 32, x1);
@@ -252,19 +277,29 @@ __device__ __forceinline__ void pf_rope_store(const PfEpi& ep, int row, int slot
         const int g = slot - nh;
         store_half32(ep.k16 + (size_t)row * KV + g * 64, x0);
         store_half32(ep.k16 + (size_t)row * KV + g * 64 + 32, x1);
-        store_codes32_perm(ep.kq + (size_t)row * KV + g * 64, q0);
-        store_codes32_perm(ep.kq + (size_t)row * KV + g * 64 + 32, q1);
-        ep.ks[(size_t)row * (KV / 32) + g * 2] = dh0;
-        ep.ks[(size_t)row * (KV / 32) + g * 2 + 1] = dh1;
+        if (f16) {                                  // FP16 cache: halves in natural order
+            store_half32(reinterpret_cast<__half*>(ep.kq) + (size_t)row * KV + g * 64, x0);
+            store_half32(reinterpret_cast<__half*>(ep.kq) + (size_t)row * KV + g * 64 + 32, x1);
+        } else {
+            store_codes32_perm(ep.kq + (size_t)row * KV + g * 64, q0);
+            store_codes32_perm(ep.kq + (size_t)row * KV + g * 64 + 32, q1);
+            ep.ks[(size_t)row * (KV / 32) + g * 2] = dh0;
+            ep.ks[(size_t)row * (KV / 32) + g * 2 + 1] = dh1;
+        }
         if (ep.cap1) for (int i = 0; i < 32; i++) { ep.cap1[(size_t)row * capw + g * 64 + i] = x0[i]; ep.cap1[(size_t)row * capw + g * 64 + 32 + i] = x1[i]; }
     } else {
         const int g = slot - nh - ng;
         store_half32(ep.v16 + (size_t)row * KV + g * 64, x0);
         store_half32(ep.v16 + (size_t)row * KV + g * 64 + 32, x1);
-        store_codes32(reinterpret_cast<int8_t*>(ep.vq) + (size_t)row * KV + g * 64, q0);
-        store_codes32(reinterpret_cast<int8_t*>(ep.vq) + (size_t)row * KV + g * 64 + 32, q1);
-        ep.vs[(size_t)row * (KV / 32) + g * 2] = dh0;
-        ep.vs[(size_t)row * (KV / 32) + g * 2 + 1] = dh1;
+        if (f16) {
+            store_half32(reinterpret_cast<__half*>(ep.vq) + (size_t)row * KV + g * 64, x0);
+            store_half32(reinterpret_cast<__half*>(ep.vq) + (size_t)row * KV + g * 64 + 32, x1);
+        } else {
+            store_codes32(reinterpret_cast<int8_t*>(ep.vq) + (size_t)row * KV + g * 64, q0);
+            store_codes32(reinterpret_cast<int8_t*>(ep.vq) + (size_t)row * KV + g * 64 + 32, q1);
+            ep.vs[(size_t)row * (KV / 32) + g * 2] = dh0;
+            ep.vs[(size_t)row * (KV / 32) + g * 2 + 1] = dh1;
+        }
         if (ep.cap2) for (int i = 0; i < 32; i++) { ep.cap2[(size_t)row * capw + g * 64 + i] = x0[i]; ep.cap2[(size_t)row * capw + g * 64 + 32 + i] = x1[i]; }
     }
 }
@@ -275,10 +310,10 @@ __device__ __forceinline__ void pf_silu_store(const PfEpi& ep, int row, int b, f
 #pragma unroll
     for (int k = 0; k < 32; k++) g[k] = pf_silu(g[k]);
     uint32_t q[32];
-    pf_roundtrip32(g, q);
+    pf_roundtrip32(g, q, ep.at);
 #pragma unroll
     for (int k = 0; k < 32; k++) g[k] = __fmul_rn(g[k], u[k]);
-    pf_roundtrip32(g, q);
+    pf_roundtrip32(g, q, ep.at);
     store_half32(ep.act16 + (size_t)row * ep.F + (size_t)b * 32, g);
     if (ep.cap0) for (int k = 0; k < 32; k++) { ep.cap0[(size_t)row * ep.capw + b * 32 + k] = g[k]; ep.cap1[(size_t)row * ep.capw + b * 32 + k] = u[k]; }
 }
@@ -322,9 +357,13 @@ __device__ __forceinline__ void pf_epilogue(const PfEpi& ep, uint32_t tacc, int 
                     store_f32x32(reinterpret_cast<float*>(ep.out0) + (size_t)row * N + col, v);
                 } else {
                     uint32_t q[32];
-                    const uint16_t dh = pf_roundtrip32(v, q);     // write_row_from_float, ops.h:645-646
-                    store_codes32(reinterpret_cast<int8_t*>(ep.out0) + (size_t)row * N + col, q);
-                    reinterpret_cast<uint16_t*>(ep.out1)[(size_t)row * (N / 32) + (col >> 5)] = dh;
+                    const uint16_t dh = pf_roundtrip32(v, q, ep.at);     // write_row_from_float, ops.h:645-646
+                    if (ep.at == DT_F16) {
+                        store_half32(reinterpret_cast<__half*>(ep.out0) + (size_t)row * N + col, v);
+                    } else {
+                        store_codes32(reinterpret_cast<int8_t*>(ep.out0) + (size_t)row * N + col, q);
+                        reinterpret_cast<uint16_t*>(ep.out1)[(size_t)row * (N / 32) + (col >> 5)] = dh;
+                    }
                 }
             }
         }
@@ -338,7 +377,7 @@ __device__ __forceinline__ void pf_epilogue(const PfEpi& ep, uint32_t tacc, int 
             tmem_ld32(tacc + (uint32_t)(c2 * 64 + 32), b);
             if (row_ok && col < N) {
                 uint32_t q0[32], q1[32];
-                const uint16_t dh0 = pf_roundtrip32(a, q0), dh1 = pf_roundtrip32(b, q1);   // the Linear's own re-encode
+                const uint16_t dh0 = pf_roundtrip32(a, q0, ep.at), dh1 = pf_roundtrip32(b, q1, ep.at);   // the Linear's own re-encode
                 if (EPI == EPI_ROPE) pf_rope_store(ep, row, col >> 6, a, b, q0, q1, dh0, dh1);
                 else pf_silu_store(ep, row, col >> 6, a, b);
             }
@@ -612,6 +651,25 @@ __global__ void k_pf_w16(const void* __restrict__ data, const uint16_t* __restri
     store_half32(out + o * 32, v);
 }
 
+// FP16 weights: lane-major device layout (gtb_internal.h) -> row-major [rows][cols]; one thread per 8 consecutive elements
+__global__ void k_pf_w16_f16(const __half* __restrict__ data, size_t ngroups, __half* __restrict__ out, int cols, int interleave_half) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;          // (row, chunk c, i8): elements 64c + 8*i8 .. +7
+    if (i >= ngroups) return;
+    const int gpr = cols / 8;
+    const size_t row = i / gpr;
+    const int gi = (int)(i % gpr), c = gi >> 3, i8 = gi & 7;
+    const __half* src = data + (row * (cols / 64) + c) * 64;
+    __half v[8];
+#pragma unroll
+    for (int l = 0; l < 8; l++) v[l] = src[l * 8 + i8];
+    size_t orow = row;
+    if (interleave_half > 0) {
+        const size_t r = row % interleave_half, up = row / interleave_half;
+        orow = (r / 32) * 64 + up * 32 + (r % 32);
+    }
+    *reinterpret_cast<uint4*>(out + orow * cols + 64 * c + 8 * i8) = *reinterpret_cast<const uint4*>(v);
+}
+
 // token_embed (ops.h:514-564): Q8 rows are copied, Q4 rows are dequantised and re-encoded as Q8
 __global__ void k_pf_embed(const void* __restrict__ wdata, const uint16_t* __restrict__ wsc, int wdtype, const int32_t* __restrict__ tokens,
                            int T, int D, int8_t* __restrict__ xq, uint16_t* __restrict__ xs, float* cap, int capw) {
@@ -620,6 +678,18 @@ __global__ void k_pf_embed(const void* __restrict__ wdata, const uint16_t* __res
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)T * nb) return;
     const int row = (int)(i / nb), b = (int)(i % nb);
+    if (wdtype == DT_F16) {                                  // memcpy of the fp16 row (ops.h:535-540), un-permuted from the lane-major layout
+        const __half* src = reinterpret_cast<const __half*>(wdata) + ((size_t)tokens[row] * (D / 64) + (b >> 1)) * 64;
+        float v[32];
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+            const int r = (b & 1) * 32 + e;
+            v[e] = __half2float(src[(r & 7) * 8 + (r >> 3)]);
+        }
+        store_half32(reinterpret_cast<__half*>(xq) + (size_t)row * D + (size_t)b * 32, v);
+        if (cap) for (int e = 0; e < 32; e++) cap[(size_t)row * capw + b * 32 + e] = v[e];
+        return;
+    }
     const size_t blk = (size_t)tokens[row] * nb + b;
     const float d = h2f(wsc[blk]);
     int q[32];
@@ -664,7 +734,7 @@ __global__ void k_pf_embed(const void* __restrict__ wdata, const uint16_t* __res
 // is three orders of magnitude below the fp16 operand rounding of the GEMMs of this path.
 __global__ void __launch_bounds__(64) k_pf_add_norm(int8_t* __restrict__ xq, uint16_t* __restrict__ xs, const int8_t* __restrict__ yq,
                                                      const uint16_t* __restrict__ ys, const uint16_t* __restrict__ normw,
-                                                     __half* __restrict__ xn16, int T, int D, float* cap_y, float* cap_x, float* cap_n, int capw) {
+                                                     __half* __restrict__ xn16, int T, int D, float* cap_y, float* cap_x, float* cap_n, int capw, int at) {
     pdl_trigger_and_wait();
     __shared__ float red[2];
     const int row = blockIdx.x, tid = threadIdx.x;
@@ -673,17 +743,21 @@ __global__ void __launch_bounds__(64) k_pf_add_norm(int8_t* __restrict__ xq, uin
     float ssq = 0.0f;
     float v[32];
     for (int b = tid; b < nb; b += 64) {
-        load_deq32(xq, xs, row, D, b, v);
+        load_act32(at, xq, xs, row, D, b, v);
         if (yq) {
             float y[32];
-            load_deq32(yq, ys, row, D, b, y);
+            load_act32(at, yq, ys, row, D, b, y);
             if (cap_y) for (int i = 0; i < 32; i++) cap_y[(size_t)row * capw + b * 32 + i] = y[i];
 #pragma unroll
             for (int i = 0; i < 32; i++) v[i] = __fadd_rn(v[i], y[i]);
             uint32_t q[32];
-            const uint16_t dh = pf_roundtrip32(v, q);
-            store_codes32(xq + (size_t)row * D + (size_t)b * 32, q);
-            xs[(size_t)row * nb + b] = dh;
+            const uint16_t dh = pf_roundtrip32(v, q, at);
+            if (at == DT_F16) {
+                store_half32(reinterpret_cast<__half*>(xq) + (size_t)row * D + (size_t)b * 32, v);
+            } else {
+                store_codes32(xq + (size_t)row * D + (size_t)b * 32, q);
+                xs[(size_t)row * nb + b] = dh;
+            }
         }
         if (cap_x) for (int i = 0; i < 32; i++) cap_x[(size_t)row * capw + b * 32 + i] = v[i];
 #pragma unroll
@@ -697,7 +771,7 @@ __global__ void __launch_bounds__(64) k_pf_add_norm(int8_t* __restrict__ xq, uin
     const float rms = sqrtf(__fdiv_rn(ssq, (float)D));
     const float denom = __fadd_rn(rms, 1e-6f);
     for (int b = tid; b < nb; b += 64) {
-        if (!single) load_deq32(xq, xs, row, D, b, v);
+        if (!single) load_act32(at, xq, xs, row, D, b, v);
         const uint4* wp = reinterpret_cast<const uint4*>(normw + b * 32);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -710,7 +784,7 @@ __global__ void __launch_bounds__(64) k_pf_add_norm(int8_t* __restrict__ xq, uin
             }
         }
         uint32_t q[32];
-        pf_roundtrip32(v, q);
+        pf_roundtrip32(v, q, at);
         if (cap_n) for (int i = 0; i < 32; i++) cap_n[(size_t)row * capw + b * 32 + i] = v[i];
         store_half32(xn16 + (size_t)row * D + (size_t)b * 32, v);
     }
@@ -749,16 +823,18 @@ __global__ void __launch_bounds__(128) k_pf_silu_mul(const int8_t* __restrict__ 
 
 // dequantised fp32 copies of row `row` for the exact final-norm + lm_head phase of the engine
 __global__ void k_pf_tail(const int8_t* __restrict__ xq, const uint16_t* __restrict__ xs, const int8_t* __restrict__ dq, const uint16_t* __restrict__ ds,
-                          int row, int D, float* __restrict__ res, float* __restrict__ down, float* cap_down, int T, int capw) {
+                          int row, int D, float* __restrict__ res, float* __restrict__ down, float* cap_down, int T, int capw, int at) {
     pdl_trigger_and_wait();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= D) return;
-    const size_t o = (size_t)row * D + e, so = (size_t)row * (D / 32) + (e >> 5);
-    res[e] = __fmul_rn((float)xq[o], h2f(xs[so]));
-    down[e] = __fmul_rn((float)dq[o], h2f(ds[so]));
+    auto val = [&](const int8_t* q, const uint16_t* sc, int r) -> float {
+        if (at == DT_F16) return __half2float(reinterpret_cast<const __half*>(q)[(size_t)r * D + e]);
+        return __fmul_rn((float)q[(size_t)r * D + e], h2f(sc[(size_t)r * (D / 32) + (e >> 5)]));
+    };
+    res[e] = val(xq, xs, row);
+    down[e] = val(dq, ds, row);
     if (cap_down)
-        for (int r = 0; r < T; r++)
-            cap_down[(size_t)r * capw + e] = __fmul_rn((float)dq[(size_t)r * D + e], h2f(ds[(size_t)r * (D / 32) + (e >> 5)]));
+        for (int r = 0; r < T; r++) cap_down[(size_t)r * capw + e] = val(dq, ds, r);
 }
 
 // =================================================================================================== attention
@@ -857,7 +933,7 @@ __device__ __forceinline__ void pa_scores(float (&S)[8][4], const uint32_t (&qa)
 //                    (relative 2^-11 per block, averaging out over the blocks of a row -- the same size as the fp16 rounding
 //                    of the V operand).  QK^T and the exps run once instead of twice; the decoded probabilities
 //                    (code x scale) are the fp16 A operand of P.V, accumulated in one set of registers.
-template <bool TWO_PASS>
+template <bool TWO_PASS, int AT>
 __global__ void __launch_bounds__(128, TWO_PASS ? 3 : 4) k_pf_attn(const __half* __restrict__ q16, const __half* __restrict__ k16, const __half* __restrict__ v16,
                                                   __half* __restrict__ out16, int T, int n_heads, int gsz, float* cap, int capw) {
     pdl_trigger_and_wait();
@@ -952,6 +1028,32 @@ __global__ void __launch_bounds__(128, TWO_PASS ? 3 : 4) k_pf_attn(const __half*
             S[j][2] = ex2_approx(fmaf(S[j][2], PA_C, nc1)); S[j][3] = ex2_approx(fmaf(S[j][3], PA_C, nc1));
             if (!TWO_PASS) { l0 += S[j][0] + S[j][1]; l1 += S[j][2] + S[j][3]; }
         }
+        if (AT == DT_F16) {
+            // FP16 activations: every probability is rounded to fp16 on its own (ops.h:996 with an fp16 row): p itself is the
+            // A operand.  The single sweep rounds e = exp(s - running max) instead of e / sum.
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                uint32_t pa[4];
+                if (TWO_PASS) {
+                    pa[0] = pack_h2(__fdiv_rn(S[2 * kk][0], l0), __fdiv_rn(S[2 * kk][1], l0));
+                    pa[1] = pack_h2(__fdiv_rn(S[2 * kk][2], l1), __fdiv_rn(S[2 * kk][3], l1));
+                    pa[2] = pack_h2(__fdiv_rn(S[2 * kk + 1][0], l0), __fdiv_rn(S[2 * kk + 1][1], l0));
+                    pa[3] = pack_h2(__fdiv_rn(S[2 * kk + 1][2], l1), __fdiv_rn(S[2 * kk + 1][3], l1));
+                } else {
+                    pa[0] = pack_h2(S[2 * kk][0], S[2 * kk][1]);
+                    pa[1] = pack_h2(S[2 * kk][2], S[2 * kk][3]);
+                    pa[2] = pack_h2(S[2 * kk + 1][0], S[2 * kk + 1][1]);
+                    pa[3] = pack_h2(S[2 * kk + 1][2], S[2 * kk + 1][3]);
+                }
+#pragma unroll
+                for (int jp = 0; jp < 4; jp++) {
+                    uint32_t b0, b1, b2, b3;
+                    ldsm_x4_t(vs_addr(cur) + (uint32_t)(((16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8) * PA_LD + 16 * jp + (lane >> 4) * 8) * 2), b0, b1, b2, b3);
+                    mma_16816(O[2 * jp], pa, b0, b1);
+                    mma_16816(O[2 * jp + 1], pa, b2, b3);
+                }
+            }
+        } else
 #pragma unroll
         for (int bb = 0; bb < 2; bb++) {                              // one Q8 block = 32 keys = 4 octets (ops.h:996)
             float a0 = 0.0f, a1 = 0.0f;
@@ -1022,8 +1124,23 @@ __global__ void __launch_bounds__(128, TWO_PASS ? 3 : 4) k_pf_attn(const __half*
         for (int j = 0; j < 8; j++) { O[j][0] *= i0; O[j][1] *= i0; O[j][2] *= i1; O[j][3] *= i1; }
     }
 
-    // ---- output row: Q8 re-encode per 32 channels (ops.h:1084), fp16 operand of the o-projection
+    // ---- output row: re-encode (ops.h:1084), fp16 operand of the o-projection
     const int r0 = qrow0 + g, r1 = r0 + 8;
+    if (AT == DT_F16) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int col = h * 64 + 8 * j + 2 * t;
+            if (r0 < T) {
+                *reinterpret_cast<uint32_t*>(out16 + (size_t)r0 * E + col) = pack_h2(O[j][0], O[j][1]);
+                if (cap) { cap[(size_t)r0 * capw + col] = f16_roundtrip(O[j][0]); cap[(size_t)r0 * capw + col + 1] = f16_roundtrip(O[j][1]); }
+            }
+            if (r1 < T) {
+                *reinterpret_cast<uint32_t*>(out16 + (size_t)r1 * E + col) = pack_h2(O[j][2], O[j][3]);
+                if (cap) { cap[(size_t)r1 * capw + col] = f16_roundtrip(O[j][2]); cap[(size_t)r1 * capw + col + 1] = f16_roundtrip(O[j][3]); }
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int cb = 0; cb < 2; cb++) {
         float a0 = 0.0f, a1 = 0.0f;
@@ -1184,7 +1301,7 @@ static int pf_alloc(PfPlan* p, void** ptr, size_t n) {
 }
 
 int pf_create(PfPlan** out, const gtb_model_config& cfg) {
-    GTB_ARG(cfg.wdtype == GTB_Q8 || cfg.wdtype == GTB_Q4);
+    GTB_ARG(cfg.wdtype == GTB_Q8 || cfg.wdtype == GTB_Q4 || cfg.wdtype == GTB_F16);
     auto* p = new PfPlan();
     p->cfg = cfg;
     p->E = cfg.n_embd; p->F = cfg.n_ffn; p->KV = 64 * cfg.n_groups; p->NQKV = p->E + 2 * p->KV;
@@ -1192,9 +1309,10 @@ int pf_create(PfPlan** out, const gtb_model_config& cfg) {
     p->L.resize(cfg.n_layers);
     const size_t T = (size_t)p->Tcap;
     int r = 0;
-    r |= pf_alloc(p, (void**)&p->xq, T * p->E); r |= pf_alloc(p, (void**)&p->xs, T * (p->E / 32) * 2);
+    const size_t eb = (cfg.wdtype == GTB_F16) ? 2 : 1;         // bytes per element of the residual-stream / o / down matrices
+    r |= pf_alloc(p, (void**)&p->xq, T * p->E * eb); r |= pf_alloc(p, (void**)&p->xs, T * (p->E / 32) * 2);
     r |= pf_alloc(p, (void**)&p->qkvq, T * p->NQKV); r |= pf_alloc(p, (void**)&p->qkvs, T * (p->NQKV / 32) * 2);
-    r |= pf_alloc(p, (void**)&p->oq, T * p->E); r |= pf_alloc(p, (void**)&p->os, T * (p->E / 32) * 2);
+    r |= pf_alloc(p, (void**)&p->oq, T * p->E * eb); r |= pf_alloc(p, (void**)&p->os, T * (p->E / 32) * 2);
     r |= pf_alloc(p, (void**)&p->guq, T * 2 * p->F); r |= pf_alloc(p, (void**)&p->gus, T * (2 * p->F / 32) * 2);
     r |= pf_alloc(p, (void**)&p->xn16, T * p->E * 2); r |= pf_alloc(p, (void**)&p->q16, T * p->E * 2);
     r |= pf_alloc(p, (void**)&p->k16, T * p->KV * 2); r |= pf_alloc(p, (void**)&p->v16, T * p->KV * 2);
@@ -1218,14 +1336,19 @@ void pf_destroy(PfPlan* p) {
 }
 
 int pf_set_weight(PfPlan* p, int layer, int which, int wdtype, const void* d_data, const uint16_t* d_scales, int rows, int cols) {
-    GTB_ARG(p && layer >= 0 && layer < (int)p->L.size() && which >= 0 && which < 4 && (wdtype == GTB_Q8 || wdtype == GTB_Q4));
+    GTB_ARG(p && layer >= 0 && layer < (int)p->L.size() && which >= 0 && which < 4 && (wdtype == GTB_Q8 || wdtype == GTB_Q4 || wdtype == GTB_F16));
     const int N[4] = {p->NQKV, p->E, 2 * p->F, p->E}, K[4] = {p->E, p->E, p->E, p->F};
     GTB_ARG(rows == N[which] && cols == K[which]);
     PfLayerW& l = p->L[layer];
     const size_t n = (size_t)rows * cols;
     if (!l.w[which]) { int r = pf_alloc(p, (void**)&l.w[which], n * 2); if (r) return r; }
     const size_t nblk = n / 32;
-    k_pf_w16<<<(unsigned)((nblk + 255) / 256), 256, 0, ctx().stream>>>(d_data, d_scales, wdtype, nblk, l.w[which], cols / 32, which == 2 ? p->F : 0);
+    if (wdtype == GTB_F16) {
+        const size_t ng8 = n / 8;
+        k_pf_w16_f16<<<(unsigned)((ng8 + 255) / 256), 256, 0, ctx().stream>>>(reinterpret_cast<const __half*>(d_data), ng8, l.w[which], cols, which == 2 ? p->F : 0);
+    } else {
+        k_pf_w16<<<(unsigned)((nblk + 255) / 256), 256, 0, ctx().stream>>>(d_data, d_scales, wdtype, nblk, l.w[which], cols / 32, which == 2 ? p->F : 0);
+    }
     GTB_LAUNCHED();
     int r = make_tmap(&l.tm[which][0], l.w[which], rows, cols, 128);
     if (!r) r = make_tmap(&l.tm[which][1], l.w[which], rows, cols, 256);
@@ -1258,6 +1381,8 @@ int pf_run(PfPlan* p, const PfRun& r) {
     cudaStream_t st = ctx().stream;
     const int T = r.T, E = p->E, F = p->F, NQKV = p->NQKV;
     const int nh = p->cfg.n_heads, ng = p->cfg.n_groups, nl = p->cfg.n_layers;
+    const int at = (p->cfg.wdtype == GTB_F16) ? DT_F16 : DT_Q8;
+    const bool fused = p->fused || at == DT_F16;          // FP16 activations only have the fused epilogues
     const int64_t l0 = ctx().launches;
     CUtensorMap ta_xn, ta_attn, ta_act;
     const int Tm = T < PF_BM ? PF_BM : T;
@@ -1278,18 +1403,19 @@ int pf_run(PfPlan* p, const PfRun& r) {
         GTB_LAUNCHED();
     }
     GTB_CUDA(pf_launch(k_pf_add_norm, dim3(T), dim3(64), 0, p->xq, p->xs, nullptr, nullptr, r.layers[0].attn_norm, p->xn16, T, E, nullptr, nullptr,
-                                            capp(0, GTB_A_ATTN_NORM), r.capw));
+                                            capp(0, GTB_A_ATTN_NORM), r.capw, at));
     GTB_LAUNCHED();
     const int bn_qkv = pick_bn(T, NQKV), bn_o = pick_bn(T, E), bn_gu = pick_bn(T, 2 * F), bn_d = pick_bn(T, E);
     for (int li = 0; li < r.n_layers_run; li++) {
         const PfLayerIO& io = r.layers[li];
         PfLayerW& w = p->L[li];
         PfEpi eq;                                   // q|k|v: Linear re-encode, RoPE, K/V append
+        eq.at = at;
         eq.out0 = p->qkvq; eq.out1 = p->qkvs;
         eq.rope_cos = r.rope_cos; eq.rope_sin = r.rope_sin; eq.q16 = p->q16; eq.k16 = p->k16; eq.v16 = p->v16;
         eq.kq = io.kq; eq.ks = io.ks; eq.vq = io.vq; eq.vs = io.vs; eq.nh = nh; eq.ng = ng;
         eq.cap0 = capp(li, GTB_A_Q); eq.cap1 = capp(li, GTB_A_K); eq.cap2 = capp(li, GTB_A_V); eq.capw = r.capw;
-        if (p->fused) {
+        if (fused) {
             rc = gemm_any<EPI_ROPE>(p->two_cta, ta_xn, w.tm[0], bn_qkv, T, NQKV, E, eq);
             if (rc) return rc;
         } else {
@@ -1299,20 +1425,31 @@ int pf_run(PfPlan* p, const PfRun& r) {
             GTB_CUDA(pf_launch(k_pf_rope_kv, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, p->qkvq, p->qkvs, T, eq));
             GTB_LAUNCHED();
         }
-        if (p->attn_two_pass) GTB_CUDA(pf_launch(k_pf_attn<true>, dim3((unsigned)(((T + 63) / 64) * nh)), dim3(128), 0, p->q16, p->k16, p->v16, p->attn16, T, nh, nh / ng, capp(li, GTB_A_ATTN_OUT), r.capw));
-        else GTB_CUDA(pf_launch(k_pf_attn<false>, dim3((unsigned)(((T + 63) / 64) * nh)), dim3(128), 0, p->q16, p->k16, p->v16, p->attn16, T, nh, nh / ng, capp(li, GTB_A_ATTN_OUT), r.capw));
+        {
+            const dim3 ag((unsigned)(((T + 63) / 64) * nh));
+            float* ac = capp(li, GTB_A_ATTN_OUT);
+            if (at == DT_F16) {
+                if (p->attn_two_pass) GTB_CUDA(pf_launch(k_pf_attn<true, DT_F16>, ag, dim3(128), 0, p->q16, p->k16, p->v16, p->attn16, T, nh, nh / ng, ac, r.capw));
+                else GTB_CUDA(pf_launch(k_pf_attn<false, DT_F16>, ag, dim3(128), 0, p->q16, p->k16, p->v16, p->attn16, T, nh, nh / ng, ac, r.capw));
+            } else {
+                if (p->attn_two_pass) GTB_CUDA(pf_launch(k_pf_attn<true, DT_Q8>, ag, dim3(128), 0, p->q16, p->k16, p->v16, p->attn16, T, nh, nh / ng, ac, r.capw));
+                else GTB_CUDA(pf_launch(k_pf_attn<false, DT_Q8>, ag, dim3(128), 0, p->q16, p->k16, p->v16, p->attn16, T, nh, nh / ng, ac, r.capw));
+            }
+        }
         GTB_LAUNCHED();
         PfEpi eo;
+        eo.at = at;
         eo.out0 = p->oq; eo.out1 = p->os;
         rc = gemm_any<EPI_Q8>(p->two_cta, ta_attn, w.tm[1], bn_o, T, E, E, eo);
         if (rc) return rc;
         GTB_CUDA(pf_launch(k_pf_add_norm, dim3(T), dim3(64), 0, p->xq, p->xs, p->oq, p->os, io.ffn_norm, p->xn16, T, E, capp(li, GTB_A_O), capp(li, GTB_A_INP_RES),
-                                        capp(li, GTB_A_FFN_NORM), r.capw));
+                                        capp(li, GTB_A_FFN_NORM), r.capw, at));
         GTB_LAUNCHED();
         PfEpi eg;                                   // gate|up: Linear re-encode, SiLU, Multiply
+        eg.at = at;
         eg.out0 = p->guq; eg.out1 = p->gus; eg.act16 = p->act16; eg.F = F;
         eg.cap0 = capp(li, GTB_A_GATE); eg.cap1 = capp(li, GTB_A_UP); eg.capw = r.capw;
-        if (p->fused) {
+        if (fused) {
             rc = gemm_any<EPI_SILU>(p->two_cta, ta_xn, w.tm[2], bn_gu, T, 2 * F, E, eg);
             if (rc) return rc;
         } else {
@@ -1326,10 +1463,10 @@ int pf_run(PfPlan* p, const PfRun& r) {
         if (rc) return rc;
         if (li + 1 < r.n_layers_run) {
             GTB_CUDA(pf_launch(k_pf_add_norm, dim3(T), dim3(64), 0, p->xq, p->xs, p->oq, p->os, r.layers[li + 1].attn_norm, p->xn16, T, E, capp(li, GTB_A_DOWN),
-                                            capp(li, GTB_A_ATTN_RES), capp(li + 1, GTB_A_ATTN_NORM), r.capw));
+                                            capp(li, GTB_A_ATTN_RES), capp(li + 1, GTB_A_ATTN_NORM), r.capw, at));
             GTB_LAUNCHED();
         } else {
-            GTB_CUDA(pf_launch(k_pf_tail, dim3((E + 255) / 256), dim3(256), 0, p->xq, p->xs, p->oq, p->os, T - 1, E, r.last_res, r.last_down, capp(li, GTB_A_DOWN), T, r.capw));
+            GTB_CUDA(pf_launch(k_pf_tail, dim3((E + 255) / 256), dim3(256), 0, p->xq, p->xs, p->oq, p->os, T - 1, E, r.last_res, r.last_down, capp(li, GTB_A_DOWN), T, r.capw, at));
             GTB_LAUNCHED();
         }
     }

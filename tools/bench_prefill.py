@@ -32,7 +32,7 @@ def prefill_flops(cfg, T):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", choices=["q8", "q4"], default="q8")
+    ap.add_argument("--workload", choices=["q8", "q4", "f16"], default="q8")
     ap.add_argument("--tokens", type=int, default=2048)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
@@ -43,7 +43,7 @@ def main():
     import torch
     from tinyllama_cpp_b200 import capi
     capi.init(0)
-    wdt = {"q8": W.Q8, "q4": W.Q4}[args.workload]
+    wdt = {"q8": W.Q8, "q4": W.Q4, "f16": W.F16}[args.workload]
     cfg = W.TINYLLAMA if not args.layers else W.mini_config(n_layers=args.layers, n_vocab=32003)
     T = args.tokens
     eng = capi.Engine(cfg, T + 128, wdt).load(W.synth_weights(cfg, wdt, seed=1))
