@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- batch-1 greedy decode throughput of the tinyllama.cpp forward hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload q4|q8|f16|prefill_q8] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload q4|q8|f16|prefill_q8|q4_seq64] [--impl b200|reference]
 
 One "step" = one decoded token = one pass of the hot path (TinyLlama::logits for one new row + argmax).
 Default workload = BASELINE.json configs[2], the configuration north_star's target is quoted on:
@@ -268,12 +268,78 @@ def run_prefill(args):
     print(json.dumps(out), flush=True)
 
 
+def run_seq64(args):
+    """`--workload q4_seq64` = BASELINE.json configs[4]: 64 independent sequences (128-token prompt + K new tokens each, K = --steps,
+    at most 256) served by N replicas, sequence s on GPU s mod N, back to back at batch 1 (the reference has no batch dimension,
+    SURVEY.md 8e).  value = generated tokens of all sequences / the slowest replica's summed decode time (CUDA events around each
+    sequence's device-resident decode; the exact prefill of the prompt is outside the timed region)."""
+    import torch
+    from tinyllama_cpp_b200 import capi, replicas as R
+    env = R.ReplicaEnv.from_env()
+    rank, world, local = env.rank, env.world, env.local_rank
+    if world > 1:
+        torch.cuda.set_device(local)
+        R.init(env, "nccl", device_id=torch.device("cuda", local))
+    capi.init(local)
+    torch.cuda.set_device(local)
+    cfg = W.TINYLLAMA
+    n_seq, n_prompt = 64, 128
+    n_new = max(2, min(args.steps, 256))
+    eng = capi.Engine(cfg, n_prompt + n_new, W.Q4).load(W.synth_weights(cfg, W.Q4, seed=1))
+    stream = torch.cuda.ExternalStream(capi.stream_handle(), device=torch.device("cuda", local))
+    mine = R.sequences_of_rank(n_seq, rank, world)
+    eng.prefill(W.synth_prompt(1000, n_prompt, cfg.n_vocab))        # warm-up sequence (not counted)
+    eng.decode(max(args.warmup, 3))
+    capi.sync()
+    R.barrier(env)
+    ms_local, toks_local, checksum = 0.0, 0, 0
+    l0 = capi.launch_count()
+    t_wall = time.perf_counter()
+    with ClockSampler(local) as clk:
+        for sidx in mine:
+            eng.prefill(W.synth_prompt(100 + sidx, n_prompt, cfg.n_vocab))      # produces the first new token
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            eng.decode(n_new - 1)
+            ev1.record(stream)
+            capi.sync()
+            ms_local += ev0.elapsed_time(ev1)
+            toks_local += n_new - 1
+            checksum = (checksum * 31 + int(eng.read_tokens(n_prompt + n_new - 1, 1)[0])) % (1 << 31)
+    wall = time.perf_counter() - t_wall
+    launches = capi.launch_count() - l0
+    ms, units, (wall_max,), (launches,) = R.aggregate(env, ms_local, toks_local, extra_max=[wall], extra_sum=[launches], device=f"cuda:{local}")
+    if rank == 0:
+        hbm_peak, peak_src = measured_peaks()
+        t_mean = n_prompt + n_new / 2.0
+        bytes_per_tok = cfg.decode_bytes(W.Q4, int(round(t_mean)))
+        per_gpu_tok_s = (len(mine) * (n_new - 1)) / (ms_local * 1e-3) if ms_local else 0.0
+        achieved = bytes_per_tok * per_gpu_tok_s / 1e9
+        print(json.dumps({
+            "metric": "decode_tokens_per_s", "value": R.throughput(units, ms), "unit": "tokens/s", "n_gpus": world, "steps": n_new - 1,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / max(1, len(mine) * (n_new - 1)), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": DTYPE_STR[W.Q4], "data": "synthetic",
+            "config": {"workload": "TinyLlama-1.1B Q4 decode, 64 independent sequences as replicas (BASELINE.json configs[4]): 128-token prompt + "
+                                   f"{n_new} new tokens each, sequence s on GPU s mod N, batch 1 per GPU", "sequences": n_seq,
+                       "sequences_per_gpu": len(mine), "n_prompt": n_prompt, "n_new": n_new, "replicas": world,
+                       "l2": "inputs larger than L2: every step streams 582 MB of weights"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_step": bytes_per_tok, "kernel": "k_mega<q4>, one launch per sequence"},
+            "e2e": {"value": units / wall_max if wall_max else None, "unit": "tokens/s", "h2d_bytes_per_step": 4 * n_prompt / (n_new - 1),
+                    "d2h_bytes_per_step": 4.0 / (n_new - 1), "note": "wall clock of the whole job on the slowest replica, prompt upload and exact prefill included"},
+            "gpu_launches": int(launches), "clocks": clk.summary(), "token_checksum_rank0": checksum}), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=512)
     ap.add_argument("--warmup", type=int, default=16)
-    ap.add_argument("--workload", choices=list(WORKLOADS) + ["prefill_q8"], default="q4")
+    ap.add_argument("--workload", choices=list(WORKLOADS) + ["prefill_q8", "q4_seq64"], default="q4")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -282,6 +348,8 @@ def main():
     args.warmup = max(args.warmup, 3)
     if args.workload == "prefill_q8":
         return run_prefill(args)
+    if args.workload == "q4_seq64":
+        return run_seq64(args)
     wdt, cfg_idx, desc = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, wdt, desc)

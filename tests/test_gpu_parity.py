@@ -286,3 +286,20 @@ def test_gten_file_roundtrip(capi, checker, tmp_path):
     prompt = W.synth_prompt(1, 5, cfg.n_vocab)
     assert np.array_equal(e.generate(prompt, 6), cm.generate(prompt, 6)[0])
     e.close(); cm.close()
+
+
+def test_config5_sequence_sample_matches_reference(capi, checker):
+    """BASELINE.json configs[4] (64 independent Q4 sequences served as replicas): one of the job's sequences (the prompt
+    recipe of bench.py --workload q4_seq64, sequence 5) at full size, greedy tokens identical to the CPU reference."""
+    cfg = W.TINYLLAMA
+    wl = list(W.synth_weights(cfg, Q4, seed=1))
+    n_prompt, n_new = 128, 12
+    prompt = W.synth_prompt(100 + 5, n_prompt, cfg.n_vocab)
+    cm = checker.model(cfg, 160, Q4).load(wl)
+    want = cm.generate(prompt, n_new)[0]
+    e = capi.Engine(cfg, 160, Q4).load(wl)
+    e.prefill(prompt)
+    e.decode(n_new - 1)
+    got = e.read_tokens(0, n_prompt + n_new)
+    assert np.array_equal(got, want)
+    e.close(); cm.close()

@@ -48,6 +48,14 @@ def test_replica_aggregation_gloo_world2():
     assert R.throughput(512, 150.0) == pytest.approx(512 / 0.150)
 
 
+def test_sequence_partition_is_disjoint_and_complete():
+    for world in (1, 2, 4, 8, 3):
+        parts = [R.sequences_of_rank(64, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(64))
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1
+    assert R.sequences_of_rank(3, 5, 8) == []            # more GPUs than sequences: the extra replicas idle
+
+
 def test_single_replica_needs_no_process_group():
     env = R.ReplicaEnv(0, 1, 0)
     assert R.init(env) is None

@@ -23,6 +23,12 @@ def sequence_seed(base_seed: int, rank: int, index: int = 0, world: int = 1) -> 
     return base_seed + index * world + rank
 
 
+def sequences_of_rank(n_sequences: int, rank: int, world: int = 1):
+    """Indices of the job's sequences that replica `rank` serves (BASELINE.json configs[4]: 64 independent sequences over
+    1/2/4/8 GPUs): sequence s goes to GPU s mod N, so the shares differ by at most one."""
+    return list(range(rank, n_sequences, world))
+
+
 def init(env: ReplicaEnv, backend: str = "nccl", device_id=None):
     if env.world <= 1:
         return None
