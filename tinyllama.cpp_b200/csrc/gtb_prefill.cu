@@ -211,6 +211,7 @@ struct PfEpi {
     __half* act16 = nullptr; int F = 0;
     float *cap0 = nullptr, *cap1 = nullptr, *cap2 = nullptr; int capw = 0;
     int at = DT_Q8;                  // activation dtype of the model: DT_Q8 (Q8/Q4 weights) or DT_F16 (tinyllama.cpp:258-265)
+    long long* dbg_cycles = nullptr; // experiment: [cta][4] = {total, waiting for TMA data, waiting for a free accumulator, k-blocks} of the MMA thread
     int dbg_same_tile = 0;           // experiment: every TMA load fetches tile (0,0) (L2-resident operands, same shared-memory/MMA work)
 };
 
@@ -319,6 +320,11 @@ __device__ __forceinline__ void pf_silu_store(const PfEpi& ep, int row, int b, f
 }
 
 // =================================================================================================== GEMM (tcgen05)
+#ifdef GTB_PF_INSTRUMENT                // build with -DGTB_PF_INSTRUMENT to let GTB_PF_CYCLES=1 time the MMA thread (tools/gemm_probe.py)
+constexpr bool PF_INSTRUMENT = true;
+#else
+constexpr bool PF_INSTRUMENT = false;
+#endif
 constexpr int PF_BM = 128;          // rows of A (prompt positions) per tile = UMMA M
 constexpr int PF_BK = 64;           // fp16 elements per k-block = one 128-byte swizzle atom
 constexpr int PF_THREADS = 320;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
@@ -439,13 +445,20 @@ k_pf_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (lane == 0) {        // ---------------- MMA issuer
             uint32_t s = 0, ph = 0;
             int it = 0;
+            const bool dbg = PF_INSTRUMENT && ep.dbg_cycles != nullptr;
+            long long c_full = 0, c_acc = 0, c_n = 0;
+            const long long c_t0 = dbg ? clock64() : 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
                 const int as = it & 1;
+                long long c0 = dbg ? clock64() : 0;
                 mbar_wait(bar_tempty(as), ((it >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+                if (dbg) c_acc += clock64() - c0;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
                 for (int kb = 0; kb < nkb; kb++) {
+                    if (dbg) c0 = clock64();
                     mbar_wait(bar_full(s), ph);
+                    if (dbg) { c_full += clock64() - c0; c_n++; }
                     tc_fence_after();
                     const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
                     const uint32_t sb = sa + Cfg::A_BYTES;
@@ -456,6 +469,10 @@ k_pf_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     if (kb == nkb - 1) umma_commit(bar_tfull(as));  // accumulator complete
                     if (++s == ST) { s = 0; ph ^= 1; }
                 }
+            }
+            if (dbg) {
+                ep.dbg_cycles[blockIdx.x * 4 + 0] = clock64() - c_t0; ep.dbg_cycles[blockIdx.x * 4 + 1] = c_full;
+                ep.dbg_cycles[blockIdx.x * 4 + 2] = c_acc; ep.dbg_cycles[blockIdx.x * 4 + 3] = c_n;
             }
         }
         __syncwarp();
@@ -564,13 +581,20 @@ k_pf_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         if (lane == 0 && leader) {   // ---------------- MMA issuer (leader CTA only)
             uint32_t s = 0, ph = 0;
             int it = 0;
+            const bool dbg = PF_INSTRUMENT && ep.dbg_cycles != nullptr;
+            long long c_full = 0, c_acc = 0, c_n = 0;
+            const long long c_t0 = dbg ? clock64() : 0;
             for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
                 const int as = it & 1;
+                long long c0 = dbg ? clock64() : 0;
                 mbar_wait(bar_tempty(as), ((it >> 1) & 1) ^ 1);
+                if (dbg) c_acc += clock64() - c0;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
                 for (int kb = 0; kb < nkb; kb++) {
+                    if (dbg) c0 = clock64();
                     mbar_wait(bar_full(s), ph);
+                    if (dbg) { c_full += clock64() - c0; c_n++; }
                     tc_fence_after();
                     const uint32_t sa = smem_base + s * STAGE_BYTES;
                     const uint32_t sb = sa + A_BYTES;
@@ -589,6 +613,10 @@ k_pf_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                                      ::"r"(bar_tfull(as)), "h"((uint16_t)3) : "memory");
                     if (++s == ST) { s = 0; ph ^= 1; }
                 }
+            }
+            if (dbg) {
+                ep.dbg_cycles[blockIdx.x * 4 + 0] = clock64() - c_t0; ep.dbg_cycles[blockIdx.x * 4 + 1] = c_full;
+                ep.dbg_cycles[blockIdx.x * 4 + 2] = c_acc; ep.dbg_cycles[blockIdx.x * 4 + 3] = c_n;
             }
         }
         __syncwarp();
@@ -1258,6 +1286,16 @@ static int pick_bn(int M, int N) {
     return c128 < c256 ? 128 : 256;
 }
 
+static void report_cycles(long long* dbg, const char* what, int M, int N, int K) {
+    std::vector<long long> h(1024 * 4);
+    cudaMemcpyAsync(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost, ctx().stream);
+    cudaStreamSynchronize(ctx().stream);
+    double tot = 0, full = 0, acc = 0, n = 0; int c = 0;
+    for (int i = 0; i < 1024; i++) if (h[i * 4 + 3] > 0) { tot += h[i * 4]; full += h[i * 4 + 1]; acc += h[i * 4 + 2]; n += h[i * 4 + 3]; c++; }
+    if (c) fprintf(stderr, "[pf_gemm %s M=%d N=%d K=%d] MMA threads: %d, cycles/k-block %.0f (ideal 540), waiting for TMA data %.1f %%, for a free accumulator %.1f %%\n",
+                   what, M, N, K, c, tot / n, 100.0 * full / tot, 100.0 * acc / tot);
+}
+
 int pf_gemm_f32(const void* d_A16, const void* d_W16, float* d_C, int M, int N, int K, int bn) {
     GTB_ARG(M > 0 && N > 0 && K > 0 && K % PF_BK == 0 && N % 32 == 0 && (bn == 128 || bn == 256 || bn == 512));
     CUtensorMap ta, tb;
@@ -1268,8 +1306,17 @@ int pf_gemm_f32(const void* d_A16, const void* d_W16, float* d_C, int M, int N, 
     PfEpi ep;
     ep.out0 = d_C;
     if (getenv("GTB_PF_SAME_TILE")) ep.dbg_same_tile = 1;
-    if (bn == 512) return gemm_epi2<EPI_F32>(ta, tb, M, N, K, ep);      // bn = 512 selects the CTA-pair kernel (256 x 256 tiles)
-    return gemm_epi<EPI_F32>(ta, tb, bn, M, N, K, ep);
+    long long* dbg = nullptr;
+    if (getenv("GTB_PF_CYCLES")) {
+        if (cudaMalloc((void**)&dbg, 1024 * 4 * 8) == cudaSuccess) { cudaMemsetAsync(dbg, 0, 1024 * 4 * 8, ctx().stream); ep.dbg_cycles = dbg; }
+    }
+    r = (bn == 512) ? gemm_epi2<EPI_F32>(ta, tb, M, N, K, ep)         // bn = 512 selects the CTA-pair kernel (256 x 256 tiles)
+                    : gemm_epi<EPI_F32>(ta, tb, bn, M, N, K, ep);
+    if (dbg) {
+        report_cycles(dbg, bn == 512 ? "probe, CTA pairs" : (bn == 256 ? "probe, 256-wide" : "probe, 128-wide"), M, N, K);
+        cudaFree(dbg);
+    }
+    return r;
 }
 
 struct PfLayerW {
@@ -1406,6 +1453,8 @@ int pf_run(PfPlan* p, const PfRun& r) {
                                             capp(0, GTB_A_ATTN_NORM), r.capw, at));
     GTB_LAUNCHED();
     const int bn_qkv = pick_bn(T, NQKV), bn_o = pick_bn(T, E), bn_gu = pick_bn(T, 2 * F), bn_d = pick_bn(T, E);
+    long long* dbgc = nullptr;                      // GTB_PF_CYCLES=1: where the MMA thread of each GEMM of layer 0 spends its cycles
+    if (getenv("GTB_PF_CYCLES") && cudaMalloc((void**)&dbgc, 4 * 1024 * 4 * 8) == cudaSuccess) cudaMemsetAsync(dbgc, 0, 4 * 1024 * 4 * 8, st);
     for (int li = 0; li < r.n_layers_run; li++) {
         const PfLayerIO& io = r.layers[li];
         PfLayerW& w = p->L[li];
@@ -1415,6 +1464,7 @@ int pf_run(PfPlan* p, const PfRun& r) {
         eq.rope_cos = r.rope_cos; eq.rope_sin = r.rope_sin; eq.q16 = p->q16; eq.k16 = p->k16; eq.v16 = p->v16;
         eq.kq = io.kq; eq.ks = io.ks; eq.vq = io.vq; eq.vs = io.vs; eq.nh = nh; eq.ng = ng;
         eq.cap0 = capp(li, GTB_A_Q); eq.cap1 = capp(li, GTB_A_K); eq.cap2 = capp(li, GTB_A_V); eq.capw = r.capw;
+        if (dbgc && li == 0) eq.dbg_cycles = dbgc;
         if (fused) {
             rc = gemm_any<EPI_ROPE>(p->two_cta, ta_xn, w.tm[0], bn_qkv, T, NQKV, E, eq);
             if (rc) return rc;
@@ -1449,6 +1499,7 @@ int pf_run(PfPlan* p, const PfRun& r) {
         eg.at = at;
         eg.out0 = p->guq; eg.out1 = p->gus; eg.act16 = p->act16; eg.F = F;
         eg.cap0 = capp(li, GTB_A_GATE); eg.cap1 = capp(li, GTB_A_UP); eg.capw = r.capw;
+        if (dbgc && li == 0) eg.dbg_cycles = dbgc + 2 * 1024 * 4;
         if (fused) {
             rc = gemm_any<EPI_SILU>(p->two_cta, ta_xn, w.tm[2], bn_gu, T, 2 * F, E, eg);
             if (rc) return rc;
@@ -1469,6 +1520,11 @@ int pf_run(PfPlan* p, const PfRun& r) {
             GTB_CUDA(pf_launch(k_pf_tail, dim3((E + 255) / 256), dim3(256), 0, p->xq, p->xs, p->oq, p->os, T - 1, E, r.last_res, r.last_down, capp(li, GTB_A_DOWN), T, r.capw, at));
             GTB_LAUNCHED();
         }
+    }
+    if (dbgc) {
+        report_cycles(dbgc, "q|k|v + RoPE", T, NQKV, E);
+        report_cycles(dbgc + 2 * 1024 * 4, "gate|up + SiLU", T, 2 * F, E);
+        cudaFree(dbgc);
     }
     p->launches_last = ctx().launches - l0;
     return GTB_OK;
