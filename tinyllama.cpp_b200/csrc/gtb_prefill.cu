@@ -223,8 +223,9 @@ __device__ __forceinline__ float pf_silu(float x) { return __fdividef(x, 1.0f + 
 // ops.h:40-96; quants.h:52-66).  Rounding is to nearest via the 1.5 * 2^23 magic number: the code sits in the low byte of
 // the biased sum.  This differs from the reference's roundf (half away from zero) only when x * scale lands exactly on
 // k + 0.5; the bit-exact path (gtb_dev.cuh) keeps roundf.
-__device__ __forceinline__ uint16_t pf_roundtrip32(float (&x)[32], uint32_t (&q)[32], int at = DT_Q8) {
-    if (at == DT_F16) {                 // FP16 activations: every element is rounded to fp16 on its own (ops.h:83-90)
+template <int AT = DT_Q8>
+__device__ __forceinline__ uint16_t pf_roundtrip32(float (&x)[32], uint32_t (&q)[32]) {
+    if (AT == DT_F16) {                 // FP16 activations: every element is rounded to fp16 on its own (ops.h:83-90)
 #pragma unroll
         for (int i = 0; i < 32; i++) x[i] = f16_roundtrip(x[i]);
         return 0;
@@ -247,6 +248,7 @@ __device__ __forceinline__ uint16_t pf_roundtrip32(float (&x)[32], uint32_t (&q)
 
 // One head slot of the q|k|v Linear output of row `row`: x0/x1 = the two decoded Q8 blocks, (q0,dh0)/(q1,dh1) their codes.
 // q and k heads: RoPE (ops.h:714-760) and the second re-encode; k and v: append to the cache in the engine's layout.
+template <int AT>
 __device__ __forceinline__ void pf_rope_store(const PfEpi& ep, int row, int slot, float (&x0)[32], float (&x1)[32],
                                               uint32_t (&q0)[32], uint32_t (&q1)[32], uint16_t dh0, uint16_t dh1) {
     const int nh = ep.nh, ng = ep.ng, E = nh * 64, KV = ng * 64;
@@ -265,11 +267,11 @@ __device__ __forceinline__ void pf_rope_store(const PfEpi& ep, int row, int slot
                 x1[4 * k + j] = __fadd_rn(__fmul_rn(a, s[j]), __fmul_rn(b, c[j]));
             }
         }
-        dh0 = pf_roundtrip32(x0, q0, ep.at);
-        dh1 = pf_roundtrip32(x1, q1, ep.at);
+        dh0 = pf_roundtrip32<AT>(x0, q0);
+        dh1 = pf_roundtrip32<AT>(x1, q1);
     }
     const int capw = ep.capw;
-    const bool f16 = ep.at == DT_F16;
+    constexpr bool f16 = AT == DT_F16;
     if (slot < nh) {
         store_half32(ep.q16 + (size_t)row * E + slot * 64, x0);
         store_half32(ep.q16 + (size_t)row * E + slot * 64 + 32, x1);
@@ -307,14 +309,15 @@ __device__ __forceinline__ void pf_rope_store(const PfEpi& ep, int row, int slot
 
 // One 32-block of the FFN: g/u = decoded gate and up Linear outputs; SiLU (ops.h:673-711), re-encode, Multiply
 // (ops.h:816-867), re-encode -> fp16 operand of the down projection
+template <int AT>
 __device__ __forceinline__ void pf_silu_store(const PfEpi& ep, int row, int b, float (&g)[32], const float (&u)[32]) {
 #pragma unroll
     for (int k = 0; k < 32; k++) g[k] = pf_silu(g[k]);
     uint32_t q[32];
-    pf_roundtrip32(g, q, ep.at);
+    pf_roundtrip32<AT>(g, q);
 #pragma unroll
     for (int k = 0; k < 32; k++) g[k] = __fmul_rn(g[k], u[k]);
-    pf_roundtrip32(g, q, ep.at);
+    pf_roundtrip32<AT>(g, q);
     store_half32(ep.act16 + (size_t)row * ep.F + (size_t)b * 32, g);
     if (ep.cap0) for (int k = 0; k < 32; k++) { ep.cap0[(size_t)row * ep.capw + b * 32 + k] = g[k]; ep.cap1[(size_t)row * ep.capw + b * 32 + k] = u[k]; }
 }
@@ -350,7 +353,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 
 // Epilogue of one accumulator tile for one thread: `tacc` = TMEM address of this thread's row (lane) at the tile's first
 // column; the two epilogue warps of a lane quarter split the columns (chalf = 0/1).
-template <int BN, int EPI>
+template <int BN, int EPI, int AT>
 __device__ __forceinline__ void pf_epilogue(const PfEpi& ep, uint32_t tacc, int row, bool row_ok, int col0, int N, int chalf) {
     if (EPI == EPI_F32 || EPI == EPI_Q8) {
 #pragma unroll 1
@@ -363,8 +366,8 @@ __device__ __forceinline__ void pf_epilogue(const PfEpi& ep, uint32_t tacc, int 
                     store_f32x32(reinterpret_cast<float*>(ep.out0) + (size_t)row * N + col, v);
                 } else {
                     uint32_t q[32];
-                    const uint16_t dh = pf_roundtrip32(v, q, ep.at);     // write_row_from_float, ops.h:645-646
-                    if (ep.at == DT_F16) {
+                    const uint16_t dh = pf_roundtrip32<AT>(v, q);        // write_row_from_float, ops.h:645-646
+                    if (AT == DT_F16) {
                         store_half32(reinterpret_cast<__half*>(ep.out0) + (size_t)row * N + col, v);
                     } else {
                         store_codes32(reinterpret_cast<int8_t*>(ep.out0) + (size_t)row * N + col, q);
@@ -383,15 +386,15 @@ __device__ __forceinline__ void pf_epilogue(const PfEpi& ep, uint32_t tacc, int 
             tmem_ld32(tacc + (uint32_t)(c2 * 64 + 32), b);
             if (row_ok && col < N) {
                 uint32_t q0[32], q1[32];
-                const uint16_t dh0 = pf_roundtrip32(a, q0, ep.at), dh1 = pf_roundtrip32(b, q1, ep.at);   // the Linear's own re-encode
-                if (EPI == EPI_ROPE) pf_rope_store(ep, row, col >> 6, a, b, q0, q1, dh0, dh1);
-                else pf_silu_store(ep, row, col >> 6, a, b);
+                const uint16_t dh0 = pf_roundtrip32<AT>(a, q0), dh1 = pf_roundtrip32<AT>(b, q1);   // the Linear's own re-encode
+                if (EPI == EPI_ROPE) pf_rope_store<AT>(ep, row, col >> 6, a, b, q0, q1, dh0, dh1);
+                else pf_silu_store<AT>(ep, row, col >> 6, a, b);
             }
         }
     }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int AT>
 __global__ void __launch_bounds__(PF_THREADS, 1)
 k_pf_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, const PfEpi ep) {
     using Cfg = PfGemmCfg<BN>;
@@ -487,7 +490,7 @@ k_pf_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             tc_fence_after();
             const int row = mt * PF_BM + lg * 32 + lane;
             const bool row_ok = row < M;
-            pf_epilogue<BN, EPI>(ep, tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN), row, row_ok, nt * BN, N, chalf);
+            pf_epilogue<BN, EPI, AT>(ep, tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN), row, row_ok, nt * BN, N, chalf);
             tc_fence_before();
             mbar_arrive(bar_tempty(as));
         }
@@ -511,7 +514,7 @@ constexpr int PF2_STAGES = 6;
 constexpr uint32_t PF2_STAGE_BYTES = PF_BM * PF_BK * 2 + 128 * PF_BK * 2;
 constexpr uint32_t PF2_SMEM = PF2_STAGES * PF2_STAGE_BYTES + 1024 + 256;
 
-template <int EPI>
+template <int EPI, int AT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PF_THREADS, 1)
 k_pf_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, const PfEpi ep) {
     constexpr int BN = 256;
@@ -630,7 +633,7 @@ k_pf_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             mbar_wait(bar_tfull(as), (it >> 1) & 1);
             tc_fence_after();
             const int row = mt * 256 + (int)rank * PF_BM + lg * 32 + lane;
-            pf_epilogue<BN, EPI>(ep, tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN), row, row < M, nt * BN, N, chalf);
+            pf_epilogue<BN, EPI, AT>(ep, tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN), row, row < M, nt * BN, N, chalf);
             tc_fence_before();
             asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, 0;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
                          ::"r"(bar_tempty(as)) : "memory");
@@ -760,9 +763,10 @@ __global__ void k_pf_embed(const void* __restrict__ wdata, const uint16_t* __res
 //   xn <- fp16( E( x / (rms(x) + 1e-6) * w ) )       the A operand of the next GEMM
 // The sum of squares is a plain parallel fp32 sum (the reference sums in element order): its relative error of ~1e-7
 // is three orders of magnitude below the fp16 operand rounding of the GEMMs of this path.
+template <int AT>
 __global__ void __launch_bounds__(64) k_pf_add_norm(int8_t* __restrict__ xq, uint16_t* __restrict__ xs, const int8_t* __restrict__ yq,
                                                      const uint16_t* __restrict__ ys, const uint16_t* __restrict__ normw,
-                                                     __half* __restrict__ xn16, int T, int D, float* cap_y, float* cap_x, float* cap_n, int capw, int at) {
+                                                     __half* __restrict__ xn16, int T, int D, float* cap_y, float* cap_x, float* cap_n, int capw) {
     pdl_trigger_and_wait();
     __shared__ float red[2];
     const int row = blockIdx.x, tid = threadIdx.x;
@@ -771,16 +775,16 @@ __global__ void __launch_bounds__(64) k_pf_add_norm(int8_t* __restrict__ xq, uin
     float ssq = 0.0f;
     float v[32];
     for (int b = tid; b < nb; b += 64) {
-        load_act32(at, xq, xs, row, D, b, v);
+        load_act32(AT, xq, xs, row, D, b, v);
         if (yq) {
             float y[32];
-            load_act32(at, yq, ys, row, D, b, y);
+            load_act32(AT, yq, ys, row, D, b, y);
             if (cap_y) for (int i = 0; i < 32; i++) cap_y[(size_t)row * capw + b * 32 + i] = y[i];
 #pragma unroll
             for (int i = 0; i < 32; i++) v[i] = __fadd_rn(v[i], y[i]);
             uint32_t q[32];
-            const uint16_t dh = pf_roundtrip32(v, q, at);
-            if (at == DT_F16) {
+            const uint16_t dh = pf_roundtrip32<AT>(v, q);
+            if (AT == DT_F16) {
                 store_half32(reinterpret_cast<__half*>(xq) + (size_t)row * D + (size_t)b * 32, v);
             } else {
                 store_codes32(xq + (size_t)row * D + (size_t)b * 32, q);
@@ -799,7 +803,7 @@ __global__ void __launch_bounds__(64) k_pf_add_norm(int8_t* __restrict__ xq, uin
     const float rms = sqrtf(__fdiv_rn(ssq, (float)D));
     const float denom = __fadd_rn(rms, 1e-6f);
     for (int b = tid; b < nb; b += 64) {
-        if (!single) load_act32(at, xq, xs, row, D, b, v);
+        if (!single) load_act32(AT, xq, xs, row, D, b, v);
         const uint4* wp = reinterpret_cast<const uint4*>(normw + b * 32);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -812,7 +816,7 @@ __global__ void __launch_bounds__(64) k_pf_add_norm(int8_t* __restrict__ xq, uin
             }
         }
         uint32_t q[32];
-        pf_roundtrip32(v, q, at);
+        pf_roundtrip32<AT>(v, q);
         if (cap_n) for (int i = 0; i < 32; i++) cap_n[(size_t)row * capw + b * 32 + i] = v[i];
         store_half32(xn16 + (size_t)row * D + (size_t)b * 32, v);
     }
@@ -833,7 +837,7 @@ __global__ void __launch_bounds__(128) k_pf_rope_kv(const int8_t* __restrict__ c
     load_deq32(cq, cs, row, D, slot * 2 + 1, x1);
     load_codes32(cq + (size_t)row * D + (size_t)slot * 64, q0);
     load_codes32(cq + (size_t)row * D + (size_t)slot * 64 + 32, q1);
-    pf_rope_store(ep, row, slot, x0, x1, q0, q1, cs[(size_t)row * (D / 32) + slot * 2], cs[(size_t)row * (D / 32) + slot * 2 + 1]);
+    pf_rope_store<DT_Q8>(ep, row, slot, x0, x1, q0, q1, cs[(size_t)row * (D / 32) + slot * 2], cs[(size_t)row * (D / 32) + slot * 2 + 1]);
 }
 
 // gate|up planar output with the rows of the two matrices interleaved in groups of 32: block 2b = gate block b, 2b+1 = up block b
@@ -846,7 +850,7 @@ __global__ void __launch_bounds__(128) k_pf_silu_mul(const int8_t* __restrict__ 
     float g[32], u[32];
     load_deq32(gq, gs, row, 2 * ep.F, 2 * b, g);
     load_deq32(gq, gs, row, 2 * ep.F, 2 * b + 1, u);
-    pf_silu_store(ep, row, b, g, u);
+    pf_silu_store<DT_Q8>(ep, row, b, g, u);
 }
 
 // dequantised fp32 copies of row `row` for the exact final-norm + lm_head phase of the engine
@@ -1240,24 +1244,25 @@ static cudaError_t pf_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int AT>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const PfEpi& ep) {
     using Cfg = PfGemmCfg<BN>;
     static bool attr = false;
     if (!attr) {
-        GTB_CUDA(cudaFuncSetAttribute(k_pf_gemm<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        GTB_CUDA(cudaFuncSetAttribute(k_pf_gemm<BN, EPI, AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         attr = true;
     }
     const int n_tiles = ((M + PF_BM - 1) / PF_BM) * ((N + BN - 1) / BN);
     const int grid = n_tiles < ctx().sm_count ? n_tiles : ctx().sm_count;
-    GTB_CUDA(pf_launch(k_pf_gemm<BN, EPI>, dim3(grid), dim3(PF_THREADS), Cfg::SMEM, ta, tb, M, N, K, ep));
+    GTB_CUDA(pf_launch(k_pf_gemm<BN, EPI, AT>, dim3(grid), dim3(PF_THREADS), Cfg::SMEM, ta, tb, M, N, K, ep));
     GTB_LAUNCHED();
     return GTB_OK;
 }
 
 template <int EPI>
 static int gemm_epi(const CUtensorMap& ta, const CUtensorMap& tb, int bn, int M, int N, int K, const PfEpi& ep) {
-    return bn == 256 ? launch_gemm<256, EPI>(ta, tb, M, N, K, ep) : launch_gemm<128, EPI>(ta, tb, M, N, K, ep);
+    if (ep.at == DT_F16) return bn == 256 ? launch_gemm<256, EPI, DT_F16>(ta, tb, M, N, K, ep) : launch_gemm<128, EPI, DT_F16>(ta, tb, M, N, K, ep);
+    return bn == 256 ? launch_gemm<256, EPI, DT_Q8>(ta, tb, M, N, K, ep) : launch_gemm<128, EPI, DT_Q8>(ta, tb, M, N, K, ep);
 }
 
 // CTA-pair variant: 256 x 256 tiles; tb128 = tensor map of W with a 128-row box (each CTA stages half of the W tile)
@@ -1265,13 +1270,15 @@ template <int EPI>
 static int gemm_epi2(const CUtensorMap& ta, const CUtensorMap& tb128, int M, int N, int K, const PfEpi& ep) {
     static bool attr = false;
     if (!attr) {
-        GTB_CUDA(cudaFuncSetAttribute(k_pf_gemm2<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF2_SMEM));
+        GTB_CUDA(cudaFuncSetAttribute(k_pf_gemm2<EPI, DT_Q8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF2_SMEM));
+        GTB_CUDA(cudaFuncSetAttribute(k_pf_gemm2<EPI, DT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF2_SMEM));
         attr = true;
     }
     const int n_tiles = ((M + 255) / 256) * ((N + 255) / 256);
     const int max_clusters = ctx().sm_count / 2;
     const int clusters = n_tiles < max_clusters ? n_tiles : max_clusters;
-    GTB_CUDA(pf_launch(k_pf_gemm2<EPI>, dim3(2 * clusters), dim3(PF_THREADS), PF2_SMEM, ta, tb128, M, N, K, ep));
+    if (ep.at == DT_F16) GTB_CUDA(pf_launch(k_pf_gemm2<EPI, DT_F16>, dim3(2 * clusters), dim3(PF_THREADS), PF2_SMEM, ta, tb128, M, N, K, ep));
+    else GTB_CUDA(pf_launch(k_pf_gemm2<EPI, DT_Q8>, dim3(2 * clusters), dim3(PF_THREADS), PF2_SMEM, ta, tb128, M, N, K, ep));
     GTB_LAUNCHED();
     return GTB_OK;
 }
@@ -1449,8 +1456,10 @@ int pf_run(PfPlan* p, const PfRun& r) {
                                                                  capp(0, GTB_A_EMB), r.capw));
         GTB_LAUNCHED();
     }
-    GTB_CUDA(pf_launch(k_pf_add_norm, dim3(T), dim3(64), 0, p->xq, p->xs, nullptr, nullptr, r.layers[0].attn_norm, p->xn16, T, E, nullptr, nullptr,
-                                            capp(0, GTB_A_ATTN_NORM), r.capw, at));
+    if (at == DT_F16) GTB_CUDA(pf_launch(k_pf_add_norm<DT_F16>, dim3(T), dim3(64), 0, p->xq, p->xs, nullptr, nullptr, r.layers[0].attn_norm, p->xn16, T, E, nullptr, nullptr,
+                                            capp(0, GTB_A_ATTN_NORM), r.capw));
+        else GTB_CUDA(pf_launch(k_pf_add_norm<DT_Q8>, dim3(T), dim3(64), 0, p->xq, p->xs, nullptr, nullptr, r.layers[0].attn_norm, p->xn16, T, E, nullptr, nullptr,
+                                            capp(0, GTB_A_ATTN_NORM), r.capw));
     GTB_LAUNCHED();
     const int bn_qkv = pick_bn(T, NQKV), bn_o = pick_bn(T, E), bn_gu = pick_bn(T, 2 * F), bn_d = pick_bn(T, E);
     long long* dbgc = nullptr;                      // GTB_PF_CYCLES=1: where the MMA thread of each GEMM of layer 0 spends its cycles
@@ -1492,8 +1501,10 @@ int pf_run(PfPlan* p, const PfRun& r) {
         eo.out0 = p->oq; eo.out1 = p->os;
         rc = gemm_any<EPI_Q8>(p->two_cta, ta_attn, w.tm[1], bn_o, T, E, E, eo);
         if (rc) return rc;
-        GTB_CUDA(pf_launch(k_pf_add_norm, dim3(T), dim3(64), 0, p->xq, p->xs, p->oq, p->os, io.ffn_norm, p->xn16, T, E, capp(li, GTB_A_O), capp(li, GTB_A_INP_RES),
-                                        capp(li, GTB_A_FFN_NORM), r.capw, at));
+        if (at == DT_F16) GTB_CUDA(pf_launch(k_pf_add_norm<DT_F16>, dim3(T), dim3(64), 0, p->xq, p->xs, p->oq, p->os, io.ffn_norm, p->xn16, T, E, capp(li, GTB_A_O), capp(li, GTB_A_INP_RES),
+                                        capp(li, GTB_A_FFN_NORM), r.capw));
+        else GTB_CUDA(pf_launch(k_pf_add_norm<DT_Q8>, dim3(T), dim3(64), 0, p->xq, p->xs, p->oq, p->os, io.ffn_norm, p->xn16, T, E, capp(li, GTB_A_O), capp(li, GTB_A_INP_RES),
+                                        capp(li, GTB_A_FFN_NORM), r.capw));
         GTB_LAUNCHED();
         PfEpi eg;                                   // gate|up: Linear re-encode, SiLU, Multiply
         eg.at = at;
@@ -1513,8 +1524,10 @@ int pf_run(PfPlan* p, const PfRun& r) {
         rc = gemm_any<EPI_Q8>(p->two_cta, ta_act, w.tm[3], bn_d, T, E, F, eo);
         if (rc) return rc;
         if (li + 1 < r.n_layers_run) {
-            GTB_CUDA(pf_launch(k_pf_add_norm, dim3(T), dim3(64), 0, p->xq, p->xs, p->oq, p->os, r.layers[li + 1].attn_norm, p->xn16, T, E, capp(li, GTB_A_DOWN),
-                                            capp(li, GTB_A_ATTN_RES), capp(li + 1, GTB_A_ATTN_NORM), r.capw, at));
+            if (at == DT_F16) GTB_CUDA(pf_launch(k_pf_add_norm<DT_F16>, dim3(T), dim3(64), 0, p->xq, p->xs, p->oq, p->os, r.layers[li + 1].attn_norm, p->xn16, T, E, capp(li, GTB_A_DOWN),
+                                            capp(li, GTB_A_ATTN_RES), capp(li + 1, GTB_A_ATTN_NORM), r.capw));
+        else GTB_CUDA(pf_launch(k_pf_add_norm<DT_Q8>, dim3(T), dim3(64), 0, p->xq, p->xs, p->oq, p->os, r.layers[li + 1].attn_norm, p->xn16, T, E, capp(li, GTB_A_DOWN),
+                                            capp(li, GTB_A_ATTN_RES), capp(li + 1, GTB_A_ATTN_NORM), r.capw));
             GTB_LAUNCHED();
         } else {
             GTB_CUDA(pf_launch(k_pf_tail, dim3((E + 255) / 256), dim3(256), 0, p->xq, p->xs, p->oq, p->os, T - 1, E, r.last_res, r.last_down, capp(li, GTB_A_DOWN), T, r.capw, at));
