@@ -53,6 +53,8 @@ public:
         GTEN_CUDA_OK(gtb_engine_logits(eng_, tokens.data_ptr<int32_t>(), tokens.numel(), start_pos, logits_.data_ptr<float>()));
         return logits_;
     }
+    // candidate set of topk_sample (tinyllama.cpp:466-478) selected on the device: values[k], ids[k], largest first
+    void topk(int k, float* values, int32_t* ids) { GTEN_CUDA_OK(gtb_engine_topk(eng_, k, values, ids)); }
     gtb_engine_t engine() { return eng_; }
 private:
     int n_ctx_;

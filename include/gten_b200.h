@@ -126,6 +126,10 @@ int gtb_pf_gemm_f32(const void* h_A16, const void* h_W16, int M, int N, int K, i
 int gtb_engine_position(gtb_engine_t e, int* pos);
 int gtb_engine_read_tokens(gtb_engine_t e, int32_t* h_tokens, int first, int count);
 int gtb_engine_read_logits(gtb_engine_t e, float* h_logits);
+/* the k (<= 64) largest logits of the last processed row and their token ids, largest first, ties to the lower id: the
+ * candidate set of topk_sample (tinyllama.cpp:466-478), so that 8k bytes instead of 128 KB return to the host per token;
+ * temperature, softmax and the draw from std::discrete_distribution stay on the host with the caller's generator */
+int gtb_engine_topk(gtb_engine_t e, int k, float* h_values, int32_t* h_ids);
 /* decoded fp32 row of a module activation for the LAST processed row (debug/parity) */
 int gtb_engine_acv(gtb_engine_t e, int layer, int acv_id, float* h_out, int* width);
 /* options: "mega" (1: persistent cooperative kernel, default; 0: one kernel per phase), "graph" (CUDA-graph replay of

@@ -303,3 +303,18 @@ def test_config5_sequence_sample_matches_reference(capi, checker):
     got = e.read_tokens(0, n_prompt + n_new)
     assert np.array_equal(got, want)
     e.close(); cm.close()
+
+
+def test_device_topk_is_the_reference_candidate_set(capi):
+    """gtb_engine_topk returns what topk_sample's partial_sort keeps (tinyllama.cpp:466-478): the k largest logits."""
+    cfg = W.mini_config(n_layers=1, n_vocab=3000)
+    e = capi.Engine(cfg, 32, Q4).load(W.synth_weights(cfg, Q4, seed=6))
+    lg = e.logits(W.synth_prompt(4, 9, cfg.n_vocab), 0)
+    for k in (1, 5, 40, 64):
+        v, ids = e.topk(k)
+        order = np.lexsort((np.arange(lg.size), -lg.astype(np.float64)))[:k]        # value descending, ties to the lower id
+        assert np.array_equal(ids, order.astype(np.int32)), k
+        assert np.array_equal(v.view(np.uint32), lg[order].view(np.uint32))
+    with pytest.raises(capi.GtbError, match="argument check failed"):
+        e.topk(65)
+    e.close()

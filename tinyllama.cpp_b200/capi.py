@@ -28,7 +28,7 @@ SYMBOLS = [
     "gtb_engine_logits", "gtb_engine_generate", "gtb_engine_reset", "gtb_engine_prefill", "gtb_engine_decode",
     "gtb_engine_position", "gtb_engine_read_tokens", "gtb_engine_read_logits", "gtb_engine_acv",
     "gtb_engine_set_option", "gtb_engine_weight_bytes", "gtb_engine_read_prof", "gtb_selftest_exact_sum", "gtb_engine_uses_megakernel",
-    "gtb_engine_prefill_fast", "gtb_engine_pf_acv", "gtb_pf_gemm_f32",
+    "gtb_engine_prefill_fast", "gtb_engine_pf_acv", "gtb_pf_gemm_f32", "gtb_engine_topk",
 ]
 
 
@@ -77,7 +77,7 @@ def lib():
             "gtb_engine_set_option": [vp, C.c_char_p, i], "gtb_engine_weight_bytes": [vp, C.POINTER(sz)],
             "gtb_engine_read_prof": [vp, vp, i], "gtb_selftest_exact_sum": [vp, i, vp], "gtb_engine_uses_megakernel": [vp, C.POINTER(C.c_int)],
             "gtb_engine_prefill_fast": [vp, vp, i], "gtb_engine_pf_acv": [vp, i, i, i, vp, C.POINTER(i)],
-            "gtb_pf_gemm_f32": [vp, vp, i, i, i, i, vp],
+            "gtb_pf_gemm_f32": [vp, vp, i, i, i, i, vp], "gtb_engine_topk": [vp, i, vp, vp],
         }
         for name, args in sigs.items():
             fn = getattr(L, name)
@@ -366,6 +366,13 @@ class Engine:
         out = np.empty(self.cfg.n_vocab, np.float32)
         check(lib().gtb_engine_read_logits(self.h, _hp(out)))
         return out
+
+    def topk(self, k: int):
+        """(values, ids) of the k largest logits of the last processed row, largest first, ties to the lower id."""
+        v = np.empty(k, np.float32)
+        ids = np.empty(k, np.int32)
+        check(lib().gtb_engine_topk(self.h, k, _hp(v), _hp(ids)))
+        return v, ids
 
     def acv(self, layer: int, aid: int) -> np.ndarray:
         out = np.empty(max(self.cfg.n_ffn, self.cfg.n_embd), np.float32)

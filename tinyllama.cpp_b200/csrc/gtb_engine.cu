@@ -240,6 +240,44 @@ __global__ void __launch_bounds__(1024) k_argmax_advance(const float* __restrict
 
 __global__ void k_advance(DevState* st) { st->pos += 1; }
 
+// The k largest logits and their token ids, largest first, ties to the lower id (the candidate set of topk_sample,
+// tinyllama.cpp:466-478): k rounds of a block-wide arg-max over the not-yet-taken entries.  One CTA of 1024 threads.
+__global__ void __launch_bounds__(1024) k_topk(const float* __restrict__ logits, int n, int k, float* __restrict__ out_v, int32_t* __restrict__ out_i) {
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    __shared__ int taken[64];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int r = 0; r < k; r++) {
+        float best = -INFINITY;
+        int arg = 0x7fffffff;
+        for (int j = tid; j < n; j += 1024) {
+            const float v = logits[j];
+            bool skip = false;
+            for (int q = 0; q < r; q++) skip |= (taken[q] == j);
+            if (!skip && (v > best || (v == best && j < arg) || arg == 0x7fffffff)) { best = v; arg = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (oi != 0x7fffffff && (arg == 0x7fffffff || ov > best || (ov == best && oi < arg))) { best = ov; arg = oi; }
+        }
+        if (lane == 0) { sv[wid] = best; si[wid] = arg; }
+        __syncthreads();
+        if (wid == 0) {
+            best = sv[lane]; arg = si[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+                if (oi != 0x7fffffff && (arg == 0x7fffffff || ov > best || (ov == best && oi < arg))) { best = ov; arg = oi; }
+            }
+            if (lane == 0) { taken[r] = arg; out_v[r] = best; out_i[r] = arg; }
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------- host side
 // self-test of the megakernel's exact in-order sum on arbitrary terms (one CTA of MT threads)
 __global__ void __launch_bounds__(MT) k_selftest_exact_sum(const float* __restrict__ terms, int n, float* out) {
@@ -991,6 +1029,22 @@ int gtb_engine_read_logits(gtb_engine_t e, float* h_logits) {
     GTB_ARG(e && h_logits);
     GTB_CUDA(cudaMemcpyAsync(h_logits, e->logits, (size_t)e->cfg.n_vocab * 4, cudaMemcpyDeviceToHost, ctx().stream));
     GTB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return GTB_OK;
+}
+
+int gtb_engine_topk(gtb_engine_t e, int k, float* h_values, int32_t* h_ids) {
+    GTB_CHECK_INIT();
+    GTB_ARG(e && h_values && h_ids && k > 0 && k <= 64 && k <= e->cfg.n_vocab);
+    float* dv = nullptr;
+    GTB_CUDA(cudaMalloc((void**)&dv, 64 * 8));
+    int32_t* di = reinterpret_cast<int32_t*>(dv + 64);
+    k_topk<<<1, 1024, 0, ctx().stream>>>(e->logits, e->cfg.n_vocab, k, dv, di);
+    ctx().launches++;
+    cudaError_t ce = cudaMemcpyAsync(h_values, dv, (size_t)k * 4, cudaMemcpyDeviceToHost, ctx().stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_ids, di, (size_t)k * 4, cudaMemcpyDeviceToHost, ctx().stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx().stream);
+    cudaFree(dv);
+    if (ce != cudaSuccess) return fail(GTB_ERR_CUDA, "top-k failed: %s", cudaGetErrorString(ce));
     return GTB_OK;
 }
 
