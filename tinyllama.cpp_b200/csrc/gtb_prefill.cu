@@ -501,11 +501,12 @@ k_pf_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// The same GEMM on CTA PAIRS (tcgen05 cta_group::2).  One M128 x N256 MMA per SM reads 12 KB of shared memory per K=16
-// step while TMA writes another 12 KB: 182 B/clk against the 128 B/clk an SM's shared memory delivers -- the measured
-// 70 % tensor-pipe ceiling of k_pf_gemm (profiles/r01_02_prefill.md).  A pair computes a 256 x 256 tile: each CTA
-// stages its own 128 rows of A and HALF of the W tile, the leader CTA issues M256 MMAs that read both halves, and each
-// CTA's TMEM receives its 128 rows.  Shared-memory traffic per SM drops to 121 B/clk and L2 traffic per flop by a third.
+// The same GEMM on CTA PAIRS (tcgen05 cta_group::2).  A pair computes a 256 x 256 tile: each CTA stages its own 128 rows of A
+// and HALF of the W tile (32 KB instead of 48 KB per k-block, so six stages fit), the leader CTA issues M256 MMAs that read
+// both halves, and each CTA's TMEM receives its 128 rows.  Shared-memory traffic per SM drops by a third (l1tex throughput
+// 62 % -> 44 %).  Measured: bit-exact on the integer tests and exactly as fast as k_pf_gemm on all four prefill shapes
+// (profiles/r01_02_prefill.md) -- the single-CTA main loop is already at 90-94 % of the nominal tensor rate, what is lost is
+// outside it -- so the engine keeps k_pf_gemm by default and this kernel behind the option "pf_2cta".
 //   full[s]   (leader only, 2 arrivals): both producers arrive; both CTAs' TMA bytes complete_tx on the LEADER's barrier
 //   empty[s]  (each CTA, 1 arrival)    : the leader's tcgen05.commit multicasts to both CTAs
 //   tfull[a]  (each CTA, 1 arrival)    : commit multicast after the last k-block of a tile
