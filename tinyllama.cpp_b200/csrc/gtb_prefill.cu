@@ -765,7 +765,7 @@ __global__ void k_pf_embed(const void* __restrict__ wdata, const uint16_t* __res
 // The sum of squares is a plain parallel fp32 sum (the reference sums in element order): its relative error of ~1e-7
 // is three orders of magnitude below the fp16 operand rounding of the GEMMs of this path.
 template <int AT>
-__global__ void __launch_bounds__(64) k_pf_add_norm(int8_t* __restrict__ xq, uint16_t* __restrict__ xs, const int8_t* __restrict__ yq,
+__global__ void __launch_bounds__(64, 14) k_pf_add_norm(int8_t* __restrict__ xq, uint16_t* __restrict__ xs, const int8_t* __restrict__ yq,
                                                      const uint16_t* __restrict__ ys, const uint16_t* __restrict__ normw,
                                                      __half* __restrict__ xn16, int T, int D, float* cap_y, float* cap_x, float* cap_n, int capw) {
     pdl_trigger_and_wait();
