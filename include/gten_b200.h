@@ -134,6 +134,9 @@ int gtb_engine_topk(gtb_engine_t e, int k, float* h_values, int32_t* h_ids);
 int gtb_engine_acv(gtb_engine_t e, int layer, int acv_id, float* h_out, int* width);
 /* options: "mega" (1: persistent cooperative kernel, default; 0: one kernel per phase), "graph" (CUDA-graph replay of
  * the per-phase path), "capture_acv", "grid", "pf_ahead" (L2 prefetch distance in GEMV phases), "prof",
+ * "fast_decode" (1: rows run through the order-free kernels of gtb_fastdec.cuh -- 128-bit streaming GEMV with warp-shuffle
+ * reductions, block-reduced RMSNorm, position-split attention with an online-softmax combine; same operations and re-encode
+ * points, free summation order: tolerance-level parity like gtb_engine_prefill_fast, Q8/Q4 models; default 0),
  * "pf_layers" (debug: batched prefill stops after this many layers), "pf_fused" (RoPE/KV append and SiLU*up inside the
  * GEMM epilogues, default 1), "pf_pdl" (programmatic dependent launch, default 1), "pf_2cta" (CTA-pair tcgen05 GEMM, default 0),
  * "pf_attn2" (second attention sweep that also reproduces the fp16 rounding of the probability-row block scales, default 0) */

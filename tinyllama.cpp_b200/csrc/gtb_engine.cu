@@ -14,6 +14,7 @@
 #include "gtb_kernels.cuh"
 #include "gtb_mega.cuh"
 #include "gtb_prefill.h"
+#include "gtb_fastdec.cuh"
 
 namespace gtb {
 
@@ -349,6 +350,14 @@ struct gtb_engine {
     gtb::PfPlan* pf = nullptr;
     float* pf_cap = nullptr;         // [n_layers*12 + 1][pf_cap_T][capw] when capture_acv is on
     int pf_cap_T = 0;
+    // fast (order-free) decode kernels (gtb_fastdec.cuh): opt-in, tolerance-level parity
+    bool fast = false;
+    float* fd_parts = nullptr;       // [n_heads][FD_CHUNKS][FD_PART] attention partials
+    unsigned* fd_cnt = nullptr;      // [n_heads + 1] arrival counters (attention chunks per head; head CTAs)
+    FdAct fd_attn{}, fd_act{};       // E(attention output) [n_embd], E(MLP activation) [n_ffn]: staged codes for the next GEMV
+    float* fd_argv = nullptr;        // per-CTA maxima of the head kernel
+    int* fd_argi = nullptr;
+    int fd_ahead = 3;                // L2 look-ahead distance in GEMV steps
     int pf_layers = 0;               // debug: run only the first pf_layers layers (0 = all)
     int pf_fused = 1;                // RoPE/KV append and SiLU*up inside the GEMM epilogues
     int pf_2cta = 0;                 // CTA-pair GEMM kernel
@@ -462,7 +471,121 @@ int enqueue_row(gtb_engine* e, bool with_head, int eos_id) {
     return GTB_OK;
 }
 
+// ---- order-free decode (gtb_fastdec.cuh): launches chained with programmatic dependent launch
+template <typename... KArgs, typename... Args>
+cudaError_t fd_launch(void (*kern)(KArgs...), int grid, size_t smem, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(FD_NT); cfg.dynamicSmemBytes = smem; cfg.stream = ctx().stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+template <int WT, int PRO, int EPI, int NBL>
+int launch_fd_k(const FdArgs& a, int grid) {
+    constexpr int R = (WT == DT_Q4) ? ((NBL <= 2) ? 4 : 2) : ((NBL <= 2) ? 2 : 1);
+    const size_t smem = fd_gemv_smem(a.K, PRO == FD_NORM);
+    static bool attr_done = false;
+    if (!attr_done) {
+        GTB_CUDA(cudaFuncSetAttribute(k_fd_gemv<WT, PRO, EPI, NBL, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_done = true;
+    }
+    GTB_CUDA(fd_launch(k_fd_gemv<WT, PRO, EPI, NBL, R>, grid, smem, a));
+    GTB_LAUNCHED();
+    return GTB_OK;
+}
+template <int WT, int PRO, int EPI>
+int launch_fd(const FdArgs& a, int grid) {
+    const int nbl = (a.K / 32 + 31) / 32;
+    if (nbl <= 2) return launch_fd_k<WT, PRO, EPI, 2>(a, grid);
+    if (nbl <= 6) return launch_fd_k<WT, PRO, EPI, 6>(a, grid);
+    return fail(GTB_ERR_STATE, "fast_decode: rows longer than 6144 elements are not instantiated");
+}
+
+// one row through the order-free kernels: 5 launches per layer (+ the head)
+template <int WT>
+int enqueue_row_fast(gtb_engine* e, bool with_head, int eos_id) {
+    const gtb_model_config& c = e->cfg;
+    const int E = c.n_embd, F = c.n_ffn, KV = e->kv_dim, L = c.n_layers;
+    const int wd = c.wdtype;
+    const int G = ctx().sm_count;
+    // GEMV steps in launch order (4 per layer + head): what the L2 look-ahead walks
+    struct Step { const void* d; size_t db; const void* s; size_t sb; };
+    std::vector<Step> steps;
+    for (int li = 0; li < L; li++) {
+        LayerW& l = e->L[li];
+        steps.push_back({l.qkv_data, weight_data_bytes(wd, E + 2 * KV, E), l.qkv_sc, weight_scale_bytes(wd, E + 2 * KV, E)});
+        steps.push_back({l.o->data, weight_data_bytes(wd, E, E), l.o->scales, weight_scale_bytes(wd, E, E)});
+        steps.push_back({l.gu_data, weight_data_bytes(wd, 2 * F, E), l.gu_sc, weight_scale_bytes(wd, 2 * F, E)});
+        steps.push_back({l.down->data, weight_data_bytes(wd, E, F), l.down->scales, weight_scale_bytes(wd, E, F)});
+    }
+    if (with_head) steps.push_back({e->lm_head->data, weight_data_bytes(wd, c.n_vocab, E), e->lm_head->scales, weight_scale_bytes(wd, c.n_vocab, E)});
+    const int ns = (int)steps.size();
+    auto set_pf = [&](const void* (&pf)[2], size_t (&pfb)[2], int step) {
+        pf[0] = pf[1] = nullptr; pfb[0] = pfb[1] = 0;
+        if (e->fd_ahead <= 0) return;
+        const Step& s = steps[(step + e->fd_ahead) % ns];
+        pf[0] = s.d; pfb[0] = s.db; pf[1] = s.s; pfb[1] = s.sb;
+    };
+    static bool attn_attr = false;
+    if (!attn_attr) {
+        GTB_CUDA(cudaFuncSetAttribute(k_fd_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attn_attr = true;
+    }
+    const size_t attn_smem = ((sizeof(FdAttnSmem) + 15) & ~(size_t)15) + (size_t)((((c.max_ctx + FD_CHUNKS - 1) / FD_CHUNKS + 31) & ~31) + 64) * 4;
+    if (attn_smem > 64 * 1024) return fail(GTB_ERR_STATE, "fast_decode: max_ctx too large for the attention kernel's score buffer");
+    int r;
+    for (int li = 0; li < L; li++) {
+        LayerW& l = e->L[li];
+        FdArgs a{};
+        a.K = E; a.n_rows = E + 2 * KV; a.w = (const uint4*)l.qkv_data; a.ws = l.qkv_sc; a.out = e->rqkv;
+        a.normw = l.attn_norm; a.res_out = e->xres; a.st = e->st;
+        if (li == 0) { a.emb_w = (const uint8_t*)e->embed->data; a.emb_s = e->embed->scales; a.tokens = e->tokens; a.emb_dt = WT; }
+        else { a.src0 = e->hres; a.src1 = e->rd; }
+        set_pf(a.pf, a.pf_bytes, 4 * li + 0);
+        if ((r = launch_fd<WT, FD_NORM, FD_RAW>(a, G))) return r;
+        FdAttnArgs t{};
+        t.rqkv = e->rqkv; t.n_embd = E; t.kv_dim = KV; t.gsz = e->gsz; t.kq = l.kq; t.ks = l.ks; t.vq = l.vq; t.vs = l.vs;
+        t.rope_cos = e->rope_cos; t.rope_sin = e->rope_sin; t.st = e->st; t.parts = e->fd_parts; t.counters = e->fd_cnt;
+        t.out = e->fd_attn;
+        GTB_CUDA(fd_launch(k_fd_attn, c.n_heads * FD_CHUNKS, attn_smem, t));
+        GTB_LAUNCHED();
+        FdArgs o{};
+        o.K = E; o.n_rows = E; o.w = (const uint4*)l.o->data; o.ws = l.o->scales; o.out = e->ro; o.in = e->fd_attn;
+        set_pf(o.pf, o.pf_bytes, 4 * li + 1);
+        if ((r = launch_fd<WT, FD_CODES, FD_RAW>(o, G))) return r;
+        FdArgs g{};
+        g.K = E; g.n_rows = 2 * F; g.w = (const uint4*)l.gu_data; g.ws = l.gu_sc; g.n_ffn = F; g.act_out = e->fd_act;
+        g.src0 = e->xres; g.src1 = e->ro; g.normw = l.ffn_norm; g.res_out = e->hres;
+        set_pf(g.pf, g.pf_bytes, 4 * li + 2);
+        if ((r = launch_fd<WT, FD_NORM, FD_SILU>(g, F / 32))) return r;
+        FdArgs d{};
+        d.K = F; d.n_rows = E; d.w = (const uint4*)l.down->data; d.ws = l.down->scales; d.out = e->rd; d.in = e->fd_act;
+        set_pf(d.pf, d.pf_bytes, 4 * li + 3);
+        if ((r = launch_fd<WT, FD_CODES, FD_RAW>(d, G))) return r;
+    }
+    if (with_head) {
+        FdArgs hd{};
+        hd.K = E; hd.n_rows = c.n_vocab; hd.w = (const uint4*)e->lm_head->data; hd.ws = e->lm_head->scales; hd.out = e->logits;
+        hd.src0 = e->hres; hd.src1 = e->rd; hd.normw = e->final_norm; hd.res_out = e->xfinal;
+        hd.arg_val = e->fd_argv; hd.arg_idx = e->fd_argi; hd.counter = e->fd_cnt + c.n_heads; hd.tok_out = e->tokens; hd.st = e->st; hd.eos_id = eos_id;
+        set_pf(hd.pf, hd.pf_bytes, 4 * L);
+        if ((r = launch_fd<WT, FD_NORM, FD_ARGMAX>(hd, 2 * G))) return r;
+    } else {
+        k_advance<<<1, 1, 0, ctx().stream>>>(e->st);
+        GTB_LAUNCHED();
+    }
+    return GTB_OK;
+}
+
 int enqueue_row_dt(gtb_engine* e, bool with_head, int eos_id) {
+    if (e->fast) {
+        if (e->cfg.wdtype == GTB_Q8) return enqueue_row_fast<DT_Q8>(e, with_head, eos_id);
+        if (e->cfg.wdtype == GTB_Q4) return enqueue_row_fast<DT_Q4>(e, with_head, eos_id);
+        return fail(GTB_ERR_STATE, "fast_decode is built for Q8-activation models (Q8, Q4 weights)");
+    }
     switch (e->cfg.wdtype) {
         case GTB_F16: return enqueue_row<DT_F16>(e, with_head, eos_id);
         case GTB_Q8: return enqueue_row<DT_Q8>(e, with_head, eos_id);
@@ -500,7 +623,7 @@ bool mega_ok(const gtb_engine* e) {
     const gtb_model_config& c = e->cfg;
     // the persistent kernel is specialised for the TinyLlama dimensions (tinyllama.cpp:12-20); anything else takes
     // the one-kernel-per-phase path
-    return e->use_mega && !e->capture && c.n_embd == ME && c.n_ffn == MF && c.n_heads == MH && c.n_groups * MGSZ == MH &&
+    return e->use_mega && !e->fast && !e->capture && c.n_embd == ME && c.n_ffn == MF && c.n_heads == MH && c.n_groups * MGSZ == MH &&
            e->grid >= MH * 4 && e->grid <= 1024 && c.max_ctx <= 4 * MT && attn_scratch_bytes(c.max_ctx) <= (size_t)PS_BYTES;
 }
 
@@ -642,6 +765,11 @@ int gtb_engine_create(gtb_engine_t* out, const gtb_model_config* cfg) {
     r |= dalloc((void**)&e->rqkv, (size_t)(E + 2 * KV) * 4); r |= dalloc((void**)&e->rattn, E * 4); r |= dalloc((void**)&e->ro, E * 4);
     r |= dalloc((void**)&e->rg, F * 4); r |= dalloc((void**)&e->ru, F * 4); r |= dalloc((void**)&e->rd, E * 4);
     r |= dalloc((void**)&e->logits, (size_t)cfg->n_vocab * 4);
+    r |= dalloc((void**)&e->fd_parts, (size_t)cfg->n_heads * FD_CHUNKS * FD_PART * 4);
+    r |= dalloc((void**)&e->fd_cnt, (size_t)(cfg->n_heads + 1) * 4);
+    r |= dalloc((void**)&e->fd_attn.codes, E); r |= dalloc((void**)&e->fd_attn.ad, E / 32 * 4); r |= dalloc((void**)&e->fd_attn.n7, E / 32 * 4);
+    r |= dalloc((void**)&e->fd_act.codes, F); r |= dalloc((void**)&e->fd_act.ad, F / 32 * 4); r |= dalloc((void**)&e->fd_act.n7, F / 32 * 4);
+    r |= dalloc((void**)&e->fd_argv, 1024 * 4); r |= dalloc((void**)&e->fd_argi, 1024 * 4);
     r |= dalloc((void**)&e->tokens, (size_t)(MC + 2) * 4);
     r |= dalloc((void**)&e->st, sizeof(DevState));
     e->capw = (F > E) ? F : E;
@@ -693,6 +821,9 @@ int gtb_engine_destroy(gtb_engine_t e) {
     for (void* b : bufs) cudaFree(b);
     if (e->pf) pf_destroy(e->pf);
     cudaFree(e->pf_cap);
+    cudaFree(e->fd_parts); cudaFree(e->fd_cnt); cudaFree(e->fd_argv); cudaFree(e->fd_argi);
+    cudaFree(e->fd_attn.codes); cudaFree(e->fd_attn.ad); cudaFree(e->fd_attn.n7);
+    cudaFree(e->fd_act.codes); cudaFree(e->fd_act.ad); cudaFree(e->fd_act.n7);
     delete e;
     return GTB_OK;
 }
@@ -1071,6 +1202,8 @@ int gtb_engine_set_option(gtb_engine_t e, const char* name, int value) {
     if (!strcmp(name, "mega")) { e->use_mega = value != 0; return GTB_OK; }
     if (!strcmp(name, "pf_ahead")) { GTB_ARG(value >= 0 && value <= 64); e->pf_ahead = value; return GTB_OK; }
     if (!strcmp(name, "prof")) { e->prof = value != 0; return GTB_OK; }
+    if (!strcmp(name, "fast_decode")) { e->fast = value != 0; drop_graphs(e); return GTB_OK; }
+    if (!strcmp(name, "fd_ahead")) { GTB_ARG(value >= 0 && value <= 16); e->fd_ahead = value; drop_graphs(e); return GTB_OK; }
     if (!strcmp(name, "pf_layers")) { GTB_ARG(value >= 0); e->pf_layers = value; return GTB_OK; }
     if (!strcmp(name, "pf_fused")) { e->pf_fused = value != 0; return GTB_OK; }
     if (!strcmp(name, "pf_2cta")) { e->pf_2cta = value != 0; return GTB_OK; }
