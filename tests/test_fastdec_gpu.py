@@ -32,11 +32,15 @@ def rel(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
-@pytest.mark.parametrize("graph", [1, 0], ids=["graph", "eager"])
+MODES = {"persistent": {"fd_mega": 1}, "pdl-graph": {"fd_mega": 0, "graph": 1}, "pdl-eager": {"fd_mega": 0, "graph": 0}}
+
+
+@pytest.mark.parametrize("mode", list(MODES))
 @pytest.mark.parametrize("wdt", [Q8, Q4])
 @pytest.mark.parametrize("n_prompt", [100, 64, 7])
-def test_fast_rows_mini(capi, checker, wdt, n_prompt, graph):
-    """Every row of the prompt through the fast kernels (row-at-a-time, like the reference's own prefill): logits of the
+def test_fast_rows_mini(capi, checker, wdt, n_prompt, mode):
+    """The PDL-chained kernels (the default) and the persistent cooperative kernel (k_fd_mega) run the same phase code.
+    Every row of the prompt through the fast kernels (row-at-a-time, like the reference's own prefill): logits of the
     last row within the reference's own build-to-build spread; then the next row through the ORDER-EXACT kernels on top of
     the K/V cache the fast kernels wrote (catches any cache-layout mistake)."""
     cfg = W.mini_config(n_layers=3, n_vocab=300)
@@ -45,7 +49,8 @@ def test_fast_rows_mini(capi, checker, wdt, n_prompt, graph):
     cm = checker.model(cfg, max_ctx, wdt).load(wl)
     e = capi.Engine(cfg, max_ctx, wdt).load(wl)
     e.set_option("fast_decode", 1)
-    e.set_option("graph", graph)
+    for k, v in MODES[mode].items():
+        e.set_option(k, v)
     assert not e.uses_megakernel()
     prompt = W.synth_prompt(5, n_prompt, cfg.n_vocab)
     want = cm.logits(prompt, 0)
@@ -65,8 +70,9 @@ def test_fast_rows_mini(capi, checker, wdt, n_prompt, graph):
     e.close(); cm.close()
 
 
+@pytest.mark.parametrize("mega", [1, 0])
 @pytest.mark.parametrize("wdt", [Q8, Q4])
-def test_fast_single_row_on_exact_cache(capi, checker, wdt):
+def test_fast_single_row_on_exact_cache(capi, checker, wdt, mega):
     """One fast row on top of a K/V cache written by the exact path: a single row's worth of reordering noise only."""
     cfg = W.mini_config(n_layers=3, n_vocab=300)
     wl = list(W.synth_weights(cfg, wdt, seed=4))
@@ -76,13 +82,15 @@ def test_fast_single_row_on_exact_cache(capi, checker, wdt):
     want = cm.logits(prompt, 0)
     e.prefill(prompt[:-1])
     e.set_option("fast_decode", 1)
+    e.set_option("fd_mega", mega)
     got = e.logits(prompt, prompt.size - 1)
     sens = max(float(SENS[k]) for k in SENS.files if k.startswith("mini_") and k.endswith("_logits"))
     assert rel(got, want) <= SLACK * sens + ABS, rel(got, want)
     e.close(); cm.close()
 
 
-def test_fast_greedy_loop_and_positions(capi):
+@pytest.mark.parametrize("mega", [1, 0])
+def test_fast_greedy_loop_and_positions(capi, mega):
     """decode() under fast_decode: device-side greedy loop, positions advance, tokens are valid ids, and the sequence is
     reproducible (the kernels have no run-to-run nondeterminism: no float atomics)."""
     cfg = W.mini_config(n_layers=2, n_vocab=300)
@@ -90,6 +98,7 @@ def test_fast_greedy_loop_and_positions(capi):
     for _ in range(2):
         e = capi.Engine(cfg, 256, Q4).load(W.synth_weights(cfg, Q4, seed=3))
         e.set_option("fast_decode", 1)
+        e.set_option("fd_mega", mega)
         prompt = W.synth_prompt(2, 40, cfg.n_vocab)
         e.prefill(prompt)
         assert e.position() == 40
@@ -109,4 +118,38 @@ def test_fast_decode_rejects_fp16_models(capi):
     e.set_option("fast_decode", 1)
     with pytest.raises(capi.GtbError):
         e.logits(np.array([1, 2, 3], np.int32), 0)
+    e.close()
+
+
+def test_fast_persistent_equals_pdl_chain(capi):
+    """Both launch schemes run the same phase functions; with the same number of position chunks they would be bit-identical.
+    They use 4 and 8 chunks, so the comparison is a tolerance one -- but a much tighter one than against the reference:
+    only the attention combine differs."""
+    cfg = W.mini_config(n_layers=2, n_vocab=300)
+    wl = list(W.synth_weights(cfg, Q4, seed=8))
+    prompt = W.synth_prompt(4, 90, cfg.n_vocab)
+    out = []
+    for mega in (1, 0):
+        e = capi.Engine(cfg, 128, Q4).load(wl)
+        e.prefill(prompt[:-1])
+        e.set_option("fast_decode", 1)
+        e.set_option("fd_mega", mega)
+        out.append(e.logits(prompt, prompt.size - 1))
+        e.close()
+    assert rel(out[0], out[1]) < 0.05, rel(out[0], out[1])
+
+
+def test_fast_generate_with_eos(capi):
+    """generate() under fast_decode stops at the EOS id like the exact path (tinyllama.cpp:426)."""
+    cfg = W.mini_config(n_layers=2, n_vocab=300)
+    wl = list(W.synth_weights(cfg, Q4, seed=3))
+    prompt = W.synth_prompt(2, 12, cfg.n_vocab)
+    e = capi.Engine(cfg, 64, Q4).load(wl)
+    e.set_option("fast_decode", 1)
+    free = e.generate(prompt, 10)
+    assert free.size == 22
+    eos = int(free[12 + 4])
+    first = 12 + int(np.argmax(free[12:] == eos))
+    stopped = e.generate(prompt, 10, eos_id=eos)
+    assert np.array_equal(stopped, free[: first + 1]), (stopped, free)
     e.close()

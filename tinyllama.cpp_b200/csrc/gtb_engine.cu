@@ -358,6 +358,13 @@ struct gtb_engine {
     float* fd_argv = nullptr;        // per-CTA maxima of the head kernel
     int* fd_argi = nullptr;
     int fd_ahead = 3;                // L2 look-ahead distance in GEMV steps
+    int fd_prof_cta = 0;             // which CTA writes the "prof" stamps of k_fd_mega
+    bool fd_mega = false;            // fast decode as one persistent cooperative kernel (k_fd_mega, measured slower); false: PDL-chained kernels
+    FdArgs* d_fd_gemv = nullptr;     // phase arguments of k_fd_mega
+    FdAttnArgs* d_fd_attn = nullptr;
+    unsigned* fd_bar = nullptr;      // grid-barrier arrival counter
+    bool fd_args_valid = false, fd_args_head = false;
+    int fd_args_eos = -2;
     int pf_layers = 0;               // debug: run only the first pf_layers layers (0 = all)
     int pf_fused = 1;                // RoPE/KV append and SiLU*up inside the GEMM epilogues
     int pf_2cta = 0;                 // CTA-pair GEMM kernel
@@ -504,80 +511,130 @@ int launch_fd(const FdArgs& a, int grid) {
     return fail(GTB_ERR_STATE, "fast_decode: rows longer than 6144 elements are not instantiated");
 }
 
-// one row through the order-free kernels: 5 launches per layer (+ the head)
-template <int WT>
-int enqueue_row_fast(gtb_engine* e, bool with_head, int eos_id) {
+// arguments of every phase of one row: gv = [4 * L (+ 1)] GEMV phases in launch order, av = [L] attention phases
+int build_fast_args(gtb_engine* e, bool with_head, int eos_id, std::vector<FdArgs>& gv, std::vector<FdAttnArgs>& av) {
     const gtb_model_config& c = e->cfg;
     const int E = c.n_embd, F = c.n_ffn, KV = e->kv_dim, L = c.n_layers;
     const int wd = c.wdtype;
-    const int G = ctx().sm_count;
-    // GEMV steps in launch order (4 per layer + head): what the L2 look-ahead walks
-    struct Step { const void* d; size_t db; const void* s; size_t sb; };
-    std::vector<Step> steps;
-    for (int li = 0; li < L; li++) {
-        LayerW& l = e->L[li];
-        steps.push_back({l.qkv_data, weight_data_bytes(wd, E + 2 * KV, E), l.qkv_sc, weight_scale_bytes(wd, E + 2 * KV, E)});
-        steps.push_back({l.o->data, weight_data_bytes(wd, E, E), l.o->scales, weight_scale_bytes(wd, E, E)});
-        steps.push_back({l.gu_data, weight_data_bytes(wd, 2 * F, E), l.gu_sc, weight_scale_bytes(wd, 2 * F, E)});
-        steps.push_back({l.down->data, weight_data_bytes(wd, E, F), l.down->scales, weight_scale_bytes(wd, E, F)});
-    }
-    if (with_head) steps.push_back({e->lm_head->data, weight_data_bytes(wd, c.n_vocab, E), e->lm_head->scales, weight_scale_bytes(wd, c.n_vocab, E)});
-    const int ns = (int)steps.size();
-    auto set_pf = [&](const void* (&pf)[2], size_t (&pfb)[2], int step) {
-        pf[0] = pf[1] = nullptr; pfb[0] = pfb[1] = 0;
-        if (e->fd_ahead <= 0) return;
-        const Step& s = steps[(step + e->fd_ahead) % ns];
-        pf[0] = s.d; pfb[0] = s.db; pf[1] = s.s; pfb[1] = s.sb;
-    };
-    static bool attn_attr = false;
-    if (!attn_attr) {
-        GTB_CUDA(cudaFuncSetAttribute(k_fd_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attn_attr = true;
-    }
-    const size_t attn_smem = ((sizeof(FdAttnSmem) + 15) & ~(size_t)15) + (size_t)((((c.max_ctx + FD_CHUNKS - 1) / FD_CHUNKS + 31) & ~31) + 64) * 4;
-    if (attn_smem > 64 * 1024) return fail(GTB_ERR_STATE, "fast_decode: max_ctx too large for the attention kernel's score buffer");
-    int r;
+    gv.clear(); av.clear();
     for (int li = 0; li < L; li++) {
         LayerW& l = e->L[li];
         FdArgs a{};
         a.K = E; a.n_rows = E + 2 * KV; a.w = (const uint4*)l.qkv_data; a.ws = l.qkv_sc; a.out = e->rqkv;
         a.normw = l.attn_norm; a.res_out = e->xres; a.st = e->st;
-        if (li == 0) { a.emb_w = (const uint8_t*)e->embed->data; a.emb_s = e->embed->scales; a.tokens = e->tokens; a.emb_dt = WT; }
+        if (li == 0) { a.emb_w = (const uint8_t*)e->embed->data; a.emb_s = e->embed->scales; a.tokens = e->tokens; a.emb_dt = wd == GTB_Q8 ? DT_Q8 : DT_Q4; }
         else { a.src0 = e->hres; a.src1 = e->rd; }
-        set_pf(a.pf, a.pf_bytes, 4 * li + 0);
-        if ((r = launch_fd<WT, FD_NORM, FD_RAW>(a, G))) return r;
+        gv.push_back(a);
         FdAttnArgs t{};
         t.rqkv = e->rqkv; t.n_embd = E; t.kv_dim = KV; t.gsz = e->gsz; t.kq = l.kq; t.ks = l.ks; t.vq = l.vq; t.vs = l.vs;
         t.rope_cos = e->rope_cos; t.rope_sin = e->rope_sin; t.st = e->st; t.parts = e->fd_parts; t.counters = e->fd_cnt;
         t.out = e->fd_attn;
-        GTB_CUDA(fd_launch(k_fd_attn, c.n_heads * FD_CHUNKS, attn_smem, t));
-        GTB_LAUNCHED();
+        av.push_back(t);
         FdArgs o{};
         o.K = E; o.n_rows = E; o.w = (const uint4*)l.o->data; o.ws = l.o->scales; o.out = e->ro; o.in = e->fd_attn;
-        set_pf(o.pf, o.pf_bytes, 4 * li + 1);
-        if ((r = launch_fd<WT, FD_CODES, FD_RAW>(o, G))) return r;
+        gv.push_back(o);
         FdArgs g{};
         g.K = E; g.n_rows = 2 * F; g.w = (const uint4*)l.gu_data; g.ws = l.gu_sc; g.n_ffn = F; g.act_out = e->fd_act;
         g.src0 = e->xres; g.src1 = e->ro; g.normw = l.ffn_norm; g.res_out = e->hres;
-        set_pf(g.pf, g.pf_bytes, 4 * li + 2);
-        if ((r = launch_fd<WT, FD_NORM, FD_SILU>(g, F / 32))) return r;
+        gv.push_back(g);
         FdArgs d{};
         d.K = F; d.n_rows = E; d.w = (const uint4*)l.down->data; d.ws = l.down->scales; d.out = e->rd; d.in = e->fd_act;
-        set_pf(d.pf, d.pf_bytes, 4 * li + 3);
-        if ((r = launch_fd<WT, FD_CODES, FD_RAW>(d, G))) return r;
+        gv.push_back(d);
     }
     if (with_head) {
         FdArgs hd{};
         hd.K = E; hd.n_rows = c.n_vocab; hd.w = (const uint4*)e->lm_head->data; hd.ws = e->lm_head->scales; hd.out = e->logits;
         hd.src0 = e->hres; hd.src1 = e->rd; hd.normw = e->final_norm; hd.res_out = e->xfinal;
         hd.arg_val = e->fd_argv; hd.arg_idx = e->fd_argi; hd.counter = e->fd_cnt + c.n_heads; hd.tok_out = e->tokens; hd.st = e->st; hd.eos_id = eos_id;
-        set_pf(hd.pf, hd.pf_bytes, 4 * L);
-        if ((r = launch_fd<WT, FD_NORM, FD_ARGMAX>(hd, 2 * G))) return r;
+        gv.push_back(hd);
+    }
+    // L2 look-ahead: phase i pushes the weights of GEMV phase i + fd_ahead (cyclic: the next row starts over) towards L2
+    const int ns = (int)gv.size();
+    for (int i = 0; i < ns && e->fd_ahead > 0; i++) {
+        const FdArgs& t = gv[(i + e->fd_ahead) % ns];
+        gv[i].pf[0] = t.w; gv[i].pf_bytes[0] = weight_data_bytes(wd, t.n_rows, t.K);
+        gv[i].pf[1] = t.ws; gv[i].pf_bytes[1] = weight_scale_bytes(wd, t.n_rows, t.K);
+    }
+    return GTB_OK;
+}
+
+// one row through the order-free kernels: 5 launches per layer (+ the head), chained with programmatic dependent launch
+template <int WT>
+int enqueue_row_fast(gtb_engine* e, bool with_head, int eos_id) {
+    const gtb_model_config& c = e->cfg;
+    const int L = c.n_layers, G = ctx().sm_count;
+    std::vector<FdArgs> gv;
+    std::vector<FdAttnArgs> av;
+    int r = build_fast_args(e, with_head, eos_id, gv, av);
+    if (r) return r;
+    static bool attn_attr = false;
+    if (!attn_attr) {
+        GTB_CUDA(cudaFuncSetAttribute(k_fd_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attn_attr = true;
+    }
+    const size_t attn_smem = fd_attn_smem(c.max_ctx, FD_CHUNKS);
+    if (attn_smem > 64 * 1024) return fail(GTB_ERR_STATE, "fast_decode: max_ctx too large for the attention kernel's score buffer");
+    for (int li = 0; li < L; li++) {
+        if ((r = launch_fd<WT, FD_NORM, FD_RAW>(gv[4 * li + 0], G))) return r;
+        GTB_CUDA(fd_launch(k_fd_attn, c.n_heads * FD_CHUNKS, attn_smem, av[li], c.n_heads));
+        GTB_LAUNCHED();
+        if ((r = launch_fd<WT, FD_CODES, FD_RAW>(gv[4 * li + 1], G))) return r;
+        if ((r = launch_fd<WT, FD_NORM, FD_SILU>(gv[4 * li + 2], c.n_ffn / 32))) return r;
+        if ((r = launch_fd<WT, FD_CODES, FD_RAW>(gv[4 * li + 3], G))) return r;
+    }
+    if (with_head) {
+        if ((r = launch_fd<WT, FD_NORM, FD_ARGMAX>(gv[4 * L], 2 * G))) return r;
     } else {
         k_advance<<<1, 1, 0, ctx().stream>>>(e->st);
         GTB_LAUNCHED();
     }
     return GTB_OK;
+}
+
+// the same phases as one persistent cooperative launch for all rows (k_fd_mega)
+bool fast_mega_ok(const gtb_engine* e) {
+    const gtb_model_config& c = e->cfg;
+    return e->fast && e->fd_mega && !e->capture && c.wdtype != GTB_F16 && c.n_embd <= 2048 && c.n_ffn <= 6144 &&
+           fd_mega_smem(c.n_embd, c.n_ffn, c.max_ctx) <= 100 * 1024;
+}
+
+template <int WT>
+int launch_fast_mega(gtb_engine* e, FdMegaParams& p) {
+    const gtb_model_config& c = e->cfg;
+    const size_t smem = fd_mega_smem(c.n_embd, c.n_ffn, c.max_ctx);
+    static bool attr_done = false;
+    if (!attr_done) {
+        GTB_CUDA(cudaFuncSetAttribute(k_fd_mega<WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        int nb = 0;
+        GTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fd_mega<WT>, FD_NT, smem));
+        if (nb < 1) return fail(GTB_ERR_CUDA, "k_fd_mega does not fit on an SM");
+        attr_done = true;
+    }
+    void* args[] = {&p};
+    GTB_CUDA(cudaLaunchCooperativeKernel((const void*)k_fd_mega<WT>, dim3(ctx().sm_count), dim3(FD_NT), args, smem, ctx().stream));
+    GTB_LAUNCHED();
+    return GTB_OK;
+}
+
+int run_rows_fast_mega(gtb_engine* e, int n_body, int n_head, int eos_id) {
+    const gtb_model_config& c = e->cfg;
+    const bool with_head = n_head > 0;
+    if (!e->fd_args_valid || e->fd_args_head != with_head || e->fd_args_eos != eos_id) {
+        std::vector<FdArgs> gv;
+        std::vector<FdAttnArgs> av;
+        int r = build_fast_args(e, with_head, eos_id, gv, av);
+        if (r) return r;
+        GTB_CUDA(cudaMemcpyAsync(e->d_fd_gemv, gv.data(), gv.size() * sizeof(FdArgs), cudaMemcpyHostToDevice, ctx().stream));
+        GTB_CUDA(cudaMemcpyAsync(e->d_fd_attn, av.data(), av.size() * sizeof(FdAttnArgs), cudaMemcpyHostToDevice, ctx().stream));
+        GTB_CUDA(cudaStreamSynchronize(ctx().stream));          // the vectors are locals
+        e->fd_args_valid = true; e->fd_args_head = with_head; e->fd_args_eos = eos_id;
+    }
+    GTB_CUDA(cudaMemsetAsync(e->fd_bar, 0, 128, ctx().stream));
+    FdMegaParams p{};
+    p.gemv = e->d_fd_gemv; p.attn = e->d_fd_attn; p.n_layers = c.n_layers; p.n_heads = c.n_heads;
+    p.n_body = n_body; p.n_head = n_head; p.bar = e->fd_bar; p.bar_base = 0; p.st = e->st;
+    p.prof = e->prof ? e->d_prof : nullptr; p.prof_cta = e->fd_prof_cta;
+    return (c.wdtype == GTB_Q8) ? launch_fast_mega<DT_Q8>(e, p) : launch_fast_mega<DT_Q4>(e, p);
 }
 
 int enqueue_row_dt(gtb_engine* e, bool with_head, int eos_id) {
@@ -594,6 +651,7 @@ int enqueue_row_dt(gtb_engine* e, bool with_head, int eos_id) {
 }
 
 void drop_graphs(gtb_engine* e) {
+    e->fd_args_valid = false;
     if (e->g_body) { cudaGraphExecDestroy(e->g_body); e->g_body = nullptr; }
     if (e->g_head) { cudaGraphExecDestroy(e->g_head); e->g_head = nullptr; }
 }
@@ -685,6 +743,7 @@ int run_rows(gtb_engine* e, int n_body, int n_head, int eos_id) {
     cudaStream_t st = ctx().stream;
     if (n_body + n_head <= 0) return GTB_OK;
     if (mega_ok(e)) return run_rows_mega(e, n_body, n_head, eos_id);
+    if (fast_mega_ok(e)) return run_rows_fast_mega(e, n_body, n_head, eos_id);
     if (e->use_graph && !e->capture) {
         if (n_body > 0 && !e->g_body) { int r = build_graph(e, false, -1, &e->g_body, &e->launches_body); if (r) return r; }
         if (n_head > 0 && (!e->g_head || e->g_eos != eos_id)) {
@@ -770,6 +829,8 @@ int gtb_engine_create(gtb_engine_t* out, const gtb_model_config* cfg) {
     r |= dalloc((void**)&e->fd_attn.codes, E); r |= dalloc((void**)&e->fd_attn.ad, E / 32 * 4); r |= dalloc((void**)&e->fd_attn.n7, E / 32 * 4);
     r |= dalloc((void**)&e->fd_act.codes, F); r |= dalloc((void**)&e->fd_act.ad, F / 32 * 4); r |= dalloc((void**)&e->fd_act.n7, F / 32 * 4);
     r |= dalloc((void**)&e->fd_argv, 1024 * 4); r |= dalloc((void**)&e->fd_argi, 1024 * 4);
+    r |= dalloc((void**)&e->d_fd_gemv, (size_t)(4 * cfg->n_layers + 1) * sizeof(FdArgs));
+    r |= dalloc((void**)&e->d_fd_attn, (size_t)cfg->n_layers * sizeof(FdAttnArgs)); r |= dalloc((void**)&e->fd_bar, 128);
     r |= dalloc((void**)&e->tokens, (size_t)(MC + 2) * 4);
     r |= dalloc((void**)&e->st, sizeof(DevState));
     e->capw = (F > E) ? F : E;
@@ -822,6 +883,7 @@ int gtb_engine_destroy(gtb_engine_t e) {
     if (e->pf) pf_destroy(e->pf);
     cudaFree(e->pf_cap);
     cudaFree(e->fd_parts); cudaFree(e->fd_cnt); cudaFree(e->fd_argv); cudaFree(e->fd_argi);
+    cudaFree(e->d_fd_gemv); cudaFree(e->d_fd_attn); cudaFree(e->fd_bar);
     cudaFree(e->fd_attn.codes); cudaFree(e->fd_attn.ad); cudaFree(e->fd_attn.n7);
     cudaFree(e->fd_act.codes); cudaFree(e->fd_act.ad); cudaFree(e->fd_act.n7);
     delete e;
@@ -1203,7 +1265,9 @@ int gtb_engine_set_option(gtb_engine_t e, const char* name, int value) {
     if (!strcmp(name, "pf_ahead")) { GTB_ARG(value >= 0 && value <= 64); e->pf_ahead = value; return GTB_OK; }
     if (!strcmp(name, "prof")) { e->prof = value != 0; return GTB_OK; }
     if (!strcmp(name, "fast_decode")) { e->fast = value != 0; drop_graphs(e); return GTB_OK; }
-    if (!strcmp(name, "fd_ahead")) { GTB_ARG(value >= 0 && value <= 16); e->fd_ahead = value; drop_graphs(e); return GTB_OK; }
+    if (!strcmp(name, "fd_ahead")) { GTB_ARG(value >= 0 && value <= 16); e->fd_ahead = value; drop_graphs(e); e->fd_args_valid = false; return GTB_OK; }
+    if (!strcmp(name, "fd_prof_cta")) { GTB_ARG(value >= 0); e->fd_prof_cta = value; return GTB_OK; }
+    if (!strcmp(name, "fd_mega")) { e->fd_mega = value != 0; return GTB_OK; }
     if (!strcmp(name, "pf_layers")) { GTB_ARG(value >= 0); e->pf_layers = value; return GTB_OK; }
     if (!strcmp(name, "pf_fused")) { e->pf_fused = value != 0; return GTB_OK; }
     if (!strcmp(name, "pf_2cta")) { e->pf_2cta = value != 0; return GTB_OK; }

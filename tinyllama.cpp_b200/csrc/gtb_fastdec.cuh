@@ -70,18 +70,32 @@ __device__ __forceinline__ float fd_block_sum(float v, float* red) {
     return t;
 }
 
-// Q8 encode (quants.h:52-66) of a block held as quads: 8 adjacent lanes x 4 consecutive elements.  Returns the decoded
+// roundf (half away from zero) without the slow path: exact except for |v| within one ulp below a .5 boundary
+__device__ __forceinline__ int fd_round_away(float v) { return (int)(v + copysignf(0.5f, v)); }
+
+// Q8 encode (quants.h:52-66; fast division: the order-free path does not promise the last bit) of a block held as quads: 8 adjacent lanes x 4 consecutive elements.  Returns the decoded
 // fp16 scale; q[] = codes.  All 32 lanes must call.
 __device__ __forceinline__ float fd_quad_encode(const float (&x)[4], int (&q)[4]) {
     float m = fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3])));
     m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
     m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
     m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
-    const float d = __fdiv_rn(m, 127.0f);
-    const float s = (d != 0.0f) ? __fdiv_rn(1.0f, d) : 0.0f;
+    const float s = (m > 0.0f) ? __fdividef(127.0f, m) : 0.0f;
 #pragma unroll
-    for (int i = 0; i < 4; i++) q[i] = (int)roundf(__fmul_rn(x[i], s));
-    return h2f(f2h(d));
+    for (int i = 0; i < 4; i++) q[i] = fd_round_away(x[i] * s);
+    return h2f(f2h(m * (1.0f / 127.0f)));
+}
+// the same for a block held one element per lane; returns the code, *d = decoded fp16 scale
+__device__ __forceinline__ int fd_lane_encode(float x, float* d) {
+    const float m = warp_max(fabsf(x));
+    const float s = (m > 0.0f) ? __fdividef(127.0f, m) : 0.0f;
+    *d = h2f(f2h(m * (1.0f / 127.0f)));
+    return fd_round_away(x * s);
+}
+__device__ __forceinline__ float fd_lane_roundtrip(float x) {
+    float d;
+    const int q = fd_lane_encode(x, &d);
+    return (float)q * d;
 }
 __device__ __forceinline__ void fd_quad_roundtrip(float (&x)[4]) {
     int q[4];
@@ -198,9 +212,10 @@ static __host__ __device__ inline size_t fd_gemv_smem(int K, bool norm) {
 }
 
 // NBL = blocks per lane (K <= 32 * 32 * NBL), R = rows per warp pass
-template <int WT, int PRO, int EPI, int NBL, int R>
-__global__ void __launch_bounds__(FD_NT, 2) k_fd_gemv(FdArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
+// `sync()` orders this phase after its producer: griddepcontrol.wait in the one-kernel-per-phase chain, a grid barrier in the
+// persistent kernel.  Everything before it touches only weights.
+template <int WT, int PRO, int EPI, int NBL, int R, typename Sync>
+__device__ __forceinline__ void fd_gemv_phase(const FdArgs& a, unsigned char* smem, Sync& sync, int pos_in) {
     const int K = a.K, nb = K / 32;
     FdStaged sv;
     sv.aw = reinterpret_cast<uint32_t*>(smem);
@@ -211,7 +226,8 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fd_gemv(FdArgs a) {
     float* scratch = reinterpret_cast<float*>(p + ((PRO == FD_NORM) ? (size_t)K * 4 : 0));      // 64 floats
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
-    fd_launch_dependents();
+    sync.arrive();
+    sync.stamp();
     // ---- work that does not depend on the previous kernel: look-ahead L2 prefetch, first weight batch into registers
     if (tid < 2 && a.pf[tid]) {
         const size_t per = ((a.pf_bytes[tid] + gridDim.x - 1) / gridDim.x + 127) & ~(size_t)127;
@@ -220,7 +236,8 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fd_gemv(FdArgs a) {
     }
     // virtual rows of this CTA: RAW/ARGMAX: an even slice of the matrix; SILU: unit = 32 gate rows + 32 up rows
     int v0, v1, unit = blockIdx.x;
-    if (EPI == FD_SILU) { v0 = 0; v1 = 64; }
+    const int n_units = (EPI == FD_SILU) ? a.n_ffn / 32 : 1;
+    if (EPI == FD_SILU) { v0 = 0; v1 = (unit < n_units) ? 64 : 0; }          // (a grid larger than the number of units: idle CTAs)
     else { v0 = (int)(((long long)blockIdx.x * a.n_rows) / gridDim.x); v1 = (int)(((long long)(blockIdx.x + 1) * a.n_rows) / gridDim.x); }
     auto rows_of = [&](int v, int (&row)[R]) {
 #pragma unroll
@@ -236,65 +253,88 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fd_gemv(FdArgs a) {
     int v = v0 + wid * R;
     rows_of(v, row);
     fd_load_batch<WT, NBL, R>(bt, a.w, a.ws, row, nb);
+    constexpr int NQ = (PRO == FD_NORM) ? NBL : 1;           // quads per thread of the NORM prologue (K <= 1024 * NBL)
+    uint2 nw[NQ];                                            // norm weights are immutable: loaded before the wait
+    if (PRO == FD_NORM) {
+#pragma unroll
+        for (int it = 0; it < NQ; it++) {
+            const int qd = it * FD_NT + tid;
+            nw[it] = *reinterpret_cast<const uint2*>(a.normw + 4 * ((qd < K / 4) ? qd : 0));
+        }
+    }
 
-    fd_wait_prior();
+    sync.wait();
+    sync.stamp();
+    const int pos = (pos_in >= 0) ? pos_in : ((PRO == FD_NORM && a.emb_w) ? __ldcg(&a.st->pos) : 0);
     // ---- prologue: the staged input vector
     if (PRO == FD_NORM) {
         // x = E(res + E(delta)) (ops.h:870-898) or the embedding row (ops.h:514-564); y = E(x / (rms(x) + 1e-6) * w) (ops.h:762-804)
+        // NQ quads per thread, all loads of the pass in flight at once, x stays in registers
         const int nq = K / 4;
+        float x[NQ][4];
         float ssq = 0.0f;
-        const size_t erow = a.emb_w ? (size_t)__ldcg(a.tokens + __ldcg(&a.st->pos)) : 0;
-        for (int base = 0; base < nq; base += FD_NT) {
-            const int qd = base + tid;
-            const bool valid = qd < nq;
-            const int e0 = 4 * (valid ? qd : 0);
-            float x[4];
-            if (a.emb_w) {
+        if (a.emb_w) {
+            const size_t erow = (size_t)__ldcg(a.tokens + pos);
+#pragma unroll
+            for (int it = 0; it < NQ; it++) {
+                const int qd = it * FD_NT + tid;
+                const int e0 = 4 * ((qd < nq) ? qd : 0);
                 const size_t blk = erow * nb + (e0 >> 5);
                 const float delta = h2f(a.emb_s[blk]);
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const int el = (e0 & 31) + i;
                     if (a.emb_dt == DT_Q8) {
-                        x[i] = __fmul_rn((float)(int8_t)a.emb_w[blk * 32 + perm_byte(el)], delta);
+                        x[it][i] = __fmul_rn((float)(int8_t)a.emb_w[blk * 32 + perm_byte(el)], delta);
                     } else {
                         const int j = el & 15;
                         const uint8_t byte = a.emb_w[blk * 16 + ((j & 7) >> 1) * 4 + (j & 1) + 2 * (j >> 3)];
-                        x[i] = __fmul_rn((float)((int)((el < 16) ? (byte >> 4) : (byte & 0x0f)) - 7), delta);
+                        x[it][i] = __fmul_rn((float)((int)((el < 16) ? (byte >> 4) : (byte & 0x0f)) - 7), delta);
                     }
                 }
-                if (a.emb_dt != DT_Q8) fd_quad_roundtrip(x);          // Q4 row: dequantise, re-encode as Q8 (ops.h:522-528)
-            } else {
-                const float4 s0 = __ldcg(reinterpret_cast<const float4*>(a.src0 + e0));
-                x[0] = s0.x; x[1] = s0.y; x[2] = s0.z; x[3] = s0.w;
+                if (a.emb_dt != DT_Q8) fd_quad_roundtrip(x[it]);      // Q4 row: dequantise, re-encode as Q8 (ops.h:522-528)
+            }
+        } else {
+            float4 s0[NQ], s1[NQ];
+#pragma unroll
+            for (int it = 0; it < NQ; it++) {
+                const int qd = it * FD_NT + tid;
+                const int e0 = 4 * ((qd < nq) ? qd : 0);
+                s0[it] = __ldcg(reinterpret_cast<const float4*>(a.src0 + e0));
+                if (a.src1) s1[it] = __ldcg(reinterpret_cast<const float4*>(a.src1 + e0));
+            }
+#pragma unroll
+            for (int it = 0; it < NQ; it++) {
+                x[it][0] = s0[it].x; x[it][1] = s0[it].y; x[it][2] = s0[it].z; x[it][3] = s0[it].w;
                 if (a.src1) {
-                    const float4 s1 = __ldcg(reinterpret_cast<const float4*>(a.src1 + e0));
-                    float t[4] = {s1.x, s1.y, s1.z, s1.w};
+                    float t[4] = {s1[it].x, s1[it].y, s1[it].z, s1[it].w};
                     fd_quad_roundtrip(t);
 #pragma unroll
-                    for (int i = 0; i < 4; i++) x[i] = __fadd_rn(x[i], t[i]);
-                    fd_quad_roundtrip(x);
+                    for (int i = 0; i < 4; i++) x[it][i] = __fadd_rn(x[it][i], t[i]);
+                    fd_quad_roundtrip(x[it]);
                 }
             }
-            if (valid) {
-                *reinterpret_cast<float4*>(xbuf + e0) = make_float4(x[0], x[1], x[2], x[3]);
-                if (blockIdx.x == 0 && a.res_out) *reinterpret_cast<float4*>(a.res_out + e0) = make_float4(x[0], x[1], x[2], x[3]);
-                ssq += (x[0] * x[0] + x[1] * x[1]) + (x[2] * x[2] + x[3] * x[3]);
+        }
+#pragma unroll
+        for (int it = 0; it < NQ; it++) {
+            const int qd = it * FD_NT + tid;
+            if (qd < nq) {
+                if (blockIdx.x == 0 && a.res_out) *reinterpret_cast<float4*>(a.res_out + 4 * qd) = make_float4(x[it][0], x[it][1], x[it][2], x[it][3]);
+                ssq += (x[it][0] * x[it][0] + x[it][1] * x[it][1]) + (x[it][2] * x[it][2] + x[it][3] * x[it][3]);
             }
         }
         ssq = fd_block_sum(ssq, scratch);
-        const float denom = sqrtf(ssq / (float)K) + 1e-6f;
-        for (int base = 0; base < nq; base += FD_NT) {
-            const int qd = base + tid;
+        const float rden = 1.0f / (sqrtf(ssq / (float)K) + 1e-6f);
+#pragma unroll
+        for (int it = 0; it < NQ; it++) {
+            const int qd = it * FD_NT + tid;
             const bool valid = qd < nq;
             const int e0 = 4 * (valid ? qd : 0);
-            const float4 xv = *reinterpret_cast<const float4*>(xbuf + e0);
-            const uint2 wv = *reinterpret_cast<const uint2*>(a.normw + e0);
             float y[4];
-            y[0] = __fmul_rn(__fdiv_rn(xv.x, denom), h2f((uint16_t)(wv.x & 0xffffu)));
-            y[1] = __fmul_rn(__fdiv_rn(xv.y, denom), h2f((uint16_t)(wv.x >> 16)));
-            y[2] = __fmul_rn(__fdiv_rn(xv.z, denom), h2f((uint16_t)(wv.y & 0xffffu)));
-            y[3] = __fmul_rn(__fdiv_rn(xv.w, denom), h2f((uint16_t)(wv.y >> 16)));
+            y[0] = __fmul_rn(x[it][0] * rden, h2f((uint16_t)(nw[it].x & 0xffffu)));
+            y[1] = __fmul_rn(x[it][1] * rden, h2f((uint16_t)(nw[it].x >> 16)));
+            y[2] = __fmul_rn(x[it][2] * rden, h2f((uint16_t)(nw[it].y & 0xffffu)));
+            y[3] = __fmul_rn(x[it][3] * rden, h2f((uint16_t)(nw[it].y >> 16)));
             fd_stage_quad(sv, e0 >> 5, (e0 & 31) >> 2, y, valid);
         }
     } else {
@@ -303,11 +343,11 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fd_gemv(FdArgs a) {
         for (int i = tid; i < nb; i += FD_NT) { sv.ad[i] = __ldcg(a.in.ad + i); sv.n7[i] = __ldcg(a.in.n7 + i); }
     }
     __syncthreads();
+    sync.stamp();
 
     // ---- rows
     float best = -INFINITY;
     int arg = 0x7fffffff;
-    const int n_units = (EPI == FD_SILU) ? a.n_ffn / 32 : 1;
     for (;;) {
         for (; v < v1; ) {
             float acc[R];
@@ -335,7 +375,7 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fd_gemv(FdArgs a) {
                 }
             }
         }
-        if (EPI != FD_SILU) break;
+        if (EPI != FD_SILU || unit >= n_units) break;
         // E(E(silu(E(gate))) * E(up)) (modules.cpp:238-247) of this unit's 32 channels -> staged codes for the down GEMV
         __syncthreads();
         const int next_unit = unit + gridDim.x;
@@ -345,22 +385,23 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fd_gemv(FdArgs a) {
             fd_load_batch<WT, NBL, R>(bt, a.w, a.ws, row, nb);
         }
         if (wid == 0) {
-            const float g1 = q8_roundtrip_lane(scratch[lane]);
-            const float u1 = q8_roundtrip_lane(scratch[32 + lane]);
-            const float g2 = q8_roundtrip_lane(__fdividef(g1, 1.0f + __expf(-g1)));
-            uint16_t dh;
-            const int q = q8_encode_lane(__fmul_rn(g2, u1), &dh);
+            const float g1 = fd_lane_roundtrip(scratch[lane]);
+            const float u1 = fd_lane_roundtrip(scratch[32 + lane]);
+            const float g2 = fd_lane_roundtrip(__fdividef(g1, 1.0f + __expf(-g1)));
+            float dd;
+            const int q = fd_lane_encode(g2 * u1, &dd);
             int s = q;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             a.act_out.codes[unit * 32 + perm_byte(lane)] = (uint8_t)(int8_t)q;
-            if (lane == 0) { a.act_out.ad[unit] = h2f(dh); a.act_out.n7[unit] = -7 * s; }
+            if (lane == 0) { a.act_out.ad[unit] = dd; a.act_out.n7[unit] = -7 * s; }
         }
         if (next_unit >= n_units) break;
         unit = next_unit;
         __syncthreads();
     }
 
+    sync.stamp();
     if (EPI == FD_ARGMAX) {
         // first maximum of this CTA's rows (tinyllama.cpp:416-424), then the last CTA to arrive reduces all of them
         float* sval = scratch;
@@ -392,15 +433,29 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fd_gemv(FdArgs a) {
             }
             if (lane == 0) {
                 if (arg == 0x7fffffff) arg = 0;
-                const int pos = a.st->pos;
-                a.tok_out[pos + 1] = arg;
-                a.st->pos = pos + 1;
-                a.st->n_gen += 1;
+                const int pcur = (pos_in >= 0) ? pos_in : __ldcg(&a.st->pos);
+                a.tok_out[pcur + 1] = arg;
+                a.st->pos = pcur + 1;
+                a.st->n_gen = __ldcg(&a.st->n_gen) + 1;
                 if (arg == a.eos_id) a.st->stop = 1;
                 *a.counter = 0u;
             }
         }
     }
+}
+
+struct FdPdlSync {
+    __device__ __forceinline__ void arrive() {}
+    __device__ __forceinline__ void wait() { fd_wait_prior(); }
+    __device__ __forceinline__ void stamp() {}
+};
+
+template <int WT, int PRO, int EPI, int NBL, int R>
+__global__ void __launch_bounds__(FD_NT, 2) k_fd_gemv(FdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    fd_launch_dependents();
+    FdPdlSync sync;
+    fd_gemv_phase<WT, PRO, EPI, NBL, R>(a, smem, sync, -1);
 }
 
 // ---------------------------------------------------------------- attention: one CTA = (head, position chunk)
@@ -421,43 +476,81 @@ struct FdAttnSmem {
     float tmp[6][32];
     float red[FD_NW];
     float part[FD_NW][64];
+    float wm[FD_NW], wl[FD_NW];
     int last;
 };
 
-__global__ void __launch_bounds__(FD_NT, 2) k_fd_attn(FdAttnArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
+static __host__ __device__ inline size_t fd_attn_smem(int max_ctx, int nch) {
+    return ((sizeof(FdAttnSmem) + 15) & ~(size_t)15) + (size_t)((((max_ctx + nch - 1) / nch + 31) & ~31) + 64) * 4;
+}
+
+// units = (head, position chunk), `nch` chunks per head; unit u runs on CTA u mod gridDim.x.  Inside a chunk every warp owns
+// whole 32-position blocks of the probability row (the re-encode unit of ops.h:996) and keeps its own running
+// (max, sum, 64 outputs); warps meet once per chunk.  KPT = blocks per warp whose K/V rows are loaded up front.
+template <int KPT, typename Sync>
+__device__ __forceinline__ void fd_attn_phase(const FdAttnArgs& a, unsigned char* smem, Sync& sync, int n_heads, int nch, int pos_in) {
     FdAttnSmem& sm = *reinterpret_cast<FdAttnSmem*>(smem);
-    float* sc = reinterpret_cast<float*>(smem + ((sizeof(FdAttnSmem) + 15) & ~(size_t)15));
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int h = blockIdx.x / FD_CHUNKS, c = blockIdx.x % FD_CHUNKS, g = h / a.gsz;
-    fd_launch_dependents();
-    if (tid < 2 && a.pf[tid]) {
-        const size_t per = ((a.pf_bytes[tid] + gridDim.x - 1) / gridDim.x + 127) & ~(size_t)127;
-        const size_t off = per * blockIdx.x;
-        if (off < a.pf_bytes[tid]) l2_prefetch(reinterpret_cast<const unsigned char*>(a.pf[tid]) + off, min(per, a.pf_bytes[tid] - off));
-    }
-    fd_wait_prior();
-    const int pos = __ldcg(&a.st->pos);
+    const int slot = lane >> 2, cq = lane & 3;          // P.V: lane = (position slot of 8, 16 channels)
+    sync.arrive();
+    sync.stamp();
+    sync.wait();
+    sync.stamp();
+    const int pos = (pos_in >= 0) ? pos_in : __ldcg(&a.st->pos);
+    for (int unit = blockIdx.x; unit < n_heads * nch; unit += gridDim.x) {
+    const int h = unit / nch, c = unit % nch, g = h / a.gsz;
     const bool writer = (h % a.gsz) == 0 && c == 0;
     // chunk of positions [lo, hi), aligned to the 32-position blocks of the probability row
-    const int per = ((pos + 1 + FD_CHUNKS - 1) / FD_CHUNKS + 31) & ~31;
+    const int per = ((pos + 1 + nch - 1) / nch + 31) & ~31;
     const int lo = c * per, hi = min(pos + 1, lo + per);
-    const int n = hi - lo;
+    const int n = hi - lo, nblk = (n + 31) / 32;
     const int kvb = a.kv_dim / 32;
-    // q, k, v of this row: Linear re-encode, RoPE, re-encode (ops.h:645-646, 733-753); K/V append by one CTA per group
+    // the few words this row's q/k/v prep waits for go first
+    float cs = 0.0f, sn = 0.0f, xin = 0.0f;
+    if (wid < 4) { cs = a.rope_cos[(size_t)pos * 32 + lane]; sn = a.rope_sin[(size_t)pos * 32 + lane]; }
     if (wid < 6) {
         const int which = wid >> 1, half = wid & 1;
         const float* src = (which == 0) ? a.rqkv + h * 64 : (which == 1) ? a.rqkv + a.n_embd + g * 64 : a.rqkv + a.n_embd + a.kv_dim + g * 64;
-        const float x = __ldcg(src + half * 32 + lane);
+        xin = __ldcg(src + half * 32 + lane);
+    }
+    // K/V rows of this warp's first blocks do not depend on this row's q: in flight while the prep runs
+    uint4 kr[KPT][4], vr[KPT][4];
+    uint32_t ksr[KPT][2], vsr[KPT][4];
+    auto load_block = [&](int blk, uint4 (&kk)[4], uint32_t (&ks)[2], uint4 (&vv)[4], uint32_t (&vs)[4]) {
+        const int k = lo + blk * 32 + lane;
+        if (k < hi && k != pos) {
+            const uint4* kp = reinterpret_cast<const uint4*>(a.kq + (size_t)k * a.kv_dim + g * 64);
+#pragma unroll
+            for (int i = 0; i < 4; i++) kk[i] = __ldcg(kp + i);
+            ks[0] = __ldcg(a.ks + (size_t)k * kvb + g * 2);
+            ks[1] = __ldcg(a.ks + (size_t)k * kvb + g * 2 + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = lo + blk * 32 + slot + 8 * u;
+            vv[u] = make_uint4(0, 0, 0, 0); vs[u] = 0;
+            if (i < hi && i != pos) {
+                vv[u] = __ldcg(reinterpret_cast<const uint4*>(a.vq + (size_t)i * a.kv_dim + g * 64 + cq * 16));
+                vs[u] = __ldcg(a.vs + (size_t)i * kvb + g * 2 + (cq >> 1));
+            }
+        }
+    };
+#pragma unroll
+    for (int j = 0; j < KPT; j++) {
+        if (wid + FD_NW * j < nblk) load_block(wid + FD_NW * j, kr[j], ksr[j], vr[j], vsr[j]);
+    }
+    // q, k, v of this row: Linear re-encode, RoPE, re-encode (ops.h:645-646, 733-753); K/V append by one CTA per group
+    if (wid < 6) {
+        const int which = wid >> 1, half = wid & 1;
         if (which < 2) {
-            sm.tmp[wid][lane] = q8_roundtrip_lane(x);
+            sm.tmp[wid][lane] = fd_lane_roundtrip(xin);
         } else {
-            uint16_t dh;
-            const int q = q8_encode_lane(x, &dh);
-            sm.vf[half * 32 + lane] = __fmul_rn((float)q, h2f(dh));
+            float dd;
+            const int q = fd_lane_encode(xin, &dd);
+            sm.vf[half * 32 + lane] = (float)q * dd;
             if (writer) {
                 a.vq[(size_t)pos * a.kv_dim + g * 64 + half * 32 + lane] = (uint8_t)(int8_t)q;
-                if (lane == 0) a.vs[(size_t)pos * kvb + g * 2 + half] = dh;
+                if (lane == 0) a.vs[(size_t)pos * kvb + g * 2 + half] = f2h(dd);
             }
         }
     }
@@ -465,156 +558,250 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fd_attn(FdAttnArgs a) {
     if (wid < 4) {
         const int which = wid >> 1, half = wid & 1;
         const float x0 = sm.tmp[which * 2][lane], x1 = sm.tmp[which * 2 + 1][lane];
-        const float cs = a.rope_cos[(size_t)pos * 32 + lane], sn = a.rope_sin[(size_t)pos * 32 + lane];
         const float o = (half == 0) ? __fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn)) : __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs));
-        uint16_t dh;
-        const int q = q8_encode_lane(o, &dh);
+        float dd;
+        const int q = fd_lane_encode(o, &dd);
         const int pb = perm_byte(lane);
         if (which == 0) {
             reinterpret_cast<int8_t*>(sm.qw)[half * 32 + pb] = (int8_t)q;
-            if (lane == 0) sm.qd[half] = h2f(dh);
+            if (lane == 0) sm.qd[half] = dd;
         } else {
             reinterpret_cast<int8_t*>(sm.kw)[half * 32 + pb] = (int8_t)q;
-            if (lane == 0) sm.kd[half] = h2f(dh);
+            if (lane == 0) sm.kd[half] = dd;
             if (writer) {
                 a.kq[(size_t)pos * a.kv_dim + g * 64 + half * 32 + pb] = (uint8_t)(int8_t)q;
-                if (lane == 0) a.ks[(size_t)pos * kvb + g * 2 + half] = dh;
+                if (lane == 0) a.ks[(size_t)pos * kvb + g * 2 + half] = f2h(dd);
             }
         }
     }
     __syncthreads();
-    float* part = a.parts + ((size_t)h * FD_CHUNKS + c) * FD_PART;
-    float mx = -INFINITY, lsum = 0.0f;
-    if (n > 0) {
-        // scores of the chunk, scaled by 1/sqrt(64); chunk maximum
+    sync.stamp();
+    float* part = a.parts + ((size_t)h * nch + c) * FD_PART;
+    // ---- this warp's blocks: scores (x 1/sqrt(64)), block softmax numerators, E(P), P.V, merged into the warp's running state
+    float m_w = -INFINITY, l_w = 0.0f;
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) acc[j] = 0.0f;
+    {
         uint32_t qx[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) qx[i] = sm.qw[i];
-        for (int k = lo + tid; k < hi; k += FD_NT) {
-            float s = 0.0f;
-#pragma unroll
-            for (int bi = 0; bi < 2; bi++) {
-                uint4 kx, ky;
-                float kdv;
+        const float qd0 = sm.qd[0], qd1 = sm.qd[1];
+        auto score = [&](const uint4 (&kk)[4], float kd0, float kd1) {
+            int i0 = __dp4a((int)kk[0].x, (int)qx[0], 0);
+            i0 = __dp4a((int)kk[0].y, (int)qx[1], i0); i0 = __dp4a((int)kk[0].z, (int)qx[2], i0); i0 = __dp4a((int)kk[0].w, (int)qx[3], i0);
+            i0 = __dp4a((int)kk[1].x, (int)qx[4], i0); i0 = __dp4a((int)kk[1].y, (int)qx[5], i0);
+            i0 = __dp4a((int)kk[1].z, (int)qx[6], i0); i0 = __dp4a((int)kk[1].w, (int)qx[7], i0);
+            int i1 = __dp4a((int)kk[2].x, (int)qx[8], 0);
+            i1 = __dp4a((int)kk[2].y, (int)qx[9], i1); i1 = __dp4a((int)kk[2].z, (int)qx[10], i1); i1 = __dp4a((int)kk[2].w, (int)qx[11], i1);
+            i1 = __dp4a((int)kk[3].x, (int)qx[12], i1); i1 = __dp4a((int)kk[3].y, (int)qx[13], i1);
+            i1 = __dp4a((int)kk[3].z, (int)qx[14], i1); i1 = __dp4a((int)kk[3].w, (int)qx[15], i1);
+            return 0.125f * fmaf((float)i1, qd1 * kd1, (float)i0 * (qd0 * kd0));
+        };
+        auto do_block = [&](int blk, const uint4 (&kk)[4], const uint32_t (&ks)[2], const uint4 (&vv)[4], const uint32_t (&vs)[4]) {
+            const int k = lo + blk * 32 + lane;
+            float s = -INFINITY;
+            if (k < hi) {
                 if (k == pos) {
-                    kx = make_uint4(sm.kw[bi * 8 + 0], sm.kw[bi * 8 + 1], sm.kw[bi * 8 + 2], sm.kw[bi * 8 + 3]);
-                    ky = make_uint4(sm.kw[bi * 8 + 4], sm.kw[bi * 8 + 5], sm.kw[bi * 8 + 6], sm.kw[bi * 8 + 7]);
-                    kdv = sm.kd[bi];
+                    const uint4 own[4] = {make_uint4(sm.kw[0], sm.kw[1], sm.kw[2], sm.kw[3]), make_uint4(sm.kw[4], sm.kw[5], sm.kw[6], sm.kw[7]),
+                                          make_uint4(sm.kw[8], sm.kw[9], sm.kw[10], sm.kw[11]), make_uint4(sm.kw[12], sm.kw[13], sm.kw[14], sm.kw[15])};
+                    s = score(own, sm.kd[0], sm.kd[1]);
                 } else {
-                    const uint4* kp = reinterpret_cast<const uint4*>(a.kq + (size_t)k * a.kv_dim + g * 64 + bi * 32);
-                    kx = __ldcg(kp); ky = __ldcg(kp + 1);
-                    kdv = h2f(__ldcg(a.ks + (size_t)k * kvb + g * 2 + bi));
-                }
-                int is = __dp4a((int)kx.x, (int)qx[bi * 8 + 0], 0);
-                is = __dp4a((int)kx.y, (int)qx[bi * 8 + 1], is); is = __dp4a((int)kx.z, (int)qx[bi * 8 + 2], is); is = __dp4a((int)kx.w, (int)qx[bi * 8 + 3], is);
-                is = __dp4a((int)ky.x, (int)qx[bi * 8 + 4], is); is = __dp4a((int)ky.y, (int)qx[bi * 8 + 5], is);
-                is = __dp4a((int)ky.z, (int)qx[bi * 8 + 6], is); is = __dp4a((int)ky.w, (int)qx[bi * 8 + 7], is);
-                s = fmaf((float)is, __fmul_rn(sm.qd[bi], kdv), s);
-            }
-            s *= 0.125f;
-            sc[k - lo] = s;
-            mx = fmaxf(mx, s);
-        }
-        mx = warp_max(mx);
-        if (lane == 0) sm.red[wid] = mx;
-        __syncthreads();
-        mx = sm.red[0];
-#pragma unroll
-        for (int w = 1; w < FD_NW; w++) mx = fmaxf(mx, sm.red[w]);
-        __syncthreads();
-        // e = exp(s - chunk max); the Q8 re-encode of the probability row per 32 positions (ops.h:996): the codes depend only
-        // on e / max(e of the block); the block scale stays relative to the chunk maximum and is normalised at the combine
-        const int nblk = (n + 31) / 32;
-        for (int b = wid; b < nblk; b += FD_NW) {
-            const int i = b * 32 + lane;
-            const float e = (i < n) ? __expf(sc[i] - mx) : 0.0f;
-            lsum += e;
-            const float emax = warp_max(e);
-            const float code = (emax > 0.0f) ? floorf(e * __fdividef(127.0f, emax) + 0.5f) : 0.0f;
-            sc[i] = code * (emax * (1.0f / 127.0f));
-        }
-        lsum = fd_block_sum(lsum, sm.red);       // (also orders the sc[] writes before the reads below)
-        // P.V: thread = (position slot pp of 64, 16 channels cq); V rows as 128-bit loads
-        const int pp = tid >> 2, cq = tid & 3;
-        float acc[16];
-#pragma unroll
-        for (int j = 0; j < 16; j++) acc[j] = 0.0f;
-        for (int i0 = pp; i0 < n; i0 += 4 * 64) {
-            uint4 vv[4];
-            float wgt[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i = i0 + u * 64;
-                vv[u] = make_uint4(0, 0, 0, 0); wgt[u] = 0.0f;
-                if (i < n && lo + i != pos) {
-                    vv[u] = __ldcg(reinterpret_cast<const uint4*>(a.vq + (size_t)(lo + i) * a.kv_dim + g * 64 + cq * 16));
-                    wgt[u] = sc[i] * h2f(__ldcg(a.vs + (size_t)(lo + i) * kvb + g * 2 + (cq >> 1)));      // ops.h:1026
+                    s = score(kk, h2f((uint16_t)ks[0]), h2f((uint16_t)ks[1]));
                 }
             }
+            const float mb = warp_max(s);
+            const float e = (k < hi) ? __expf(s - mb) : 0.0f;
+            float lb = e;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) lb += __shfl_xor_sync(0xffffffffu, lb, o);
+            // Q8 re-encode of the probability row per 32 positions (ops.h:996): the block's largest e is exp(0) = 1, so the codes
+            // are round(127 e); the block scale stays relative to the block maximum and is normalised at the combine
+            const float p = floorf(e * 127.0f + 0.5f) * (1.0f / 127.0f);
+            const float m_new = fmaxf(m_w, mb);
+            const float f_old = __expf(m_w - m_new), f_b = __expf(mb - m_new);       // m_w = -inf: f_old = 0
+            l_w = fmaf(l_w, f_old, lb * f_b);
+            m_w = m_new;
+#pragma unroll
+            for (int j = 0; j < 16; j++) acc[j] *= f_old;
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const uint32_t wds[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
+                const int i = lo + blk * 32 + slot + 8 * u;
+                const float pi = __shfl_sync(0xffffffffu, p, slot + 8 * u) * f_b;
+                if (i < hi) {
+                    if (i == pos) {          // this row's own v is not read back from the cache
 #pragma unroll
-                for (int j = 0; j < 16; j++) acc[j] = fmaf((float)(int)(int8_t)(wds[j >> 2] >> (8 * (j & 3))), wgt[u], acc[j]);
+                        for (int j = 0; j < 16; j++) acc[j] = fmaf(sm.vf[cq * 16 + j], pi, acc[j]);
+                    } else {
+                        const float wgt = pi * h2f((uint16_t)vs[u]);          // ops.h:1026
+                        const uint32_t wds[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
+#pragma unroll
+                        for (int j = 0; j < 16; j++) acc[j] = fmaf((float)(int)(int8_t)(wds[j >> 2] >> (8 * (j & 3))), wgt, acc[j]);
+                    }
+                }
             }
-        }
-        if (pos >= lo && pos < hi && ((pos - lo) & 63) == pp) {      // this row's own v is not read back from the cache
-            const float p = sc[pos - lo];
+        };
 #pragma unroll
-            for (int j = 0; j < 16; j++) acc[j] = fmaf(sm.vf[cq * 16 + j], p, acc[j]);
+        for (int j = 0; j < KPT; j++) {
+            if (wid + FD_NW * j < nblk) do_block(wid + FD_NW * j, kr[j], ksr[j], vr[j], vsr[j]);
         }
-#pragma unroll
-        for (int j = 0; j < 16; j++) {
-            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
-            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
-            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+        for (int blk = wid + FD_NW * KPT; blk < nblk; blk += FD_NW) {          // chunks longer than KPT * 256 positions
+            uint4 kk[4], vv[4];
+            uint32_t ks[2], vs[4];
+            load_block(blk, kk, ks, vv, vs);
+            do_block(blk, kk, ks, vv, vs);
         }
-        if (lane < 4) {
-#pragma unroll
-            for (int j = 0; j < 16; j++) sm.part[wid][lane * 16 + j] = acc[j];
-        }
-        __syncthreads();
     }
-    if (tid < 64) {
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+    }
+    if (lane < 4) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) sm.part[wid][lane * 16 + j] = acc[j];
+    }
+    if (lane == 0) { sm.wm[wid] = m_w; sm.wl[wid] = l_w; }
+    __syncthreads();
+    sync.stamp();
+    if (tid < 65) {          // 64 channels + the chunk sum (tid 64), all relative to the chunk maximum
+        float m = sm.wm[0];
+#pragma unroll
+        for (int w = 1; w < FD_NW; w++) m = fmaxf(m, sm.wm[w]);
         float o = 0.0f;
-        if (n > 0) {
 #pragma unroll
-            for (int w = 0; w < FD_NW; w++) o += sm.part[w][tid];
+        for (int w = 0; w < FD_NW; w++) {
+            const float f = (sm.wm[w] == -INFINITY) ? 0.0f : __expf(sm.wm[w] - m);
+            o = fmaf((tid < 64) ? sm.part[w][tid] : sm.wl[w], f, o);
         }
-        part[tid] = o;
+        part[(tid < 64) ? tid : 65] = o;
+        if (tid == 64) part[64] = m;
     }
-    if (tid == 64) part[64] = mx;
-    if (tid == 65) part[65] = lsum;
     // ---- the last chunk of this head to finish combines: o = sum_c o_c * exp(m_c - m) / sum_c l_c * exp(m_c - m), E(o)
     __threadfence();
     __syncthreads();
-    if (tid == 0) sm.last = (atomicAdd(a.counters + h, 1u) == FD_CHUNKS - 1);
+    if (tid == 0) sm.last = (atomicAdd(a.counters + h, 1u) == (unsigned)(nch - 1));
     __syncthreads();
-    if (!sm.last) return;
+    if (sm.last) {
     __threadfence();
     if (wid < 2) {
-        const float* p = a.parts + (size_t)h * FD_CHUNKS * FD_PART;
+        const float* p = a.parts + (size_t)h * nch * FD_PART;
         float m = -INFINITY;
-#pragma unroll
-        for (int cc = 0; cc < FD_CHUNKS; cc++) m = fmaxf(m, __ldcg(p + cc * FD_PART + 64));
+        for (int cc = 0; cc < nch; cc++) m = fmaxf(m, __ldcg(p + cc * FD_PART + 64));
         float l = 0.0f, o = 0.0f;
-#pragma unroll
-        for (int cc = 0; cc < FD_CHUNKS; cc++) {
+        for (int cc = 0; cc < nch; cc++) {
             const float mc = __ldcg(p + cc * FD_PART + 64);
             const float f = (mc == -INFINITY) ? 0.0f : __expf(mc - m);
             l = fmaf(__ldcg(p + cc * FD_PART + 65), f, l);
             o = fmaf(__ldcg(p + cc * FD_PART + tid), f, o);
         }
-        uint16_t dh;
-        const int q = q8_encode_lane(__fdividef(o, l), &dh);          // E(attention output), ops.h:1084
+        float dd;
+        const int q = fd_lane_encode(__fdividef(o, l), &dd);          // E(attention output), ops.h:1084
         int s = q;
 #pragma unroll
         for (int ofs = 16; ofs > 0; ofs >>= 1) s += __shfl_xor_sync(0xffffffffu, s, ofs);
         const int b = 2 * h + wid;
         a.out.codes[b * 32 + perm_byte(lane)] = (uint8_t)(int8_t)q;
-        if (lane == 0) { a.out.ad[b] = h2f(dh); a.out.n7[b] = -7 * s; }
+        if (lane == 0) { a.out.ad[b] = dd; a.out.n7[b] = -7 * s; }
     }
     if (tid == 0) a.counters[h] = 0u;
+    }
+    __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(FD_NT, 2) k_fd_attn(FdAttnArgs a, int n_heads) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    fd_launch_dependents();
+    FdPdlSync sync;
+    fd_attn_phase<1>(a, smem, sync, n_heads, FD_CHUNKS, -1);
+}
+
+// ---------------------------------------------------------------- the same phases as ONE persistent cooperative kernel
+// One CTA per SM; rows (prefill rows and greedy steps) loop inside; a phase boundary is a grid barrier (one relaxed atomic
+// arrival per CTA + one polling thread per CTA) instead of a kernel boundary.  A CTA issues the register loads of its first
+// weight rows of the NEXT phase before it arrives at the barrier, so weights never sit on the dependency chain.
+constexpr int FDM_CHUNKS = 4;          // 32 heads x 4 chunks = 128 attention units on 148 CTAs
+
+struct FdMegaParams {
+    const FdArgs* gemv;       // [4 * n_layers + 1]: per layer q|k|v, o, gate|up, down; the head last
+    const FdAttnArgs* attn;   // [n_layers]
+    int n_layers, n_heads;
+    int n_body, n_head;       // rows without / with lm_head + argmax
+    unsigned* bar;            // arrival counter (own 128-byte line), monotonic across launches
+    unsigned bar_base;        // its value before this launch
+    DevState* st;
+    long long* prof; int prof_cta;
+};
+
+static inline size_t fd_mega_smem(int n_embd, int n_ffn, int max_ctx) {
+    size_t s = fd_gemv_smem(n_embd, true);
+    if (fd_gemv_smem(n_ffn, false) > s) s = fd_gemv_smem(n_ffn, false);
+    if (fd_attn_smem(max_ctx, FDM_CHUNKS) > s) s = fd_attn_smem(max_ctx, FDM_CHUNKS);          // (>= the 8-chunk variant's)
+    return s;
+}
+
+struct FdGridSync {
+    unsigned* bar;
+    unsigned target;
+    long long* prof;          // option "prof": SM-clock stamps of CTA `prof_cta` along the phases of the last row
+    int idx;
+    __device__ __forceinline__ void stamp() {
+        if (prof && threadIdx.x == 0 && idx < 4000) prof[idx++] = clock64();
+    }
+    // arrive: this CTA's writes of the finished phase are published; wait: every CTA has arrived.  Weight loads of the
+    // next phase are issued between the two (a fence after them would wait for them).
+    __device__ __forceinline__ void arrive() {
+        target += gridDim.x;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+        }
+    }
+    __device__ __forceinline__ void wait() {
+        if (threadIdx.x == 0) {
+            unsigned v;
+            long long spins = 0;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+                if ((int)(v - target) >= 0) break;
+                if (++spins > (1ll << 26)) __trap();          // a lost CTA must not hang the GPU
+            }
+        }
+        __syncthreads();
+    }
+};
+
+// (A variant with two CTAs per SM -- 296 CTAs, 128 registers, every gate|up unit and 8 chunks per head in one wave -- measured
+// slower: 762 vs 729 us per token; profiles/r01_04_fastdec.md.)
+template <int WT>
+__global__ void __launch_bounds__(FD_NT, 1) k_fd_mega(FdMegaParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int R2 = (WT == DT_Q4) ? 4 : 2, R6 = (WT == DT_Q4) ? 2 : 1, RS = 2 * R2;      // RS: a gate|up unit in one pass (Q4)
+    constexpr int NCH = FDM_CHUNKS, KPT = 2;
+    FdGridSync sync{P.bar, P.bar_base, nullptr, 0};
+    const int n_rows = P.n_body + P.n_head;
+    int pos = __ldcg(&P.st->pos);          // rows advance it in lockstep in every CTA
+    for (int r = 0; r < n_rows; r++, pos++) {
+        if (r == n_rows - 1 && (int)blockIdx.x == P.prof_cta) sync.prof = P.prof;
+        for (int li = 0; li < P.n_layers; li++) {
+            fd_gemv_phase<WT, FD_NORM, FD_RAW, 2, R2>(P.gemv[4 * li + 0], smem, sync, pos);
+            fd_attn_phase<KPT>(P.attn[li], smem, sync, P.n_heads, NCH, pos);
+            fd_gemv_phase<WT, FD_CODES, FD_RAW, 2, R2>(P.gemv[4 * li + 1], smem, sync, pos);
+            fd_gemv_phase<WT, FD_NORM, FD_SILU, 2, RS>(P.gemv[4 * li + 2], smem, sync, pos);
+            fd_gemv_phase<WT, FD_CODES, FD_RAW, 6, R6>(P.gemv[4 * li + 3], smem, sync, pos);
+        }
+        if (r >= P.n_body) {
+            fd_gemv_phase<WT, FD_NORM, FD_ARGMAX, 2, R2>(P.gemv[4 * P.n_layers], smem, sync, pos);
+            sync.arrive(); sync.wait();                       // the new token, position and stop flag are visible to every CTA
+            if (__ldcg(&P.st->stop)) break;
+        } else {
+            // nobody reads the position between the last attention phase and the next row's first barrier
+            if (blockIdx.x == 0 && threadIdx.x == 0) P.st->pos = pos + 1;
+        }
+    }
 }
 
 }  // namespace gtb

@@ -15,6 +15,7 @@ eng = capi.Engine(cfg, 2048, wdt).load(W.synth_weights(cfg, wdt, seed=1))
 eng.prefill_fast(W.synth_prompt(7, ctx, cfg.n_vocab))
 eng.set_option("fast_decode", 1)
 eng.set_option("graph", 0)
+eng.set_option("fd_mega", 0)
 eng.decode(rows)
 capi.sync()
 print("pos", eng.position())

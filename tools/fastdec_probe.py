@@ -24,8 +24,10 @@ fast = eng.logits(toks, ctx)
 err = float(np.linalg.norm(fast.astype(np.float64) - exact) / np.linalg.norm(exact.astype(np.float64)))
 print(f"logits at t={ctx + 1}: fast vs exact rel L2 {err:.3e}; top-1 {int(np.argmax(fast))} vs {int(np.argmax(exact))}")
 bytes_tok = cfg.decode_bytes(wdt, ctx + steps // 2)
-cases = [("exact megakernel", {"fast_decode": 0}), ("fast, eager", {"fast_decode": 1, "graph": 0})]
-cases += [(f"fast, graph, ahead {d}", {"fast_decode": 1, "graph": 1, "fd_ahead": d}) for d in (0, 1, 2, 3, 4, 6)]
+cases = [("exact megakernel", {"fast_decode": 0}), ("fast, pdl eager", {"fast_decode": 1, "fd_mega": 0, "graph": 0}),
+         ("fast, pdl graph", {"fast_decode": 1, "fd_mega": 0, "graph": 1})]
+cases += [(f"fast, pdl graph, ahead {d}", {"fast_decode": 1, "fd_mega": 0, "graph": 1, "fd_ahead": d}) for d in (0, 6)]
+cases += [(f"fast, persistent, ahead {d}", {"fast_decode": 1, "fd_mega": 1, "fd_ahead": d}) for d in (0, 3)]
 for label, opts in cases:
     for k, v in opts.items():
         eng.set_option(k, v)
@@ -36,4 +38,4 @@ for label, opts in cases:
     eng.decode(steps)
     capi.sync()
     dt = (time.perf_counter() - t0) / steps
-    print(f"{label:22s}: {dt * 1e6:8.1f} us/token  {1 / dt:8.1f} tok/s  {bytes_tok / dt / 1e9:7.1f} GB/s algorithmic")
+    print(f"{label:32s}: {dt * 1e6:8.1f} us/token  {1 / dt:8.1f} tok/s  {bytes_tok / dt / 1e9:7.1f} GB/s algorithmic")
