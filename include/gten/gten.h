@@ -40,6 +40,10 @@ public:
     // of the prompt rows becomes one tcgen05 GEMM.  Its results match the reference within a tolerance, not bit for bit
     // (DESIGN.md 4.4); later calls (start_pos > 0) always take the order-exact path.  Prompts of >= 2 tokens.
     void set_batched_prefill(bool on) { batched_prefill_ = on; }
+    // Opt in to the order-free decode kernels (gtb_fastdec.cuh) for every row: same operations and re-encode points as
+    // ops.h, free summation order -- 2.2x the token rate of the bit-exact path, results within the same tolerance as the
+    // batched prefill, greedy tokens no longer guaranteed identical.  Q8 / Q4 models.
+    void set_fast_decode(bool on) { GTEN_CUDA_OK(gtb_engine_set_option(eng_, "fast_decode", on ? 1 : 0)); }
     Tensor logits(const Tensor& tokens, const int start_pos = 0) {
         if (tokens.numel() > n_ctx_) {
             std::cerr << "Number of prompt tokens (" << tokens.numel() << ") exceed provided maximum ctx size (" << n_ctx_ << ")\n";

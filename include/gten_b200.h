@@ -137,6 +137,8 @@ int gtb_engine_acv(gtb_engine_t e, int layer, int acv_id, float* h_out, int* wid
  * "fast_decode" (1: rows run through the order-free kernels of gtb_fastdec.cuh -- 128-bit streaming GEMV with warp-shuffle
  * reductions, block-reduced RMSNorm, position-split attention with an online-softmax combine; same operations and re-encode
  * points, free summation order: tolerance-level parity like gtb_engine_prefill_fast, Q8/Q4 models; default 0),
+ * "fd_mega" (fast_decode as one persistent cooperative kernel with grid barriers instead of the PDL-chained kernels, default 0),
+ * "fd_ahead" (fast_decode: L2 look-ahead distance in GEMV steps, default 3), "fd_prof_cta" (which CTA writes the "prof" stamps),
  * "pf_layers" (debug: batched prefill stops after this many layers), "pf_fused" (RoPE/KV append and SiLU*up inside the
  * GEMM epilogues, default 1), "pf_pdl" (programmatic dependent launch, default 1), "pf_2cta" (CTA-pair tcgen05 GEMM, default 0),
  * "pf_attn2" (second attention sweep that also reproduces the fp16 rounding of the probability-row block scales, default 0) */
