@@ -258,6 +258,7 @@ def fast_decode_section(eng, capi, torch, stream, cfg, wdt, prompt, n_prompt, Wm
            "parity": {"kind": "tolerance (summation order free; the reference's two own builds differ by the same amount, DESIGN.md 4.4/4.6)",
                       "logits_rel_l2_vs_exact_path_same_cache": rel, "same_top1": bool(int(np.argmax(fast)) == int(np.argmax(exact)))},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                        "traffic": measured_traffic(("q4" if wdt == W.Q4 else "q8") + "_fast_decode", K),
                         "peak_source": peak_src, "algorithmic_bytes_per_step": bytes_per_tok,
                         "kernel": "k_fd_gemv / k_fd_attn chain (achieved = bytes of K steps / time of K steps)"},
            "gpu_launches": int(launches)}
