@@ -223,7 +223,7 @@ def prefill_section(capi, torch, stream, iters=5, warmup=3, T=2048, cpu=True):
 
 def fast_decode_section(eng, capi, torch, stream, cfg, wdt, prompt, n_prompt, Wm, K, hbm_peak, peak_src, e2e=True):
     """The same workload through the ORDER-FREE decode kernels (option fast_decode, gtb_fastdec.cuh): same operations and
-    re-encode points as the reference, free summation order -> tolerance-level parity (DESIGN.md 4.6), NOT identical tokens.
+    re-encode points as the reference, free summation order -> tolerance-level parity (DESIGN.md 4.5), NOT identical tokens.
     Reported next to the headline (which stays the bit-identical path); same timing protocol."""
     eng.set_option("fast_decode", 0)
     eng.prefill(prompt)                                   # K/V cache and first token by the exact path
