@@ -143,6 +143,20 @@ int gtb_engine_acv(gtb_engine_t e, int layer, int acv_id, float* h_out, int* wid
  * GEMM epilogues, default 1), "pf_pdl" (programmatic dependent launch, default 1), "pf_2cta" (CTA-pair tcgen05 GEMM, default 0),
  * "pf_attn2" (second attention sweep that also reproduces the fp16 rounding of the probability-row block scales, default 0) */
 int gtb_engine_set_option(gtb_engine_t e, const char* name, int value);
+
+/* Batched decode (the reference decodes one sequence, tinyllama.cpp:395-440): up to 8 sequences advance
+ * together through the order-free kernels (tolerance contract of "fast_decode"), every weight is read once per step for all of
+ * them.  A sequence decoded in a batch gives the same bits as the same sequence decoded alone with "fast_decode".
+ *   gtb_engine_batch_create(e, n)   allocate n slots (own K/V cache, tokens, position each); n = 0 frees them
+ *   gtb_engine_batch_adopt(e, s)    slot s <- the engine's current sequence (after gtb_engine_prefill / _prefill_fast / decode)
+ *   gtb_engine_batch_decode(e, k)   k greedy steps of every slot (device-side argmax, tokens stay on the device)
+ *   gtb_engine_batch_position / _read_tokens / _read_logits: per-slot state */
+int gtb_engine_batch_create(gtb_engine_t e, int n_seq);
+int gtb_engine_batch_adopt(gtb_engine_t e, int seq);
+int gtb_engine_batch_decode(gtb_engine_t e, int n_steps);
+int gtb_engine_batch_position(gtb_engine_t e, int seq, int* pos);
+int gtb_engine_batch_read_tokens(gtb_engine_t e, int seq, int32_t* h_tokens, int first, int count);
+int gtb_engine_batch_read_logits(gtb_engine_t e, int seq, float* h_logits);
 /* "prof": globaltimer stamps (ns) taken by CTA 0 at every phase boundary of the last processed row */
 int gtb_engine_read_prof(gtb_engine_t e, long long* h_out, int count);
 /* 1 if rows run in the persistent kernel (TinyLlama dimensions, max_ctx <= 2048, grid >= 128), 0 if one kernel per phase */

@@ -153,3 +153,60 @@ def test_fast_generate_with_eos(capi):
     stopped = e.generate(prompt, 10, eos_id=eos)
     assert np.array_equal(stopped, free[: first + 1]), (stopped, free)
     e.close()
+
+
+# ---------------------------------------------------------------- batched decode (gtb_engine_batch_*)
+@pytest.mark.parametrize("graph", [1, 0], ids=["graph", "eager"])
+@pytest.mark.parametrize("wdt,lens", [(Q4, (20, 37, 64)), (Q8, (5, 33, 40, 41, 64, 90, 100, 7)), (Q4, (50,))], ids=["q4x3", "q8x8", "q4x1"])
+def test_batch_decode_equals_single_sequence(capi, wdt, lens, graph):
+    """A sequence decoded in a batch gives the SAME BITS (tokens and logits) as the same sequence decoded alone through the
+    order-free kernels: the batch only shares the weight reads.  Sequences have different lengths (own positions, own K/V)."""
+    cfg = W.mini_config(n_layers=2, n_vocab=300)
+    wl = list(W.synth_weights(cfg, wdt, seed=6))
+    steps = 7
+    e = capi.Engine(cfg, 128, wdt).load(wl)
+    e.set_option("graph", graph)
+    e.batch_create(len(lens))
+    prompts = [W.synth_prompt(40 + i, n, cfg.n_vocab) for i, n in enumerate(lens)]
+    for s, p in enumerate(prompts):
+        e.prefill(p)                      # exact path; slot s takes over tokens, position and K/V cache
+        e.batch_adopt(s)
+    e.batch_decode(steps)
+    for s, p in enumerate(prompts):
+        one = capi.Engine(cfg, 128, wdt).load(wl)
+        one.prefill(p)
+        one.set_option("fast_decode", 1)
+        one.decode(steps)
+        n = len(p)
+        assert e.batch_position(s) == one.position() == n + steps
+        want = one.read_tokens(0, n + steps + 1)
+        got = e.batch_read_tokens(s, 0, n + steps + 1)
+        assert np.array_equal(got, want), (s, got[n:], want[n:])
+        assert np.array_equal(e.batch_read_logits(s).view(np.uint32), one.read_logits().view(np.uint32)), s
+        one.close()
+    e.close()
+
+
+def test_batch_decode_argument_errors(capi):
+    cfg = W.mini_config(n_layers=1, n_vocab=64)
+    e = capi.Engine(cfg, 32, Q4).load(W.synth_weights(cfg, Q4, seed=1))
+    with pytest.raises(capi.GtbError):
+        e.batch_create(9)
+    with pytest.raises(capi.GtbError):
+        e.batch_decode(1)                 # no slots
+    e.batch_create(2)
+    with pytest.raises(capi.GtbError):
+        e.batch_adopt(2)
+    e.prefill(np.array([1, 2, 3], np.int32))
+    e.batch_adopt(0); e.batch_adopt(1)
+    with pytest.raises(capi.GtbError):
+        e.batch_decode(40)                # past max_ctx
+    e.batch_decode(2)
+    assert e.batch_position(0) == e.batch_position(1) == 5
+    assert np.array_equal(e.batch_read_tokens(0, 0, 6), e.batch_read_tokens(1, 0, 6))
+    e.batch_create(0)
+    e.close()
+    f = capi.Engine(cfg, 32, F16).load(W.synth_weights(cfg, F16, seed=1))
+    with pytest.raises(capi.GtbError):
+        f.batch_create(2)
+    f.close()

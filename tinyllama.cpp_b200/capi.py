@@ -29,6 +29,8 @@ SYMBOLS = [
     "gtb_engine_position", "gtb_engine_read_tokens", "gtb_engine_read_logits", "gtb_engine_acv",
     "gtb_engine_set_option", "gtb_engine_weight_bytes", "gtb_engine_read_prof", "gtb_selftest_exact_sum", "gtb_engine_uses_megakernel",
     "gtb_engine_prefill_fast", "gtb_engine_pf_acv", "gtb_pf_gemm_f32", "gtb_engine_topk",
+    "gtb_engine_batch_create", "gtb_engine_batch_adopt", "gtb_engine_batch_decode", "gtb_engine_batch_position",
+    "gtb_engine_batch_read_tokens", "gtb_engine_batch_read_logits",
 ]
 
 
@@ -78,6 +80,9 @@ def lib():
             "gtb_engine_read_prof": [vp, vp, i], "gtb_selftest_exact_sum": [vp, i, vp], "gtb_engine_uses_megakernel": [vp, C.POINTER(C.c_int)],
             "gtb_engine_prefill_fast": [vp, vp, i], "gtb_engine_pf_acv": [vp, i, i, i, vp, C.POINTER(i)],
             "gtb_pf_gemm_f32": [vp, vp, i, i, i, i, vp], "gtb_engine_topk": [vp, i, vp, vp],
+            "gtb_engine_batch_create": [vp, i], "gtb_engine_batch_adopt": [vp, i], "gtb_engine_batch_decode": [vp, i],
+            "gtb_engine_batch_position": [vp, i, C.POINTER(i)], "gtb_engine_batch_read_tokens": [vp, i, vp, i, i],
+            "gtb_engine_batch_read_logits": [vp, i, vp],
         }
         for name, args in sigs.items():
             fn = getattr(L, name)
@@ -379,6 +384,32 @@ class Engine:
         w = C.c_int()
         check(lib().gtb_engine_acv(self.h, layer, aid, _hp(out), C.byref(w)))
         return out[: w.value].copy()
+
+    # ---- batched decode (gtb_engine_batch_*): up to 8 sequences share every weight read
+    def batch_create(self, n_seq: int):
+        check(lib().gtb_engine_batch_create(self.h, n_seq))
+
+    def batch_adopt(self, seq: int):
+        """Slot `seq` <- the engine's current sequence (tokens, position, K/V cache)."""
+        check(lib().gtb_engine_batch_adopt(self.h, seq))
+
+    def batch_decode(self, n_steps: int):
+        check(lib().gtb_engine_batch_decode(self.h, n_steps))
+
+    def batch_position(self, seq: int) -> int:
+        p = C.c_int()
+        check(lib().gtb_engine_batch_position(self.h, seq, C.byref(p)))
+        return p.value
+
+    def batch_read_tokens(self, seq: int, first: int, count: int) -> np.ndarray:
+        out = np.empty(count, np.int32)
+        check(lib().gtb_engine_batch_read_tokens(self.h, seq, _hp(out), first, count))
+        return out
+
+    def batch_read_logits(self, seq: int) -> np.ndarray:
+        out = np.empty(self.cfg.n_vocab, np.float32)
+        check(lib().gtb_engine_batch_read_logits(self.h, seq, _hp(out)))
+        return out
 
     def uses_megakernel(self) -> bool:
         y = C.c_int()

@@ -358,6 +358,22 @@ struct gtb_engine {
     float* fd_argv = nullptr;        // per-CTA maxima of the head kernel
     int* fd_argi = nullptr;
     int fd_ahead = 3;                // L2 look-ahead distance in GEMV steps
+    // batched decode (gtb_engine_batch_*): per-sequence buffers [n][...] and K/V caches [n][max_ctx][kv_dim] per layer
+    struct BatchBufs {
+        int n = 0;
+        float *rqkv = nullptr, *ro = nullptr, *rd = nullptr, *xres = nullptr, *hres = nullptr, *xfinal = nullptr, *logits = nullptr;
+        float *parts = nullptr, *argv = nullptr;
+        int* argi = nullptr;
+        unsigned* cnt = nullptr;
+        int32_t* tokens = nullptr;
+        DevState* st = nullptr;
+        FdAct norm_act{}, attn_act{}, mlp_act{};
+        std::vector<uint8_t*> kq, vq;
+        std::vector<uint16_t*> ks, vs;
+        std::vector<int> host_pos;
+        cudaGraphExec_t graph = nullptr;
+        int graph_launches = 0;
+    } bb;
     int fd_prof_cta = 0;             // which CTA writes the "prof" stamps of k_fd_mega
     bool fd_mega = false;            // fast decode as one persistent cooperative kernel (k_fd_mega, measured slower); false: PDL-chained kernels
     FdArgs* d_fd_gemv = nullptr;     // phase arguments of k_fd_mega
@@ -637,6 +653,150 @@ int run_rows_fast_mega(gtb_engine* e, int n_body, int n_head, int eos_id) {
     return (c.wdtype == GTB_Q8) ? launch_fast_mega<DT_Q8>(e, p) : launch_fast_mega<DT_Q4>(e, p);
 }
 
+// ---------------------------------------------------------------- batched order-free decode
+void batch_free(gtb_engine* e) {
+    auto& b = e->bb;
+    if (b.graph) { cudaGraphExecDestroy(b.graph); b.graph = nullptr; }
+    void* p[] = {b.rqkv, b.ro, b.rd, b.xres, b.hres, b.xfinal, b.logits, b.parts, b.argv, b.argi, b.cnt, b.tokens, b.st,
+                 b.norm_act.codes, b.norm_act.ad, b.norm_act.n7, b.attn_act.codes, b.attn_act.ad, b.attn_act.n7,
+                 b.mlp_act.codes, b.mlp_act.ad, b.mlp_act.n7};
+    for (void* q : p) cudaFree(q);
+    for (auto q : b.kq) cudaFree(q);
+    for (auto q : b.vq) cudaFree(q);
+    for (auto q : b.ks) cudaFree(q);
+    for (auto q : b.vs) cudaFree(q);
+    b = gtb_engine::BatchBufs{};
+}
+
+int batch_alloc(gtb_engine* e, int n) {
+    batch_free(e);
+    if (n <= 0) return GTB_OK;
+    const gtb_model_config& c = e->cfg;
+    const int E = c.n_embd, F = c.n_ffn, KV = e->kv_dim, MC = c.max_ctx;
+    auto& b = e->bb;
+    auto dalloc = [&](void** p, size_t bytes) -> int { GTB_CUDA(cudaMalloc(p, bytes)); GTB_CUDA(cudaMemsetAsync(*p, 0, bytes, ctx().stream)); ctx().mem += (int64_t)bytes; return GTB_OK; };
+    int r = 0;
+    const size_t N = (size_t)n;
+    r |= dalloc((void**)&b.rqkv, N * (E + 2 * KV) * 4); r |= dalloc((void**)&b.ro, N * E * 4); r |= dalloc((void**)&b.rd, N * E * 4);
+    r |= dalloc((void**)&b.xres, N * E * 4); r |= dalloc((void**)&b.hres, N * E * 4); r |= dalloc((void**)&b.xfinal, N * E * 4);
+    r |= dalloc((void**)&b.logits, N * c.n_vocab * 4);
+    r |= dalloc((void**)&b.parts, N * c.n_heads * FD_CHUNKS * FD_PART * 4);
+    r |= dalloc((void**)&b.argv, N * 1024 * 4); r |= dalloc((void**)&b.argi, N * 1024 * 4);
+    r |= dalloc((void**)&b.cnt, (N * (c.n_heads + 1) + 1) * 4);
+    r |= dalloc((void**)&b.tokens, N * (MC + 2) * 4); r |= dalloc((void**)&b.st, N * sizeof(DevState));
+    FdAct* acts[3] = {&b.norm_act, &b.attn_act, &b.mlp_act};
+    const int widths[3] = {E, E, F};
+    for (int i = 0; i < 3; i++) {
+        r |= dalloc((void**)&acts[i]->codes, N * widths[i]); r |= dalloc((void**)&acts[i]->ad, N * (widths[i] / 32) * 4);
+        r |= dalloc((void**)&acts[i]->n7, N * (widths[i] / 32) * 4);
+    }
+    b.kq.assign(c.n_layers, nullptr); b.vq.assign(c.n_layers, nullptr); b.ks.assign(c.n_layers, nullptr); b.vs.assign(c.n_layers, nullptr);
+    for (int li = 0; li < c.n_layers; li++) {
+        r |= dalloc((void**)&b.kq[li], N * MC * KV); r |= dalloc((void**)&b.vq[li], N * MC * KV);
+        r |= dalloc((void**)&b.ks[li], N * MC * (KV / 32) * 2); r |= dalloc((void**)&b.vs[li], N * MC * (KV / 32) * 2);
+    }
+    if (r) { batch_free(e); return fail(GTB_ERR_CUDA, "batch buffers: allocation failed"); }
+    b.n = n;
+    b.host_pos.assign(n, 0);
+    return GTB_OK;
+}
+
+template <int WT, int EPI>
+int launch_fdb(const FdArgs& a, int grid) {
+    const int nbl = (a.K / 32 + 31) / 32;
+    const size_t smem = fdb_gemv_smem(a.K, a.n_seq);
+    if (nbl <= 2) {
+        constexpr int R = (WT == DT_Q4) ? 4 : 2;
+        static bool done = false;
+        if (!done) { GTB_CUDA(cudaFuncSetAttribute(k_fdb_gemv<WT, EPI, 2, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); done = true; }
+        GTB_CUDA(fd_launch(k_fdb_gemv<WT, EPI, 2, R>, grid, smem, a));
+    } else {
+        constexpr int R = (WT == DT_Q4) ? 2 : 1;
+        static bool done = false;
+        if (!done) { GTB_CUDA(cudaFuncSetAttribute(k_fdb_gemv<WT, EPI, 6, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); done = true; }
+        GTB_CUDA(fd_launch(k_fdb_gemv<WT, EPI, 6, R>, grid, smem, a));
+    }
+    GTB_LAUNCHED();
+    return GTB_OK;
+}
+
+// one row of every sequence of the batch: 7 launches per layer + 2 for the head
+template <int WT>
+int enqueue_batch_row(gtb_engine* e) {
+    const gtb_model_config& c = e->cfg;
+    auto& b = e->bb;
+    const int E = c.n_embd, F = c.n_ffn, KV = e->kv_dim, L = c.n_layers, G = ctx().sm_count, NS = b.n, MC = c.max_ctx;
+    const int wd = c.wdtype;
+    std::vector<FdArgs> gv;          // GEMV steps in launch order (4 per layer + head), for the L2 look-ahead
+    for (int li = 0; li < L; li++) {
+        LayerW& l = e->L[li];
+        FdArgs q{}; q.K = E; q.n_rows = E + 2 * KV; q.w = (const uint4*)l.qkv_data; q.ws = l.qkv_sc; q.out = b.rqkv; q.in = b.norm_act;
+        FdArgs o{}; o.K = E; o.n_rows = E; o.w = (const uint4*)l.o->data; o.ws = l.o->scales; o.out = b.ro; o.in = b.attn_act;
+        FdArgs g{}; g.K = E; g.n_rows = 2 * F; g.w = (const uint4*)l.gu_data; g.ws = l.gu_sc; g.n_ffn = F; g.in = b.norm_act; g.act_out = b.mlp_act;
+        FdArgs d{}; d.K = F; d.n_rows = E; d.w = (const uint4*)l.down->data; d.ws = l.down->scales; d.out = b.rd; d.in = b.mlp_act;
+        gv.push_back(q); gv.push_back(o); gv.push_back(g); gv.push_back(d);
+    }
+    {
+        FdArgs hd{}; hd.K = E; hd.n_rows = c.n_vocab; hd.w = (const uint4*)e->lm_head->data; hd.ws = e->lm_head->scales; hd.out = b.logits;
+        hd.in = b.norm_act; hd.arg_val = b.argv; hd.arg_idx = b.argi; hd.counter = b.cnt + (size_t)NS * (c.n_heads + 1);
+        hd.tok_out = b.tokens; hd.st = b.st; hd.eos_id = -1;
+        gv.push_back(hd);
+    }
+    const int ns = (int)gv.size();
+    for (int i = 0; i < ns; i++) {
+        gv[i].n_seq = NS; gv[i].tok_stride = MC + 2;
+        if (e->fd_ahead > 0) {
+            const FdArgs& t = gv[(i + e->fd_ahead) % ns];
+            gv[i].pf[0] = t.w; gv[i].pf_bytes[0] = weight_data_bytes(wd, t.n_rows, t.K);
+            gv[i].pf[1] = t.ws; gv[i].pf_bytes[1] = weight_scale_bytes(wd, t.n_rows, t.K);
+        }
+    }
+    static bool attr = false;
+    if (!attr) {
+        GTB_CUDA(cudaFuncSetAttribute(k_fdb_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        GTB_CUDA(cudaFuncSetAttribute(k_fdb_norm, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr = true;
+    }
+    const size_t attn_smem = fd_attn_smem(MC, FD_CHUNKS);
+    if (attn_smem > 64 * 1024) return fail(GTB_ERR_STATE, "batched decode: max_ctx too large for the attention kernel's score buffer");
+    const size_t norm_smem = fd_gemv_smem(E, true);
+    auto norm = [&](const float* src0, const float* src1, const uint16_t* w, float* res_out, bool embed) -> int {
+        FdArgs a{};
+        a.K = E; a.src0 = src0; a.src1 = src1; a.normw = w; a.res_out = res_out; a.st = b.st; a.act_out = b.norm_act;
+        a.n_seq = NS; a.tok_stride = MC + 2;
+        if (embed) { a.emb_w = (const uint8_t*)e->embed->data; a.emb_s = e->embed->scales; a.tokens = b.tokens; a.emb_dt = wd == GTB_Q8 ? DT_Q8 : DT_Q4; }
+        GTB_CUDA(fd_launch(k_fdb_norm, NS, norm_smem, a));
+        GTB_LAUNCHED();
+        return GTB_OK;
+    };
+    int r;
+    for (int li = 0; li < L; li++) {
+        LayerW& l = e->L[li];
+        if ((r = norm(li ? b.hres : nullptr, li ? b.rd : nullptr, l.attn_norm, b.xres, li == 0))) return r;
+        if ((r = launch_fdb<WT, FD_RAW>(gv[4 * li + 0], G))) return r;
+        FdAttnArgs t{};
+        t.rqkv = b.rqkv; t.n_embd = E; t.kv_dim = KV; t.gsz = e->gsz; t.kq = b.kq[li]; t.ks = b.ks[li]; t.vq = b.vq[li]; t.vs = b.vs[li];
+        t.rope_cos = e->rope_cos; t.rope_sin = e->rope_sin; t.st = b.st; t.parts = b.parts; t.counters = b.cnt; t.out = b.attn_act;
+        t.seq_kv_codes = (size_t)MC * KV; t.seq_kv_scales = (size_t)MC * (KV / 32); t.n_heads = c.n_heads;
+        {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(c.n_heads * FD_CHUNKS, NS); cfg.blockDim = dim3(FD_NT); cfg.dynamicSmemBytes = attn_smem; cfg.stream = ctx().stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            GTB_CUDA(cudaLaunchKernelEx(&cfg, k_fdb_attn, t));
+            GTB_LAUNCHED();
+        }
+        if ((r = launch_fdb<WT, FD_RAW>(gv[4 * li + 1], G))) return r;
+        if ((r = norm(b.xres, b.ro, l.ffn_norm, b.hres, false))) return r;
+        if ((r = launch_fdb<WT, FD_SILU>(gv[4 * li + 2], F / 32))) return r;
+        if ((r = launch_fdb<WT, FD_RAW>(gv[4 * li + 3], G))) return r;
+    }
+    if ((r = norm(b.hres, b.rd, e->final_norm, b.xfinal, false))) return r;
+    return launch_fdb<WT, FD_ARGMAX>(gv[4 * L], 2 * G);
+}
+
 int enqueue_row_dt(gtb_engine* e, bool with_head, int eos_id) {
     if (e->fast) {
         if (e->cfg.wdtype == GTB_Q8) return enqueue_row_fast<DT_Q8>(e, with_head, eos_id);
@@ -652,6 +812,7 @@ int enqueue_row_dt(gtb_engine* e, bool with_head, int eos_id) {
 
 void drop_graphs(gtb_engine* e) {
     e->fd_args_valid = false;
+    if (e->bb.graph) { cudaGraphExecDestroy(e->bb.graph); e->bb.graph = nullptr; }
     if (e->g_body) { cudaGraphExecDestroy(e->g_body); e->g_body = nullptr; }
     if (e->g_head) { cudaGraphExecDestroy(e->g_head); e->g_head = nullptr; }
 }
@@ -884,6 +1045,7 @@ int gtb_engine_destroy(gtb_engine_t e) {
     cudaFree(e->pf_cap);
     cudaFree(e->fd_parts); cudaFree(e->fd_cnt); cudaFree(e->fd_argv); cudaFree(e->fd_argi);
     cudaFree(e->d_fd_gemv); cudaFree(e->d_fd_attn); cudaFree(e->fd_bar);
+    batch_free(e);
     cudaFree(e->fd_attn.codes); cudaFree(e->fd_attn.ad); cudaFree(e->fd_attn.n7);
     cudaFree(e->fd_act.codes); cudaFree(e->fd_act.ad); cudaFree(e->fd_act.n7);
     delete e;
@@ -1196,6 +1358,104 @@ int gtb_engine_generate(gtb_engine_t e, int32_t* h_tokens, int n_prompt, int n_n
     GTB_CUDA(cudaStreamSynchronize(ctx().stream));
     e->host_pos = n_prompt + produced - 1;
     if (n_generated) *n_generated = produced;
+    return GTB_OK;
+}
+
+// ---- batched decode: n sequences advance together, one weight read per step for all of them
+int gtb_engine_batch_create(gtb_engine_t e, int n_seq) {
+    GTB_CHECK_INIT();
+    GTB_ARG(e && n_seq >= 0 && n_seq <= FDB_MAX);
+    if (e->cfg.wdtype == GTB_F16) return fail(GTB_ERR_STATE, "batched decode is built for Q8-activation models (Q8, Q4 weights)");
+    if (e->cfg.n_embd > 2048 || e->cfg.n_ffn > 6144) return fail(GTB_ERR_STATE, "batched decode: n_embd <= 2048 and n_ffn <= 6144");
+    return batch_alloc(e, n_seq);
+}
+
+// slot `seq` <- the engine's current sequence (tokens, position, K/V cache), e.g. after gtb_engine_prefill[_fast]
+int gtb_engine_batch_adopt(gtb_engine_t e, int seq) {
+    GTB_CHECK_INIT();
+    GTB_ARG(e && seq >= 0 && seq < e->bb.n);
+    const gtb_model_config& c = e->cfg;
+    auto& b = e->bb;
+    cudaStream_t st = ctx().stream;
+    DevState s;
+    GTB_CUDA(cudaMemcpyAsync(&s, e->st, sizeof s, cudaMemcpyDeviceToHost, st));
+    GTB_CUDA(cudaStreamSynchronize(st));
+    const int pos = s.pos;
+    GTB_ARG(pos >= 0 && pos < c.max_ctx);
+    const size_t KV = e->kv_dim, MC = c.max_ctx;
+    for (int li = 0; li < c.n_layers; li++) {
+        LayerW& l = e->L[li];
+        GTB_CUDA(cudaMemcpyAsync(b.kq[li] + seq * MC * KV, l.kq, (size_t)pos * KV, cudaMemcpyDeviceToDevice, st));
+        GTB_CUDA(cudaMemcpyAsync(b.vq[li] + seq * MC * KV, l.vq, (size_t)pos * KV, cudaMemcpyDeviceToDevice, st));
+        GTB_CUDA(cudaMemcpyAsync(b.ks[li] + seq * MC * (KV / 32), l.ks, (size_t)pos * (KV / 32) * 2, cudaMemcpyDeviceToDevice, st));
+        GTB_CUDA(cudaMemcpyAsync(b.vs[li] + seq * MC * (KV / 32), l.vs, (size_t)pos * (KV / 32) * 2, cudaMemcpyDeviceToDevice, st));
+    }
+    GTB_CUDA(cudaMemcpyAsync(b.tokens + (size_t)seq * (MC + 2), e->tokens, (size_t)(pos + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    DevState ns{pos, 0, 0, 0};
+    GTB_CUDA(cudaMemcpyAsync(b.st + seq, &ns, sizeof ns, cudaMemcpyHostToDevice, st));
+    GTB_CUDA(cudaStreamSynchronize(st));
+    b.host_pos[seq] = pos;
+    return GTB_OK;
+}
+
+int gtb_engine_batch_decode(gtb_engine_t e, int n_steps) {
+    GTB_CHECK_INIT();
+    GTB_ARG(e && n_steps > 0 && e->bb.n > 0);
+    int r = check_loaded(e);
+    if (r) return r;
+    auto& b = e->bb;
+    for (int s = 0; s < b.n; s++)
+        if (b.host_pos[s] + n_steps > e->cfg.max_ctx) return fail(GTB_ERR_ARG, "batch decode past max_ctx (sequence %d: %d + %d > %d)", s, b.host_pos[s], n_steps, e->cfg.max_ctx);
+    cudaStream_t st = ctx().stream;
+    if (e->use_graph) {
+        if (!b.graph) {
+            const int64_t before = ctx().launches;
+            GTB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            r = (e->cfg.wdtype == GTB_Q8) ? enqueue_batch_row<DT_Q8>(e) : enqueue_batch_row<DT_Q4>(e);
+            cudaGraph_t g = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(st, &g);
+            b.graph_launches = (int)(ctx().launches - before);
+            ctx().launches = before;
+            if (r) { if (g) cudaGraphDestroy(g); return r; }
+            if (ce != cudaSuccess) return fail(GTB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&b.graph, g, 0);
+            cudaGraphDestroy(g);
+            if (ce != cudaSuccess) return fail(GTB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+        }
+        for (int i = 0; i < n_steps; i++) { GTB_CUDA(cudaGraphLaunch(b.graph, st)); ctx().launches += b.graph_launches; }
+    } else {
+        for (int i = 0; i < n_steps; i++) {
+            r = (e->cfg.wdtype == GTB_Q8) ? enqueue_batch_row<DT_Q8>(e) : enqueue_batch_row<DT_Q4>(e);
+            if (r) return r;
+        }
+    }
+    for (int s = 0; s < b.n; s++) b.host_pos[s] += n_steps;
+    return GTB_OK;
+}
+
+int gtb_engine_batch_position(gtb_engine_t e, int seq, int* pos) {
+    GTB_CHECK_INIT();
+    GTB_ARG(e && pos && seq >= 0 && seq < e->bb.n);
+    DevState s;
+    GTB_CUDA(cudaMemcpyAsync(&s, e->bb.st + seq, sizeof s, cudaMemcpyDeviceToHost, ctx().stream));
+    GTB_CUDA(cudaStreamSynchronize(ctx().stream));
+    *pos = s.pos;
+    return GTB_OK;
+}
+
+int gtb_engine_batch_read_tokens(gtb_engine_t e, int seq, int32_t* h_tokens, int first, int count) {
+    GTB_CHECK_INIT();
+    GTB_ARG(e && h_tokens && seq >= 0 && seq < e->bb.n && first >= 0 && count > 0 && first + count <= e->cfg.max_ctx + 2);
+    GTB_CUDA(cudaMemcpyAsync(h_tokens, e->bb.tokens + (size_t)seq * (e->cfg.max_ctx + 2) + first, (size_t)count * 4, cudaMemcpyDeviceToHost, ctx().stream));
+    GTB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return GTB_OK;
+}
+
+int gtb_engine_batch_read_logits(gtb_engine_t e, int seq, float* h_logits) {
+    GTB_CHECK_INIT();
+    GTB_ARG(e && h_logits && seq >= 0 && seq < e->bb.n);
+    GTB_CUDA(cudaMemcpyAsync(h_logits, e->bb.logits + (size_t)seq * e->cfg.n_vocab, (size_t)e->cfg.n_vocab * 4, cudaMemcpyDeviceToHost, ctx().stream));
+    GTB_CUDA(cudaStreamSynchronize(ctx().stream));
     return GTB_OK;
 }
 

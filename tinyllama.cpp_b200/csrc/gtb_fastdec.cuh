@@ -52,6 +52,7 @@ struct FdArgs {
     FdAct act_out; int n_ffn;                                 // SILU epilogue
     float* arg_val; int* arg_idx; unsigned* counter; int32_t* tok_out; DevState* st; int eos_id;   // ARGMAX epilogue
     const void* pf[2]; size_t pf_bytes[2];                    // L2 look-ahead: data and scale planes of a later GEMV
+    int n_seq, tok_stride;                                    // batched decode (k_fdb_*): sequences, tokens row stride
 };
 
 __device__ __forceinline__ void fd_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -212,6 +213,80 @@ static __host__ __device__ inline size_t fd_gemv_smem(int K, bool norm) {
 }
 
 // NBL = blocks per lane (K <= 32 * 32 * NBL), R = rows per warp pass
+// NORM prologue: x = E(res + E(delta)) or the embedding row, RMSNorm, E -> staged vector `sv` (shared memory).  Whole CTA.
+template <int NQ>
+__device__ __forceinline__ void fd_norm_stage(const FdArgs& a, const FdStaged& sv, float* scratch, const uint2 (&nw)[NQ], int pos, bool write_res) {
+    const int K = a.K, nb = K / 32, tid = threadIdx.x;
+    // x = E(res + E(delta)) (ops.h:870-898) or the embedding row (ops.h:514-564); y = E(x / (rms(x) + 1e-6) * w) (ops.h:762-804)
+    // NQ quads per thread, all loads of the pass in flight at once, x stays in registers
+    const int nq = K / 4;
+    float x[NQ][4];
+    float ssq = 0.0f;
+    if (a.emb_w) {
+        const size_t erow = (size_t)__ldcg(a.tokens + pos);
+#pragma unroll
+        for (int it = 0; it < NQ; it++) {
+            const int qd = it * FD_NT + tid;
+            const int e0 = 4 * ((qd < nq) ? qd : 0);
+            const size_t blk = erow * nb + (e0 >> 5);
+            const float delta = h2f(a.emb_s[blk]);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int el = (e0 & 31) + i;
+                if (a.emb_dt == DT_Q8) {
+                    x[it][i] = __fmul_rn((float)(int8_t)a.emb_w[blk * 32 + perm_byte(el)], delta);
+                } else {
+                    const int j = el & 15;
+                    const uint8_t byte = a.emb_w[blk * 16 + ((j & 7) >> 1) * 4 + (j & 1) + 2 * (j >> 3)];
+                    x[it][i] = __fmul_rn((float)((int)((el < 16) ? (byte >> 4) : (byte & 0x0f)) - 7), delta);
+                }
+            }
+            if (a.emb_dt != DT_Q8) fd_quad_roundtrip(x[it]);      // Q4 row: dequantise, re-encode as Q8 (ops.h:522-528)
+        }
+    } else {
+        float4 s0[NQ], s1[NQ];
+#pragma unroll
+        for (int it = 0; it < NQ; it++) {
+            const int qd = it * FD_NT + tid;
+            const int e0 = 4 * ((qd < nq) ? qd : 0);
+            s0[it] = __ldcg(reinterpret_cast<const float4*>(a.src0 + e0));
+            if (a.src1) s1[it] = __ldcg(reinterpret_cast<const float4*>(a.src1 + e0));
+        }
+#pragma unroll
+        for (int it = 0; it < NQ; it++) {
+            x[it][0] = s0[it].x; x[it][1] = s0[it].y; x[it][2] = s0[it].z; x[it][3] = s0[it].w;
+            if (a.src1) {
+                float t[4] = {s1[it].x, s1[it].y, s1[it].z, s1[it].w};
+                fd_quad_roundtrip(t);
+#pragma unroll
+                for (int i = 0; i < 4; i++) x[it][i] = __fadd_rn(x[it][i], t[i]);
+                fd_quad_roundtrip(x[it]);
+            }
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < NQ; it++) {
+        const int qd = it * FD_NT + tid;
+        if (qd < nq) {
+            if (write_res && a.res_out) *reinterpret_cast<float4*>(a.res_out + 4 * qd) = make_float4(x[it][0], x[it][1], x[it][2], x[it][3]);
+            ssq += (x[it][0] * x[it][0] + x[it][1] * x[it][1]) + (x[it][2] * x[it][2] + x[it][3] * x[it][3]);
+        }
+    }
+    ssq = fd_block_sum(ssq, scratch);
+    const float rden = 1.0f / (sqrtf(ssq / (float)K) + 1e-6f);
+#pragma unroll
+    for (int it = 0; it < NQ; it++) {
+        const int qd = it * FD_NT + tid;
+        const bool valid = qd < nq;
+        const int e0 = 4 * (valid ? qd : 0);
+        float y[4];
+        y[0] = __fmul_rn(x[it][0] * rden, h2f((uint16_t)(nw[it].x & 0xffffu)));
+        y[1] = __fmul_rn(x[it][1] * rden, h2f((uint16_t)(nw[it].x >> 16)));
+        y[2] = __fmul_rn(x[it][2] * rden, h2f((uint16_t)(nw[it].y & 0xffffu)));
+        y[3] = __fmul_rn(x[it][3] * rden, h2f((uint16_t)(nw[it].y >> 16)));
+        fd_stage_quad(sv, e0 >> 5, (e0 & 31) >> 2, y, valid);
+    }
+}
 // `sync()` orders this phase after its producer: griddepcontrol.wait in the one-kernel-per-phase chain, a grid barrier in the
 // persistent kernel.  Everything before it touches only weights.
 template <int WT, int PRO, int EPI, int NBL, int R, typename Sync>
@@ -268,75 +343,7 @@ __device__ __forceinline__ void fd_gemv_phase(const FdArgs& a, unsigned char* sm
     const int pos = (pos_in >= 0) ? pos_in : ((PRO == FD_NORM && a.emb_w) ? __ldcg(&a.st->pos) : 0);
     // ---- prologue: the staged input vector
     if (PRO == FD_NORM) {
-        // x = E(res + E(delta)) (ops.h:870-898) or the embedding row (ops.h:514-564); y = E(x / (rms(x) + 1e-6) * w) (ops.h:762-804)
-        // NQ quads per thread, all loads of the pass in flight at once, x stays in registers
-        const int nq = K / 4;
-        float x[NQ][4];
-        float ssq = 0.0f;
-        if (a.emb_w) {
-            const size_t erow = (size_t)__ldcg(a.tokens + pos);
-#pragma unroll
-            for (int it = 0; it < NQ; it++) {
-                const int qd = it * FD_NT + tid;
-                const int e0 = 4 * ((qd < nq) ? qd : 0);
-                const size_t blk = erow * nb + (e0 >> 5);
-                const float delta = h2f(a.emb_s[blk]);
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int el = (e0 & 31) + i;
-                    if (a.emb_dt == DT_Q8) {
-                        x[it][i] = __fmul_rn((float)(int8_t)a.emb_w[blk * 32 + perm_byte(el)], delta);
-                    } else {
-                        const int j = el & 15;
-                        const uint8_t byte = a.emb_w[blk * 16 + ((j & 7) >> 1) * 4 + (j & 1) + 2 * (j >> 3)];
-                        x[it][i] = __fmul_rn((float)((int)((el < 16) ? (byte >> 4) : (byte & 0x0f)) - 7), delta);
-                    }
-                }
-                if (a.emb_dt != DT_Q8) fd_quad_roundtrip(x[it]);      // Q4 row: dequantise, re-encode as Q8 (ops.h:522-528)
-            }
-        } else {
-            float4 s0[NQ], s1[NQ];
-#pragma unroll
-            for (int it = 0; it < NQ; it++) {
-                const int qd = it * FD_NT + tid;
-                const int e0 = 4 * ((qd < nq) ? qd : 0);
-                s0[it] = __ldcg(reinterpret_cast<const float4*>(a.src0 + e0));
-                if (a.src1) s1[it] = __ldcg(reinterpret_cast<const float4*>(a.src1 + e0));
-            }
-#pragma unroll
-            for (int it = 0; it < NQ; it++) {
-                x[it][0] = s0[it].x; x[it][1] = s0[it].y; x[it][2] = s0[it].z; x[it][3] = s0[it].w;
-                if (a.src1) {
-                    float t[4] = {s1[it].x, s1[it].y, s1[it].z, s1[it].w};
-                    fd_quad_roundtrip(t);
-#pragma unroll
-                    for (int i = 0; i < 4; i++) x[it][i] = __fadd_rn(x[it][i], t[i]);
-                    fd_quad_roundtrip(x[it]);
-                }
-            }
-        }
-#pragma unroll
-        for (int it = 0; it < NQ; it++) {
-            const int qd = it * FD_NT + tid;
-            if (qd < nq) {
-                if (blockIdx.x == 0 && a.res_out) *reinterpret_cast<float4*>(a.res_out + 4 * qd) = make_float4(x[it][0], x[it][1], x[it][2], x[it][3]);
-                ssq += (x[it][0] * x[it][0] + x[it][1] * x[it][1]) + (x[it][2] * x[it][2] + x[it][3] * x[it][3]);
-            }
-        }
-        ssq = fd_block_sum(ssq, scratch);
-        const float rden = 1.0f / (sqrtf(ssq / (float)K) + 1e-6f);
-#pragma unroll
-        for (int it = 0; it < NQ; it++) {
-            const int qd = it * FD_NT + tid;
-            const bool valid = qd < nq;
-            const int e0 = 4 * (valid ? qd : 0);
-            float y[4];
-            y[0] = __fmul_rn(x[it][0] * rden, h2f((uint16_t)(nw[it].x & 0xffffu)));
-            y[1] = __fmul_rn(x[it][1] * rden, h2f((uint16_t)(nw[it].x >> 16)));
-            y[2] = __fmul_rn(x[it][2] * rden, h2f((uint16_t)(nw[it].y & 0xffffu)));
-            y[3] = __fmul_rn(x[it][3] * rden, h2f((uint16_t)(nw[it].y >> 16)));
-            fd_stage_quad(sv, e0 >> 5, (e0 & 31) >> 2, y, valid);
-        }
+        fd_norm_stage<NQ>(a, sv, scratch, nw, pos, blockIdx.x == 0);
     } else {
         const uint4* src = reinterpret_cast<const uint4*>(a.in.codes);
         for (int i = tid; i < K / 16; i += FD_NT) reinterpret_cast<uint4*>(sv.aw)[i] = __ldcg(src + i);
@@ -467,6 +474,8 @@ struct FdAttnArgs {
     unsigned* counters;       // [n_heads]
     FdAct out;                // E(attention output) staged for the o GEMV
     const void* pf[2]; size_t pf_bytes[2];
+    size_t seq_kv_codes, seq_kv_scales;          // batched decode: per-sequence strides of the K/V cache planes
+    int n_heads;
 };
 
 struct FdAttnSmem {
@@ -802,6 +811,256 @@ __global__ void __launch_bounds__(FD_NT, 1) k_fd_mega(FdMegaParams P) {
             if (blockIdx.x == 0 && threadIdx.x == 0) P.st->pos = pos + 1;
         }
     }
+}
+
+// ---------------------------------------------------------------- batched decode: FDB_MAX sequences share every weight read
+// SURVEY.md 8(f3).  The same phases with a sequence dimension: per-sequence buffers are [n_seq][...] arrays, every sequence
+// has its own position (DevState), token row and K/V cache.  A weight block is loaded once and dotted against the staged
+// vectors of all sequences; per sequence the arithmetic (block order, lane split, reductions) is exactly that of the
+// single-sequence chain, so a sequence decoded in a batch gives the same bits as decoded alone (tests/test_fastdec_gpu.py).
+// The redundant per-CTA NORM prologue would cost n_seq times as much, so the norm is its own small kernel here (one CTA per
+// sequence) and every GEMV starts from staged codes.
+constexpr int FDB_MAX = 8;
+
+__global__ void __launch_bounds__(FD_NT) k_fdb_norm(FdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int K = a.K, nb = K / 32, s = blockIdx.x, tid = threadIdx.x;
+    FdStaged sv;
+    sv.aw = reinterpret_cast<uint32_t*>(smem);
+    sv.ad = reinterpret_cast<float*>(smem + (size_t)nb * 32);
+    sv.n7 = reinterpret_cast<int*>(smem + (size_t)nb * 36);
+    float* scratch = reinterpret_cast<float*>(smem + ((((size_t)nb * 40) + 15) & ~(size_t)15));
+    fd_launch_dependents();
+    constexpr int NQ = 2;
+    uint2 nw[NQ];
+#pragma unroll
+    for (int it = 0; it < NQ; it++) {
+        const int qd = it * FD_NT + tid;
+        nw[it] = *reinterpret_cast<const uint2*>(a.normw + 4 * ((qd < K / 4) ? qd : 0));
+    }
+    fd_wait_prior();
+    FdArgs b = a;
+    if (b.src0) b.src0 += (size_t)s * K;
+    if (b.src1) b.src1 += (size_t)s * K;
+    if (b.res_out) b.res_out += (size_t)s * K;
+    if (b.tokens) b.tokens += (size_t)s * a.tok_stride;
+    const int pos = a.emb_w ? __ldcg(&a.st[s].pos) : 0;
+    fd_norm_stage<NQ>(b, sv, scratch, nw, pos, true);
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(a.act_out.codes + (size_t)s * K);
+    for (int i = tid; i < K / 16; i += FD_NT) dst[i] = reinterpret_cast<const uint4*>(sv.aw)[i];
+    for (int i = tid; i < nb; i += FD_NT) { a.act_out.ad[(size_t)s * nb + i] = sv.ad[i]; a.act_out.n7[(size_t)s * nb + i] = sv.n7[i]; }
+}
+
+static __host__ __device__ inline size_t fdb_gemv_smem(int K, int n_seq) {
+    return (size_t)n_seq * (K / 32) * 40 + (size_t)FDB_MAX * 64 * 4 + 256;
+}
+
+template <int WT, int EPI, int NBL, int R>
+__global__ void __launch_bounds__(FD_NT, 2) k_fdb_gemv(FdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int K = a.K, nb = K / 32, NS = a.n_seq;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // staged vectors of all sequences: [NS][nb][8] words, [NS][nb] scales, [NS][nb] -7 * code sums
+    uint32_t* s_aw = reinterpret_cast<uint32_t*>(smem);
+    float* s_ad = reinterpret_cast<float*>(smem + (size_t)NS * nb * 32);
+    int* s_n7 = reinterpret_cast<int*>(smem + (size_t)NS * nb * 36);
+    float* scratch = reinterpret_cast<float*>(smem + (((size_t)NS * nb * 40 + 15) & ~(size_t)15));          // [FDB_MAX][64]
+    fd_launch_dependents();
+    if (tid < 2 && a.pf[tid]) {
+        const size_t per = ((a.pf_bytes[tid] + gridDim.x - 1) / gridDim.x + 127) & ~(size_t)127;
+        const size_t off = per * blockIdx.x;
+        if (off < a.pf_bytes[tid]) l2_prefetch(reinterpret_cast<const unsigned char*>(a.pf[tid]) + off, min(per, a.pf_bytes[tid] - off));
+    }
+    int v0, v1, unit = blockIdx.x;
+    const int n_units = (EPI == FD_SILU) ? a.n_ffn / 32 : 1;
+    if (EPI == FD_SILU) { v0 = 0; v1 = (unit < n_units) ? 64 : 0; }
+    else { v0 = (int)(((long long)blockIdx.x * a.n_rows) / gridDim.x); v1 = (int)(((long long)(blockIdx.x + 1) * a.n_rows) / gridDim.x); }
+    auto rows_of = [&](int v, int (&row)[R]) {
+#pragma unroll
+        for (int u = 0; u < R; u++) {
+            const int vv = v + u;
+            if (vv >= v1) row[u] = -1;
+            else if (EPI == FD_SILU) row[u] = (vv < 32) ? unit * 32 + vv : a.n_ffn + unit * 32 + (vv - 32);
+            else row[u] = vv;
+        }
+    };
+    FdBatch<WT, NBL, R> bt;
+    int row[R];
+    int v = v0 + wid * R;
+    rows_of(v, row);
+    fd_load_batch<WT, NBL, R>(bt, a.w, a.ws, row, nb);
+    fd_wait_prior();
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(a.in.codes);
+        for (int i = tid; i < NS * (K / 16); i += FD_NT) reinterpret_cast<uint4*>(s_aw)[i] = __ldcg(src + i);
+        for (int i = tid; i < NS * nb; i += FD_NT) { s_ad[i] = __ldcg(a.in.ad + i); s_n7[i] = __ldcg(a.in.n7 + i); }
+    }
+    __syncthreads();
+    float best = -INFINITY;          // ARGMAX: lane u * 8 + s tracks sequence s over its rows
+    int arg = 0x7fffffff;
+    for (; v < v1;) {
+        float acc[R][FDB_MAX];
+#pragma unroll
+        for (int u = 0; u < R; u++)
+#pragma unroll
+            for (int s = 0; s < FDB_MAX; s++) acc[u][s] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NBL; i++) {
+            const int b = lane + 32 * i;
+            if (b < nb) {
+                float dw[R];
+#pragma unroll
+                for (int u = 0; u < R; u++) dw[u] = h2f((uint16_t)bt.sc[u][i]);
+#pragma unroll
+                for (int s = 0; s < FDB_MAX; s++) {
+                    if (s < NS) {
+                        const uint4 ax = reinterpret_cast<const uint4*>(s_aw)[((size_t)s * nb + b) * 2];
+                        const uint4 ay = reinterpret_cast<const uint4*>(s_aw)[((size_t)s * nb + b) * 2 + 1];
+                        const int n7 = (WT == DT_Q4) ? s_n7[s * nb + b] : 0;
+                        const float ad = s_ad[s * nb + b];
+#pragma unroll
+                        for (int u = 0; u < R; u++) {
+                            const int is = fd_block_isum<WT>(bt.a[u][i], bt.b[(WT == DT_Q8) ? u : 0][(WT == DT_Q8) ? i : 0], ax, ay, n7);
+                            acc[u][s] = fmaf((float)is, __fmul_rn(ad, dw[u]), acc[u][s]);
+                        }
+                    }
+                }
+            }
+        }
+        // warp reduce-scatter of the R x 8 sums: lane j ends up with the total of (row j / 8, sequence j % 8).  Offsets run
+        // 16, 8, 4, 2, 1 like the butterfly of the single-sequence kernel, so every total is the same tree of additions.
+        constexpr int NV = R * FDB_MAX;
+        float vals[NV];
+#pragma unroll
+        for (int u = 0; u < R; u++)
+#pragma unroll
+            for (int s = 0; s < FDB_MAX; s++) vals[u * FDB_MAX + s] = acc[u][s];
+        {
+            int n = NV;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                if (n > off) {                       // halve: keep one half of the values, receive the partner's sums of it
+                    const int half = n / 2;
+                    const bool up = (lane & off) != 0;
+#pragma unroll
+                    for (int k = 0; k < NV / 2; k++) {
+                        if (k < half) {
+                            const float send = up ? vals[k] : vals[k + half];
+                            const float keep = up ? vals[k + half] : vals[k];
+                            vals[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                    }
+                    n = half;
+                } else {                             // fewer values than lanes: plain butterfly for the leading offsets
+#pragma unroll
+                    for (int k = 0; k < NV; k++) vals[k] += __shfl_xor_sync(0xffffffffu, vals[k], off);
+                }
+            }
+        }
+        const float mine = vals[0];
+        const int vcur = v;
+        int rcur[R];
+#pragma unroll
+        for (int u = 0; u < R; u++) rcur[u] = row[u];
+        v += FD_NW * R;
+        if (v < v1) { rows_of(v, row); fd_load_batch<WT, NBL, R>(bt, a.w, a.ws, row, nb); }
+        const int mu = (lane & (NV - 1)) / FDB_MAX, ms = lane % FDB_MAX;
+        int mrow = -1;
+#pragma unroll
+        for (int u = 0; u < R; u++) if (mu == u) mrow = rcur[u];
+        if (lane < NV && ms < NS && mrow >= 0) {
+            if (EPI == FD_SILU) {
+                scratch[ms * 64 + vcur + mu] = mine;
+            } else {
+                a.out[(size_t)ms * a.n_rows + mrow] = mine;
+                if (EPI == FD_ARGMAX && mine > best) { best = mine; arg = mrow; }
+            }
+        }
+    }
+    if (EPI == FD_SILU && unit < n_units) {
+        __syncthreads();
+        if (wid < NS) {                  // warp s: E(E(silu(E(gate))) * E(up)) of sequence s (modules.cpp:238-247)
+            const float g1 = fd_lane_roundtrip(scratch[wid * 64 + lane]);
+            const float u1 = fd_lane_roundtrip(scratch[wid * 64 + 32 + lane]);
+            const float g2 = fd_lane_roundtrip(__fdividef(g1, 1.0f + __expf(-g1)));
+            float dd;
+            const int q = fd_lane_encode(g2 * u1, &dd);
+            int sum = q;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            a.act_out.codes[(size_t)wid * a.n_ffn + unit * 32 + perm_byte(lane)] = (uint8_t)(int8_t)q;
+            if (lane == 0) { a.act_out.ad[(size_t)wid * n_units + unit] = dd; a.act_out.n7[(size_t)wid * n_units + unit] = -7 * sum; }
+        }
+    }
+    if (EPI == FD_ARGMAX) {
+        // rows of this warp for sequence ms: lanes ms, 8 + ms, 16 + ms, 24 + ms; then the 8 warps; then the last CTA over all CTAs
+        float* sval = scratch;                                   // [FD_NW][FDB_MAX]
+        int* sidx = reinterpret_cast<int*>(scratch + 64);        // [FD_NW][FDB_MAX]
+        __shared__ bool is_last;
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
+        }
+        if (lane < FDB_MAX) { sval[wid * FDB_MAX + lane] = best; sidx[wid * FDB_MAX + lane] = arg; }
+        __syncthreads();
+        if (tid < NS) {
+            best = sval[tid]; arg = sidx[tid];
+            for (int w = 1; w < FD_NW; w++) {
+                const float ov = sval[w * FDB_MAX + tid];
+                const int oi = sidx[w * FDB_MAX + tid];
+                if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
+            }
+            a.arg_val[(size_t)tid * gridDim.x + blockIdx.x] = best;
+            a.arg_idx[(size_t)tid * gridDim.x + blockIdx.x] = arg;
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) is_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (is_last && wid < NS) {
+            __threadfence();
+            best = -INFINITY; arg = 0x7fffffff;
+            for (int c = lane; c < (int)gridDim.x; c += 32) {
+                const float ov = __ldcg(a.arg_val + (size_t)wid * gridDim.x + c);
+                const int oi = __ldcg(a.arg_idx + (size_t)wid * gridDim.x + c);
+                if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+                if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
+            }
+            if (lane == 0) {
+                if (arg == 0x7fffffff) arg = 0;
+                DevState* st = a.st + wid;
+                const int pcur = __ldcg(&st->pos);
+                a.tok_out[(size_t)wid * a.tok_stride + pcur + 1] = arg;
+                st->pos = pcur + 1;
+                st->n_gen = __ldcg(&st->n_gen) + 1;
+            }
+        }
+        if (is_last && tid == 0) *a.counter = 0u;
+    }
+}
+
+// attention of sequence blockIdx.y: the single-sequence phase on that sequence's slices
+__global__ void __launch_bounds__(FD_NT, 2) k_fdb_attn(FdAttnArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    fd_launch_dependents();
+    const int s = blockIdx.y;
+    FdAttnArgs b = a;
+    b.rqkv += (size_t)s * (a.n_embd + 2 * a.kv_dim);
+    b.kq += s * a.seq_kv_codes; b.vq += s * a.seq_kv_codes; b.ks += s * a.seq_kv_scales; b.vs += s * a.seq_kv_scales;
+    b.st += s;
+    b.parts += (size_t)s * a.n_heads * FD_CHUNKS * FD_PART;
+    b.counters += (size_t)s * (a.n_heads + 1);
+    b.out.codes += (size_t)s * a.n_embd; b.out.ad += (size_t)s * (a.n_embd / 32); b.out.n7 += (size_t)s * (a.n_embd / 32);
+    FdPdlSync sync;
+    fd_attn_phase<1>(b, smem, sync, a.n_heads, FD_CHUNKS, -1);
 }
 
 }  // namespace gtb
