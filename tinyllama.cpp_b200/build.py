@@ -67,5 +67,6 @@ def build(force: bool = False, verbose: bool = False, extra: list[str] | None = 
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True, extra=["-Xptxas", "-v"] if "--ptxas" in sys.argv else None)
+    extra = (["-Xptxas", "-v"] if "--ptxas" in sys.argv else []) + (["-DGTB_FD_TRACE"] if "--trace" in sys.argv else [])
+    build(force="--force" in sys.argv or "--trace" in sys.argv, verbose=True, extra=extra or None)
     print("built", LIB)

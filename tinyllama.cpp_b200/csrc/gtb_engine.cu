@@ -1527,6 +1527,13 @@ int gtb_engine_set_option(gtb_engine_t e, const char* name, int value) {
     if (!strcmp(name, "fast_decode")) { e->fast = value != 0; drop_graphs(e); return GTB_OK; }
     if (!strcmp(name, "fd_ahead")) { GTB_ARG(value >= 0 && value <= 16); e->fd_ahead = value; drop_graphs(e); e->fd_args_valid = false; return GTB_OK; }
     if (!strcmp(name, "fd_prof_cta")) { GTB_ARG(value >= 0); e->fd_prof_cta = value; return GTB_OK; }
+    if (!strcmp(name, "fd_trace")) {          // debug timeline of the fast-decode chains into the "prof" buffer (gtb_engine_read_prof)
+        long long* p = value ? e->d_prof : nullptr;
+        GTB_CUDA(cudaMemsetAsync(e->d_prof, 0, 8, ctx().stream));
+        GTB_CUDA(cudaMemcpyToSymbolAsync(g_fd_trace, &p, sizeof p, 0, cudaMemcpyHostToDevice, ctx().stream));
+        GTB_CUDA(cudaStreamSynchronize(ctx().stream));
+        return GTB_OK;
+    }
     if (!strcmp(name, "fd_mega")) { e->fd_mega = value != 0; return GTB_OK; }
     if (!strcmp(name, "pf_layers")) { GTB_ARG(value >= 0); e->pf_layers = value; return GTB_OK; }
     if (!strcmp(name, "pf_fused")) { e->pf_fused = value != 0; return GTB_OK; }

@@ -55,6 +55,21 @@ struct FdArgs {
     int n_seq, tok_stride;                                    // batched decode (k_fdb_*): sequences, tokens row stride
 };
 
+// debug timeline (option "fd_trace"): CTA 0 of every kernel of the chains stamps %globaltimer at entry, after the dependency wait
+// and at its end; entry i = (tag << 48) | ns, tag = kernel kind * 4 + stage
+// Compiled in with -DGTB_FD_TRACE only (python tinyllama.cpp_b200/build.py --trace): the pointer load alone costs ~0.5 us per kernel.
+__device__ long long* g_fd_trace = nullptr;
+#ifdef GTB_FD_TRACE
+__device__ __forceinline__ void fd_trace(int tag) {
+    if (g_fd_trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        const unsigned slot = atomicAdd(reinterpret_cast<unsigned*>(g_fd_trace), 1u);
+        if (slot < 4000) g_fd_trace[1 + slot] = ((long long)tag << 48) | (gtimer() & 0xffffffffffffll);
+    }
+}
+#else
+__device__ __forceinline__ void fd_trace(int) {}
+#endif
+
 __device__ __forceinline__ void fd_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void fd_wait_prior() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
@@ -453,16 +468,18 @@ __device__ __forceinline__ void fd_gemv_phase(const FdArgs& a, unsigned char* sm
 
 struct FdPdlSync {
     __device__ __forceinline__ void arrive() {}
-    __device__ __forceinline__ void wait() { fd_wait_prior(); }
+    __device__ __forceinline__ void wait() { fd_wait_prior(); fd_trace(7 * 4 + 1); }
     __device__ __forceinline__ void stamp() {}
 };
 
 template <int WT, int PRO, int EPI, int NBL, int R>
 __global__ void __launch_bounds__(FD_NT, 2) k_fd_gemv(FdArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
+    fd_trace((1 + EPI) * 4 + 0);
     fd_launch_dependents();
     FdPdlSync sync;
     fd_gemv_phase<WT, PRO, EPI, NBL, R>(a, smem, sync, -1);
+    fd_trace((1 + EPI) * 4 + 2);
 }
 
 // ---------------------------------------------------------------- attention: one CTA = (head, position chunk)
@@ -497,7 +514,7 @@ static __host__ __device__ inline size_t fd_attn_smem(int max_ctx, int nch) {
 // whole 32-position blocks of the probability row (the re-encode unit of ops.h:996) and keeps its own running
 // (max, sum, 64 outputs); warps meet once per chunk.  KPT = blocks per warp whose K/V rows are loaded up front.
 template <int KPT, typename Sync>
-__device__ __forceinline__ void fd_attn_phase(const FdAttnArgs& a, unsigned char* smem, Sync& sync, int n_heads, int nch, int pos_in) {
+__device__ __forceinline__ void fd_attn_phase(const FdAttnArgs& a, unsigned char* smem, Sync& sync, int n_heads, int nch_max, int pos_in) {
     FdAttnSmem& sm = *reinterpret_cast<FdAttnSmem*>(smem);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int slot = lane >> 2, cq = lane & 3;          // P.V: lane = (position slot of 8, 16 channels)
@@ -506,8 +523,12 @@ __device__ __forceinline__ void fd_attn_phase(const FdAttnArgs& a, unsigned char
     sync.wait();
     sync.stamp();
     const int pos = (pos_in >= 0) ? pos_in : __ldcg(&a.st->pos);
-    for (int unit = blockIdx.x; unit < n_heads * nch; unit += gridDim.x) {
-    const int h = unit / nch, c = unit % nch, g = h / a.gsz;
+    // chunks in use grow with the context (one per KPT * 256 positions, at most nch_max): short contexts do not pay for
+    // partials, counters and combines of empty chunks
+    const int nch = min(nch_max, max(1, (pos + KPT * 256) / (KPT * 256)));
+    for (int unit = blockIdx.x; unit < n_heads * nch_max; unit += gridDim.x) {
+    const int h = unit / nch_max, c = unit % nch_max, g = h / a.gsz;
+    if (c >= nch) continue;
     const bool writer = (h % a.gsz) == 0 && c == 0;
     // chunk of positions [lo, hi), aligned to the 32-position blocks of the probability row
     const int per = ((pos + 1 + nch - 1) / nch + 31) & ~31;
@@ -585,7 +606,7 @@ __device__ __forceinline__ void fd_attn_phase(const FdAttnArgs& a, unsigned char
     }
     __syncthreads();
     sync.stamp();
-    float* part = a.parts + ((size_t)h * nch + c) * FD_PART;
+    float* part = a.parts + ((size_t)h * nch_max + c) * FD_PART;
     // ---- this warp's blocks: scores (x 1/sqrt(64)), block softmax numerators, E(P), P.V, merged into the warp's running state
     float m_w = -INFINITY, l_w = 0.0f;
     float acc[16];
@@ -695,7 +716,7 @@ __device__ __forceinline__ void fd_attn_phase(const FdAttnArgs& a, unsigned char
     if (sm.last) {
     __threadfence();
     if (wid < 2) {
-        const float* p = a.parts + (size_t)h * nch * FD_PART;
+        const float* p = a.parts + (size_t)h * nch_max * FD_PART;
         float m = -INFINITY;
         for (int cc = 0; cc < nch; cc++) m = fmaxf(m, __ldcg(p + cc * FD_PART + 64));
         float l = 0.0f, o = 0.0f;
@@ -722,9 +743,11 @@ __device__ __forceinline__ void fd_attn_phase(const FdAttnArgs& a, unsigned char
 
 __global__ void __launch_bounds__(FD_NT, 2) k_fd_attn(FdAttnArgs a, int n_heads) {
     extern __shared__ __align__(16) unsigned char smem[];
+    fd_trace(4 * 4 + 0);
     fd_launch_dependents();
     FdPdlSync sync;
     fd_attn_phase<1>(a, smem, sync, n_heads, FD_CHUNKS, -1);
+    fd_trace(4 * 4 + 2);
 }
 
 // ---------------------------------------------------------------- the same phases as ONE persistent cooperative kernel
@@ -830,6 +853,7 @@ __global__ void __launch_bounds__(FD_NT) k_fdb_norm(FdArgs a) {
     sv.ad = reinterpret_cast<float*>(smem + (size_t)nb * 32);
     sv.n7 = reinterpret_cast<int*>(smem + (size_t)nb * 36);
     float* scratch = reinterpret_cast<float*>(smem + ((((size_t)nb * 40) + 15) & ~(size_t)15));
+    fd_trace(0 * 4 + 0);
     fd_launch_dependents();
     constexpr int NQ = 2;
     uint2 nw[NQ];
@@ -839,6 +863,7 @@ __global__ void __launch_bounds__(FD_NT) k_fdb_norm(FdArgs a) {
         nw[it] = *reinterpret_cast<const uint2*>(a.normw + 4 * ((qd < K / 4) ? qd : 0));
     }
     fd_wait_prior();
+    fd_trace(0 * 4 + 1);
     FdArgs b = a;
     if (b.src0) b.src0 += (size_t)s * K;
     if (b.src1) b.src1 += (size_t)s * K;
@@ -850,6 +875,7 @@ __global__ void __launch_bounds__(FD_NT) k_fdb_norm(FdArgs a) {
     uint4* dst = reinterpret_cast<uint4*>(a.act_out.codes + (size_t)s * K);
     for (int i = tid; i < K / 16; i += FD_NT) dst[i] = reinterpret_cast<const uint4*>(sv.aw)[i];
     for (int i = tid; i < nb; i += FD_NT) { a.act_out.ad[(size_t)s * nb + i] = sv.ad[i]; a.act_out.n7[(size_t)s * nb + i] = sv.n7[i]; }
+    fd_trace(0 * 4 + 2);
 }
 
 static __host__ __device__ inline size_t fdb_gemv_smem(int K, int n_seq) {
@@ -866,6 +892,7 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fdb_gemv(FdArgs a) {
     float* s_ad = reinterpret_cast<float*>(smem + (size_t)NS * nb * 32);
     int* s_n7 = reinterpret_cast<int*>(smem + (size_t)NS * nb * 36);
     float* scratch = reinterpret_cast<float*>(smem + (((size_t)NS * nb * 40 + 15) & ~(size_t)15));          // [FDB_MAX][64]
+    fd_trace((1 + EPI) * 4 + 0);
     fd_launch_dependents();
     if (tid < 2 && a.pf[tid]) {
         const size_t per = ((a.pf_bytes[tid] + gridDim.x - 1) / gridDim.x + 127) & ~(size_t)127;
@@ -891,12 +918,14 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fdb_gemv(FdArgs a) {
     rows_of(v, row);
     fd_load_batch<WT, NBL, R>(bt, a.w, a.ws, row, nb);
     fd_wait_prior();
+    fd_trace((1 + EPI) * 4 + 1);
     {
         const uint4* src = reinterpret_cast<const uint4*>(a.in.codes);
         for (int i = tid; i < NS * (K / 16); i += FD_NT) reinterpret_cast<uint4*>(s_aw)[i] = __ldcg(src + i);
         for (int i = tid; i < NS * nb; i += FD_NT) { s_ad[i] = __ldcg(a.in.ad + i); s_n7[i] = __ldcg(a.in.n7 + i); }
     }
     __syncthreads();
+    fd_trace((1 + EPI) * 4 + 3);
     float best = -INFINITY;          // ARGMAX: lane u * 8 + s tracks sequence s over its rows
     int arg = 0x7fffffff;
     for (; v < v1;) {
@@ -914,16 +943,15 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fdb_gemv(FdArgs a) {
                 for (int u = 0; u < R; u++) dw[u] = h2f((uint16_t)bt.sc[u][i]);
 #pragma unroll
                 for (int s = 0; s < FDB_MAX; s++) {
-                    if (s < NS) {
-                        const uint4 ax = reinterpret_cast<const uint4*>(s_aw)[((size_t)s * nb + b) * 2];
-                        const uint4 ay = reinterpret_cast<const uint4*>(s_aw)[((size_t)s * nb + b) * 2 + 1];
-                        const int n7 = (WT == DT_Q4) ? s_n7[s * nb + b] : 0;
-                        const float ad = s_ad[s * nb + b];
+                    if (s >= NS) break;          // a real (warp-uniform) branch: if-converted code would issue all 8 sequences
+                    const uint4 ax = reinterpret_cast<const uint4*>(s_aw)[((size_t)s * nb + b) * 2];
+                    const uint4 ay = reinterpret_cast<const uint4*>(s_aw)[((size_t)s * nb + b) * 2 + 1];
+                    const int n7 = (WT == DT_Q4) ? s_n7[s * nb + b] : 0;
+                    const float ad = s_ad[s * nb + b];
 #pragma unroll
-                        for (int u = 0; u < R; u++) {
-                            const int is = fd_block_isum<WT>(bt.a[u][i], bt.b[(WT == DT_Q8) ? u : 0][(WT == DT_Q8) ? i : 0], ax, ay, n7);
-                            acc[u][s] = fmaf((float)is, __fmul_rn(ad, dw[u]), acc[u][s]);
-                        }
+                    for (int u = 0; u < R; u++) {
+                        const int is = fd_block_isum<WT>(bt.a[u][i], bt.b[(WT == DT_Q8) ? u : 0][(WT == DT_Q8) ? i : 0], ax, ay, n7);
+                        acc[u][s] = fmaf((float)is, __fmul_rn(ad, dw[u]), acc[u][s]);
                     }
                 }
             }
@@ -978,6 +1006,7 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fdb_gemv(FdArgs a) {
             }
         }
     }
+    fd_trace((1 + EPI) * 4 + 2);
     if (EPI == FD_SILU && unit < n_units) {
         __syncthreads();
         if (wid < NS) {                  // warp s: E(E(silu(E(gate))) * E(up)) of sequence s (modules.cpp:238-247)
@@ -1050,6 +1079,7 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fdb_gemv(FdArgs a) {
 // attention of sequence blockIdx.y: the single-sequence phase on that sequence's slices
 __global__ void __launch_bounds__(FD_NT, 2) k_fdb_attn(FdAttnArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
+    fd_trace(4 * 4 + 0);
     fd_launch_dependents();
     const int s = blockIdx.y;
     FdAttnArgs b = a;
@@ -1061,6 +1091,7 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fdb_attn(FdAttnArgs a) {
     b.out.codes += (size_t)s * a.n_embd; b.out.ad += (size_t)s * (a.n_embd / 32); b.out.n7 += (size_t)s * (a.n_embd / 32);
     FdPdlSync sync;
     fd_attn_phase<1>(b, smem, sync, a.n_heads, FD_CHUNKS, -1);
+    fd_trace(4 * 4 + 2);
 }
 
 }  // namespace gtb
