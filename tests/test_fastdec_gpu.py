@@ -176,6 +176,7 @@ def test_batch_decode_equals_single_sequence(capi, wdt, lens, graph):
         one = capi.Engine(cfg, 128, wdt).load(wl)
         one.prefill(p)
         one.set_option("fast_decode", 1)
+        one.set_option("fd_chunk", 128)       # the batch's attention chunk length (the single-sequence default is 64: lower latency)
         one.decode(steps)
         n = len(p)
         assert e.batch_position(s) == one.position() == n + steps

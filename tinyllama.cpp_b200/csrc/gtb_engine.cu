@@ -352,7 +352,7 @@ struct gtb_engine {
     int pf_cap_T = 0;
     // fast (order-free) decode kernels (gtb_fastdec.cuh): opt-in, tolerance-level parity
     bool fast = false;
-    float* fd_parts = nullptr;       // [n_heads][FD_CHUNKS][FD_PART] attention partials
+    float* fd_parts = nullptr;       // [n_heads][FD_MAXCH][FD_PART] attention partials
     unsigned* fd_cnt = nullptr;      // [n_heads + 1] arrival counters (attention chunks per head; head CTAs)
     FdAct fd_attn{}, fd_act{};       // E(attention output) [n_embd], E(MLP activation) [n_ffn]: staged codes for the next GEMV
     float* fd_argv = nullptr;        // per-CTA maxima of the head kernel
@@ -374,6 +374,7 @@ struct gtb_engine {
         cudaGraphExec_t graph = nullptr;
         int graph_launches = 0;
     } bb;
+    int fd_chunk = 64;               // positions per attention chunk of the single-sequence fast path (the batch uses 128)
     int fd_prof_cta = 0;             // which CTA writes the "prof" stamps of k_fd_mega
     bool fd_mega = false;            // fast decode as one persistent cooperative kernel (k_fd_mega, measured slower); false: PDL-chained kernels
     FdArgs* d_fd_gemv = nullptr;     // phase arguments of k_fd_mega
@@ -532,6 +533,7 @@ int build_fast_args(gtb_engine* e, bool with_head, int eos_id, std::vector<FdArg
     const gtb_model_config& c = e->cfg;
     const int E = c.n_embd, F = c.n_ffn, KV = e->kv_dim, L = c.n_layers;
     const int wd = c.wdtype;
+    if (e->gsz > FD_NW) return fail(GTB_ERR_STATE, "fast_decode: at most %d query heads per KV group", FD_NW);
     gv.clear(); av.clear();
     for (int li = 0; li < L; li++) {
         LayerW& l = e->L[li];
@@ -544,7 +546,7 @@ int build_fast_args(gtb_engine* e, bool with_head, int eos_id, std::vector<FdArg
         FdAttnArgs t{};
         t.rqkv = e->rqkv; t.n_embd = E; t.kv_dim = KV; t.gsz = e->gsz; t.kq = l.kq; t.ks = l.ks; t.vq = l.vq; t.vs = l.vs;
         t.rope_cos = e->rope_cos; t.rope_sin = e->rope_sin; t.st = e->st; t.parts = e->fd_parts; t.counters = e->fd_cnt;
-        t.out = e->fd_attn;
+        t.out = e->fd_attn; t.n_heads = c.n_heads; t.n_groups = c.n_groups; t.chunk_len = fd_chunk_len(c.max_ctx, e->fd_chunk);
         av.push_back(t);
         FdArgs o{};
         o.K = E; o.n_rows = E; o.w = (const uint4*)l.o->data; o.ws = l.o->scales; o.out = e->ro; o.in = e->fd_attn;
@@ -588,11 +590,11 @@ int enqueue_row_fast(gtb_engine* e, bool with_head, int eos_id) {
         GTB_CUDA(cudaFuncSetAttribute(k_fd_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attn_attr = true;
     }
-    const size_t attn_smem = fd_attn_smem(c.max_ctx, FD_CHUNKS);
+    const size_t attn_smem = fd_attn_smem(fd_chunk_len(c.max_ctx, e->fd_chunk));
     if (attn_smem > 64 * 1024) return fail(GTB_ERR_STATE, "fast_decode: max_ctx too large for the attention kernel's score buffer");
     for (int li = 0; li < L; li++) {
         if ((r = launch_fd<WT, FD_NORM, FD_RAW>(gv[4 * li + 0], G))) return r;
-        GTB_CUDA(fd_launch(k_fd_attn, c.n_heads * FD_CHUNKS, attn_smem, av[li], c.n_heads));
+        GTB_CUDA(fd_launch(k_fd_attn, c.n_groups * FD_MAXCH, attn_smem, av[li]));
         GTB_LAUNCHED();
         if ((r = launch_fd<WT, FD_CODES, FD_RAW>(gv[4 * li + 1], G))) return r;
         if ((r = launch_fd<WT, FD_NORM, FD_SILU>(gv[4 * li + 2], c.n_ffn / 32))) return r;
@@ -680,7 +682,7 @@ int batch_alloc(gtb_engine* e, int n) {
     r |= dalloc((void**)&b.rqkv, N * (E + 2 * KV) * 4); r |= dalloc((void**)&b.ro, N * E * 4); r |= dalloc((void**)&b.rd, N * E * 4);
     r |= dalloc((void**)&b.xres, N * E * 4); r |= dalloc((void**)&b.hres, N * E * 4); r |= dalloc((void**)&b.xfinal, N * E * 4);
     r |= dalloc((void**)&b.logits, N * c.n_vocab * 4);
-    r |= dalloc((void**)&b.parts, N * c.n_heads * FD_CHUNKS * FD_PART * 4);
+    r |= dalloc((void**)&b.parts, N * c.n_heads * FD_MAXCH * FD_PART * 4);
     r |= dalloc((void**)&b.argv, N * 1024 * 4); r |= dalloc((void**)&b.argi, N * 1024 * 4);
     r |= dalloc((void**)&b.cnt, (N * (c.n_heads + 1) + 1) * 4);
     r |= dalloc((void**)&b.tokens, N * (MC + 2) * 4); r |= dalloc((void**)&b.st, N * sizeof(DevState));
@@ -757,7 +759,7 @@ int enqueue_batch_row(gtb_engine* e) {
         GTB_CUDA(cudaFuncSetAttribute(k_fdb_norm, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr = true;
     }
-    const size_t attn_smem = fd_attn_smem(MC, FD_CHUNKS);
+    const size_t attn_smem = fd_attn_smem(fd_chunk_len(MC, 128));
     if (attn_smem > 64 * 1024) return fail(GTB_ERR_STATE, "batched decode: max_ctx too large for the attention kernel's score buffer");
     const size_t norm_smem = fd_gemv_smem(E, true);
     auto norm = [&](const float* src0, const float* src1, const uint16_t* w, float* res_out, bool embed) -> int {
@@ -777,10 +779,11 @@ int enqueue_batch_row(gtb_engine* e) {
         FdAttnArgs t{};
         t.rqkv = b.rqkv; t.n_embd = E; t.kv_dim = KV; t.gsz = e->gsz; t.kq = b.kq[li]; t.ks = b.ks[li]; t.vq = b.vq[li]; t.vs = b.vs[li];
         t.rope_cos = e->rope_cos; t.rope_sin = e->rope_sin; t.st = b.st; t.parts = b.parts; t.counters = b.cnt; t.out = b.attn_act;
-        t.seq_kv_codes = (size_t)MC * KV; t.seq_kv_scales = (size_t)MC * (KV / 32); t.n_heads = c.n_heads;
+        t.seq_kv_codes = (size_t)MC * KV; t.seq_kv_scales = (size_t)MC * (KV / 32); t.n_heads = c.n_heads; t.n_groups = c.n_groups;
+        t.chunk_len = fd_chunk_len(MC, 128);
         {
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(c.n_heads * FD_CHUNKS, NS); cfg.blockDim = dim3(FD_NT); cfg.dynamicSmemBytes = attn_smem; cfg.stream = ctx().stream;
+            cfg.gridDim = dim3(c.n_groups * FD_MAXCH, NS); cfg.blockDim = dim3(FD_NT); cfg.dynamicSmemBytes = attn_smem; cfg.stream = ctx().stream;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -985,7 +988,7 @@ int gtb_engine_create(gtb_engine_t* out, const gtb_model_config* cfg) {
     r |= dalloc((void**)&e->rqkv, (size_t)(E + 2 * KV) * 4); r |= dalloc((void**)&e->rattn, E * 4); r |= dalloc((void**)&e->ro, E * 4);
     r |= dalloc((void**)&e->rg, F * 4); r |= dalloc((void**)&e->ru, F * 4); r |= dalloc((void**)&e->rd, E * 4);
     r |= dalloc((void**)&e->logits, (size_t)cfg->n_vocab * 4);
-    r |= dalloc((void**)&e->fd_parts, (size_t)cfg->n_heads * FD_CHUNKS * FD_PART * 4);
+    r |= dalloc((void**)&e->fd_parts, (size_t)cfg->n_heads * FD_MAXCH * FD_PART * 4);
     r |= dalloc((void**)&e->fd_cnt, (size_t)(cfg->n_heads + 1) * 4);
     r |= dalloc((void**)&e->fd_attn.codes, E); r |= dalloc((void**)&e->fd_attn.ad, E / 32 * 4); r |= dalloc((void**)&e->fd_attn.n7, E / 32 * 4);
     r |= dalloc((void**)&e->fd_act.codes, F); r |= dalloc((void**)&e->fd_act.ad, F / 32 * 4); r |= dalloc((void**)&e->fd_act.n7, F / 32 * 4);
@@ -1367,6 +1370,7 @@ int gtb_engine_batch_create(gtb_engine_t e, int n_seq) {
     GTB_ARG(e && n_seq >= 0 && n_seq <= FDB_MAX);
     if (e->cfg.wdtype == GTB_F16) return fail(GTB_ERR_STATE, "batched decode is built for Q8-activation models (Q8, Q4 weights)");
     if (e->cfg.n_embd > 2048 || e->cfg.n_ffn > 6144) return fail(GTB_ERR_STATE, "batched decode: n_embd <= 2048 and n_ffn <= 6144");
+    if (e->gsz > FD_NW) return fail(GTB_ERR_STATE, "batched decode: at most %d query heads per KV group", FD_NW);
     return batch_alloc(e, n_seq);
 }
 
@@ -1526,6 +1530,7 @@ int gtb_engine_set_option(gtb_engine_t e, const char* name, int value) {
     if (!strcmp(name, "prof")) { e->prof = value != 0; return GTB_OK; }
     if (!strcmp(name, "fast_decode")) { e->fast = value != 0; drop_graphs(e); return GTB_OK; }
     if (!strcmp(name, "fd_ahead")) { GTB_ARG(value >= 0 && value <= 16); e->fd_ahead = value; drop_graphs(e); e->fd_args_valid = false; return GTB_OK; }
+    if (!strcmp(name, "fd_chunk")) { GTB_ARG(value >= 32 && value <= 1024 && value % 32 == 0); e->fd_chunk = value; drop_graphs(e); return GTB_OK; }
     if (!strcmp(name, "fd_prof_cta")) { GTB_ARG(value >= 0); e->fd_prof_cta = value; return GTB_OK; }
     if (!strcmp(name, "fd_trace")) {          // debug timeline of the fast-decode chains into the "prof" buffer (gtb_engine_read_prof)
         long long* p = value ? e->d_prof : nullptr;

@@ -13,8 +13,9 @@
 // streaming is thereby decoupled from the dependency chain of the row.
 //
 //   k_fd_gemv<NORM, RAW>     x = E(h + E(down)) | embedding row; RMSNorm; E -> staged;  q|k|v rows           (148 CTAs)
-//   k_fd_attn                (head, position chunk): E/RoPE/E of q,k,v, K/V append, scores, chunk softmax, E(P), P.V;
-//                            the last chunk of a head to finish combines the chunks and writes E(attention) staged
+//   k_fd_attn                (KV group, position chunk), warp = query head: K/V rows of the chunk once in shared memory for the 8
+//                            heads, E/RoPE/E of q (and k, v of the row), scores, block softmax, E(P), P.V; the last chunk of a
+//                            group to finish combines the chunks and writes E(attention) staged
 //   k_fd_gemv<CODES, RAW>    o rows
 //   k_fd_gemv<NORM, SILU>    h = E(x + E(o)); RMSNorm; one CTA = one 32-channel block of the MLP: its 32 gate rows and 32 up
 //                            rows, then E(E(silu(E(gate))) * E(up)) -> staged codes
@@ -28,7 +29,7 @@ namespace gtb {
 
 constexpr int FD_NT = 256;            // threads per CTA (two CTAs of consecutive kernels share an SM)
 constexpr int FD_NW = FD_NT / 32;
-constexpr int FD_CHUNKS = 8;          // position chunks per head (flash-decoding split)
+constexpr int FD_MAXCH = 32;          // position chunks per KV group at most (flash-decoding split)
 constexpr int FD_PART = 68;           // floats per (head, chunk) partial: 64 channels, chunk max, chunk sum, 2 pad
 
 enum { FD_NORM = 0, FD_CODES = 1 };
@@ -482,40 +483,46 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fd_gemv(FdArgs a) {
     fd_trace((1 + EPI) * 4 + 2);
 }
 
-// ---------------------------------------------------------------- attention: one CTA = (head, position chunk)
+// ---------------------------------------------------------------- attention: one CTA = (KV group, position chunk), warp = query head
 struct FdAttnArgs {
     const float* rqkv; int n_embd, kv_dim, gsz;
     uint8_t* kq; uint16_t* ks; uint8_t* vq; uint16_t* vs;
     const float* rope_cos; const float* rope_sin; const DevState* st;
-    float* parts;             // [n_heads][FD_CHUNKS][FD_PART]
-    unsigned* counters;       // [n_heads]
+    float* parts;             // [n_heads][FD_MAXCH][FD_PART]
+    unsigned* counters;       // [n_groups] arrivals of a group's chunks
     FdAct out;                // E(attention output) staged for the o GEMV
     const void* pf[2]; size_t pf_bytes[2];
     size_t seq_kv_codes, seq_kv_scales;          // batched decode: per-sequence strides of the K/V cache planes
-    int n_heads;
+    int n_heads, n_groups;
+    int chunk_len;            // positions per chunk: multiple of 32, FD_MAXCH chunks cover max_ctx (fd_chunk_len)
 };
 
-struct FdAttnSmem {
-    uint32_t qw[16]; float qd[2];
-    uint32_t kw[16]; float kd[2];
-    float vf[64];
-    float tmp[6][32];
-    float red[FD_NW];
-    float part[FD_NW][64];
-    float wm[FD_NW], wl[FD_NW];
-    int last;
-};
-
-static __host__ __device__ inline size_t fd_attn_smem(int max_ctx, int nch) {
-    return ((sizeof(FdAttnSmem) + 15) & ~(size_t)15) + (size_t)((((max_ctx + nch - 1) / nch + 31) & ~31) + 64) * 4;
+// `want` positions per chunk (64: lowest latency for one sequence; 128: fewer, fuller CTAs for a batch), raised until
+// FD_MAXCH chunks cover max_ctx
+static __host__ __device__ inline int fd_chunk_len(int max_ctx, int want) {
+    const int cl = (((max_ctx + FD_MAXCH - 1) / FD_MAXCH) + 31) & ~31;
+    return cl < want ? want : cl;
+}
+// shared memory of a chunk: K codes transposed [16 words][CL], K scales [2][CL], V rows [CL][64 B], V scales [CL][2],
+// the staged q of the 8 heads, a flag
+static __host__ __device__ inline size_t fd_attn_smem(int chunk_len) {
+    return (size_t)chunk_len * 144 + FD_NW * 18 * 4 + 16;
 }
 
-// units = (head, position chunk), `nch` chunks per head; unit u runs on CTA u mod gridDim.x.  Inside a chunk every warp owns
-// whole 32-position blocks of the probability row (the re-encode unit of ops.h:996) and keeps its own running
-// (max, sum, 64 outputs); warps meet once per chunk.  KPT = blocks per warp whose K/V rows are loaded up front.
-template <int KPT, typename Sync>
-__device__ __forceinline__ void fd_attn_phase(const FdAttnArgs& a, unsigned char* smem, Sync& sync, int n_heads, int nch_max, int pos_in) {
-    FdAttnSmem& sm = *reinterpret_cast<FdAttnSmem*>(smem);
+// The 8 query heads of a KV group share one copy of the chunk's K/V rows in shared memory (GQA: 32 heads, 4 groups,
+// tinyllama.cpp:12-20); warp w runs head g * gsz + w over the chunk's 32-position blocks (the re-encode unit of ops.h:996)
+// with its own running (max, sum, 64 outputs).  The chunk that holds the row's own position also encodes and appends this
+// row's k and v.  The last chunk of a group to finish (arrival counter) combines the chunks of its 8 heads.
+template <typename Sync>
+__device__ __forceinline__ void fd_attn_phase(const FdAttnArgs& a, unsigned char* smem, Sync& sync, int pos_in) {
+    const int CL = a.chunk_len;
+    uint32_t* kT = reinterpret_cast<uint32_t*>(smem);                       // [16][CL]
+    float* kd = reinterpret_cast<float*>(smem + (size_t)CL * 64);           // [2][CL]
+    uint4* vR = reinterpret_cast<uint4*>(smem + (size_t)CL * 72);           // [CL][4]
+    float* vd = reinterpret_cast<float*>(smem + (size_t)CL * 136);          // [CL][2]
+    uint32_t* qw = reinterpret_cast<uint32_t*>(smem + (size_t)CL * 144);    // [FD_NW][16]
+    float* qd = reinterpret_cast<float*>(qw + FD_NW * 16);                  // [FD_NW][2]
+    int* last = reinterpret_cast<int*>(qd + FD_NW * 2);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int slot = lane >> 2, cq = lane & 3;          // P.V: lane = (position slot of 8, 16 channels)
     sync.arrive();
@@ -523,230 +530,228 @@ __device__ __forceinline__ void fd_attn_phase(const FdAttnArgs& a, unsigned char
     sync.wait();
     sync.stamp();
     const int pos = (pos_in >= 0) ? pos_in : __ldcg(&a.st->pos);
-    // chunks in use grow with the context (one per KPT * 256 positions, at most nch_max): short contexts do not pay for
-    // partials, counters and combines of empty chunks
-    const int nch = min(nch_max, max(1, (pos + KPT * 256) / (KPT * 256)));
-    for (int unit = blockIdx.x; unit < n_heads * nch_max; unit += gridDim.x) {
-    const int h = unit / nch_max, c = unit % nch_max, g = h / a.gsz;
-    if (c >= nch) continue;
-    const bool writer = (h % a.gsz) == 0 && c == 0;
-    // chunk of positions [lo, hi), aligned to the 32-position blocks of the probability row
-    const int per = ((pos + 1 + nch - 1) / nch + 31) & ~31;
-    const int lo = c * per, hi = min(pos + 1, lo + per);
-    const int n = hi - lo, nblk = (n + 31) / 32;
+    const int nch = (pos + CL) / CL;                    // chunks in use follow the context
     const int kvb = a.kv_dim / 32;
-    // the few words this row's q/k/v prep waits for go first
-    float cs = 0.0f, sn = 0.0f, xin = 0.0f;
-    if (wid < 4) { cs = a.rope_cos[(size_t)pos * 32 + lane]; sn = a.rope_sin[(size_t)pos * 32 + lane]; }
-    if (wid < 6) {
-        const int which = wid >> 1, half = wid & 1;
-        const float* src = (which == 0) ? a.rqkv + h * 64 : (which == 1) ? a.rqkv + a.n_embd + g * 64 : a.rqkv + a.n_embd + a.kv_dim + g * 64;
-        xin = __ldcg(src + half * 32 + lane);
-    }
-    // K/V rows of this warp's first blocks do not depend on this row's q: in flight while the prep runs
-    uint4 kr[KPT][4], vr[KPT][4];
-    uint32_t ksr[KPT][2], vsr[KPT][4];
-    auto load_block = [&](int blk, uint4 (&kk)[4], uint32_t (&ks)[2], uint4 (&vv)[4], uint32_t (&vs)[4]) {
-        const int k = lo + blk * 32 + lane;
-        if (k < hi && k != pos) {
-            const uint4* kp = reinterpret_cast<const uint4*>(a.kq + (size_t)k * a.kv_dim + g * 64);
-#pragma unroll
-            for (int i = 0; i < 4; i++) kk[i] = __ldcg(kp + i);
-            ks[0] = __ldcg(a.ks + (size_t)k * kvb + g * 2);
-            ks[1] = __ldcg(a.ks + (size_t)k * kvb + g * 2 + 1);
+    for (int unit = blockIdx.x; unit < a.n_groups * FD_MAXCH; unit += gridDim.x) {
+        const int g = unit / FD_MAXCH, c = unit % FD_MAXCH;
+        if (c >= nch) continue;
+        const int lo = c * CL, hi = min(pos + 1, lo + CL), n = hi - lo, nblk = (n + 31) / 32;
+        const bool own = (c == nch - 1);                // this chunk holds the row's own position
+        const int h = g * a.gsz + wid;
+        const bool head_warp = wid < a.gsz;
+        // ---- the few words the prep waits for go first
+        const float cs = a.rope_cos[(size_t)pos * 32 + lane], sn = a.rope_sin[(size_t)pos * 32 + lane];
+        float xq0 = 0.0f, xq1 = 0.0f, xo0 = 0.0f, xo1 = 0.0f;
+        if (head_warp) { xq0 = __ldcg(a.rqkv + h * 64 + lane); xq1 = __ldcg(a.rqkv + h * 64 + 32 + lane); }
+        if (own && wid >= FD_NW - 2) {                  // warp 6: this row's k, warp 7: its v
+            const float* src = a.rqkv + a.n_embd + (wid == FD_NW - 1 ? a.kv_dim : 0) + g * 64;
+            xo0 = __ldcg(src + lane); xo1 = __ldcg(src + 32 + lane);
         }
+        // ---- the chunk's K/V rows: in flight while the prep runs (first 512 uint4 of each; longer chunks loop below)
+        uint4 kreg[2], vreg[2];
+        uint32_t ksreg = 0, vsreg = 0;
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int i = lo + blk * 32 + slot + 8 * u;
-            vv[u] = make_uint4(0, 0, 0, 0); vs[u] = 0;
-            if (i < hi && i != pos) {
-                vv[u] = __ldcg(reinterpret_cast<const uint4*>(a.vq + (size_t)i * a.kv_dim + g * 64 + cq * 16));
-                vs[u] = __ldcg(a.vs + (size_t)i * kvb + g * 2 + (cq >> 1));
+        for (int j = 0; j < 2; j++) {
+            const int idx = tid + FD_NT * j, p = idx >> 2, q4 = idx & 3;
+            if (p < n && lo + p != pos) {
+                kreg[j] = __ldcg(reinterpret_cast<const uint4*>(a.kq + (size_t)(lo + p) * a.kv_dim + g * 64) + q4);
+                vreg[j] = __ldcg(reinterpret_cast<const uint4*>(a.vq + (size_t)(lo + p) * a.kv_dim + g * 64) + q4);
             }
         }
-    };
-#pragma unroll
-    for (int j = 0; j < KPT; j++) {
-        if (wid + FD_NW * j < nblk) load_block(wid + FD_NW * j, kr[j], ksr[j], vr[j], vsr[j]);
-    }
-    // q, k, v of this row: Linear re-encode, RoPE, re-encode (ops.h:645-646, 733-753); K/V append by one CTA per group
-    if (wid < 6) {
-        const int which = wid >> 1, half = wid & 1;
-        if (which < 2) {
-            sm.tmp[wid][lane] = fd_lane_roundtrip(xin);
-        } else {
-            float dd;
-            const int q = fd_lane_encode(xin, &dd);
-            sm.vf[half * 32 + lane] = (float)q * dd;
-            if (writer) {
-                a.vq[(size_t)pos * a.kv_dim + g * 64 + half * 32 + lane] = (uint8_t)(int8_t)q;
-                if (lane == 0) a.vs[(size_t)pos * kvb + g * 2 + half] = f2h(dd);
+        {
+            const int p = tid >> 1, bsel = tid & 1;
+            if (p < n && lo + p != pos) {
+                ksreg = __ldcg(a.ks + (size_t)(lo + p) * kvb + g * 2 + bsel);
+                vsreg = __ldcg(a.vs + (size_t)(lo + p) * kvb + g * 2 + bsel);
             }
         }
-    }
-    __syncthreads();
-    if (wid < 4) {
-        const int which = wid >> 1, half = wid & 1;
-        const float x0 = sm.tmp[which * 2][lane], x1 = sm.tmp[which * 2 + 1][lane];
-        const float o = (half == 0) ? __fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn)) : __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs));
-        float dd;
-        const int q = fd_lane_encode(o, &dd);
-        const int pb = perm_byte(lane);
-        if (which == 0) {
-            reinterpret_cast<int8_t*>(sm.qw)[half * 32 + pb] = (int8_t)q;
-            if (lane == 0) sm.qd[half] = dd;
-        } else {
-            reinterpret_cast<int8_t*>(sm.kw)[half * 32 + pb] = (int8_t)q;
-            if (lane == 0) sm.kd[half] = dd;
-            if (writer) {
-                a.kq[(size_t)pos * a.kv_dim + g * 64 + half * 32 + pb] = (uint8_t)(int8_t)q;
-                if (lane == 0) a.ks[(size_t)pos * kvb + g * 2 + half] = f2h(dd);
-            }
-        }
-    }
-    __syncthreads();
-    sync.stamp();
-    float* part = a.parts + ((size_t)h * nch_max + c) * FD_PART;
-    // ---- this warp's blocks: scores (x 1/sqrt(64)), block softmax numerators, E(P), P.V, merged into the warp's running state
-    float m_w = -INFINITY, l_w = 0.0f;
-    float acc[16];
-#pragma unroll
-    for (int j = 0; j < 16; j++) acc[j] = 0.0f;
-    {
-        uint32_t qx[16];
-#pragma unroll
-        for (int i = 0; i < 16; i++) qx[i] = sm.qw[i];
-        const float qd0 = sm.qd[0], qd1 = sm.qd[1];
-        auto score = [&](const uint4 (&kk)[4], float kd0, float kd1) {
-            int i0 = __dp4a((int)kk[0].x, (int)qx[0], 0);
-            i0 = __dp4a((int)kk[0].y, (int)qx[1], i0); i0 = __dp4a((int)kk[0].z, (int)qx[2], i0); i0 = __dp4a((int)kk[0].w, (int)qx[3], i0);
-            i0 = __dp4a((int)kk[1].x, (int)qx[4], i0); i0 = __dp4a((int)kk[1].y, (int)qx[5], i0);
-            i0 = __dp4a((int)kk[1].z, (int)qx[6], i0); i0 = __dp4a((int)kk[1].w, (int)qx[7], i0);
-            int i1 = __dp4a((int)kk[2].x, (int)qx[8], 0);
-            i1 = __dp4a((int)kk[2].y, (int)qx[9], i1); i1 = __dp4a((int)kk[2].z, (int)qx[10], i1); i1 = __dp4a((int)kk[2].w, (int)qx[11], i1);
-            i1 = __dp4a((int)kk[3].x, (int)qx[12], i1); i1 = __dp4a((int)kk[3].y, (int)qx[13], i1);
-            i1 = __dp4a((int)kk[3].z, (int)qx[14], i1); i1 = __dp4a((int)kk[3].w, (int)qx[15], i1);
-            return 0.125f * fmaf((float)i1, qd1 * kd1, (float)i0 * (qd0 * kd0));
+        // ---- q of this warp's head: Linear re-encode, RoPE, re-encode (ops.h:645-646, 733-753)
+        auto rope_encode = [&](float x0, float x1, int (&q)[2], float (&d)[2]) {
+            x0 = fd_lane_roundtrip(x0); x1 = fd_lane_roundtrip(x1);
+            const float o0 = __fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn)), o1 = __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs));
+            q[0] = fd_lane_encode(o0, &d[0]); q[1] = fd_lane_encode(o1, &d[1]);
         };
-        auto do_block = [&](int blk, const uint4 (&kk)[4], const uint32_t (&ks)[2], const uint4 (&vv)[4], const uint32_t (&vs)[4]) {
-            const int k = lo + blk * 32 + lane;
-            float s = -INFINITY;
-            if (k < hi) {
-                if (k == pos) {
-                    const uint4 own[4] = {make_uint4(sm.kw[0], sm.kw[1], sm.kw[2], sm.kw[3]), make_uint4(sm.kw[4], sm.kw[5], sm.kw[6], sm.kw[7]),
-                                          make_uint4(sm.kw[8], sm.kw[9], sm.kw[10], sm.kw[11]), make_uint4(sm.kw[12], sm.kw[13], sm.kw[14], sm.kw[15])};
-                    s = score(own, sm.kd[0], sm.kd[1]);
-                } else {
-                    s = score(kk, h2f((uint16_t)ks[0]), h2f((uint16_t)ks[1]));
-                }
+        const int pb = perm_byte(lane);
+        if (head_warp) {
+            int q[2]; float d[2];
+            rope_encode(xq0, xq1, q, d);
+            reinterpret_cast<int8_t*>(qw + wid * 16)[pb] = (int8_t)q[0];
+            reinterpret_cast<int8_t*>(qw + wid * 16)[32 + pb] = (int8_t)q[1];
+            if (lane == 0) { qd[wid * 2] = d[0]; qd[wid * 2 + 1] = d[1]; }
+        }
+        if (own && wid == FD_NW - 2) {                  // k of this row: into the chunk and the cache (K rows are stored permuted)
+            int q[2]; float d[2];
+            rope_encode(xo0, xo1, q, d);
+            const int pp = pos - lo;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const int byte = half * 32 + pb;
+                reinterpret_cast<int8_t*>(kT)[((size_t)(byte >> 2) * CL + pp) * 4 + (byte & 3)] = (int8_t)q[half];
+                a.kq[(size_t)pos * a.kv_dim + g * 64 + byte] = (uint8_t)(int8_t)q[half];
+                if (lane == 0) { kd[half * CL + pp] = d[half]; a.ks[(size_t)pos * kvb + g * 2 + half] = f2h(d[half]); }
             }
-            const float mb = warp_max(s);
-            const float e = (k < hi) ? __expf(s - mb) : 0.0f;
-            float lb = e;
+        }
+        if (own && wid == FD_NW - 1) {                  // v of this row: Linear re-encode only
+            const int pp = pos - lo;
+            float d0, d1;
+            const int q0 = fd_lane_encode(xo0, &d0), q1 = fd_lane_encode(xo1, &d1);
+            reinterpret_cast<int8_t*>(vR)[(size_t)pp * 64 + lane] = (int8_t)q0;
+            reinterpret_cast<int8_t*>(vR)[(size_t)pp * 64 + 32 + lane] = (int8_t)q1;
+            a.vq[(size_t)pos * a.kv_dim + g * 64 + lane] = (uint8_t)(int8_t)q0;
+            a.vq[(size_t)pos * a.kv_dim + g * 64 + 32 + lane] = (uint8_t)(int8_t)q1;
+            if (lane == 0) {
+                vd[pp * 2] = d0; vd[pp * 2 + 1] = d1;
+                a.vs[(size_t)pos * kvb + g * 2] = f2h(d0); a.vs[(size_t)pos * kvb + g * 2 + 1] = f2h(d1);
+            }
+        }
+        // ---- K/V rows into shared memory
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) lb += __shfl_xor_sync(0xffffffffu, lb, o);
-            // Q8 re-encode of the probability row per 32 positions (ops.h:996): the block's largest e is exp(0) = 1, so the codes
-            // are round(127 e); the block scale stays relative to the block maximum and is normalised at the combine
-            const float p = floorf(e * 127.0f + 0.5f) * (1.0f / 127.0f);
-            const float m_new = fmaxf(m_w, mb);
-            const float f_old = __expf(m_w - m_new), f_b = __expf(mb - m_new);       // m_w = -inf: f_old = 0
-            l_w = fmaf(l_w, f_old, lb * f_b);
-            m_w = m_new;
+        for (int j = 0; j < 2; j++) {
+            const int idx = tid + FD_NT * j, p = idx >> 2, q4 = idx & 3;
+            if (p < n && lo + p != pos) {
+                kT[(q4 * 4 + 0) * CL + p] = kreg[j].x; kT[(q4 * 4 + 1) * CL + p] = kreg[j].y;
+                kT[(q4 * 4 + 2) * CL + p] = kreg[j].z; kT[(q4 * 4 + 3) * CL + p] = kreg[j].w;
+                vR[p * 4 + q4] = vreg[j];
+            }
+        }
+        {
+            const int p = tid >> 1, bsel = tid & 1;
+            if (p < n && lo + p != pos) { kd[bsel * CL + p] = h2f((uint16_t)ksreg); vd[p * 2 + bsel] = h2f((uint16_t)vsreg); }
+        }
+        for (int idx = tid + 2 * FD_NT; idx < 4 * n; idx += FD_NT) {          // chunks longer than 128 positions
+            const int p = idx >> 2, q4 = idx & 3;
+            if (lo + p != pos) {
+                const uint4 kk = __ldcg(reinterpret_cast<const uint4*>(a.kq + (size_t)(lo + p) * a.kv_dim + g * 64) + q4);
+                kT[(q4 * 4 + 0) * CL + p] = kk.x; kT[(q4 * 4 + 1) * CL + p] = kk.y; kT[(q4 * 4 + 2) * CL + p] = kk.z; kT[(q4 * 4 + 3) * CL + p] = kk.w;
+                vR[p * 4 + q4] = __ldcg(reinterpret_cast<const uint4*>(a.vq + (size_t)(lo + p) * a.kv_dim + g * 64) + q4);
+            }
+        }
+        for (int idx = tid + FD_NT; idx < 2 * n; idx += FD_NT) {
+            const int p = idx >> 1, bsel = idx & 1;
+            if (lo + p != pos) {
+                kd[bsel * CL + p] = h2f(__ldcg(a.ks + (size_t)(lo + p) * kvb + g * 2 + bsel));
+                vd[p * 2 + bsel] = h2f(__ldcg(a.vs + (size_t)(lo + p) * kvb + g * 2 + bsel));
+            }
+        }
+        __syncthreads();
+        sync.stamp();
+        // ---- this head's blocks: scores (x 1/sqrt(64)), block softmax numerators, E(P), P.V, merged into the running state
+        if (head_warp) {
+            float m_w = -INFINITY, l_w = 0.0f;
+            float acc[16];
 #pragma unroll
-            for (int j = 0; j < 16; j++) acc[j] *= f_old;
+            for (int j = 0; j < 16; j++) acc[j] = 0.0f;
+            uint32_t qx[16];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i = lo + blk * 32 + slot + 8 * u;
-                const float pi = __shfl_sync(0xffffffffu, p, slot + 8 * u) * f_b;
-                if (i < hi) {
-                    if (i == pos) {          // this row's own v is not read back from the cache
+            for (int i = 0; i < 16; i++) qx[i] = qw[wid * 16 + i];
+            const float qd0 = qd[wid * 2], qd1 = qd[wid * 2 + 1];
+            for (int blk = 0; blk < nblk; blk++) {
+                const int p = blk * 32 + lane;
+                float s = -INFINITY;
+                if (p < n) {
+                    int i0 = 0, i1 = 0;
 #pragma unroll
-                        for (int j = 0; j < 16; j++) acc[j] = fmaf(sm.vf[cq * 16 + j], pi, acc[j]);
-                    } else {
-                        const float wgt = pi * h2f((uint16_t)vs[u]);          // ops.h:1026
-                        const uint32_t wds[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
+                    for (int w = 0; w < 8; w++) { i0 = __dp4a((int)kT[w * CL + p], (int)qx[w], i0); i1 = __dp4a((int)kT[(8 + w) * CL + p], (int)qx[8 + w], i1); }
+                    s = 0.125f * fmaf((float)i1, qd1 * kd[CL + p], (float)i0 * (qd0 * kd[p]));
+                }
+                const float mb = warp_max(s);
+                const float e = (p < n) ? __expf(s - mb) : 0.0f;
+                float lb = e;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) lb += __shfl_xor_sync(0xffffffffu, lb, o);
+                // Q8 re-encode of the probability row per 32 positions (ops.h:996): the block's largest e is exp(0) = 1, so the codes
+                // are round(127 e); the block scale stays relative to the block maximum and is normalised at the combine
+                const float pc = floorf(e * 127.0f + 0.5f) * (1.0f / 127.0f);
+                const float m_new = fmaxf(m_w, mb);
+                const float f_old = __expf(m_w - m_new), f_b = __expf(mb - m_new);       // m_w = -inf: f_old = 0
+                l_w = fmaf(l_w, f_old, lb * f_b);
+                m_w = m_new;
+#pragma unroll
+                for (int j = 0; j < 16; j++) acc[j] *= f_old;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = blk * 32 + slot + 8 * u;
+                    const float pi = __shfl_sync(0xffffffffu, pc, slot + 8 * u) * f_b;
+                    if (i < n) {
+                        const float wgt = pi * vd[i * 2 + (cq >> 1)];          // ops.h:1026
+                        const uint4 vw = vR[i * 4 + cq];
+                        const uint32_t wds[4] = {vw.x, vw.y, vw.z, vw.w};
 #pragma unroll
                         for (int j = 0; j < 16; j++) acc[j] = fmaf((float)(int)(int8_t)(wds[j >> 2] >> (8 * (j & 3))), wgt, acc[j]);
                     }
                 }
             }
-        };
 #pragma unroll
-        for (int j = 0; j < KPT; j++) {
-            if (wid + FD_NW * j < nblk) do_block(wid + FD_NW * j, kr[j], ksr[j], vr[j], vsr[j]);
+            for (int j = 0; j < 16; j++) {
+                acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
+                acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+                acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+            }
+            float* part = a.parts + ((size_t)h * FD_MAXCH + c) * FD_PART;
+            if (lane < 4) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(part + lane * 16 + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            }
+            if (lane == 4) { part[64] = m_w; part[65] = l_w; }
         }
-        for (int blk = wid + FD_NW * KPT; blk < nblk; blk += FD_NW) {          // chunks longer than KPT * 256 positions
-            uint4 kk[4], vv[4];
-            uint32_t ks[2], vs[4];
-            load_block(blk, kk, ks, vv, vs);
-            do_block(blk, kk, ks, vv, vs);
+        sync.stamp();
+        // ---- the last chunk of this group to finish combines: o = sum_c o_c * exp(m_c - m) / sum_c l_c * exp(m_c - m), E(o)
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) *last = (atomicAdd(a.counters + g, 1u) == (unsigned)(nch - 1));
+        __syncthreads();
+        if (*last) {
+            __threadfence();
+            if (head_warp) {
+                // lane cc holds chunk cc's (max, sum); all loads of the combine are in flight at once
+                const float* p = a.parts + (size_t)h * FD_MAXCH * FD_PART;
+                const float mc = (lane < nch) ? __ldcg(p + lane * FD_PART + 64) : -INFINITY;
+                const float lc = (lane < nch) ? __ldcg(p + lane * FD_PART + 65) : 0.0f;
+                const float m = warp_max(mc);
+                const float fc = (lane < nch) ? __expf(mc - m) : 0.0f;
+                float l = lc * fc;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+                float o0 = 0.0f, o1 = 0.0f;
+                for (int c0 = 0; c0 < nch; c0 += 16) {          // 32 partial loads in flight per pass
+                    float pv0[16], pv1[16];
+#pragma unroll
+                    for (int cc = 0; cc < 16; cc++) {
+                        pv0[cc] = (c0 + cc < nch) ? __ldcg(p + (c0 + cc) * FD_PART + lane) : 0.0f;
+                        pv1[cc] = (c0 + cc < nch) ? __ldcg(p + (c0 + cc) * FD_PART + 32 + lane) : 0.0f;
+                    }
+#pragma unroll
+                    for (int cc = 0; cc < 16; cc++) {
+                        const float f = __shfl_sync(0xffffffffu, fc, (c0 + cc) & 31);
+                        o0 = fmaf(pv0[cc], f, o0);
+                        o1 = fmaf(pv1[cc], f, o1);
+                    }
+                }
+                const float inv = __fdividef(1.0f, l);
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    float dd;
+                    const int q = fd_lane_encode((half ? o1 : o0) * inv, &dd);          // E(attention output), ops.h:1084
+                    int sum = q;
+#pragma unroll
+                    for (int ofs = 16; ofs > 0; ofs >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, ofs);
+                    const int b = 2 * h + half;
+                    a.out.codes[b * 32 + pb] = (uint8_t)(int8_t)q;
+                    if (lane == 0) { a.out.ad[b] = dd; a.out.n7[b] = -7 * sum; }
+                }
+            }
+            if (tid == 0) a.counters[g] = 0u;
         }
-    }
-#pragma unroll
-    for (int j = 0; j < 16; j++) {
-        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
-        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
-        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
-    }
-    if (lane < 4) {
-#pragma unroll
-        for (int j = 0; j < 16; j++) sm.part[wid][lane * 16 + j] = acc[j];
-    }
-    if (lane == 0) { sm.wm[wid] = m_w; sm.wl[wid] = l_w; }
-    __syncthreads();
-    sync.stamp();
-    if (tid < 65) {          // 64 channels + the chunk sum (tid 64), all relative to the chunk maximum
-        float m = sm.wm[0];
-#pragma unroll
-        for (int w = 1; w < FD_NW; w++) m = fmaxf(m, sm.wm[w]);
-        float o = 0.0f;
-#pragma unroll
-        for (int w = 0; w < FD_NW; w++) {
-            const float f = (sm.wm[w] == -INFINITY) ? 0.0f : __expf(sm.wm[w] - m);
-            o = fmaf((tid < 64) ? sm.part[w][tid] : sm.wl[w], f, o);
-        }
-        part[(tid < 64) ? tid : 65] = o;
-        if (tid == 64) part[64] = m;
-    }
-    // ---- the last chunk of this head to finish combines: o = sum_c o_c * exp(m_c - m) / sum_c l_c * exp(m_c - m), E(o)
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) sm.last = (atomicAdd(a.counters + h, 1u) == (unsigned)(nch - 1));
-    __syncthreads();
-    if (sm.last) {
-    __threadfence();
-    if (wid < 2) {
-        const float* p = a.parts + (size_t)h * nch_max * FD_PART;
-        float m = -INFINITY;
-        for (int cc = 0; cc < nch; cc++) m = fmaxf(m, __ldcg(p + cc * FD_PART + 64));
-        float l = 0.0f, o = 0.0f;
-        for (int cc = 0; cc < nch; cc++) {
-            const float mc = __ldcg(p + cc * FD_PART + 64);
-            const float f = (mc == -INFINITY) ? 0.0f : __expf(mc - m);
-            l = fmaf(__ldcg(p + cc * FD_PART + 65), f, l);
-            o = fmaf(__ldcg(p + cc * FD_PART + tid), f, o);
-        }
-        float dd;
-        const int q = fd_lane_encode(__fdividef(o, l), &dd);          // E(attention output), ops.h:1084
-        int s = q;
-#pragma unroll
-        for (int ofs = 16; ofs > 0; ofs >>= 1) s += __shfl_xor_sync(0xffffffffu, s, ofs);
-        const int b = 2 * h + wid;
-        a.out.codes[b * 32 + perm_byte(lane)] = (uint8_t)(int8_t)q;
-        if (lane == 0) { a.out.ad[b] = dd; a.out.n7[b] = -7 * s; }
-    }
-    if (tid == 0) a.counters[h] = 0u;
-    }
-    __syncthreads();
+        __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(FD_NT, 2) k_fd_attn(FdAttnArgs a, int n_heads) {
+__global__ void __launch_bounds__(FD_NT, 2) k_fd_attn(FdAttnArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     fd_trace(4 * 4 + 0);
     fd_launch_dependents();
     FdPdlSync sync;
-    fd_attn_phase<1>(a, smem, sync, n_heads, FD_CHUNKS, -1);
+    fd_attn_phase(a, smem, sync, -1);
     fd_trace(4 * 4 + 2);
 }
 
@@ -754,7 +759,6 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fd_attn(FdAttnArgs a, int n_heads)
 // One CTA per SM; rows (prefill rows and greedy steps) loop inside; a phase boundary is a grid barrier (one relaxed atomic
 // arrival per CTA + one polling thread per CTA) instead of a kernel boundary.  A CTA issues the register loads of its first
 // weight rows of the NEXT phase before it arrives at the barrier, so weights never sit on the dependency chain.
-constexpr int FDM_CHUNKS = 4;          // 32 heads x 4 chunks = 128 attention units on 148 CTAs
 
 struct FdMegaParams {
     const FdArgs* gemv;       // [4 * n_layers + 1]: per layer q|k|v, o, gate|up, down; the head last
@@ -770,7 +774,7 @@ struct FdMegaParams {
 static inline size_t fd_mega_smem(int n_embd, int n_ffn, int max_ctx) {
     size_t s = fd_gemv_smem(n_embd, true);
     if (fd_gemv_smem(n_ffn, false) > s) s = fd_gemv_smem(n_ffn, false);
-    if (fd_attn_smem(max_ctx, FDM_CHUNKS) > s) s = fd_attn_smem(max_ctx, FDM_CHUNKS);          // (>= the 8-chunk variant's)
+    if (fd_attn_smem(fd_chunk_len(max_ctx, 128)) > s) s = fd_attn_smem(fd_chunk_len(max_ctx, 128));
     return s;
 }
 
@@ -812,7 +816,6 @@ template <int WT>
 __global__ void __launch_bounds__(FD_NT, 1) k_fd_mega(FdMegaParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int R2 = (WT == DT_Q4) ? 4 : 2, R6 = (WT == DT_Q4) ? 2 : 1, RS = 2 * R2;      // RS: a gate|up unit in one pass (Q4)
-    constexpr int NCH = FDM_CHUNKS, KPT = 2;
     FdGridSync sync{P.bar, P.bar_base, nullptr, 0};
     const int n_rows = P.n_body + P.n_head;
     int pos = __ldcg(&P.st->pos);          // rows advance it in lockstep in every CTA
@@ -820,7 +823,7 @@ __global__ void __launch_bounds__(FD_NT, 1) k_fd_mega(FdMegaParams P) {
         if (r == n_rows - 1 && (int)blockIdx.x == P.prof_cta) sync.prof = P.prof;
         for (int li = 0; li < P.n_layers; li++) {
             fd_gemv_phase<WT, FD_NORM, FD_RAW, 2, R2>(P.gemv[4 * li + 0], smem, sync, pos);
-            fd_attn_phase<KPT>(P.attn[li], smem, sync, P.n_heads, NCH, pos);
+            fd_attn_phase(P.attn[li], smem, sync, pos);
             fd_gemv_phase<WT, FD_CODES, FD_RAW, 2, R2>(P.gemv[4 * li + 1], smem, sync, pos);
             fd_gemv_phase<WT, FD_NORM, FD_SILU, 2, RS>(P.gemv[4 * li + 2], smem, sync, pos);
             fd_gemv_phase<WT, FD_CODES, FD_RAW, 6, R6>(P.gemv[4 * li + 3], smem, sync, pos);
@@ -1086,11 +1089,11 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fdb_attn(FdAttnArgs a) {
     b.rqkv += (size_t)s * (a.n_embd + 2 * a.kv_dim);
     b.kq += s * a.seq_kv_codes; b.vq += s * a.seq_kv_codes; b.ks += s * a.seq_kv_scales; b.vs += s * a.seq_kv_scales;
     b.st += s;
-    b.parts += (size_t)s * a.n_heads * FD_CHUNKS * FD_PART;
+    b.parts += (size_t)s * a.n_heads * FD_MAXCH * FD_PART;
     b.counters += (size_t)s * (a.n_heads + 1);
     b.out.codes += (size_t)s * a.n_embd; b.out.ad += (size_t)s * (a.n_embd / 32); b.out.n7 += (size_t)s * (a.n_embd / 32);
     FdPdlSync sync;
-    fd_attn_phase<1>(b, smem, sync, a.n_heads, FD_CHUNKS, -1);
+    fd_attn_phase(b, smem, sync, -1);
     fd_trace(4 * 4 + 2);
 }
 

@@ -21,7 +21,7 @@ eng.set_option("fd_prof_cta", cta)
 eng.decode(8)
 capi.sync()
 GEMV = ["entry", "barrier", "prologue", "rows"]          # stamps: entry, after barrier, after prologue, after rows
-ATTN = ["entry", "barrier", "qkv-prep", "blocks"] if cta < 128 else ["entry", "barrier"]   # combine lands in o:entry
+ATTN = ["entry", "barrier", "prep+K/V staged", "blocks"] if cta < 64 and cta % 16 < 15 else ["entry", "barrier"]   # combine lands in o:entry
 n = cfg.n_layers * (4 * 4 + len(ATTN)) + 4
 t = eng.read_prof(n + 1).astype(np.int64)
 names, layout = [], [("qkv", GEMV), ("attn", ATTN), ("o", GEMV), ("gate|up", GEMV), ("down", GEMV)]
