@@ -224,11 +224,10 @@ static __host__ __device__ inline size_t fd_gemv_smem(int K, bool norm) {
     const int nb = K / 32;
     size_t s = (size_t)nb * 32 + (size_t)nb * 8;        // codes, ad, n7
     s = (s + 15) & ~(size_t)15;
-    if (norm) s += (size_t)K * 4;
+    (void)norm;
     return s + 64 * 4 + 64;                             // reduction scratch / gate|up block
 }
 
-// NBL = blocks per lane (K <= 32 * 32 * NBL), R = rows per warp pass
 // NORM prologue: x = E(res + E(delta)) or the embedding row, RMSNorm, E -> staged vector `sv` (shared memory).  Whole CTA.
 template <int NQ>
 __device__ __forceinline__ void fd_norm_stage(const FdArgs& a, const FdStaged& sv, float* scratch, const uint2 (&nw)[NQ], int pos, bool write_res) {
@@ -303,6 +302,7 @@ __device__ __forceinline__ void fd_norm_stage(const FdArgs& a, const FdStaged& s
         fd_stage_quad(sv, e0 >> 5, (e0 & 31) >> 2, y, valid);
     }
 }
+// NBL = blocks per lane (K <= 32 * 32 * NBL), R = rows per warp pass.
 // `sync()` orders this phase after its producer: griddepcontrol.wait in the one-kernel-per-phase chain, a grid barrier in the
 // persistent kernel.  Everything before it touches only weights.
 template <int WT, int PRO, int EPI, int NBL, int R, typename Sync>
@@ -312,9 +312,7 @@ __device__ __forceinline__ void fd_gemv_phase(const FdArgs& a, unsigned char* sm
     sv.aw = reinterpret_cast<uint32_t*>(smem);
     sv.ad = reinterpret_cast<float*>(smem + (size_t)nb * 32);
     sv.n7 = reinterpret_cast<int*>(smem + (size_t)nb * 36);
-    unsigned char* p = smem + ((((size_t)nb * 40) + 15) & ~(size_t)15);
-    float* xbuf = reinterpret_cast<float*>(p);
-    float* scratch = reinterpret_cast<float*>(p + ((PRO == FD_NORM) ? (size_t)K * 4 : 0));      // 64 floats
+    float* scratch = reinterpret_cast<float*>(smem + ((((size_t)nb * 40) + 15) & ~(size_t)15));      // 64 floats
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
     sync.arrive();
