@@ -59,7 +59,7 @@ public:
     }
     // candidate set of topk_sample (tinyllama.cpp:466-478) selected on the device: values[k], ids[k], largest first
     void topk(int k, float* values, int32_t* ids) { GTEN_CUDA_OK(gtb_engine_topk(eng_, k, values, ids)); }
-    // Batched decode (gtb_engine_batch_*, include/gten_b200.h): up to 8 sequences advance together and share every weight read.
+    // Batched decode (gtb_engine_batch_*, include/gten_b200.h): up to 16 sequences advance together and share every weight read.
     // batch_adopt(s) moves the sequence of the last logits()/prefill call into slot s; batch_decode(k) runs k greedy steps of all slots.
     void batch_create(int n_seq) { GTEN_CUDA_OK(gtb_engine_batch_create(eng_, n_seq)); }
     void batch_adopt(int slot) { GTEN_CUDA_OK(gtb_engine_batch_adopt(eng_, slot)); }

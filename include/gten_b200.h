@@ -144,7 +144,7 @@ int gtb_engine_acv(gtb_engine_t e, int layer, int acv_id, float* h_out, int* wid
  * "pf_attn2" (second attention sweep that also reproduces the fp16 rounding of the probability-row block scales, default 0) */
 int gtb_engine_set_option(gtb_engine_t e, const char* name, int value);
 
-/* Batched decode (the reference decodes one sequence, tinyllama.cpp:395-440): up to 8 sequences advance
+/* Batched decode (the reference decodes one sequence, tinyllama.cpp:395-440): up to 16 sequences advance
  * together through the order-free kernels (tolerance contract of "fast_decode"), every weight is read once per step for all of
  * them.  A sequence decoded in a batch gives the same bits as the same sequence decoded alone with "fast_decode".
  *   gtb_engine_batch_create(e, n)   allocate n slots (own K/V cache, tokens, position each); n = 0 frees them

@@ -112,6 +112,19 @@ def test_fast_greedy_loop_and_positions(capi, mega):
     assert np.array_equal(seqs[0], seqs[1])
 
 
+def test_fast_decode_refuses_activation_capture(capi):
+    """capture_acv dumps the per-op activations of the order-exact kernels; the order-free chain keeps them in staged form only."""
+    cfg = W.mini_config(n_layers=1, n_vocab=64)
+    e = capi.Engine(cfg, 32, Q4).load(W.synth_weights(cfg, Q4, seed=1))
+    e.set_option("fast_decode", 1)
+    e.set_option("capture_acv", 1)
+    with pytest.raises(capi.GtbError):
+        e.logits(np.array([1, 2, 3], np.int32), 0)
+    e.set_option("capture_acv", 0)
+    assert e.logits(np.array([1, 2, 3], np.int32), 0).shape == (64,)
+    e.close()
+
+
 def test_fast_decode_rejects_fp16_models(capi):
     cfg = W.mini_config(n_layers=1, n_vocab=64)
     e = capi.Engine(cfg, 32, F16).load(W.synth_weights(cfg, F16, seed=1))
@@ -157,7 +170,9 @@ def test_fast_generate_with_eos(capi):
 
 # ---------------------------------------------------------------- batched decode (gtb_engine_batch_*)
 @pytest.mark.parametrize("graph", [1, 0], ids=["graph", "eager"])
-@pytest.mark.parametrize("wdt,lens", [(Q4, (20, 37, 64)), (Q8, (5, 33, 40, 41, 64, 90, 100, 7)), (Q4, (50,))], ids=["q4x3", "q8x8", "q4x1"])
+@pytest.mark.parametrize("wdt,lens", [(Q4, (20, 37, 64)), (Q8, (5, 33, 40, 41, 64, 90, 100, 7)), (Q4, (50,)),
+                                      (Q4, (3, 9, 17, 20, 31, 32, 33, 40, 47, 55, 64, 65, 70, 90, 100, 110)), (Q8, tuple(range(10, 100, 10)))],
+                         ids=["q4x3", "q8x8", "q4x1", "q4x16", "q8x9"])
 def test_batch_decode_equals_single_sequence(capi, wdt, lens, graph):
     """A sequence decoded in a batch gives the SAME BITS (tokens and logits) as the same sequence decoded alone through the
     order-free kernels: the batch only shares the weight reads.  Sequences have different lengths (own positions, own K/V)."""
@@ -192,7 +207,7 @@ def test_batch_decode_argument_errors(capi):
     cfg = W.mini_config(n_layers=1, n_vocab=64)
     e = capi.Engine(cfg, 32, Q4).load(W.synth_weights(cfg, Q4, seed=1))
     with pytest.raises(capi.GtbError):
-        e.batch_create(9)
+        e.batch_create(17)
     with pytest.raises(capi.GtbError):
         e.batch_decode(1)                 # no slots
     e.batch_create(2)

@@ -385,7 +385,7 @@ class Engine:
         check(lib().gtb_engine_acv(self.h, layer, aid, _hp(out), C.byref(w)))
         return out[: w.value].copy()
 
-    # ---- batched decode (gtb_engine_batch_*): up to 8 sequences share every weight read
+    # ---- batched decode (gtb_engine_batch_*): up to 16 sequences share every weight read
     def batch_create(self, n_seq: int):
         check(lib().gtb_engine_batch_create(self.h, n_seq))
 

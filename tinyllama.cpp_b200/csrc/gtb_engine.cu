@@ -703,23 +703,22 @@ int batch_alloc(gtb_engine* e, int n) {
     return GTB_OK;
 }
 
-template <int WT, int EPI>
-int launch_fdb(const FdArgs& a, int grid) {
-    const int nbl = (a.K / 32 + 31) / 32;
+template <int WT, int EPI, int NBL, int R, int NSM>
+int launch_fdb_k(const FdArgs& a, int grid) {
     const size_t smem = fdb_gemv_smem(a.K, a.n_seq);
-    if (nbl <= 2) {
-        constexpr int R = (WT == DT_Q4) ? 4 : 2;
-        static bool done = false;
-        if (!done) { GTB_CUDA(cudaFuncSetAttribute(k_fdb_gemv<WT, EPI, 2, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); done = true; }
-        GTB_CUDA(fd_launch(k_fdb_gemv<WT, EPI, 2, R>, grid, smem, a));
-    } else {
-        constexpr int R = (WT == DT_Q4) ? 2 : 1;
-        static bool done = false;
-        if (!done) { GTB_CUDA(cudaFuncSetAttribute(k_fdb_gemv<WT, EPI, 6, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); done = true; }
-        GTB_CUDA(fd_launch(k_fdb_gemv<WT, EPI, 6, R>, grid, smem, a));
-    }
+    static bool done = false;
+    if (!done) { GTB_CUDA(cudaFuncSetAttribute(k_fdb_gemv<WT, EPI, NBL, R, NSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (NSM > 8 ? 128 : 64) * 1024)); done = true; }
+    GTB_CUDA(fd_launch(k_fdb_gemv<WT, EPI, NBL, R, NSM>, grid, smem, a));
     GTB_LAUNCHED();
     return GTB_OK;
+}
+// rows per warp pass x sequence slots = 32 sums per lane at most: up to 8 sequences R = 4 (2 for long rows / Q8), up to 16 half of that
+template <int WT, int EPI>
+int launch_fdb(const FdArgs& a, int grid) {
+    const bool wide = (a.K / 32 + 31) / 32 > 2, big = a.n_seq > 8;
+    constexpr int R2 = (WT == DT_Q4) ? 4 : 2, R6 = (WT == DT_Q4) ? 2 : 1;
+    if (!big) return wide ? launch_fdb_k<WT, EPI, 6, R6, 8>(a, grid) : launch_fdb_k<WT, EPI, 2, R2, 8>(a, grid);
+    return wide ? launch_fdb_k<WT, EPI, 6, 1, 16>(a, grid) : launch_fdb_k<WT, EPI, 2, 2, 16>(a, grid);
 }
 
 // one row of every sequence of the batch: 7 launches per layer + 2 for the head
@@ -802,6 +801,7 @@ int enqueue_batch_row(gtb_engine* e) {
 
 int enqueue_row_dt(gtb_engine* e, bool with_head, int eos_id) {
     if (e->fast) {
+        if (e->capture) return fail(GTB_ERR_STATE, "capture_acv records the order-exact kernels; switch fast_decode off");
         if (e->cfg.wdtype == GTB_Q8) return enqueue_row_fast<DT_Q8>(e, with_head, eos_id);
         if (e->cfg.wdtype == GTB_Q4) return enqueue_row_fast<DT_Q4>(e, with_head, eos_id);
         return fail(GTB_ERR_STATE, "fast_decode is built for Q8-activation models (Q8, Q4 weights)");

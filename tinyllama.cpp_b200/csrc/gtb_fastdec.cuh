@@ -844,7 +844,7 @@ __global__ void __launch_bounds__(FD_NT, 1) k_fd_mega(FdMegaParams P) {
 // single-sequence chain, so a sequence decoded in a batch gives the same bits as decoded alone (tests/test_fastdec_gpu.py).
 // The redundant per-CTA NORM prologue would cost n_seq times as much, so the norm is its own small kernel here (one CTA per
 // sequence) and every GEMV starts from staged codes.
-constexpr int FDB_MAX = 8;
+constexpr int FDB_MAX = 16;         // sequences per batch at most; kernels are instantiated for 8 (R x 8 sums per lane) and 16 (R x 16)
 
 __global__ void __launch_bounds__(FD_NT) k_fdb_norm(FdArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -883,8 +883,10 @@ static __host__ __device__ inline size_t fdb_gemv_smem(int K, int n_seq) {
     return (size_t)n_seq * (K / 32) * 40 + (size_t)FDB_MAX * 64 * 4 + 256;
 }
 
-template <int WT, int EPI, int NBL, int R>
+// NSM = sequence slots the instantiation carries (8 or 16); R * NSM <= 32 row sums per lane
+template <int WT, int EPI, int NBL, int R, int NSM>
 __global__ void __launch_bounds__(FD_NT, 2) k_fdb_gemv(FdArgs a) {
+    static_assert(R * NSM <= 32 && (R * NSM & (R * NSM - 1)) == 0, "the warp reduce-scatter hands one (row, sequence) sum to each lane");
     extern __shared__ __align__(16) unsigned char smem[];
     const int K = a.K, nb = K / 32, NS = a.n_seq;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -892,7 +894,7 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fdb_gemv(FdArgs a) {
     uint32_t* s_aw = reinterpret_cast<uint32_t*>(smem);
     float* s_ad = reinterpret_cast<float*>(smem + (size_t)NS * nb * 32);
     int* s_n7 = reinterpret_cast<int*>(smem + (size_t)NS * nb * 36);
-    float* scratch = reinterpret_cast<float*>(smem + (((size_t)NS * nb * 40 + 15) & ~(size_t)15));          // [FDB_MAX][64]
+    float* scratch = reinterpret_cast<float*>(smem + (((size_t)NS * nb * 40 + 15) & ~(size_t)15));          // [NSM][64]
     fd_trace((1 + EPI) * 4 + 0);
     fd_launch_dependents();
     if (tid < 2 && a.pf[tid]) {
@@ -930,11 +932,11 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fdb_gemv(FdArgs a) {
     float best = -INFINITY;          // ARGMAX: lane u * 8 + s tracks sequence s over its rows
     int arg = 0x7fffffff;
     for (; v < v1;) {
-        float acc[R][FDB_MAX];
+        float acc[R][NSM];
 #pragma unroll
         for (int u = 0; u < R; u++)
 #pragma unroll
-            for (int s = 0; s < FDB_MAX; s++) acc[u][s] = 0.0f;
+            for (int s = 0; s < NSM; s++) acc[u][s] = 0.0f;
 #pragma unroll
         for (int i = 0; i < NBL; i++) {
             const int b = lane + 32 * i;
@@ -943,7 +945,7 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fdb_gemv(FdArgs a) {
 #pragma unroll
                 for (int u = 0; u < R; u++) dw[u] = h2f((uint16_t)bt.sc[u][i]);
 #pragma unroll
-                for (int s = 0; s < FDB_MAX; s++) {
+                for (int s = 0; s < NSM; s++) {
                     if (s >= NS) break;          // a real (warp-uniform) branch: if-converted code would issue all 8 sequences
                     const uint4 ax = reinterpret_cast<const uint4*>(s_aw)[((size_t)s * nb + b) * 2];
                     const uint4 ay = reinterpret_cast<const uint4*>(s_aw)[((size_t)s * nb + b) * 2 + 1];
@@ -959,12 +961,12 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fdb_gemv(FdArgs a) {
         }
         // warp reduce-scatter of the R x 8 sums: lane j ends up with the total of (row j / 8, sequence j % 8).  Offsets run
         // 16, 8, 4, 2, 1 like the butterfly of the single-sequence kernel, so every total is the same tree of additions.
-        constexpr int NV = R * FDB_MAX;
+        constexpr int NV = R * NSM;
         float vals[NV];
 #pragma unroll
         for (int u = 0; u < R; u++)
 #pragma unroll
-            for (int s = 0; s < FDB_MAX; s++) vals[u * FDB_MAX + s] = acc[u][s];
+            for (int s = 0; s < NSM; s++) vals[u * NSM + s] = acc[u][s];
         {
             int n = NV;
 #pragma unroll
@@ -994,7 +996,7 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fdb_gemv(FdArgs a) {
         for (int u = 0; u < R; u++) rcur[u] = row[u];
         v += FD_NW * R;
         if (v < v1) { rows_of(v, row); fd_load_batch<WT, NBL, R>(bt, a.w, a.ws, row, nb); }
-        const int mu = (lane & (NV - 1)) / FDB_MAX, ms = lane % FDB_MAX;
+        const int mu = (lane & (NV - 1)) / NSM, ms = lane % NSM;
         int mrow = -1;
 #pragma unroll
         for (int u = 0; u < R; u++) if (mu == u) mrow = rcur[u];
@@ -1010,37 +1012,37 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fdb_gemv(FdArgs a) {
     fd_trace((1 + EPI) * 4 + 2);
     if (EPI == FD_SILU && unit < n_units) {
         __syncthreads();
-        if (wid < NS) {                  // warp s: E(E(silu(E(gate))) * E(up)) of sequence s (modules.cpp:238-247)
-            const float g1 = fd_lane_roundtrip(scratch[wid * 64 + lane]);
-            const float u1 = fd_lane_roundtrip(scratch[wid * 64 + 32 + lane]);
+        for (int sq = wid; sq < NS; sq += FD_NW) {          // a warp per sequence: E(E(silu(E(gate))) * E(up)) (modules.cpp:238-247)
+            const float g1 = fd_lane_roundtrip(scratch[sq * 64 + lane]);
+            const float u1 = fd_lane_roundtrip(scratch[sq * 64 + 32 + lane]);
             const float g2 = fd_lane_roundtrip(__fdividef(g1, 1.0f + __expf(-g1)));
             float dd;
             const int q = fd_lane_encode(g2 * u1, &dd);
             int sum = q;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            a.act_out.codes[(size_t)wid * a.n_ffn + unit * 32 + perm_byte(lane)] = (uint8_t)(int8_t)q;
-            if (lane == 0) { a.act_out.ad[(size_t)wid * n_units + unit] = dd; a.act_out.n7[(size_t)wid * n_units + unit] = -7 * sum; }
+            a.act_out.codes[(size_t)sq * a.n_ffn + unit * 32 + perm_byte(lane)] = (uint8_t)(int8_t)q;
+            if (lane == 0) { a.act_out.ad[(size_t)sq * n_units + unit] = dd; a.act_out.n7[(size_t)sq * n_units + unit] = -7 * sum; }
         }
     }
     if (EPI == FD_ARGMAX) {
-        // rows of this warp for sequence ms: lanes ms, 8 + ms, 16 + ms, 24 + ms; then the 8 warps; then the last CTA over all CTAs
-        float* sval = scratch;                                   // [FD_NW][FDB_MAX]
-        int* sidx = reinterpret_cast<int*>(scratch + 64);        // [FD_NW][FDB_MAX]
+        // rows of this warp for sequence ms: lanes ms, NSM + ms, ...; then the 8 warps; then the last CTA over all CTAs
+        float* sval = scratch;                                          // [FD_NW][NSM]
+        int* sidx = reinterpret_cast<int*>(scratch + FD_NW * NSM);      // [FD_NW][NSM]
         __shared__ bool is_last;
 #pragma unroll
-        for (int o = 8; o <= 16; o <<= 1) {
+        for (int o = NSM; o <= 16; o <<= 1) {
             const float ov = __shfl_xor_sync(0xffffffffu, best, o);
             const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
             if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
         }
-        if (lane < FDB_MAX) { sval[wid * FDB_MAX + lane] = best; sidx[wid * FDB_MAX + lane] = arg; }
+        if (lane < NSM) { sval[wid * NSM + lane] = best; sidx[wid * NSM + lane] = arg; }
         __syncthreads();
         if (tid < NS) {
             best = sval[tid]; arg = sidx[tid];
             for (int w = 1; w < FD_NW; w++) {
-                const float ov = sval[w * FDB_MAX + tid];
-                const int oi = sidx[w * FDB_MAX + tid];
+                const float ov = sval[w * NSM + tid];
+                const int oi = sidx[w * NSM + tid];
                 if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
             }
             a.arg_val[(size_t)tid * gridDim.x + blockIdx.x] = best;
@@ -1050,27 +1052,29 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fdb_gemv(FdArgs a) {
         __syncthreads();
         if (tid == 0) is_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
         __syncthreads();
-        if (is_last && wid < NS) {
+        if (is_last) {
             __threadfence();
-            best = -INFINITY; arg = 0x7fffffff;
-            for (int c = lane; c < (int)gridDim.x; c += 32) {
-                const float ov = __ldcg(a.arg_val + (size_t)wid * gridDim.x + c);
-                const int oi = __ldcg(a.arg_idx + (size_t)wid * gridDim.x + c);
-                if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
-            }
+            for (int sq = wid; sq < NS; sq += FD_NW) {
+                best = -INFINITY; arg = 0x7fffffff;
+                for (int c = lane; c < (int)gridDim.x; c += 32) {
+                    const float ov = __ldcg(a.arg_val + (size_t)sq * gridDim.x + c);
+                    const int oi = __ldcg(a.arg_idx + (size_t)sq * gridDim.x + c);
+                    if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
+                }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
-                if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
-            }
-            if (lane == 0) {
-                if (arg == 0x7fffffff) arg = 0;
-                DevState* st = a.st + wid;
-                const int pcur = __ldcg(&st->pos);
-                a.tok_out[(size_t)wid * a.tok_stride + pcur + 1] = arg;
-                st->pos = pcur + 1;
-                st->n_gen = __ldcg(&st->n_gen) + 1;
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+                    if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
+                }
+                if (lane == 0) {
+                    if (arg == 0x7fffffff) arg = 0;
+                    DevState* st = a.st + sq;
+                    const int pcur = __ldcg(&st->pos);
+                    a.tok_out[(size_t)sq * a.tok_stride + pcur + 1] = arg;
+                    st->pos = pcur + 1;
+                    st->n_gen = __ldcg(&st->n_gen) + 1;
+                }
             }
         }
         if (is_last && tid == 0) *a.counter = 0u;

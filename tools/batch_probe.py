@@ -25,7 +25,7 @@ eng.decode(steps)
 capi.sync()
 print(f"single-sequence fast_decode: {(time.perf_counter() - t0) / steps * 1e6:8.1f} us/step")
 eng.set_option("fast_decode", 0)
-for B in (1, 2, 4, 8):
+for B in (1, 2, 4, 8, 12, 16):
     eng.batch_create(B)
     for s in range(B):
         eng.prefill_fast(W.synth_prompt(7 + s, ctx, cfg.n_vocab))
