@@ -26,4 +26,10 @@ for wdt in (W.Q4, W.Q8):
         e.batch_adopt(s)
     e.batch_decode(2)
     print(wdt, "batch", [e.batch_position(s) for s in range(3)], float(np.abs(e.batch_read_logits(2)).max()))
+    e.batch_create(10)                   # the 16-slot instantiation of the batch kernels
+    for s in range(10):
+        e.prefill_fast(W.synth_prompt(30 + s, 20 + 31 * s, cfg.n_vocab))
+        e.batch_adopt(s)
+    e.batch_decode(2)
+    print(wdt, "batch10", [e.batch_position(s) for s in range(10)], float(np.abs(e.batch_read_logits(9)).max()))
     e.close()
