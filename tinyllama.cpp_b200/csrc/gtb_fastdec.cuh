@@ -74,8 +74,12 @@ __device__ __forceinline__ void fd_trace(int) {}
 __device__ __forceinline__ void fd_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void fd_wait_prior() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// the warp index through a shuffle: the compiler then knows it is warp-uniform, so branches and loops on it keep the warp
+// converged and the shuffles inside them need no WARPSYNC / reconvergence wrappers
+__device__ __forceinline__ int fd_warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ float fd_block_sum(float v, float* red) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wid = fd_warp_id();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) red[wid] = v;
@@ -313,7 +317,7 @@ __device__ __forceinline__ void fd_gemv_phase(const FdArgs& a, unsigned char* sm
     sv.ad = reinterpret_cast<float*>(smem + (size_t)nb * 32);
     sv.n7 = reinterpret_cast<int*>(smem + (size_t)nb * 36);
     float* scratch = reinterpret_cast<float*>(smem + ((((size_t)nb * 40) + 15) & ~(size_t)15));      // 64 floats
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wid = fd_warp_id();
 
     sync.arrive();
     sync.stamp();
@@ -521,7 +525,7 @@ __device__ __forceinline__ void fd_attn_phase(const FdAttnArgs& a, unsigned char
     uint32_t* qw = reinterpret_cast<uint32_t*>(smem + (size_t)CL * 144);    // [FD_NW][16]
     float* qd = reinterpret_cast<float*>(qw + FD_NW * 16);                  // [FD_NW][2]
     int* last = reinterpret_cast<int*>(qd + FD_NW * 2);
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wid = fd_warp_id();
     const int slot = lane >> 2, cq = lane & 3;          // P.V: lane = (position slot of 8, 16 channels)
     sync.arrive();
     sync.stamp();
@@ -889,7 +893,7 @@ __global__ void __launch_bounds__(FD_NT, 2) k_fdb_gemv(FdArgs a) {
     static_assert(R * NSM <= 32 && (R * NSM & (R * NSM - 1)) == 0, "the warp reduce-scatter hands one (row, sequence) sum to each lane");
     extern __shared__ __align__(16) unsigned char smem[];
     const int K = a.K, nb = K / 32, NS = a.n_seq;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wid = fd_warp_id();
     // staged vectors of all sequences: [NS][nb][8] words, [NS][nb] scales, [NS][nb] -7 * code sums
     uint32_t* s_aw = reinterpret_cast<uint32_t*>(smem);
     float* s_ad = reinterpret_cast<float*>(smem + (size_t)NS * nb * 32);
