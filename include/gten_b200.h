@@ -110,7 +110,9 @@ int gtb_engine_logits(gtb_engine_t e, const int32_t* h_tokens, int n_tokens, int
 int gtb_engine_generate(gtb_engine_t e, int32_t* h_tokens, int n_prompt, int n_new, int eos_id, int* n_generated);
 /* fine-grained control used by bench.py and the tests */
 int gtb_engine_reset(gtb_engine_t e);
-int gtb_engine_prefill(gtb_engine_t e, const int32_t* h_tokens, int n_tokens);     /* exact path, rows [0,n) */
+/* exact path, rows [0,n): Q8/Q4 models run them 64 at a time through the multi-row kernels (gtb_xrows.cu), bit-identical to
+ * the reference's row loop (gten/ops.h:632); the last row also samples the first new token */
+int gtb_engine_prefill(gtb_engine_t e, const int32_t* h_tokens, int n_tokens);
 int gtb_engine_decode(gtb_engine_t e, int n_steps);                                /* n greedy steps, device-resident */
 /* Batched prefill of rows [0,n): every Linear of the n rows (ops.h:613-670) is one tcgen05/TMEM GEMM fed by TMA
  * (fp16 operands dequantised from the Q8/Q4 blocks), the reference's re-encode points are applied in the epilogues,
@@ -141,17 +143,24 @@ int gtb_engine_acv(gtb_engine_t e, int layer, int acv_id, float* h_out, int* wid
  * "fd_ahead" (fast_decode: L2 look-ahead distance in GEMV steps, default 3), "fd_prof_cta" (which CTA writes the "prof" stamps),
  * "pf_layers" (debug: batched prefill stops after this many layers), "pf_fused" (RoPE/KV append and SiLU*up inside the
  * GEMM epilogues, default 1), "pf_pdl" (programmatic dependent launch, default 1), "pf_2cta" (CTA-pair tcgen05 GEMM, default 0),
- * "pf_attn2" (second attention sweep that also reproduces the fp16 rounding of the probability-row block scales, default 0) */
+ * "pf_attn2" (second attention sweep that also reproduces the fp16 rounding of the probability-row block scales, default 0),
+ * "xrows" (1, default: runs of >= "xr_min_rows" (4) rows whose positions the host knows -- gtb_engine_prefill, _logits, _generate --
+ * go through the order-exact multi-row kernels in passes of "xr_rows" (64) rows: same bits as the row-at-a-time kernels, one weight
+ * read per pass; 0: every row through the persistent kernel), "batch_exact" (see gtb_engine_batch_*) */
 int gtb_engine_set_option(gtb_engine_t e, const char* name, int value);
 
-/* Batched decode (the reference decodes one sequence, tinyllama.cpp:395-440): up to 16 sequences advance
- * together through the order-free kernels (tolerance contract of "fast_decode"), every weight is read once per step for all of
- * them.  A sequence decoded in a batch gives the same bits as the same sequence decoded alone with "fast_decode".
- *   gtb_engine_batch_create(e, n)   allocate n slots (own K/V cache, tokens, position each); n = 0 frees them
- *   gtb_engine_batch_adopt(e, s)    slot s <- the engine's current sequence (after gtb_engine_prefill / _prefill_fast / decode)
- *   gtb_engine_batch_decode(e, k)   k greedy steps of every slot (device-side argmax, tokens stay on the device)
+/* Batched decode (BASELINE.json configs[4]; the reference decodes one sequence, tinyllama.cpp:395-440): up to 64
+ * sequences advance together and every weight block is loaded once per step for all of them.  Default ("batch_exact" = 1): the
+ * ORDER-EXACT multi-row kernels (gtb_xrows.cu) -- every sequence's tokens and logits are bit-identical to the same sequence decoded
+ * alone by gtb_engine_decode, i.e. to the reference.  "batch_exact" = 0: the order-free kernels (tolerance contract of "fast_decode",
+ * at most 16 sequences).
+ *   gtb_engine_batch_create(e, n)        allocate n slots (own K/V cache, tokens, position each); n = 0 frees them
+ *   gtb_engine_batch_prefill(e, s, t, n) exact prefill of n prompt ids into slot s (multi-row passes of up to 64 rows), first token appended
+ *   gtb_engine_batch_adopt(e, s)         slot s <- the engine's current sequence (after gtb_engine_prefill / _prefill_fast / decode)
+ *   gtb_engine_batch_decode(e, k)        k greedy steps of every slot (device-side argmax, tokens stay on the device)
  *   gtb_engine_batch_position / _read_tokens / _read_logits: per-slot state */
 int gtb_engine_batch_create(gtb_engine_t e, int n_seq);
+int gtb_engine_batch_prefill(gtb_engine_t e, int seq, const int32_t* h_tokens, int n_tokens);
 int gtb_engine_batch_adopt(gtb_engine_t e, int seq);
 int gtb_engine_batch_decode(gtb_engine_t e, int n_steps);
 int gtb_engine_batch_position(gtb_engine_t e, int seq, int* pos);

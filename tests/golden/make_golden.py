@@ -32,6 +32,9 @@ FULL = {
 }
 
 
+SEQ64 = dict(n_seq=4, n_prompt=128, n_new=64, max_ctx=192)
+
+
 def op_inputs(seed=1234):
     """Seeded op-level inputs shared by make_golden and the tests."""
     rng = np.random.default_rng(seed)
@@ -137,6 +140,18 @@ def main(argv):
                                 keep_steps=np.array(keep), keep_logits=lg[keep],
                                 cpu_prefill_s=times[0], cpu_decode_s=times[1], n_prompt=n_prompt, n_new=n_new, max_ctx=max_ctx)
             print(f"  reference CPU here: prefill {n_prompt / times[0]:.1f} tok/s, decode {(n_new - 1) / times[1]:.2f} tok/s")
+        elif what == "seq64_q4":
+            # BASELINE.json config 5 (bench.py --workload q4_seq64): the first SEQ64["n_seq"] of the 64 sequences, 128 + 64 tokens each
+            S = SEQ64
+            cfg = W.TINYLLAMA
+            m = lib.model(cfg, S["max_ctx"], Q4).load(W.synth_weights(cfg, Q4, seed=1))
+            toks, last, csum = [], [], []
+            for sidx in range(S["n_seq"]):
+                t, _, lg = m.generate(W.synth_prompt(100 + sidx, S["n_prompt"], cfg.n_vocab), S["n_new"], want_logits=True)
+                toks.append(t); last.append(lg[-1].copy()); csum.append(lg.astype(np.float64).sum(axis=1))
+                print(f"  sequence {sidx} done", flush=True)
+            m.close()
+            np.savez_compressed(OUT / "seq64_q4.npz", tokens=np.stack(toks), last_logits=np.stack(last), checksum=np.stack(csum))
         elif what == "prefill_q8":
             # BASELINE.json config 4: Q8 prefill of 2048 tokens; the oracle needs max_ctx >= 2176
             toks, times, lg = run_full(lib, Q8, 2048, 1, 2176)

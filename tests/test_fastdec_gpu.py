@@ -183,6 +183,7 @@ def test_batch_decode_equals_single_sequence(capi, wdt, lens, graph):
     steps = 7
     e = capi.Engine(cfg, 128, wdt).load(wl)
     e.set_option("graph", graph)
+    e.set_option("batch_exact", 0)        # the order-free batch kernels (the default batch mode is the exact one, tests/test_xrows_gpu.py)
     e.batch_create(len(lens))
     prompts = [W.synth_prompt(40 + i, n, cfg.n_vocab) for i, n in enumerate(lens)]
     for s, p in enumerate(prompts):
@@ -208,6 +209,7 @@ def test_batch_decode_equals_single_sequence(capi, wdt, lens, graph):
 def test_batch_decode_argument_errors(capi):
     cfg = W.mini_config(n_layers=1, n_vocab=64)
     e = capi.Engine(cfg, 32, Q4).load(W.synth_weights(cfg, Q4, seed=1))
+    e.set_option("batch_exact", 0)
     with pytest.raises(capi.GtbError):
         e.batch_create(17)
     with pytest.raises(capi.GtbError):

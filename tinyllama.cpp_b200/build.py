@@ -13,7 +13,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libgten_b200.so"
-SOURCES = ["gtb_api.cu", "gtb_ops.cu", "gtb_engine.cu", "gtb_prefill.cu"]
+SOURCES = ["gtb_api.cu", "gtb_ops.cu", "gtb_engine.cu", "gtb_prefill.cu", "gtb_xrows.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr",

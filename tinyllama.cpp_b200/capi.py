@@ -30,7 +30,7 @@ SYMBOLS = [
     "gtb_engine_set_option", "gtb_engine_weight_bytes", "gtb_engine_read_prof", "gtb_selftest_exact_sum", "gtb_engine_uses_megakernel",
     "gtb_engine_prefill_fast", "gtb_engine_pf_acv", "gtb_pf_gemm_f32", "gtb_engine_topk",
     "gtb_engine_batch_create", "gtb_engine_batch_adopt", "gtb_engine_batch_decode", "gtb_engine_batch_position",
-    "gtb_engine_batch_read_tokens", "gtb_engine_batch_read_logits",
+    "gtb_engine_batch_read_tokens", "gtb_engine_batch_read_logits", "gtb_engine_batch_prefill",
 ]
 
 
@@ -82,7 +82,7 @@ def lib():
             "gtb_pf_gemm_f32": [vp, vp, i, i, i, i, vp], "gtb_engine_topk": [vp, i, vp, vp],
             "gtb_engine_batch_create": [vp, i], "gtb_engine_batch_adopt": [vp, i], "gtb_engine_batch_decode": [vp, i],
             "gtb_engine_batch_position": [vp, i, C.POINTER(i)], "gtb_engine_batch_read_tokens": [vp, i, vp, i, i],
-            "gtb_engine_batch_read_logits": [vp, i, vp],
+            "gtb_engine_batch_read_logits": [vp, i, vp], "gtb_engine_batch_prefill": [vp, i, vp, i],
         }
         for name, args in sigs.items():
             fn = getattr(L, name)
@@ -388,6 +388,11 @@ class Engine:
     # ---- batched decode (gtb_engine_batch_*): up to 16 sequences share every weight read
     def batch_create(self, n_seq: int):
         check(lib().gtb_engine_batch_create(self.h, n_seq))
+
+    def batch_prefill(self, seq: int, tokens):
+        """Exact multi-row prefill of `tokens` straight into slot `seq`; the first greedy token is appended."""
+        tokens = np.ascontiguousarray(tokens, np.int32)
+        check(lib().gtb_engine_batch_prefill(self.h, seq, _hp(tokens), tokens.size))
 
     def batch_adopt(self, seq: int):
         """Slot `seq` <- the engine's current sequence (tokens, position, K/V cache)."""

@@ -158,6 +158,8 @@ int gtb_device_count(int* n) {
 int gtb_init(int device) {
     Context& c = ctx();
     if (c.ready && c.device == device) return GTB_OK;
+    // one library instance <-> one GPU: the stream and every kernel attribute set so far belong to the first device
+    if (c.ready) return fail(GTB_ERR_STATE, "libgten_b200 is bound to device %d; use one process per GPU (asked for device %d)", c.device, device);
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {

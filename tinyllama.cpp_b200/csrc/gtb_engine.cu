@@ -15,6 +15,7 @@
 #include "gtb_mega.cuh"
 #include "gtb_prefill.h"
 #include "gtb_fastdec.cuh"
+#include "gtb_xrows.h"
 
 namespace gtb {
 
@@ -240,6 +241,7 @@ __global__ void __launch_bounds__(1024) k_argmax_advance(const float* __restrict
 }
 
 __global__ void k_advance(DevState* st) { st->pos += 1; }
+__global__ void k_set_pos(DevState* st, int pos) { st->pos = pos; }     // stream-ordered, everything else untouched
 
 // The k largest logits and their token ids, largest first, ties to the lower id (the candidate set of topk_sample,
 // tinyllama.cpp:466-478): k rounds of a block-wide arg-max over the not-yet-taken entries.  One CTA of 1024 threads.
@@ -373,6 +375,8 @@ struct gtb_engine {
         std::vector<int> host_pos;
         cudaGraphExec_t graph = nullptr;
         int graph_launches = 0;
+        int graph_tcap = 0;          // exact mode: score-buffer capacity the captured graph was built for
+        bool graph_exact = false;
     } bb;
     int fd_chunk = 64;               // positions per attention chunk of the single-sequence fast path (the batch uses 128)
     int fd_prof_cta = 0;             // which CTA writes the "prof" stamps of k_fd_mega
@@ -387,6 +391,15 @@ struct gtb_engine {
     int pf_2cta = 0;                 // CTA-pair GEMM kernel
     int pf_pdl = 1;                  // programmatic dependent launch inside the batched prefill
     int pf_attn2 = 0;                // 1: two-sweep attention (also reproduces the fp16 rounding of the P-row block scales)
+    // order-exact multi-row path (gtb_xrows.cu): exact prefill in passes of up to 64 rows, exact batched decode
+    gtb::XrPlan* xr = nullptr;
+    bool use_xr = true;
+    int xr_min_rows = 4;             // fewer rows than this stay on the row-at-a-time kernels
+    int xr_rows = XR_MAX_ROWS;       // rows per prefill pass
+    bool batch_exact = true;         // gtb_engine_batch_decode through the exact multi-row kernels (false: order-free kernels)
+    std::vector<XrLayerW> xr_layers;
+    std::vector<uint8_t*> xr_kq, xr_vq;
+    std::vector<uint16_t*> xr_ks, xr_vs;
 };
 
 namespace {
@@ -902,10 +915,68 @@ int run_rows_mega(gtb_engine* e, int n_body, int n_head, int eos_id) {
     }
 }
 
-// rows to run: `n_body` rows without lm_head, then `n_head` rows with lm_head + argmax
-int run_rows(gtb_engine* e, int n_body, int n_head, int eos_id) {
+// ---- order-exact multi-row path (gtb_xrows.cu)
+bool xr_ok(const gtb_engine* e) {
+    return e->use_xr && !e->fast && !e->capture && xr_supported(e->cfg, e->gsz);
+}
+
+// host-side view of the weights / caches for the multi-row kernels
+int xr_model(gtb_engine* e, XrModel& m) {
+    const gtb_model_config& c = e->cfg;
+    if (!e->xr) { int r = xr_create(&e->xr, c); if (r) return r; }
+    e->xr_layers.resize(c.n_layers);
+    e->xr_kq.resize(c.n_layers); e->xr_vq.resize(c.n_layers); e->xr_ks.resize(c.n_layers); e->xr_vs.resize(c.n_layers);
+    for (int i = 0; i < c.n_layers; i++) {
+        LayerW& l = e->L[i];
+        XrLayerW& x = e->xr_layers[i];
+        x.w[0] = (const uint4*)l.qkv_data; x.s[0] = l.qkv_sc;
+        x.w[1] = (const uint4*)l.o->data; x.s[1] = l.o->scales;
+        x.w[2] = (const uint4*)l.gu_data; x.s[2] = l.gu_sc;
+        x.w[3] = (const uint4*)l.down->data; x.s[3] = l.down->scales;
+        x.attn_norm = l.attn_norm; x.ffn_norm = l.ffn_norm;
+        e->xr_kq[i] = l.kq; e->xr_vq[i] = l.vq; e->xr_ks[i] = l.ks; e->xr_vs[i] = l.vs;
+    }
+    m.cfg = c;
+    m.emb_w = e->embed->data; m.emb_s = e->embed->scales;
+    m.head_w = (const uint4*)e->lm_head->data; m.head_s = e->lm_head->scales;
+    m.final_norm = e->final_norm; m.rope_cos = e->rope_cos; m.rope_sin = e->rope_sin;
+    m.layers = e->xr_layers.data();
+    return GTB_OK;
+}
+
+// rows [p0, p0 + n_rows) of the engine's own sequence in passes of up to xr_rows rows; the last row samples if with_head
+int run_rows_xr(gtb_engine* e, int p0, int n_rows, int n_ctx, bool with_head, int eos_id) {
+    XrModel m{};
+    int r = xr_model(e, m);
+    if (r) return r;
+    XrKV kv{e->xr_kq.data(), e->xr_ks.data(), e->xr_vq.data(), e->xr_vs.data(), 0, 0};
+    XrSeq sq{e->tokens, 0, e->st};
+    for (int done = 0; done < n_rows;) {
+        const int n = (n_rows - done < e->xr_rows) ? n_rows - done : e->xr_rows;
+        const bool last = done + n == n_rows;
+        r = xr_prefill_pass(e->xr, m, kv, sq, 0, p0 + done, n, n_ctx, with_head && last, eos_id, e->logits);
+        if (r) return r;
+        done += n;
+    }
+    return GTB_OK;
+}
+
+int set_pos(gtb_engine* e, int pos);
+
+// rows to run: `n_body` rows without lm_head, then `n_head` rows with lm_head + argmax.  p0 >= 0: the position of the first
+// row and the call's n_ctx are known on the host, so runs of rows can go through the exact multi-row kernels.
+int run_rows(gtb_engine* e, int n_body, int n_head, int eos_id, int p0 = -1, int n_ctx = 0) {
     cudaStream_t st = ctx().stream;
     if (n_body + n_head <= 0) return GTB_OK;
+    if (p0 >= 0 && xr_ok(e) && n_body + (n_head > 0 ? 1 : 0) >= e->xr_min_rows) {
+        // the prompt rows (and the first sampling row) side by side, bit-identical to the row-at-a-time kernels
+        const int nx = n_body + (n_head > 0 ? 1 : 0);
+        int r = run_rows_xr(e, p0, nx, n_ctx, n_head > 0, eos_id);
+        if (r) return r;
+        if (n_head == 0) return set_pos(e, p0 + n_body);       // no sampling row: only the position moves
+        n_body = 0; n_head -= 1;
+        if (n_head == 0) return GTB_OK;
+    }
     if (mega_ok(e)) return run_rows_mega(e, n_body, n_head, eos_id);
     if (fast_mega_ok(e)) return run_rows_fast_mega(e, n_body, n_head, eos_id);
     if (e->use_graph && !e->capture) {
@@ -922,6 +993,12 @@ int run_rows(gtb_engine* e, int n_body, int n_head, int eos_id) {
         for (int i = 0; i < n_body; i++) { int r = enqueue_row_dt(e, false, -1); if (r) return r; }
         for (int i = 0; i < n_head; i++) { int r = enqueue_row_dt(e, true, eos_id); if (r) return r; }
     }
+    return GTB_OK;
+}
+
+int set_pos(gtb_engine* e, int pos) {
+    k_set_pos<<<1, 1, 0, ctx().stream>>>(e->st, pos);
+    GTB_LAUNCHED();
     return GTB_OK;
 }
 
@@ -969,7 +1046,15 @@ int gtb_engine_create(gtb_engine_t* out, const gtb_model_config* cfg) {
     e->grid = ctx().sm_count;
     e->L.resize(cfg->n_layers);
     const int E = cfg->n_embd, F = cfg->n_ffn, KV = e->kv_dim, MC = cfg->max_ctx;
-    auto dalloc = [&](void** p, size_t n) -> int { GTB_CUDA(cudaMalloc(p, n)); GTB_CUDA(cudaMemsetAsync(*p, 0, n, ctx().stream)); ctx().mem += (int64_t)n; return GTB_OK; };
+    int first_err = 0;
+    auto dalloc = [&](void** p, size_t n) -> int {
+        if (first_err) return first_err;          // after the first failure nothing else is attempted
+        cudaError_t ce = cudaMalloc(p, n);
+        if (ce == cudaSuccess) ce = cudaMemsetAsync(*p, 0, n, ctx().stream);
+        if (ce != cudaSuccess) { first_err = fail(GTB_ERR_CUDA, "engine buffers: %s", cudaGetErrorString(ce)); return first_err; }
+        ctx().mem += (int64_t)n;
+        return GTB_OK;
+    };
     int r = 0;
     for (auto& l : e->L) {
         const size_t code_bytes = (size_t)MC * KV * (e->adtype == GTB_F16 ? 2 : 1);
@@ -1008,7 +1093,7 @@ int gtb_engine_create(gtb_engine_t* out, const gtb_model_config* cfg) {
     r |= dalloc((void**)&e->x_arg, (size_t)2 * 1024 * 8); r |= dalloc((void**)&e->dbg, 64); r |= dalloc((void**)&e->epoch, 16);
     r |= dalloc((void**)&e->cnt, (size_t)CNT_TOTAL * CNT_STRIDE * 4);
     r |= dalloc((void**)&e->d_prof, (size_t)PROF_SLOTS * 8); r |= dalloc((void**)&e->d_layers, (size_t)cfg->n_layers * sizeof(MegaLayer));
-    if (r) { return r; }
+    if (r || first_err) { gtb_engine_destroy(e); return first_err ? first_err : GTB_ERR_CUDA; }
     {   // RoPE table with the reference's own expressions and libm (gten/ops.h:728-746; SURVEY §7 hard part 4)
         std::vector<float> cs((size_t)MC * 32), sn((size_t)MC * 32);
         const float d = 64.0f;
@@ -1020,8 +1105,11 @@ int gtb_engine_create(gtb_engine_t* out, const gtb_model_config* cfg) {
                 sn[(size_t)p * 32 + j] = sinf(m_theta_i);
             }
         }
-        GTB_CUDA(cudaMemcpy(e->rope_cos, cs.data(), cs.size() * 4, cudaMemcpyHostToDevice));
-        GTB_CUDA(cudaMemcpy(e->rope_sin, sn.data(), sn.size() * 4, cudaMemcpyHostToDevice));
+        // on the library stream, i.e. AFTER the zero-fill of dalloc: a default-stream copy would overtake a memset that is still
+        // queued behind other engines' work and the table would end up zeroed
+        GTB_CUDA(cudaMemcpyAsync(e->rope_cos, cs.data(), cs.size() * 4, cudaMemcpyHostToDevice, ctx().stream));
+        GTB_CUDA(cudaMemcpyAsync(e->rope_sin, sn.data(), sn.size() * 4, cudaMemcpyHostToDevice, ctx().stream));
+        GTB_CUDA(cudaStreamSynchronize(ctx().stream));          // cs / sn are locals
     }
     GTB_CUDA(cudaStreamSynchronize(ctx().stream));
     *out = e;
@@ -1045,6 +1133,7 @@ int gtb_engine_destroy(gtb_engine_t e) {
                     e->x_down, e->x_arg, e->dbg, e->epoch, e->cnt, e->d_prof, e->d_layers};
     for (void* b : bufs) cudaFree(b);
     if (e->pf) pf_destroy(e->pf);
+    if (e->xr) xr_destroy(e->xr);
     cudaFree(e->pf_cap);
     cudaFree(e->fd_parts); cudaFree(e->fd_cnt); cudaFree(e->fd_argv); cudaFree(e->fd_argi);
     cudaFree(e->d_fd_gemv); cudaFree(e->d_fd_attn); cudaFree(e->fd_bar);
@@ -1067,7 +1156,8 @@ int gtb_engine_set_weight(gtb_engine_t e, int layer, int tensor_id, const void* 
     GTB_ARG(!per_layer || (layer >= 0 && layer < e->cfg.n_layers));
     if (dt == GTB_F16 && rows == 1) {
         uint16_t* dst = (tensor_id == GTB_T_FINAL_NORM) ? e->final_norm : (tensor_id == GTB_T_ATTN_NORM) ? e->L[layer].attn_norm : e->L[layer].ffn_norm;
-        GTB_CUDA(cudaMemcpy(dst, h_payload, nbytes, cudaMemcpyHostToDevice));
+        GTB_CUDA(cudaMemcpyAsync(dst, h_payload, nbytes, cudaMemcpyHostToDevice, ctx().stream));     // stream-ordered with the kernels that read it
+        GTB_CUDA(cudaStreamSynchronize(ctx().stream));
         return GTB_OK;
     }
     gtb_weight_t* slot = nullptr;
@@ -1167,7 +1257,7 @@ int gtb_engine_logits(gtb_engine_t e, const int32_t* h_tokens, int n_tokens, int
     GTB_CUDA(cudaMemcpyAsync(e->tokens + start_pos, h_tokens + start_pos, (size_t)(n_tokens - start_pos) * 4, cudaMemcpyHostToDevice, ctx().stream));
     r = set_state(e, start_pos, n_tokens);
     if (r) return r;
-    r = run_rows(e, n_tokens - start_pos - 1, 1, -1);
+    r = run_rows(e, n_tokens - start_pos - 1, 1, -1, start_pos, n_tokens);
     if (r) return r;
     e->host_pos = n_tokens;
     if (h_logits) {
@@ -1186,7 +1276,7 @@ int gtb_engine_prefill(gtb_engine_t e, const int32_t* h_tokens, int n_tokens) {
     r = set_state(e, 0, n_tokens);
     if (r) return r;
     // the last prompt row also produces logits and the first generated token (greedy_sample's i == 0 step)
-    r = run_rows(e, n_tokens - 1, 1, -1);
+    r = run_rows(e, n_tokens - 1, 1, -1, 0, n_tokens);
     if (r) return r;
     e->host_pos = n_tokens;
     return GTB_OK;
@@ -1306,7 +1396,9 @@ int gtb_engine_decode(gtb_engine_t e, int n_steps) {
     GTB_CHECK_INIT();
     GTB_ARG(e && n_steps >= 0);
     if (e->host_pos + n_steps > e->cfg.max_ctx) return fail(GTB_ERR_ARG, "decode past max_ctx (%d + %d > %d)", e->host_pos, n_steps, e->cfg.max_ctx);
-    int r = run_rows(e, 0, n_steps, -1);
+    int r = check_loaded(e);
+    if (r) return r;
+    r = run_rows(e, 0, n_steps, -1);
     if (r) return r;
     e->host_pos += n_steps;
     return GTB_OK;
@@ -1324,7 +1416,7 @@ int gtb_engine_generate(gtb_engine_t e, int32_t* h_tokens, int n_prompt, int n_n
     int produced = 1;
     if (mega_ok(e)) {
         // prefill rows, the first token and every further greedy step in ONE launch; an EOS ends the loop on the device
-        r = run_rows(e, n_prompt - 1, n_new, eos_id);
+        r = run_rows(e, n_prompt - 1, n_new, eos_id, 0, n_prompt);
         if (r) return r;
         DevState s;
         GTB_CUDA(cudaMemcpyAsync(&s, e->st, sizeof s, cudaMemcpyDeviceToHost, ctx().stream));
@@ -1336,7 +1428,7 @@ int gtb_engine_generate(gtb_engine_t e, int32_t* h_tokens, int n_prompt, int n_n
         if (n_generated) *n_generated = produced;
         return GTB_OK;
     }
-    r = run_rows(e, n_prompt - 1, 1, eos_id);
+    r = run_rows(e, n_prompt - 1, 1, eos_id, 0, n_prompt);
     if (r) return r;
     if (eos_id < 0) {
         r = run_rows(e, 0, n_new - 1, eos_id);
@@ -1365,13 +1457,52 @@ int gtb_engine_generate(gtb_engine_t e, int32_t* h_tokens, int n_prompt, int n_n
 }
 
 // ---- batched decode: n sequences advance together, one weight read per step for all of them
+static bool batch_is_exact(const gtb_engine* e) { return e->batch_exact && xr_ok(e); }
+
 int gtb_engine_batch_create(gtb_engine_t e, int n_seq) {
     GTB_CHECK_INIT();
-    GTB_ARG(e && n_seq >= 0 && n_seq <= FDB_MAX);
+    GTB_ARG(e && n_seq >= 0);
     if (e->cfg.wdtype == GTB_F16) return fail(GTB_ERR_STATE, "batched decode is built for Q8-activation models (Q8, Q4 weights)");
-    if (e->cfg.n_embd > 2048 || e->cfg.n_ffn > 6144) return fail(GTB_ERR_STATE, "batched decode: n_embd <= 2048 and n_ffn <= 6144");
-    if (e->gsz > FD_NW) return fail(GTB_ERR_STATE, "batched decode: at most %d query heads per KV group", FD_NW);
+    if (batch_is_exact(e)) {
+        if (n_seq > XR_MAX_ROWS) return fail(GTB_ERR_ARG, "batched decode: at most %d sequences", XR_MAX_ROWS);
+    } else {
+        GTB_ARG(n_seq <= FDB_MAX);
+        if (e->cfg.n_embd > 2048 || e->cfg.n_ffn > 6144) return fail(GTB_ERR_STATE, "batched decode: n_embd <= 2048 and n_ffn <= 6144");
+        if (e->gsz > FD_NW) return fail(GTB_ERR_STATE, "batched decode: at most %d query heads per KV group", FD_NW);
+    }
     return batch_alloc(e, n_seq);
+}
+
+// Exact prefill of `n_tokens` prompt ids straight into slot `seq` (multi-row kernels, bit-identical to gtb_engine_prefill
+// followed by gtb_engine_batch_adopt): K/V land in the slot's cache, the first greedy token is appended.
+int gtb_engine_batch_prefill(gtb_engine_t e, int seq, const int32_t* h_tokens, int n_tokens) {
+    GTB_CHECK_INIT();
+    GTB_ARG(e && h_tokens && seq >= 0 && seq < e->bb.n && n_tokens > 0 && n_tokens < e->cfg.max_ctx);
+    int r = check_loaded(e);
+    if (r) return r;
+    if (!xr_ok(e)) return fail(GTB_ERR_STATE, "gtb_engine_batch_prefill needs the multi-row path (Q8/Q4 model, option xrows on)");
+    auto& b = e->bb;
+    const gtb_model_config& c = e->cfg;
+    const size_t KV = e->kv_dim, MC = c.max_ctx;
+    cudaStream_t st = ctx().stream;
+    GTB_CUDA(cudaMemcpyAsync(b.tokens + (size_t)seq * (MC + 2), h_tokens, (size_t)n_tokens * 4, cudaMemcpyHostToDevice, st));
+    DevState ns{0, n_tokens, 0, 0};
+    GTB_CUDA(cudaMemcpyAsync(b.st + seq, &ns, sizeof ns, cudaMemcpyHostToDevice, st));
+    GTB_CUDA(cudaStreamSynchronize(st));                  // `ns` is a stack object
+    XrModel m{};
+    r = xr_model(e, m);
+    if (r) return r;
+    XrKV kv{b.kq.data(), b.ks.data(), b.vq.data(), b.vs.data(), MC * KV, MC * (KV / 32)};
+    XrSeq sq{b.tokens, (int)MC + 2, b.st};
+    for (int done = 0; done < n_tokens;) {
+        const int n = (n_tokens - done < e->xr_rows) ? n_tokens - done : e->xr_rows;
+        const bool last = done + n == n_tokens;
+        r = xr_prefill_pass(e->xr, m, kv, sq, seq, done, n, n_tokens, last, -1, b.logits + (size_t)seq * c.n_vocab);
+        if (r) return r;
+        done += n;
+    }
+    b.host_pos[seq] = n_tokens;
+    return GTB_OK;
 }
 
 // slot `seq` <- the engine's current sequence (tokens, position, K/V cache), e.g. after gtb_engine_prefill[_fast]
@@ -1408,14 +1539,36 @@ int gtb_engine_batch_decode(gtb_engine_t e, int n_steps) {
     int r = check_loaded(e);
     if (r) return r;
     auto& b = e->bb;
-    for (int s = 0; s < b.n; s++)
+    int max_pos = 0;
+    for (int s = 0; s < b.n; s++) {
         if (b.host_pos[s] + n_steps > e->cfg.max_ctx) return fail(GTB_ERR_ARG, "batch decode past max_ctx (sequence %d: %d + %d > %d)", s, b.host_pos[s], n_steps, e->cfg.max_ctx);
+        if (b.host_pos[s] > max_pos) max_pos = b.host_pos[s];
+    }
+    const bool exact = batch_is_exact(e);
+    if (!exact && b.n > FDB_MAX) return fail(GTB_ERR_STATE, "the order-free batched decode takes at most %d sequences", FDB_MAX);
     cudaStream_t st = ctx().stream;
+    // exact mode: rows of all slots through the multi-row kernels (gtb_xrows.cu); the attention score buffer is sized for the
+    // longest context the call reaches, in steps of 256 positions
+    XrModel m{};
+    int t_cap = 0;
+    if (exact) {
+        r = xr_model(e, m);
+        if (r) return r;
+        t_cap = ((max_pos + n_steps + 255) / 256) * 256 + 32;
+    }
+    const size_t KV = e->kv_dim, MC = e->cfg.max_ctx;
+    XrKV kv{b.kq.data(), b.ks.data(), b.vq.data(), b.vs.data(), MC * KV, MC * (KV / 32)};
+    XrSeq sq{b.tokens, (int)MC + 2, b.st};
+    auto enqueue = [&]() -> int {
+        if (exact) return xr_decode_pass(e->xr, m, kv, sq, b.n, t_cap, -1, b.logits);
+        return (e->cfg.wdtype == GTB_Q8) ? enqueue_batch_row<DT_Q8>(e) : enqueue_batch_row<DT_Q4>(e);
+    };
     if (e->use_graph) {
+        if (b.graph && (b.graph_exact != exact || (exact && b.graph_tcap < t_cap))) { cudaGraphExecDestroy(b.graph); b.graph = nullptr; }
         if (!b.graph) {
             const int64_t before = ctx().launches;
             GTB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            r = (e->cfg.wdtype == GTB_Q8) ? enqueue_batch_row<DT_Q8>(e) : enqueue_batch_row<DT_Q4>(e);
+            r = enqueue();
             cudaGraph_t g = nullptr;
             cudaError_t ce = cudaStreamEndCapture(st, &g);
             b.graph_launches = (int)(ctx().launches - before);
@@ -1425,11 +1578,12 @@ int gtb_engine_batch_decode(gtb_engine_t e, int n_steps) {
             ce = cudaGraphInstantiate(&b.graph, g, 0);
             cudaGraphDestroy(g);
             if (ce != cudaSuccess) return fail(GTB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+            b.graph_exact = exact; b.graph_tcap = t_cap;
         }
         for (int i = 0; i < n_steps; i++) { GTB_CUDA(cudaGraphLaunch(b.graph, st)); ctx().launches += b.graph_launches; }
     } else {
         for (int i = 0; i < n_steps; i++) {
-            r = (e->cfg.wdtype == GTB_Q8) ? enqueue_batch_row<DT_Q8>(e) : enqueue_batch_row<DT_Q4>(e);
+            r = enqueue();
             if (r) return r;
         }
     }
@@ -1545,6 +1699,10 @@ int gtb_engine_set_option(gtb_engine_t e, const char* name, int value) {
     if (!strcmp(name, "pf_2cta")) { e->pf_2cta = value != 0; return GTB_OK; }
     if (!strcmp(name, "pf_pdl")) { e->pf_pdl = value != 0; return GTB_OK; }
     if (!strcmp(name, "pf_attn2")) { e->pf_attn2 = value != 0; return GTB_OK; }
+    if (!strcmp(name, "xrows")) { e->use_xr = value != 0; return GTB_OK; }
+    if (!strcmp(name, "xr_min_rows")) { GTB_ARG(value >= 1); e->xr_min_rows = value; return GTB_OK; }
+    if (!strcmp(name, "xr_rows")) { GTB_ARG(value >= 1 && value <= XR_MAX_ROWS); e->xr_rows = value; return GTB_OK; }
+    if (!strcmp(name, "batch_exact")) { e->batch_exact = value != 0; drop_graphs(e); return GTB_OK; }
     return fail(GTB_ERR_ARG, "unknown option %s", name);
 }
 

@@ -34,6 +34,7 @@ int ensure_init();
     do {                                      \
         int _r = gtb::ensure_init();          \
         if (_r) return _r;                    \
+        cudaSetDevice(gtb::ctx().device);     /* the current device is per host thread */ \
     } while (0)
 #define GTB_ARG(cond)                                                                                \
     do {                                                                                             \

@@ -1115,7 +1115,7 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
     int pos = P.st->pos;
     const int nctx_min = P.st->nctx_min;
     const int n_rows = P.n_body + P.n_head;
-    int n_gen = 0, stop = 0, next_tok = -1;
+    int n_gen = 0, stop = P.st->stop, next_tok = -1;      // an EOS sampled by the multi-row prefill's last row stops this launch too
     __syncthreads();
     WRegs<WT> w;
     PhaseDesc pd = phase_desc(P, 0);
