@@ -8,15 +8,18 @@ Default workload = BASELINE.json configs[2], the configuration north_star's targ
 TinyLlama-1.1B Q4, batch 1, greedy, context ending at the full 2048-token KV cache (prompt = 2048 - K - W
 synthetic ids, then W untimed + K timed decode steps).  Random-init weights in gten format (seeded, synthetic).
 
-value   : tokens/s with everything resident in HBM: K CUDA-graph replays back to back, device-side argmax,
-          timed with CUDA events on the library stream (max over ranks).
+value   : tokens/s with everything resident in HBM: ONE persistent cooperative launch (k_mega) runs the K steps, device-side
+          argmax, timed with CUDA events on the library stream (max over ranks).
 e2e     : the same K steps through the reference-facing call with HOST buffers, exactly the protocol of
           greedy_sample (tinyllama.cpp:402-434): gtb_engine_logits(tokens, n, n-1) -> 128 KB of fp32 logits back
           to the host -> host argmax -> append; H2D/D2H inside the timed region.
 N > 1   : independent replicas (one process per GPU, disjoint sequences, no collective on the data path);
           torch.distributed is used only for the start barrier and the max-over-ranks reduction.
+seq64   : (Q4 workload, every N) BASELINE.json configs[4] in the same line: 64 sequences, sequence s on GPU s mod N, each GPU
+          serves its share TOGETHER through the order-exact batched path (gtb_engine_batch_*: bit-identical tokens).
 --impl reference : the reference's own CPU implementation (oracle/_ref, the unmodified sources built with
-          -O3 -fopenmp -mavx -mf16c; the plain-C port if that library is absent) on all host threads.
+          -O3 -fopenmp -mavx -mf16c; the plain-C port if that library is absent) on all host threads, on the SAME
+          configuration: the same prompt is prefilled by the reference and the same sequence positions are timed.
 """
 from __future__ import annotations
 
@@ -56,14 +59,31 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def measured_traffic(workload: str, steps: int):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the kernel from the committed `ncu --set full` capture, scaled to the
-    K steps one launch of this run processes (profiles/roofline_traffic.json: bytes per step), or None."""
+def traffic_profile(workload: str):
+    """The DRAM traffic of the kernel is NOT measured in this run (that needs ncu): `roofline.traffic` is null and this object
+    points at the committed `ncu --set full` capture (profiles/roofline_traffic.json: bytes per step, one code state, one t)."""
     p = ROOT / "profiles" / "roofline_traffic.json"
     if not p.exists():
         return None
-    d = json.loads(p.read_text()).get(workload)
-    return None if d is None else d["dram_bytes_per_step"] * steps
+    j = json.loads(p.read_text())
+    d = j.get(workload)
+    if d is None:
+        return None
+    return {"dram_bytes_per_step": d["dram_bytes_per_step"], "static": True, "source": d.get("_source", j.get("_source"))}
+
+
+def use_all_host_threads():
+    """The reference parallelises one loop with OpenMP (ops.h:635-637).  torchrun exports OMP_NUM_THREADS=1, so the variable is
+    SET (not defaulted) before libgomp loads, and the ICV is set again through omp_set_num_threads in case it already has."""
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    try:
+        import ctypes
+        g = ctypes.CDLL("libgomp.so.1")
+        g.omp_set_num_threads(cores)
+        return int(g.omp_get_max_threads())
+    except OSError:
+        return cores
 
 
 class ClockSampler:
@@ -102,47 +122,70 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
+def workload_shape(workload: str, K: int, Wm: int):
+    """(n_prompt, max_ctx) of a decode workload: Q4 ends at the full 2048-token KV cache (configs[2]); Q8 / FP16 follow a
+    128-token prompt (configs[1], [0])."""
+    if workload == "q4":
+        max_ctx = 2048
+        n_prompt = max_ctx + 1 - K - Wm          # the last timed row is position 2047 (t = 2048)
+        if n_prompt < 16:
+            n_prompt, max_ctx = 16, 16 + K + Wm - 1
+    else:
+        n_prompt = 128
+        max_ctx = n_prompt + K + Wm - 1
+    return n_prompt, max_ctx
+
+
 def run_reference(args, wdt, desc):
-    """The reference's CPU implementation on the host cores (rank 0 only)."""
+    """The reference's CPU implementation on the host cores (rank 0 only), SAME configuration as the B200 arm: the same
+    synthetic prompt is prefilled by the reference itself (tinyllama.cpp:45-61 with start_pos 0), then W warm-up and K timed
+    greedy steps at the same sequence positions.  For configs[2] that is a ~2000-token CPU prefill: minutes, outside the timed
+    region like the B200 arm's own prefill."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    threads = use_all_host_threads()
     import oracle
     lib = oracle.best()
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     cfg = W.TINYLLAMA
-    n_prompt = 32
-    max_ctx = n_prompt + args.warmup + args.steps + 2
-    m = lib.model(cfg, max_ctx, wdt).load(W.synth_weights(cfg, wdt, seed=1))
+    K, Wm = args.steps, args.warmup
+    n_prompt, max_ctx = workload_shape(args.workload, K, Wm)
+    # the reference's multi-row attention needs ceil(n/32)*34 <= max_ctx for Q8 activations, 2n <= max_ctx for FP16 (SURVEY App. B1)
+    ref_ctx = max(max_ctx, 2 * n_prompt + 64 if wdt == W.F16 else ((n_prompt + 31) // 32) * 34 + 64)
+    t_setup = time.perf_counter()
+    m = lib.model(cfg, ref_ctx, wdt).load(W.synth_weights(cfg, wdt, seed=1))
     toks = list(W.synth_prompt(7, n_prompt, cfg.n_vocab))
+    t0 = time.perf_counter()
     lg = m.logits(np.array(toks, np.int32), 0)
+    prefill_s = time.perf_counter() - t0
     toks.append(int(np.argmax(lg)))
-    for _ in range(args.warmup):
+    for _ in range(Wm - 1):                       # the prefill produced the first new token, as on the B200 arm
         lg = m.logits(np.array(toks, np.int32), len(toks) - 1)
         toks.append(int(np.argmax(lg)))
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(K):
         lg = m.logits(np.array(toks, np.int32), len(toks) - 1)
         toks.append(int(np.argmax(lg)))
     dt = time.perf_counter() - t0
-    v = args.steps / dt
-    sample = f"{args.steps} decode steps after a {n_prompt}-token prompt (t = {n_prompt + args.warmup + 1}..{len(toks) - 1}); short context: the reference's attention is single-threaded"
+    v = K / dt
+    sample = (f"{K} decode steps at t = {n_prompt + Wm}..{n_prompt + Wm + K - 1} after the reference's own prefill of the same {n_prompt}-token prompt "
+              f"({prefill_s:.1f} s = {n_prompt / prefill_s:.1f} tok/s, untimed); same weights, same positions as the B200 arm")
     print(json.dumps({
         "impl": "reference", "metric": "decode_tokens_per_s", "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "steps": K, "warmup": Wm, "ms_per_step": 1e3 * dt / K, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_STR[wdt], "data": "synthetic",
-        "config": {"workload": desc, "sample": sample},
-        "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": lib.kind, "sample": sample},
+        "config": {"workload": desc, "n_prompt": n_prompt, "max_ctx": max_ctx, "seq_len_timed": [n_prompt + Wm, n_prompt + Wm + K - 1],
+                   "batch": 1, "sample": sample, "reference_prefill_s": prefill_s, "omp_threads": threads,
+                   "setup_s": round(time.perf_counter() - t_setup, 1)},
+        "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": threads, "kind": lib.kind, "sample": sample},
         "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
 
 def cpu_baseline(wdt, seconds_budget=20.0):
     """Reference CPU path on a bounded sample (rank 0, N=1 only)."""
+    cores = use_all_host_threads()
     import oracle
     lib = oracle.best()
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     cfg = W.TINYLLAMA
     n_prompt, n_steps = 16, 48
     m = lib.model(cfg, n_prompt + n_steps + 4, wdt).load(W.synth_weights(cfg, wdt, seed=1))
@@ -160,7 +203,9 @@ def cpu_baseline(wdt, seconds_budget=20.0):
     dt = time.perf_counter() - t0
     m.close()
     return {"value": done / dt, "unit": "tokens/s", "cores": cores, "kind": lib.kind,
-            "sample": f"{done} decode steps after a {n_prompt}-token prompt (t = {n_prompt + 1}..{n_prompt + done}), same synthetic weights"}
+            "same_config": False,
+            "sample": f"{done} decode steps after a {n_prompt}-token prompt (t = {n_prompt + 1}..{n_prompt + done}), same synthetic weights: a BOUNDED "
+                      "short-context sample (the reference's attention is single-threaded and O(t)); `--impl reference` times the same positions as the headline"}
 
 
 def prefill_flops(cfg, T):
@@ -208,6 +253,7 @@ def prefill_section(capi, torch, stream, iters=5, warmup=3, T=2048, cpu=True):
            "e2e": {"value": T / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": T * 4, "d2h_bytes_per_step": cfg.n_vocab * 4},
            "gpu_launches": int(launches), "argmax_last_row": int(np.argmax(lg))}
     if cpu:
+        cores = use_all_host_threads()
         import oracle
         lib = oracle.best()
         n = 24
@@ -216,7 +262,7 @@ def prefill_section(capi, torch, stream, iters=5, warmup=3, T=2048, cpu=True):
         m.logits(prompt[:n], 0)
         dt = time.perf_counter() - t0
         m.close()
-        out["cpu_baseline"] = {"value": n / dt, "unit": "tokens/s", "cores": os.cpu_count() or 1, "kind": lib.kind,
+        out["cpu_baseline"] = {"value": n / dt, "unit": "tokens/s", "cores": cores, "kind": lib.kind,
                                "sample": f"prefill of the first {n} prompt tokens (the reference's prefill is row-by-row GEMV, ops.h:632)"}
     return out
 
@@ -258,7 +304,7 @@ def fast_decode_section(eng, capi, torch, stream, cfg, wdt, prompt, n_prompt, Wm
            "parity": {"kind": "tolerance (summation order free; the reference's two own builds differ by the same amount, DESIGN.md 4.4/4.6)",
                       "logits_rel_l2_vs_exact_path_same_cache": rel, "same_top1": bool(int(np.argmax(fast)) == int(np.argmax(exact)))},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                        "traffic": measured_traffic(("q4" if wdt == W.Q4 else "q8") + "_fast_decode", K),
+                        "traffic": None, "traffic_profile": traffic_profile(("q4" if wdt == W.Q4 else "q8") + "_fast_decode"),
                         "peak_source": peak_src, "algorithmic_bytes_per_step": bytes_per_tok,
                         "kernel": "k_fd_gemv / k_fd_attn chain (achieved = bytes of K steps / time of K steps)"},
            "gpu_launches": int(launches)}
@@ -279,7 +325,9 @@ def fast_decode_section(eng, capi, torch, stream, cfg, wdt, prompt, n_prompt, Wm
         capi.sync()
         out["e2e"] = {"value": K / (time.perf_counter() - t0), "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": cfg.n_vocab * 4}
     eng.set_option("fast_decode", 0)
-    # 8 and 16 sequences of the same length advancing together (gtb_engine_batch_*): every weight read is shared
+    # 8 and 16 sequences of the same length advancing together through the ORDER-FREE batch kernels (option batch_exact = 0; the
+    # default batch path is the exact one, see `seq64` / `exact_batch`): every weight read is shared
+    eng.set_option("batch_exact", 0)
     for B in (8, 16):
         eng.batch_create(B)
         for s in range(B):
@@ -302,7 +350,101 @@ def fast_decode_section(eng, capi, torch, stream, cfg, wdt, prompt, n_prompt, Wm
             "gpu_launches": int(capi.launch_count() - l0),
             "parity": "bit-identical to the same sequences decoded one at a time with fast_decode (tests/test_fastdec_gpu.py)"}
     eng.batch_create(0)
+    eng.set_option("batch_exact", 1)
     return out
+
+
+def exact_batch_section(eng, capi, torch, stream, cfg, wdt, prompt, n_prompt, Wm, K):
+    """B sequences at the headline's context (t ~ 2030 for configs[2]) advancing together through the ORDER-EXACT multi-row
+    kernels (gtb_xrows.cu): every weight block is loaded once per step for all of them and every sequence's tokens are
+    bit-identical to the headline's (checked here: all slots hold the same sequence, so they must reproduce its tokens)."""
+    out = {}
+    eng.prefill(prompt)
+    eng.decode(Wm - 1 + K)
+    want = eng.read_tokens(0, n_prompt + Wm + K)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for B in (8, 64):
+        eng.batch_create(B)
+        eng.prefill(prompt)
+        for s in range(B):
+            eng.batch_adopt(s)
+        eng.batch_decode(Wm - 1)
+        capi.sync()
+        torch.cuda.synchronize()
+        l0 = capi.launch_count()
+        ev0.record(stream)
+        eng.batch_decode(K)
+        ev1.record(stream)
+        capi.sync()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        same = all(np.array_equal(eng.batch_read_tokens(s, 0, n_prompt + Wm + K), want) for s in (0, B - 1))
+        t_mean = n_prompt + Wm + (K - 1) / 2.0
+        kvb = cfg.kv_bytes_per_pos(wdt) * int(round(t_mean))
+        bbytes = cfg.weight_bytes_per_token(wdt) + cfg.norm_bytes_per_token() + B * kvb
+        out[f"batch{B}"] = {"batch": B, "value": B * K / (ms * 1e-3), "unit": "tokens/s", "ms_per_step": ms / K,
+                            "tokens_identical_to_headline": bool(same), "algorithmic_bytes_per_step": bbytes,
+                            "achieved_gbs": bbytes * K / (ms * 1e-3) / 1e9, "gpu_launches": int(capi.launch_count() - l0)}
+    eng.batch_create(0)
+    out["path"] = ("gtb_engine_batch_decode, exact mode: k_xr_gemm (dp4a lane sums + ordered fp32 chains, R rows per weight load), "
+                   "k_xr_attn, k_xr_norm; bit-identical to the reference (tests/test_xrows_gpu.py)")
+    return out
+
+
+def seq64_section(eng, capi, torch, stream, env, R, cfg, n_new=64, n_seq=64, n_prompt=128):
+    """BASELINE.json configs[4]: 64 independent Q4 sequences (128-token prompt + n_new tokens), sequence s on GPU s mod N; each
+    GPU serves its share TOGETHER: exact multi-row prefill of every prompt into its slot, then n_new - 1 steps of the exact
+    batched decode (gtb_engine_batch_*).  Tokens are bit-identical to the reference's (tests/test_xrows_gpu.py checks 4 of these
+    sequences at full size against committed golden tokens).  Strong scaling: the job is fixed, the GPUs share it."""
+    rank, world = env.rank, env.world
+    mine = R.sequences_of_rank(n_seq, rank, world)
+    B = len(mine)
+    prompts = [W.synth_prompt(100 + sidx, n_prompt, cfg.n_vocab) for sidx in mine]
+    eng.batch_create(B)
+    eng.batch_prefill(0, prompts[0])
+    for s in range(1, B):
+        eng.batch_prefill(s, prompts[s][:8])
+    eng.batch_decode(2)                               # graph capture + warm-up
+    capi.sync()
+    torch.cuda.synchronize()
+    R.barrier(env)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    l0 = capi.launch_count()
+    ev[0].record(stream)
+    for s, p in enumerate(prompts):
+        eng.batch_prefill(s, p)
+    ev[1].record(stream)
+    eng.batch_decode(n_new - 1)
+    ev[2].record(stream)
+    capi.sync()
+    torch.cuda.synchronize()
+    pf_ms, dec_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+    launches = capi.launch_count() - l0
+    # end to end: prompts from host memory, every generated token back on the host, wall clock
+    R.barrier(env)
+    t0 = time.perf_counter()
+    for s, p in enumerate(prompts):
+        eng.batch_prefill(s, p)
+    eng.batch_decode(n_new - 1)
+    toks = [eng.batch_read_tokens(s, n_prompt, n_new) for s in range(B)]
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    checksum = 0
+    for t in toks:
+        for v in t.tolist():
+            checksum = (checksum * 31 + int(v)) % (1 << 31)
+    eng.batch_create(0)
+    dec_max, n_dec, (pf_max, all_max, wall_max), (launches,) = R.aggregate(
+        env, dec_ms, B * (n_new - 1), extra_max=[pf_ms, pf_ms + dec_ms, wall_ms], extra_sum=[launches], device=f"cuda:{env.local_rank}")
+    n_all = n_seq * n_new
+    return {"metric": "decode_tokens_per_s", "value": R.throughput(n_dec, dec_max), "unit": "tokens/s", "scaling": "strong",
+            "n_gpus": world, "sequences": n_seq, "sequences_per_gpu": B, "n_prompt": n_prompt, "n_new": n_new,
+            "ms_per_step": dec_max / (n_new - 1), "prefill_ms": pf_max, "prefill_tokens_per_s": n_seq * n_prompt / (pf_max * 1e-3),
+            "value_incl_prefill": n_all / (all_max * 1e-3),
+            "e2e": {"value": n_all / (wall_max * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": 4.0 * n_prompt / n_new,
+                    "d2h_bytes_per_step": 4.0, "note": "wall clock of the whole job on the slowest replica: prompt upload, exact prefill, decode, tokens read back"},
+            "workload": "TinyLlama-1.1B Q4 decode, 64 independent sequences over the GPUs (BASELINE.json configs[4])",
+            "path": "exact multi-row prefill + exact batched decode (gtb_xrows.cu): tokens bit-identical to the reference",
+            "gpu_launches": int(launches), "token_checksum_rank0": checksum}
 
 
 def cfg_max_ctx(eng):
@@ -317,10 +459,9 @@ def run_prefill(args):
     cfg = W.TINYLLAMA
     T = 2048
     if args.impl == "reference":
+        cores = use_all_host_threads()
         import oracle
         lib = oracle.best()
-        cores = os.cpu_count() or 1
-        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
         n = 32
         m = lib.model(cfg, 2 * n + 64, W.Q8).load(W.synth_weights(cfg, W.Q8, seed=1))
         prompt = W.synth_prompt(7, T, cfg.n_vocab)
@@ -357,10 +498,9 @@ def run_prefill(args):
 
 
 def run_seq64(args):
-    """`--workload q4_seq64` = BASELINE.json configs[4]: 64 independent sequences (128-token prompt + K new tokens each, K = --steps,
-    at most 256) served by N replicas, sequence s on GPU s mod N, back to back at batch 1 (the reference has no batch dimension,
-    SURVEY.md 8e).  value = generated tokens of all sequences / the slowest replica's summed decode time (CUDA events around each
-    sequence's device-resident decode; the exact prefill of the prompt is outside the timed region)."""
+    """`--workload q4_seq64` = BASELINE.json configs[4] as the whole line: 64 independent sequences (128-token prompt + K new tokens
+    each, K = --steps, at most 256) over N GPUs, sequence s on GPU s mod N; every GPU serves its share together through the
+    order-exact batched path (seq64_section).  `one_at_a_time` repeats the job the round-1 way (batch 1 per GPU, k_mega)."""
     import torch
     from tinyllama_cpp_b200 import capi, replicas as R
     env = R.ReplicaEnv.from_env()
@@ -375,17 +515,18 @@ def run_seq64(args):
     n_new = max(2, min(args.steps, 256))
     eng = capi.Engine(cfg, n_prompt + n_new, W.Q4).load(W.synth_weights(cfg, W.Q4, seed=1))
     stream = torch.cuda.ExternalStream(capi.stream_handle(), device=torch.device("cuda", local))
-    mine = R.sequences_of_rank(n_seq, rank, world)
-    eng.prefill(W.synth_prompt(1000, n_prompt, cfg.n_vocab))        # warm-up sequence (not counted)
-    eng.decode(max(args.warmup, 3))
-    capi.sync()
-    R.barrier(env)
-    ms_local, toks_local, checksum = 0.0, 0, 0
-    l0 = capi.launch_count()
-    t_wall = time.perf_counter()
     with ClockSampler(local) as clk:
+        sec = seq64_section(eng, capi, torch, stream, env, R, cfg, n_new=n_new, n_seq=n_seq, n_prompt=n_prompt)
+    one = None
+    if not args.no_fast:
+        mine = R.sequences_of_rank(n_seq, rank, world)
+        ms_local, toks_local = 0.0, 0
+        eng.prefill(W.synth_prompt(1000, n_prompt, cfg.n_vocab))
+        eng.decode(3)
+        capi.sync()
+        R.barrier(env)
         for sidx in mine:
-            eng.prefill(W.synth_prompt(100 + sidx, n_prompt, cfg.n_vocab))      # produces the first new token
+            eng.prefill(W.synth_prompt(100 + sidx, n_prompt, cfg.n_vocab))
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(stream)
             eng.decode(n_new - 1)
@@ -393,63 +534,27 @@ def run_seq64(args):
             capi.sync()
             ms_local += ev0.elapsed_time(ev1)
             toks_local += n_new - 1
-            checksum = (checksum * 31 + int(eng.read_tokens(n_prompt + n_new - 1, 1)[0])) % (1 << 31)
-    wall = time.perf_counter() - t_wall
-    launches = capi.launch_count() - l0
-    ms, units, (wall_max,), (launches,) = R.aggregate(env, ms_local, toks_local, extra_max=[wall], extra_sum=[launches], device=f"cuda:{local}")
-    # the same job through the batched order-free decode (gtb_engine_batch_*): this replica's sequences in groups
-    # of up to 16 that share every weight read; tolerance-level parity, reported next to the bit-exact number
-    BATCH = 16
-    bms_local, btoks_local, bl0 = 0.0, 0, capi.launch_count()
-    if not args.no_fast:
-        for g0 in range(0, len(mine), BATCH):
-            grp = mine[g0:g0 + BATCH]
-            eng.batch_create(len(grp))
-            for slot, sidx in enumerate(grp):
-                eng.prefill(W.synth_prompt(100 + sidx, n_prompt, cfg.n_vocab))
-                eng.batch_adopt(slot)
-            if g0 == 0:
-                eng.batch_decode(1)           # graph capture outside the timed region; re-adopt so that every sequence starts at n_prompt
-                for slot, sidx in enumerate(grp):
-                    eng.prefill(W.synth_prompt(100 + sidx, n_prompt, cfg.n_vocab))
-                    eng.batch_adopt(slot)
-            capi.sync()
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record(stream)
-            eng.batch_decode(n_new - 1)
-            ev1.record(stream)
-            capi.sync()
-            bms_local += ev0.elapsed_time(ev1)
-            btoks_local += len(grp) * (n_new - 1)
-            assert all(eng.batch_position(slot) == n_prompt + n_new - 1 for slot in range(len(grp)))
-        eng.batch_create(0)
-    blaunches = capi.launch_count() - bl0
-    bms, bunits, _, (blaunches,) = R.aggregate(env, bms_local, btoks_local, extra_max=[0.0], extra_sum=[blaunches], device=f"cuda:{local}")
+        ms1, units1, _, _ = R.aggregate(env, ms_local, toks_local, device=f"cuda:{local}")
+        one = {"value": R.throughput(units1, ms1), "unit": "tokens/s", "path": "k_mega, one sequence at a time per GPU (round 1's way)"}
     if rank == 0:
         hbm_peak, peak_src = measured_peaks()
+        B = sec["sequences_per_gpu"]
         t_mean = n_prompt + n_new / 2.0
-        bytes_per_tok = cfg.decode_bytes(W.Q4, int(round(t_mean)))
-        per_gpu_tok_s = (len(mine) * (n_new - 1)) / (ms_local * 1e-3) if ms_local else 0.0
-        achieved = bytes_per_tok * per_gpu_tok_s / 1e9
+        bytes_per_step = (cfg.weight_bytes_per_token(W.Q4) + cfg.norm_bytes_per_token() + B * cfg.kv_bytes_per_pos(W.Q4) * int(round(t_mean)))
+        achieved = bytes_per_step / (sec["ms_per_step"] * 1e-3) / 1e9
         print(json.dumps({
-            "metric": "decode_tokens_per_s", "value": R.throughput(units, ms), "unit": "tokens/s", "n_gpus": world, "steps": n_new - 1,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / max(1, len(mine) * (n_new - 1)), "higher_is_better": True, "scaling": "strong",
+            "metric": "decode_tokens_per_s", "value": sec["value"], "unit": "tokens/s", "n_gpus": world, "steps": n_new - 1,
+            "warmup": 3, "ms_per_step": sec["ms_per_step"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": DTYPE_STR[W.Q4], "data": "synthetic",
-            "config": {"workload": "TinyLlama-1.1B Q4 decode, 64 independent sequences as replicas (BASELINE.json configs[4]): 128-token prompt + "
-                                   f"{n_new} new tokens each, sequence s on GPU s mod N, batch 1 per GPU", "sequences": n_seq,
-                       "sequences_per_gpu": len(mine), "n_prompt": n_prompt, "n_new": n_new, "replicas": world,
+            "config": {"workload": sec["workload"] + f": 128-token prompt + {n_new} new tokens each, sequence s on GPU s mod N, every GPU's share decoded together (exact batched path)",
+                       "sequences": n_seq, "sequences_per_gpu": B, "n_prompt": n_prompt, "n_new": n_new, "replicas": world,
                        "l2": "inputs larger than L2: every step streams 582 MB of weights"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                         "peak_source": peak_src, "algorithmic_bytes_per_step": bytes_per_tok, "kernel": "k_mega<q4>, one launch per sequence"},
-            "e2e": {"value": units / wall_max if wall_max else None, "unit": "tokens/s", "h2d_bytes_per_step": 4 * n_prompt / (n_new - 1),
-                    "d2h_bytes_per_step": 4.0 / (n_new - 1), "note": "wall clock of the whole job on the slowest replica, prompt upload and exact prefill included"},
-            "batched": None if args.no_fast or not bms else {
-                "value": R.throughput(bunits, bms), "unit": "tokens/s", "batch_per_gpu": min(BATCH, len(mine)),
-                "ms_per_step": bms / max(1, -(-len(mine) // BATCH) * (n_new - 1)),
-                "path": "gtb_engine_batch_decode: order-free kernels, up to 16 sequences share every weight read; a sequence decoded in a batch "
-                        "gives the same bits as decoded alone with fast_decode (tests/test_fastdec_gpu.py); tolerance-level parity with the reference",
-                "gpu_launches": int(blaunches)},
-            "gpu_launches": int(launches), "clocks": clk.summary(), "token_checksum_rank0": checksum}), flush=True)
+                         "peak_source": peak_src, "algorithmic_bytes_per_step": bytes_per_step,
+                         "kernel": "k_xr_gemm chain of one batched step (weights once + every sequence's K/V); the step is ALU-bound (dp4a + ordered fp32 chains), not HBM-bound"},
+            "e2e": sec["e2e"], "prefill_ms": sec["prefill_ms"], "prefill_tokens_per_s": sec["prefill_tokens_per_s"],
+            "value_incl_prefill": sec["value_incl_prefill"], "one_at_a_time": one,
+            "gpu_launches": sec["gpu_launches"], "clocks": clk.summary(), "token_checksum_rank0": sec["token_checksum_rank0"]}), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
@@ -467,6 +572,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-prefill", action="store_true", help="skip the configs[3] prefill measurement appended to the N=1 line")
     ap.add_argument("--no-fast", action="store_true", help="skip the order-free decode measurement appended to the N=1 line")
+    ap.add_argument("--no-seq64", action="store_true", help="skip the configs[4] (64 sequences) measurement appended to the Q4 line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.workload == "prefill_q8":
@@ -488,14 +594,7 @@ def main():
     torch.cuda.set_device(local)
     cfg = W.TINYLLAMA
     K, Wm = args.steps, args.warmup
-    if args.workload == "q4":
-        max_ctx = 2048
-        n_prompt = max_ctx + 1 - K - Wm          # the last timed row is position 2047 (t = 2048)
-        if n_prompt < 16:
-            n_prompt, max_ctx = 16, 16 + K + Wm - 1
-    else:
-        n_prompt = 128
-        max_ctx = n_prompt + K + Wm - 1
+    n_prompt, max_ctx = workload_shape(args.workload, K, Wm)
     t_setup = time.time()
     eng = capi.Engine(cfg, max_ctx, wdt).load(W.synth_weights(cfg, wdt, seed=1))
     assert eng.uses_megakernel(), "bench must run the persistent-kernel path"
@@ -508,8 +607,16 @@ def main():
         torch.cuda.synchronize()
         R.barrier(env)
 
-    # ---- resident path: prefill (untimed, exact row-by-row path), W warm-up steps, K timed steps
+    # ---- resident path: exact prefill (outside the headline's timed region; timed on its own), W warm-up steps, K timed steps
+    eng.prefill(prompt[:70])
+    barrier()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record(stream)
     eng.prefill(prompt)
+    pe1.record(stream)
+    capi.sync()
+    torch.cuda.synchronize()
+    prefill_ms = pe0.elapsed_time(pe1)
     eng.decode(Wm - 1)            # prefill already produced the first new token
     barrier()
     l0 = capi.launch_count()
@@ -566,7 +673,7 @@ def main():
                        "weights": "random-init, seeded, gten format", "l2": "inputs larger than L2: every step streams "
                        f"{cfg.weight_bytes_per_token(wdt) / 1e6:.0f} MB of weights (L2 = 126 MB)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": measured_traffic(args.workload, K), "peak_source": peak_src,
+                         "traffic": None, "traffic_profile": traffic_profile(args.workload), "peak_source": peak_src,
                          "kernel": "k_mega<%s>: one persistent cooperative launch runs all K steps (achieved = bytes of K steps / launch time)" % args.workload,
                          "algorithmic_bytes_per_step": bytes_per_tok},
             "gpu_launches": launches, "clocks": clocks,
@@ -574,9 +681,21 @@ def main():
         if not args.no_e2e:
             out["e2e"] = {"value": units / (e2e_ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": 4,
                           "d2h_bytes_per_step": cfg.n_vocab * 4}
+        out["exact_prefill"] = {"tokens": n_prompt, "ms": prefill_ms, "tokens_per_s": n_prompt / (prefill_ms * 1e-3),
+                                "path": ("order-exact multi-row kernels (gtb_xrows.cu), 64 rows per pass: bit-identical to the reference's row loop" if wdt != W.F16
+                                         else "k_mega row loop (the multi-row kernels cover Q8-activation models)")}
         if world == 1 and not args.no_fast and wdt != W.F16:
             out["fast_decode"] = fast_decode_section(eng, capi, torch, stream, cfg, wdt, prompt, n_prompt, Wm, K, hbm_peak, peak_src,
                                                      e2e=not args.no_e2e)
+        if world == 1 and not args.no_fast and wdt != W.F16:
+            out["exact_batch"] = exact_batch_section(eng, capi, torch, stream, cfg, wdt, prompt, n_prompt, Wm, K)
+    # configs[4] at this N (every rank takes part: strong scaling over the replicas)
+    seq64 = None
+    if args.workload == "q4" and not args.no_seq64:
+        seq64 = seq64_section(eng, capi, torch, stream, env, R, cfg)
+    if rank == 0:
+        if seq64 is not None:
+            out["seq64"] = seq64
         if world == 1 and not args.no_prefill:
             eng.close()
             out["prefill"] = prefill_section(capi, torch, stream, cpu=not args.no_cpu_baseline)

@@ -175,6 +175,9 @@ int gtb_engine_weight_bytes(gtb_engine_t e, size_t* nbytes);
  * (gten/ops.h:765-767, 982-988) on n non-negative host terms; h_out[0] must equal the sequential sum bit for bit,
  * h_out[1..4] receive the SM cycles of four back-to-back evaluations (cold and warm instruction cache) */
 int gtb_selftest_exact_sum(const float* h_terms, int n, float* h_out);
+/* self-test: the device restatement of glibc 2.39 expf (gten/ops.h:692, 985 call it) on the float bit patterns
+ * [first_bits, first_bits + count), count <= 2^26; tests/test_expf_gpu.py walks all 2^32 inputs against the host libm */
+int gtb_selftest_expf(uint32_t first_bits, uint32_t count, float* h_out);
 
 #ifdef __cplusplus
 }

@@ -98,6 +98,8 @@ class CpuLib:
         sig("add", None, vp, vp, i, i, i, vp, i)
         sig("qkv_attn", None, vp, vp, vp, vp, vp, i, i, i, i, i, i, i)
         sig("expf", f, f)
+        if prefix == "orc_":
+            sig("expf_bits_range", None, C.c_uint32, C.c_uint32, vp)
         sig("rope_angles", None, i, i, vp, vp)
         sig("model_new", vp, i, i, i, i, i, i, i, i)
         sig("model_free", None, vp)
@@ -144,6 +146,12 @@ class CpuLib:
 
     def expf(self, x) -> np.float32:
         return np.float32(self._expf(float(np.float32(x))))
+
+    def expf_bits_range(self, first: int, count: int) -> np.ndarray:
+        """Host libm expf of the float bit patterns [first, first + count) (port library only: it is libm, not a restatement)."""
+        out = np.empty(count, np.float32)
+        self._expf_bits_range(first, count, _ptr(out))
+        return out
 
     def rope_angles(self, pos: int, d_head: int):
         c = np.zeros(d_head // 2, np.float32)

@@ -309,6 +309,15 @@ static void rope_row(uint8_t* x, int xdt, int n_embd, int d_head, int pos, float
 }
 
 float orc_expf(float x) { return expf(x); }
+/* host libm expf over the bit patterns [first, first + count): the yardstick of the device restatement (tests/test_expf_gpu.py) */
+void orc_expf_bits_range(uint32_t first, uint32_t count, float* out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)count; i++) {
+        union { uint32_t u; float f; } v;
+        v.u = first + (uint32_t)i;
+        out[i] = expf(v.f);
+    }
+}
 
 /* gten/ops.h:687-696 */
 static void silu_row(const uint8_t* x, int xdt, int n, uint8_t* out, float* buf) {

@@ -56,6 +56,7 @@ void orc_add(const void* a, const void* b, int xdt, int n_ctx, int n_embd, void*
 void orc_qkv_attn(const void* q, const void* k, const void* v, void* qk, void* out, int xdt,
                   int n_ctx, int n_heads, int n_kv_heads, int d_head, int max_ctx, int start_pos);
 float orc_expf(float x);
+void orc_expf_bits_range(uint32_t first, uint32_t count, float* out);
 void  orc_rope_angles(int pos, int d_head, float* cos_out, float* sin_out);
 
 /* model */

@@ -141,12 +141,13 @@ def _full_case(name):
     gt = gold["tokens"]
     first_bad = next((i for i in range(toks.size) if toks[i] != gt[i]), None)
     assert first_bad is None, f"{name}: greedy tokens diverge at index {first_bad} (step {first_bad - n_prompt}); margin there {gold['margin'][max(first_bad - n_prompt, 0)]}"
-    # logits of the kept steps, teacher forced
+    # logits of EVERY kept step, teacher forced on the golden tokens: the prefill call for step 0, then single rows on top of the
+    # cache the greedy run left behind (rows < n - 1 are those of the golden sequence, which the run reproduced)
     for step, glog in zip(gold["keep_steps"], gold["keep_logits"]):
-        n = n_prompt + int(step)
-        lg = e.logits(gt[:n], 0 if step == 0 else n - 1) if step == 0 else None
-        if lg is not None:
-            _eq(lg, glog, f"{name} logits step {step}")
+        step = int(step)
+        n = n_prompt + step
+        lg = e.logits(gt[:n], 0) if step == 0 else e.logits(gt[:n], n - 1)
+        _eq(lg, glog, f"{name} logits step {step}")
     e.close()
 
 

@@ -206,16 +206,16 @@ def test_attention(capi, checker, adt, n_ctx, max_ctx):
 
 
 @pytest.mark.parametrize("adt", [Q8, F16])
-def test_attention_long_context_decode_row(capi, adt):
-    """A single decode row at t = 2048 (full KV, BASELINE config 3) against the plain-C restatement."""
-    port = oracle.port()
+def test_attention_long_context_decode_row(capi, checker, adt):
+    """A single decode row at t = 2048 (full KV, BASELINE config 3) against the reference itself (`_ref` where its library
+    travelled).  max_ctx = 2176 keeps the Q8 score row of 64 blocks x 34 B inside its own stride."""
     rng = np.random.default_rng(2048)
-    H, G, D, n_ctx = 32, 4, 64, 2048
-    q = port.encode_rows(rand_rows(rng, n_ctx, H * D), adt)
-    k = port.encode_rows(rand_rows(rng, n_ctx, G * D), adt)
-    v = port.encode_rows(rand_rows(rng, n_ctx, G * D), adt)
-    got = capi.qkv_attn(q, k, v, adt, n_ctx, H, G, D, n_ctx, start_pos=n_ctx - 1)
-    ref = port.qkv_attn(q, k, v, adt, n_ctx, H, G, D, n_ctx, start_pos=n_ctx - 1)
+    H, G, D, n_ctx, max_ctx = 32, 4, 64, 2048, 2176
+    q = checker.encode_rows(rand_rows(rng, n_ctx, H * D), adt)
+    k = checker.encode_rows(rand_rows(rng, n_ctx, G * D), adt)
+    v = checker.encode_rows(rand_rows(rng, n_ctx, G * D), adt)
+    got = capi.qkv_attn(q, k, v, adt, n_ctx, H, G, D, max_ctx, start_pos=n_ctx - 1)
+    ref = checker.qkv_attn(q, k, v, adt, n_ctx, H, G, D, max_ctx, start_pos=n_ctx - 1)
     assert np.array_equal(got[-1], ref[-1])
 
 

@@ -8,6 +8,7 @@ Contract: BIT equality.  R rows share every weight load but each (row, output, l
   * the exact batched decode gives, for every slot, the tokens and logits of the same sequence decoded alone by the reference
     (BASELINE.json configs[4] at full size: 4 sequences of the q4_seq64 recipe against committed golden tokens).
 """
+import sys
 from pathlib import Path
 
 import numpy as np
@@ -18,6 +19,8 @@ from tinyllama_cpp_b200 import weights as W
 
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).resolve().parent / "golden"
+sys.path.insert(0, str(GOLD))
+import make_golden as MG  # noqa: E402
 
 
 @pytest.fixture(scope="module")
@@ -161,7 +164,6 @@ def test_full_size_seq64_batch_identity(capi):
     f = GOLD / "seq64_q4.npz"
     if not f.exists():
         pytest.skip("seq64_q4.npz not generated")
-    import tests.golden.make_golden as MG
     S = MG.SEQ64
     gold = np.load(f)
     cfg = W.TINYLLAMA

@@ -30,7 +30,7 @@ SYMBOLS = [
     "gtb_engine_set_option", "gtb_engine_weight_bytes", "gtb_engine_read_prof", "gtb_selftest_exact_sum", "gtb_engine_uses_megakernel",
     "gtb_engine_prefill_fast", "gtb_engine_pf_acv", "gtb_pf_gemm_f32", "gtb_engine_topk",
     "gtb_engine_batch_create", "gtb_engine_batch_adopt", "gtb_engine_batch_decode", "gtb_engine_batch_position",
-    "gtb_engine_batch_read_tokens", "gtb_engine_batch_read_logits", "gtb_engine_batch_prefill",
+    "gtb_engine_batch_read_tokens", "gtb_engine_batch_read_logits", "gtb_engine_batch_prefill", "gtb_selftest_expf",
 ]
 
 
@@ -83,6 +83,7 @@ def lib():
             "gtb_engine_batch_create": [vp, i], "gtb_engine_batch_adopt": [vp, i], "gtb_engine_batch_decode": [vp, i],
             "gtb_engine_batch_position": [vp, i, C.POINTER(i)], "gtb_engine_batch_read_tokens": [vp, i, vp, i, i],
             "gtb_engine_batch_read_logits": [vp, i, vp], "gtb_engine_batch_prefill": [vp, i, vp, i],
+            "gtb_selftest_expf": [C.c_uint32, C.c_uint32, vp],
         }
         for name, args in sigs.items():
             fn = getattr(L, name)
@@ -287,6 +288,13 @@ def selftest_exact_sum(terms, cycles: bool = False):
     if cycles:
         return out[0], out[1:5].copy()
     return out[0]
+
+
+def selftest_expf(first_bits: int, count: int) -> np.ndarray:
+    """Device expf of the float bit patterns [first_bits, first_bits + count)."""
+    out = np.empty(count, np.float32)
+    check(lib().gtb_selftest_expf(first_bits, count, _hp(out)))
+    return out
 
 
 class Engine:

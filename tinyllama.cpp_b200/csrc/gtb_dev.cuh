@@ -83,7 +83,7 @@ __device__ __forceinline__ float q8_roundtrip_lane(float x) {
 __device__ __forceinline__ float f16_roundtrip(float x) { return h2f(f2h(x)); }
 
 // ---------------------------------------------------------------- glibc 2.39 expf (sysdeps/ieee754/flt-32/e_expf.c,
-// FMA ifunc variant).  Verified over all 2^32 inputs against the host libm by oracle/check_expf.c:
+// FMA ifunc variant).  Verified over all 2^32 inputs against the host libm by tests/test_expf_gpu.py (gtb_selftest_expf):
 // the range reduction is r = fma(InvLn2N, x, -kd); the polynomial uses fused steps.
 __constant__ uint64_t c_exp2f_tab[32] = {
     0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,

@@ -299,6 +299,12 @@ __global__ void __launch_bounds__(MT) k_selftest_exact_sum(const float* __restri
     if (threadIdx.x == 0) *out = r;
 }
 
+// glibc-exact expf of the bit patterns [first, first + count) (exhaustive self-test against the host libm)
+__global__ void k_selftest_expf(uint32_t first, uint32_t count, float* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = expf_glibc(__uint_as_float(first + (uint32_t)i));
+}
+
 struct LayerW {
     gtb_weight_t q = nullptr, k = nullptr, v = nullptr, o = nullptr, gate = nullptr, up = nullptr, down = nullptr;
     uint16_t* attn_norm = nullptr;
@@ -1735,6 +1741,20 @@ int gtb_selftest_exact_sum(const float* h_terms, int n, float* h_out) {
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx().stream);
     cudaFree(d); cudaFree(o);
     if (ce != cudaSuccess) return fail(GTB_ERR_CUDA, "exact-sum self-test failed: %s", cudaGetErrorString(ce));
+    return GTB_OK;
+}
+
+int gtb_selftest_expf(uint32_t first_bits, uint32_t count, float* h_out) {
+    GTB_CHECK_INIT();
+    GTB_ARG(h_out && count > 0 && count <= (1u << 26));
+    float* d = nullptr;
+    GTB_CUDA(cudaMalloc((void**)&d, (size_t)count * 4));
+    k_selftest_expf<<<ctx().sm_count * 8, 256, 0, ctx().stream>>>(first_bits, count, d);
+    ctx().launches++;
+    cudaError_t ce = cudaMemcpyAsync(h_out, d, (size_t)count * 4, cudaMemcpyDeviceToHost, ctx().stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx().stream);
+    cudaFree(d);
+    if (ce != cudaSuccess) return fail(GTB_ERR_CUDA, "expf self-test failed: %s", cudaGetErrorString(ce));
     return GTB_OK;
 }
 

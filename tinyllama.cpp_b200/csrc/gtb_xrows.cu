@@ -113,8 +113,9 @@ struct XrNormArgs {
 
 __global__ void __launch_bounds__(NT) k_xr_norm(XrNormArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    float* xbuf = reinterpret_cast<float*>(smem);
-    ExactSumSmem& es = *reinterpret_cast<ExactSumSmem*>(smem + (((size_t)a.E * 4 + 15) & ~(size_t)15));
+    float* xbuf = reinterpret_cast<float*>(smem);                 // [E] the row
+    float* sq = xbuf + a.E;                                       // [E] its squares
+    __shared__ float s_sum;
     const int row = a.row0 + blockIdx.x;
     const XrRow rw = a.rows[row];
     if (rw.slot < 0) return;
@@ -142,10 +143,32 @@ __global__ void __launch_bounds__(NT) k_xr_norm(XrNormArgs a) {
             v = res[e];
         }
         xbuf[e] = v;
+        sq[e] = __fmul_rn(v, v);
     }
     __syncthreads();
-    const float sq_sum = exact_sum_block([&](int i) { const float v = xbuf[i]; return __fmul_rn(v, v); }, a.E, es);
-    const float denom = __fadd_rn(sqrtf(__fdiv_rn(sq_sum, (float)a.E)), 1e-6f);
+    // ops.h:765-767: the sum of squares strictly in order.  One thread walks the chain (4 cycles per add): the rows of a pass
+    // run side by side on different SMs, so the plain chain costs one chain latency for all of them.
+    if (threadIdx.x == 0) {
+        float s = 0.0f;
+        const float4* p4 = reinterpret_cast<const float4*>(sq);
+        float4 cur[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) cur[u] = p4[u];
+        for (int i = 0; i < a.E / 4; i += 4) {
+            float4 nxt[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) nxt[u] = (i + 4 + u < a.E / 4) ? p4[i + 4 + u] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                s = __fadd_rn(s, cur[u].x); s = __fadd_rn(s, cur[u].y); s = __fadd_rn(s, cur[u].z); s = __fadd_rn(s, cur[u].w);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) cur[u] = nxt[u];
+        }
+        s_sum = s;
+    }
+    __syncthreads();
+    const float denom = __fadd_rn(sqrtf(__fdiv_rn(s_sum, (float)a.E)), 1e-6f);
     for (int b = wid; b < nb; b += NWARP) {
         const int e = b * 32 + lane;
         const float y = __fmul_rn(__fdiv_rn(xbuf[e], denom), h2f(a.normw[e]));
@@ -156,7 +179,7 @@ __global__ void __launch_bounds__(NT) k_xr_norm(XrNormArgs a) {
 }
 
 // ---------------------------------------------------------------- the multi-row GEMM
-constexpr int XG_NT = 128, XG_BM = 16, XG_BN = 64, XG_KC = 8, XG_STAGES = 3;
+constexpr int XG_BM = 16, XG_BN = 64, XG_KC = 8, XG_STAGES = 3;
 enum { XEPI_QKV = 0, XEPI_RES = 1, XEPI_SILU = 2, XEPI_HEAD = 3 };
 
 template <int WT>
@@ -182,8 +205,11 @@ struct XrGemmArgs {
     float* logits; int ld_logits; float* arg_val; int* arg_idx; int n_tiles;   // EPI_HEAD
 };
 
-template <int WT, int EPI>
-__global__ void __launch_bounds__(XG_NT) k_xr_gemm(XrGemmArgs a) {
+// NW warps per CTA, TR = 16 / NW rows per warp: (4, 4) amortises a weight block over 4 rows (fewest instructions; large N),
+// (8, 2) doubles the warps per tile for the matrices with few column tiles (N <= 2560: q|k|v, o, down)
+template <int WT, int EPI, int NW>
+__global__ void __launch_bounds__(NW * 32, (NW == 4) ? 4 : 2) k_xr_gemm(XrGemmArgs a) {
+    constexpr int XG_NT = NW * 32, TR = XG_BM / NW;
     extern __shared__ __align__(16) unsigned char smem[];
     XgStage<WT>* stages = reinterpret_cast<XgStage<WT>*>(smem);
     constexpr int WB = XgStage<WT>::WB, WPC = XG_KC * WB;
@@ -213,9 +239,9 @@ __global__ void __launch_bounds__(XG_NT) k_xr_gemm(XrGemmArgs a) {
             cp_async16(reinterpret_cast<uint4*>(&st.act[r][0]) + j, src, ok);
         }
     };
-    float acc[4][2][4];
+    float acc[TR][2][4];
 #pragma unroll
-    for (int r = 0; r < 4; r++)
+    for (int r = 0; r < TR; r++)
 #pragma unroll
         for (int c = 0; c < 2; c++)
 #pragma unroll
@@ -256,8 +282,8 @@ __global__ void __launch_bounds__(XG_NT) k_xr_gemm(XrGemmArgs a) {
             }
             const float dw[2] = {__half2float(hA[b]), __half2float(hB[b])};
 #pragma unroll
-            for (int r = 0; r < 4; r++) {
-                const XBlk& ab = st.act[wid * 4 + r][b];
+            for (int r = 0; r < TR; r++) {
+                const XBlk& ab = st.act[wid * TR + r][b];
                 const uint4 ax4 = *reinterpret_cast<const uint4*>(&ab.w[0]);
                 const uint4 ay4 = *reinterpret_cast<const uint4*>(&ab.w[4]);
                 const uint32_t ax[4] = {ax4.x, ax4.y, ax4.z, ax4.w}, ay[4] = {ay4.x, ay4.y, ay4.z, ay4.w};
@@ -283,10 +309,10 @@ __global__ void __launch_bounds__(XG_NT) k_xr_gemm(XrGemmArgs a) {
         }
     }
     cp_async_wait<0>();
-    // ---------------- epilogue: lane = column inside each 32-block, warp = 4 rows: every re-encode is warp-local
+    // ---------------- epilogue: lane = column inside each 32-block, warp = TR rows: every re-encode is warp-local
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const int row = rbase + wid * 4 + r;
+    for (int r = 0; r < TR; r++) {
+        const int row = rbase + wid * TR + r;
         if (row >= rend) continue;                                   // warp-uniform
         const XrRow rw = a.rows[row];
         if (rw.slot < 0) continue;
@@ -605,7 +631,7 @@ struct XrPlan {
 
 bool xr_supported(const gtb_model_config& c, int gsz) {
     return (c.wdtype == GTB_Q8 || c.wdtype == GTB_Q4) && gsz == 8 && c.n_embd % 256 == 0 && c.n_ffn % 256 == 0 && c.n_embd / c.n_heads == 64 &&
-           c.n_embd <= NT * ES_EPT * 4;
+           c.n_embd % 16 == 0 && c.n_embd <= 4096;
 }
 
 int xr_create(XrPlan** out, const gtb_model_config& c) {
@@ -644,18 +670,25 @@ void xr_destroy(XrPlan* p) {
 
 namespace {
 
-template <int WT, int EPI>
-int launch_gemm(const XrGemmArgs& a, int n_tiles) {
+template <int WT, int EPI, int NW>
+int launch_gemm_nw(const XrGemmArgs& a, int n_tiles) {
     const size_t smem = sizeof(XgStage<WT>) * XG_STAGES;
     static bool attr = false;
     if (!attr) {
-        GTB_CUDA(cudaFuncSetAttribute(k_xr_gemm<WT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GTB_CUDA(cudaFuncSetAttribute(k_xr_gemm<WT, EPI, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
     dim3 grid(n_tiles, (a.n_rows + XG_BM - 1) / XG_BM);
-    k_xr_gemm<WT, EPI><<<grid, XG_NT, smem, ctx().stream>>>(a);
+    k_xr_gemm<WT, EPI, NW><<<grid, NW * 32, smem, ctx().stream>>>(a);
     GTB_LAUNCHED();
     return GTB_OK;
+}
+template <int WT, int EPI>
+int launch_gemm(const XrGemmArgs& a, int n_tiles) {
+    // few column tiles: 8 warps x 2 rows per tile keep two warps per scheduler busy; many tiles: 4 warps x 4 rows
+    const int ctas = n_tiles * ((a.n_rows + XG_BM - 1) / XG_BM);
+    if (EPI != XEPI_SILU && EPI != XEPI_HEAD && ctas <= 2 * ctx().sm_count) return launch_gemm_nw<WT, EPI, 8>(a, n_tiles);
+    return launch_gemm_nw<WT, EPI, 4>(a, n_tiles);
 }
 
 template <int WT>
@@ -666,7 +699,7 @@ int run_pass(XrPlan* p, const XrModel& m, const XrKV& kv, const XrSeq& sq, const
     cudaStream_t st = ctx().stream;
     k_xr_plan<<<1, XR_MAX_ROWS, 0, st>>>(plan);
     GTB_LAUNCHED();
-    const size_t norm_smem = (((size_t)E * 4 + 15) & ~(size_t)15) + sizeof(ExactSumSmem);
+    const size_t norm_smem = (size_t)E * 8;
     const size_t attn_smem = xr_attn_smem(t_cap);
     static bool attr = false;
     if (!attr) {

@@ -10,11 +10,19 @@ def main(path, split_gemm=True):
     rows = list(csv.DictReader(lines))
     agg = collections.OrderedDict()
     gi = 0
+    ri = 0
     for x in rows:
         name = x["Kernel Name"].split("(")[0].replace("void ", "")
         if split_gemm and "k_pf_gemm" in name:
             name += " [" + ["q|k|v", "o", "gate|up", "down"][gi % 4] + "]"
             gi += 1
+        if "k_xr_gemm" in name:
+            epi = name.split(",")[-1].strip(" >")
+            if "1" in epi:
+                name += " [" + ["o", "down"][ri % 2] + "]"
+                ri += 1
+            else:
+                name += " [" + {"0": "q|k|v", "2": "gate|up+silu", "3": "lm_head"}.get(epi.replace("(int)", ""), epi) + "]"
         agg.setdefault(name, []).append(float(x["Metric Value"].replace(",", "")))
     tot = sum(sum(v) for v in agg.values())
     print(f"{'kernel':48s} {'n':>4s} {'total ms':>9s} {'share':>6s} {'avg us':>8s}")

@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--batches", default="64,32,16,8")
     ap.add_argument("--max-ctx", type=int, default=2048)
     ap.add_argument("--skip-prefill", action="store_true")
+    ap.add_argument("--adopt", action="store_true", help="one prefill on the engine's own sequence, copied into every slot (few launches: for ncu)")
+    ap.add_argument("--prefill-reps", type=int, default=2)
     args = ap.parse_args()
     wdt = W.WDTYPE_BY_NAME[args.wdt if args.wdt != "f16" else "fp16"]
     capi.init(0)
@@ -33,27 +35,34 @@ def main():
     out = {}
     if not args.skip_prefill:
         prompt = W.synth_prompt(7, args.prompt, cfg.n_vocab)
-        eng.prefill(prompt[:70])
+        if args.prefill_reps > 1:
+            eng.prefill(prompt[:70])
         capi.sync()
-        for rep in range(2):
+        for rep in range(args.prefill_reps):
             t0 = time.perf_counter()
             eng.prefill(prompt)
             capi.sync()
             ms = (time.perf_counter() - t0) * 1e3
         out["exact_prefill"] = {"tokens": args.prompt, "ms": ms, "tok_s": args.prompt / ms * 1e3, "first_token": int(eng.read_tokens(args.prompt, 1)[0])}
-        eng.set_option("xrows", 0)
-        t0 = time.perf_counter()
-        eng.prefill(prompt[:256])
-        capi.sync()
-        ms1 = (time.perf_counter() - t0) * 1e3
-        eng.set_option("xrows", 1)
-        out["row_at_a_time_prefill_256"] = {"ms": ms1, "tok_s": 256 / ms1 * 1e3}
+        if args.prefill_reps > 1:
+            eng.set_option("xrows", 0)
+            t0 = time.perf_counter()
+            eng.prefill(prompt[:256])
+            capi.sync()
+            ms1 = (time.perf_counter() - t0) * 1e3
+            eng.set_option("xrows", 1)
+            out["row_at_a_time_prefill_256"] = {"ms": ms1, "tok_s": 256 / ms1 * 1e3}
         print(json.dumps(out), flush=True)
-    for B in [int(x) for x in args.batches.split(",")]:
+    for B in [int(x) for x in args.batches.split(",") if x]:
         eng.batch_create(B)
         t0 = time.perf_counter()
+        if args.adopt:
+            eng.prefill(W.synth_prompt(100, args.seq_prompt, cfg.n_vocab))
         for s in range(B):
-            eng.batch_prefill(s, W.synth_prompt(100 + s, args.seq_prompt, cfg.n_vocab))
+            if args.adopt:
+                eng.batch_adopt(s)
+            else:
+                eng.batch_prefill(s, W.synth_prompt(100 + s, args.seq_prompt, cfg.n_vocab))
         capi.sync()
         pf_ms = (time.perf_counter() - t0) * 1e3
         eng.batch_decode(2)                     # graph capture + warm-up
