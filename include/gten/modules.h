@@ -5,6 +5,8 @@
 // resident on the GPU as one persistent kernel per call.
 #pragma once
 #include <chrono>
+#include <cstdlib>
+#include <unordered_map>
 
 #include "ops.h"
 
@@ -12,18 +14,41 @@ namespace gten {
 
 struct ModuleDtype { Dtype wdtype; Dtype adtype; };
 
+// Profiling mode: device work is asynchronous, so a host clock around a launch measures launch overhead.  With profiling on
+// (gten::set_profiling(true), or GTEN_PROFILE=1 in the environment) a Timer drains the library stream before it reads the
+// clock at both ends, so `exec_time` is the device time of the op and print_perf (tinyllama.cpp:515-582) reports real numbers.
+inline bool& profiling_flag() {
+    static bool on = [] { const char* e = std::getenv("GTEN_PROFILE"); return e && *e && *e != '0'; }();
+    return on;
+}
+inline void set_profiling(bool on) { profiling_flag() = on; }
+
 class Timer {                       // adds whole milliseconds to *time_tracker (reference modules.h:170-192)
 public:
-    explicit Timer(int64_t* time_tracker) : tracker_{time_tracker}, t0_{std::chrono::high_resolution_clock::now()} {}
+    explicit Timer(int64_t* time_tracker) : tracker_{time_tracker} {
+        if (profiling_flag()) gtb_sync();
+        t0_ = std::chrono::high_resolution_clock::now();
+    }
     ~Timer() { stop(); }
     void stop() {
         if (done_) return;
-        using ms = std::chrono::milliseconds;
-        const auto t1 = std::chrono::high_resolution_clock::now();
-        *tracker_ += std::chrono::time_point_cast<ms>(t1).time_since_epoch().count() - std::chrono::time_point_cast<ms>(t0_).time_since_epoch().count();
+        if (profiling_flag()) {
+            // sub-millisecond ops would all truncate to 0: carry the nanoseconds per tracker
+            gtb_sync();
+            const auto t1 = std::chrono::high_resolution_clock::now();
+            int64_t& rem = remainder()[tracker_];
+            rem += std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0_).count();
+            *tracker_ += rem / 1000000;
+            rem %= 1000000;
+        } else {
+            using ms = std::chrono::milliseconds;
+            const auto t1 = std::chrono::high_resolution_clock::now();
+            *tracker_ += std::chrono::time_point_cast<ms>(t1).time_since_epoch().count() - std::chrono::time_point_cast<ms>(t0_).time_since_epoch().count();
+        }
         done_ = true;
     }
 private:
+    static std::unordered_map<int64_t*, int64_t>& remainder() { static std::unordered_map<int64_t*, int64_t> m; return m; }
     int64_t* tracker_;
     std::chrono::time_point<std::chrono::high_resolution_clock> t0_;
     bool done_ = false;

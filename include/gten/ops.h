@@ -77,6 +77,14 @@ static void qkv_attn(const Tensor& q, const Tensor& k, const Tensor& v, Tensor& 
                               q.dimsize(1) / d_head, k.dimsize(1) / d_head, d_head, max_ctx, start_pos));
 }
 
+/// dot product of two HOST rows in the given dtypes (reference ops.h:482-512): (Q8, Q8), (Q8, Q4), (F16, F16), (F32, F32);
+/// evaluated on the device in the reference's AVX order (4 integer lanes per block / 8 float lanes), bit-identical
+inline float vec_dot_product(const char* inp0, Dtype inp0_dtype, const char* inp1, Dtype inp1_dtype, int vecsize) {
+    float r = 0.0f;
+    GTEN_CUDA_OK(gtb_vec_dot_product(inp0, gdt(inp0_dtype), inp1, gdt(inp1_dtype), vecsize, &r));
+    return r;
+}
+
 /// row codecs on host buffers (reference ops.h:40-96): decode / encode one row in the given dtype
 inline void read_row_to_float(const char* inp, Dtype inp_dtype, float* out_buf, const int rowsize) {
     switch (inp_dtype) {

@@ -17,6 +17,8 @@ struct Q4Block { Float16 delta; Qint4 data[16]; };       // byte i = (elt i + 7)
 static_assert(sizeof(Q8Block) == 34, "Q8Block is 34 bytes");
 static_assert(sizeof(Q4Block) == 18, "Q4Block is 18 bytes");
 
+namespace ops {          // the codecs live in gten::ops like the reference's (gten/quants.h:34-152)
+
 [[nodiscard]] inline Qint8 q8_quantize_single(float x, float delta) {
     const float scale = delta ? 1.0f / delta : 0.0f;
     return static_cast<Qint8>(roundf(x * scale));
@@ -63,5 +65,12 @@ inline void q4_dequantize_row(const Q4Block* inp, float* out, int rowsize) {
 inline void q8_dequantize_row_delta(const Qint8* x, float* out, float delta, int size) {
     for (int i = 0; i < size; i++) out[i] = x[i] * delta;
 }
+
+}  // namespace ops
+
+// round 1 exposed the codecs in gten:: ; both spellings stay valid
+using ops::q8_quantize_single; using ops::q8_dequantize_single; using ops::q8_quantize_block; using ops::q8_dequantize_block;
+using ops::q4_dequantize_block; using ops::q8_quantize_row; using ops::q8_quantize_row_delta; using ops::q8_dequantize_row;
+using ops::q4_dequantize_row; using ops::q8_dequantize_row_delta;
 
 }  // namespace gten

@@ -74,6 +74,10 @@ int gtb_weight_dequant(gtb_weight_t w, int row0, int nrows, float* h_out);
 int gtb_write_rows_from_float(const float* d_in, void* d_out, int out_dtype, int rows, int n);
 int gtb_read_rows_to_float(const void* d_in, int in_dtype, float* d_out, int rows, int n);
 
+/* ops::vec_dot_product (gten/ops.h:482-512): dot of two HOST rows in the reference layout, evaluated on the device in the
+ * reference's AVX order; dtype pairs (Q8, Q8), (Q8, Q4), (F16, F16), (F32, F32) like the reference's switch */
+int gtb_vec_dot_product(const void* h_a, int a_dtype, const void* h_b, int b_dtype, int n, float* h_out);
+
 /* ---- ops (gten/ops.h); activations are device buffers in the reference's own row layout ---------- */
 int gtb_token_embed(gtb_weight_t w, const int32_t* d_tokens, void* d_out, int out_dtype, int n_ctx, int start_pos); /* ops.h:554 */
 int gtb_matmul_2d(const void* d_x, int x_dtype, int n_ctx, gtb_weight_t w, void* d_out, int out_dtype,

@@ -11,9 +11,9 @@ import oracle
 ROOT = Path(__file__).resolve().parent.parent
 
 SRC = r"""
-#include "gten/gten_types.h"
-#include "gten/quants.h"
+#include "gten/gten.h"
 #include <cstdio>
+#include <cstring>
 #include <vector>
 using namespace gten;
 int main(int argc, char** argv) {
@@ -33,7 +33,12 @@ int main(int argc, char** argv) {
     q8_quantize_row(x.data(), q.data(), n);
     std::fwrite(q.data(), sizeof(Q8Block), nb, fo);
     std::vector<float> dq(n);
-    q8_dequantize_row(q.data(), dq.data(), n);
+    gten::ops::q8_dequantize_row(q.data(), dq.data(), n);     // the reference's spelling (gten/quants.h:34: namespace ops) ...
+    std::vector<float> dq2(n);
+    gten::q8_dequantize_row(q.data(), dq2.data(), n);          // ... and round 1's alias
+    if (std::memcmp(dq.data(), dq2.data(), 4 * n) != 0) return 2;
+    float (*vdp)(const char*, Dtype, const char*, Dtype, int) = &gten::ops::vec_dot_product;   // ops.h:482: the entry point exists
+    if (!vdp || !gten::ops::q8_quantize_single(1.0f, 0.5f)) return 3;
     std::fwrite(dq.data(), 4, n, fo);
     return 0;
 }
@@ -45,7 +50,11 @@ def exe(tmp_path_factory):
     d = tmp_path_factory.mktemp("dropin")
     (d / "t.cpp").write_text(SRC)
     cxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
-    subprocess.run([cxx, "-std=c++17", "-O1", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(d / "t.cpp"), "-o", str(d / "t")], check=True)
+    from tinyllama_cpp_b200 import build
+    build.build()
+    libdir = ROOT / "tinyllama.cpp_b200"
+    subprocess.run([cxx, "-std=c++17", "-O1", "-Wall", "-Werror", "-Wno-unused-function", f"-I{ROOT / 'include'}", str(d / "t.cpp"), "-o", str(d / "t"),
+                    f"-L{libdir}", "-lgten_b200", f"-Wl,-rpath,{libdir}"], check=True)
     return d / "t"
 
 

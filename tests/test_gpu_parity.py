@@ -176,6 +176,20 @@ def test_megakernel_exact_sum_adversarial(capi):
         assert got.view(np.uint32) == want.view(np.uint32), (i, t.size, got, want)
 
 
+@pytest.mark.parametrize("adt,bdt,n", [(Q8, Q8, 64), (Q8, Q8, 2048), (Q8, Q4, 2048), (Q8, Q4, 5632), (F16, F16, 2048), (F16, F16, 67),
+                                       (F32, F32, 2048), (F32, F32, 131), (F32, F32, 5)])
+def test_vec_dot_product(capi, checker, adt, bdt, n):
+    """ops::vec_dot_product (gten/ops.h:482-512) on host rows, every dtype pair of the reference's switch: the float returned
+    is bit-identical to the reference's AVX build (4 integer lanes per block / 8 float lanes + in-order tail)."""
+    rng = np.random.default_rng(n + 7 * adt + bdt)
+    x, y = rand_rows(rng, 1, n, 1.3)[0], rand_rows(rng, 1, n, 0.02)[0]
+    a = x if adt == F32 else checker.write_row(x, adt)
+    b = y if bdt == F32 else (W.quantize_payload(y.reshape(1, -1), Q4) if bdt == Q4 else checker.write_row(y, bdt))
+    got = capi.vec_dot_product(a, adt, b, bdt, n)
+    want = checker.vec_dot(a, adt, b, bdt, n)
+    assert bits(np.float32(got)) == bits(np.float32(want)), (got, want)
+
+
 @pytest.mark.parametrize("wdt", [Q4, Q8, F16])
 def test_token_embed(capi, checker, wdt):
     rng = np.random.default_rng(9)

@@ -30,7 +30,7 @@ SYMBOLS = [
     "gtb_engine_set_option", "gtb_engine_weight_bytes", "gtb_engine_read_prof", "gtb_selftest_exact_sum", "gtb_engine_uses_megakernel",
     "gtb_engine_prefill_fast", "gtb_engine_pf_acv", "gtb_pf_gemm_f32", "gtb_engine_topk",
     "gtb_engine_batch_create", "gtb_engine_batch_adopt", "gtb_engine_batch_decode", "gtb_engine_batch_position",
-    "gtb_engine_batch_read_tokens", "gtb_engine_batch_read_logits", "gtb_engine_batch_prefill", "gtb_selftest_expf",
+    "gtb_engine_batch_read_tokens", "gtb_engine_batch_read_logits", "gtb_engine_batch_prefill", "gtb_selftest_expf", "gtb_vec_dot_product",
 ]
 
 
@@ -84,6 +84,7 @@ def lib():
             "gtb_engine_batch_position": [vp, i, C.POINTER(i)], "gtb_engine_batch_read_tokens": [vp, i, vp, i, i],
             "gtb_engine_batch_read_logits": [vp, i, vp], "gtb_engine_batch_prefill": [vp, i, vp, i],
             "gtb_selftest_expf": [C.c_uint32, C.c_uint32, vp],
+            "gtb_vec_dot_product": [vp, i, vp, i, i, C.POINTER(C.c_float)],
         }
         for name, args in sigs.items():
             fn = getattr(L, name)
@@ -288,6 +289,14 @@ def selftest_exact_sum(terms, cycles: bool = False):
     if cycles:
         return out[0], out[1:5].copy()
     return out[0]
+
+
+def vec_dot_product(a: np.ndarray, adt: int, b: np.ndarray, bdt: int, n: int) -> np.float32:
+    """ops::vec_dot_product on two host rows in the reference layout (gten/ops.h:482-512)."""
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    out = C.c_float()
+    check(lib().gtb_vec_dot_product(_hp(a), adt, _hp(b), bdt, n, C.byref(out)))
+    return np.float32(out.value)
 
 
 def selftest_expf(first_bits: int, count: int) -> np.ndarray:

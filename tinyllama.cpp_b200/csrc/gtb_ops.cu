@@ -239,6 +239,50 @@ static int matmul_launch(const void* d_x, int n_ctx, gtb_weight_t w, float* tmp,
 
 using namespace gtb;
 
+
+// ---------------------------------------------------------------- ops::vec_dot_product (gten/ops.h:482-512) on two rows
+// One thread walks the reference's AVX evaluation order; rows are in the reference's own layout.
+__global__ void k_vec_dot(const uint8_t* __restrict__ a, int adt, const uint8_t* __restrict__ b, int bdt, int n, float* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float r = 0.0f;
+    if (adt == DT_Q8) {
+        // ops.h:224-292 (Q8 x Q8) / 319-391 (Q8 x Q4): lane l = elements {2l, 2l+1, 2l+8, 2l+9} and the same + 16
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (int blk = 0; blk < n / 32; blk++) {
+            const uint8_t* ab = a + (size_t)blk * Q8_BYTES;
+            const uint8_t* bb = b + (size_t)blk * ((bdt == DT_Q4) ? Q4_BYTES : Q8_BYTES);
+            const float da = h2f((uint16_t)ab[0] | ((uint16_t)ab[1] << 8)), db = h2f((uint16_t)bb[0] | ((uint16_t)bb[1] << 8));
+            const float s = __fmul_rn(da, db);
+            for (int l = 0; l < 4; l++) {
+                int sum = 0;
+                for (int half = 0; half < 2; half++)
+                    for (int j = 0; j < 4; j++) {
+                        const int e = 16 * half + 2 * l + (j & 1) + 8 * (j >> 1);
+                        const int qa = (int)(int8_t)ab[2 + e];
+                        int qb;
+                        if (bdt == DT_Q4) { const uint8_t by = bb[2 + (e & 15)]; qb = (int)((e < 16) ? (by >> 4) : (by & 0x0f)) - 7; }
+                        else qb = (int)(int8_t)bb[2 + e];
+                        sum += qa * qb;
+                    }
+                acc[l] = __fadd_rn(acc[l], __fmul_rn((float)sum, s));
+            }
+        }
+        r = __fadd_rn(__fadd_rn(acc[0], acc[1]), __fadd_rn(acc[2], acc[3]));
+    } else {
+        // ops.h:140-160 (fp16) / 177-197 (fp32): eight lane accumulators over elements 8i + l, mul and add rounded separately
+        // (simd_ops.h:59-61), lanes summed left to right (simd_ops.h:63-66), then the tail in order
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const int n8 = (n / 8) * 8;
+        auto ld = [&](const uint8_t* p, int dt, int i) { return dt == DT_F16 ? h2f(reinterpret_cast<const uint16_t*>(p)[i]) : reinterpret_cast<const float*>(p)[i]; };
+        for (int i = 0; i < n8; i += 8)
+            for (int l = 0; l < 8; l++) acc[l] = __fadd_rn(__fmul_rn(ld(a, adt, i + l), ld(b, bdt, i + l)), acc[l]);
+        r = __fadd_rn(acc[0], acc[1]);
+        for (int l = 2; l < 8; l++) r = __fadd_rn(r, acc[l]);
+        for (int i = n8; i < n; i++) r = __fadd_rn(r, __fmul_rn(ld(a, adt, i), ld(b, bdt, i)));
+    }
+    *out = r;
+}
+
 extern "C" {
 
 int gtb_token_embed(gtb_weight_t w, const int32_t* d_tokens, void* d_out, int out_dtype, int n_ctx, int start_pos) {
@@ -349,6 +393,31 @@ int gtb_qkv_attn(const void* d_q, const void* d_k, const void* d_v, void* d_qk, 
         r = gtb_write_rows_from_float(tmp, (uint8_t*)d_out + (size_t)start_pos * row_nbytes(dtype, n_embd), dtype, rows, n_embd);
     cudaFreeAsync(kq, st); cudaFreeAsync(vq, st); cudaFreeAsync(ks, st); cudaFreeAsync(vs, st); cudaFreeAsync(tmp, st);
     return r;
+}
+
+int gtb_vec_dot_product(const void* h_a, int a_dtype, const void* h_b, int b_dtype, int n, float* h_out) {
+    GTB_CHECK_INIT();
+    GTB_ARG(h_a && h_b && h_out && n > 0);
+    const bool q = a_dtype == GTB_Q8 && (b_dtype == GTB_Q8 || b_dtype == GTB_Q4);
+    const bool f = (a_dtype == GTB_F16 && b_dtype == GTB_F16) || (a_dtype == GTB_F32 && b_dtype == GTB_F32);
+    if (!q && !f) return fail(GTB_ERR_ARG, "vec_dot_product: unsupported dtype pair (%d, %d)", a_dtype, b_dtype);   // ops.h:506-509 asserts
+    if (q && n % 32 != 0) return fail(GTB_ERR_ARG, "vec_dot_product: %d is not a multiple of the block size", n);   // ops.h:229
+    const size_t na = row_nbytes(a_dtype, n), nb = row_nbytes(b_dtype, n);
+    uint8_t* d = nullptr;
+    const size_t oa = 0, ob = (na + 15) & ~(size_t)15, oo = ob + ((nb + 15) & ~(size_t)15);
+    GTB_CUDA(cudaMalloc((void**)&d, oo + 16));
+    cudaStream_t st = ctx().stream;
+    cudaError_t ce = cudaMemcpyAsync(d + oa, h_a, na, cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d + ob, h_b, nb, cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) {
+        k_vec_dot<<<1, 32, 0, st>>>(d + oa, a_dtype, d + ob, b_dtype, n, reinterpret_cast<float*>(d + oo));
+        ctx().launches++;
+        ce = cudaMemcpyAsync(h_out, d + oo, 4, cudaMemcpyDeviceToHost, st);
+    }
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (ce != cudaSuccess) return fail(GTB_ERR_CUDA, "vec_dot_product failed: %s", cudaGetErrorString(ce));
+    return GTB_OK;
 }
 
 }  // extern "C"
