@@ -64,7 +64,8 @@ extern "C" int dropin_greedy_sample(const char* gten_path, int wdtype, int extra
     if (!ckpt.is_open()) return 2;
     Tokenizer tokenizer{tokenizer_path, 32000};
     std::string prompt{prompt_text};
-    std::vector<int> ids = tokenizer.encode(prompt);
+    std::string prompt_copy{prompt_text};                              // Tokenizer::encode edits its argument (tokenizer.h:150)
+    std::vector<int> ids = tokenizer.encode(prompt_copy);
     *n_prompt_ids = (int)ids.size();
     for (size_t i = 0; i < ids.size(); i++) prompt_ids[i] = ids[i];
     const int n_predict = (int)ids.size() + extra_tokens;             // main(): max_ctx = n_predict (tinyllama.cpp:267)

@@ -230,3 +230,29 @@ def test_batch_decode_argument_errors(capi):
     with pytest.raises(capi.GtbError):
         f.batch_create(2)
     f.close()
+
+
+# ---------------------------------------------------------------- token-level contract at full size
+MARGIN_BOUND = 0.35       # logits; the reference's median top-1/top-2 margin on these weights is 0.15, sigma(logit) 0.90
+
+
+@pytest.mark.parametrize("name,steps", [("full_q4", 512), ("full_q8", 256)])
+def test_fast_decode_token_agreement_full_size(capi, name, steps):
+    """What the tolerance means in tokens.  Teacher-forced on the reference's own greedy sequence at full size (golden tokens of
+    BASELINE.json configs[2] / [1], generated from the unmodified reference), every step's row runs through the order-free
+    kernels on an exact K/V cache.  Measured: top-1 agreement 80 % (Q4, 512 steps) / 83 % (Q8, 256 steps); EVERY disagreement
+    sits at a step where the reference's own top-1/top-2 margin is below 0.26 logits (stated bound: 0.35), i.e. the order-free
+    path only flips near-ties -- which with random-init weights is one step in five.  It is NOT greedy-identical (the exact
+    kernels are), and this test pins how far from it it is."""
+    import sys
+    from pathlib import Path
+    if not (GOLD / f"{name}.npz").exists():
+        pytest.skip(f"{name}.npz not generated")
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    from fastdec_agreement import agreement
+    r = agreement(name, steps)
+    print(f"{name}: agreement {r['agree']}/{r['steps']} = {r['agreement_rate']:.3f}, largest reference margin at a mismatch "
+          f"{r['max_mismatch_margin']:.3f}, logits rel-L2 mean {r['mean_rel_l2']:.3f} max {r['max_rel_l2']:.3f}")
+    assert r["agreement_rate"] >= 0.70, r["agreement_rate"]
+    assert r["max_mismatch_margin"] <= MARGIN_BOUND, [m for m in r["mismatches"] if m["ref_margin"] > MARGIN_BOUND]
+    assert r["max_rel_l2"] <= 0.15, r["max_rel_l2"]

@@ -302,6 +302,56 @@ def test_gten_file_roundtrip(capi, checker, tmp_path):
     e.close(); cm.close()
 
 
+@pytest.mark.parametrize("wdt", [Q4, F16])
+def test_gten_loader_pipeline_and_name_check(capi, checker, tmp_path, wdt):
+    """gtb_engine_load_gten (mmap + pinned double-buffered staging + on-device repack): payloads larger than one 16 MB staging chunk,
+    three layers; a file whose records are out of order, renamed or truncated is refused with the reference's kind of message."""
+    cfg = W.mini_config(n_layers=3, n_vocab=9000)           # embedding / lm_head payloads of 10-37 MB: several staging chunks
+    wl = list(W.synth_weights(cfg, wdt, seed=14))
+    path = tmp_path / "m.gten"
+    W.write_gten(path, cfg, wdt, wl)
+    e = capi.Engine(cfg, 32, wdt).load_gten(path)
+    cm = checker.model(cfg, 32, wdt).load(wl)
+    prompt = W.synth_prompt(2, 6, cfg.n_vocab)
+    assert np.array_equal(e.generate(prompt, 5), cm.generate(prompt, 5)[0])
+    e.close(); cm.close()
+    raw = bytearray(path.read_bytes())
+    # rename the second record (q_proj of layer 0 -> k_proj): same length, wrong tensor
+    i = raw.find(b"model.layers.0.self_attn.q_proj.weight")
+    bad = bytearray(raw); bad[i:i + 38] = b"model.layers.0.self_attn.k_proj.weight"
+    (tmp_path / "bad_name.gten").write_bytes(bad)
+    (tmp_path / "short.gten").write_bytes(raw[: len(raw) // 2])
+    badmagic = bytearray(raw); badmagic[0] ^= 0xff
+    (tmp_path / "magic.gten").write_bytes(badmagic)
+    for name, msg in (("bad_name.gten", "unexpected record"), ("short.gten", "truncated"), ("magic.gten", "Magic number")):
+        f = capi.Engine(cfg, 32, wdt)
+        with pytest.raises(capi.GtbError, match=msg):
+            f.load_gten(tmp_path / name)
+        f.close()
+    # a file of another shape (different n_ffn) fails the reference's per-tensor size check (tinyllama.cpp:316-319)
+    g = capi.Engine(W.mini_config(n_layers=3, n_vocab=9000, n_ffn=2816), 32, wdt)
+    with pytest.raises(capi.GtbError, match="does not match the expected size"):
+        g.load_gten(path)
+    g.close()
+
+
+def test_real_weights_golden_tokens(capi):
+    """Optional: with GTEN_REAL_MODEL=/path/to/tinyllama.<fp16|q8|q4>.gten (the reference's own model files, README.md:6) the prompt
+    ids and the first 30 greedy output ids must be those of the reference's golden comment (tinyllama.cpp:101-104)."""
+    import os
+    path = os.environ.get("GTEN_REAL_MODEL")
+    if not path or not os.path.exists(path):
+        pytest.skip("GTEN_REAL_MODEL not set (no network in this environment: the real checkpoint is not available)")
+    wdt = {"fp16": F16, "q8": Q8, "q4": Q4}[[k for k in ("fp16", "q8", "q4") if f".{k}." in os.path.basename(path)][0]]
+    prompt = np.array([1, 32001, 1404, 13, 22110, 338, 8425, 28579, 29973, 32002, 29871, 13, 32001, 20255, 13], np.int32)
+    golden = [24115, 29880, 28579, 338, 263, 5332, 8578, 359, 13434, 322, 7766, 391, 1058, 338, 5545,
+              697, 310, 278, 1556, 4100, 13994, 297, 278, 5849, 310, 28579, 391, 6368, 322, 6944]
+    e = capi.Engine(W.TINYLLAMA, 64, wdt).load_gten(path)
+    toks = e.generate(prompt, 30)
+    e.close()
+    assert toks[15:].tolist() == golden, toks[15:].tolist()
+
+
 def test_config5_sequence_sample_matches_reference(capi, checker):
     """BASELINE.json configs[4] (64 independent Q4 sequences served as replicas): one of the job's sequences (the prompt
     recipe of bench.py --workload q4_seq64, sequence 5) at full size, greedy tokens identical to the CPU reference."""

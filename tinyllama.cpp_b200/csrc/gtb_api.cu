@@ -357,6 +357,9 @@ int gtb_read_rows_to_float(const void* d_in, int in_dtype, float* d_out, int row
 }  // extern "C"
 
 namespace gtb {
+int weight_device_view(gtb_weight_t* out, const void* d_payload, int dtype, int rows, int cols, void* d_data, uint16_t* d_scales) {
+    return weight_from_device_impl(out, d_payload, dtype, rows, cols, d_data, d_scales);
+}
 int weight_upload_view(gtb_weight_t* out, const void* h_payload, int dtype, int rows, int cols, void* d_data, uint16_t* d_scales) {
     if (!d_data) return fail(GTB_ERR_ARG, "weight_upload_view: no destination");
     return weight_upload_impl(out, h_payload, dtype, rows, cols, d_data, d_scales);

@@ -7,7 +7,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <fstream>
+#include <string>
 #include <vector>
 
 #include "gtb_internal.h"
@@ -1150,7 +1156,9 @@ int gtb_engine_destroy(gtb_engine_t e) {
     return GTB_OK;
 }
 
-int gtb_engine_set_weight(gtb_engine_t e, int layer, int tensor_id, const void* h_payload, size_t nbytes) {
+// src = host payload, or (on_device) a device buffer that holds it already: then nothing here synchronises and the caller
+// keeps the buffer alive until the stream has passed the repack kernel (the pipelined loader below)
+static int set_weight_from(gtb_engine_t e, int layer, int tensor_id, const void* h_payload, size_t nbytes, bool on_device) {
     GTB_CHECK_INIT();
     GTB_ARG(e && h_payload);
     int rows = 0, cols = 0, dt = 0;
@@ -1162,8 +1170,9 @@ int gtb_engine_set_weight(gtb_engine_t e, int layer, int tensor_id, const void* 
     GTB_ARG(!per_layer || (layer >= 0 && layer < e->cfg.n_layers));
     if (dt == GTB_F16 && rows == 1) {
         uint16_t* dst = (tensor_id == GTB_T_FINAL_NORM) ? e->final_norm : (tensor_id == GTB_T_ATTN_NORM) ? e->L[layer].attn_norm : e->L[layer].ffn_norm;
-        GTB_CUDA(cudaMemcpyAsync(dst, h_payload, nbytes, cudaMemcpyHostToDevice, ctx().stream));     // stream-ordered with the kernels that read it
-        GTB_CUDA(cudaStreamSynchronize(ctx().stream));
+        // stream-ordered with the kernels that read it
+        GTB_CUDA(cudaMemcpyAsync(dst, h_payload, nbytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx().stream));
+        if (!on_device) GTB_CUDA(cudaStreamSynchronize(ctx().stream));
         return GTB_OK;
     }
     gtb_weight_t* slot = nullptr;
@@ -1197,45 +1206,112 @@ int gtb_engine_set_weight(gtb_engine_t e, int layer, int tensor_id, const void* 
             default: break;
         }
     }
-    if (row_off >= 0)
-        r = weight_upload_view(slot, h_payload, dt, rows, cols, fdata + weight_data_bytes(dt, row_off, cols),
-                               fsc ? fsc + weight_scale_bytes(dt, row_off, cols) / 2 : nullptr);
-    else
-        r = gtb_weight_upload(slot, h_payload, dt, rows, cols);
+    void* vd = (row_off >= 0) ? fdata + weight_data_bytes(dt, row_off, cols) : nullptr;
+    uint16_t* vs = (row_off >= 0 && fsc) ? fsc + weight_scale_bytes(dt, row_off, cols) / 2 : nullptr;
+    if (on_device) r = weight_device_view(slot, h_payload, dt, rows, cols, vd, vs);
+    else if (row_off >= 0) r = weight_upload_view(slot, h_payload, dt, rows, cols, vd, vs);
+    else r = gtb_weight_upload(slot, h_payload, dt, rows, cols);
     if (r == GTB_OK) e->weight_bytes += (*slot)->nbytes;
     return r;
 }
 
+int gtb_engine_set_weight(gtb_engine_t e, int layer, int tensor_id, const void* h_payload, size_t nbytes) {
+    return set_weight_from(e, layer, tensor_id, h_payload, nbytes, false);
+}
+
+// load_from_ckpt (tinyllama.cpp:336-392) as a pipeline: the file is mapped, every payload travels through two pinned staging
+// buffers (the memcpy out of the mapping is what pulls the pages from disk) into one of two device buffers in the gten layout,
+// and the repack kernel (gtb_api.cu) writes the device layout from there -- disk read, H2D copy and repack of consecutive
+// chunks / tensors overlap.  Record names are checked against the converter's order (tinyllama_to_gten.py:157-201).
 int gtb_engine_load_gten(gtb_engine_t e, const char* path) {
     GTB_CHECK_INIT();
     GTB_ARG(e && path);
-    std::ifstream f(path, std::ios::binary);
-    if (!f.is_open()) return fail(GTB_ERR_ARG, "cannot open %s", path);
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(GTB_ERR_ARG, "cannot open %s", path);
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || sb.st_size < 8) { close(fd); return fail(GTB_ERR_ARG, "cannot stat %s", path); }
+    const size_t fsize = (size_t)sb.st_size;
+    const uint8_t* base = static_cast<const uint8_t*>(mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0));
+    close(fd);
+    if (base == MAP_FAILED) return fail(GTB_ERR_ARG, "cannot map %s", path);
+    madvise(const_cast<uint8_t*>(base), fsize, MADV_SEQUENTIAL);
+    constexpr size_t CHUNK = 16u << 20;
+    void* pinned[2] = {nullptr, nullptr};
+    uint8_t* dtmp[2] = {nullptr, nullptr};
+    cudaEvent_t pev[2] = {nullptr, nullptr}, dev[2] = {nullptr, nullptr};
+    size_t dcap = 0;
+    cudaStream_t st = ctx().stream;
+    int r = GTB_OK, pk = 0, dk = 0;
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(st);
+        for (int i = 0; i < 2; i++) {
+            if (pinned[i]) cudaFreeHost(pinned[i]);
+            if (dtmp[i]) cudaFree(dtmp[i]);
+            if (pev[i]) cudaEventDestroy(pev[i]);
+            if (dev[i]) cudaEventDestroy(dev[i]);
+        }
+        munmap(const_cast<uint8_t*>(base), fsize);
+    };
     int64_t magic = 0;
-    f.read(reinterpret_cast<char*>(&magic), 8);
-    if (magic != 0x454c49464e455447LL) return fail(GTB_ERR_ARG, "Magic number in the binary does not match the expected one.");
-    std::vector<char> buf;
-    auto one = [&](int layer, int tid) -> int {
-        for (int rep = 0; rep < 2; rep++) {                       // layer header, then weight name (tinyllama.cpp:301-334)
+    memcpy(&magic, base, 8);
+    if (magic != 0x454c49464e455447LL) { cleanup(); return fail(GTB_ERR_ARG, "Magic number in the binary does not match the expected one."); }
+    // the largest payload sizes the two device staging buffers
+    {
+        static const int tids[] = {GTB_T_EMBED, GTB_T_Q, GTB_T_K, GTB_T_GATE, GTB_T_DOWN, GTB_T_LM_HEAD, GTB_T_ATTN_NORM};
+        for (int t : tids) { int a, b, c; const size_t n = expect_bytes(e, t, &a, &b, &c); if (n > dcap) dcap = n; }
+    }
+    for (int i = 0; i < 2 && r == GTB_OK; i++) {
+        if (cudaMallocHost(&pinned[i], CHUNK) != cudaSuccess || cudaMalloc((void**)&dtmp[i], dcap) != cudaSuccess ||
+            cudaEventCreateWithFlags(&pev[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&dev[i], cudaEventDisableTiming) != cudaSuccess)
+            r = fail(GTB_ERR_CUDA, "loader staging buffers: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    size_t off = 8;
+    auto rd_i32 = [&](int32_t* v) -> bool { if (off + 4 > fsize) return false; memcpy(v, base + off, 4); off += 4; return true; };
+    auto one = [&](int layer, int tid, const std::string& expect_name) -> int {
+        for (int rep = 0; rep < 2; rep++) {                       // layer header, then weight name (tinyllama.cpp:301-334): both carry the tensor name
             int32_t n = 0;
-            f.read(reinterpret_cast<char*>(&n), 4);
-            if (!f || n < 0 || n > 4096) return fail(GTB_ERR_ARG, "corrupt .gten record header");
-            f.seekg(n, std::ios::cur);
+            if (!rd_i32(&n) || n < 0 || n > 4096 || off + (size_t)n > fsize) return fail(GTB_ERR_ARG, "corrupt .gten record header");
+            if ((size_t)n != expect_name.size() || memcmp(base + off, expect_name.data(), (size_t)n) != 0)
+                return fail(GTB_ERR_ARG, "unexpected record `%.*s` where `%s` belongs: not a TinyLlama .gten file of this shape, or records out of order",
+                            n, reinterpret_cast<const char*>(base + off), expect_name.c_str());
+            off += (size_t)n;
         }
         int32_t nb = 0;
-        f.read(reinterpret_cast<char*>(&nb), 4);
-        if (!f || nb < 0) return fail(GTB_ERR_ARG, "corrupt .gten payload size");
-        buf.resize((size_t)nb);
-        f.read(buf.data(), nb);
-        if (!f) return fail(GTB_ERR_ARG, "truncated .gten file");
-        return gtb_engine_set_weight(e, layer, tid, buf.data(), (size_t)nb);
+        if (!rd_i32(&nb) || nb < 0) return fail(GTB_ERR_ARG, "corrupt .gten payload size");
+        if (off + (size_t)nb > fsize) return fail(GTB_ERR_ARG, "truncated .gten file");
+        int rows, cols, dt;
+        const size_t expect = expect_bytes(e, tid, &rows, &cols, &dt);
+        if ((size_t)nb != expect)   // the reference's per-tensor check, tinyllama.cpp:316-319
+            return fail(GTB_ERR_ARG, "Weight `%s` data size: %d does not match the expected size: %zu.", expect_name.c_str(), nb, expect);
+        uint8_t* d = dtmp[dk];
+        GTB_CUDA(cudaEventSynchronize(dev[dk]));                // the repack that read this buffer two tensors ago is done
+        for (size_t o = 0; o < (size_t)nb; o += CHUNK) {
+            const size_t n = ((size_t)nb - o < CHUNK) ? (size_t)nb - o : CHUNK;
+            GTB_CUDA(cudaEventSynchronize(pev[pk]));            // the copy out of this pinned buffer is done
+            memcpy(pinned[pk], base + off + o, n);              // page-in from disk happens here, while the previous chunk is on the bus
+            GTB_CUDA(cudaMemcpyAsync(d + o, pinned[pk], n, cudaMemcpyHostToDevice, st));
+            GTB_CUDA(cudaEventRecord(pev[pk], st));
+            pk ^= 1;
+        }
+        off += (size_t)nb;
+        int rr = set_weight_from(e, layer, tid, d, (size_t)nb, true);
+        if (rr) return rr;
+        GTB_CUDA(cudaEventRecord(dev[dk], st));
+        dk ^= 1;
+        return GTB_OK;
     };
-    int r = one(0, GTB_T_EMBED);
-    static const int order[] = {GTB_T_Q, GTB_T_K, GTB_T_V, GTB_T_O, GTB_T_GATE, GTB_T_UP, GTB_T_DOWN, GTB_T_ATTN_NORM, GTB_T_FFN_NORM};
+    if (r == GTB_OK) r = one(0, GTB_T_EMBED, "model.embed_tokens.weight");
+    static const struct { int tid; const char* name; } order[] = {
+        {GTB_T_Q, "self_attn.q_proj.weight"}, {GTB_T_K, "self_attn.k_proj.weight"}, {GTB_T_V, "self_attn.v_proj.weight"},
+        {GTB_T_O, "self_attn.o_proj.weight"}, {GTB_T_GATE, "mlp.gate_proj.weight"}, {GTB_T_UP, "mlp.up_proj.weight"},
+        {GTB_T_DOWN, "mlp.down_proj.weight"}, {GTB_T_ATTN_NORM, "input_layernorm.weight"}, {GTB_T_FFN_NORM, "post_attention_layernorm.weight"}};
     for (int li = 0; li < e->cfg.n_layers && !r; li++)
-        for (int t : order) { r = one(li, t); if (r) break; }
-    if (!r) r = one(0, GTB_T_FINAL_NORM);
-    if (!r) r = one(0, GTB_T_LM_HEAD);
+        for (const auto& t : order) { r = one(li, t.tid, "model.layers." + std::to_string(li) + "." + t.name); if (r) break; }
+    if (!r) r = one(0, GTB_T_FINAL_NORM, "model.norm.weight");
+    if (!r) r = one(0, GTB_T_LM_HEAD, "lm_head.weight");
+    const std::string err = ctx().err;
+    cleanup();
+    if (r) ctx().err = err;
     return r;
 }
 
@@ -1709,6 +1785,7 @@ int gtb_engine_set_option(gtb_engine_t e, const char* name, int value) {
     if (!strcmp(name, "xr_min_rows")) { GTB_ARG(value >= 1); e->xr_min_rows = value; return GTB_OK; }
     if (!strcmp(name, "xr_rows")) { GTB_ARG(value >= 1 && value <= XR_MAX_ROWS); e->xr_rows = value; return GTB_OK; }
     if (!strcmp(name, "batch_exact")) { e->batch_exact = value != 0; drop_graphs(e); return GTB_OK; }
+    if (!strcmp(name, "xr_pdl")) { xr_set_pdl(value != 0); drop_graphs(e); return GTB_OK; }
     return fail(GTB_ERR_ARG, "unknown option %s", name);
 }
 

@@ -68,6 +68,9 @@ struct gtb_weight {
 namespace gtb {
 // repack a host payload into caller-provided device storage (slices of a fused buffer); *out is a non-owning view
 int weight_upload_view(gtb_weight_t* out, const void* h_payload, int dtype, int rows, int cols, void* d_data, uint16_t* d_scales);
+// repack a payload that already sits in DEVICE memory (gten layout); no synchronisation: the caller keeps d_payload alive until the
+// stream has passed the repack kernel.  d_data == nullptr: the weight owns freshly allocated storage.
+int weight_device_view(gtb_weight_t* out, const void* d_payload, int dtype, int rows, int cols, void* d_data, uint16_t* d_scales);
 inline size_t weight_data_bytes(int dtype, int rows, int cols) {
     return dtype == GTB_F16 ? (size_t)rows * cols * 2 : (size_t)rows * cols / 32 * (dtype == GTB_Q4 ? 16 : 32);
 }

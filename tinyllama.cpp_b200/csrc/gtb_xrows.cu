@@ -47,6 +47,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// programmatic dependent launch: the next kernel of the chain may start while this one drains; nothing that a predecessor wrote
+// is touched before pdl_wait()
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // store one encoded block (one code per lane) as an XBlk record
 __device__ __forceinline__ void xblk_store(XBlk* dst, int lane, int q, uint16_t dh) {
     const uint32_t qb = (uint32_t)q & 0xffu;
@@ -86,6 +91,8 @@ struct XrPlanArgs {
     XrRow* rows;
 };
 __global__ void k_xr_plan(XrPlanArgs a) {
+    pdl_launch();
+    pdl_wait();
     const int r = threadIdx.x;
     if (r >= XR_MAX_ROWS) return;
     XrRow row{-1, 0, 0, 0};
@@ -111,18 +118,24 @@ struct XrNormArgs {
     const void* emb_w; const uint16_t* emb_s; int emb_dt;   // emb_w != null: the row is the token's embedding (ops.h:514-564)
 };
 
-__global__ void __launch_bounds__(NT) k_xr_norm(XrNormArgs a) {
+constexpr int XN_NT = 512, XN_NW = XN_NT / 32;
+__global__ void __launch_bounds__(XN_NT) k_xr_norm(XrNormArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     float* xbuf = reinterpret_cast<float*>(smem);                 // [E] the row
     float* sq = xbuf + a.E;                                       // [E] its squares
     __shared__ float s_sum;
-    const int row = a.row0 + blockIdx.x;
-    const XrRow rw = a.rows[row];
-    if (rw.slot < 0) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int nb = a.E / 32;
+    const int row = a.row0 + blockIdx.x;
+    // the norm weights do not depend on the previous kernel: fetch them before waiting for it
+    float nw[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const int b = wid + u * XN_NW; nw[u] = (b < nb) ? h2f(a.normw[b * 32 + lane]) : 0.0f; }
+    pdl_wait();
+    const XrRow rw = a.rows[row];
+    if (rw.slot < 0) return;
     float* res = a.res + (size_t)row * a.E;
-    for (int b = wid; b < nb; b += NWARP) {
+    for (int b = wid; b < nb; b += XN_NW) {
         const int e = b * 32 + lane;
         float v;
         if (a.emb_w) {
@@ -168,10 +181,11 @@ __global__ void __launch_bounds__(NT) k_xr_norm(XrNormArgs a) {
         s_sum = s;
     }
     __syncthreads();
+    pdl_launch();
     const float denom = __fadd_rn(sqrtf(__fdiv_rn(s_sum, (float)a.E)), 1e-6f);
-    for (int b = wid; b < nb; b += NWARP) {
+    for (int b = wid, u = 0; b < nb; b += XN_NW, u++) {
         const int e = b * 32 + lane;
-        const float y = __fmul_rn(__fdiv_rn(xbuf[e], denom), h2f(a.normw[e]));
+        const float y = __fmul_rn(__fdiv_rn(xbuf[e], denom), (u < 4) ? nw[u] : h2f(a.normw[e]));
         uint16_t dh;
         const int q = q8_encode_lane(y, &dh);
         xblk_store(a.out + (size_t)row * nb + b, lane, q, dh);
@@ -222,7 +236,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 4) ? 4 : 2) k_xr_gemm(XrGemmAr
         int r = (EPI == XEPI_SILU) ? ((c < 32) ? 32 * n + c : a.up_off + 32 * n + c - 32) : 64 * n + c;
         return min(r, a.N - 1);
     };
-    auto load_chunk = [&](int s, int kc) {
+    auto load_weights = [&](int s, int kc) {
         XgStage<WT>& st = stages[s];
 #pragma unroll
         for (int i = tid; i < XG_BN * WPC; i += XG_NT) {
@@ -230,6 +244,9 @@ __global__ void __launch_bounds__(NW * 32, (NW == 4) ? 4 : 2) k_xr_gemm(XrGemmAr
             cp_async16(&st.wd[c][j], a.wd + ((size_t)wrow(c) * nb + (size_t)kc * XG_KC) * WB + j, true);
         }
         if (tid < XG_BN) cp_async16(&st.ws[tid], a.ws + (size_t)wrow(tid) * nb + (size_t)kc * XG_KC, true);
+    };
+    auto load_act = [&](int s, int kc) {
+        XgStage<WT>& st = stages[s];
 #pragma unroll
         for (int i = tid; i < XG_BM * XG_KC * 4; i += XG_NT) {
             const int r = i >> 5, j = i & 31;
@@ -246,15 +263,23 @@ __global__ void __launch_bounds__(NW * 32, (NW == 4) ? 4 : 2) k_xr_gemm(XrGemmAr
         for (int c = 0; c < 2; c++)
 #pragma unroll
             for (int l = 0; l < 4; l++) acc[r][c][l] = 0.0f;
+    // weights never depend on the previous kernel of the chain: their first chunks are in flight before it has finished
+#pragma unroll
+    for (int s = 0; s < XG_STAGES - 1; s++)
+        if (s < nchunk) load_weights(s, s);
+    pdl_wait();
 #pragma unroll
     for (int s = 0; s < XG_STAGES - 1; s++) {
-        if (s < nchunk) load_chunk(s, s);
+        if (s < nchunk) load_act(s, s);
         cp_async_commit();
     }
     for (int kc = 0; kc < nchunk; kc++) {
         cp_async_wait<XG_STAGES - 2>();
         __syncthreads();
-        if (kc + XG_STAGES - 1 < nchunk) load_chunk((kc + XG_STAGES - 1) % XG_STAGES, kc + XG_STAGES - 1);
+        if (kc + XG_STAGES - 1 < nchunk) {
+            load_weights((kc + XG_STAGES - 1) % XG_STAGES, kc + XG_STAGES - 1);
+            load_act((kc + XG_STAGES - 1) % XG_STAGES, kc + XG_STAGES - 1);
+        }
         cp_async_commit();
         const XgStage<WT>& st = stages[kc % XG_STAGES];
         const uint4 sA = st.ws[lane], sB = st.ws[lane + 32];
@@ -309,6 +334,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 4) ? 4 : 2) k_xr_gemm(XrGemmAr
         }
     }
     cp_async_wait<0>();
+    pdl_launch();            // the next kernel may become resident while this one runs its epilogue (not earlier: waiting CTAs hold SM resources)
     // ---------------- epilogue: lane = column inside each 32-block, warp = TR rows: every re-encode is warp-local
 #pragma unroll
     for (int r = 0; r < TR; r++) {
@@ -398,6 +424,8 @@ struct XrArgmaxArgs {
 __global__ void __launch_bounds__(128) k_xr_argmax(XrArgmaxArgs a) {
     __shared__ float sv[4];
     __shared__ int si[4];
+    pdl_launch();
+    pdl_wait();
     const int row = a.row0 + blockIdx.x;
     const XrRow rw = a.rows[row];
     if (rw.slot < 0) return;
@@ -462,6 +490,7 @@ __global__ void __launch_bounds__(XA_NT) k_xr_attn(XrAttnArgs a) {
     float (*ob)[64] = reinterpret_cast<float (*)[64]>(u + 16384 + XA_VT * XA_VP * 4);
     float* sums = reinterpret_cast<float*>(u + 16384 + XA_VT * XA_VP * 4 + 8 * 64 * 4);
     const int g = blockIdx.x, row = a.row0 + blockIdx.y;
+    pdl_wait();
     const XrRow rw = a.rows[row];
     if (rw.slot < 0) return;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -594,6 +623,7 @@ __global__ void __launch_bounds__(XA_NT) k_xr_attn(XrAttnArgs a) {
         i0_last = i0;
         if (i0 + XA_VT < t) __syncthreads();
     }
+    pdl_launch();
 #pragma unroll
     for (int uu = 0; uu < 2; uu++)
 #pragma unroll
@@ -617,6 +647,12 @@ __global__ void __launch_bounds__(XA_NT) k_xr_attn(XrAttnArgs a) {
 }
 
 // ---------------------------------------------------------------- host side
+// Programmatic dependent launch between the kernels of a pass.  Measured (tools/xrows_probe.py --pdl 0/1, same box): it helps the
+// latency-bound small passes (8 rows: 2.66 vs 2.76 ms per step) and costs 17 % on full ones (64 rows: 4.58 vs 3.91 ms: the early
+// resident CTAs of the next kernel take SM resources from the tail of the running one), so it is used for passes of <= 16 rows.
+static bool g_xr_pdl = true;
+static bool g_xr_pdl_now = false;
+
 struct XrPlan {
     gtb_model_config cfg{};
     XrRow* rows = nullptr;
@@ -628,6 +664,8 @@ struct XrPlan {
     int n_tiles = 0;
     size_t bytes = 0;
 };
+
+void xr_set_pdl(bool on) { g_xr_pdl = on; }
 
 bool xr_supported(const gtb_model_config& c, int gsz) {
     return (c.wdtype == GTB_Q8 || c.wdtype == GTB_Q4) && gsz == 8 && c.n_embd % 256 == 0 && c.n_ffn % 256 == 0 && c.n_embd / c.n_heads == 64 &&
@@ -670,6 +708,17 @@ void xr_destroy(XrPlan* p) {
 
 namespace {
 
+template <typename... KArgs, typename... Args>
+cudaError_t xr_launch(void (*kern)(KArgs...), dim3 grid, int block, size_t smem, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = ctx().stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_xr_pdl_now ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 template <int WT, int EPI, int NW>
 int launch_gemm_nw(const XrGemmArgs& a, int n_tiles) {
     const size_t smem = sizeof(XgStage<WT>) * XG_STAGES;
@@ -679,7 +728,7 @@ int launch_gemm_nw(const XrGemmArgs& a, int n_tiles) {
         attr = true;
     }
     dim3 grid(n_tiles, (a.n_rows + XG_BM - 1) / XG_BM);
-    k_xr_gemm<WT, EPI, NW><<<grid, NW * 32, smem, ctx().stream>>>(a);
+    GTB_CUDA(xr_launch(k_xr_gemm<WT, EPI, NW>, grid, NW * 32, smem, a));
     GTB_LAUNCHED();
     return GTB_OK;
 }
@@ -696,8 +745,8 @@ int run_pass(XrPlan* p, const XrModel& m, const XrKV& kv, const XrSeq& sq, const
              int head_rows, int eos_id, float* d_logits) {
     const gtb_model_config& c = m.cfg;
     const int E = c.n_embd, F = c.n_ffn, KVD = 64 * c.n_groups, R = plan.n_rows;
-    cudaStream_t st = ctx().stream;
-    k_xr_plan<<<1, XR_MAX_ROWS, 0, st>>>(plan);
+    g_xr_pdl_now = g_xr_pdl && R <= 16;
+    GTB_CUDA(xr_launch(k_xr_plan, dim3(1), XR_MAX_ROWS, 0, plan));
     GTB_LAUNCHED();
     const size_t norm_smem = (size_t)E * 8;
     const size_t attn_smem = xr_attn_smem(t_cap);
@@ -712,7 +761,7 @@ int run_pass(XrPlan* p, const XrModel& m, const XrKV& kv, const XrSeq& sq, const
         XrNormArgs a{};
         a.rows = p->rows; a.row0 = row0; a.res = p->res; a.normw = w; a.out = p->act_norm; a.E = E;
         if (emb) { a.emb_w = m.emb_w; a.emb_s = m.emb_s; a.emb_dt = (c.wdtype == GTB_Q8) ? DT_Q8 : DT_Q4; }
-        k_xr_norm<<<rows, NT, norm_smem, st>>>(a);
+        GTB_CUDA(xr_launch(k_xr_norm, dim3(rows), XN_NT, norm_smem, a));
         GTB_LAUNCHED();
         return GTB_OK;
     };
@@ -735,7 +784,7 @@ int run_pass(XrPlan* p, const XrModel& m, const XrKV& kv, const XrSeq& sq, const
             a.rows = p->rows; a.row0 = 0; a.qst = p->qst; a.kq = kv.kq[li]; a.ks = kv.ks[li]; a.vq = kv.vq[li]; a.vs = kv.vs[li];
             a.slot_codes = kv.slot_codes; a.slot_scales = kv.slot_scales; a.kv_dim = KVD; a.n_heads = c.n_heads;
             a.out = p->act_attn; a.out_nb = E / 32; a.t_cap = t_cap;
-            k_xr_attn<<<dim3(c.n_groups, R), XA_NT, attn_smem, st>>>(a);
+            GTB_CUDA(xr_launch(k_xr_attn, dim3(c.n_groups, R), XA_NT, attn_smem, a));
             GTB_LAUNCHED();
         }
         {
@@ -768,7 +817,7 @@ int run_pass(XrPlan* p, const XrModel& m, const XrKV& kv, const XrSeq& sq, const
         XrArgmaxArgs g{};
         g.rows = p->rows; g.row0 = head_row0; g.arg_val = p->arg_val; g.arg_idx = p->arg_idx; g.n_tiles = p->n_tiles;
         g.tokens = sq.tokens; g.tok_stride = sq.tok_stride; g.st = sq.st; g.eos_id = eos_id;
-        k_xr_argmax<<<head_rows, 128, 0, st>>>(g);
+        GTB_CUDA(xr_launch(k_xr_argmax, dim3(head_rows), 128, 0, g));
         GTB_LAUNCHED();
     }
     return GTB_OK;

@@ -47,6 +47,7 @@ constexpr int XR_MAX_ROWS = 64;        // rows per pass
 int xr_create(XrPlan** out, const gtb_model_config& cfg);
 void xr_destroy(XrPlan* p);
 bool xr_supported(const gtb_model_config& cfg, int gsz);
+void xr_set_pdl(bool on);            // programmatic dependent launch inside a pass (default on)
 
 // Prefill pass: rows = positions [p0, p0 + n_rows) of slot `slot`; n_ctx = the call's row count (P.V lane split, SURVEY
 // App. A).  with_head: the LAST row also runs final norm + lm_head + argmax, appends the token and advances the slot.

@@ -27,12 +27,14 @@ def main():
     ap.add_argument("--skip-prefill", action="store_true")
     ap.add_argument("--adopt", action="store_true", help="one prefill on the engine's own sequence, copied into every slot (few launches: for ncu)")
     ap.add_argument("--prefill-reps", type=int, default=2)
+    ap.add_argument("--pdl", type=int, default=1)
     args = ap.parse_args()
     wdt = W.WDTYPE_BY_NAME[args.wdt if args.wdt != "f16" else "fp16"]
     capi.init(0)
     cfg = W.TINYLLAMA
     eng = capi.Engine(cfg, args.max_ctx, wdt).load(W.synth_weights(cfg, wdt, seed=1))
     out = {}
+    eng.set_option("xr_pdl", args.pdl)
     if not args.skip_prefill:
         prompt = W.synth_prompt(7, args.prompt, cfg.n_vocab)
         if args.prefill_reps > 1:
