@@ -230,44 +230,38 @@ __device__ __forceinline__ void stage_quad(const ActView& av, const float x[4]) 
 }
 
 // ---------------------------------------------------------------- exact in-order sum, 512 threads x 4 elements per pass
-// Same algorithm as exact_sum_block (gtb_dev.cuh), restructured: cross-warp prefixes are 16-lane shuffle scans,
-// four barriers per pass, the serial resolve reads its items with 128-bit loads.
-// branch-free map of "add t to a running sum whose binade is e" (e >= exponent of t; t normal, or zero -> identity)
-__device__ __forceinline__ PMap pmap_of2(float tv, int e) {
-    const uint32_t tb = __float_as_uint(tv);
-    const int sh = min(e - ((int)(tb >> 23) - 127), 25);
-    const uint32_t mt = (tb & 0x7fffffu) | 0x800000u;
-    const uint32_t k = mt >> sh;
-    const uint32_t rem2 = (mt & ((1u << sh) - 1u)) << 1, full = 1u << sh;
-    const uint32_t up = rem2 > full ? 1u : 0u, tie = rem2 == full ? 1u : 0u;
-    PMap m;
-    m.a = k + (up | (tie & k & 1u));
-    m.b = k + (up | (tie & ~k & 1u));
-    return m;
-}
-
 constexpr int ES2_MAXEXP = 96;
 struct ExactSum2Smem {
     float wsum[MWARP];
-    PMap wtail[MWARP];
-    int wflag[MWARP];
-    int wcnt[MWARP];
-    uint4 item[2 * ES2_MAXEXP + 2];       // {a, b, type, -}
+    uint32_t wint[MWARP];                 // per-warp totals of the integer increments
+    int wcnt[MWARP];                      // per-warp counts of explicit elements
+    uint2 item[ES2_MAXEXP + 1];           // {integer prefix at the element, term bits}, in element order
     float result;
 };
 
 struct NoSpill { __device__ __forceinline__ void operator()() const {} };
 
-// load4(i, q): the four terms starting at element i (i % 4 == 0; elements >= n come back as 0).  In the normal path
-// every thread asks only for its own i = 4 * tid (+ pass offset); the serial fallback makes thread 0 ask for every i,
-// so a caller that keeps its terms in registers passes `spill`, which writes them where load4 can find them.
+// In-order fp32 sum of non-negative terms, emulated exactly in parallel.
+//
+// While the running sum s stays inside one binade (ulp u), adding a term t is an integer step on the BIT PATTERN of s:
+// bits(s) += floor(t / u) + (remainder > u/2).  Every term whose step is of that kind ("plain") contributes an integer that does
+// not depend on s, so the plain terms between two special ones contribute the DIFFERENCE of one integer prefix sum -- a single
+// 32-bit add scan over the CTA, no per-element state.  Special ("explicit") terms are applied as real float adds, in order, by
+// one thread: those adjacent to a power-of-two crossing of the running sum (located by an approximate fp32 prefix sum with a
+// proven allowance, see below), exact ties (remainder == u/2: round-to-even depends on s), terms larger than the sum, denormals.
+// A 2048-term sum has 13-42 explicit terms; more than ES2_MAXEXP falls back to the plain serial chain.
+//
+// load4(i, q): the four terms starting at element i (i % 4 == 0; elements >= n come back as 0).  In the normal path every thread
+// asks only for its own i = 4 * tid (+ pass offset); the serial fallback makes thread 0 ask for every i, so a caller that keeps
+// its terms in registers passes `spill`, which writes them where load4 can find them.
 template <typename LoadT, typename SpillT = NoSpill>
 __device__ __forceinline__ float exact_sum512(LoadT load4, int n, ExactSum2Smem& sm, SpillT spill = SpillT()) {
-    // No FP64 here: the prefix sums that locate the running sum's binade are plain fp32 scans.  Terms are
-    // non-negative, so a sum taken through any addition tree of depth d is within d * 2^-24 (relative) of the exact
-    // one (d <= 16 here), and the strictly sequential chain being emulated is within k * 2^-24 of exact after k
-    // terms; the allowance below, (4k + 64) * 2^-24, covers both with room to spare.
+    // No FP64 here: the prefix sums that locate the running sum's binade are plain fp32 scans.  Terms are non-negative, so a sum
+    // taken through any addition tree of depth d is within d * 2^-24 (relative) of the exact one (d <= 16 here), and the strictly
+    // sequential chain being emulated is within k * 2^-24 of exact after k terms; the allowance below, (4k + 64) * 2^-24, covers
+    // both with room to spare: a plain term's running sum provably stays in the binade its increment was computed for.
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     float s_run = 0.0f;
     float carry = 0.0f;
     for (int p0 = 0; p0 < n; p0 += MT * 4) {
@@ -287,99 +281,54 @@ __device__ __forceinline__ float exact_sum512(LoadT load4, int n, ExactSum2Smem&
         const float wbase = __shfl_sync(0xffffffffu, ws, (wid + 31) & 31);       // inclusive total of warp wid-1
         const float total_f = __shfl_sync(0xffffffffu, ws, MWARP - 1);
         float A = __fadd_rn(__fadd_rn(carry, (wid > 0) ? wbase : 0.0f), (lane > 0) ? lane_pre : 0.0f);
-        PMap em[4];
+        // classify: integer increment of a plain term, or explicit
+        uint32_t pre[5];                                   // pre[j] = increments of this thread's elements before element j
+        pre[0] = 0u;
         uint32_t exmask = 0;
-        {
-            // fast path: the running sum stays inside one binade from before the first to after the last of the four
-            const float rel4 = (float)(i0 + 20) * 0x1p-22f;
-            const float A4 = __fadd_rn(A, loc);
-            const float lo4 = __fsub_rn(A, __fmul_rn(A, rel4)), hi4 = __fadd_rn(A4, __fmul_rn(A4, rel4));
-            const int eL4 = (int)(__float_as_uint(lo4) >> 23) - 127;
-            bool fast = (lo4 > 0x1p-100f) && (eL4 == (int)(__float_as_uint(hi4) >> 23) - 127);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t tb = __float_as_uint(tv[j]);
-                if (tv[j] != 0.0f && ((tb >> 23) == 0u || ((int)(tb >> 23) - 127) > eL4)) fast = false;
-            }
-            if (fast) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) em[j] = pmap_of2(tv[j], eL4);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float An = __fadd_rn(A, tv[j]);
-                    em[j] = PMap{0u, 0u};
-                    if (tv[j] != 0.0f) {
-                        const float rel = (float)(i0 + j + 16) * 0x1p-22f;
-                        const float lo = __fsub_rn(A, __fmul_rn(A, rel)), hi = __fadd_rn(An, __fmul_rn(An, rel));
-                        const int eL = (int)(__float_as_uint(lo) >> 23) - 127, eU = (int)(__float_as_uint(hi) >> 23) - 127;
-                        const uint32_t tb = __float_as_uint(tv[j]);
-                        const bool ex = !(lo > 0x1p-100f) || eL != eU || (tb >> 23) == 0u || ((int)(tb >> 23) - 127) > eL;
-                        if (ex) exmask |= 1u << j;
-                        else em[j] = pmap_of2(tv[j], eL);
-                    }
-                    A = An;
-                }
-            }
-        }
-        const int nexp = __popc(exmask);
-        // per-thread pieces: maps between explicit elements
-        PMap cur{0u, 0u}, head{0u, 0u};
-        PMap mids[3] = {PMap{0u, 0u}, PMap{0u, 0u}, PMap{0u, 0u}};
-        int ne = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            if (exmask & (1u << j)) {
-                if (ne == 0) head = cur;
-                else if (ne == 1) mids[0] = cur;
-                else if (ne == 2) mids[1] = cur;
-                else mids[2] = cur;
-                cur = PMap{0u, 0u};
-                ne++;
-            } else {
-                cur = pmap_compose(cur, em[j]);
+            const float An = __fadd_rn(A, tv[j]);
+            uint32_t add = 0u;
+            if (tv[j] != 0.0f) {
+                const float rel = (float)(i0 + j + 16) * 0x1p-22f;
+                const float lo = __fsub_rn(A, __fmul_rn(A, rel)), hi = __fadd_rn(An, __fmul_rn(An, rel));
+                const int eL = (int)(__float_as_uint(lo) >> 23) - 127, eU = (int)(__float_as_uint(hi) >> 23) - 127;
+                const uint32_t tb = __float_as_uint(tv[j]);
+                const int te = (int)(tb >> 23) - 127;
+                bool ex = !(lo > 0x1p-100f) || eL != eU || (tb >> 23) == 0u || te > eL;
+                if (!ex) {
+                    const int sh = min(eL - te, 25);
+                    const uint32_t mt = (tb & 0x7fffffu) | 0x800000u;
+                    const uint32_t rem2 = (mt & ((1u << sh) - 1u)) << 1, full = 1u << sh;
+                    if (rem2 == full && sh > 0) ex = true;                     // exact tie: round-to-even depends on the running sum
+                    else add = (mt >> sh) + (rem2 > full ? 1u : 0u);
+                }
+                if (ex) exmask |= 1u << j;
             }
+            pre[j + 1] = pre[j] + add;
+            A = An;
         }
-        // warp scans: explicit count (inclusive) and segmented composition of the tails
-        int cinc = nexp;
-        PMap sc = cur;
-        int fl = (ne > 0) ? 1 : 0;
+        // one integer add scan over the CTA (wrap-around is harmless: only differences are used) + ranks of the explicit terms
+        uint32_t pinc = pre[4];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int cv = __shfl_up_sync(0xffffffffu, cinc, o);
-            const uint32_t pa = __shfl_up_sync(0xffffffffu, sc.a, o);
-            const uint32_t pb = __shfl_up_sync(0xffffffffu, sc.b, o);
-            const int pf = __shfl_up_sync(0xffffffffu, fl, o);
-            if (lane >= o) {
-                cinc += cv;
-                if (!fl) sc = pmap_compose(PMap{pa, pb}, sc);
-                fl |= pf;
-            }
-        }
-        if (lane == 31) { sm.wcnt[wid] = cinc; sm.wtail[wid] = sc; sm.wflag[wid] = fl; }
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, pinc, o); if (lane >= o) pinc += v; }
+        const uint32_t b0 = __ballot_sync(0xffffffffu, exmask & 1u), b1 = __ballot_sync(0xffffffffu, exmask & 2u);
+        const uint32_t b2 = __ballot_sync(0xffffffffu, exmask & 4u), b3 = __ballot_sync(0xffffffffu, exmask & 8u);
+        const int rank_w = __popc(b0 & lt_mask) + __popc(b1 & lt_mask) + __popc(b2 & lt_mask) + __popc(b3 & lt_mask);
+        if (lane == 31) { sm.wint[wid] = pinc; sm.wcnt[wid] = __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3); }
         __syncthreads();                                   // (2)
+        uint32_t wi = (lane < MWARP) ? sm.wint[lane] : 0u;
         int wc = (lane < MWARP) ? sm.wcnt[lane] : 0;
-        PMap wt = (lane < MWARP) ? sm.wtail[lane] : PMap{0u, 0u};
-        int wf = (lane < MWARP) ? sm.wflag[lane] : 0;
 #pragma unroll
         for (int o = 1; o < MWARP; o <<= 1) {
-            const int cv = __shfl_up_sync(0xffffffffu, wc, o);
-            const uint32_t pa = __shfl_up_sync(0xffffffffu, wt.a, o);
-            const uint32_t pb = __shfl_up_sync(0xffffffffu, wt.b, o);
-            const int pf = __shfl_up_sync(0xffffffffu, wf, o);
-            if (lane >= o) {
-                wc += cv;
-                if (!wf) wt = pmap_compose(PMap{pa, pb}, wt);
-                wf |= pf;
-            }
+            const uint32_t vi = __shfl_up_sync(0xffffffffu, wi, o);
+            const int vc = __shfl_up_sync(0xffffffffu, wc, o);
+            if (lane >= o) { wi += vi; wc += vc; }
         }
+        const uint32_t ibase = ((wid > 0) ? __shfl_sync(0xffffffffu, wi, (wid + 31) & 31) : 0u) + pinc - pre[4];
+        const int cbase = ((wid > 0) ? __shfl_sync(0xffffffffu, wc, (wid + 31) & 31) : 0) + rank_w;
+        const uint32_t itotal = __shfl_sync(0xffffffffu, wi, MWARP - 1);
         const int total = __shfl_sync(0xffffffffu, wc, MWARP - 1);
-        const int cb_w = __shfl_sync(0xffffffffu, wc, (wid + 31) & 31);
-        const uint32_t wpa = __shfl_sync(0xffffffffu, wt.a, (wid + 31) & 31);
-        const uint32_t wpb = __shfl_sync(0xffffffffu, wt.b, (wid + 31) & 31);
-        const int cbase = ((wid > 0) ? cb_w : 0) + cinc - nexp;
-        // composition of everything since the last explicit element before this warp
-        const PMap wpre = (wid > 0) ? PMap{wpa, wpb} : PMap{0u, 0u};
         if (total > ES2_MAXEXP) {                          // pathological input: plain serial chain (still exact)
             spill();
             __syncthreads();
@@ -400,55 +349,34 @@ __device__ __forceinline__ float exact_sum512(LoadT load4, int n, ExactSum2Smem&
             __syncthreads();
             continue;
         }
-        const PMap incl = fl ? sc : pmap_compose(wpre, sc);
-        const uint32_t ea = __shfl_up_sync(0xffffffffu, incl.a, 1), eb = __shfl_up_sync(0xffffffffu, incl.b, 1);
-        const PMap excl = (lane == 0) ? wpre : PMap{ea, eb};
-        if (ne > 0) {
-            const PMap r = pmap_compose(excl, head);
-            sm.item[2 * cbase] = make_uint4(r.a, r.b, 0u, 0u);
-            int k = 0;
+        if (exmask) {
+            int k = cbase;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (exmask & (1u << j)) {
-                    sm.item[2 * (cbase + k) + 1] = make_uint4(__float_as_uint(tv[j]), 0u, 1u, 0u);
-                    if (k == 1) sm.item[2 * (cbase + 1)] = make_uint4(mids[0].a, mids[0].b, 0u, 0u);
-                    else if (k == 2) sm.item[2 * (cbase + 2)] = make_uint4(mids[1].a, mids[1].b, 0u, 0u);
-                    else if (k == 3) sm.item[2 * (cbase + 3)] = make_uint4(mids[2].a, mids[2].b, 0u, 0u);
-                    k++;
-                }
-            }
+            for (int j = 0; j < 4; j++)
+                if (exmask & (1u << j)) sm.item[k++] = make_uint2(ibase + pre[j], __float_as_uint(tv[j]));
         }
-        if (tid == MT - 1) sm.item[2 * total] = make_uint4(incl.a, incl.b, 0u, 0u);
         __syncthreads();                                   // (3)
         if (tid == 0) {
-            // items alternate: map, explicit element, map, ..., map
-            uint32_t sb = __float_as_uint(s_run);
-            {
-                const uint4 m0 = sm.item[0];
-                sb += (sb & 1u) ? m0.y : m0.x;
-            }
+            uint32_t sb = __float_as_uint(s_run), prev = 0u;
             int k = 0;
             for (; k + 4 <= total; k += 4) {
-                uint32_t tt[4];
-                uint2 mm[4];
+                uint2 it[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) it[u] = sm.item[k + u];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    tt[u] = sm.item[2 * (k + u) + 1].x;
-                    const uint4 m = sm.item[2 * (k + u) + 2];
-                    mm[u] = make_uint2(m.x, m.y);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    sb = __float_as_uint(__fadd_rn(__uint_as_float(sb), __uint_as_float(tt[u])));
-                    sb += (sb & 1u) ? mm[u].y : mm[u].x;
+                    sb += it[u].x - prev;                  // the plain terms since the previous explicit one
+                    prev = it[u].x;
+                    sb = __float_as_uint(__fadd_rn(__uint_as_float(sb), __uint_as_float(it[u].y)));
                 }
             }
             for (; k < total; k++) {
-                const uint32_t t1 = sm.item[2 * k + 1].x;
-                const uint4 m = sm.item[2 * k + 2];
-                sb = __float_as_uint(__fadd_rn(__uint_as_float(sb), __uint_as_float(t1)));
-                sb += (sb & 1u) ? m.y : m.x;
+                const uint2 it = sm.item[k];
+                sb += it.x - prev;
+                prev = it.x;
+                sb = __float_as_uint(__fadd_rn(__uint_as_float(sb), __uint_as_float(it.y)));
             }
+            sb += itotal - prev;
             sm.result = __uint_as_float(sb);
         }
         __syncthreads();                                   // (4)
