@@ -85,7 +85,9 @@ __device__ __forceinline__ float f16_roundtrip(float x) { return h2f(f2h(x)); }
 // ---------------------------------------------------------------- glibc 2.39 expf (sysdeps/ieee754/flt-32/e_expf.c,
 // FMA ifunc variant).  Verified over all 2^32 inputs against the host libm by tests/test_expf_gpu.py (gtb_selftest_expf):
 // the range reduction is r = fma(InvLn2N, x, -kd); the polynomial uses fused steps.
-__constant__ uint64_t c_exp2f_tab[32] = {
+// In global memory, read through the L1 (ld.global.nc): the index differs per lane, and a __constant__ table would serialise the
+// up to 32 distinct addresses of a warp (measured in k_mega: 4 expf per thread cost 1.5 us with the constant-bank table).
+static __device__ const uint64_t c_exp2f_tab[32] = {
     0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
     0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
     0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
@@ -115,7 +117,7 @@ __device__ __forceinline__ float expf_glibc(float x) {
     const uint64_t ki = (uint64_t)__double_as_longlong(kd);
     kd = __dadd_rn(kd, -SHIFT);
     const double r = fma(InvLn2N, xd, -kd);
-    uint64_t t = c_exp2f_tab[ki & 31u];
+    uint64_t t = __ldg(&c_exp2f_tab[ki & 31u]);
     t += ki << 47;
     const double s = __longlong_as_double((long long)t);
     const double p = fma(C0, r, C1);

@@ -247,6 +247,24 @@ __global__ void __launch_bounds__(1024) k_argmax_advance(const float* __restrict
 }
 
 __global__ void k_advance(DevState* st) { st->pos += 1; }
+// rows [p0, p1) of a layer's natural K/V rows -> the chunk-major copies k_mega reads (one 16-byte chunk per thread; the thread
+// of chunk c < 2 * n_groups also moves one scale of each cache)
+__global__ void k_kv_transpose(const uint8_t* __restrict__ kq, const uint8_t* __restrict__ vq, const uint16_t* __restrict__ ks,
+                               const uint16_t* __restrict__ vs, uint8_t* __restrict__ kqt, uint8_t* __restrict__ vqt,
+                               uint16_t* __restrict__ kst, uint16_t* __restrict__ vst, int p0, int p1, int max_ctx, int n_groups) {
+    const int cpr = n_groups * 4;                                  // 16-byte chunks per row
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)(p1 - p0) * cpr) return;
+    const int pos = p0 + (int)(i / cpr), c = (int)(i % cpr);
+    const size_t src = ((size_t)pos * cpr + c) * 16;
+    *reinterpret_cast<uint4*>(kqt + ((size_t)c * max_ctx + pos) * 16) = *reinterpret_cast<const uint4*>(kq + src);
+    *reinterpret_cast<uint4*>(vqt + ((size_t)c * max_ctx + pos) * 16) = *reinterpret_cast<const uint4*>(vq + src);
+    if (c < 2 * n_groups) {
+        kst[(size_t)c * max_ctx + pos] = ks[(size_t)pos * 2 * n_groups + c];
+        vst[(size_t)c * max_ctx + pos] = vs[(size_t)pos * 2 * n_groups + c];
+    }
+}
+
 __global__ void k_set_pos(DevState* st, int pos) { st->pos = pos; }     // stream-ordered, everything else untouched
 
 // The k largest logits and their token ids, largest first, ties to the lower id (the candidate set of topk_sample,
@@ -317,6 +335,8 @@ struct LayerW {
     uint16_t* ffn_norm = nullptr;
     uint8_t *kq = nullptr, *vq = nullptr;
     uint16_t *ks = nullptr, *vs = nullptr;
+    uint8_t *kqt = nullptr, *vqt = nullptr;      // chunk-major copies of the Q8 K/V codes and scales for k_mega (gtb_mega.cuh: MegaLayer)
+    uint16_t *kst = nullptr, *vst = nullptr;
     // q|k|v and gate|up live in one buffer each so that a GEMV phase of the persistent kernel streams ONE matrix
     uint8_t *qkv_data = nullptr, *gu_data = nullptr;
     uint16_t *qkv_sc = nullptr, *gu_sc = nullptr;
@@ -346,6 +366,8 @@ struct gtb_engine {
     int g_eos = -2;
     int grid = 0;
     int host_pos = 0;
+    int kvt_pos = 0;                 // positions [0, kvt_pos) of the transposed K/V copies are current
+    long long mega_rows = 0;         // rows run by k_mega since the exchange buffers were last cleared (epoch tags are 32-bit)
     size_t weight_bytes = 0;
     int launches_body = 0, launches_head = 0;
     // persistent megakernel (gtb_mega.cuh)
@@ -893,8 +915,32 @@ int launch_mega(gtb_engine* e, MegaParams& p) {
     return GTB_OK;
 }
 
-int run_rows_mega(gtb_engine* e, int n_body, int n_head, int eos_id) {
+int run_rows_mega(gtb_engine* e, int n_body, int n_head, int eos_id, int start_pos) {
     const gtb_model_config& c = e->cfg;
+    if (e->adtype == GTB_Q8) {
+        // rows [kvt_pos, start_pos) were appended by other kernels (multi-row prefill, tensor-core prefill, ...): bring the copies up to date
+        if (e->kvt_pos < start_pos) {
+            const int n = start_pos - e->kvt_pos, cpr = c.n_groups * 4;
+            for (auto& l : e->L) {
+                k_kv_transpose<<<(unsigned)(((size_t)n * cpr + 255) / 256), 256, 0, ctx().stream>>>(l.kq, l.vq, l.ks, l.vs, l.kqt, l.vqt, l.kst, l.vst, e->kvt_pos, start_pos, c.max_ctx, c.n_groups);
+                GTB_LAUNCHED();
+            }
+        }
+        e->kvt_pos = start_pos + n_body + n_head;      // this launch maintains them for the rows it appends
+    }
+    // The exchange words carry a 32-bit epoch tag that advances < 200 per row; long before it could wrap (tag 0 = "never
+    // written") the buffers and the epoch are cleared.  ~10^7 rows apart: hours of decoding.
+    e->mega_rows += n_body + n_head;
+    if (e->mega_rows > (1ll << 31) / 256) {
+        cudaStream_t st = ctx().stream;
+        const size_t E = c.n_embd, F = c.n_ffn, KV = e->kv_dim;
+        GTB_CUDA(cudaStreamSynchronize(st));
+        GTB_CUDA(cudaMemsetAsync(e->x_qkv, 0, (E + 2 * KV) * 8, st)); GTB_CUDA(cudaMemsetAsync(e->x_sc, 0, (size_t)c.n_heads * e->sc_stride * 8, st));
+        GTB_CUDA(cudaMemsetAsync(e->x_attn, 0, E * 8, st)); GTB_CUDA(cudaMemsetAsync(e->x_o, 0, E * 8, st)); GTB_CUDA(cudaMemsetAsync(e->x_gu, 0, 2 * F * 8, st));
+        GTB_CUDA(cudaMemsetAsync(e->x_act, 0, (F / 32) * 16 * 8, st)); GTB_CUDA(cudaMemsetAsync(e->x_down, 0, E * 8, st));
+        GTB_CUDA(cudaMemsetAsync(e->x_arg, 0, (size_t)2 * 1024 * 8, st)); GTB_CUDA(cudaMemsetAsync(e->epoch, 0, 16, st));
+        e->mega_rows = n_body + n_head;
+    }
     if (!e->layers_valid) {
         std::vector<MegaLayer> h(c.n_layers);
         for (int i = 0; i < c.n_layers; i++) {
@@ -904,7 +950,7 @@ int run_rows_mega(gtb_engine* e, int n_body, int n_head, int eos_id) {
             h[i].w[2] = (const uint4*)l.gu_data; h[i].s[2] = l.gu_sc;
             h[i].w[3] = (const uint4*)l.down->data; h[i].s[3] = l.down->scales;
             h[i].attn_norm = l.attn_norm; h[i].ffn_norm = l.ffn_norm;
-            h[i].kq = l.kq; h[i].ks = l.ks; h[i].vq = l.vq; h[i].vs = l.vs;
+            h[i].kq = l.kq; h[i].ks = l.ks; h[i].vq = l.vq; h[i].vs = l.vs; h[i].kqt = l.kqt; h[i].vqt = l.vqt; h[i].kst = l.kst; h[i].vst = l.vst;
         }
         GTB_CUDA(cudaMemcpyAsync(e->d_layers, h.data(), h.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice, ctx().stream));
         GTB_CUDA(cudaStreamSynchronize(ctx().stream));
@@ -980,6 +1026,8 @@ int set_pos(gtb_engine* e, int pos);
 int run_rows(gtb_engine* e, int n_body, int n_head, int eos_id, int p0 = -1, int n_ctx = 0) {
     cudaStream_t st = ctx().stream;
     if (n_body + n_head <= 0) return GTB_OK;
+    int start = (p0 >= 0) ? p0 : e->host_pos;              // first row of this call
+    if (start < e->kvt_pos) e->kvt_pos = start;            // rows >= start are rewritten: k_mega's K/V copies end there
     if (p0 >= 0 && xr_ok(e) && n_body + (n_head > 0 ? 1 : 0) >= e->xr_min_rows) {
         // the prompt rows (and the first sampling row) side by side, bit-identical to the row-at-a-time kernels
         const int nx = n_body + (n_head > 0 ? 1 : 0);
@@ -987,9 +1035,10 @@ int run_rows(gtb_engine* e, int n_body, int n_head, int eos_id, int p0 = -1, int
         if (r) return r;
         if (n_head == 0) return set_pos(e, p0 + n_body);       // no sampling row: only the position moves
         n_body = 0; n_head -= 1;
+        start += nx;
         if (n_head == 0) return GTB_OK;
     }
-    if (mega_ok(e)) return run_rows_mega(e, n_body, n_head, eos_id);
+    if (mega_ok(e)) return run_rows_mega(e, n_body, n_head, eos_id, start);
     if (fast_mega_ok(e)) return run_rows_fast_mega(e, n_body, n_head, eos_id);
     if (e->use_graph && !e->capture) {
         if (n_body > 0 && !e->g_body) { int r = build_graph(e, false, -1, &e->g_body, &e->launches_body); if (r) return r; }
@@ -1071,7 +1120,11 @@ int gtb_engine_create(gtb_engine_t* out, const gtb_model_config* cfg) {
     for (auto& l : e->L) {
         const size_t code_bytes = (size_t)MC * KV * (e->adtype == GTB_F16 ? 2 : 1);
         r |= dalloc((void**)&l.kq, code_bytes); r |= dalloc((void**)&l.vq, code_bytes);
-        if (e->adtype == GTB_Q8) { r |= dalloc((void**)&l.ks, (size_t)MC * (KV / 32) * 2); r |= dalloc((void**)&l.vs, (size_t)MC * (KV / 32) * 2); }
+        if (e->adtype == GTB_Q8) {
+            r |= dalloc((void**)&l.ks, (size_t)MC * (KV / 32) * 2); r |= dalloc((void**)&l.vs, (size_t)MC * (KV / 32) * 2);
+            r |= dalloc((void**)&l.kqt, code_bytes); r |= dalloc((void**)&l.vqt, code_bytes);
+            r |= dalloc((void**)&l.kst, (size_t)MC * (KV / 32) * 2); r |= dalloc((void**)&l.vst, (size_t)MC * (KV / 32) * 2);
+        }
         r |= dalloc((void**)&l.attn_norm, (size_t)E * 2); r |= dalloc((void**)&l.ffn_norm, (size_t)E * 2);
         r |= dalloc((void**)&l.qkv_data, weight_data_bytes(cfg->wdtype, E + 2 * KV, E));
         r |= dalloc((void**)&l.gu_data, weight_data_bytes(cfg->wdtype, 2 * F, E));
@@ -1136,7 +1189,7 @@ int gtb_engine_destroy(gtb_engine_t e) {
     for (auto& l : e->L) {
         gtb_weight_free(l.q); gtb_weight_free(l.k); gtb_weight_free(l.v); gtb_weight_free(l.o);
         gtb_weight_free(l.gate); gtb_weight_free(l.up); gtb_weight_free(l.down);
-        cudaFree(l.attn_norm); cudaFree(l.ffn_norm); cudaFree(l.kq); cudaFree(l.vq); cudaFree(l.ks); cudaFree(l.vs);
+        cudaFree(l.attn_norm); cudaFree(l.ffn_norm); cudaFree(l.kq); cudaFree(l.vq); cudaFree(l.ks); cudaFree(l.vs); cudaFree(l.kqt); cudaFree(l.vqt); cudaFree(l.kst); cudaFree(l.vst);
         cudaFree(l.qkv_data); cudaFree(l.gu_data); cudaFree(l.qkv_sc); cudaFree(l.gu_sc);
     }
     gtb_weight_free(e->embed); gtb_weight_free(e->lm_head);
@@ -1326,6 +1379,7 @@ int gtb_engine_reset(gtb_engine_t e) {
     GTB_CHECK_INIT();
     GTB_ARG(e);
     e->host_pos = 0;
+    e->kvt_pos = 0;
     return set_state(e, 0, 0);
 }
 
@@ -1412,6 +1466,7 @@ int gtb_engine_prefill_fast(gtb_engine_t e, const int32_t* h_tokens, int n_token
         e->pf_cap_T = n_tokens;
     }
     GTB_CUDA(cudaMemcpyAsync(e->tokens, h_tokens, (size_t)n_tokens * 4, cudaMemcpyHostToDevice, ctx().stream));
+    e->kvt_pos = 0;                  // the tensor-core prefill rewrites the natural K/V rows only
     std::vector<PfLayerIO> io(c.n_layers);
     for (int li = 0; li < c.n_layers; li++) {
         LayerW& l = e->L[li];

@@ -40,7 +40,7 @@ constexpr int MT = 512;                    // threads per CTA
 constexpr int MWARP = MT / 32;
 constexpr int ME = 2048, MF = 5632, MKV = 256, MH = 32, MGSZ = 8;     // TinyLLamaParams, tinyllama.cpp:12-20
 constexpr int NBE = ME / 32, NBF = MF / 32;
-constexpr int PS_BYTES = 140 * 1024;       // product staging; during attention: scores + the unit's V slice as fp32
+constexpr int PS_BYTES = 142 * 1024;       // product staging; during attention: probabilities + the unit's V slice as fp32
 constexpr int IT_Q4 = 10;                  // (row, block) items per thread per tile: MT*IT items in registers
 constexpr int IT_Q8 = 5;
 constexpr int SPIN_LIMIT = 1 << 24;        // ~ seconds; a stuck exchange traps instead of hanging the GPU
@@ -56,6 +56,10 @@ struct MegaLayer {
     const uint16_t* attn_norm;
     const uint16_t* ffn_norm;
     uint8_t* kq; uint16_t* ks; uint8_t* vq; uint16_t* vs;
+    // chunk-major copies of the Q8 K/V codes and scales, maintained for THIS kernel: kqt / vqt [group][4 chunks][max_ctx][16],
+    // kst / vst [group][2 blocks][max_ctx].  Consecutive positions are contiguous there, so a warp's loads are coalesced (the
+    // natural rows are 256 B apart: 32 cache lines per warp instruction, which made ISSUING the loads cost 4.4 us per layer)
+    uint8_t* kqt; uint8_t* vqt; uint16_t* kst; uint16_t* vst;
 };
 
 struct MegaParams {
@@ -90,7 +94,7 @@ __device__ __forceinline__ ull ll_load1(const ull* p) {
     asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
     return a;
 }
-__device__ __noinline__ void ll_timeout(ull* dbg, uint32_t tag, const void* p, ull seen) {
+static __device__ __noinline__ void ll_timeout(ull* dbg, uint32_t tag, const void* p, ull seen) {
     if (dbg) {
         dbg[1] = tag; dbg[2] = (ull)p; dbg[3] = seen; dbg[4] = blockIdx.x; dbg[5] = threadIdx.x;
         __threadfence_system();
@@ -679,19 +683,31 @@ __device__ __forceinline__ float mega_score(const MegaSm& sm, const MegaLayer& L
     }
 }
 
-// attention scratch carved from the product staging area
+// attention scratch carved from the product staging area.  Both arrays are LANE-MAJOR: position i = 8 k + l lives at index k of lane
+// l (the position lane of vec_dot_product_f32, ops.h:181-197), so a P.V chain reads four consecutive steps with one 128-bit load.
+//   sc [8][kp]            probabilities of the row
+//   vf [8][16][kp] (+4/l) the unit's V slice, decoded (exact: 7-bit code x fp16 scale, or fp16)
+// kp = padded positions per lane, == 4 (mod 32): 128-bit reads down 8 (lane, channel) rows hit 8 distinct bank groups; every lane
+// block is shifted by 4 floats so that the 8 lanes of one position (the staging writes) do too.
 struct AttnScratch {
-    float* sc;          // [max_ctx + 32] probabilities
-    float* vf;          // [max_ctx][16] the unit's V slice, decoded (exact: 7-bit code x fp16 scale, or fp16)
+    float* sc;
+    float* vf;
+    int kp, lst;        // floats per (lane, channel) row; floats per lane block of vf
+    __device__ __forceinline__ int sci(int i) const { return (i & 7) * kp + (i >> 3); }
+    __device__ __forceinline__ int vfi(int i, int c) const { return (i & 7) * lst + c * kp + (i >> 3); }
 };
+__host__ __device__ inline int attn_kp(int max_ctx) { return (((max_ctx + 7) / 8 + 31) / 32) * 32 + 4; }
 __device__ __forceinline__ AttnScratch attn_scratch(float* ps, int max_ctx) {
     AttnScratch a;
+    a.kp = attn_kp(max_ctx);
+    a.lst = 16 * a.kp + 4;
     a.sc = ps;
-    a.vf = ps + ((max_ctx + 32 + 3) & ~3);
+    a.vf = ps + 8 * a.kp;
     return a;
 }
 __host__ __device__ inline size_t attn_scratch_bytes(int max_ctx) {
-    return (size_t)((max_ctx + 32 + 3) & ~3) * 4 + (size_t)max_ctx * 64 + 64;
+    const size_t kp = (size_t)attn_kp(max_ctx);
+    return (8 * kp + 8 * (16 * kp + 4)) * 4 + 64;
 }
 
 // K row of one cached position for group g, as loaded from the cache (Q8: 64 permuted codes + 2 scales)
@@ -700,7 +716,8 @@ struct KRow { uint4 x0, y0, x1, y1; uint32_t s0, s1; };
 // P2a: re-encode / RoPE the unit's q, k, v (gten/ops.h:645-646, 733-753), append K/V, publish the scores of quarter j
 template <int AT>
 __device__ __forceinline__ void mega_attn_a(const MegaParams& P, const MegaLayer& L, MegaSm& sm, float* ps, int cta, int pos,
-                                            uint32_t tag_qkv, uint32_t tag_sc) {
+                                            uint32_t tag_qkv, uint32_t tag_sc, long long* prof, int& prof_i) {
+#define SUB_PROF(code) do { if (prof) { prof[prof_i++] = (code); prof[prof_i++] = gtimer(); } } while (0)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int h = cta >> 2, j = cta & 3, g = h / MGSZ;
     const bool writer = (h % MGSZ) == 0 && j == 0;
@@ -712,43 +729,61 @@ __device__ __forceinline__ void mega_attn_a(const MegaParams& P, const MegaLayer
     const int k0 = lo + tid;
     KRow kr;
     if (AT != DT_F16 && k0 < hi && k0 != pos) {
-        const uint4* kp = reinterpret_cast<const uint4*>(L.kq + (size_t)k0 * MKV + g * 64);
-        kr.x0 = __ldcg(kp); kr.y0 = __ldcg(kp + 1); kr.x1 = __ldcg(kp + 2); kr.y1 = __ldcg(kp + 3);
-        kr.s0 = __ldcg(L.ks + (size_t)k0 * (MKV / 32) + g * 2);
-        kr.s1 = __ldcg(L.ks + (size_t)k0 * (MKV / 32) + g * 2 + 1);
+        const size_t mc = (size_t)P.max_ctx;
+        const uint4* kp = reinterpret_cast<const uint4*>(L.kqt + ((size_t)g * 4 * mc + k0) * 16);
+        kr.x0 = __ldcg(kp); kr.y0 = __ldcg(kp + mc); kr.x1 = __ldcg(kp + 2 * mc); kr.y1 = __ldcg(kp + 3 * mc);
+        kr.s0 = __ldcg(L.kst + (size_t)(g * 2) * mc + k0);
+        kr.s1 = __ldcg(L.kst + (size_t)(g * 2 + 1) * mc + k0);
     }
+    SUB_PROF(99);                                              // entry barrier + K row loads issued
     {
         const int ch0 = g * 64 + j * 16;
-        for (int i = tid; i < pos; i += MT) {
-            float4* dst = reinterpret_cast<float4*>(as.vf + (size_t)i * 16);
-            if (AT == DT_F16) {
+        if (AT == DT_F16) {
+            for (int i = tid; i < pos; i += MT) {
+                float* dst = as.vf + as.vfi(i, 0);
                 const uint4* vp = reinterpret_cast<const uint4*>(L.vq + ((size_t)i * MKV + ch0) * 2);
                 const uint4 a = __ldcg(vp), b = __ldcg(vp + 1);
-                const __half2* ha = reinterpret_cast<const __half2*>(&a);
-                const __half2* hb = reinterpret_cast<const __half2*>(&b);
+                const __half* ha = reinterpret_cast<const __half*>(&a);
+                const __half* hb = reinterpret_cast<const __half*>(&b);
 #pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    const float2 p0 = __half22float2(ha[2 * u]), p1 = __half22float2(ha[2 * u + 1]);
-                    const float2 q0 = __half22float2(hb[2 * u]), q1 = __half22float2(hb[2 * u + 1]);
-                    dst[u] = make_float4(p0.x, p0.y, p1.x, p1.y);
-                    dst[2 + u] = make_float4(q0.x, q0.y, q1.x, q1.y);
+                for (int u = 0; u < 8; u++) { dst[u * as.kp] = __half2float(ha[u]); dst[(8 + u) * as.kp] = __half2float(hb[u]); }
+            }
+        } else {
+            // max_ctx <= 4 * MT: at most four positions per thread; ALL their loads are issued before the first is decoded, so the
+            // cache misses (the K/V lines were last touched a token ago, 600 MB of weight streaming earlier) overlap instead of queueing
+            uint4 cv[4];
+            uint32_t dv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = tid + u * MT;
+                if (i < pos) {
+                    cv[u] = __ldcg(reinterpret_cast<const uint4*>(L.vqt + ((size_t)(g * 4 + j) * P.max_ctx + i) * 16));
+                    dv[u] = __ldcg(L.vst + (size_t)(g * 2 + (j >> 1)) * P.max_ctx + i);
                 }
-            } else {
-                const uint4 c = __ldcg(reinterpret_cast<const uint4*>(L.vq + (size_t)i * MKV + ch0));
-                const float d = h2f(__ldcg(L.vs + (size_t)i * (MKV / 32) + g * 2 + (j >> 1)));
-                const uint32_t cw[4] = {c.x ^ 0x80808080u, c.y ^ 0x80808080u, c.z ^ 0x80808080u, c.w ^ 0x80808080u};
+            }
+            SUB_PROF(100);                                     // V loads issued
 #pragma unroll
-                for (int u = 0; u < 4; u++) {                      // value = code * delta (ops.h:1026), exact in fp32
-                    // int8 -> float without the conversion pipe: (2^23 + 128 + code) - (2^23 + 128)
-                    const float f0 = __fsub_rn(__uint_as_float(__byte_perm(cw[u], 0x4b000000u, 0x7650)), 8388736.0f);
-                    const float f1 = __fsub_rn(__uint_as_float(__byte_perm(cw[u], 0x4b000000u, 0x7651)), 8388736.0f);
-                    const float f2 = __fsub_rn(__uint_as_float(__byte_perm(cw[u], 0x4b000000u, 0x7652)), 8388736.0f);
-                    const float f3 = __fsub_rn(__uint_as_float(__byte_perm(cw[u], 0x4b000000u, 0x7653)), 8388736.0f);
-                    dst[u] = make_float4(__fmul_rn(f0, d), __fmul_rn(f1, d), __fmul_rn(f2, d), __fmul_rn(f3, d));
+            for (int u = 0; u < 4; u++) {
+                const int i = tid + u * MT;
+                if (i < pos) {
+                    float* dst = as.vf + as.vfi(i, 0);
+                    const float d = h2f((uint16_t)dv[u]);
+                    const uint32_t cw[4] = {cv[u].x ^ 0x80808080u, cv[u].y ^ 0x80808080u, cv[u].z ^ 0x80808080u, cv[u].w ^ 0x80808080u};
+#pragma unroll
+                    for (int w4 = 0; w4 < 4; w4++) {                   // value = code * delta (ops.h:1026), exact in fp32
+                        // int8 -> float without the conversion pipe: (2^23 + 128 + code) - (2^23 + 128)
+                        const float f0 = __fsub_rn(__uint_as_float(__byte_perm(cw[w4], 0x4b000000u, 0x7650)), 8388736.0f);
+                        const float f1 = __fsub_rn(__uint_as_float(__byte_perm(cw[w4], 0x4b000000u, 0x7651)), 8388736.0f);
+                        const float f2 = __fsub_rn(__uint_as_float(__byte_perm(cw[w4], 0x4b000000u, 0x7652)), 8388736.0f);
+                        const float f3 = __fsub_rn(__uint_as_float(__byte_perm(cw[w4], 0x4b000000u, 0x7653)), 8388736.0f);
+                        dst[(4 * w4 + 0) * as.kp] = __fmul_rn(f0, d); dst[(4 * w4 + 1) * as.kp] = __fmul_rn(f1, d);
+                        dst[(4 * w4 + 2) * as.kp] = __fmul_rn(f2, d); dst[(4 * w4 + 3) * as.kp] = __fmul_rn(f3, d);
+                    }
                 }
             }
         }
     }
+    SUB_PROF(96);                                              // K row + V slice loads issued / decoded
     if (tid < 96) {
         const int seg = tid >> 5, o = (tid & 31) * 2;
         const ull* src = P.x_qkv + (seg == 0 ? h * 64 : (seg == 1 ? ME + g * 64 : ME + MKV + g * 64)) + o;
@@ -758,6 +793,7 @@ __device__ __forceinline__ void mega_attn_a(const MegaParams& P, const MegaLayer
         sm.raw[seg * 64 + o + 1] = __uint_as_float(b);
     }
     __syncthreads();
+    SUB_PROF(97);                                              // q, k, v of this row arrived
     if (wid < 6) {
         const int which = wid >> 1, half = wid & 1;
         const float x = sm.raw[which * 64 + half * 32 + lane];
@@ -777,10 +813,11 @@ __device__ __forceinline__ void mega_attn_a(const MegaParams& P, const MegaLayer
                 d = __fmul_rn((float)q, h2f(dh));
                 if (writer) {
                     L.vq[(size_t)pos * MKV + g * 64 + ch] = (uint8_t)(int8_t)q;
-                    if (lane == 0) L.vs[(size_t)pos * (MKV / 32) + g * 2 + half] = dh;
+                    L.vqt[((size_t)(g * 4 + (ch >> 4)) * P.max_ctx + pos) * 16 + (ch & 15)] = (uint8_t)(int8_t)q;
+                    if (lane == 0) { L.vs[(size_t)pos * (MKV / 32) + g * 2 + half] = dh; L.vst[(size_t)(g * 2 + half) * P.max_ctx + pos] = dh; }
                 }
             }
-            if (sl >= 0 && sl < 16) as.vf[(size_t)pos * 16 + sl] = d;      // this row's own v is not read back from the cache
+            if (sl >= 0 && sl < 16) as.vf[as.vfi(pos, sl)] = d;            // this row's own v is not read back from the cache
         }
     }
     __syncthreads();
@@ -811,12 +848,14 @@ __device__ __forceinline__ void mega_attn_a(const MegaParams& P, const MegaLayer
                 if (lane == 0) sm.kd[half] = delta;
                 if (writer) {
                     L.kq[(size_t)pos * MKV + g * 64 + half * 32 + pb] = (uint8_t)(int8_t)q;
-                    if (lane == 0) L.ks[(size_t)pos * (MKV / 32) + g * 2 + half] = dh;
+                    L.kqt[((size_t)(g * 4 + half * 2 + (pb >> 4)) * P.max_ctx + pos) * 16 + (pb & 15)] = (uint8_t)(int8_t)q;
+                    if (lane == 0) { L.ks[(size_t)pos * (MKV / 32) + g * 2 + half] = dh; L.kst[(size_t)(g * 2 + half) * P.max_ctx + pos] = dh; }
                 }
             }
         }
     }
     __syncthreads();
+    SUB_PROF(98);                                              // E / RoPE / E done
     // scores of this unit's quarter of the positions, scaled by 1/sqrt(64) (exactly 0.125)
     ull* dst = P.x_sc + (size_t)h * P.sc_stride;
     for (int k = k0; k < hi; k += MT) {
@@ -850,7 +889,7 @@ __device__ __forceinline__ void mega_attn_a(const MegaParams& P, const MegaLayer
 // Thread t owns positions 4t .. 4t+3 (max_ctx <= 4 * MT): scores, exponentials and probabilities stay in registers.
 template <int AT>
 __device__ __forceinline__ void mega_attn_b(const MegaParams& P, MegaSm& sm, float* ps, float* xbuf, int cta, int pos, int n_ctx,
-                                            uint32_t tag_sc, uint32_t tag_attn) {
+                                            uint32_t tag_sc, uint32_t tag_attn, long long* prof, int& prof_i) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int h = cta >> 2, j = cta & 3;
     const AttnScratch as = attn_scratch(ps, P.max_ctx);
@@ -865,15 +904,18 @@ __device__ __forceinline__ void mega_attn_b(const MegaParams& P, MegaSm& sm, flo
         if (i0 + 3 <= pos) { ll_wait2(src + i0 + 2, tag_sc, a, b, P.dbg); s[2] = __uint_as_float(a); s[3] = __uint_as_float(b); }
         else if (i0 + 2 == pos) s[2] = __uint_as_float(ll_wait1(src + i0 + 2, tag_sc, P.dbg));
     }
+    SUB_PROF(80);                                              // scores loaded
     float mx = warp_max(fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3])));
     if (lane == 0) sm.red[wid] = mx;
     __syncthreads();
     mx = sm.red[0];
 #pragma unroll
     for (int w = 1; w < MWARP; w++) mx = fmaxf(mx, sm.red[w]);
+    SUB_PROF(81);                                              // max
     float e[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) e[u] = (i0 + u <= pos) ? expf_glibc(__fsub_rn(s[u], mx)) : 0.0f;
+    SUB_PROF(82);                                              // expf
     const float sum = exact_sum512([&](int i, float q[4]) {
         if (i == i0) { q[0] = e[0]; q[1] = e[1]; q[2] = e[2]; q[3] = e[3]; }
         else {                                               // serial fallback: thread 0 walks every element
@@ -881,41 +923,52 @@ __device__ __forceinline__ void mega_attn_b(const MegaParams& P, MegaSm& sm, flo
             for (int u = 0; u < 4; u++) q[u] = xbuf[i + u];
         }
     }, pos + 1, sm.es, [&]() { *reinterpret_cast<float4*>(xbuf + i0) = make_float4(e[0], e[1], e[2], e[3]); });
+    SUB_PROF(83);                                              // exact sum
     // probabilities, re-encoded as a row (blocks of 32 positions = 8 consecutive threads); masked entries are exact zeros
     float p[4], ph[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) p[u] = (i0 + u <= pos) ? __fdiv_rn(e[u], sum) : 0.0f;
     roundtrip_quad<AT>(p, ph);
-    if (i0 <= pos) *reinterpret_cast<float4*>(sc + i0) = make_float4(ph[0], ph[1], ph[2], ph[3]);      // sc holds max_ctx + 32 entries
+    if (i0 <= pos) {                                           // positions 4 t .. 4 t + 3: lanes 4 (t & 1) + u, step t >> 1
+#pragma unroll
+        for (int u = 0; u < 4; u++) sc[as.sci(i0 + u)] = ph[u];
+    }
     __syncthreads();
+    SUB_PROF(84);                                              // probabilities encoded
     // P.V: eight position-lanes (i mod 8) per channel over [0, n8), lanes summed left to right, then the tail
     const int n8 = (n_ctx / 8) * 8;
     const float* vf = as.vf;
     if (tid < 128) {
         const int l = tid >> 4, cc = tid & 15;
         const int hi = min(n8, pos + 1);
+        const int nk = (hi > l) ? ((hi - l + 7) >> 3) : 0;     // steps of lane l: positions l, l + 8, ... < hi
+        const float* pl = sc + l * as.kp;
+        const float* vl = vf + l * as.lst + cc * as.kp;
         float a = 0.0f;
-        int i = l;
-        for (; i + 56 < hi; i += 64) {
-            float pp[8], vv[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) { pp[u] = sc[i + 8 * u]; vv[u] = vf[(size_t)(i + 8 * u) * 16 + cc]; }
-#pragma unroll
-            for (int u = 0; u < 8; u++) a = __fadd_rn(__fmul_rn(pp[u], vv[u]), a);
+        int k = 0;
+        for (; k + 8 <= nk; k += 8) {
+            const float4 p0 = *reinterpret_cast<const float4*>(pl + k), p1 = *reinterpret_cast<const float4*>(pl + k + 4);
+            const float4 v0 = *reinterpret_cast<const float4*>(vl + k), v1 = *reinterpret_cast<const float4*>(vl + k + 4);
+            a = __fadd_rn(__fmul_rn(p0.x, v0.x), a); a = __fadd_rn(__fmul_rn(p0.y, v0.y), a);
+            a = __fadd_rn(__fmul_rn(p0.z, v0.z), a); a = __fadd_rn(__fmul_rn(p0.w, v0.w), a);
+            a = __fadd_rn(__fmul_rn(p1.x, v1.x), a); a = __fadd_rn(__fmul_rn(p1.y, v1.y), a);
+            a = __fadd_rn(__fmul_rn(p1.z, v1.z), a); a = __fadd_rn(__fmul_rn(p1.w, v1.w), a);
         }
-        for (; i < hi; i += 8) a = __fadd_rn(__fmul_rn(sc[i], vf[(size_t)i * 16 + cc]), a);
+        for (; k < nk; k++) a = __fadd_rn(__fmul_rn(pl[k], vl[k]), a);
         sm.part[l][cc] = a;
     }
     __syncthreads();
+    SUB_PROF(85);                                              // P.V lanes
     if (tid < 16) {
         float d = __fadd_rn(sm.part[0][tid], sm.part[1][tid]);
 #pragma unroll
         for (int l = 2; l < 8; l++) d = __fadd_rn(d, sm.part[l][tid]);
-        for (int i = n8; i < n_ctx && i <= pos; i++) d = __fadd_rn(d, __fmul_rn(sc[i], vf[(size_t)i * 16 + tid]));
+        for (int i = n8; i < n_ctx && i <= pos; i++) d = __fadd_rn(d, __fmul_rn(sc[as.sci(i)], vf[as.vfi(i, tid)]));
         ll_store(P.x_attn + h * 64 + j * 16 + tid, __float_as_uint(d), tag_attn);
     }
 }
 
+#undef SUB_PROF
 // P4b: one warp per block of 32 FFN channels: E(E(silu(E(gate))) * E(up)) (gten/modules.cpp:238-247), published as
 // packed words in the staged layout (Q8: pairs (X_l, Y_l), the fp16 scale, a pad; F16: 16 half2 words)
 template <int AT>
@@ -1149,7 +1202,10 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
             ull* outp = (kind == 0) ? P.x_qkv : ((kind == 1) ? P.x_o : ((kind == 2) ? P.x_gu : P.x_down));
             float best = -INFINITY;
             int arg = 0x7fffffff;
-            gemv_phase<WT>(pd, r0, r1, av, ps, w, nx, sm.rr[nx.kind][0], sm.rr[nx.kind][1], more, [&](int row, float v) {
+            // q|k|v phase of a CTA with an attention unit: the next phase's weight tile (needed only at P3) is loaded AFTER the unit's
+            // K/V loads have been issued -- the L1 load queue is in order, and the attention loads are the ones on the critical path
+            const bool defer_tile = (WT != DT_F16) && kind == 0 && cta < n_units;
+            gemv_phase<WT>(pd, r0, r1, av, ps, w, nx, sm.rr[nx.kind][0], sm.rr[nx.kind][1], more && !defer_tile, [&](int row, float v) {
                 if (kind == 4) {
                     P.logits[row] = v;
                     if (v > best) { best = v; arg = row; }          // rows ascend per thread: first maximum wins
@@ -1166,13 +1222,33 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
                 const uint32_t tag_attn = ++ep;
                 if (cta < n_units) {
                     __syncthreads();                               // product staging is reused as attention scratch
-                    mega_attn_a<AT>(P, L, sm, ps, cta, pos, tag, tag_sc);
+                    mega_attn_a<AT>(P, L, sm, ps, cta, pos, tag, tag_sc, (P.prof && cta == 0 && tid == 0) ? P.prof : nullptr, prof_i);
+                    if (defer_tile && more) load_tile<WT>(nx, sm.rr[nx.kind][0], min(tile_rows<WT>(nx.nb), sm.rr[nx.kind][1] - sm.rr[nx.kind][0]), w);
                     MEGA_PROF(kind * 16 + 5);
                     exp_sc += 4;
                     xwait(P.cnt + (CNT_SC0 + (cta >> 2)) * CNT_STRIDE, P.cnt + (CNT_SC0 + (cta >> 2)) * CNT_STRIDE, exp_sc, P.dbg);
                     MEGA_PROF(kind * 16 + 6);
-                    mega_attn_b<AT>(P, sm, ps, xbuf, cta, pos, n_ctx, tag_sc, tag_attn);
+                    mega_attn_b<AT>(P, sm, ps, xbuf, cta, pos, n_ctx, tag_sc, tag_attn, (P.prof && cta == 0 && tid == 0) ? P.prof : nullptr, prof_i);
                     __threadfence();                               // K/V appends visible before anything later is published
+                } else if (tid == 0 && AT != DT_F16) {
+                    // the CTAs without an attention unit pull the NEXT layer's K/V rows (last touched a token ago) towards L2
+                    const int nl = (s >> 2) + 1;
+                    const MegaLayer& LN = P.layers[(nl < P.n_layers) ? nl : 0];     // after the last layer: layer 0 of the next row
+                    const int nidle = G - n_units, me = cta - n_units;
+                    const size_t rows0 = ((size_t)pos * me) / nidle, rows1 = ((size_t)pos * (me + 1)) / nidle;
+                    if (rows1 > rows0 && (nl < P.n_layers || !last_row)) {
+                        for (int q4 = 0; q4 < 4; q4++) {       // the four groups' K rows; their V slices
+#pragma unroll
+                            for (int c4 = 0; c4 < 4; c4++) {
+                                l2_prefetch(LN.kqt + ((size_t)(q4 * 4 + c4) * P.max_ctx + rows0) * 16, (rows1 - rows0) * 16);
+                                l2_prefetch(LN.vqt + ((size_t)(q4 * 4 + c4) * P.max_ctx + rows0) * 16, (rows1 - rows0) * 16);
+                            }
+                        }
+                        for (int b8 = 0; b8 < MKV / 32; b8++) {
+                            l2_prefetch(LN.kst + (size_t)b8 * P.max_ctx + rows0, (rows1 - rows0) * 2);
+                            l2_prefetch(LN.vst + (size_t)b8 * P.max_ctx + rows0, (rows1 - rows0) * 2);
+                        }
+                    }
                 }
                 tag_in = tag_attn;
                 MEGA_PROF(kind * 16 + 7);

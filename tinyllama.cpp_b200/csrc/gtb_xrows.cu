@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "gtb_xrows.h"
+#include "gtb_mega.cuh"        // exact_sum512: the in-order sum emulated exactly by 512 threads
 
 namespace gtb {
 
@@ -123,7 +124,8 @@ __global__ void __launch_bounds__(XN_NT) k_xr_norm(XrNormArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     float* xbuf = reinterpret_cast<float*>(smem);                 // [E] the row
     float* sq = xbuf + a.E;                                       // [E] its squares
-    __shared__ float s_sum;
+    __shared__ ExactSum2Smem es;
+    static_assert(XN_NT == MT, "exact_sum512 runs on MT threads");
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int nb = a.E / 32;
     const int row = a.row0 + blockIdx.x;
@@ -159,30 +161,14 @@ __global__ void __launch_bounds__(XN_NT) k_xr_norm(XrNormArgs a) {
         sq[e] = __fmul_rn(v, v);
     }
     __syncthreads();
-    // ops.h:765-767: the sum of squares strictly in order.  One thread walks the chain (4 cycles per add): the rows of a pass
-    // run side by side on different SMs, so the plain chain costs one chain latency for all of them.
-    if (threadIdx.x == 0) {
-        float s = 0.0f;
-        const float4* p4 = reinterpret_cast<const float4*>(sq);
-        float4 cur[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) cur[u] = p4[u];
-        for (int i = 0; i < a.E / 4; i += 4) {
-            float4 nxt[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) nxt[u] = (i + 4 + u < a.E / 4) ? p4[i + 4 + u] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                s = __fadd_rn(s, cur[u].x); s = __fadd_rn(s, cur[u].y); s = __fadd_rn(s, cur[u].z); s = __fadd_rn(s, cur[u].w);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) cur[u] = nxt[u];
-        }
-        s_sum = s;
-    }
-    __syncthreads();
+    // ops.h:765-767: the sum of squares strictly in order, emulated exactly in parallel (gtb_mega.cuh: one integer add scan; 1.9 us
+    // against 4.2 us for the plain 2048-step chain)
+    const float sq_sum = exact_sum512([&](int i, float q[4]) {
+        if (i < a.E) { const float4 v = *reinterpret_cast<const float4*>(sq + i); q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w; }
+        else { q[0] = q[1] = q[2] = q[3] = 0.0f; }
+    }, a.E, es);
     pdl_launch();
-    const float denom = __fadd_rn(sqrtf(__fdiv_rn(s_sum, (float)a.E)), 1e-6f);
+    const float denom = __fadd_rn(sqrtf(__fdiv_rn(sq_sum, (float)a.E)), 1e-6f);
     for (int b = wid, u = 0; b < nb; b += XN_NW, u++) {
         const int e = b * 32 + lane;
         const float y = __fmul_rn(__fdiv_rn(xbuf[e], denom), (u < 4) ? nw[u] : h2f(a.normw[e]));
@@ -646,6 +632,149 @@ __global__ void __launch_bounds__(XA_NT) k_xr_attn(XrAttnArgs a) {
     }
 }
 
+// ---------------------------------------------------------------- attention, CTA = (row, query head): passes of few rows
+// The group kernel above reads K/V once for 8 heads but gives a pass of R rows only 4 R CTAs; with R <= 32 rows at a long context
+// that leaves most SMs idle behind one long CTA each.  This variant spreads the same arithmetic over 32 R CTAs (K/V are re-read
+// per head from L2, harmless at this size): thread = position for the scores, (position lane, channel pair) for P.V.
+struct XrHeadSmem {
+    uint32_t qw[16]; float qd[2];
+    float part[8][64];
+    float red[8];
+    float sum;
+    float ob[64];
+};
+__host__ __device__ inline size_t xr_attn_head_smem(int t_cap) { return ((sizeof(XrHeadSmem) + 15) & ~(size_t)15) + (size_t)t_cap * 4; }
+
+__global__ void __launch_bounds__(XA_NT) k_xr_attn_head(XrAttnArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    XrHeadSmem& sm = *reinterpret_cast<XrHeadSmem*>(smem);
+    float* sc = reinterpret_cast<float*>(smem + ((sizeof(XrHeadSmem) + 15) & ~(size_t)15));
+    const int h = blockIdx.x, g = h / 8, row = a.row0 + blockIdx.y;
+    pdl_wait();
+    const XrRow rw = a.rows[row];
+    if (rw.slot < 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int t = rw.pos + 1, n_ctx = rw.n_ctx;
+    const int nsc = a.kv_dim / 32;
+    if (tid < 18) {
+        const XBlk* qb = a.qst + ((size_t)row * a.n_heads + h) * 2;
+        if (tid < 16) sm.qw[tid] = qb[tid >> 3].w[tid & 7];
+        else sm.qd[tid - 16] = qb[tid - 16].d;
+    }
+    __syncthreads();
+    const uint8_t* kqb = a.kq + (size_t)rw.slot * a.slot_codes + g * 64;
+    const uint16_t* ksb = a.ks + (size_t)rw.slot * a.slot_scales + g * 2;
+    // ---- scores (gten/ops.h:224-292 over the two blocks of the head), scaled by 1/8
+    float mx = -INFINITY;
+    for (int k = tid; k < t; k += XA_NT) {
+        const uint4* kp = reinterpret_cast<const uint4*>(kqb + (size_t)k * a.kv_dim);
+        const uint4 x0 = __ldg(kp), y0 = __ldg(kp + 1), x1 = __ldg(kp + 2), y1 = __ldg(kp + 3);
+        const uint32_t s2 = __ldg(reinterpret_cast<const uint32_t*>(ksb + (size_t)k * nsc));
+        const float s0 = __fmul_rn(sm.qd[0], h2f((uint16_t)(s2 & 0xffffu))), s1 = __fmul_rn(sm.qd[1], h2f((uint16_t)(s2 >> 16)));
+        const float m0 = __fmul_rn(-XB_M, s0), m1 = __fmul_rn(-XB_M, s1);
+        const uint32_t kx0[4] = {x0.x, x0.y, x0.z, x0.w}, ky0[4] = {y0.x, y0.y, y0.z, y0.w};
+        const uint32_t kx1[4] = {x1.x, x1.y, x1.z, x1.w}, ky1[4] = {y1.x, y1.y, y1.z, y1.w};
+        float al[4];
+#pragma unroll
+        for (int l = 0; l < 4; l++) {
+            const int t0 = __dp4a((int)ky0[l], (int)sm.qw[4 + l], __dp4a((int)kx0[l], (int)sm.qw[l], XB_BIAS));
+            const int t1 = __dp4a((int)ky1[l], (int)sm.qw[12 + l], __dp4a((int)kx1[l], (int)sm.qw[8 + l], XB_BIAS));
+            al[l] = __fadd_rn(fmaf(__int_as_float(t0), s0, m0), fmaf(__int_as_float(t1), s1, m1));
+        }
+        const float s = __fmul_rn(__fadd_rn(__fadd_rn(al[0], al[1]), __fadd_rn(al[2], al[3])), 0.125f);
+        sc[k] = s;
+        mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    if (lane == 0) sm.red[wid] = mx;
+    __syncthreads();
+    mx = sm.red[0];
+#pragma unroll
+    for (int w = 1; w < 8; w++) mx = fmaxf(mx, sm.red[w]);
+    for (int k = tid; k < t; k += XA_NT) sc[k] = expf_glibc(__fsub_rn(sc[k], mx));
+    __syncthreads();
+    if (tid == 0) {                                        // ops.h:982-988: the sum strictly in order
+        float s = 0.0f;
+        int k = 0;
+        for (; k + 8 <= t; k += 8) {
+            const float4 e0 = *reinterpret_cast<const float4*>(sc + k), e1 = *reinterpret_cast<const float4*>(sc + k + 4);
+            s = __fadd_rn(s, e0.x); s = __fadd_rn(s, e0.y); s = __fadd_rn(s, e0.z); s = __fadd_rn(s, e0.w);
+            s = __fadd_rn(s, e1.x); s = __fadd_rn(s, e1.y); s = __fadd_rn(s, e1.z); s = __fadd_rn(s, e1.w);
+        }
+        for (; k < t; k++) s = __fadd_rn(s, sc[k]);
+        sm.sum = s;
+    }
+    __syncthreads();
+    {
+        const float sum = sm.sum;
+        const int nblk = (t + 31) / 32;
+        for (int b = wid; b < nblk; b += 8) {
+            const int i = b * 32 + lane;
+            const float p = (i < t && i < n_ctx) ? __fdiv_rn(sc[i], sum) : 0.0f;
+            const float ph = q8_roundtrip_lane(p);
+            if (i < t) sc[i] = ph;
+        }
+    }
+    __syncthreads();
+    pdl_launch();
+    // ---- P.V (ops.h:181-197, 1046-1087): warp = position lane (i mod 8), lane = channels (lane, lane + 32)
+    const int n8 = (n_ctx / 8) * 8, hi = min(n8, t);
+    const uint8_t* vqb = a.vq + (size_t)rw.slot * a.slot_codes + g * 64;
+    const uint16_t* vsb = a.vs + (size_t)rw.slot * a.slot_scales + g * 2;
+    {
+        float a0 = 0.0f, a1 = 0.0f;
+        int i = wid;
+        for (; i + 56 < hi; i += 64) {                     // eight positions of this lane per round: all loads first (L2 latency), then the chain
+            uint32_t s2[8];
+            int c0[8], c1[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int ii = i + 8 * u;
+                s2[u] = __ldg(reinterpret_cast<const uint32_t*>(vsb + (size_t)ii * nsc));
+                const uint8_t* vp = vqb + (size_t)ii * a.kv_dim;
+                c0[u] = (int)(int8_t)__ldg(vp + lane);
+                c1[u] = (int)(int8_t)__ldg(vp + 32 + lane);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const float p = sc[i + 8 * u];
+                const float v0 = __fmul_rn((float)c0[u], h2f((uint16_t)(s2[u] & 0xffffu)));                     // ops.h:1026
+                const float v1 = __fmul_rn((float)c1[u], h2f((uint16_t)(s2[u] >> 16)));
+                a0 = __fadd_rn(__fmul_rn(p, v0), a0);
+                a1 = __fadd_rn(__fmul_rn(p, v1), a1);
+            }
+        }
+        for (; i < hi; i += 8) {
+            const float p = sc[i];
+            const uint32_t s2 = __ldg(reinterpret_cast<const uint32_t*>(vsb + (size_t)i * nsc));
+            const uint8_t* vp = vqb + (size_t)i * a.kv_dim;
+            const float v0 = __fmul_rn((float)(int8_t)__ldg(vp + lane), h2f((uint16_t)(s2 & 0xffffu)));
+            const float v1 = __fmul_rn((float)(int8_t)__ldg(vp + 32 + lane), h2f((uint16_t)(s2 >> 16)));
+            a0 = __fadd_rn(__fmul_rn(p, v0), a0);
+            a1 = __fadd_rn(__fmul_rn(p, v1), a1);
+        }
+        sm.part[wid][lane] = a0;
+        sm.part[wid][lane + 32] = a1;
+    }
+    __syncthreads();
+    if (tid < 64) {
+        float d = __fadd_rn(sm.part[0][tid], sm.part[1][tid]);
+#pragma unroll
+        for (int l = 2; l < 8; l++) d = __fadd_rn(d, sm.part[l][tid]);
+        for (int i = n8; i < t; i++) {
+            const float dl = h2f(__ldg(vsb + (size_t)i * nsc + (tid >> 5)));
+            d = __fadd_rn(d, __fmul_rn(sc[i], __fmul_rn((float)(int8_t)__ldg(vqb + (size_t)i * a.kv_dim + tid), dl)));
+        }
+        sm.ob[tid] = d;
+    }
+    __syncthreads();
+    if (wid < 2) {
+        uint16_t dh;
+        const int q = q8_encode_lane(sm.ob[wid * 32 + lane], &dh);
+        xblk_store(a.out + (size_t)row * a.out_nb + h * 2 + wid, lane, q, dh);
+    }
+}
+
 // ---------------------------------------------------------------- host side
 // Programmatic dependent launch between the kernels of a pass.  Measured (tools/xrows_probe.py --pdl 0/1, same box): it helps the
 // latency-bound small passes (8 rows: 2.66 vs 2.76 ms per step) and costs 17 % on full ones (64 rows: 4.58 vs 3.91 ms: the early
@@ -753,6 +882,7 @@ int run_pass(XrPlan* p, const XrModel& m, const XrKV& kv, const XrSeq& sq, const
     static bool attr = false;
     if (!attr) {
         GTB_CUDA(cudaFuncSetAttribute(k_xr_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        GTB_CUDA(cudaFuncSetAttribute(k_xr_attn_head, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         GTB_CUDA(cudaFuncSetAttribute(k_xr_norm, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr = true;
     }
@@ -784,7 +914,8 @@ int run_pass(XrPlan* p, const XrModel& m, const XrKV& kv, const XrSeq& sq, const
             a.rows = p->rows; a.row0 = 0; a.qst = p->qst; a.kq = kv.kq[li]; a.ks = kv.ks[li]; a.vq = kv.vq[li]; a.vs = kv.vs[li];
             a.slot_codes = kv.slot_codes; a.slot_scales = kv.slot_scales; a.kv_dim = KVD; a.n_heads = c.n_heads;
             a.out = p->act_attn; a.out_nb = E / 32; a.t_cap = t_cap;
-            GTB_CUDA(xr_launch(k_xr_attn, dim3(c.n_groups, R), XA_NT, attn_smem, a));
+            if (R <= 32) GTB_CUDA(xr_launch(k_xr_attn_head, dim3(c.n_heads, R), XA_NT, xr_attn_head_smem(t_cap), a));
+            else GTB_CUDA(xr_launch(k_xr_attn, dim3(c.n_groups, R), XA_NT, attn_smem, a));
             GTB_LAUNCHED();
         }
         {
