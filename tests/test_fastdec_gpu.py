@@ -227,6 +227,7 @@ def test_batch_decode_argument_errors(capi):
     e.batch_create(0)
     e.close()
     f = capi.Engine(cfg, 32, F16).load(W.synth_weights(cfg, F16, seed=1))
+    f.set_option("batch_exact", 0)        # FP16 models batch through the exact multi-row kernels only
     with pytest.raises(capi.GtbError):
         f.batch_create(2)
     f.close()

@@ -14,7 +14,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from oracle import Q4, Q8
+from oracle import F16, Q4, Q8
 from tinyllama_cpp_b200 import weights as W
 
 pytestmark = pytest.mark.gpu
@@ -34,14 +34,14 @@ def bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
 
 
-@pytest.mark.parametrize("wdt", [Q8, Q4], ids=["q8", "q4"])
+@pytest.mark.parametrize("wdt", [Q8, Q4, F16], ids=["q8", "q4", "f16"])
 @pytest.mark.parametrize("n_prompt", [4, 7, 16, 63, 64, 65, 100, 129, 190])
 def test_exact_prefill_matches_reference(capi, checker, wdt, n_prompt):
     """Prefill logits (bit for bit) and the following greedy tokens equal the CPU reference's; the same engine with the
     multi-row path switched off (row-at-a-time persistent kernel) gives the same bits."""
     cfg = W.mini_config(n_layers=2, n_vocab=300)
     wl = list(W.synth_weights(cfg, wdt, seed=31))
-    max_ctx = 256                      # Q8 prefill rows of the oracle need ceil(n/32)*34 <= max_ctx (SURVEY App. B1)
+    max_ctx = 400 if wdt == F16 else 256   # the oracle's prefill rows need ceil(n/32)*34 <= max_ctx (Q8) / 2n <= max_ctx (FP16), SURVEY App. B1
     n_new = 6
     cm = checker.model(cfg, max_ctx, wdt).load(wl)
     prompt = W.synth_prompt(9, n_prompt, cfg.n_vocab)
@@ -58,14 +58,14 @@ def test_exact_prefill_matches_reference(capi, checker, wdt, n_prompt):
     cm.close()
 
 
-@pytest.mark.parametrize("wdt", [Q8, Q4], ids=["q8", "q4"])
+@pytest.mark.parametrize("wdt", [Q8, Q4, F16], ids=["q8", "q4", "f16"])
 def test_exact_multi_row_continuation(capi, checker, wdt):
     """logits(tokens, start_pos) with several new rows on top of an existing cache (tinyllama.cpp:45-61 with start_pos > 0):
     the rows use the call's n_ctx for the P.V lane split."""
     cfg = W.mini_config(n_layers=2, n_vocab=300)
     wl = list(W.synth_weights(cfg, wdt, seed=32))
-    cm = checker.model(cfg, 256, wdt).load(wl)
-    e = capi.Engine(cfg, 256, wdt).load(wl)
+    cm = checker.model(cfg, 320, wdt).load(wl)
+    e = capi.Engine(cfg, 320, wdt).load(wl)
     toks = W.synth_prompt(4, 150, cfg.n_vocab)
     for a, b in ((0, 40), (40, 53), (53, 54), (54, 150)):
         want = cm.logits(toks[:b], a)
@@ -77,15 +77,16 @@ def test_exact_multi_row_continuation(capi, checker, wdt):
 
 @pytest.mark.parametrize("graph", [1, 0], ids=["graph", "eager"])
 @pytest.mark.parametrize("wdt,lens", [(Q4, (20, 37, 64)), (Q8, (5, 33, 40, 41, 64, 90, 100, 7)), (Q4, (50,)),
-                                      (Q4, tuple(range(3, 3 + 37 * 3, 3))), (Q8, tuple(range(10, 100, 10)))],
-                         ids=["q4x3", "q8x8", "q4x1", "q4x37", "q8x9"])
+                                      (Q4, tuple(range(3, 3 + 37 * 3, 3))), (Q8, tuple(range(10, 100, 10))), (F16, (9, 33, 64, 70, 12))],
+                         ids=["q4x3", "q8x8", "q4x1", "q4x37", "q8x9", "f16x5"])
 def test_exact_batch_decode_matches_reference(capi, checker, wdt, lens, graph):
     """Every slot of the exact batched decode: tokens and last logits bit-identical to the SAME sequence generated alone by
     the CPU reference (different prompt lengths per slot: own positions, own K/V)."""
     cfg = W.mini_config(n_layers=2, n_vocab=300)
     wl = list(W.synth_weights(cfg, wdt, seed=6))
     steps = 7
-    e = capi.Engine(cfg, 160, wdt).load(wl)
+    mc = 160
+    e = capi.Engine(cfg, mc, wdt).load(wl)
     e.set_option("graph", graph)
     e.batch_create(len(lens))
     prompts = [W.synth_prompt(40 + i, n, cfg.n_vocab) for i, n in enumerate(lens)]
@@ -178,4 +179,27 @@ def test_full_size_seq64_batch_identity(capi):
         bad = next((i for i in range(got.size) if got[i] != want[i]), None)
         assert bad is None, f"sequence {s}: tokens diverge at index {bad}"
         assert np.array_equal(bits(e.batch_read_logits(s)), bits(gold["last_logits"][s])), s
+    e.close()
+
+
+def test_full_size_f16_batch_identity(capi):
+    """BASELINE.json configs[0] (FP16, 128-token prompt) at full size through the exact batched path: the slot that holds the golden
+    prompt reproduces the reference's greedy tokens while another sequence advances in the same steps."""
+    f = GOLD / "full_f16.npz"
+    if not f.exists():
+        pytest.skip("full_f16.npz not generated")
+    gold = np.load(f)
+    wdt, n_prompt, n_new, max_ctx = MG.FULL["full_f16"]
+    cfg = W.TINYLLAMA
+    steps = 48
+    e = capi.Engine(cfg, max_ctx, wdt).load(W.synth_weights(cfg, wdt, seed=1))
+    e.batch_create(2)
+    e.batch_prefill(0, W.synth_prompt(7, n_prompt, cfg.n_vocab))
+    e.batch_prefill(1, W.synth_prompt(8, 77, cfg.n_vocab))
+    e.batch_decode(steps)
+    got = e.batch_read_tokens(0, 0, n_prompt + steps + 1)
+    want = gold["tokens"][: n_prompt + steps + 1]
+    bad = next((i for i in range(got.size) if got[i] != want[i]), None)
+    assert bad is None, f"tokens diverge at index {bad}"
+    assert e.batch_position(1) == 77 + steps
     e.close()

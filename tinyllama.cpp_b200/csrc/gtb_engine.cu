@@ -741,7 +741,8 @@ int batch_alloc(gtb_engine* e, int n) {
     }
     b.kq.assign(c.n_layers, nullptr); b.vq.assign(c.n_layers, nullptr); b.ks.assign(c.n_layers, nullptr); b.vs.assign(c.n_layers, nullptr);
     for (int li = 0; li < c.n_layers; li++) {
-        r |= dalloc((void**)&b.kq[li], N * MC * KV); r |= dalloc((void**)&b.vq[li], N * MC * KV);
+        const size_t esz = (e->adtype == GTB_F16) ? 2 : 1;           // fp16 K/V rows of an FP16 model, Q8 codes otherwise
+        r |= dalloc((void**)&b.kq[li], N * MC * KV * esz); r |= dalloc((void**)&b.vq[li], N * MC * KV * esz);
         r |= dalloc((void**)&b.ks[li], N * MC * (KV / 32) * 2); r |= dalloc((void**)&b.vs[li], N * MC * (KV / 32) * 2);
     }
     if (r) { batch_free(e); return fail(GTB_ERR_CUDA, "batch buffers: allocation failed"); }
@@ -1599,7 +1600,7 @@ static bool batch_is_exact(const gtb_engine* e) { return e->batch_exact && xr_ok
 int gtb_engine_batch_create(gtb_engine_t e, int n_seq) {
     GTB_CHECK_INIT();
     GTB_ARG(e && n_seq >= 0);
-    if (e->cfg.wdtype == GTB_F16) return fail(GTB_ERR_STATE, "batched decode is built for Q8-activation models (Q8, Q4 weights)");
+    if (e->cfg.wdtype == GTB_F16 && !batch_is_exact(e)) return fail(GTB_ERR_STATE, "the order-free batched decode is built for Q8-activation models (Q8, Q4 weights)");
     if (batch_is_exact(e)) {
         if (n_seq > XR_MAX_ROWS) return fail(GTB_ERR_ARG, "batched decode: at most %d sequences", XR_MAX_ROWS);
     } else {
@@ -1654,13 +1655,15 @@ int gtb_engine_batch_adopt(gtb_engine_t e, int seq) {
     GTB_CUDA(cudaStreamSynchronize(st));
     const int pos = s.pos;
     GTB_ARG(pos >= 0 && pos < c.max_ctx);
-    const size_t KV = e->kv_dim, MC = c.max_ctx;
+    const size_t KV = e->kv_dim, MC = c.max_ctx, esz = (e->adtype == GTB_F16) ? 2 : 1;
     for (int li = 0; li < c.n_layers; li++) {
         LayerW& l = e->L[li];
-        GTB_CUDA(cudaMemcpyAsync(b.kq[li] + seq * MC * KV, l.kq, (size_t)pos * KV, cudaMemcpyDeviceToDevice, st));
-        GTB_CUDA(cudaMemcpyAsync(b.vq[li] + seq * MC * KV, l.vq, (size_t)pos * KV, cudaMemcpyDeviceToDevice, st));
-        GTB_CUDA(cudaMemcpyAsync(b.ks[li] + seq * MC * (KV / 32), l.ks, (size_t)pos * (KV / 32) * 2, cudaMemcpyDeviceToDevice, st));
-        GTB_CUDA(cudaMemcpyAsync(b.vs[li] + seq * MC * (KV / 32), l.vs, (size_t)pos * (KV / 32) * 2, cudaMemcpyDeviceToDevice, st));
+        GTB_CUDA(cudaMemcpyAsync(b.kq[li] + seq * MC * KV * esz, l.kq, (size_t)pos * KV * esz, cudaMemcpyDeviceToDevice, st));
+        GTB_CUDA(cudaMemcpyAsync(b.vq[li] + seq * MC * KV * esz, l.vq, (size_t)pos * KV * esz, cudaMemcpyDeviceToDevice, st));
+        if (l.ks) {
+            GTB_CUDA(cudaMemcpyAsync(b.ks[li] + seq * MC * (KV / 32), l.ks, (size_t)pos * (KV / 32) * 2, cudaMemcpyDeviceToDevice, st));
+            GTB_CUDA(cudaMemcpyAsync(b.vs[li] + seq * MC * (KV / 32), l.vs, (size_t)pos * (KV / 32) * 2, cudaMemcpyDeviceToDevice, st));
+        }
     }
     GTB_CUDA(cudaMemcpyAsync(b.tokens + (size_t)seq * (MC + 2), e->tokens, (size_t)(pos + 1) * 4, cudaMemcpyDeviceToDevice, st));
     DevState ns{pos, 0, 0, 0};

@@ -775,6 +775,307 @@ __global__ void __launch_bounds__(XA_NT) k_xr_attn_head(XrAttnArgs a) {
     }
 }
 
+// ================================================================ FP16 models (FP16 weights, FP16 activations; tinyllama.cpp:258-260)
+// Same pass structure; the arithmetic is gten/ops.h:140-160: eight lane accumulators over elements 8m + l (products of fp16 values are
+// exact in fp32, so one fused multiply-add equals the reference's separate mul and add), lanes summed left to right, and every
+// activation re-encode is a round-to-nearest-even to fp16.  Staged rows are the fp32 values of the fp16 activations in the weight
+// layout's chunk order: element 64c + 8i + l at index (8c + l) * 8 + i, so the eight elements a lane needs are two 128-bit reads.
+__device__ __forceinline__ int xf_index(int e) { return (((e >> 6) * 8) + (e & 7)) * 8 + ((e >> 3) & 7); }
+
+struct XfNormArgs {
+    const XrRow* rows;
+    int row0;
+    float* res;                // [rows][E]
+    const uint16_t* normw;
+    float* out;                // [rows][E] staged
+    int E;
+    const uint16_t* emb_w;     // device layout of the fp16 embedding table, or null
+};
+
+__global__ void __launch_bounds__(XN_NT) k_xf_norm(XfNormArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float* xbuf = reinterpret_cast<float*>(smem);
+    float* sq = xbuf + a.E;
+    __shared__ ExactSum2Smem es;
+    pdl_wait();
+    const int row = a.row0 + blockIdx.x;
+    const XrRow rw = a.rows[row];
+    if (rw.slot < 0) return;
+    float* res = a.res + (size_t)row * a.E;
+    for (int e = threadIdx.x; e < a.E; e += XN_NT) {
+        float v;
+        if (a.emb_w) { v = h2f(a.emb_w[(size_t)rw.tok * a.E + xf_index(e)]); res[e] = v; }     // the fp16 row is copied (ops.h:514-564)
+        else v = res[e];
+        xbuf[e] = v;
+        sq[e] = __fmul_rn(v, v);
+    }
+    __syncthreads();
+    const float sq_sum = exact_sum512([&](int i, float q[4]) {
+        if (i < a.E) { const float4 v = *reinterpret_cast<const float4*>(sq + i); q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w; }
+        else { q[0] = q[1] = q[2] = q[3] = 0.0f; }
+    }, a.E, es);
+    pdl_launch();
+    const float denom = __fadd_rn(sqrtf(__fdiv_rn(sq_sum, (float)a.E)), 1e-6f);
+    float* out = a.out + (size_t)row * a.E;
+    for (int e = threadIdx.x; e < a.E; e += XN_NT)
+        out[xf_index(e)] = f16_roundtrip(__fmul_rn(__fdiv_rn(xbuf[e], denom), h2f(a.normw[e])));
+}
+
+constexpr int XF_KC = 2;                                        // 64-element chunks per pipeline stage
+struct XfStage {
+    uint4 wd[XG_BN][XF_KC * 8 + 1];                             // [column][chunk][lane]: 8 halves each; odd pitch
+    float act[XG_BM][XF_KC * 64];
+};
+
+struct XfGemmArgs {
+    const XrRow* rows;
+    int row0, n_rows;
+    const float* act; int K;           // staged input rows [row][K]
+    const uint4* wd; int N;            // fp16 weights, device layout uint4[N][K/64][8]
+    int up_off;
+    float* res; int E;
+    float* out; int out_ld;            // EPI_SILU: staged MLP rows [row][n_ffn]; EPI_QKV: q after RoPE [row][n_embd], natural order
+    uint16_t* kq; uint16_t* vq; size_t slot_elems;
+    int kv_dim, n_heads, n_groups;
+    const float* rope_cos; const float* rope_sin;
+    float* logits; int ld_logits; float* arg_val; int* arg_idx; int n_tiles;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(256, 2) k_xf_gemm(XfGemmArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    XfStage* stages = reinterpret_cast<XfStage*>(smem);
+    constexpr int NTH = 256, TR = 2;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = blockIdx.x;
+    const int rbase = a.row0 + blockIdx.y * XG_BM, rend = a.row0 + a.n_rows;
+    const int cpr = a.K / 64, nstage = cpr / XF_KC;
+    auto wrow = [&](int c) -> int {
+        int r = (EPI == XEPI_SILU) ? ((c < 32) ? 32 * n + c : a.up_off + 32 * n + c - 32) : 64 * n + c;
+        return min(r, a.N - 1);
+    };
+    auto load_weights = [&](int s, int st_i) {
+        XfStage& st = stages[s];
+#pragma unroll
+        for (int i = tid; i < XG_BN * XF_KC * 8; i += NTH) {
+            const int c = i / (XF_KC * 8), j = i % (XF_KC * 8);
+            cp_async16(&st.wd[c][j], a.wd + ((size_t)wrow(c) * cpr + (size_t)st_i * XF_KC) * 8 + j, true);
+        }
+    };
+    auto load_act = [&](int s, int st_i) {
+        XfStage& st = stages[s];
+#pragma unroll
+        for (int i = tid; i < XG_BM * XF_KC * 16; i += NTH) {
+            const int r = i / (XF_KC * 16), j = i % (XF_KC * 16);
+            const int gr = rbase + r;
+            const bool ok = gr < rend;
+            cp_async16(reinterpret_cast<uint4*>(&st.act[r][0]) + j,
+                       reinterpret_cast<const uint4*>(a.act + (size_t)(ok ? gr : a.row0) * a.K + (size_t)st_i * XF_KC * 64) + j, ok);
+        }
+    };
+    float acc[TR][2][8];
+#pragma unroll
+    for (int r = 0; r < TR; r++)
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+            for (int l = 0; l < 8; l++) acc[r][c][l] = 0.0f;
+#pragma unroll
+    for (int s = 0; s < XG_STAGES - 1; s++)
+        if (s < nstage) load_weights(s, s);
+    pdl_wait();
+#pragma unroll
+    for (int s = 0; s < XG_STAGES - 1; s++) {
+        if (s < nstage) load_act(s, s);
+        cp_async_commit();
+    }
+    for (int si = 0; si < nstage; si++) {
+        cp_async_wait<XG_STAGES - 2>();
+        __syncthreads();
+        if (si + XG_STAGES - 1 < nstage) {
+            load_weights((si + XG_STAGES - 1) % XG_STAGES, si + XG_STAGES - 1);
+            load_act((si + XG_STAGES - 1) % XG_STAGES, si + XG_STAGES - 1);
+        }
+        cp_async_commit();
+        const XfStage& st = stages[si % XG_STAGES];
+#pragma unroll
+        for (int c = 0; c < XF_KC; c++) {
+#pragma unroll
+            for (int l = 0; l < 8; l++) {
+                const uint4 w0 = st.wd[lane][c * 8 + l], w1 = st.wd[lane + 32][c * 8 + l];
+                const __half2* h0 = reinterpret_cast<const __half2*>(&w0);
+                const __half2* h1 = reinterpret_cast<const __half2*>(&w1);
+                float f0[8], f1[8];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const float2 p = __half22float2(h0[u]), q = __half22float2(h1[u]);
+                    f0[2 * u] = p.x; f0[2 * u + 1] = p.y; f1[2 * u] = q.x; f1[2 * u + 1] = q.y;
+                }
+#pragma unroll
+                for (int r = 0; r < TR; r++) {
+                    const float4 xa = *reinterpret_cast<const float4*>(&st.act[wid * TR + r][(c * 8 + l) * 8]);
+                    const float4 xb = *reinterpret_cast<const float4*>(&st.act[wid * TR + r][(c * 8 + l) * 8 + 4]);
+                    const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {                         // elements 64c + 8i + l, ascending i: the lane's own order
+                        acc[r][0][l] = fmaf(x[i], f0[i], acc[r][0][l]);
+                        acc[r][1][l] = fmaf(x[i], f1[i], acc[r][1][l]);
+                    }
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    pdl_launch();
+#pragma unroll
+    for (int r = 0; r < TR; r++) {
+        const int row = rbase + wid * TR + r;
+        if (row >= rend) continue;
+        const XrRow rw = a.rows[row];
+        if (rw.slot < 0) continue;
+        float v[2];
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            float d = __fadd_rn(acc[r][c][0], acc[r][c][1]);            // simd_ops.h:63-66: lanes left to right
+#pragma unroll
+            for (int l = 2; l < 8; l++) d = __fadd_rn(d, acc[r][c][l]);
+            v[c] = d;
+        }
+        if (EPI == XEPI_RES) {
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                float* px = a.res + (size_t)row * a.E + 64 * n + 32 * c + lane;
+                *px = f16_roundtrip(__fadd_rn(*px, f16_roundtrip(v[c])));
+            }
+        } else if (EPI == XEPI_SILU) {
+            const float g1 = f16_roundtrip(v[0]), u1 = f16_roundtrip(v[1]);
+            const float g2 = f16_roundtrip(silu_ref(g1));
+            a.out[(size_t)row * a.out_ld + xf_index(32 * n + lane)] = f16_roundtrip(__fmul_rn(g2, u1));
+        } else if (EPI == XEPI_QKV) {
+            const int pos = rw.pos;
+            if (n < a.n_heads + a.n_groups) {
+                const float x0 = f16_roundtrip(v[0]), x1 = f16_roundtrip(v[1]);
+                const float cs = __ldg(a.rope_cos + (size_t)pos * 32 + lane), sn = __ldg(a.rope_sin + (size_t)pos * 32 + lane);
+                const uint16_t o0 = f2h(__fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn)));
+                const uint16_t o1 = f2h(__fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs)));
+                if (n < a.n_heads) {
+                    float* q = a.out + (size_t)row * a.out_ld + n * 64;
+                    q[lane] = h2f(o0); q[32 + lane] = h2f(o1);
+                } else {
+                    uint16_t* k = a.kq + (size_t)rw.slot * a.slot_elems + (size_t)pos * a.kv_dim + (n - a.n_heads) * 64;
+                    k[lane] = o0; k[32 + lane] = o1;
+                }
+            } else {
+                uint16_t* vv = a.vq + (size_t)rw.slot * a.slot_elems + (size_t)pos * a.kv_dim + (n - a.n_heads - a.n_groups) * 64;
+                vv[lane] = f2h(v[0]); vv[32 + lane] = f2h(v[1]);
+            }
+        } else {
+            const int c0 = 64 * n + lane, c1 = c0 + 32;
+            float best = -INFINITY;
+            int arg = 0x7fffffff;
+            if (c0 < a.N) { a.logits[(size_t)(row - a.row0) * a.ld_logits + c0] = v[0]; if (v[0] > best) { best = v[0]; arg = c0; } }
+            if (c1 < a.N) { a.logits[(size_t)(row - a.row0) * a.ld_logits + c1] = v[1]; if (v[1] > best) { best = v[1]; arg = c1; } }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+                if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
+            }
+            if (lane == 0) { a.arg_val[(size_t)row * a.n_tiles + n] = best; a.arg_idx[(size_t)row * a.n_tiles + n] = arg; }
+        }
+    }
+}
+
+struct XfAttnArgs {
+    const XrRow* rows;
+    int row0;
+    const float* q;            // [row][n_embd] after RoPE, natural order
+    const uint16_t* kq; const uint16_t* vq; size_t slot_elems;
+    int kv_dim, n_heads;
+    float* out; int out_ld;    // staged attention output [row][n_embd]
+    int t_cap;
+};
+struct XfHeadSmem { float qf[64]; float part[8][64]; float red[8]; float sum; };
+__host__ __device__ inline size_t xf_attn_smem(int t_cap) { return ((sizeof(XfHeadSmem) + 15) & ~(size_t)15) + (size_t)t_cap * 4; }
+
+__global__ void __launch_bounds__(XA_NT) k_xf_attn_head(XfAttnArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    XfHeadSmem& sm = *reinterpret_cast<XfHeadSmem*>(smem);
+    float* sc = reinterpret_cast<float*>(smem + ((sizeof(XfHeadSmem) + 15) & ~(size_t)15));
+    const int h = blockIdx.x, g = h / 8, row = a.row0 + blockIdx.y;
+    pdl_wait();
+    const XrRow rw = a.rows[row];
+    if (rw.slot < 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int t = rw.pos + 1, n_ctx = rw.n_ctx;
+    if (tid < 64) sm.qf[tid] = a.q[(size_t)row * (a.n_heads * 64) + h * 64 + tid];
+    __syncthreads();
+    const uint16_t* kb = a.kq + (size_t)rw.slot * a.slot_elems + g * 64;
+    const uint16_t* vb = a.vq + (size_t)rw.slot * a.slot_elems + g * 64;
+    float mx = -INFINITY;
+    for (int k = tid; k < t; k += XA_NT) {
+        const uint4* kp = reinterpret_cast<const uint4*>(kb + (size_t)k * a.kv_dim);
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {                          // ops.h:140-160: lane l accumulates elements 8 i + l
+            const uint4 w = __ldg(kp + i);
+            const __half2* hw = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const float2 f = __half22float2(hw[u]);
+                acc[2 * u] = fmaf(sm.qf[8 * i + 2 * u], f.x, acc[2 * u]);
+                acc[2 * u + 1] = fmaf(sm.qf[8 * i + 2 * u + 1], f.y, acc[2 * u + 1]);
+            }
+        }
+        float d = __fadd_rn(acc[0], acc[1]);
+#pragma unroll
+        for (int l = 2; l < 8; l++) d = __fadd_rn(d, acc[l]);
+        const float s = __fmul_rn(d, 0.125f);
+        sc[k] = s;
+        mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    if (lane == 0) sm.red[wid] = mx;
+    __syncthreads();
+    mx = sm.red[0];
+#pragma unroll
+    for (int w = 1; w < 8; w++) mx = fmaxf(mx, sm.red[w]);
+    for (int k = tid; k < t; k += XA_NT) sc[k] = expf_glibc(__fsub_rn(sc[k], mx));
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.0f;
+        for (int k = 0; k < t; k++) s = __fadd_rn(s, sc[k]);
+        sm.sum = s;
+    }
+    __syncthreads();
+    {
+        const float sum = sm.sum;
+        for (int k = tid; k < t; k += XA_NT) sc[k] = f16_roundtrip((k < n_ctx) ? __fdiv_rn(sc[k], sum) : 0.0f);
+    }
+    __syncthreads();
+    pdl_launch();
+    const int n8 = (n_ctx / 8) * 8, hi = min(n8, t);
+    {
+        float a0 = 0.0f, a1 = 0.0f;
+        for (int i = wid; i < hi; i += 8) {
+            const float p = sc[i];
+            const uint16_t* vp = vb + (size_t)i * a.kv_dim;
+            a0 = __fadd_rn(__fmul_rn(p, h2f(__ldg(vp + lane))), a0);
+            a1 = __fadd_rn(__fmul_rn(p, h2f(__ldg(vp + 32 + lane))), a1);
+        }
+        sm.part[wid][lane] = a0;
+        sm.part[wid][lane + 32] = a1;
+    }
+    __syncthreads();
+    if (tid < 64) {
+        float d = __fadd_rn(sm.part[0][tid], sm.part[1][tid]);
+#pragma unroll
+        for (int l = 2; l < 8; l++) d = __fadd_rn(d, sm.part[l][tid]);
+        for (int i = n8; i < t; i++) d = __fadd_rn(d, __fmul_rn(sc[i], h2f(__ldg(vb + (size_t)i * a.kv_dim + tid))));
+        a.out[(size_t)row * a.out_ld + xf_index(h * 64 + tid)] = f16_roundtrip(d);
+    }
+}
+
 // ---------------------------------------------------------------- host side
 // Programmatic dependent launch between the kernels of a pass.  Measured (tools/xrows_probe.py --pdl 0/1, same box): it helps the
 // latency-bound small passes (8 rows: 2.66 vs 2.76 ms per step) and costs 17 % on full ones (64 rows: 4.58 vs 3.91 ms: the early
@@ -790,6 +1091,7 @@ struct XrPlan {
     float* arg_val = nullptr;
     int* arg_idx = nullptr;
     float* logits = nullptr;           // [XR_MAX_ROWS][n_vocab] when the caller passes none
+    float *f_norm = nullptr, *f_attn = nullptr, *f_mlp = nullptr, *f_q = nullptr;   // FP16 models: staged fp32 rows
     int n_tiles = 0;
     size_t bytes = 0;
 };
@@ -797,7 +1099,7 @@ struct XrPlan {
 void xr_set_pdl(bool on) { g_xr_pdl = on; }
 
 bool xr_supported(const gtb_model_config& c, int gsz) {
-    return (c.wdtype == GTB_Q8 || c.wdtype == GTB_Q4) && gsz == 8 && c.n_embd % 256 == 0 && c.n_ffn % 256 == 0 && c.n_embd / c.n_heads == 64 &&
+    return (c.wdtype == GTB_Q8 || c.wdtype == GTB_Q4 || c.wdtype == GTB_F16) && gsz == 8 && c.n_embd % 256 == 0 && c.n_ffn % 256 == 0 && c.n_embd / c.n_heads == 64 &&
            c.n_embd % 16 == 0 && c.n_embd <= 4096;
 }
 
@@ -815,10 +1117,15 @@ int xr_create(XrPlan** out, const gtb_model_config& c) {
     int r = 0;
     r |= dalloc((void**)&p->rows, R * sizeof(XrRow));
     r |= dalloc((void**)&p->res, R * c.n_embd * 4);
-    r |= dalloc((void**)&p->act_norm, R * (c.n_embd / 32) * sizeof(XBlk));
-    r |= dalloc((void**)&p->act_attn, R * (c.n_embd / 32) * sizeof(XBlk));
-    r |= dalloc((void**)&p->act_mlp, R * (c.n_ffn / 32) * sizeof(XBlk));
-    r |= dalloc((void**)&p->qst, R * c.n_heads * 2 * sizeof(XBlk));
+    if (c.wdtype == GTB_F16) {
+        r |= dalloc((void**)&p->f_norm, R * c.n_embd * 4); r |= dalloc((void**)&p->f_attn, R * c.n_embd * 4);
+        r |= dalloc((void**)&p->f_mlp, R * c.n_ffn * 4); r |= dalloc((void**)&p->f_q, R * c.n_embd * 4);
+    } else {
+        r |= dalloc((void**)&p->act_norm, R * (c.n_embd / 32) * sizeof(XBlk));
+        r |= dalloc((void**)&p->act_attn, R * (c.n_embd / 32) * sizeof(XBlk));
+        r |= dalloc((void**)&p->act_mlp, R * (c.n_ffn / 32) * sizeof(XBlk));
+        r |= dalloc((void**)&p->qst, R * c.n_heads * 2 * sizeof(XBlk));
+    }
     r |= dalloc((void**)&p->arg_val, R * p->n_tiles * 4);
     r |= dalloc((void**)&p->arg_idx, R * p->n_tiles * 4);
     r |= dalloc((void**)&p->logits, R * c.n_vocab * 4);
@@ -829,7 +1136,7 @@ int xr_create(XrPlan** out, const gtb_model_config& c) {
 
 void xr_destroy(XrPlan* p) {
     if (!p) return;
-    void* b[] = {p->rows, p->res, p->act_norm, p->act_attn, p->act_mlp, p->qst, p->arg_val, p->arg_idx, p->logits};
+    void* b[] = {p->rows, p->res, p->act_norm, p->act_attn, p->act_mlp, p->qst, p->arg_val, p->arg_idx, p->logits, p->f_norm, p->f_attn, p->f_mlp, p->f_q};
     for (void* q : b) cudaFree(q);
     ctx().mem -= (int64_t)p->bytes;
     delete p;
@@ -954,6 +1261,101 @@ int run_pass(XrPlan* p, const XrModel& m, const XrKV& kv, const XrSeq& sq, const
     return GTB_OK;
 }
 
+template <int EPI>
+int launch_gemm_f16(const XfGemmArgs& a, int n_tiles) {
+    const size_t smem = sizeof(XfStage) * XG_STAGES;
+    static bool attr = false;
+    if (!attr) {
+        GTB_CUDA(cudaFuncSetAttribute(k_xf_gemm<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    dim3 grid(n_tiles, (a.n_rows + XG_BM - 1) / XG_BM);
+    GTB_CUDA(xr_launch(k_xf_gemm<EPI>, grid, 256, smem, a));
+    GTB_LAUNCHED();
+    return GTB_OK;
+}
+
+// one pass of an FP16 model (same structure as run_pass)
+int run_pass_f16(XrPlan* p, const XrModel& m, const XrKV& kv, const XrSeq& sq, const XrPlanArgs& plan, int t_cap, int head_row0,
+                 int head_rows, int eos_id, float* d_logits) {
+    const gtb_model_config& c = m.cfg;
+    const int E = c.n_embd, F = c.n_ffn, KVD = 64 * c.n_groups, R = plan.n_rows;
+    g_xr_pdl_now = g_xr_pdl && R <= 16;
+    GTB_CUDA(xr_launch(k_xr_plan, dim3(1), XR_MAX_ROWS, 0, plan));
+    GTB_LAUNCHED();
+    const size_t norm_smem = (size_t)E * 8;
+    const size_t attn_smem = xf_attn_smem(t_cap);
+    static bool attr = false;
+    if (!attr) {
+        GTB_CUDA(cudaFuncSetAttribute(k_xf_attn_head, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        GTB_CUDA(cudaFuncSetAttribute(k_xf_norm, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr = true;
+    }
+    if (attn_smem > 64 * 1024) return fail(GTB_ERR_STATE, "multi-row attention: context too long for the score buffer");
+    auto norm = [&](const uint16_t* w, bool emb, int row0, int rows) -> int {
+        XfNormArgs a{};
+        a.rows = p->rows; a.row0 = row0; a.res = p->res; a.normw = w; a.out = p->f_norm; a.E = E;
+        a.emb_w = emb ? reinterpret_cast<const uint16_t*>(m.emb_w) : nullptr;
+        GTB_CUDA(xr_launch(k_xf_norm, dim3(rows), XN_NT, norm_smem, a));
+        GTB_LAUNCHED();
+        return GTB_OK;
+    };
+    XfGemmArgs base{};
+    base.rows = p->rows; base.row0 = 0; base.n_rows = R; base.res = p->res; base.E = E;
+    base.slot_elems = kv.slot_codes; base.kv_dim = KVD; base.n_heads = c.n_heads; base.n_groups = c.n_groups;
+    base.rope_cos = m.rope_cos; base.rope_sin = m.rope_sin;
+    int r;
+    for (int li = 0; li < c.n_layers; li++) {
+        const XrLayerW& L = m.layers[li];
+        if ((r = norm(L.attn_norm, li == 0, 0, R))) return r;
+        {
+            XfGemmArgs a = base;
+            a.act = p->f_norm; a.K = E; a.wd = L.w[0]; a.N = E + 2 * KVD; a.out = p->f_q; a.out_ld = E;
+            a.kq = reinterpret_cast<uint16_t*>(kv.kq[li]); a.vq = reinterpret_cast<uint16_t*>(kv.vq[li]);
+            if ((r = launch_gemm_f16<XEPI_QKV>(a, a.N / 64))) return r;
+        }
+        {
+            XfAttnArgs a{};
+            a.rows = p->rows; a.row0 = 0; a.q = p->f_q; a.kq = reinterpret_cast<const uint16_t*>(kv.kq[li]);
+            a.vq = reinterpret_cast<const uint16_t*>(kv.vq[li]); a.slot_elems = kv.slot_codes; a.kv_dim = KVD; a.n_heads = c.n_heads;
+            a.out = p->f_attn; a.out_ld = E; a.t_cap = t_cap;
+            GTB_CUDA(xr_launch(k_xf_attn_head, dim3(c.n_heads, R), XA_NT, attn_smem, a));
+            GTB_LAUNCHED();
+        }
+        {
+            XfGemmArgs a = base;
+            a.act = p->f_attn; a.K = E; a.wd = L.w[1]; a.N = E;
+            if ((r = launch_gemm_f16<XEPI_RES>(a, E / 64))) return r;
+        }
+        if ((r = norm(L.ffn_norm, false, 0, R))) return r;
+        {
+            XfGemmArgs a = base;
+            a.act = p->f_norm; a.K = E; a.wd = L.w[2]; a.N = 2 * F; a.up_off = F; a.out = p->f_mlp; a.out_ld = F;
+            if ((r = launch_gemm_f16<XEPI_SILU>(a, F / 32))) return r;
+        }
+        {
+            XfGemmArgs a = base;
+            a.act = p->f_mlp; a.K = F; a.wd = L.w[3]; a.N = E;
+            if ((r = launch_gemm_f16<XEPI_RES>(a, E / 64))) return r;
+        }
+    }
+    if (head_rows > 0) {
+        if ((r = norm(m.final_norm, false, head_row0, head_rows))) return r;
+        XfGemmArgs a = base;
+        a.row0 = head_row0; a.n_rows = head_rows;
+        a.act = p->f_norm; a.K = E; a.wd = m.head_w; a.N = c.n_vocab;
+        a.logits = d_logits ? d_logits : p->logits; a.ld_logits = c.n_vocab;
+        a.arg_val = p->arg_val; a.arg_idx = p->arg_idx; a.n_tiles = p->n_tiles;
+        if ((r = launch_gemm_f16<XEPI_HEAD>(a, p->n_tiles))) return r;
+        XrArgmaxArgs g{};
+        g.rows = p->rows; g.row0 = head_row0; g.arg_val = p->arg_val; g.arg_idx = p->arg_idx; g.n_tiles = p->n_tiles;
+        g.tokens = sq.tokens; g.tok_stride = sq.tok_stride; g.st = sq.st; g.eos_id = eos_id;
+        GTB_CUDA(xr_launch(k_xr_argmax, dim3(head_rows), 128, 0, g));
+        GTB_LAUNCHED();
+    }
+    return GTB_OK;
+}
+
 }  // namespace
 
 int xr_prefill_pass(XrPlan* p, const XrModel& m, const XrKV& kv, const XrSeq& sq, int slot, int p0, int n_rows, int n_ctx,
@@ -964,6 +1366,7 @@ int xr_prefill_pass(XrPlan* p, const XrModel& m, const XrKV& kv, const XrSeq& sq
     plan.tokens = sq.tokens; plan.st = sq.st; plan.rows = p->rows;
     const int t_cap = ((p0 + n_rows + 31) / 32) * 32 + 32;
     const int hr = with_head ? 1 : 0;
+    if (m.cfg.wdtype == GTB_F16) return run_pass_f16(p, m, kv, sq, plan, t_cap, n_rows - 1, hr, eos_id, d_logits);
     return (m.cfg.wdtype == GTB_Q8) ? run_pass<DT_Q8>(p, m, kv, sq, plan, t_cap, n_rows - 1, hr, eos_id, d_logits)
                                     : run_pass<DT_Q4>(p, m, kv, sq, plan, t_cap, n_rows - 1, hr, eos_id, d_logits);
 }
@@ -973,6 +1376,7 @@ int xr_decode_pass(XrPlan* p, const XrModel& m, const XrKV& kv, const XrSeq& sq,
     XrPlanArgs plan{};
     plan.mode = 1; plan.n_rows = n_slots; plan.slot0 = 0; plan.tok_stride = sq.tok_stride;
     plan.tokens = sq.tokens; plan.st = sq.st; plan.rows = p->rows;
+    if (m.cfg.wdtype == GTB_F16) return run_pass_f16(p, m, kv, sq, plan, t_cap, 0, n_slots, eos_id, d_logits);
     return (m.cfg.wdtype == GTB_Q8) ? run_pass<DT_Q8>(p, m, kv, sq, plan, t_cap, 0, n_slots, eos_id, d_logits)
                                     : run_pass<DT_Q4>(p, m, kv, sq, plan, t_cap, 0, n_slots, eos_id, d_logits);
 }
