@@ -682,7 +682,7 @@ def main():
             out["e2e"] = {"value": units / (e2e_ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": 4,
                           "d2h_bytes_per_step": cfg.n_vocab * 4}
         out["exact_prefill"] = {"tokens": n_prompt, "ms": prefill_ms, "tokens_per_s": n_prompt / (prefill_ms * 1e-3),
-                                "path": "order-exact multi-row kernels (gtb_xrows.cu), 64 rows per pass: bit-identical to the reference's row loop"}
+                                "path": "order-exact multi-row kernels (gtb_xrows.cu), 512 rows per pass: bit-identical to the reference's row loop"}
         if world == 1 and not args.no_fast and wdt != W.F16:
             out["fast_decode"] = fast_decode_section(eng, capi, torch, stream, cfg, wdt, prompt, n_prompt, Wm, K, hbm_peak, peak_src,
                                                      e2e=not args.no_e2e)

@@ -61,7 +61,7 @@ public:
     void topk(int k, float* values, int32_t* ids) { GTEN_CUDA_OK(gtb_engine_topk(eng_, k, values, ids)); }
     // Batched decode (gtb_engine_batch_*, include/gten_b200.h): up to 64 sequences advance together and share every weight read,
     // through the ORDER-EXACT multi-row kernels: every slot's tokens are the reference's.  batch_prefill(s, ids, n) prefills a prompt
-    // straight into slot s (64 rows per pass); batch_adopt(s) moves the sequence of the last logits()/prefill call into slot s;
+    // straight into slot s (up to 512 rows per pass); batch_adopt(s) moves the sequence of the last logits()/prefill call into slot s;
     // batch_decode(k) runs k greedy steps of all slots.
     void batch_create(int n_seq) { GTEN_CUDA_OK(gtb_engine_batch_create(eng_, n_seq)); }
     void batch_prefill(int slot, const int32_t* ids, int n) { GTEN_CUDA_OK(gtb_engine_batch_prefill(eng_, slot, ids, n)); }

@@ -114,7 +114,7 @@ int gtb_engine_logits(gtb_engine_t e, const int32_t* h_tokens, int n_tokens, int
 int gtb_engine_generate(gtb_engine_t e, int32_t* h_tokens, int n_prompt, int n_new, int eos_id, int* n_generated);
 /* fine-grained control used by bench.py and the tests */
 int gtb_engine_reset(gtb_engine_t e);
-/* exact path, rows [0,n): Q8/Q4 models run them 64 at a time through the multi-row kernels (gtb_xrows.cu), bit-identical to
+/* exact path, rows [0,n): up to 512 rows per pass through the multi-row kernels (gtb_xrows.cu), bit-identical to
  * the reference's row loop (gten/ops.h:632); the last row also samples the first new token */
 int gtb_engine_prefill(gtb_engine_t e, const int32_t* h_tokens, int n_tokens);
 int gtb_engine_decode(gtb_engine_t e, int n_steps);                                /* n greedy steps, device-resident */
@@ -149,7 +149,7 @@ int gtb_engine_acv(gtb_engine_t e, int layer, int acv_id, float* h_out, int* wid
  * GEMM epilogues, default 1), "pf_pdl" (programmatic dependent launch, default 1), "pf_2cta" (CTA-pair tcgen05 GEMM, default 0),
  * "pf_attn2" (second attention sweep that also reproduces the fp16 rounding of the probability-row block scales, default 0),
  * "xrows" (1, default: runs of >= "xr_min_rows" (4) rows whose positions the host knows -- gtb_engine_prefill, _logits, _generate --
- * go through the order-exact multi-row kernels in passes of "xr_rows" (64) rows: same bits as the row-at-a-time kernels, one weight
+ * go through the order-exact multi-row kernels in passes of "xr_rows" (512, at most 1024) rows: same bits as the row-at-a-time kernels, one weight
  * read per pass; 0: every row through the persistent kernel), "batch_exact" (see gtb_engine_batch_*) */
 int gtb_engine_set_option(gtb_engine_t e, const char* name, int value);
 
@@ -159,7 +159,7 @@ int gtb_engine_set_option(gtb_engine_t e, const char* name, int value);
  * alone by gtb_engine_decode, i.e. to the reference.  "batch_exact" = 0: the order-free kernels (tolerance contract of "fast_decode",
  * at most 16 sequences).
  *   gtb_engine_batch_create(e, n)        allocate n slots (own K/V cache, tokens, position each); n = 0 frees them
- *   gtb_engine_batch_prefill(e, s, t, n) exact prefill of n prompt ids into slot s (multi-row passes of up to 64 rows), first token appended
+ *   gtb_engine_batch_prefill(e, s, t, n) exact prefill of n prompt ids into slot s (multi-row passes of up to 512 rows), first token appended
  *   gtb_engine_batch_adopt(e, s)         slot s <- the engine's current sequence (after gtb_engine_prefill / _prefill_fast / decode)
  *   gtb_engine_batch_decode(e, k)        k greedy steps of every slot (device-side argmax, tokens stay on the device)
  *   gtb_engine_batch_position / _read_tokens / _read_logits: per-slot state */

@@ -47,8 +47,14 @@ def test_exact_prefill_matches_reference(capi, checker, wdt, n_prompt):
     prompt = W.synth_prompt(9, n_prompt, cfg.n_vocab)
     want_toks, _, want_lg = cm.generate(prompt, n_new, want_logits=True)
     e = capi.Engine(cfg, max_ctx, wdt).load(wl)
+    e.set_option("xr_rows", 64)        # 64 rows per pass: prompts of 65, 100, 129, 190 rows cross pass boundaries
     got = e.logits(prompt, 0)
     assert np.array_equal(bits(got), bits(want_lg[0])), f"prefill logits differ from the {checker.kind} oracle"
+    e.set_option("xr_rows", 512)       # the default: one pass
+    assert np.array_equal(bits(e.logits(prompt, 0)), bits(got))
+    e.set_option("xr_rows", 24)        # small passes: the per-head attention kernel
+    assert np.array_equal(bits(e.logits(prompt, 0)), bits(got))
+    e.set_option("xr_rows", 64)
     toks = e.generate(prompt, n_new)
     assert np.array_equal(toks, want_toks), (toks[n_prompt:], want_toks[n_prompt:])
     assert np.array_equal(bits(e.read_logits()), bits(want_lg[-1]))

@@ -429,7 +429,7 @@ struct gtb_engine {
     gtb::XrPlan* xr = nullptr;
     bool use_xr = true;
     int xr_min_rows = 4;             // fewer rows than this stay on the row-at-a-time kernels
-    int xr_rows = XR_MAX_ROWS;       // rows per prefill pass
+    int xr_rows = 512;               // rows per prefill pass (2024-token prompt: 159 ms at 64 rows per pass, 107 ms at 512, 103 ms at 1024)
     bool batch_exact = true;         // gtb_engine_batch_decode through the exact multi-row kernels (false: order-free kernels)
     std::vector<XrLayerW> xr_layers;
     std::vector<uint8_t*> xr_kq, xr_vq;
@@ -1602,7 +1602,7 @@ int gtb_engine_batch_create(gtb_engine_t e, int n_seq) {
     GTB_ARG(e && n_seq >= 0);
     if (e->cfg.wdtype == GTB_F16 && !batch_is_exact(e)) return fail(GTB_ERR_STATE, "the order-free batched decode is built for Q8-activation models (Q8, Q4 weights)");
     if (batch_is_exact(e)) {
-        if (n_seq > XR_MAX_ROWS) return fail(GTB_ERR_ARG, "batched decode: at most %d sequences", XR_MAX_ROWS);
+        if (n_seq > XR_MAX_SLOTS) return fail(GTB_ERR_ARG, "batched decode: at most %d sequences", XR_MAX_SLOTS);
     } else {
         GTB_ARG(n_seq <= FDB_MAX);
         if (e->cfg.n_embd > 2048 || e->cfg.n_ffn > 6144) return fail(GTB_ERR_STATE, "batched decode: n_embd <= 2048 and n_ffn <= 6144");
@@ -1843,6 +1843,7 @@ int gtb_engine_set_option(gtb_engine_t e, const char* name, int value) {
     if (!strcmp(name, "xr_min_rows")) { GTB_ARG(value >= 1); e->xr_min_rows = value; return GTB_OK; }
     if (!strcmp(name, "xr_rows")) { GTB_ARG(value >= 1 && value <= XR_MAX_ROWS); e->xr_rows = value; return GTB_OK; }
     if (!strcmp(name, "batch_exact")) { e->batch_exact = value != 0; drop_graphs(e); return GTB_OK; }
+    if (!strcmp(name, "xr_variant")) { xr_set_variant(value); drop_graphs(e); return GTB_OK; }
     if (!strcmp(name, "xr_pdl")) { xr_set_pdl(value != 0); drop_graphs(e); return GTB_OK; }
     return fail(GTB_ERR_ARG, "unknown option %s", name);
 }

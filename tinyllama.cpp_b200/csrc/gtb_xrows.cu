@@ -207,8 +207,8 @@ struct XrGemmArgs {
 
 // NW warps per CTA, TR = 16 / NW rows per warp: (4, 4) amortises a weight block over 4 rows (fewest instructions; large N),
 // (8, 2) doubles the warps per tile for the matrices with few column tiles (N <= 2560: q|k|v, o, down)
-template <int WT, int EPI, int NW>
-__global__ void __launch_bounds__(NW * 32, (NW == 4) ? 4 : 2) k_xr_gemm(XrGemmArgs a) {
+template <int WT, int EPI, int NW, int NS = XG_STAGES, int MINB = (NW == 4) ? 4 : 2>
+__global__ void __launch_bounds__(NW * 32, MINB) k_xr_gemm(XrGemmArgs a) {
     constexpr int XG_NT = NW * 32, TR = XG_BM / NW;
     extern __shared__ __align__(16) unsigned char smem[];
     XgStage<WT>* stages = reinterpret_cast<XgStage<WT>*>(smem);
@@ -251,23 +251,23 @@ __global__ void __launch_bounds__(NW * 32, (NW == 4) ? 4 : 2) k_xr_gemm(XrGemmAr
             for (int l = 0; l < 4; l++) acc[r][c][l] = 0.0f;
     // weights never depend on the previous kernel of the chain: their first chunks are in flight before it has finished
 #pragma unroll
-    for (int s = 0; s < XG_STAGES - 1; s++)
+    for (int s = 0; s < NS - 1; s++)
         if (s < nchunk) load_weights(s, s);
     pdl_wait();
 #pragma unroll
-    for (int s = 0; s < XG_STAGES - 1; s++) {
+    for (int s = 0; s < NS - 1; s++) {
         if (s < nchunk) load_act(s, s);
         cp_async_commit();
     }
     for (int kc = 0; kc < nchunk; kc++) {
-        cp_async_wait<XG_STAGES - 2>();
+        cp_async_wait<NS - 2>();
         __syncthreads();
-        if (kc + XG_STAGES - 1 < nchunk) {
-            load_weights((kc + XG_STAGES - 1) % XG_STAGES, kc + XG_STAGES - 1);
-            load_act((kc + XG_STAGES - 1) % XG_STAGES, kc + XG_STAGES - 1);
+        if (kc + NS - 1 < nchunk) {
+            load_weights((kc + NS - 1) % NS, kc + NS - 1);
+            load_act((kc + NS - 1) % NS, kc + NS - 1);
         }
         cp_async_commit();
-        const XgStage<WT>& st = stages[kc % XG_STAGES];
+        const XgStage<WT>& st = stages[kc % NS];
         const uint4 sA = st.ws[lane], sB = st.ws[lane + 32];
         const __half* hA = reinterpret_cast<const __half*>(&sA);
         const __half* hB = reinterpret_cast<const __half*>(&sB);
@@ -1082,6 +1082,7 @@ __global__ void __launch_bounds__(XA_NT) k_xf_attn_head(XfAttnArgs a) {
 // resident CTAs of the next kernel take SM resources from the tail of the running one), so it is used for passes of <= 16 rows.
 static bool g_xr_pdl = true;
 static bool g_xr_pdl_now = false;
+static int g_xr_variant = 0;        // experiment switch for the large-N GEMM configuration
 
 struct XrPlan {
     gtb_model_config cfg{};
@@ -1097,6 +1098,7 @@ struct XrPlan {
 };
 
 void xr_set_pdl(bool on) { g_xr_pdl = on; }
+void xr_set_variant(int v) { g_xr_variant = v; }
 
 bool xr_supported(const gtb_model_config& c, int gsz) {
     return (c.wdtype == GTB_Q8 || c.wdtype == GTB_Q4 || c.wdtype == GTB_F16) && gsz == 8 && c.n_embd % 256 == 0 && c.n_ffn % 256 == 0 && c.n_embd / c.n_heads == 64 &&
@@ -1128,7 +1130,7 @@ int xr_create(XrPlan** out, const gtb_model_config& c) {
     }
     r |= dalloc((void**)&p->arg_val, R * p->n_tiles * 4);
     r |= dalloc((void**)&p->arg_idx, R * p->n_tiles * 4);
-    r |= dalloc((void**)&p->logits, R * c.n_vocab * 4);
+    r |= dalloc((void**)&p->logits, (size_t)XR_MAX_SLOTS * c.n_vocab * 4);      // only when a caller passes no logits buffer
     if (r) { xr_destroy(p); return fail(GTB_ERR_CUDA, "multi-row buffers: allocation failed"); }
     *out = p;
     return GTB_OK;
@@ -1155,16 +1157,16 @@ cudaError_t xr_launch(void (*kern)(KArgs...), dim3 grid, int block, size_t smem,
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
-template <int WT, int EPI, int NW>
+template <int WT, int EPI, int NW, int NS = XG_STAGES, int MINB = (NW == 4) ? 4 : 2>
 int launch_gemm_nw(const XrGemmArgs& a, int n_tiles) {
-    const size_t smem = sizeof(XgStage<WT>) * XG_STAGES;
+    const size_t smem = sizeof(XgStage<WT>) * NS;
     static bool attr = false;
     if (!attr) {
-        GTB_CUDA(cudaFuncSetAttribute(k_xr_gemm<WT, EPI, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GTB_CUDA(cudaFuncSetAttribute(k_xr_gemm<WT, EPI, NW, NS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
     dim3 grid(n_tiles, (a.n_rows + XG_BM - 1) / XG_BM);
-    GTB_CUDA(xr_launch(k_xr_gemm<WT, EPI, NW>, grid, NW * 32, smem, a));
+    GTB_CUDA(xr_launch(k_xr_gemm<WT, EPI, NW, NS, MINB>, grid, NW * 32, smem, a));
     GTB_LAUNCHED();
     return GTB_OK;
 }
@@ -1173,6 +1175,7 @@ int launch_gemm(const XrGemmArgs& a, int n_tiles) {
     // few column tiles: 8 warps x 2 rows per tile keep two warps per scheduler busy; many tiles: 4 warps x 4 rows
     const int ctas = n_tiles * ((a.n_rows + XG_BM - 1) / XG_BM);
     if (EPI != XEPI_SILU && EPI != XEPI_HEAD && ctas <= 2 * ctx().sm_count) return launch_gemm_nw<WT, EPI, 8>(a, n_tiles);
+    if (g_xr_variant == 1 && (EPI == XEPI_SILU || EPI == XEPI_HEAD)) return launch_gemm_nw<WT, EPI, 4, 2, 5>(a, n_tiles);   // 2 stages, 5 CTAs / SM
     return launch_gemm_nw<WT, EPI, 4>(a, n_tiles);
 }
 
@@ -1372,7 +1375,7 @@ int xr_prefill_pass(XrPlan* p, const XrModel& m, const XrKV& kv, const XrSeq& sq
 }
 
 int xr_decode_pass(XrPlan* p, const XrModel& m, const XrKV& kv, const XrSeq& sq, int n_slots, int t_cap, int eos_id, float* d_logits) {
-    if (n_slots <= 0 || n_slots > XR_MAX_ROWS) return fail(GTB_ERR_ARG, "multi-row pass: 1..%d rows", XR_MAX_ROWS);
+    if (n_slots <= 0 || n_slots > XR_MAX_SLOTS) return fail(GTB_ERR_ARG, "multi-row decode pass: 1..%d sequences", XR_MAX_SLOTS);
     XrPlanArgs plan{};
     plan.mode = 1; plan.n_rows = n_slots; plan.slot0 = 0; plan.tok_stride = sq.tok_stride;
     plan.tokens = sq.tokens; plan.st = sq.st; plan.rows = p->rows;

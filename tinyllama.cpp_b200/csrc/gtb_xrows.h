@@ -42,11 +42,13 @@ struct XrSeq {                         // token rows and positions of the slots
     DevState* st;                      // [n_slots]
 };
 
-constexpr int XR_MAX_ROWS = 64;        // rows per pass
+constexpr int XR_MAX_ROWS = 1024;      // rows per pass (prefill); the launch overheads and chain latencies of a pass are paid once per pass
+constexpr int XR_MAX_SLOTS = 64;       // sequences of a batched decode
 
 int xr_create(XrPlan** out, const gtb_model_config& cfg);
 void xr_destroy(XrPlan* p);
 bool xr_supported(const gtb_model_config& cfg, int gsz);
+void xr_set_variant(int v);          // tuning experiments (large-N GEMM configuration)
 void xr_set_pdl(bool on);            // programmatic dependent launch inside a pass (default on)
 
 // Prefill pass: rows = positions [p0, p0 + n_rows) of slot `slot`; n_ctx = the call's row count (P.V lane split, SURVEY

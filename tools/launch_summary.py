@@ -17,8 +17,9 @@ def main(path, split_gemm=True):
             name += " [" + ["q|k|v", "o", "gate|up", "down"][gi % 4] + "]"
             gi += 1
         if "k_xr_gemm" in name:
-            epi = name.split(",")[-1].strip(" >")
-            if "1" in epi:
+            targs = name[name.index("<") + 1:name.rindex(">")].split(",") if "<" in name else []
+            epi = targs[1].strip() if len(targs) > 1 else ""
+            if epi.replace("(int)", "") == "1":
                 name += " [" + ["o", "down"][ri % 2] + "]"
                 ri += 1
             else:

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--adopt", action="store_true", help="one prefill on the engine's own sequence, copied into every slot (few launches: for ncu)")
     ap.add_argument("--prefill-reps", type=int, default=2)
     ap.add_argument("--pdl", type=int, default=1)
+    ap.add_argument("--variant", type=int, default=0)
     args = ap.parse_args()
     wdt = W.WDTYPE_BY_NAME[args.wdt if args.wdt != "f16" else "fp16"]
     capi.init(0)
@@ -35,6 +36,7 @@ def main():
     eng = capi.Engine(cfg, args.max_ctx, wdt).load(W.synth_weights(cfg, wdt, seed=1))
     out = {}
     eng.set_option("xr_pdl", args.pdl)
+    eng.set_option("xr_variant", args.variant)
     if not args.skip_prefill:
         prompt = W.synth_prompt(7, args.prompt, cfg.n_vocab)
         if args.prefill_reps > 1:
