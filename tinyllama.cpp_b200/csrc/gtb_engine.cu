@@ -374,6 +374,7 @@ struct gtb_engine {
     bool use_mega = true;
     int pf_ahead = 4;
     bool prof = false;
+    int prof_cta = 0;                // which CTA of k_mega writes the stamps
     MegaLayer* d_layers = nullptr;
     bool layers_valid = false;
     unsigned long long *x_qkv = nullptr, *x_sc = nullptr, *x_attn = nullptr, *x_o = nullptr, *x_gu = nullptr, *x_act = nullptr,
@@ -966,7 +967,7 @@ int run_rows_mega(gtb_engine* e, int n_body, int n_head, int eos_id, int start_p
     p.x_down = e->x_down; p.x_arg = e->x_arg; p.cnt = e->cnt;
     p.logits = e->logits; p.tokens = e->tokens; p.st = e->st; p.epoch = e->epoch;
     p.n_body = n_body; p.n_head = n_head; p.eos_id = eos_id; p.pf_ahead = e->pf_ahead;
-    p.dbg = e->dbg; p.prof = e->prof ? e->d_prof : nullptr;
+    p.dbg = e->dbg; p.prof = e->prof ? e->d_prof : nullptr; p.prof_cta = e->prof_cta;
     switch (c.wdtype) {
         case GTB_F16: return launch_mega<DT_F16>(e, p);
         case GTB_Q8: return launch_mega<DT_Q8>(e, p);
@@ -1822,6 +1823,7 @@ int gtb_engine_set_option(gtb_engine_t e, const char* name, int value) {
     if (!strcmp(name, "mega")) { e->use_mega = value != 0; return GTB_OK; }
     if (!strcmp(name, "pf_ahead")) { GTB_ARG(value >= 0 && value <= 64); e->pf_ahead = value; return GTB_OK; }
     if (!strcmp(name, "prof")) { e->prof = value != 0; return GTB_OK; }
+    if (!strcmp(name, "prof_cta")) { GTB_ARG(value >= 0); e->prof_cta = value; return GTB_OK; }
     if (!strcmp(name, "fast_decode")) { e->fast = value != 0; drop_graphs(e); return GTB_OK; }
     if (!strcmp(name, "fd_ahead")) { GTB_ARG(value >= 0 && value <= 16); e->fd_ahead = value; drop_graphs(e); e->fd_args_valid = false; return GTB_OK; }
     if (!strcmp(name, "fd_chunk")) { GTB_ARG(value >= 32 && value <= 1024 && value % 32 == 0); e->fd_chunk = value; drop_graphs(e); return GTB_OK; }

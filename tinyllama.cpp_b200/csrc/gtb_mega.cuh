@@ -78,7 +78,8 @@ struct MegaParams {
     int n_body, n_head, eos_id;
     int pf_ahead;                          // L2 prefetch distance in GEMV phases
     ull* dbg;                              // [8] watchdog diagnostics
-    long long* prof;                       // optional: CTA 0 timestamps of the last row
+    long long* prof;                       // optional: timestamps of the last row, written by CTA prof_cta
+    int prof_cta;
 };
 
 // ---------------------------------------------------------------- exchange primitives
@@ -360,7 +361,9 @@ __device__ __forceinline__ float exact_sum512(LoadT load4, int n, ExactSum2Smem&
                 if (exmask & (1u << j)) sm.item[k++] = make_uint2(ibase + pre[j], __float_as_uint(tv[j]));
         }
         __syncthreads();                                   // (3)
-        if (tid == 0) {
+        {
+            // every thread walks the explicit items itself (shared-memory broadcasts): no result to publish, one barrier less.  The item
+            // buffer is not written again before all threads have passed the next call's first two barriers.
             uint32_t sb = __float_as_uint(s_run), prev = 0u;
             int k = 0;
             for (; k + 4 <= total; k += 4) {
@@ -381,10 +384,8 @@ __device__ __forceinline__ float exact_sum512(LoadT load4, int n, ExactSum2Smem&
                 sb = __float_as_uint(__fadd_rn(__uint_as_float(sb), __uint_as_float(it.y)));
             }
             sb += itotal - prev;
-            sm.result = __uint_as_float(sb);
+            s_run = __uint_as_float(sb);
         }
-        __syncthreads();                                   // (4)
-        s_run = sm.result;
         carry = __fadd_rn(carry, total_f);
     }
     return s_run;
@@ -946,13 +947,24 @@ __device__ __forceinline__ void mega_attn_b(const MegaParams& P, MegaSm& sm, flo
         const float* vl = vf + l * as.lst + cc * as.kp;
         float a = 0.0f;
         int k = 0;
-        for (; k + 8 <= nk; k += 8) {
-            const float4 p0 = *reinterpret_cast<const float4*>(pl + k), p1 = *reinterpret_cast<const float4*>(pl + k + 4);
-            const float4 v0 = *reinterpret_cast<const float4*>(vl + k), v1 = *reinterpret_cast<const float4*>(vl + k + 4);
+        if (nk >= 8) {
+            // the chain is 4 cycles per step; the 128-bit loads of the NEXT eight steps are issued before the chain of the current eight
+            float4 p0 = *reinterpret_cast<const float4*>(pl), p1 = *reinterpret_cast<const float4*>(pl + 4);
+            float4 v0 = *reinterpret_cast<const float4*>(vl), v1 = *reinterpret_cast<const float4*>(vl + 4);
+            for (; k + 16 <= nk; k += 8) {
+                const float4 np0 = *reinterpret_cast<const float4*>(pl + k + 8), np1 = *reinterpret_cast<const float4*>(pl + k + 12);
+                const float4 nv0 = *reinterpret_cast<const float4*>(vl + k + 8), nv1 = *reinterpret_cast<const float4*>(vl + k + 12);
+                a = __fadd_rn(__fmul_rn(p0.x, v0.x), a); a = __fadd_rn(__fmul_rn(p0.y, v0.y), a);
+                a = __fadd_rn(__fmul_rn(p0.z, v0.z), a); a = __fadd_rn(__fmul_rn(p0.w, v0.w), a);
+                a = __fadd_rn(__fmul_rn(p1.x, v1.x), a); a = __fadd_rn(__fmul_rn(p1.y, v1.y), a);
+                a = __fadd_rn(__fmul_rn(p1.z, v1.z), a); a = __fadd_rn(__fmul_rn(p1.w, v1.w), a);
+                p0 = np0; p1 = np1; v0 = nv0; v1 = nv1;
+            }
             a = __fadd_rn(__fmul_rn(p0.x, v0.x), a); a = __fadd_rn(__fmul_rn(p0.y, v0.y), a);
             a = __fadd_rn(__fmul_rn(p0.z, v0.z), a); a = __fadd_rn(__fmul_rn(p0.w, v0.w), a);
             a = __fadd_rn(__fmul_rn(p1.x, v1.x), a); a = __fadd_rn(__fmul_rn(p1.y, v1.y), a);
             a = __fadd_rn(__fmul_rn(p1.z, v1.z), a); a = __fadd_rn(__fmul_rn(p1.w, v1.w), a);
+            k += 8;
         }
         for (; k < nk; k++) a = __fadd_rn(__fmul_rn(pl[k], vl[k]), a);
         sm.part[l][cc] = a;
@@ -1064,10 +1076,10 @@ __device__ __forceinline__ void mega_embed(const MegaParams& P, int tok, float r
     }
 }
 
-// profiling stamps of CTA 0: (code, globaltimer) pairs; code = phase kind * 16 + step
+// profiling stamps of one CTA (option "prof_cta", default 0): (code, globaltimer) pairs; code = phase kind * 16 + step
 #define MEGA_PROF(code)                                                                                   \
     do {                                                                                                  \
-        if (P.prof && cta == 0 && threadIdx.x == 0) { P.prof[prof_i++] = (code); P.prof[prof_i++] = gtimer(); } \
+        if (P.prof && cta == P.prof_cta && threadIdx.x == 0) { P.prof[prof_i++] = (code); P.prof[prof_i++] = gtimer(); } \
     } while (0)
 
 template <int WT>
@@ -1222,13 +1234,13 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
                 const uint32_t tag_attn = ++ep;
                 if (cta < n_units) {
                     __syncthreads();                               // product staging is reused as attention scratch
-                    mega_attn_a<AT>(P, L, sm, ps, cta, pos, tag, tag_sc, (P.prof && cta == 0 && tid == 0) ? P.prof : nullptr, prof_i);
+                    mega_attn_a<AT>(P, L, sm, ps, cta, pos, tag, tag_sc, (P.prof && cta == P.prof_cta && tid == 0) ? P.prof : nullptr, prof_i);
                     if (defer_tile && more) load_tile<WT>(nx, sm.rr[nx.kind][0], min(tile_rows<WT>(nx.nb), sm.rr[nx.kind][1] - sm.rr[nx.kind][0]), w);
                     MEGA_PROF(kind * 16 + 5);
                     exp_sc += 4;
                     xwait(P.cnt + (CNT_SC0 + (cta >> 2)) * CNT_STRIDE, P.cnt + (CNT_SC0 + (cta >> 2)) * CNT_STRIDE, exp_sc, P.dbg);
                     MEGA_PROF(kind * 16 + 6);
-                    mega_attn_b<AT>(P, sm, ps, xbuf, cta, pos, n_ctx, tag_sc, tag_attn, (P.prof && cta == 0 && tid == 0) ? P.prof : nullptr, prof_i);
+                    mega_attn_b<AT>(P, sm, ps, xbuf, cta, pos, n_ctx, tag_sc, tag_attn, (P.prof && cta == P.prof_cta && tid == 0) ? P.prof : nullptr, prof_i);
                     __threadfence();                               // K/V appends visible before anything later is published
                 } else if (tid == 0 && AT != DT_F16) {
                     // the CTAs without an attention unit pull the NEXT layer's K/V rows (last touched a token ago) towards L2

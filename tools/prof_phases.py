@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--pf", type=int, default=-1)
     ap.add_argument("--layers", type=int, default=22)
+    ap.add_argument("--cta", type=int, default=0, help="which CTA writes the stamps")
     a = ap.parse_args()
     wdt = W.WDTYPE_BY_NAME[{"f16": "fp16"}.get(a.workload, a.workload)]
     capi.init(0)
@@ -42,6 +43,7 @@ def main():
     eng.prefill(W.synth_prompt(7, a.ctx, cfg.n_vocab))
     eng.decode(4)
     eng.set_option("prof", 1)
+    eng.set_option("prof_cta", a.cta)
     L = cfg.n_layers
     agg = {}
     tot = 0.0
@@ -56,7 +58,7 @@ def main():
             agg.setdefault(int(codes[i]), []).append(times[i] - times[i - 1])
         tot += times[n - 1] - times[0]
     tot /= a.steps
-    print(f"workload {a.workload} ctx {a.ctx}: row {tot / 1e3:.1f} us (with prof stamps), {L} layers")
+    print(f"workload {a.workload} ctx {a.ctx} cta {a.cta}: row {tot / 1e3:.1f} us (with prof stamps), {L} layers")
     total = 0.0
     for code in sorted(agg):
         v = np.array(agg[code])
