@@ -895,7 +895,7 @@ bool mega_ok(const gtb_engine* e) {
     // the persistent kernel is specialised for the TinyLlama dimensions (tinyllama.cpp:12-20); anything else takes
     // the one-kernel-per-phase path
     return e->use_mega && !e->fast && !e->capture && c.n_embd == ME && c.n_ffn == MF && c.n_heads == MH && c.n_groups * MGSZ == MH &&
-           e->grid >= MH * 4 && e->grid <= 1024 && c.max_ctx <= 4 * MT && attn_scratch_bytes(c.max_ctx) <= (size_t)PS_BYTES;
+           e->grid >= MH * 4 && e->grid <= 1024 && c.max_ctx <= 4 * MT && c.n_layers <= MEGA_MAX_LAYERS && attn_scratch_bytes(c.max_ctx) <= (size_t)PS_BYTES;
 }
 
 template <int WT>

@@ -43,6 +43,7 @@ constexpr int NBE = ME / 32, NBF = MF / 32;
 constexpr int PS_BYTES = 142 * 1024;       // product staging; during attention: probabilities + the unit's V slice as fp32
 constexpr int IT_Q4 = 10;                  // (row, block) items per thread per tile: MT*IT items in registers
 constexpr int IT_Q8 = 5;
+constexpr int MEGA_MAX_LAYERS = 32;        // the layer table is copied into shared memory (a phase descriptor is then 30 cycles away, not an L2 round trip)
 constexpr int SPIN_LIMIT = 1 << 24;        // ~ seconds; a stuck exchange traps instead of hanging the GPU
 static_assert(ME == MT * 4, "quad layout: 4 elements of an n_embd vector per thread");
 
@@ -410,6 +411,7 @@ struct MegaSm {
     float red[MWARP];
     float part[8][16];
     float bestv[MWARP]; int besti[MWARP];
+    MegaLayer layers[MEGA_MAX_LAYERS];
 };
 
 __host__ __device__ inline size_t mega_smem_bytes(int at) {
@@ -446,13 +448,13 @@ __device__ __forceinline__ int tile_rows(int nb) {
     }
 }
 
-__device__ __forceinline__ PhaseDesc phase_desc(const MegaParams& P, int s) {
+__device__ __forceinline__ PhaseDesc phase_desc(const MegaParams& P, const MegaLayer* layers, int s) {
     PhaseDesc pd;
     if (s >= 4 * P.n_layers) {
         pd.d = P.head_w; pd.s = P.head_s; pd.nb = NBE; pd.kind = 4;
         return pd;
     }
-    const MegaLayer& L = P.layers[s >> 2];
+    const MegaLayer& L = layers[s >> 2];
     const int k = s & 3;
     pd.d = L.w[k]; pd.s = L.s[k]; pd.nb = (k == 3) ? NBF : NBE; pd.kind = k;
     return pd;
@@ -596,10 +598,13 @@ __device__ __forceinline__ float f16_row_lane(const uint4* __restrict__ src, int
 
 // One GEMV phase over this CTA's rows [r0, r1).  sink(row, value) is called by one thread per finished row.
 // For Q4/Q8 `w` holds the first tile's weights on entry; on exit it holds the first tile of `next` (if next_valid).
-template <int WT, typename Sink>
+template <int WT, typename Sink, typename Bg>
 __device__ __forceinline__ void gemv_phase(const PhaseDesc& pd, int r0, int r1, const ActView& av, float* ps, WRegs<WT>& w,
-                                           const PhaseDesc& next, int n0, int n1, bool next_valid, Sink sink) {
+                                           const PhaseDesc& next, int n0, int n1, bool next_valid, Sink sink, Bg background,
+                                           long long* prof = nullptr, int* prof_ip = nullptr, int prof_base = 0) {
+#define GEMV_PROF(code) do { if (prof) { prof[(*prof_ip)++] = prof_base + (code); prof[(*prof_ip)++] = gtimer(); } } while (0)
     if (WT == DT_F16) {
+        background();
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, rl = lane >> 3, l = lane & 7;
         const int cpr = pd.nb / 2;                                   // 64-element chunks per row
         for (int row0 = r0 + wid * 4; row0 < r1; row0 += MWARP * 4) {
@@ -618,14 +623,23 @@ __device__ __forceinline__ void gemv_phase(const PhaseDesc& pd, int r0, int r1, 
     for (int t0 = r0; t0 < r1; t0 += tr) {
         const int nrows = min(tr, r1 - t0);
         tile_products<WT>(nb, nrows, w, av, ps);
+        GEMV_PROF(0);
         if (t0 + tr < r1) load_tile<WT>(pd, t0 + tr, min(tr, r1 - t0 - tr), w);
         else if (next_valid) load_tile<WT>(next, n0, min(tile_rows<WT>(next.nb), n1 - n0), w);
+        GEMV_PROF(1);
         __syncthreads();
+        GEMV_PROF(2);
+        if (t0 == r0) background();       // off the critical path: runs in a warp that owns no chain while the chains run
         const float v = tile_chain(nb, nrows, ps);
+        GEMV_PROF(3);
         if ((threadIdx.x & 3) == 0 && threadIdx.x < nrows * 4) sink(t0 + (threadIdx.x >> 2), v);
         if (t0 + tr < r1) __syncthreads();
     }
-    if (r1 <= r0 && next_valid) load_tile<WT>(next, n0, min(tile_rows<WT>(next.nb), n1 - n0), w);
+    if (r1 <= r0) {
+        background();
+        if (next_valid) load_tile<WT>(next, n0, min(tile_rows<WT>(next.nb), n1 - n0), w);
+    }
+#undef GEMV_PROF
 }
 
 // ---------------------------------------------------------------- attention, unit = (head h, quarter j)
@@ -1095,6 +1109,9 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
     unsigned int ep = *reinterpret_cast<volatile unsigned int*>(P.epoch);
     const int n_units = MH * 4;
     const int nL4 = 4 * P.n_layers;                // GEMV phases of a row without the lm_head
+    static_assert(sizeof(MegaLayer) % 8 == 0, "layer table is copied as 64-bit words");
+    for (int i = tid; i < P.n_layers * (int)(sizeof(MegaLayer) / 8); i += MT)
+        reinterpret_cast<ull*>(sm.layers)[i] = reinterpret_cast<const ull*>(P.layers)[i];
     if (tid < 5) {
         const int R = (tid == 0) ? ME + 2 * MKV : ((tid == 2) ? 2 * MF : ((tid == 4) ? P.n_vocab : ME));
         sm.rr[tid][0] = (int)(((long long)cta * R) / G);
@@ -1111,10 +1128,10 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
     int n_gen = 0, stop = P.st->stop, next_tok = -1;      // an EOS sampled by the multi-row prefill's last row stops this launch too
     __syncthreads();
     WRegs<WT> w;
-    PhaseDesc pd = phase_desc(P, 0);
+    PhaseDesc pd = phase_desc(P, sm.layers, 0);
     if (WT != DT_F16) load_tile<WT>(pd, sm.rr[0][0], min(tile_rows<WT>(pd.nb), sm.rr[0][1] - sm.rr[0][0]), w);
     if (tid == 0) {
-        for (int a = 1; a < P.pf_ahead && a < nL4; a++) prefetch_rows<WT>(phase_desc(P, a), sm.rr[a & 3][0], sm.rr[a & 3][1]);
+        for (int a = 1; a < P.pf_ahead && a < nL4; a++) prefetch_rows<WT>(phase_desc(P, sm.layers, a), sm.rr[a & 3][0], sm.rr[a & 3][1]);
     }
     float res[4] = {0.0f, 0.0f, 0.0f, 0.0f};      // this thread's quad of the residual stream
     const int e0 = quad_e0(tid);
@@ -1133,7 +1150,7 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
         uint32_t tag_in = 0;                        // tag of the exchange the next prologue consumes
         for (int s = 0; s < nphase; s++) {
             const int kind = pd.kind;
-            const MegaLayer& L = P.layers[min(s >> 2, P.n_layers - 1)];
+            const MegaLayer& L = sm.layers[min(s >> 2, P.n_layers - 1)];
             // ---------------- prologue: wait for the input vector and stage it as this phase's GEMV input
             if (kind == 3) {
                 exp_act += NBF;
@@ -1200,17 +1217,22 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
             // ---------------- GEMV
             const uint32_t tag = ++ep;
             const int r0 = sm.rr[kind][0], r1 = sm.rr[kind][1];
-            if (tid == 0 && P.pf_ahead > 0) {       // L2 prefetch of this CTA's rows, pf_ahead phases ahead (wraps into the next row)
-                int t = s + P.pf_ahead;
-                bool ok = true;
-                if (t >= nphase) { t -= nphase; ok = !last_row && t < nL4; }
-                if (ok) {
-                    const PhaseDesc pf = phase_desc(P, t);
-                    prefetch_rows<WT>(pf, sm.rr[pf.kind][0], sm.rr[pf.kind][1]);
+            // L2 prefetch of this CTA's rows, pf_ahead phases ahead (wraps into the next row).  Issuing the two bulk-prefetch instructions
+            // blocks the issuing thread for ~0.45 us whatever their size: they go out from the last warp (it owns no ordered chain) after
+            // the product barrier, while the other warps run the chains
+            auto background = [&]() {
+                if (tid == MT - 32 && P.pf_ahead > 0) {
+                    int t = s + P.pf_ahead;
+                    bool ok = true;
+                    if (t >= nphase) { t -= nphase; ok = !last_row && t < nL4; }
+                    if (ok) {
+                        const PhaseDesc pf = phase_desc(P, sm.layers, t);
+                        prefetch_rows<WT>(pf, sm.rr[pf.kind][0], sm.rr[pf.kind][1]);
+                    }
                 }
-            }
+            };
             const bool more = (s + 1 < nphase) || !last_row;
-            const PhaseDesc nx = phase_desc(P, (s + 1 < nphase) ? s + 1 : 0);
+            const PhaseDesc nx = phase_desc(P, sm.layers, (s + 1 < nphase) ? s + 1 : 0);
             ull* outp = (kind == 0) ? P.x_qkv : ((kind == 1) ? P.x_o : ((kind == 2) ? P.x_gu : P.x_down));
             float best = -INFINITY;
             int arg = 0x7fffffff;
@@ -1224,7 +1246,7 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
                 } else {
                     ll_store(outp + row, __float_as_uint(v), tag);
                 }
-            });
+            }, background, (P.prof && cta == P.prof_cta && tid == 0) ? P.prof : nullptr, &prof_i, 128 + kind * 8);
             pd = nx;
             tag_in = tag;
             MEGA_PROF(kind * 16 + 4);
@@ -1245,7 +1267,7 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
                 } else if (tid == 0 && AT != DT_F16) {
                     // the CTAs without an attention unit pull the NEXT layer's K/V rows (last touched a token ago) towards L2
                     const int nl = (s >> 2) + 1;
-                    const MegaLayer& LN = P.layers[(nl < P.n_layers) ? nl : 0];     // after the last layer: layer 0 of the next row
+                    const MegaLayer& LN = sm.layers[(nl < P.n_layers) ? nl : 0];     // after the last layer: layer 0 of the next row
                     const int nidle = G - n_units, me = cta - n_units;
                     const size_t rows0 = ((size_t)pos * me) / nidle, rows1 = ((size_t)pos * (me + 1)) / nidle;
                     if (rows1 > rows0 && (nl < P.n_layers || !last_row)) {

@@ -18,11 +18,12 @@ import gtb  # noqa: E402,F401
 from tinyllama_cpp_b200 import capi, weights as W  # noqa: E402
 
 KIND = {0: "P1 q|k|v", 1: "P3 o", 2: "P4 gate|up", 3: "P5 down", 4: "head", 5: "  P2b", 6: "  P2a"}
+GEMV = {0: "gemv: products of the tile", 1: "gemv: next tile loads issued", 2: "gemv: barrier", 3: "gemv: ordered chain"}
 SUB = {80: "scores loaded (LL words)", 81: "max over the row", 82: "expf x 4", 83: "exact in-order sum", 84: "p = e / sum, re-encode, publish to smem",
        85: "P.V lane chains", 96: "V slice arrived, decoded, staged", 99: "entry barrier + K row loads issued", 100: "V loads issued", 97: "wait: this row's q, k, v", 98: "E / RoPE / E of q, k, v"}
 STEP = {0: "wait for input (exchange)", 1: "LL loads + residual/encodes + squares", 2: "exact in-order sum", 3: "normalise/encode/stage (prologue done)",
         4: "gemv (products, chain, publish)", 5: "P2a: q/k/v encode, rope, scores", 6: "P2: wait scores", 7: "P2b: softmax, P.V",
-        8: "P4b: silu*up", 9: "argmax exchange"}
+        8: "P4b: silu*up", 9: "argmax exchange", 10: "L2 prefetch instructions issued (thread 0)"}
 
 
 def main():
@@ -64,7 +65,11 @@ def main():
         v = np.array(agg[code])
         per_row = v.sum() / a.steps
         total += per_row
-        print(f"  {KIND[code >> 4]:11s} {SUB.get(code, STEP.get(code & 15, '?')):46s} mean {v.mean():8.0f} ns  x{len(v) // a.steps:3d} = {per_row / 1e3:7.1f} us/row")
+        if code >= 128:
+            kname, sname = "  " + KIND[(code - 128) >> 3], GEMV[(code - 128) & 7]
+        else:
+            kname, sname = KIND[code >> 4], SUB.get(code, STEP.get(code & 15, '?'))
+        print(f"  {kname:11s} {sname:46s} mean {v.mean():8.0f} ns  x{len(v) // a.steps:3d} = {per_row / 1e3:7.1f} us/row")
     print(f"  sum {total / 1e3:.1f} us")
 
 
