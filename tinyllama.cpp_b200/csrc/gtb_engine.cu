@@ -1845,6 +1845,7 @@ int gtb_engine_set_option(gtb_engine_t e, const char* name, int value) {
     if (!strcmp(name, "xr_min_rows")) { GTB_ARG(value >= 1); e->xr_min_rows = value; return GTB_OK; }
     if (!strcmp(name, "xr_rows")) { GTB_ARG(value >= 1 && value <= XR_MAX_ROWS); e->xr_rows = value; return GTB_OK; }
     if (!strcmp(name, "batch_exact")) { e->batch_exact = value != 0; drop_graphs(e); return GTB_OK; }
+    if (!strcmp(name, "xr_tensor")) { xr_set_tensor(value != 0); drop_graphs(e); return GTB_OK; }
     if (!strcmp(name, "xr_variant")) { xr_set_variant(value); drop_graphs(e); return GTB_OK; }
     if (!strcmp(name, "xr_pdl")) { xr_set_pdl(value != 0); drop_graphs(e); return GTB_OK; }
     return fail(GTB_ERR_ARG, "unknown option %s", name);

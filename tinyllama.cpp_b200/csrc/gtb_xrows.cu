@@ -21,6 +21,7 @@
 // The GEMM is a SIMT kernel on purpose: the contract is integer lane sums (dp4a) followed by ORDERED fp32 adds, which
 // tensor cores cannot express.  CTA = 4 warps = 16 rows x 64 output columns; lane = column (2 per lane), warp = 4 rows;
 // weights and staged rows stream through a 3-stage cp.async ring in chunks of 8 blocks (256 elements of K).
+#include <algorithm>
 #include <vector>
 
 #include "gtb_xrows.h"
@@ -205,6 +206,76 @@ struct XrGemmArgs {
     float* logits; int ld_logits; float* arg_val; int* arg_idx; int n_tiles;   // EPI_HEAD
 };
 
+// The epilogue of one (row, 64-column tile n) for one warp: lane = column inside each 32-block (v[0]: column 64 n + lane, v[1]: column
+// 64 n + 32 + lane; gate|up: gate channel 32 n + lane and up channel 32 n + lane), every re-encode is warp-local.  Shared by the SIMT
+// GEMM (accumulators in registers) and the tensor-core GEMM's epilogue kernel (accumulated rows read back from HBM).
+template <int EPI>
+__device__ __forceinline__ void xr_epilogue(const XrGemmArgs& a, int row, const XrRow& rw, int n, int lane, const float (&v)[2], bool store_logits) {
+    if (EPI == XEPI_RES) {
+        // Residual (gten/ops.h:870-898): x = E(x + E(linear output))
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            float* px = a.res + (size_t)row * a.E + 64 * n + 32 * c + lane;
+            const float d1 = q8_roundtrip_lane(v[c]);
+            *px = q8_roundtrip_lane(__fadd_rn(*px, d1));
+        }
+    } else if (EPI == XEPI_SILU) {
+        // gten/modules.cpp:238-247: E(E(silu(E(gate))) * E(up))
+        const float g1 = q8_roundtrip_lane(v[0]);
+        const float u1 = q8_roundtrip_lane(v[1]);
+        const float g2 = q8_roundtrip_lane(silu_ref(g1));
+        uint16_t dh;
+        const int q = q8_encode_lane(__fmul_rn(g2, u1), &dh);
+        xblk_store(a.out + (size_t)row * a.out_nb + n, lane, q, dh);
+    } else if (EPI == XEPI_QKV) {
+        const int pos = rw.pos;
+        if (n < a.n_heads + a.n_groups) {
+            // q / k head: E, RoPE on the pair (j, j + 32) (ops.h:733-751), E
+            const float x0 = q8_roundtrip_lane(v[0]), x1 = q8_roundtrip_lane(v[1]);
+            const float cs = __ldg(a.rope_cos + (size_t)pos * 32 + lane), sn = __ldg(a.rope_sin + (size_t)pos * 32 + lane);
+            const float o0 = __fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn));
+            const float o1 = __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs));
+            uint16_t dh0, dh1;
+            const int q0 = q8_encode_lane(o0, &dh0), q1 = q8_encode_lane(o1, &dh1);
+            if (n < a.n_heads) {
+                XBlk* dst = a.out + ((size_t)row * a.n_heads + n) * 2;
+                xblk_store(dst, lane, q0, dh0);
+                xblk_store(dst + 1, lane, q1, dh1);
+            } else {
+                const int g = n - a.n_heads;
+                const uint32_t w0 = perm_word(lane, q0), w1 = perm_word(lane, q1);
+                uint32_t* kc = reinterpret_cast<uint32_t*>(a.kq + (size_t)rw.slot * a.slot_codes + (size_t)pos * a.kv_dim + g * 64);
+                uint16_t* ks = a.ks + (size_t)rw.slot * a.slot_scales + (size_t)pos * (a.kv_dim / 32) + g * 2;
+                if (lane < 8) { kc[lane] = w0; kc[8 + lane] = w1; }
+                if (lane == 8) { ks[0] = dh0; ks[1] = dh1; }
+            }
+        } else {
+            const int g = n - a.n_heads - a.n_groups;
+            uint16_t dh0, dh1;
+            const int q0 = q8_encode_lane(v[0], &dh0), q1 = q8_encode_lane(v[1], &dh1);
+            const uint32_t w0 = natural_word(lane, q0), w1 = natural_word(lane, q1);
+            uint32_t* vc = reinterpret_cast<uint32_t*>(a.vq + (size_t)rw.slot * a.slot_codes + (size_t)pos * a.kv_dim + g * 64);
+            uint16_t* vs = a.vs + (size_t)rw.slot * a.slot_scales + (size_t)pos * (a.kv_dim / 32) + g * 2;
+            if (lane < 8) { vc[lane] = w0; vc[8 + lane] = w1; }
+            if (lane == 8) { vs[0] = dh0; vs[1] = dh1; }
+        }
+    } else {
+        // lm_head (modules.cpp:70-81): fp32 logits + the tile's first maximum (tinyllama.cpp:416-424)
+        const int c0 = 64 * n + lane, c1 = c0 + 32;
+        float best = -INFINITY;
+        int arg = 0x7fffffff;
+        if (c0 < a.N) { if (store_logits) a.logits[(size_t)(row - a.row0) * a.ld_logits + c0] = v[0]; if (v[0] > best) { best = v[0]; arg = c0; } }
+        if (c1 < a.N) { if (store_logits) a.logits[(size_t)(row - a.row0) * a.ld_logits + c1] = v[1]; if (v[1] > best) { best = v[1]; arg = c1; } }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
+        }
+        if (lane == 0) { a.arg_val[(size_t)row * a.n_tiles + n] = best; a.arg_idx[(size_t)row * a.n_tiles + n] = arg; }
+    }
+}
+
 // NW warps per CTA, TR = 16 / NW rows per warp: (4, 4) amortises a weight block over 4 rows (fewest instructions; large N),
 // (8, 2) doubles the warps per tile for the matrices with few column tiles (N <= 2560: q|k|v, o, down)
 template <int WT, int EPI, int NW, int NS = XG_STAGES, int MINB = (NW == 4) ? 4 : 2>
@@ -332,73 +403,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_xr_gemm(XrGemmArgs a) {
 #pragma unroll
         for (int c = 0; c < 2; c++)
             v[c] = __fadd_rn(__fadd_rn(acc[r][c][0], acc[r][c][1]), __fadd_rn(acc[r][c][2], acc[r][c][3]));
-        if (EPI == XEPI_RES) {
-            // Residual (gten/ops.h:870-898): x = E(x + E(linear output))
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-                float* px = a.res + (size_t)row * a.E + 64 * n + 32 * c + lane;
-                const float d1 = q8_roundtrip_lane(v[c]);
-                *px = q8_roundtrip_lane(__fadd_rn(*px, d1));
-            }
-        } else if (EPI == XEPI_SILU) {
-            // gten/modules.cpp:238-247: E(E(silu(E(gate))) * E(up))
-            const float g1 = q8_roundtrip_lane(v[0]);
-            const float u1 = q8_roundtrip_lane(v[1]);
-            const float g2 = q8_roundtrip_lane(silu_ref(g1));
-            uint16_t dh;
-            const int q = q8_encode_lane(__fmul_rn(g2, u1), &dh);
-            xblk_store(a.out + (size_t)row * a.out_nb + n, lane, q, dh);
-        } else if (EPI == XEPI_QKV) {
-            const int pos = rw.pos;
-            if (n < a.n_heads + a.n_groups) {
-                // q / k head: E, RoPE on the pair (j, j + 32) (ops.h:733-751), E
-                const float x0 = q8_roundtrip_lane(v[0]), x1 = q8_roundtrip_lane(v[1]);
-                const float cs = __ldg(a.rope_cos + (size_t)pos * 32 + lane), sn = __ldg(a.rope_sin + (size_t)pos * 32 + lane);
-                const float o0 = __fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn));
-                const float o1 = __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs));
-                uint16_t dh0, dh1;
-                const int q0 = q8_encode_lane(o0, &dh0), q1 = q8_encode_lane(o1, &dh1);
-                if (n < a.n_heads) {
-                    XBlk* dst = a.out + ((size_t)row * a.n_heads + n) * 2;
-                    xblk_store(dst, lane, q0, dh0);
-                    xblk_store(dst + 1, lane, q1, dh1);
-                } else {
-                    const int g = n - a.n_heads;
-                    const uint32_t w0 = perm_word(lane, q0), w1 = perm_word(lane, q1);
-                    uint32_t* kc = reinterpret_cast<uint32_t*>(a.kq + (size_t)rw.slot * a.slot_codes + (size_t)pos * a.kv_dim + g * 64);
-                    uint16_t* ks = a.ks + (size_t)rw.slot * a.slot_scales + (size_t)pos * (a.kv_dim / 32) + g * 2;
-                    if (lane < 8) { kc[lane] = w0; kc[8 + lane] = w1; }
-                    if (lane == 8) { ks[0] = dh0; ks[1] = dh1; }
-                }
-            } else {
-                const int g = n - a.n_heads - a.n_groups;
-                uint16_t dh0, dh1;
-                const int q0 = q8_encode_lane(v[0], &dh0), q1 = q8_encode_lane(v[1], &dh1);
-                const uint32_t w0 = natural_word(lane, q0), w1 = natural_word(lane, q1);
-                uint32_t* vc = reinterpret_cast<uint32_t*>(a.vq + (size_t)rw.slot * a.slot_codes + (size_t)pos * a.kv_dim + g * 64);
-                uint16_t* vs = a.vs + (size_t)rw.slot * a.slot_scales + (size_t)pos * (a.kv_dim / 32) + g * 2;
-                if (lane < 8) { vc[lane] = w0; vc[8 + lane] = w1; }
-                if (lane == 8) { vs[0] = dh0; vs[1] = dh1; }
-            }
-        } else {
-            // lm_head (modules.cpp:70-81): fp32 logits + the tile's first maximum (tinyllama.cpp:416-424)
-            const int c0 = 64 * n + lane, c1 = c0 + 32;
-            float best = -INFINITY;
-            int arg = 0x7fffffff;
-            if (c0 < a.N) { a.logits[(size_t)(row - a.row0) * a.ld_logits + c0] = v[0]; if (v[0] > best) { best = v[0]; arg = c0; } }
-            if (c1 < a.N) { a.logits[(size_t)(row - a.row0) * a.ld_logits + c1] = v[1]; if (v[1] > best) { best = v[1]; arg = c1; } }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
-                if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
-            }
-            if (lane == 0) { a.arg_val[(size_t)row * a.n_tiles + n] = best; a.arg_idx[(size_t)row * a.n_tiles + n] = arg; }
-        }
+        xr_epilogue<EPI>(a, row, rw, n, lane, v, true);
     }
 }
 
 // ---------------------------------------------------------------- argmax over the tiles + bookkeeping (tinyllama.cpp:416-434)
+#include "gtb_xtensor.cuh"
+
 struct XrArgmaxArgs {
     const XrRow* rows;
     int row0;
@@ -1083,6 +1094,7 @@ __global__ void __launch_bounds__(XA_NT) k_xf_attn_head(XfAttnArgs a) {
 static bool g_xr_pdl = true;
 static bool g_xr_pdl_now = false;
 static int g_xr_variant = 0;        // experiment switch for the large-N GEMM configuration
+static bool g_xr_tensor = true;     // Q4 / Q8 Linears on the tensor cores (gtb_xtensor.cuh); false: the SIMT kernel k_xr_gemm
 
 struct XrPlan {
     gtb_model_config cfg{};
@@ -1093,12 +1105,14 @@ struct XrPlan {
     int* arg_idx = nullptr;
     float* logits = nullptr;           // [XR_MAX_ROWS][n_vocab] when the caller passes none
     float *f_norm = nullptr, *f_attn = nullptr, *f_mlp = nullptr, *f_q = nullptr;   // FP16 models: staged fp32 rows
+    float* raw = nullptr; int ld_raw = 0;   // tensor-core GEMM: finished fp32 rows of one Linear [XR_MAX_ROWS][ld_raw]
     int n_tiles = 0;
     size_t bytes = 0;
 };
 
 void xr_set_pdl(bool on) { g_xr_pdl = on; }
 void xr_set_variant(int v) { g_xr_variant = v; }
+void xr_set_tensor(bool on) { g_xr_tensor = on; }
 
 bool xr_supported(const gtb_model_config& c, int gsz) {
     return (c.wdtype == GTB_Q8 || c.wdtype == GTB_Q4 || c.wdtype == GTB_F16) && gsz == 8 && c.n_embd % 256 == 0 && c.n_ffn % 256 == 0 && c.n_embd / c.n_heads == 64 &&
@@ -1127,6 +1141,8 @@ int xr_create(XrPlan** out, const gtb_model_config& c) {
         r |= dalloc((void**)&p->act_attn, R * (c.n_embd / 32) * sizeof(XBlk));
         r |= dalloc((void**)&p->act_mlp, R * (c.n_ffn / 32) * sizeof(XBlk));
         r |= dalloc((void**)&p->qst, R * c.n_heads * 2 * sizeof(XBlk));
+        p->ld_raw = std::max(2 * c.n_ffn, c.n_embd + 2 * 64 * c.n_groups);
+        r |= dalloc((void**)&p->raw, R * (size_t)p->ld_raw * 4);
     }
     r |= dalloc((void**)&p->arg_val, R * p->n_tiles * 4);
     r |= dalloc((void**)&p->arg_idx, R * p->n_tiles * 4);
@@ -1138,7 +1154,7 @@ int xr_create(XrPlan** out, const gtb_model_config& c) {
 
 void xr_destroy(XrPlan* p) {
     if (!p) return;
-    void* b[] = {p->rows, p->res, p->act_norm, p->act_attn, p->act_mlp, p->qst, p->arg_val, p->arg_idx, p->logits, p->f_norm, p->f_attn, p->f_mlp, p->f_q};
+    void* b[] = {p->rows, p->res, p->act_norm, p->act_attn, p->act_mlp, p->qst, p->arg_val, p->arg_idx, p->logits, p->f_norm, p->f_attn, p->f_mlp, p->f_q, p->raw};
     for (void* q : b) cudaFree(q);
     ctx().mem -= (int64_t)p->bytes;
     delete p;
@@ -1179,12 +1195,59 @@ int launch_gemm(const XrGemmArgs& a, int n_tiles) {
     return launch_gemm_nw<WT, EPI, 4>(a, n_tiles);
 }
 
+// ---- tensor-core Linear (gtb_xtensor.cuh): rows per thread chosen so that the (tile, row group) units fill the SMs
+template <int WT, int RPT>
+int launch_xt_rpt(const XtGemmArgs& a) {
+    using Cfg = XtCfg<WT, RPT>;
+    static bool attr = false;
+    if (!attr) {
+        GTB_CUDA(cudaFuncSetAttribute(k_xt_gemm<WT, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr = true;
+    }
+    dim3 grid((a.N + XT_BM - 1) / XT_BM, (a.n_rows + Cfg::ROWS - 1) / Cfg::ROWS);
+    GTB_CUDA(xr_launch(k_xt_gemm<WT, RPT>, grid, XT_NT, Cfg::SMEM, a));
+    GTB_LAUNCHED();
+    return GTB_OK;
+}
+template <int WT>
+int launch_xt(const XtGemmArgs& a) {
+    const int tiles = (a.N + XT_BM - 1) / XT_BM, sms = ctx().sm_count;
+    int best = 16;
+    long best_cost = -1;
+    for (int rpt = 16; rpt >= 2; rpt >>= 1) {
+        const long units = (long)tiles * ((a.n_rows + 4 * rpt - 1) / (4 * rpt));
+        const long cost = ((units + sms - 1) / sms) * (90 + 60 * rpt);       // cycles per K block: fixed part + per row of a thread
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = rpt; }
+    }
+    if (g_xr_variant >= 2) best = g_xr_variant;                               // tuning experiments: force the shape
+    switch (best) {
+        case 16: return launch_xt_rpt<WT, 16>(a);
+        case 8: return launch_xt_rpt<WT, 8>(a);
+        case 4: return launch_xt_rpt<WT, 4>(a);
+        default: return launch_xt_rpt<WT, 2>(a);
+    }
+}
+// one Linear of the pass: tensor-core GEMM + re-encode epilogue kernel, or the SIMT kernel with the fused epilogue
+template <int WT, int EPI>
+int xr_linear(XrPlan* p, const XrGemmArgs& a, int n_tiles) {
+    if (!g_xr_tensor) return launch_gemm<WT, EPI>(a, n_tiles);
+    XtGemmArgs t{};
+    t.act = a.act; t.nb = a.nb; t.wd = a.wd; t.ws = a.ws; t.N = a.N; t.row0 = a.row0; t.n_rows = a.n_rows;
+    if (EPI == XEPI_HEAD) { t.out = a.logits; t.ldo = a.ld_logits; t.out_row_sub = a.row0; }
+    else { t.out = p->raw; t.ldo = p->ld_raw; t.out_row_sub = 0; }
+    int r = launch_xt<WT>(t);
+    if (r) return r;
+    GTB_CUDA(xr_launch(k_xt_epi<EPI>, dim3(n_tiles, (a.n_rows + 7) / 8), 256, 0, a, (const float*)t.out, t.ldo));
+    GTB_LAUNCHED();
+    return GTB_OK;
+}
+
 template <int WT>
 int run_pass(XrPlan* p, const XrModel& m, const XrKV& kv, const XrSeq& sq, const XrPlanArgs& plan, int t_cap, int head_row0,
              int head_rows, int eos_id, float* d_logits) {
     const gtb_model_config& c = m.cfg;
     const int E = c.n_embd, F = c.n_ffn, KVD = 64 * c.n_groups, R = plan.n_rows;
-    g_xr_pdl_now = g_xr_pdl && R <= 16;
+    g_xr_pdl_now = g_xr_pdl && R <= 16 && !g_xr_tensor;      // the tensor-core kernels do not carry the dependent-launch protocol
     GTB_CUDA(xr_launch(k_xr_plan, dim3(1), XR_MAX_ROWS, 0, plan));
     GTB_LAUNCHED();
     const size_t norm_smem = (size_t)E * 8;
@@ -1217,7 +1280,7 @@ int run_pass(XrPlan* p, const XrModel& m, const XrKV& kv, const XrSeq& sq, const
             XrGemmArgs a = base;
             a.act = p->act_norm; a.nb = E / 32; a.wd = L.w[0]; a.ws = L.s[0]; a.N = E + 2 * KVD;
             a.out = p->qst; a.kq = kv.kq[li]; a.ks = kv.ks[li]; a.vq = kv.vq[li]; a.vs = kv.vs[li];
-            if ((r = launch_gemm<WT, XEPI_QKV>(a, a.N / 64))) return r;
+            if ((r = xr_linear<WT, XEPI_QKV>(p, a, a.N / 64))) return r;
         }
         {
             XrAttnArgs a{};
@@ -1231,19 +1294,19 @@ int run_pass(XrPlan* p, const XrModel& m, const XrKV& kv, const XrSeq& sq, const
         {
             XrGemmArgs a = base;
             a.act = p->act_attn; a.nb = E / 32; a.wd = L.w[1]; a.ws = L.s[1]; a.N = E;
-            if ((r = launch_gemm<WT, XEPI_RES>(a, E / 64))) return r;
+            if ((r = xr_linear<WT, XEPI_RES>(p, a, E / 64))) return r;
         }
         if ((r = norm(L.ffn_norm, false, 0, R))) return r;
         {
             XrGemmArgs a = base;
             a.act = p->act_norm; a.nb = E / 32; a.wd = L.w[2]; a.ws = L.s[2]; a.N = 2 * F; a.up_off = F;
             a.out = p->act_mlp; a.out_nb = F / 32;
-            if ((r = launch_gemm<WT, XEPI_SILU>(a, F / 32))) return r;
+            if ((r = xr_linear<WT, XEPI_SILU>(p, a, F / 32))) return r;
         }
         {
             XrGemmArgs a = base;
             a.act = p->act_mlp; a.nb = F / 32; a.wd = L.w[3]; a.ws = L.s[3]; a.N = E;
-            if ((r = launch_gemm<WT, XEPI_RES>(a, E / 64))) return r;
+            if ((r = xr_linear<WT, XEPI_RES>(p, a, E / 64))) return r;
         }
     }
     if (head_rows > 0) {
@@ -1254,7 +1317,7 @@ int run_pass(XrPlan* p, const XrModel& m, const XrKV& kv, const XrSeq& sq, const
         a.act = p->act_norm; a.nb = E / 32; a.wd = m.head_w; a.ws = m.head_s; a.N = c.n_vocab;
         a.logits = lg; a.ld_logits = c.n_vocab;          // logits of row (head_row0 + i) land in row i of the buffer
         a.arg_val = p->arg_val; a.arg_idx = p->arg_idx; a.n_tiles = p->n_tiles;
-        if ((r = launch_gemm<WT, XEPI_HEAD>(a, p->n_tiles))) return r;
+        if ((r = xr_linear<WT, XEPI_HEAD>(p, a, p->n_tiles))) return r;
         XrArgmaxArgs g{};
         g.rows = p->rows; g.row0 = head_row0; g.arg_val = p->arg_val; g.arg_idx = p->arg_idx; g.n_tiles = p->n_tiles;
         g.tokens = sq.tokens; g.tok_stride = sq.tok_stride; g.st = sq.st; g.eos_id = eos_id;

@@ -49,6 +49,7 @@ int xr_create(XrPlan** out, const gtb_model_config& cfg);
 void xr_destroy(XrPlan* p);
 bool xr_supported(const gtb_model_config& cfg, int gsz);
 void xr_set_variant(int v);          // tuning experiments (large-N GEMM configuration)
+void xr_set_tensor(bool on);         // Q4 / Q8 Linears on the tensor cores (default on); off: the SIMT dp4a kernel
 void xr_set_pdl(bool on);            // programmatic dependent launch inside a pass (default on)
 
 // Prefill pass: rows = positions [p0, p0 + n_rows) of slot `slot`; n_ctx = the call's row count (P.V lane split, SURVEY
