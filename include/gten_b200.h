@@ -150,7 +150,10 @@ int gtb_engine_acv(gtb_engine_t e, int layer, int acv_id, float* h_out, int* wid
  * "pf_attn2" (second attention sweep that also reproduces the fp16 rounding of the probability-row block scales, default 0),
  * "xrows" (1, default: runs of >= "xr_min_rows" (4) rows whose positions the host knows -- gtb_engine_prefill, _logits, _generate --
  * go through the order-exact multi-row kernels in passes of "xr_rows" (512, at most 1024) rows: same bits as the row-at-a-time kernels, one weight
- * read per pass; 0: every row through the persistent kernel), "batch_exact" (see gtb_engine_batch_*) */
+ * read per pass; 0: every row through the persistent kernel), "batch_exact" (see gtb_engine_batch_*),
+ * "xr_tensor" (process-wide experiment, default 0: the multi-row Linears of Q4 / Q8 models on the tensor cores -- kind::f16 tcgen05 MMAs
+ * return the integer lane sums exactly, epilogue warps run the ordered fp32 chains out of TMEM; same bits, measured slower end to end),
+ * "prof_cta" (which CTA of the persistent kernel writes the "prof" stamps) */
 int gtb_engine_set_option(gtb_engine_t e, const char* name, int value);
 
 /* Batched decode (BASELINE.json configs[4]; the reference decodes one sequence, tinyllama.cpp:395-440): up to 64

@@ -188,6 +188,39 @@ def test_full_size_seq64_batch_identity(capi):
     e.close()
 
 
+@pytest.mark.parametrize("wdt", [Q8, Q4], ids=["q8", "q4"])
+def test_tensor_core_linears_are_bit_identical(capi, checker, wdt):
+    """Option "xr_tensor": the multi-row Linears on tcgen05 (gtb_xtensor.cuh) -- integer lane sums out of kind::f16 MMAs, ordered fp32
+    chains in the epilogue warps -- against the reference: prefill logits for pass shapes that select 2, 4 and 8 rows per thread,
+    a continuation, and a batch of sequences at different positions."""
+    cfg = W.mini_config(n_layers=2, n_vocab=300)
+    wl = list(W.synth_weights(cfg, wdt, seed=33))
+    cm = checker.model(cfg, 256, wdt).load(wl)
+    e = capi.Engine(cfg, 256, wdt).load(wl)
+    e.set_option("xr_tensor", 1)
+    try:
+        for n in (5, 37, 130, 190):
+            prompt = W.synth_prompt(11, n, cfg.n_vocab)
+            assert np.array_equal(bits(e.logits(prompt, 0)), bits(cm.logits(prompt, 0))), n
+        toks = W.synth_prompt(4, 150, cfg.n_vocab)
+        for a, b in ((0, 40), (40, 53), (53, 150)):
+            assert np.array_equal(bits(e.logits(toks[:b], a)), bits(cm.logits(toks[:b], a))), (a, b)
+        lens = (5, 33, 40, 41, 64, 90, 100, 7, 12)
+        e.batch_create(len(lens))
+        prompts = [W.synth_prompt(40 + i, n, cfg.n_vocab) for i, n in enumerate(lens)]
+        for s, p in enumerate(prompts):
+            e.batch_prefill(s, p)
+        e.batch_decode(6)
+        for s, p in enumerate(prompts):
+            want, _, lg = cm.generate(p, 7, want_logits=True)
+            assert np.array_equal(e.batch_read_tokens(s, 0, len(p) + 7), want), s
+            assert np.array_equal(bits(e.batch_read_logits(s)), bits(lg[-1])), s
+    finally:
+        e.set_option("xr_tensor", 0)
+        e.close()
+        cm.close()
+
+
 def test_full_size_f16_batch_identity(capi):
     """BASELINE.json configs[0] (FP16, 128-token prompt) at full size through the exact batched path: the slot that holds the golden
     prompt reproduces the reference's greedy tokens while another sequence advances in the same steps."""

@@ -1846,6 +1846,11 @@ int gtb_engine_set_option(gtb_engine_t e, const char* name, int value) {
     if (!strcmp(name, "xr_rows")) { GTB_ARG(value >= 1 && value <= XR_MAX_ROWS); e->xr_rows = value; return GTB_OK; }
     if (!strcmp(name, "batch_exact")) { e->batch_exact = value != 0; drop_graphs(e); return GTB_OK; }
     if (!strcmp(name, "xr_tensor")) { xr_set_tensor(value != 0); drop_graphs(e); return GTB_OK; }
+    if (!strcmp(name, "xr_trace")) {           // cycle counters of the tensor-core GEMM into the "prof" buffer (gtb_engine_read_prof)
+        GTB_CUDA(cudaMemsetAsync(e->d_prof, 0, 64 * 8, ctx().stream));
+        xr_set_trace(value ? e->d_prof : nullptr); drop_graphs(e);
+        return GTB_OK;
+    }
     if (!strcmp(name, "xr_variant")) { xr_set_variant(value); drop_graphs(e); return GTB_OK; }
     if (!strcmp(name, "xr_pdl")) { xr_set_pdl(value != 0); drop_graphs(e); return GTB_OK; }
     return fail(GTB_ERR_ARG, "unknown option %s", name);

@@ -18,8 +18,8 @@
 //   k_xr_gemm<EPI_RES>      down Linear; x = E(x + E(down))
 // plus final norm, k_xr_gemm<EPI_HEAD> (logits + per-tile first maximum) and k_xr_argmax for the rows that sample.
 //
-// The GEMM is a SIMT kernel on purpose: the contract is integer lane sums (dp4a) followed by ORDERED fp32 adds, which
-// tensor cores cannot express.  CTA = 4 warps = 16 rows x 64 output columns; lane = column (2 per lane), warp = 4 rows;
+// The default GEMM is a SIMT kernel: the contract is integer lane sums (dp4a) followed by ORDERED fp32 adds; the ordered adds
+// cannot go to a tensor core.  (The lane sums can, exactly: gtb_xtensor.cuh is that experiment -- bit-identical, not faster.)  CTA = 4 warps = 16 rows x 64 output columns; lane = column (2 per lane), warp = 4 rows;
 // weights and staged rows stream through a 3-stage cp.async ring in chunks of 8 blocks (256 elements of K).
 #include <algorithm>
 #include <vector>
@@ -1094,7 +1094,8 @@ __global__ void __launch_bounds__(XA_NT) k_xf_attn_head(XfAttnArgs a) {
 static bool g_xr_pdl = true;
 static bool g_xr_pdl_now = false;
 static int g_xr_variant = 0;        // experiment switch for the large-N GEMM configuration
-static bool g_xr_tensor = true;     // Q4 / Q8 Linears on the tensor cores (gtb_xtensor.cuh); false: the SIMT kernel k_xr_gemm
+static bool g_xr_tensor = false;    // opt-in experiment: Q4 / Q8 Linears on the tensor cores (gtb_xtensor.cuh).  Bit-identical, but end to end
+                                    // slower than the SIMT kernel k_xr_gemm (profiles/r02_03_tensor_exact.md), which stays the default
 
 struct XrPlan {
     gtb_model_config cfg{};
@@ -1113,6 +1114,8 @@ struct XrPlan {
 void xr_set_pdl(bool on) { g_xr_pdl = on; }
 void xr_set_variant(int v) { g_xr_variant = v; }
 void xr_set_tensor(bool on) { g_xr_tensor = on; }
+static long long* g_xr_trace = nullptr;
+void xr_set_trace(long long* d_buf) { g_xr_trace = d_buf; }
 
 bool xr_supported(const gtb_model_config& c, int gsz) {
     return (c.wdtype == GTB_Q8 || c.wdtype == GTB_Q4 || c.wdtype == GTB_F16) && gsz == 8 && c.n_embd % 256 == 0 && c.n_ffn % 256 == 0 && c.n_embd / c.n_heads == 64 &&
@@ -1212,16 +1215,15 @@ int launch_xt_rpt(const XtGemmArgs& a) {
 template <int WT>
 int launch_xt(const XtGemmArgs& a) {
     const int tiles = (a.N + XT_BM - 1) / XT_BM, sms = ctx().sm_count;
-    int best = 16;
+    int best = 8;
     long best_cost = -1;
-    for (int rpt = 16; rpt >= 2; rpt >>= 1) {
+    for (int rpt = 8; rpt >= 2; rpt >>= 1) {
         const long units = (long)tiles * ((a.n_rows + 4 * rpt - 1) / (4 * rpt));
         const long cost = ((units + sms - 1) / sms) * (90 + 60 * rpt);       // cycles per K block: fixed part + per row of a thread
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = rpt; }
     }
     if (g_xr_variant >= 2) best = g_xr_variant;                               // tuning experiments: force the shape
     switch (best) {
-        case 16: return launch_xt_rpt<WT, 16>(a);
         case 8: return launch_xt_rpt<WT, 8>(a);
         case 4: return launch_xt_rpt<WT, 4>(a);
         default: return launch_xt_rpt<WT, 2>(a);
@@ -1232,7 +1234,7 @@ template <int WT, int EPI>
 int xr_linear(XrPlan* p, const XrGemmArgs& a, int n_tiles) {
     if (!g_xr_tensor) return launch_gemm<WT, EPI>(a, n_tiles);
     XtGemmArgs t{};
-    t.act = a.act; t.nb = a.nb; t.wd = a.wd; t.ws = a.ws; t.N = a.N; t.row0 = a.row0; t.n_rows = a.n_rows;
+    t.act = a.act; t.nb = a.nb; t.wd = a.wd; t.ws = a.ws; t.N = a.N; t.row0 = a.row0; t.n_rows = a.n_rows; t.dbg = g_xr_trace;
     if (EPI == XEPI_HEAD) { t.out = a.logits; t.ldo = a.ld_logits; t.out_row_sub = a.row0; }
     else { t.out = p->raw; t.ldo = p->ld_raw; t.out_row_sub = 0; }
     int r = launch_xt<WT>(t);

@@ -49,7 +49,8 @@ int xr_create(XrPlan** out, const gtb_model_config& cfg);
 void xr_destroy(XrPlan* p);
 bool xr_supported(const gtb_model_config& cfg, int gsz);
 void xr_set_variant(int v);          // tuning experiments (large-N GEMM configuration)
-void xr_set_tensor(bool on);         // Q4 / Q8 Linears on the tensor cores (default on); off: the SIMT dp4a kernel
+void xr_set_tensor(bool on);         // experiment: Q4 / Q8 Linears on the tensor cores (gtb_xtensor.cuh); default off = the SIMT dp4a kernel
+void xr_set_trace(long long* d_buf);  // debugging: cycle counters of the tensor-core GEMM into a device buffer of >= 32 words (nullptr: off)
 void xr_set_pdl(bool on);            // programmatic dependent launch inside a pass (default on)
 
 // Prefill pass: rows = positions [p0, p0 + n_rows) of slot `slot`; n_ctx = the call's row count (P.V lane split, SURVEY

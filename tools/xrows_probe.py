@@ -29,7 +29,7 @@ def main():
     ap.add_argument("--prefill-reps", type=int, default=2)
     ap.add_argument("--pdl", type=int, default=1)
     ap.add_argument("--variant", type=int, default=0)
-    ap.add_argument("--tensor", type=int, default=1, help="Linears on the tensor cores (1) or the SIMT dp4a kernel (0)")
+    ap.add_argument("--tensor", type=int, default=0, help="Linears on the tensor cores (1) or the SIMT dp4a kernel (0)")
     args = ap.parse_args()
     wdt = W.WDTYPE_BY_NAME[args.wdt if args.wdt != "f16" else "fp16"]
     capi.init(0)
