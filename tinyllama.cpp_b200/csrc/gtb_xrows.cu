@@ -206,6 +206,14 @@ struct XrGemmArgs {
     float* logits; int ld_logits; float* arg_val; int* arg_idx; int n_tiles;   // EPI_HEAD
 };
 
+// Packed fp32 pairs (Blackwell f32x2 instructions): two independent IEEE round-to-nearest operations per instruction -- the same bits
+// as two scalar operations, half the issue slots for the four lane chains of a (row, column)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
 // The epilogue of one (row, 64-column tile n) for one warp: lane = column inside each 32-block (v[0]: column 64 n + lane, v[1]: column
 // 64 n + 32 + lane; gate|up: gate channel 32 n + lane and up channel 32 n + lane), every re-encode is warp-local.  Shared by the SIMT
 // GEMM (accumulators in registers) and the tensor-core GEMM's epilogue kernel (accumulated rows read back from HBM).
@@ -313,13 +321,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_xr_gemm(XrGemmArgs a) {
             cp_async16(reinterpret_cast<uint4*>(&st.act[r][0]) + j, src, ok);
         }
     };
-    float acc[TR][2][4];
+    f32x2 acc[TR][2][2];                                             // lanes (0, 1) and (2, 3) of each (row, column)
 #pragma unroll
     for (int r = 0; r < TR; r++)
 #pragma unroll
-        for (int c = 0; c < 2; c++)
-#pragma unroll
-            for (int l = 0; l < 4; l++) acc[r][c][l] = 0.0f;
+        for (int c = 0; c < 2; c++) { acc[r][c][0] = pk2(0.0f, 0.0f); acc[r][c][1] = pk2(0.0f, 0.0f); }
     // weights never depend on the previous kernel of the chain: their first chunks are in flight before it has finished
 #pragma unroll
     for (int s = 0; s < NS - 1; s++)
@@ -381,11 +387,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_xr_gemm(XrGemmArgs a) {
                     // single rounding of l * s: exactly `(float)lane * (da * dw)` of ops.h:282-287
                     const float s = __fmul_rn(ad, dw[c]);
                     const float ms = __fmul_rn(-XB_M, s);
+                    const f32x2 ss = pk2(s, s), mm = pk2(ms, ms);
+                    int t[4];
 #pragma unroll
-                    for (int l = 0; l < 4; l++) {
-                        const int t = __dp4a((int)wy[c][l], (int)ay[l], __dp4a((int)wx[c][l], (int)ax[l], ini[l]));
-                        acc[r][c][l] = __fadd_rn(acc[r][c][l], fmaf(__int_as_float(t), s, ms));
-                    }
+                    for (int l = 0; l < 4; l++) t[l] = __dp4a((int)wy[c][l], (int)ay[l], __dp4a((int)wx[c][l], (int)ax[l], ini[l]));
+                    acc[r][c][0] = add2(acc[r][c][0], fma2(pk2(__int_as_float(t[0]), __int_as_float(t[1])), ss, mm));
+                    acc[r][c][1] = add2(acc[r][c][1], fma2(pk2(__int_as_float(t[2]), __int_as_float(t[3])), ss, mm));
                 }
             }
         }
@@ -401,8 +408,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_xr_gemm(XrGemmArgs a) {
         if (rw.slot < 0) continue;
         float v[2];
 #pragma unroll
-        for (int c = 0; c < 2; c++)
-            v[c] = __fadd_rn(__fadd_rn(acc[r][c][0], acc[r][c][1]), __fadd_rn(acc[r][c][2], acc[r][c][3]));
+        for (int c = 0; c < 2; c++) {
+            float a0, a1, a2, a3;
+            unpk2(acc[r][c][0], a0, a1); unpk2(acc[r][c][1], a2, a3);
+            v[c] = __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
+        }
         xr_epilogue<EPI>(a, row, rw, n, lane, v, true);
     }
 }
