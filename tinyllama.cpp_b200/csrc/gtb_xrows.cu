@@ -604,8 +604,12 @@ __global__ void __launch_bounds__(XA_NT) k_xr_attn(XrAttnArgs a) {
                 float4* dst = reinterpret_cast<float4*>(&vt[p][qt * 16]);
 #pragma unroll
                 for (int uu = 0; uu < 4; uu++) {              // value = code * delta (ops.h:1026), exact
-                    const float f0 = (float)(int8_t)(cw[uu] & 0xffu), f1 = (float)(int8_t)((cw[uu] >> 8) & 0xffu);
-                    const float f2 = (float)(int8_t)((cw[uu] >> 16) & 0xffu), f3 = (float)(int8_t)(cw[uu] >> 24);
+                    // int8 -> float without the conversion unit (a quarter-rate pipe): byte + 128 placed in the mantissa of 2^23
+                    const uint32_t wv = cw[uu] ^ 0x80808080u;
+                    const float f0 = __fsub_rn(__uint_as_float(__byte_perm(wv, 0x4b000000u, 0x7650)), 8388736.0f);
+                    const float f1 = __fsub_rn(__uint_as_float(__byte_perm(wv, 0x4b000000u, 0x7651)), 8388736.0f);
+                    const float f2 = __fsub_rn(__uint_as_float(__byte_perm(wv, 0x4b000000u, 0x7652)), 8388736.0f);
+                    const float f3 = __fsub_rn(__uint_as_float(__byte_perm(wv, 0x4b000000u, 0x7653)), 8388736.0f);
                     dst[uu] = make_float4(__fmul_rn(f0, d), __fmul_rn(f1, d), __fmul_rn(f2, d), __fmul_rn(f3, d));
                 }
             }
@@ -759,8 +763,9 @@ __global__ void __launch_bounds__(XA_NT) k_xr_attn_head(XrAttnArgs a) {
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 const float p = sc[i + 8 * u];
-                const float v0 = __fmul_rn((float)c0[u], h2f((uint16_t)(s2[u] & 0xffffu)));                     // ops.h:1026
-                const float v1 = __fmul_rn((float)c1[u], h2f((uint16_t)(s2[u] >> 16)));
+                // ops.h:1026; the int -> float step goes through the mantissa of 1.5 * 2^23 instead of the conversion unit
+                const float v0 = __fmul_rn(__fsub_rn(__int_as_float(XB_BIAS + c0[u]), XB_M), h2f((uint16_t)(s2[u] & 0xffffu)));
+                const float v1 = __fmul_rn(__fsub_rn(__int_as_float(XB_BIAS + c1[u]), XB_M), h2f((uint16_t)(s2[u] >> 16)));
                 a0 = __fadd_rn(__fmul_rn(p, v0), a0);
                 a1 = __fadd_rn(__fmul_rn(p, v1), a1);
             }
