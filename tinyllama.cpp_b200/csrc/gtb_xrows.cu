@@ -212,6 +212,9 @@ typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ void unpk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// There is deliberately NO packed multiply here: ptxas 12.9 contracts `mul.rn.f32x2` followed by `add.rn.f32x2` into one FFMA2 (and
+// does the same to `fma.rn.f32x2(a, b, -0.0)` + add), -fmad=false or not -- the product's rounding would be lost.  Products that feed
+// an addition are scalar `__fmul_rn`; only the additions (and explicit FMAs) are packed.
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 
 // The epilogue of one (row, 64-column tile n) for one warp: lane = column inside each 32-block (v[0]: column 64 n + lane, v[1]: column
@@ -586,11 +589,11 @@ __global__ void __launch_bounds__(XA_NT) k_xr_attn(XrAttnArgs a) {
     // ---- D: P.V.  warp = 8 channels, lane = (head, position-lane pair {pl, pl + 4}): a V value is read once for 8 heads
     const int n8 = (n_ctx / 8) * 8, hi = min(n8, t);
     const int hh = lane & 7, pl = lane >> 3;
-    float accv[2][8];
+    f32x2 accv[2][4];                                     // channel pairs: packed fp32 (two independent rounded operations per instruction)
 #pragma unroll
     for (int uu = 0; uu < 2; uu++)
 #pragma unroll
-        for (int c = 0; c < 8; c++) accv[uu][c] = 0.0f;
+        for (int c = 0; c < 4; c++) accv[uu][c] = pk2(0.0f, 0.0f);
     const uint8_t* vqb = a.vq + (size_t)rw.slot * a.slot_codes + g * 64;
     const uint16_t* vsb = a.vs + (size_t)rw.slot * a.slot_scales + g * 2;
     int i0_last = 0;
@@ -624,10 +627,11 @@ __global__ void __launch_bounds__(XA_NT) k_xr_attn(XrAttnArgs a) {
                     const float p = sc[(i0 + il) * 8 + hh];
                     const float4 va = *reinterpret_cast<const float4*>(&vt[il][8 * wid]);
                     const float4 vb = *reinterpret_cast<const float4*>(&vt[il][8 * wid + 4]);
-                    accv[uu][0] = __fadd_rn(__fmul_rn(p, va.x), accv[uu][0]); accv[uu][1] = __fadd_rn(__fmul_rn(p, va.y), accv[uu][1]);
-                    accv[uu][2] = __fadd_rn(__fmul_rn(p, va.z), accv[uu][2]); accv[uu][3] = __fadd_rn(__fmul_rn(p, va.w), accv[uu][3]);
-                    accv[uu][4] = __fadd_rn(__fmul_rn(p, vb.x), accv[uu][4]); accv[uu][5] = __fadd_rn(__fmul_rn(p, vb.y), accv[uu][5]);
-                    accv[uu][6] = __fadd_rn(__fmul_rn(p, vb.z), accv[uu][6]); accv[uu][7] = __fadd_rn(__fmul_rn(p, vb.w), accv[uu][7]);
+                    // acc = (p * v) + acc per channel, both operations rounded (ops.h:181-197)
+                    accv[uu][0] = add2(pk2(__fmul_rn(p, va.x), __fmul_rn(p, va.y)), accv[uu][0]);
+                    accv[uu][1] = add2(pk2(__fmul_rn(p, va.z), __fmul_rn(p, va.w)), accv[uu][1]);
+                    accv[uu][2] = add2(pk2(__fmul_rn(p, vb.x), __fmul_rn(p, vb.y)), accv[uu][2]);
+                    accv[uu][3] = add2(pk2(__fmul_rn(p, vb.z), __fmul_rn(p, vb.w)), accv[uu][3]);
                 }
             }
         }
@@ -638,7 +642,11 @@ __global__ void __launch_bounds__(XA_NT) k_xr_attn(XrAttnArgs a) {
 #pragma unroll
     for (int uu = 0; uu < 2; uu++)
 #pragma unroll
-        for (int c = 0; c < 8; c++) part[pl + 4 * uu][hh][8 * wid + c] = accv[uu][c];
+        for (int c = 0; c < 4; c++) {
+            float x0, x1;
+            unpk2(accv[uu][c], x0, x1);
+            part[pl + 4 * uu][hh][8 * wid + 2 * c] = x0; part[pl + 4 * uu][hh][8 * wid + 2 * c + 1] = x1;
+        }
     __syncthreads();
     for (int o = tid; o < 512; o += XA_NT) {
         const int h2 = o >> 6, ch = o & 63;
@@ -747,7 +755,7 @@ __global__ void __launch_bounds__(XA_NT) k_xr_attn_head(XrAttnArgs a) {
     const uint8_t* vqb = a.vq + (size_t)rw.slot * a.slot_codes + g * 64;
     const uint16_t* vsb = a.vs + (size_t)rw.slot * a.slot_scales + g * 2;
     {
-        float a0 = 0.0f, a1 = 0.0f;
+        f32x2 a01 = pk2(0.0f, 0.0f);                       // the lane's two channels as one packed pair
         int i = wid;
         for (; i + 56 < hi; i += 64) {                     // eight positions of this lane per round: all loads first (L2 latency), then the chain
             uint32_t s2[8];
@@ -766,8 +774,7 @@ __global__ void __launch_bounds__(XA_NT) k_xr_attn_head(XrAttnArgs a) {
                 // ops.h:1026; the int -> float step goes through the mantissa of 1.5 * 2^23 instead of the conversion unit
                 const float v0 = __fmul_rn(__fsub_rn(__int_as_float(XB_BIAS + c0[u]), XB_M), h2f((uint16_t)(s2[u] & 0xffffu)));
                 const float v1 = __fmul_rn(__fsub_rn(__int_as_float(XB_BIAS + c1[u]), XB_M), h2f((uint16_t)(s2[u] >> 16)));
-                a0 = __fadd_rn(__fmul_rn(p, v0), a0);
-                a1 = __fadd_rn(__fmul_rn(p, v1), a1);
+                a01 = add2(pk2(__fmul_rn(p, v0), __fmul_rn(p, v1)), a01);
             }
         }
         for (; i < hi; i += 8) {
@@ -776,9 +783,10 @@ __global__ void __launch_bounds__(XA_NT) k_xr_attn_head(XrAttnArgs a) {
             const uint8_t* vp = vqb + (size_t)i * a.kv_dim;
             const float v0 = __fmul_rn((float)(int8_t)__ldg(vp + lane), h2f((uint16_t)(s2 & 0xffffu)));
             const float v1 = __fmul_rn((float)(int8_t)__ldg(vp + 32 + lane), h2f((uint16_t)(s2 >> 16)));
-            a0 = __fadd_rn(__fmul_rn(p, v0), a0);
-            a1 = __fadd_rn(__fmul_rn(p, v1), a1);
+            a01 = add2(pk2(__fmul_rn(p, v0), __fmul_rn(p, v1)), a01);
         }
+        float a0, a1;
+        unpk2(a01, a0, a1);
         sm.part[wid][lane] = a0;
         sm.part[wid][lane + 32] = a1;
     }
