@@ -165,7 +165,10 @@ int gtb_engine_set_option(gtb_engine_t e, const char* name, int value);
  *   gtb_engine_batch_prefill(e, s, t, n) exact prefill of n prompt ids into slot s (multi-row passes of up to 512 rows), first token appended
  *   gtb_engine_batch_adopt(e, s)         slot s <- the engine's current sequence (after gtb_engine_prefill / _prefill_fast / decode)
  *   gtb_engine_batch_decode(e, k)        k greedy steps of every slot (device-side argmax, tokens stay on the device)
- *   gtb_engine_batch_position / _read_tokens / _read_logits: per-slot state */
+ *   gtb_engine_batch_position / _read_tokens / _read_logits: per-slot state
+ * Join / leave: a slot can be (re)filled with gtb_engine_batch_prefill or _adopt between decode calls while the others keep their state; with
+ * option "batch_eos" = id (exact mode) a slot that samples id keeps it as its last token and leaves the batch -- its row is no longer
+ * computed (tinyllama.cpp:426 `break`), the other slots' bits do not change. */
 int gtb_engine_batch_create(gtb_engine_t e, int n_seq);
 int gtb_engine_batch_prefill(gtb_engine_t e, int seq, const int32_t* h_tokens, int n_tokens);
 int gtb_engine_batch_adopt(gtb_engine_t e, int seq);

@@ -141,6 +141,48 @@ def test_exact_batch_equals_single_sequence_long_context(capi):
     e.close()
 
 
+def test_exact_batch_eos_leave_and_rejoin(capi, checker):
+    """Option "batch_eos": a slot that samples the id stops there (the reference's `break`, tinyllama.cpp:426) and leaves the batch; the
+    other slots keep producing the reference's tokens; the freed slot takes a new prompt between decode calls (join)."""
+    cfg = W.mini_config(n_layers=2, n_vocab=300)
+    wl = list(W.synth_weights(cfg, Q4, seed=6))
+    cm = checker.model(cfg, 160, Q4).load(wl)
+    lens = (20, 37, 64, 9)
+    steps = 12
+    prompts = [W.synth_prompt(40 + i, n, cfg.n_vocab) for i, n in enumerate(lens)]
+    want = [cm.generate(p, steps + 1)[0] for p in prompts]
+    # an id that slot 1 samples in the middle of the run and that no other slot samples: that slot must stop, alone
+    cands = [int(t) for t in want[1][lens[1] + 2: lens[1] + steps - 2]
+             if all(int(t) not in want[s][lens[s]:] for s in (0, 2, 3)) and list(want[1][lens[1]:]).index(t) >= 2]
+    assert cands, "no suitable EOS id in this synthetic run"
+    eos = cands[0]
+    stop_at = lens[1] + list(want[1][lens[1]:]).index(eos)          # index of the EOS token in slot 1's sequence
+    e = capi.Engine(cfg, 160, Q4).load(wl)
+    e.set_option("batch_eos", eos)
+    e.batch_create(len(lens))
+    for s, p in enumerate(prompts):
+        e.batch_prefill(s, p)
+    e.batch_decode(steps)
+    for s, p in enumerate(prompts):
+        if s == 1:
+            assert e.batch_position(s) == stop_at
+            assert np.array_equal(e.batch_read_tokens(s, 0, stop_at + 1), want[s][: stop_at + 1])
+        else:
+            assert e.batch_position(s) == len(p) + steps
+            assert np.array_equal(e.batch_read_tokens(s, 0, len(p) + steps + 1), want[s]), s
+    # join: the freed slot takes a new prompt; it and the others continue with the reference's tokens
+    p_new = W.synth_prompt(77, 15, cfg.n_vocab)
+    e.set_option("batch_eos", -1)
+    e.batch_prefill(1, p_new)
+    e.batch_decode(4)
+    w_new = cm.generate(p_new, 5)[0]
+    assert np.array_equal(e.batch_read_tokens(1, 0, 15 + 5), w_new)
+    w0 = cm.generate(prompts[0], steps + 5)[0]
+    assert np.array_equal(e.batch_read_tokens(0, 0, lens[0] + steps + 5), w0)
+    e.close()
+    cm.close()
+
+
 def test_exact_batch_argument_errors(capi):
     cfg = W.mini_config(n_layers=1, n_vocab=64)
     e = capi.Engine(cfg, 32, Q4).load(W.synth_weights(cfg, Q4, seed=1))

@@ -375,6 +375,7 @@ struct gtb_engine {
     int pf_ahead = 4;
     bool prof = false;
     int prof_cta = 0;                // which CTA of k_mega writes the stamps
+    int batch_eos = -1;              // exact batched decode: a slot that samples this id stops (tinyllama.cpp:426); -1: none
     MegaLayer* d_layers = nullptr;
     bool layers_valid = false;
     unsigned long long *x_qkv = nullptr, *x_sc = nullptr, *x_attn = nullptr, *x_o = nullptr, *x_gu = nullptr, *x_act = nullptr,
@@ -1636,7 +1637,7 @@ int gtb_engine_batch_prefill(gtb_engine_t e, int seq, const int32_t* h_tokens, i
     for (int done = 0; done < n_tokens;) {
         const int n = (n_tokens - done < e->xr_rows) ? n_tokens - done : e->xr_rows;
         const bool last = done + n == n_tokens;
-        r = xr_prefill_pass(e->xr, m, kv, sq, seq, done, n, n_tokens, last, -1, b.logits + (size_t)seq * c.n_vocab);
+        r = xr_prefill_pass(e->xr, m, kv, sq, seq, done, n, n_tokens, last, e->batch_eos, b.logits + (size_t)seq * c.n_vocab);
         if (r) return r;
         done += n;
     }
@@ -1701,7 +1702,7 @@ int gtb_engine_batch_decode(gtb_engine_t e, int n_steps) {
     XrKV kv{b.kq.data(), b.ks.data(), b.vq.data(), b.vs.data(), MC * KV, MC * (KV / 32)};
     XrSeq sq{b.tokens, (int)MC + 2, b.st};
     auto enqueue = [&]() -> int {
-        if (exact) return xr_decode_pass(e->xr, m, kv, sq, b.n, t_cap, -1, b.logits);
+        if (exact) return xr_decode_pass(e->xr, m, kv, sq, b.n, t_cap, e->batch_eos, b.logits);
         return (e->cfg.wdtype == GTB_Q8) ? enqueue_batch_row<DT_Q8>(e) : enqueue_batch_row<DT_Q4>(e);
     };
     if (e->use_graph) {
@@ -1845,6 +1846,7 @@ int gtb_engine_set_option(gtb_engine_t e, const char* name, int value) {
     if (!strcmp(name, "xr_min_rows")) { GTB_ARG(value >= 1); e->xr_min_rows = value; return GTB_OK; }
     if (!strcmp(name, "xr_rows")) { GTB_ARG(value >= 1 && value <= XR_MAX_ROWS); e->xr_rows = value; return GTB_OK; }
     if (!strcmp(name, "batch_exact")) { e->batch_exact = value != 0; drop_graphs(e); return GTB_OK; }
+    if (!strcmp(name, "batch_eos")) { GTB_ARG(value >= -1); e->batch_eos = value; drop_graphs(e); return GTB_OK; }
     if (!strcmp(name, "xr_tensor")) { xr_set_tensor(value != 0); drop_graphs(e); return GTB_OK; }
     if (!strcmp(name, "xr_trace")) {           // cycle counters of the tensor-core GEMM into the "prof" buffer (gtb_engine_read_prof)
         GTB_CUDA(cudaMemsetAsync(e->d_prof, 0, 64 * 8, ctx().stream));

@@ -103,8 +103,9 @@ __global__ void k_xr_plan(XrPlanArgs a) {
             row.slot = a.slot0; row.pos = a.p0 + r; row.n_ctx = a.n_ctx;
         } else {
             row.slot = a.slot0 + r; row.pos = a.st[row.slot].pos; row.n_ctx = row.pos + 1;
+            if (a.st[row.slot].stop) row.slot = -1;       // a sequence that sampled EOS has left the batch (tinyllama.cpp:426: break)
         }
-        row.tok = a.tokens[(size_t)row.slot * a.tok_stride + row.pos];
+        if (row.slot >= 0) row.tok = a.tokens[(size_t)row.slot * a.tok_stride + row.pos];
     }
     a.rows[r] = row;
 }
