@@ -9,9 +9,11 @@ from tinyllama_cpp_b200 import capi, weights as W
 capi.init(0)
 cfg = W.mini_config(n_layers=1, n_vocab=300)
 QUICK = "--quick" in sys.argv               # racecheck is slow: one quantised and the fp16 model, fewer prompt lengths
+TENSOR = "--tensor" in sys.argv             # the xr_tensor experiment (tcgen05 Linears) instead of the SIMT GEMM
 for wdt in ((W.Q4, W.F16) if QUICK else (W.Q4, W.Q8, W.F16)):
     e = capi.Engine(cfg, 400, wdt).load(W.synth_weights(cfg, wdt, seed=3))
     e.set_option("graph", 0)
+    e.set_option("xr_tensor", 1 if (TENSOR and wdt != W.F16) else 0)
     for T in ((5, 70) if QUICK else (5, 40, 70, 150)):                  # per-head attention (<= 32 rows per pass), group attention (64 rows), tails
         toks = e.generate(W.synth_prompt(2, T, cfg.n_vocab), 3)      # multi-row prefill, then k_mega (K/V copies transposed first)
         print(wdt, "prefill", T, toks[-3:].tolist(), flush=True)
