@@ -579,7 +579,16 @@ __global__ void __launch_bounds__(XA_NT) k_xr_attn(XrAttnArgs a) {
     {
         const float sum = sums[wid];
         const int nblk = (t + 31) / 32;
-        for (int b = 0; b < nblk; b++) {
+        int b = 0;
+        for (; b + 2 <= nblk; b += 2) {             // two independent blocks in flight: the re-encode is a long dependent chain
+            const int i = b * 32 + lane, j = i + 32;
+            const float p0 = (i < t && i < n_ctx) ? __fdiv_rn(sc[i * 8 + wid], sum) : 0.0f;
+            const float p1 = (j < t && j < n_ctx) ? __fdiv_rn(sc[j * 8 + wid], sum) : 0.0f;
+            const float h0 = q8_roundtrip_lane(p0), h1 = q8_roundtrip_lane(p1);
+            if (i < t) sc[i * 8 + wid] = h0;
+            if (j < t) sc[j * 8 + wid] = h1;
+        }
+        for (; b < nblk; b++) {
             const int i = b * 32 + lane;
             const float p = (i < t && i < n_ctx) ? __fdiv_rn(sc[i * 8 + wid], sum) : 0.0f;
             const float ph = q8_roundtrip_lane(p);
@@ -620,7 +629,30 @@ __global__ void __launch_bounds__(XA_NT) k_xr_attn(XrAttnArgs a) {
         }
         __syncthreads();
         const int lim = min(hi - i0, XA_VT);
-        for (int i8 = 0; i8 < lim; i8 += 8) {
+        // one (position, 8 channels) step of this thread's chains: acc = (p * v) + acc per channel, both operations rounded (ops.h:181-197)
+        auto pv_step = [&](int uu, float p, const float4& va, const float4& vb) {
+            accv[uu][0] = add2(pk2(__fmul_rn(p, va.x), __fmul_rn(p, va.y)), accv[uu][0]);
+            accv[uu][1] = add2(pk2(__fmul_rn(p, va.z), __fmul_rn(p, va.w)), accv[uu][1]);
+            accv[uu][2] = add2(pk2(__fmul_rn(p, vb.x), __fmul_rn(p, vb.y)), accv[uu][2]);
+            accv[uu][3] = add2(pk2(__fmul_rn(p, vb.z), __fmul_rn(p, vb.w)), accv[uu][3]);
+        };
+        int i8 = 0;
+        // two octets per round, all twelve shared-memory loads issued before the arithmetic: with one or two CTAs per SM (decode batches)
+        // nothing else hides their latency
+        for (; i8 + 16 <= lim; i8 += 16) {
+            float p[4];
+            float4 va[4], vb[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int il = i8 + pl + 4 * q;               // q = 0, 1: first octet (lanes pl, pl + 4); q = 2, 3: second octet
+                p[q] = sc[(i0 + il) * 8 + hh];
+                va[q] = *reinterpret_cast<const float4*>(&vt[il][8 * wid]);
+                vb[q] = *reinterpret_cast<const float4*>(&vt[il][8 * wid + 4]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) pv_step(q & 1, p[q], va[q], vb[q]);
+        }
+        for (; i8 < lim; i8 += 8) {
 #pragma unroll
             for (int uu = 0; uu < 2; uu++) {
                 const int il = i8 + pl + 4 * uu;
@@ -628,11 +660,7 @@ __global__ void __launch_bounds__(XA_NT) k_xr_attn(XrAttnArgs a) {
                     const float p = sc[(i0 + il) * 8 + hh];
                     const float4 va = *reinterpret_cast<const float4*>(&vt[il][8 * wid]);
                     const float4 vb = *reinterpret_cast<const float4*>(&vt[il][8 * wid + 4]);
-                    // acc = (p * v) + acc per channel, both operations rounded (ops.h:181-197)
-                    accv[uu][0] = add2(pk2(__fmul_rn(p, va.x), __fmul_rn(p, va.y)), accv[uu][0]);
-                    accv[uu][1] = add2(pk2(__fmul_rn(p, va.z), __fmul_rn(p, va.w)), accv[uu][1]);
-                    accv[uu][2] = add2(pk2(__fmul_rn(p, vb.x), __fmul_rn(p, vb.y)), accv[uu][2]);
-                    accv[uu][3] = add2(pk2(__fmul_rn(p, vb.z), __fmul_rn(p, vb.w)), accv[uu][3]);
+                    pv_step(uu, p, va, vb);
                 }
             }
         }
