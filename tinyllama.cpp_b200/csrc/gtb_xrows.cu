@@ -936,13 +936,11 @@ __global__ void __launch_bounds__(256, 2) k_xf_gemm(XfGemmArgs a) {
                        reinterpret_cast<const uint4*>(a.act + (size_t)(ok ? gr : a.row0) * a.K + (size_t)st_i * XF_KC * 64) + j, ok);
         }
     };
-    float acc[TR][2][8];
+    f32x2 acc[TR][8];                                       // per (row, lane): the two columns' chains as one packed pair
 #pragma unroll
     for (int r = 0; r < TR; r++)
 #pragma unroll
-        for (int c = 0; c < 2; c++)
-#pragma unroll
-            for (int l = 0; l < 8; l++) acc[r][c][l] = 0.0f;
+        for (int l = 0; l < 8; l++) acc[r][l] = pk2(0.0f, 0.0f);
 #pragma unroll
     for (int s = 0; s < XG_STAGES - 1; s++)
         if (s < nstage) load_weights(s, s);
@@ -980,10 +978,8 @@ __global__ void __launch_bounds__(256, 2) k_xf_gemm(XfGemmArgs a) {
                     const float4 xb = *reinterpret_cast<const float4*>(&st.act[wid * TR + r][(c * 8 + l) * 8 + 4]);
                     const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {                         // elements 64c + 8i + l, ascending i: the lane's own order
-                        acc[r][0][l] = fmaf(x[i], f0[i], acc[r][0][l]);
-                        acc[r][1][l] = fmaf(x[i], f1[i], acc[r][1][l]);
-                    }
+                    for (int i = 0; i < 8; i++)                           // elements 64c + 8i + l, ascending i: the lane's own order;
+                        acc[r][l] = fma2(pk2(x[i], x[i]), pk2(f0[i], f1[i]), acc[r][l]);   // one FFMA2 = the two columns' fused multiply-adds
                 }
             }
         }
@@ -997,12 +993,11 @@ __global__ void __launch_bounds__(256, 2) k_xf_gemm(XfGemmArgs a) {
         const XrRow rw = a.rows[row];
         if (rw.slot < 0) continue;
         float v[2];
+        {
+            f32x2 d = add2(acc[r][0], acc[r][1]);                       // simd_ops.h:63-66: lanes left to right (both columns at once)
 #pragma unroll
-        for (int c = 0; c < 2; c++) {
-            float d = __fadd_rn(acc[r][c][0], acc[r][c][1]);            // simd_ops.h:63-66: lanes left to right
-#pragma unroll
-            for (int l = 2; l < 8; l++) d = __fadd_rn(d, acc[r][c][l]);
-            v[c] = d;
+            for (int l = 2; l < 8; l++) d = add2(d, acc[r][l]);
+            unpk2(d, v[0], v[1]);
         }
         if (EPI == XEPI_RES) {
 #pragma unroll
