@@ -547,12 +547,23 @@ __device__ __forceinline__ float tile_chain(int nb, int nrows, const float* ps) 
     if (ct < nrows * 4) {
         const float* src = ps + (size_t)(ct >> 2) * (nb + 1) * 4 + (ct & 3);
         int b = 0;
-        for (; b + 8 <= nb; b += 8) {
+        if (nb >= 8) {
+            // the chain is one dependent FADD per block (4 cycles); the loads of the next eight blocks are in flight while it runs
             float v[8];
 #pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = src[(b + u) * 4];
+            for (int u = 0; u < 8; u++) v[u] = src[u * 4];
+            for (; b + 16 <= nb; b += 8) {
+                float nx[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) nx[u] = src[(b + 8 + u) * 4];
+#pragma unroll
+                for (int u = 0; u < 8; u++) acc = __fadd_rn(acc, v[u]);
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[u] = nx[u];
+            }
 #pragma unroll
             for (int u = 0; u < 8; u++) acc = __fadd_rn(acc, v[u]);
+            b += 8;
         }
         for (; b < nb; b++) acc = __fadd_rn(acc, src[b * 4]);
     }
