@@ -67,6 +67,8 @@ public:
     void batch_prefill(int slot, const int32_t* ids, int n) { GTEN_CUDA_OK(gtb_engine_batch_prefill(eng_, slot, ids, n)); }
     void batch_adopt(int slot) { GTEN_CUDA_OK(gtb_engine_batch_adopt(eng_, slot)); }
     void batch_decode(int n_steps) { GTEN_CUDA_OK(gtb_engine_batch_decode(eng_, n_steps)); }
+    // a slot that samples `eot_token` keeps it as its last token and leaves the batch (tinyllama.cpp:426 `break`); -1: never
+    void batch_set_eos(int eot_token) { GTEN_CUDA_OK(gtb_engine_set_option(eng_, "batch_eos", eot_token)); }
     int batch_position(int slot) { int p = 0; GTEN_CUDA_OK(gtb_engine_batch_position(eng_, slot, &p)); return p; }
     void batch_read_tokens(int slot, int32_t* out, int first, int count) { GTEN_CUDA_OK(gtb_engine_batch_read_tokens(eng_, slot, out, first, count)); }
     gtb_engine_t engine() { return eng_; }
