@@ -899,23 +899,27 @@ bool mega_ok(const gtb_engine* e) {
            e->grid >= MH * 4 && e->grid <= 1024 && c.max_ctx <= 4 * MT && c.n_layers <= MEGA_MAX_LAYERS && attn_scratch_bytes(c.max_ctx) <= (size_t)PS_BYTES;
 }
 
-template <int WT>
-int launch_mega(gtb_engine* e, MegaParams& p) {
+template <int WT, bool PROF>
+int launch_mega_v(gtb_engine* e, MegaParams& p) {
     constexpr int AT = (WT == DT_F16) ? DT_F16 : DT_Q8;
     const size_t smem = mega_smem_bytes(AT);
     static bool attr_done = false;
     if (!attr_done) {
-        GTB_CUDA(cudaFuncSetAttribute(k_mega<WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GTB_CUDA(cudaFuncSetAttribute(k_mega<WT, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
-        GTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_mega<WT>, MT, smem));
+        GTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_mega<WT, PROF>, MT, smem));
         if (nb < 1) return fail(GTB_ERR_CUDA, "megakernel does not fit on an SM (%zu B shared memory)", smem);
         attr_done = true;
     }
     if (e->grid > ctx().sm_count) return fail(GTB_ERR_ARG, "cooperative grid (%d) exceeds the SM count (%d)", e->grid, ctx().sm_count);
     void* args[] = {&p};
-    GTB_CUDA(cudaLaunchCooperativeKernel((const void*)k_mega<WT>, dim3(e->grid), dim3(MT), args, smem, ctx().stream));
+    GTB_CUDA(cudaLaunchCooperativeKernel((const void*)k_mega<WT, PROF>, dim3(e->grid), dim3(MT), args, smem, ctx().stream));
     GTB_LAUNCHED();
     return GTB_OK;
+}
+template <int WT>
+int launch_mega(gtb_engine* e, MegaParams& p) {
+    return p.prof ? launch_mega_v<WT, true>(e, p) : launch_mega_v<WT, false>(e, p);     // the stamped build only under option "prof"
 }
 
 int run_rows_mega(gtb_engine* e, int n_body, int n_head, int eos_id, int start_pos) {

@@ -1104,10 +1104,12 @@ __device__ __forceinline__ void mega_embed(const MegaParams& P, int tok, float r
 // profiling stamps of one CTA (option "prof_cta", default 0): (code, globaltimer) pairs; code = phase kind * 16 + step
 #define MEGA_PROF(code)                                                                                   \
     do {                                                                                                  \
-        if (P.prof && cta == P.prof_cta && threadIdx.x == 0) { P.prof[prof_i++] = (code); P.prof[prof_i++] = gtimer(); } \
+        if (PROF && profp) { profp[prof_i++] = (code); profp[prof_i++] = gtimer(); }                     \
     } while (0)
 
-template <int WT>
+// PROF: the stamps are compiled in only for the instantiation the option "prof" selects (they cost issue slots and instruction-cache
+// footprint in a kernel whose layer loop already exceeds the instruction cache)
+template <int WT, bool PROF>
 __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
     constexpr int AT = (WT == DT_F16) ? DT_F16 : DT_Q8;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -1117,6 +1119,7 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
     MegaSm& sm = *reinterpret_cast<MegaSm*>(reinterpret_cast<unsigned char*>(ps) + PS_BYTES);
     const int cta = blockIdx.x, G = gridDim.x, tid = threadIdx.x;
     int prof_i = 0;
+    long long* const profp = (PROF && P.prof && cta == P.prof_cta && tid == 0) ? P.prof : nullptr;
     unsigned int ep = *reinterpret_cast<volatile unsigned int*>(P.epoch);
     const int n_units = MH * 4;
     const int nL4 = 4 * P.n_layers;                // GEMV phases of a row without the lm_head
@@ -1257,7 +1260,7 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
                 } else {
                     ll_store(outp + row, __float_as_uint(v), tag);
                 }
-            }, background, (P.prof && cta == P.prof_cta && tid == 0) ? P.prof : nullptr, &prof_i, 128 + kind * 8);
+            }, background, profp, &prof_i, 128 + kind * 8);
             pd = nx;
             tag_in = tag;
             MEGA_PROF(kind * 16 + 4);
@@ -1267,13 +1270,13 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
                 const uint32_t tag_attn = ++ep;
                 if (cta < n_units) {
                     __syncthreads();                               // product staging is reused as attention scratch
-                    mega_attn_a<AT>(P, L, sm, ps, cta, pos, tag, tag_sc, (P.prof && cta == P.prof_cta && tid == 0) ? P.prof : nullptr, prof_i);
+                    mega_attn_a<AT>(P, L, sm, ps, cta, pos, tag, tag_sc, profp, prof_i);
                     if (defer_tile && more) load_tile<WT>(nx, sm.rr[nx.kind][0], min(tile_rows<WT>(nx.nb), sm.rr[nx.kind][1] - sm.rr[nx.kind][0]), w);
                     MEGA_PROF(kind * 16 + 5);
                     exp_sc += 4;
                     xwait(P.cnt + (CNT_SC0 + (cta >> 2)) * CNT_STRIDE, P.cnt + (CNT_SC0 + (cta >> 2)) * CNT_STRIDE, exp_sc, P.dbg);
                     MEGA_PROF(kind * 16 + 6);
-                    mega_attn_b<AT>(P, sm, ps, xbuf, cta, pos, n_ctx, tag_sc, tag_attn, (P.prof && cta == P.prof_cta && tid == 0) ? P.prof : nullptr, prof_i);
+                    mega_attn_b<AT>(P, sm, ps, xbuf, cta, pos, n_ctx, tag_sc, tag_attn, profp, prof_i);
                     __threadfence();                               // K/V appends visible before anything later is published
                 } else if (tid == 0 && AT != DT_F16) {
                     // the CTAs without an attention unit pull the NEXT layer's K/V rows (last touched a token ago) towards L2
