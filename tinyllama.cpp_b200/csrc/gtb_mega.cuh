@@ -41,7 +41,7 @@ constexpr int MWARP = MT / 32;
 constexpr int ME = 2048, MF = 5632, MKV = 256, MH = 32, MGSZ = 8;     // TinyLLamaParams, tinyllama.cpp:12-20
 constexpr int NBE = ME / 32, NBF = MF / 32;
 constexpr int PS_BYTES = 142 * 1024;       // product staging; during attention: probabilities + the unit's V slice as fp32
-constexpr int IT_Q4 = 10;                  // (row, block) items per thread per tile: MT*IT items in registers
+constexpr int IT_Q4 = 5;                   // (row, block) items per thread per tile: MT*IT items in registers
 constexpr int IT_Q8 = 5;
 constexpr int MEGA_MAX_LAYERS = 32;        // the layer table is copied into shared memory (a phase descriptor is then 30 cycles away, not an L2 round trip)
 constexpr int SPIN_LIMIT = 1 << 24;        // ~ seconds; a stuck exchange traps instead of hanging the GPU
