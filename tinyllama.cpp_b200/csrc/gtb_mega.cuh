@@ -136,9 +136,12 @@ __device__ __forceinline__ unsigned int cnt_load(const unsigned int* c) {
 }
 // CTA-wide: (optionally) announce that this CTA's contribution to `sig` is on its way, then wait until counter
 // `cnt` has reached `expected`.  One thread spins; everybody else is parked in the barrier.
-__device__ __forceinline__ void xwait(unsigned int* sig, const unsigned int* cnt, unsigned int expected, ull* dbg) {
+__device__ __forceinline__ void xwait(unsigned int* sig, const unsigned int* cnt, unsigned int* expect_sm, unsigned int inc, ull* dbg) {
     __syncthreads();
     if (threadIdx.x == 0) {
+        // the running expectation lives in shared memory: only this thread ever needs it (six registers less in every thread)
+        const unsigned int expected = *expect_sm + inc;
+        *expect_sm = expected;
         if (sig) cnt_add(sig, 1u);
         int spins = 0;
         while ((int)(cnt_load(cnt) - expected) < 0) {
@@ -411,6 +414,7 @@ struct MegaSm {
     float red[MWARP];
     float part[8][16];
     float bestv[MWARP]; int besti[MWARP];
+    unsigned int expect[6];    // arrival-counter expectations (xwait): attn, o, act, down, arg, scores of this CTA's head
     MegaLayer layers[MEGA_MAX_LAYERS];
 };
 
@@ -1132,10 +1136,12 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
         sm.rr[tid][1] = (int)(((long long)(cta + 1) * R) / G);
     }
     // arrival counters only ever grow; what this launch waits for is relative to their value at its start
-    unsigned int exp_attn = cnt_load(P.cnt + CNT_ATTN * CNT_STRIDE), exp_o = cnt_load(P.cnt + CNT_O * CNT_STRIDE);
-    unsigned int exp_act = cnt_load(P.cnt + CNT_ACT * CNT_STRIDE), exp_down = cnt_load(P.cnt + CNT_DOWN * CNT_STRIDE);
-    unsigned int exp_arg = cnt_load(P.cnt + CNT_ARG * CNT_STRIDE);
-    unsigned int exp_sc = (cta < n_units) ? cnt_load(P.cnt + (CNT_SC0 + (cta >> 2)) * CNT_STRIDE) : 0u;
+    if (tid == 0) {
+        sm.expect[0] = cnt_load(P.cnt + CNT_ATTN * CNT_STRIDE); sm.expect[1] = cnt_load(P.cnt + CNT_O * CNT_STRIDE);
+        sm.expect[2] = cnt_load(P.cnt + CNT_ACT * CNT_STRIDE); sm.expect[3] = cnt_load(P.cnt + CNT_DOWN * CNT_STRIDE);
+        sm.expect[4] = cnt_load(P.cnt + CNT_ARG * CNT_STRIDE);
+        sm.expect[5] = (cta < n_units) ? cnt_load(P.cnt + (CNT_SC0 + (cta >> 2)) * CNT_STRIDE) : 0u;
+    }
     int pos = P.st->pos;
     const int nctx_min = P.st->nctx_min;
     const int n_rows = P.n_body + P.n_head;
@@ -1167,8 +1173,7 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
             const MegaLayer& L = sm.layers[min(s >> 2, P.n_layers - 1)];
             // ---------------- prologue: wait for the input vector and stage it as this phase's GEMV input
             if (kind == 3) {
-                exp_act += NBF;
-                xwait(nullptr, P.cnt + CNT_ACT * CNT_STRIDE, exp_act, P.dbg);
+                xwait(nullptr, P.cnt + CNT_ACT * CNT_STRIDE, &sm.expect[2], NBF, P.dbg);
                 MEGA_PROF(kind * 16 + 0);
                 mega_gather_act<AT, WT>(P, av, tag_in);
             } else {
@@ -1176,16 +1181,13 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
                 if (s > 0) {
                     const ull* src;
                     if (kind == 1) {
-                        exp_attn += n_units;
-                        xwait((cta < n_units) ? P.cnt + CNT_ATTN * CNT_STRIDE : nullptr, P.cnt + CNT_ATTN * CNT_STRIDE, exp_attn, P.dbg);
+                        xwait((cta < n_units) ? P.cnt + CNT_ATTN * CNT_STRIDE : nullptr, P.cnt + CNT_ATTN * CNT_STRIDE, &sm.expect[0], n_units, P.dbg);
                         src = P.x_attn;
                     } else if (kind == 2) {
-                        exp_o += G;
-                        xwait(P.cnt + CNT_O * CNT_STRIDE, P.cnt + CNT_O * CNT_STRIDE, exp_o, P.dbg);
+                        xwait(P.cnt + CNT_O * CNT_STRIDE, P.cnt + CNT_O * CNT_STRIDE, &sm.expect[1], G, P.dbg);
                         src = P.x_o;
                     } else {
-                        exp_down += G;
-                        xwait(P.cnt + CNT_DOWN * CNT_STRIDE, P.cnt + CNT_DOWN * CNT_STRIDE, exp_down, P.dbg);
+                        xwait(P.cnt + CNT_DOWN * CNT_STRIDE, P.cnt + CNT_DOWN * CNT_STRIDE, &sm.expect[3], G, P.dbg);
                         src = P.x_down;
                     }
                     MEGA_PROF(kind * 16 + 0);
@@ -1273,8 +1275,7 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
                     mega_attn_a<AT>(P, L, sm, ps, cta, pos, tag, tag_sc, profp, prof_i);
                     if (defer_tile && more) load_tile<WT>(nx, sm.rr[nx.kind][0], min(tile_rows<WT>(nx.nb), sm.rr[nx.kind][1] - sm.rr[nx.kind][0]), w);
                     MEGA_PROF(kind * 16 + 5);
-                    exp_sc += 4;
-                    xwait(P.cnt + (CNT_SC0 + (cta >> 2)) * CNT_STRIDE, P.cnt + (CNT_SC0 + (cta >> 2)) * CNT_STRIDE, exp_sc, P.dbg);
+                    xwait(P.cnt + (CNT_SC0 + (cta >> 2)) * CNT_STRIDE, P.cnt + (CNT_SC0 + (cta >> 2)) * CNT_STRIDE, &sm.expect[5], 4, P.dbg);
                     MEGA_PROF(kind * 16 + 6);
                     mega_attn_b<AT>(P, sm, ps, xbuf, cta, pos, n_ctx, tag_sc, tag_attn, profp, prof_i);
                     __threadfence();                               // K/V appends visible before anything later is published
@@ -1325,8 +1326,7 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
                     ll_store(P.x_arg + 2 * cta, __float_as_uint(best), tag_arg);
                     ll_store(P.x_arg + 2 * cta + 1, (uint32_t)arg, tag_arg);
                 }
-                exp_arg += G;
-                xwait(P.cnt + CNT_ARG * CNT_STRIDE, P.cnt + CNT_ARG * CNT_STRIDE, exp_arg, P.dbg);
+                xwait(P.cnt + CNT_ARG * CNT_STRIDE, P.cnt + CNT_ARG * CNT_STRIDE, &sm.expect[4], G, P.dbg);
                 if (tid < 32) {
                     float bv = -INFINITY;
                     int bi = 0x7fffffff;
