@@ -19,6 +19,9 @@
 //   * the model dimensions are compile-time constants (tinyllama.cpp:12-20); vectors of n_embd elements are
 //     held 4 elements per thread ("quad": one staged 32-bit code word per thread, 8 threads per Q8 block), so
 //     the per-op re-encodes (App. A) cost ~70 instructions per thread and the residual stream lives in registers.
+//   * the kernel is as sensitive to its own size as to the arithmetic: the layer loop executes ~100 KB of code against a 32 KB
+//     instruction cache level and sits at the 128-register limit, so profiling stamps are compiled in only for k_mega<WT, true>
+//     and anything only one thread needs lives in shared memory (profiles/r02_02_megakernel.md).
 //
 // Phases of one layer (all CTAs walk the same sequence; the tag of each exchange is the next epoch):
 //   P1   [x' = E(h + E(down)); E(rmsnorm(x'))] -> q|k|v rows                      -> x_qkv   (raw fp32)
@@ -41,7 +44,10 @@ constexpr int MWARP = MT / 32;
 constexpr int ME = 2048, MF = 5632, MKV = 256, MH = 32, MGSZ = 8;     // TinyLLamaParams, tinyllama.cpp:12-20
 constexpr int NBE = ME / 32, NBF = MF / 32;
 constexpr int PS_BYTES = 142 * 1024;       // product staging; during attention: probabilities + the unit's V slice as fp32
-constexpr int IT_Q4 = 5;                   // (row, block) items per thread per tile: MT*IT items in registers
+// (row, block) weight items per thread per tile: MT*IT items in registers.  5 covers q|k|v, o and down in one tile; gate|up runs as two.
+// Round 1 held 10 Q4 items (one gate|up tile): 25 more live registers through every phase = 384 B of spills and 840 more instructions
+// in a loop that overflows the instruction cache -- 0.968 vs 0.889 ms per token (profiles/r02_02_megakernel.md).
+constexpr int IT_Q4 = 5;
 constexpr int IT_Q8 = 5;
 constexpr int MEGA_MAX_LAYERS = 32;        // the layer table is copied into shared memory (a phase descriptor is then 30 cycles away, not an L2 round trip)
 constexpr int SPIN_LIMIT = 1 << 24;        // ~ seconds; a stuck exchange traps instead of hanging the GPU
