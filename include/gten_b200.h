@@ -153,7 +153,11 @@ int gtb_engine_acv(gtb_engine_t e, int layer, int acv_id, float* h_out, int* wid
  * read per pass; 0: every row through the persistent kernel), "batch_exact" (see gtb_engine_batch_*),
  * "xr_tensor" (process-wide experiment, default 0: the multi-row Linears of Q4 / Q8 models on the tensor cores -- kind::f16 tcgen05 MMAs
  * return the integer lane sums exactly, epilogue warps run the ordered fp32 chains out of TMEM; same bits, measured slower end to end),
- * "prof_cta" (which CTA of the persistent kernel writes the "prof" stamps) */
+ * "prof_cta" (which CTA of the persistent kernel writes the "prof" stamps; "prof" itself selects the stamped build of the kernel),
+ * "batch_eos" (see gtb_engine_batch_*).  Tuning / debugging switches, not part of the contract: "fd_chunk" (positions per attention chunk of the
+ * order-free path), "fd_trace" and "xr_trace" (cycle counters of the order-free chain / of the tensor-core experiment into the "prof"
+ * buffer), "xr_pdl" (programmatic dependent launch inside multi-row passes of <= 16 rows, default 1), "xr_variant" (tile-shape experiments
+ * of the multi-row GEMMs, default 0) */
 int gtb_engine_set_option(gtb_engine_t e, const char* name, int value);
 
 /* Batched decode (BASELINE.json configs[4]; the reference decodes one sequence, tinyllama.cpp:395-440): up to 64

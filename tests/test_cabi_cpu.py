@@ -49,3 +49,15 @@ def test_product_does_not_import_oracle():
     for f in (ROOT / "include").rglob("*"):
         if f.is_file():
             assert "oracle" not in f.read_text(), f
+
+
+def test_every_engine_option_is_documented_in_the_header():
+    """gtb_engine_set_option names handled in gtb_engine.cu all appear in include/gten_b200.h (the C-ABI's documentation)."""
+    import re
+    root = Path(__file__).resolve().parent.parent
+    src = (root / "tinyllama.cpp_b200" / "csrc" / "gtb_engine.cu").read_text()
+    hdr = (root / "include" / "gten_b200.h").read_text()
+    names = sorted(set(re.findall(r'!strcmp\(name, "([a-z_0-9]+)"\)', src)))
+    assert len(names) > 20
+    missing = [n for n in names if f'"{n}"' not in hdr]
+    assert not missing, f"options without documentation in gten_b200.h: {missing}"
