@@ -1154,8 +1154,10 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
     int n_gen = 0, stop = P.st->stop, next_tok = -1;      // an EOS sampled by the multi-row prefill's last row stops this launch too
     __syncthreads();
     WRegs<WT> w;
-    PhaseDesc pd = phase_desc(P, sm.layers, 0);
-    if (WT != DT_F16) load_tile<WT>(pd, sm.rr[0][0], min(tile_rows<WT>(pd.nb), sm.rr[0][1] - sm.rr[0][0]), w);
+    {
+        const PhaseDesc pd0 = phase_desc(P, sm.layers, 0);
+        if (WT != DT_F16) load_tile<WT>(pd0, sm.rr[0][0], min(tile_rows<WT>(pd0.nb), sm.rr[0][1] - sm.rr[0][0]), w);
+    }
     if (tid == 0) {
         for (int a = 1; a < P.pf_ahead && a < nL4; a++) prefetch_rows<WT>(phase_desc(P, sm.layers, a), sm.rr[a & 3][0], sm.rr[a & 3][1]);
     }
@@ -1175,7 +1177,7 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
         mega_embed<WT>(P, tok, res);
         uint32_t tag_in = 0;                        // tag of the exchange the next prologue consumes
         for (int s = 0; s < nphase; s++) {
-            const int kind = pd.kind;
+            const int kind = (s < nL4) ? (s & 3) : 4;              // the phase descriptor (two pointers) is read from shared memory where it is used
             const MegaLayer& L = sm.layers[min(s >> 2, P.n_layers - 1)];
             // ---------------- prologue: wait for the input vector and stage it as this phase's GEMV input
             if (kind == 3) {
@@ -1261,6 +1263,7 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
             // q|k|v phase of a CTA with an attention unit: the next phase's weight tile (needed only at P3) is loaded AFTER the unit's
             // K/V loads have been issued -- the L1 load queue is in order, and the attention loads are the ones on the critical path
             const bool defer_tile = (WT != DT_F16) && kind == 0 && cta < n_units;
+            const PhaseDesc pd = phase_desc(P, sm.layers, s);
             gemv_phase<WT>(pd, r0, r1, av, ps, w, nx, sm.rr[nx.kind][0], sm.rr[nx.kind][1], more && !defer_tile, [&](int row, float v) {
                 if (kind == 4) {
                     P.logits[row] = v;
@@ -1269,7 +1272,6 @@ __global__ void __launch_bounds__(MT, 1) k_mega(const MegaParams P) {
                     ll_store(outp + row, __float_as_uint(v), tag);
                 }
             }, background, profp, &prof_i, 128 + kind * 8);
-            pd = nx;
             tag_in = tag;
             MEGA_PROF(kind * 16 + 4);
             // ---------------- what follows the GEMV
