@@ -41,7 +41,7 @@ public:
     // (DESIGN.md 4.4); later calls (start_pos > 0) always take the order-exact path.  Prompts of >= 2 tokens.
     void set_batched_prefill(bool on) { batched_prefill_ = on; }
     // Opt in to the order-free decode kernels (gtb_fastdec.cuh) for every row: same operations and re-encode points as
-    // ops.h, free summation order -- 1.56x the token rate of the bit-exact path (0.56 vs 0.87 ms per token), results within the same tolerance as the
+    // ops.h, free summation order -- 1.5x the token rate of the bit-exact path (0.56 vs 0.85 ms per token), results within the same tolerance as the
     // batched prefill, greedy tokens no longer guaranteed identical.  Q8 / Q4 models.
     void set_fast_decode(bool on) { GTEN_CUDA_OK(gtb_engine_set_option(eng_, "fast_decode", on ? 1 : 0)); }
     Tensor logits(const Tensor& tokens, const int start_pos = 0) {
